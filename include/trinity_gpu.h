@@ -1,0 +1,138 @@
+/* trinity_gpu.h -- C ABI of libtrinity_gpu: the B200 (sm_100a) implementation of Trinity's k-mer hot path.
+ *
+ * The reference (trinityrnaseq v2.15.2) has NO in-process API for this path: its boundary is three
+ * executables driven by shell strings (PerlLib/Pipeliner.pm:176, util/insilico_read_normalization.pl:803).
+ * Each entry point below therefore names the reference *function* whose work it replaces; the three
+ * drop-in executables (`jellyfish`, `fastaToKmerCoverageStats`, `ReadsToTranscripts`, built from
+ * trinityrnaseq_b200/host/) are thin argv/file-format shells over these calls.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every function returns TG_OK (0) or a negative TG_ERR_* code and leaves a
+ *     message for tg_last_error() (thread-local).  There is no CPU fallback: without a usable CUDA device
+ *     tg_init fails with TG_ERR_NOGPU.
+ *   - "record buffer": sequences stored back to back, each followed by ONE terminator byte '\n'
+ *     (exactly what a single-line FASTA sequence line looks like).  offs[i] is the byte offset of record i,
+ *     offs[n] the end of the last terminator; record i has offs[i+1]-offs[i]-1 bases.  Bases are
+ *     case-insensitive; any byte other than ACGTacgt is "not a base" and breaks every k-mer window over it.
+ *   - "packed k-mer": 2 bits per base, A=0 C=1 G=2 T=3, first base most significant, in the low 2k bits of
+ *     a uint64_t (so integer order == lexicographic order).  1 <= k <= 31.
+ *   - host buffers may be pageable; buffers from tg_host_alloc (pinned) are copied at full PCIe speed.
+ *   - a tg_ctx owns one device and its streams; calls on one ctx must not overlap in time.
+ */
+#ifndef TRINITY_GPU_H
+#define TRINITY_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tg_ctx tg_ctx;
+typedef struct tg_table tg_table;
+
+enum { TG_OK = 0, TG_ERR_CUDA = -1, TG_ERR_ARG = -2, TG_ERR_NOMEM = -3, TG_ERR_TABLE = -4, TG_ERR_NOGPU = -5 };
+enum { TG_TABLE_COUNT = 0, TG_TABLE_LABEL = 1 };
+#define TG_HISTO_BINS 10002 /* bins[c] for c = 0..10000, bins[10001] = all larger counts */
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+int tg_version(void);
+const char* tg_last_error(void);
+int tg_device_count(void);
+int tg_init(int device, tg_ctx** ctx);
+void tg_destroy(tg_ctx* ctx);
+int tg_device_info(tg_ctx* ctx, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes);
+int tg_sync(tg_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
+uint64_t tg_launch_count(tg_ctx* ctx);
+
+void* tg_host_alloc(uint64_t bytes); /* pinned host memory */
+void tg_host_free(void* p);
+void tg_free(void* p); /* releases arrays returned by tg_table_export */
+
+/* ---- k-mer tables ------------------------------------------------------------------------------------
+ * TG_TABLE_COUNT replaces Inchworm's KmerCounter (hash_map<u64,u32>, Inchworm/src/KmerCounter.hpp:55) and
+ * jellyfish's .jf hash; TG_TABLE_LABEL replaces Chrysalis' NonRedKmerTable (sorted vector<string> +
+ * vector<int>, Chrysalis/analysis/NonRedKmerTable.h:84-86).  Tables grow on demand. */
+int tg_table_create(tg_ctx* ctx, int kind, int k, uint64_t expected_keys, tg_table** out);
+void tg_table_destroy(tg_table* t);
+int tg_table_reserve(tg_table* t, uint64_t additional_keys);
+int tg_table_info(tg_table* t, uint64_t* capacity_slots, uint64_t* distinct_keys);
+int tg_table_clear(tg_table* t);
+
+/* ---- stage J: jellyfish count / dump / histo ----------------------------------------------------------
+ * tg_count_reads: `jellyfish count -m k [--canonical]` (Trinity:2612-2619) and
+ *   KmerCounter::add_sequence (Inchworm/src/KmerCounter.cpp:34-44): table[key(w)] += 1 for every window w of
+ *   k bases in every record; canonical != 0 folds a k-mer and its reverse complement onto one key. */
+int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical);
+/* tg_table_load_pairs: populate_kmer_counter_from_kmers / KmerCounter::add_kmer(kmer,count)
+ *   (Inchworm/src/fastaToKmerCoverageStats.cpp:181-228, KmerCounter.cpp:476-489): table[canon(key)] += val
+ *   (u32 wrap-around like the reference's unsigned int). */
+int tg_table_load_pairs(tg_table* t, const uint64_t* packed_keys, const uint32_t* vals, uint64_t n, int canonical);
+/* tg_table_export: `jellyfish dump -L min -U max` (Trinity:2625).  Returns malloc'ed arrays (tg_free) of
+ *   packed k-mers and counts with min <= count <= max; sorted != 0 orders them by k-mer;
+ *   canonical_repr != 0 reports the lexicographically smaller of k-mer / reverse complement (what jellyfish
+ *   prints for a --canonical table). */
+int tg_table_export(tg_table* t, uint32_t min_count, uint32_t max_count, int sorted, int canonical_repr,
+                    uint64_t** packed_keys, uint32_t** counts, uint64_t* n);
+/* tg_histo: `jellyfish histo` (Trinity:2630): bins[c] = number of distinct k-mers with count c. */
+int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]);
+
+/* ---- stage S: fastaToKmerCoverageStats ------------------------------------------------------------------
+ * compute_kmer_coverage + median_coverage + mean + stDev (Inchworm/src/fastaToKmerCoverageStats.cpp:300-402)
+ * for every record: per window c = max(1, table[canon(w)]) (0 -> 1 also for windows with a non-base);
+ * median as u32 (even n: wrapping u32 mean of the two middles), mean = (float)sum/n, stdev = sequential fp32
+ * sqrtf(sum((c-mean)^2)/(n-1)) without FMA, bit-identical to the x86-64 reference (n==1 -> -nan, n==0 -> -0).
+ * per_kmer (optional, may be NULL): per_kmer[offs[i]+j] = coverage of window j of record i
+ * (--capture_coverage_info); it must have offs[nreads] entries. */
+int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nreads, int canonical,
+                 uint32_t* median, float* mean, float* stdev, uint32_t* per_kmer);
+
+/* ---- stage R: ReadsToTranscripts ------------------------------------------------------------------------
+ * tg_label_bundles: NonRedKmerTable::SetUp(dna,true) + the SetCount loop
+ *   (Chrysalis/analysis/ReadsToTranscripts.cc:144-169): every all-ACGT forward k-mer of bundle i gets label
+ *   first_index + i; a k-mer present in several bundles keeps the HIGHEST index (the reference's
+ *   single-thread last-writer-wins order). */
+int tg_label_bundles(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nbundles, uint32_t first_index);
+/* tg_assign_reads: the per-read loop of ReadsToTranscripts.cc:216-274.  entropy_ok is a 26*26*26 byte table
+ *   indexed [nG][nA][nT] (tg_entropy_table builds it with the reference's expression); strand != 0 skips the
+ *   reverse-complement pass.  Outputs per read: best = bundle index or -1, pct = pct_read_mapped,
+ *   score (optional, may be NULL) = the winning run length `max`. */
+int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nreads, int strand,
+                    const uint8_t* entropy_ok, int32_t* best, int32_t* pct, int32_t* score);
+/* compute_entropy(string&) >= min_entropy for every (nG,nA,nT,nC) with sum k
+ * (Chrysalis/analysis/sequenceUtil.cc:326-355); host-side, evaluated with the reference's fp32 expression. */
+void tg_entropy_table(int k, float min_entropy, uint8_t* entropy_ok /* 26*26*26 */);
+
+/* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ---------------------- */
+int tg_dev_alloc(tg_ctx* ctx, uint64_t bytes, void** dptr);
+int tg_dev_records_alloc(tg_ctx* ctx, uint64_t nbytes, void** dptr); /* padded + '\n'-filled for the tile kernels */
+int tg_dev_free(tg_ctx* ctx, void* dptr);
+int tg_memcpy_h2d(tg_ctx* ctx, void* dptr, const void* host, uint64_t bytes);
+int tg_memcpy_d2h(tg_ctx* ctx, void* host, const void* dptr, uint64_t bytes);
+int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int canonical);
+int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
+                     void* d_median, void* d_mean, void* d_stdev);
+int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,
+                         uint32_t first_index);
+int tg_assign_reads_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int strand,
+                        const void* d_entropy_ok, void* d_best, void* d_pct);
+/* CUDA-event timer on the ctx's primary stream (the stream every *_dev call launches on) */
+int tg_timer_start(tg_ctx* ctx);
+int tg_timer_stop(tg_ctx* ctx, float* ms);
+
+/* ---- measurement utilities ------------------------------------------------------------------------------ */
+/* random-access roofline probe on a table of `slots` 16-B slots: mode 0 = random 16-B loads, 1 = 8-B load +
+ * red.add on the same slot (steady-state count), 2 = CAS + red.add.  Returns the best of `reps` timings. */
+int tg_gups(tg_ctx* ctx, uint64_t slots, uint64_t nops, int mode, int reps, float* best_ms);
+/* synthetic paired reads generated on the device into a record buffer of 2*npairs*(read_len+1) bytes
+ * (allocate it with tg_dev_records_alloc).  tx/tx_offs/tx_cum are HOST arrays: transcript bases, offsets
+ * (ntx+1) and cumulative expression thresholds scaled to 2^64 (ntx). */
+int tg_synth_reads_dev(tg_ctx* ctx, const char* tx, const uint64_t* tx_offs, const uint64_t* tx_cum, uint32_t ntx,
+                       uint64_t npairs, int read_len, int frag_mean, int frag_sd, uint32_t err_per_million,
+                       uint32_t n_per_million, uint64_t seed, int stranded, void* d_recs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRINITY_GPU_H */

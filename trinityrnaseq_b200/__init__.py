@@ -1,0 +1,8 @@
+"""trinityrnaseq_b200 -- B200-native k-mer hot path of Trinity (count -> coverage stats -> read assignment).
+
+Python here is only the host-side mirror of the reference's interfaces for tests and bench; the product is
+libtrinity_gpu.so (CUDA, sm_100a) plus the drop-in executables in trinityrnaseq_b200/bin/.
+"""
+from .api import (Context, KmerCounter, BundleKmerTable, records_from_sequences, format_stats_line,  # noqa: F401
+                  packed_to_kmer, kmer_to_packed)
+from ._lib import TrinityGpuError  # noqa: F401

@@ -1,0 +1,832 @@
+// C-ABI host layer of libtrinity_gpu (declared in include/trinity_gpu.h).
+// Owns device memory, streams and batching; all arithmetic happens in the kernels of tg_kernels.cu.
+// There is deliberately no CPU path here: if CUDA is unusable every call fails with an error code.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/trinity_gpu.h"
+#include "tg_internal.h"
+
+using namespace tg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? TG_ERR_NOMEM : TG_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e__), __FILE__, __LINE__);                             \
+    } while (0)
+
+constexpr double MAX_LOAD = 0.70;      // grow before a batch could push occupancy past this
+constexpr double TARGET_LOAD = 0.45;   // occupancy right after a growth
+constexpr uint64_t MIN_SLOTS = 1u << 12;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct tg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    uint64_t launches = 0;
+    size_t batch_bytes = 64ull << 20;
+    // per-stream staging for the host-buffer entry points
+    DevBuf recs[2], offs[2], out_a[2], out_b[2], out_c[2], per_kmer[2], long_idx[2], scratch;
+    DevBuf lut;
+    unsigned int* d_long_hdr[2] = {nullptr, nullptr};   // {count, max_win}
+    unsigned int* h_long_hdr = nullptr;                 // pinned, 2 x 2
+};
+
+struct tg_table {
+    tg_ctx* ctx = nullptr;
+    int kind = TG_TABLE_COUNT;
+    int k = 25;
+    Slot* slots = nullptr;
+    uint64_t cap = 0;
+    unsigned long long* d_claimed = nullptr;   // [0] = distinct keys
+    int* d_error = nullptr;
+    uint64_t distinct_ub = 0;   // host-side upper bound on distinct keys (refreshed from the device at syncs)
+    TableView view() const { return TableView{slots, cap, d_claimed, d_error}; }
+};
+
+static int bind(tg_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return TG_OK;
+}
+
+static int sync_all(tg_ctx* c) {
+    CU(cudaStreamSynchronize(c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[1]));
+    return TG_OK;
+}
+
+static int table_refresh(tg_table* t) {   // after a sync: read back distinct count and the error flag
+    unsigned long long n = 0;
+    int err = 0;
+    CU(cudaMemcpy(&n, t->d_claimed, sizeof n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&err, t->d_error, sizeof err, cudaMemcpyDeviceToHost));
+    t->distinct_ub = n;
+    if (err) return fail(TG_ERR_TABLE, "k-mer table overflow (capacity %llu slots)", (unsigned long long)t->cap);
+    return TG_OK;
+}
+
+static int table_alloc(tg_ctx* c, uint64_t slots, Slot** out) {
+    if (slots < MIN_SLOTS) slots = MIN_SLOTS;
+    Slot* p = nullptr;
+    CU(cudaMalloc(&p, slots * sizeof(Slot)));
+    cudaError_t e = cudaMemsetAsync(p, 0, slots * sizeof(Slot), c->stream[0]);
+    if (e != cudaSuccess) { cudaFree(p); CU(e); }
+    *out = p;
+    return TG_OK;
+}
+
+extern "C" {
+
+int tg_version(void) { return 100; }
+const char* tg_last_error(void) { return g_err.c_str(); }
+
+int tg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tg_init(int device, tg_ctx** out) {
+    if (!out) return fail(TG_ERR_ARG, "tg_init: null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TG_ERR_NOGPU, "no CUDA device available (%s); libtrinity_gpu has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(TG_ERR_ARG, "tg_init: device %d out of range (0..%d)", device, n - 1);
+    tg_ctx* c = new tg_ctx();
+    c->device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete c;
+        return fail(TG_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 2; i++) {
+        CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+        CU(cudaMalloc(&c->d_long_hdr[i], 2 * sizeof(unsigned int)));
+    }
+    CU(cudaEventCreate(&c->t0));
+    CU(cudaEventCreate(&c->t1));
+    CU(cudaMallocHost(&c->h_long_hdr, 4 * sizeof(unsigned int)));
+    if (const char* mb = getenv("TG_BATCH_MB")) {
+        long v = atol(mb);
+        if (v >= 1 && v <= 4096) c->batch_bytes = (size_t)v << 20;
+    }
+    *out = c;
+    return TG_OK;
+}
+
+void tg_destroy(tg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        c->recs[i].release(); c->offs[i].release(); c->out_a[i].release(); c->out_b[i].release();
+        c->out_c[i].release(); c->per_kmer[i].release(); c->long_idx[i].release();
+        if (c->d_long_hdr[i]) cudaFree(c->d_long_hdr[i]);
+        if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+    }
+    c->scratch.release(); c->lut.release();
+    if (c->h_long_hdr) cudaFreeHost(c->h_long_hdr);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    delete c;
+}
+
+int tg_device_info(tg_ctx* c, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = c->sm_count;
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return TG_OK;
+}
+
+int tg_sync(tg_ctx* c) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    return sync_all(c);
+}
+
+uint64_t tg_launch_count(tg_ctx* c) { return c ? c->launches : 0; }
+
+void* tg_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        fail(TG_ERR_NOMEM, "cudaMallocHost(%llu) failed", (unsigned long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+void tg_host_free(void* p) { if (p) cudaFreeHost(p); }
+void tg_free(void* p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------------------
+int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table** out) {
+    if (!c || !out) return fail(TG_ERR_ARG, "tg_table_create: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (kind != TG_TABLE_COUNT && kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "unknown table kind %d", kind);
+    if (bind(c)) return TG_ERR_CUDA;
+    tg_table* t = new tg_table();
+    t->ctx = c; t->kind = kind; t->k = k;
+    uint64_t slots = (uint64_t)((double)expected_keys / TARGET_LOAD) + 1;
+    if (slots < MIN_SLOTS) slots = MIN_SLOTS;
+    int rc = table_alloc(c, slots, &t->slots);
+    if (rc) { delete t; return rc; }
+    t->cap = slots;
+    CU(cudaMalloc(&t->d_claimed, sizeof(unsigned long long)));
+    CU(cudaMalloc(&t->d_error, sizeof(int)));
+    CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
+    CU(cudaMemsetAsync(t->d_error, 0, sizeof(int), c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    *out = t;
+    return TG_OK;
+}
+
+void tg_table_destroy(tg_table* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaDeviceSynchronize();
+    if (t->slots) cudaFree(t->slots);
+    if (t->d_claimed) cudaFree(t->d_claimed);
+    if (t->d_error) cudaFree(t->d_error);
+    delete t;
+}
+
+int tg_table_clear(tg_table* t) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(t->slots, 0, t->cap * sizeof(Slot), c->stream[0]));
+    CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
+    CU(cudaMemsetAsync(t->d_error, 0, sizeof(int), c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    t->distinct_ub = 0;
+    return TG_OK;
+}
+
+// Make room for `additional` more distinct keys.  distinct_ub is an upper bound; it is tightened from the
+// device counter (one sync) only when the bound alone would force a growth.
+int tg_table_reserve(tg_table* t, uint64_t additional) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if ((double)(t->distinct_ub + additional) <= MAX_LOAD * (double)t->cap) {
+        t->distinct_ub += additional;
+        return TG_OK;
+    }
+    int rc = sync_all(c);
+    if (rc) return rc;
+    if ((rc = table_refresh(t))) return rc;
+    if ((double)(t->distinct_ub + additional) <= MAX_LOAD * (double)t->cap) {
+        t->distinct_ub += additional;
+        return TG_OK;
+    }
+    uint64_t want = (uint64_t)((double)(t->distinct_ub + additional) / TARGET_LOAD) + 1;
+    if (want < t->cap + t->cap / 2) want = t->cap + t->cap / 2;
+    // never ask for more than the device can hold next to the old table
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    const uint64_t fit = (uint64_t)((double)fr * 0.92) / sizeof(Slot);
+    if (want > fit) want = fit;
+    if ((double)(t->distinct_ub + additional) > 0.92 * (double)want)
+        return fail(TG_ERR_NOMEM, "k-mer table cannot grow: need room for %llu keys, device has room for %llu slots",
+                    (unsigned long long)(t->distinct_ub + additional), (unsigned long long)fit);
+    Slot* fresh = nullptr;
+    if ((rc = table_alloc(c, want, &fresh))) return rc;
+    CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
+    TableView nv{fresh, want, t->d_claimed, t->d_error};
+    CU(launch_rehash(t->slots, t->cap, nv, t->kind == TG_TABLE_LABEL, c->stream[0]));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream[0]));
+    CU(cudaFree(t->slots));
+    t->slots = fresh;
+    t->cap = want;
+    if ((rc = table_refresh(t))) return rc;
+    t->distinct_ub += additional;
+    return TG_OK;
+}
+
+int tg_table_info(tg_table* t, uint64_t* capacity, uint64_t* distinct) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    if (bind(t->ctx)) return TG_ERR_CUDA;
+    int rc = sync_all(t->ctx);
+    if (rc) return rc;
+    if ((rc = table_refresh(t))) return rc;
+    if (capacity) *capacity = t->cap;
+    if (distinct) *distinct = t->distinct_ub;
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers for the host-buffer entry points
+// ---------------------------------------------------------------------------------------------------------
+// end (exclusive) of the batch starting at pos: at most batch_bytes, cut after a record terminator
+static uint64_t batch_end(const char* recs, uint64_t pos, uint64_t nbytes, size_t batch_bytes) {
+    uint64_t end = pos + batch_bytes;
+    if (end >= nbytes) return nbytes;
+    const void* nl = memrchr(recs + pos, '\n', end - pos);
+    if (nl) return (const char*)nl - recs + 1;
+    nl = memchr(recs + end, '\n', nbytes - end);   // one record longer than a batch: take all of it
+    return nl ? (uint64_t)((const char*)nl - recs + 1) : nbytes;
+}
+
+static int upload_records(tg_ctx* c, int b, const char* src, uint64_t n) {
+    const uint64_t padded = padded_record_bytes(n);
+    CU(c->recs[b].ensure(padded));
+    CU(cudaMemcpyAsync(c->recs[b].p, src, n, cudaMemcpyHostToDevice, c->stream[b]));
+    CU(cudaMemsetAsync((char*)c->recs[b].p + n, '\n', padded - n, c->stream[b]));
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage J
+// ---------------------------------------------------------------------------------------------------------
+int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical) {
+    if (!t || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_count_reads: null argument");
+    if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads needs a TG_TABLE_COUNT table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    uint64_t pos = 0;
+    for (int it = 0; pos < nbytes; it++) {
+        const int b = it & 1;
+        const uint64_t end = batch_end(recs, pos, nbytes, c->batch_bytes);
+        const uint64_t n = end - pos;
+        if ((rc = tg_table_reserve(t, n))) return rc;     // may rehash: syncs both streams itself
+        CU(cudaStreamSynchronize(c->stream[b]));          // staging buffer b is free again
+        if ((rc = upload_records(c, b, recs + pos, n))) return rc;
+        CU(launch_count_tiles((const uint8_t*)c->recs[b].p, n, t->k, canonical, t->view(), c->sm_count, c->stream[b]));
+        c->launches++;
+        pos = end;
+    }
+    if ((rc = sync_all(c))) return rc;
+    return table_refresh(t);
+}
+
+int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int canonical) {
+    if (!t || !d_recs) return fail(TG_ERR_ARG, "tg_count_reads_dev: null argument");
+    if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads_dev needs a TG_TABLE_COUNT table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    if ((rc = tg_table_reserve(t, nbytes))) return rc;
+    CU(launch_count_tiles((const uint8_t*)d_recs, nbytes, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+
+int tg_table_load_pairs(tg_table* t, const uint64_t* keys, const uint32_t* vals, uint64_t n, int canonical) {
+    if (!t || ((!keys || !vals) && n)) return fail(TG_ERR_ARG, "tg_table_load_pairs: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    const uint64_t chunk = std::max<uint64_t>(1, c->batch_bytes / 12);
+    for (uint64_t pos = 0, it = 0; pos < n; pos += chunk, it++) {
+        const int b = (int)(it & 1);
+        const uint64_t m = std::min(chunk, n - pos);
+        if ((rc = tg_table_reserve(t, m))) return rc;
+        CU(cudaStreamSynchronize(c->stream[b]));
+        CU(c->out_a[b].ensure(m * 8));
+        CU(c->out_b[b].ensure(m * 4));
+        CU(cudaMemcpyAsync(c->out_a[b].p, keys + pos, m * 8, cudaMemcpyHostToDevice, c->stream[b]));
+        CU(cudaMemcpyAsync(c->out_b[b].p, vals + pos, m * 4, cudaMemcpyHostToDevice, c->stream[b]));
+        CU(launch_load_pairs((const uint64_t*)c->out_a[b].p, (const uint32_t*)c->out_b[b].p, m, t->k, canonical,
+                             t->view(), c->stream[b]));
+        c->launches++;
+    }
+    if ((rc = sync_all(c))) return rc;
+    return table_refresh(t);
+}
+
+int tg_table_export(tg_table* t, uint32_t min_count, uint32_t max_count, int sorted, int canonical_repr,
+                    uint64_t** keys, uint32_t** counts, uint64_t* n_out) {
+    if (!t || !keys || !counts || !n_out) return fail(TG_ERR_ARG, "tg_table_export: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    *keys = nullptr; *counts = nullptr; *n_out = 0;
+    int rc;
+    if ((rc = sync_all(c))) return rc;
+    if ((rc = table_refresh(t))) return rc;
+    cudaStream_t s = c->stream[0];
+    unsigned long long* d_n = nullptr;
+    CU(cudaMalloc(&d_n, sizeof *d_n));
+    CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, s));
+    CU(launch_export(t->slots, t->cap, min_count, max_count, t->k, canonical_repr, nullptr, nullptr, d_n, s));
+    c->launches++;
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (n == 0) { cudaFree(d_n); *keys = (uint64_t*)malloc(8); *counts = (uint32_t*)malloc(4); return TG_OK; }
+    uint64_t* d_keys = nullptr; uint32_t* d_vals = nullptr;
+    CU(cudaMalloc(&d_keys, n * 8));
+    CU(cudaMalloc(&d_vals, n * 4));
+    CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, s));
+    CU(launch_export(t->slots, t->cap, min_count, max_count, t->k, canonical_repr, d_keys, d_vals, d_n, s));
+    c->launches++;
+    if (sorted) { CU(sort_pairs(d_keys, d_vals, n, t->k, s)); c->launches += 8; }
+    uint64_t* hk = (uint64_t*)malloc(n * 8);
+    uint32_t* hv = (uint32_t*)malloc(n * 4);
+    if (!hk || !hv) { free(hk); free(hv); cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_n);
+                      return fail(TG_ERR_NOMEM, "tg_table_export: host allocation of %llu pairs failed", n); }
+    CU(cudaMemcpyAsync(hk, d_keys, n * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hv, d_vals, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_n);
+    *keys = hk; *counts = hv; *n_out = n;
+    return TG_OK;
+}
+
+int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]) {
+    if (!t || !bins) return fail(TG_ERR_ARG, "tg_histo: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    if ((rc = sync_all(c))) return rc;
+    unsigned long long* d_bins = nullptr;
+    CU(cudaMalloc(&d_bins, TG_HISTO_BINS * sizeof *d_bins));
+    CU(cudaMemsetAsync(d_bins, 0, TG_HISTO_BINS * sizeof *d_bins, c->stream[0]));
+    CU(launch_histo(t->slots, t->cap, d_bins, c->stream[0]));
+    c->launches++;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+    CU(cudaMemcpyAsync(bins, d_bins, TG_HISTO_BINS * sizeof *d_bins, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(d_bins);
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage S / stage R: batches of whole records, double buffered over the two streams
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct ReadBatch { uint64_t r0, r1; };
+
+static std::vector<ReadBatch> split_reads(const uint64_t* offs, uint64_t nreads, size_t batch_bytes) {
+    std::vector<ReadBatch> v;
+    uint64_t r0 = 0;
+    while (r0 < nreads) {
+        // largest r1 with offs[r1] - offs[r0] <= batch_bytes (at least one read)
+        const uint64_t* e = std::upper_bound(offs + r0 + 1, offs + nreads + 1, offs[r0] + batch_bytes);
+        uint64_t r1 = (uint64_t)(e - offs) - 1;
+        if (r1 <= r0) r1 = r0 + 1;
+        if (r1 - r0 > 0x7FFFFFF0ull) r1 = r0 + 0x7FFFFFF0ull;
+        v.push_back({r0, r1});
+        r0 = r1;
+    }
+    return v;
+}
+
+// after the warp-path kernel of batch b: run the CTA-per-read kernel if any read was too long for it
+template <typename LaunchLong, typename ScratchBytes>
+static int finish_long(tg_ctx* c, int b, int k, ScratchBytes scratch_bytes, LaunchLong launch_long) {
+    unsigned int* h = c->h_long_hdr + 2 * b;
+    CU(cudaMemcpyAsync(h, c->d_long_hdr[b], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream[b]));
+    CU(cudaStreamSynchronize(c->stream[b]));
+    if (h[0] == 0) return TG_OK;
+    int nctas = (int)std::min<unsigned>(h[0], (unsigned)c->sm_count * 2);
+    size_t need = scratch_bytes(h[1], k, nctas);
+    while (nctas > 1 && need > (1ull << 30)) { nctas = (nctas + 1) / 2; need = scratch_bytes(h[1], k, nctas); }
+    // the scratch buffer is shared by both streams: make sure the other stream's long kernel is done
+    CU(cudaStreamSynchronize(c->stream[b ^ 1]));
+    CU(c->scratch.ensure(need));
+    CU(launch_long(h[0], h[1], c->scratch.p, nctas));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream[b]));
+    return TG_OK;
+}
+
+extern "C" {
+
+int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nreads, int canonical,
+                 uint32_t* median, float* mean, float* stdev, uint32_t* per_kmer) {
+    if (!t || ((!recs || !offs || !median || !mean || !stdev) && nreads))
+        return fail(TG_ERR_ARG, "tg_cov_stats: null argument");
+    if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_cov_stats needs a TG_TABLE_COUNT table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (nreads == 0) return TG_OK;
+    int rc;
+    if ((rc = sync_all(c))) return rc;
+    const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
+    struct Pending { bool live = false; ReadBatch rb; } pend[2];
+    auto drain = [&](int b) -> int {   // long-read pass + results back to the caller for the batch in flight on b
+        if (!pend[b].live) return TG_OK;
+        const ReadBatch rb = pend[b].rb;
+        const uint64_t m = rb.r1 - rb.r0, base = offs[rb.r0];
+        int r2 = finish_long(c, b, t->k, cov_stats_long_scratch_bytes,
+            [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
+                return launch_cov_stats_long((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, t->k,
+                                             canonical, t->slots, t->cap, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p,
+                                             (float*)c->out_c[b].p, per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr,
+                                             (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
+                                             c->stream[b]);
+            });
+        if (r2) return r2;
+        CU(cudaMemcpyAsync(median + rb.r0, c->out_a[b].p, m * 4, cudaMemcpyDeviceToHost, c->stream[b]));
+        CU(cudaMemcpyAsync(mean + rb.r0, c->out_b[b].p, m * 4, cudaMemcpyDeviceToHost, c->stream[b]));
+        CU(cudaMemcpyAsync(stdev + rb.r0, c->out_c[b].p, m * 4, cudaMemcpyDeviceToHost, c->stream[b]));
+        if (per_kmer)
+            CU(cudaMemcpyAsync(per_kmer + base, c->per_kmer[b].p, (offs[rb.r1] - base) * 4, cudaMemcpyDeviceToHost,
+                               c->stream[b]));
+        CU(cudaStreamSynchronize(c->stream[b]));
+        pend[b].live = false;
+        return TG_OK;
+    };
+    for (size_t i = 0; i < batches.size(); i++) {
+        const int b = (int)(i & 1);
+        if ((rc = drain(b))) return rc;
+        const ReadBatch rb = batches[i];
+        const uint64_t m = rb.r1 - rb.r0, base = offs[rb.r0], nb = offs[rb.r1] - base;
+        if ((rc = upload_records(c, b, recs + base, nb))) return rc;
+        CU(c->offs[b].ensure((m + 1) * 8));
+        CU(c->out_a[b].ensure(m * 4)); CU(c->out_b[b].ensure(m * 4)); CU(c->out_c[b].ensure(m * 4));
+        CU(c->long_idx[b].ensure(m * 4));
+        if (per_kmer) { CU(c->per_kmer[b].ensure(nb * 4)); CU(cudaMemsetAsync(c->per_kmer[b].p, 0, nb * 4, c->stream[b])); }
+        CU(cudaMemcpyAsync(c->offs[b].p, offs + rb.r0, (m + 1) * 8, cudaMemcpyHostToDevice, c->stream[b]));
+        CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
+        LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+        CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
+                            t->slots, t->cap, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
+                            per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, c->stream[b]));
+        c->launches++;
+        pend[b].live = true; pend[b].rb = rb;
+    }
+    if ((rc = drain(0))) return rc;
+    if ((rc = drain(1))) return rc;
+    return TG_OK;
+}
+
+int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
+                     void* d_median, void* d_mean, void* d_stdev) {
+    if (!t || !d_recs || !d_offs || !d_median || !d_mean || !d_stdev)
+        return fail(TG_ERR_ARG, "tg_cov_stats_dev: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_cov_stats_dev: at most 2^31 reads per call");
+    const int b = 0;
+    CU(c->long_idx[b].ensure(nreads * 4));
+    CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
+    LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+    CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->cap,
+                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->stream[b]));
+    c->launches++;
+    return finish_long(c, b, t->k, cov_stats_long_scratch_bytes,
+        [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
+            return launch_cov_stats_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots,
+                                         t->cap, (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr,
+                                         (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
+                                         c->stream[b]);
+        });
+}
+
+int tg_label_bundles(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nbundles, uint32_t first_index) {
+    if (!t || ((!recs || !offs) && nbundles)) return fail(TG_ERR_ARG, "tg_label_bundles: null argument");
+    if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles needs a TG_TABLE_LABEL table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (nbundles == 0) return TG_OK;
+    int rc;
+    const std::vector<ReadBatch> batches = split_reads(offs, nbundles, c->batch_bytes);
+    for (size_t i = 0; i < batches.size(); i++) {
+        const int b = (int)(i & 1);
+        const ReadBatch rb = batches[i];
+        const uint64_t m = rb.r1 - rb.r0, base = offs[rb.r0], nb = offs[rb.r1] - base;
+        if ((rc = tg_table_reserve(t, nb))) return rc;
+        CU(cudaStreamSynchronize(c->stream[b]));
+        if ((rc = upload_records(c, b, recs + base, nb))) return rc;
+        CU(c->offs[b].ensure((m + 1) * 8));
+        CU(cudaMemcpyAsync(c->offs[b].p, offs + rb.r0, (m + 1) * 8, cudaMemcpyHostToDevice, c->stream[b]));
+        CU(launch_label_tiles((const uint8_t*)c->recs[b].p, nb, (const uint64_t*)c->offs[b].p, base, m,
+                              first_index + (uint32_t)rb.r0, t->k, t->view(), c->sm_count, c->stream[b]));
+        c->launches++;
+    }
+    if ((rc = sync_all(c))) return rc;
+    return table_refresh(t);
+}
+
+int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,
+                         uint32_t first_index) {
+    if (!t || !d_recs || !d_offs) return fail(TG_ERR_ARG, "tg_label_bundles_dev: null argument");
+    if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles_dev needs a TG_TABLE_LABEL table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    if ((rc = tg_table_reserve(t, nbytes))) return rc;
+    CU(launch_label_tiles((const uint8_t*)d_recs, nbytes, (const uint64_t*)d_offs, 0, nbundles, first_index, t->k,
+                          t->view(), c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+
+static int ensure_lut(tg_ctx* c, const uint8_t* entropy_ok) {
+    CU(c->lut.ensure(26 * 26 * 26));
+    CU(cudaMemcpyAsync(c->lut.p, entropy_ok, 26 * 26 * 26, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nreads, int strand,
+                    const uint8_t* entropy_ok, int32_t* best, int32_t* pct, int32_t* score) {
+    if (!t || !entropy_ok || ((!recs || !offs || !best || !pct) && nreads))
+        return fail(TG_ERR_ARG, "tg_assign_reads: null argument");
+    if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_assign_reads needs a TG_TABLE_LABEL table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (nreads == 0) return TG_OK;
+    int rc;
+    if ((rc = sync_all(c))) return rc;
+    if ((rc = ensure_lut(c, entropy_ok))) return rc;
+    const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
+    struct Pending { bool live = false; ReadBatch rb; } pend[2];
+    auto drain = [&](int b) -> int {
+        if (!pend[b].live) return TG_OK;
+        const ReadBatch rb = pend[b].rb;
+        const uint64_t m = rb.r1 - rb.r0, base = offs[rb.r0];
+        int r2 = finish_long(c, b, t->k, assign_long_scratch_bytes,
+            [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
+                return launch_assign_long((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, t->k, strand,
+                                          t->slots, t->cap, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p,
+                                          (int32_t*)c->out_b[b].p, (int32_t*)c->out_c[b].p,
+                                          (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
+                                          c->stream[b]);
+            });
+        if (r2) return r2;
+        CU(cudaMemcpyAsync(best + rb.r0, c->out_a[b].p, m * 4, cudaMemcpyDeviceToHost, c->stream[b]));
+        CU(cudaMemcpyAsync(pct + rb.r0, c->out_b[b].p, m * 4, cudaMemcpyDeviceToHost, c->stream[b]));
+        if (score) CU(cudaMemcpyAsync(score + rb.r0, c->out_c[b].p, m * 4, cudaMemcpyDeviceToHost, c->stream[b]));
+        CU(cudaStreamSynchronize(c->stream[b]));
+        pend[b].live = false;
+        return TG_OK;
+    };
+    for (size_t i = 0; i < batches.size(); i++) {
+        const int b = (int)(i & 1);
+        if ((rc = drain(b))) return rc;
+        const ReadBatch rb = batches[i];
+        const uint64_t m = rb.r1 - rb.r0, base = offs[rb.r0], nb = offs[rb.r1] - base;
+        if ((rc = upload_records(c, b, recs + base, nb))) return rc;
+        CU(c->offs[b].ensure((m + 1) * 8));
+        CU(c->out_a[b].ensure(m * 4)); CU(c->out_b[b].ensure(m * 4)); CU(c->out_c[b].ensure(m * 4));
+        CU(c->long_idx[b].ensure(m * 4));
+        CU(cudaMemcpyAsync(c->offs[b].p, offs + rb.r0, (m + 1) * 8, cudaMemcpyHostToDevice, c->stream[b]));
+        CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
+        LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+        CU(launch_assign((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, strand, t->slots,
+                         t->cap, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
+                         (int32_t*)c->out_c[b].p, ll, c->stream[b]));
+        c->launches++;
+        pend[b].live = true; pend[b].rb = rb;
+    }
+    if ((rc = drain(0))) return rc;
+    if ((rc = drain(1))) return rc;
+    return TG_OK;
+}
+
+int tg_assign_reads_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int strand,
+                        const void* d_entropy_ok, void* d_best, void* d_pct) {
+    if (!t || !d_recs || !d_offs || !d_entropy_ok || !d_best || !d_pct)
+        return fail(TG_ERR_ARG, "tg_assign_reads_dev: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_assign_reads_dev: at most 2^31 reads per call");
+    const int b = 0;
+    CU(c->long_idx[b].ensure(nreads * 4));
+    CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
+    LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+    CU(launch_assign((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, strand, t->slots, t->cap,
+                     (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll, c->stream[b]));
+    c->launches++;
+    return finish_long(c, b, t->k, assign_long_scratch_bytes,
+        [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
+            return launch_assign_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, strand, t->slots, t->cap,
+                                      (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr,
+                                      (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
+                                      c->stream[b]);
+        });
+}
+
+// compute_entropy(string&) of Chrysalis/analysis/sequenceUtil.cc:326-355, evaluated for every count tuple:
+// fp32 throughout, slots in G,A,T,C order, log() on a float argument resolves to the float overload.
+void tg_entropy_table(int k, float min_entropy, uint8_t* ok) {
+    memset(ok, 0, 26 * 26 * 26);
+    if (k > 25) k = 25;   // the table is dimensioned for k <= 25 (ReadsToTranscripts hard-codes k = 25)
+    for (int g = 0; g <= k; g++)
+        for (int a = 0; a + g <= k; a++)
+            for (int tt = 0; tt + a + g <= k; tt++) {
+                const int cnt[4] = {g, a, tt, k - g - a - tt};
+                float entropy = 0;
+                for (int i = 0; i < 4; i++) {
+                    const float prob = (float)cnt[i] / (float)k;
+                    if (prob > 0) {
+                        const float val = prob * logf(1 / prob) / logf(2.0f);
+                        entropy += val;
+                    }
+                }
+                ok[(g * 26 + a) * 26 + tt] = !(entropy < min_entropy);
+            }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device memory + timing + measurement utilities
+// ---------------------------------------------------------------------------------------------------------
+int tg_dev_alloc(tg_ctx* c, uint64_t bytes, void** dptr) {
+    if (!c || !dptr) return fail(TG_ERR_ARG, "tg_dev_alloc: null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaMalloc(dptr, bytes ? bytes : 1));
+    return TG_OK;
+}
+
+int tg_dev_records_alloc(tg_ctx* c, uint64_t nbytes, void** dptr) {
+    if (!c || !dptr) return fail(TG_ERR_ARG, "tg_dev_records_alloc: null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    const uint64_t padded = padded_record_bytes(nbytes);
+    CU(cudaMalloc(dptr, padded));
+    CU(cudaMemsetAsync((char*)*dptr + nbytes, '\n', padded - nbytes, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_dev_free(tg_ctx* c, void* dptr) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    if (dptr) CU(cudaFree(dptr));
+    return TG_OK;
+}
+
+int tg_memcpy_h2d(tg_ctx* c, void* dptr, const void* host, uint64_t bytes) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_memcpy_d2h(tg_ctx* c, void* host, const void* dptr, uint64_t bytes) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_timer_start(tg_ctx* c) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaEventRecord(c->t0, c->stream[0]));
+    return TG_OK;
+}
+
+int tg_timer_stop(tg_ctx* c, float* ms) {
+    if (!c || !ms) return fail(TG_ERR_ARG, "null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaEventRecord(c->t1, c->stream[0]));
+    CU(cudaEventSynchronize(c->t1));
+    CU(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return TG_OK;
+}
+
+int tg_gups(tg_ctx* c, uint64_t slots, uint64_t nops, int mode, int reps, float* best_ms) {
+    if (!c || !best_ms || slots == 0) return fail(TG_ERR_ARG, "tg_gups: bad argument");
+    if (mode < 0 || mode > 2) return fail(TG_ERR_ARG, "tg_gups: mode must be 0, 1 or 2");
+    if (bind(c)) return TG_ERR_CUDA;
+    Slot* p = nullptr;
+    unsigned long long* sink = nullptr;
+    CU(cudaMalloc(&p, slots * sizeof(Slot)));
+    CU(cudaMalloc(&sink, 8));
+    CU(cudaMemsetAsync(p, 0, slots * sizeof(Slot), c->stream[0]));
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; r++) {   // first repetition is the warm-up
+        CU(cudaEventRecord(c->t0, c->stream[0]));
+        CU(launch_gups(p, slots, nops, mode, sink, c->sm_count, c->stream[0]));
+        c->launches++;
+        CU(cudaEventRecord(c->t1, c->stream[0]));
+        CU(cudaEventSynchronize(c->t1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->t0, c->t1));
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaFree(p); cudaFree(sink);
+    *best_ms = best;
+    return TG_OK;
+}
+
+int tg_synth_reads_dev(tg_ctx* c, const char* tx, const uint64_t* tx_offs, const uint64_t* tx_cum, uint32_t ntx,
+                       uint64_t npairs, int read_len, int frag_mean, int frag_sd, uint32_t err_per_million,
+                       uint32_t n_per_million, uint64_t seed, int stranded, void* d_recs) {
+    if (!c || !tx || !tx_offs || !tx_cum || !d_recs || ntx == 0) return fail(TG_ERR_ARG, "tg_synth_reads_dev: bad argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    uint8_t* d_tx = nullptr; uint64_t* d_offs = nullptr; uint64_t* d_cum = nullptr;
+    const uint64_t txb = tx_offs[ntx];
+    CU(cudaMalloc(&d_tx, txb ? txb : 1));
+    CU(cudaMalloc(&d_offs, (ntx + 1) * 8));
+    CU(cudaMalloc(&d_cum, ntx * 8));
+    CU(cudaMemcpyAsync(d_tx, tx, txb, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaMemcpyAsync(d_offs, tx_offs, (ntx + 1) * 8, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaMemcpyAsync(d_cum, tx_cum, ntx * 8, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(launch_synth_reads(d_tx, d_offs, d_cum, ntx, npairs, read_len, frag_mean, frag_sd, err_per_million,
+                          n_per_million, seed, stranded, (uint8_t*)d_recs, c->stream[0]));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(d_tx); cudaFree(d_offs); cudaFree(d_cum);
+    return TG_OK;
+}
+
+}  // extern "C"

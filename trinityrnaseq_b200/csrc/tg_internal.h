@@ -1,0 +1,88 @@
+// Internal launch interface between the C-ABI host layer (tg_api.cu) and the kernels (tg_kernels.cu,
+// tg_sort.cu, tg_synth.cu).  Nothing here is exported.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "tg_device.cuh"
+
+namespace tg {
+
+// ---- geometry of the flat-tile kernels (count / label) ------------------------------------------------
+constexpr int CT_THREADS = 256;
+constexpr int CT_TILE = CT_THREADS * 32;   // bases per tile: one 32-base chunk per thread
+constexpr int CT_HALO = 32;                // one extra chunk so windows may run past the tile end (k <= 32)
+constexpr int CT_LOAD = CT_TILE + CT_HALO; // bytes per TMA bulk copy (multiple of 16)
+
+// bytes a device record buffer of nbytes must be allocated (and '\n'-padded) to
+inline uint64_t padded_record_bytes(uint64_t nbytes) {
+    uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
+    if (ntiles == 0) ntiles = 1;
+    return ntiles * CT_TILE + CT_HALO;
+}
+
+// ---- geometry of the per-read kernels (stats / assign) ------------------------------------------------
+constexpr int PR_WARPS = 8;          // warps (= reads in flight) per CTA
+constexpr int PR_MAXWIN = 256;       // windows per read handled by the warp path (reads up to 256+k-1 bases)
+constexpr int PR_MAXCH = (PR_MAXWIN + 32) / 32 + 2;  // plane chunks per read incl. sentinel
+constexpr int LONG_THREADS = 256;    // CTA-per-read path for longer reads
+
+struct LongList {            // filled by the warp-path kernels, consumed by the CTA-per-read kernels
+    unsigned int* count;     // number of long reads found
+    unsigned int* max_win;   // largest window count among them
+    unsigned int* idx;       // their read indices (capacity = nreads)
+};
+
+int max_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device);
+
+// flat tiles: count every valid k-mer window of a '\n'-padded record buffer into a count table
+cudaError_t launch_count_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, TableView t,
+                               int sm_count, cudaStream_t s);
+// flat tiles: label every valid forward window with (bundle index + 1), highest index wins
+// (d_offs are offsets in the caller's frame; d_recs[0] is the byte at offset rec_base of that frame)
+cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uint64_t* d_offs, uint64_t rec_base,
+                               uint64_t nbundles, uint32_t first_bundle_index, int k, TableView t, int sm_count,
+                               cudaStream_t s);
+// (packed key, value) pairs -> table[canon(key)] += value
+cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
+                              TableView t, cudaStream_t s);
+// re-insert every live slot of `from` into `to` (growth)
+cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, cudaStream_t s);
+
+// per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
+cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                             int canonical, const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean,
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s);
+cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
+                                  const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean, float* d_stdev,
+                                  uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
+                                  unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s);
+size_t cov_stats_long_scratch_bytes(unsigned int max_win, int k, int nctas);
+
+cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                          int strand, const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok,
+                          int32_t* d_best, int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s);
+cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
+                               const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok, int32_t* d_best,
+                               int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
+                               unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s);
+size_t assign_long_scratch_bytes(unsigned int max_win, int k, int nctas);
+
+// table scans
+cudaError_t launch_histo(const Slot* slots, uint64_t cap, unsigned long long* d_bins /*10002*/, cudaStream_t s);
+cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, uint32_t max_count, int k,
+                          int canonical_repr, uint64_t* d_keys, uint32_t* d_vals, unsigned long long* d_n,
+                          cudaStream_t s);
+// tg_sort.cu: in-place ascending sort of (key,value) pairs on the low 2k bits (CUB radix sort)
+cudaError_t sort_pairs(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, int k, cudaStream_t s);
+
+// random-access roofline probes (GUPS): mode 0 = 16-B loads, 1 = 8-B load + RED.add, 2 = CAS + RED.add
+cudaError_t launch_gups(Slot* slots, uint64_t cap, uint64_t nops, int mode, unsigned long long* d_sink,
+                        int sm_count, cudaStream_t s);
+
+// tg_synth.cu: synthetic RNA-seq style reads generated on the device (bench / tests only)
+cudaError_t launch_synth_reads(const uint8_t* d_tx, const uint64_t* d_tx_offs, const uint64_t* d_tx_cum,
+                               uint32_t ntx, uint64_t npairs, int read_len, int frag_mean, int frag_sd,
+                               uint32_t err_per_million, uint32_t n_per_million, uint64_t seed, int stranded,
+                               uint8_t* d_recs, cudaStream_t s);
+
+}  // namespace tg

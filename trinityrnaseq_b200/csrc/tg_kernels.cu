@@ -1,0 +1,745 @@
+// Hand-written sm_100a kernels of the Trinity k-mer hot path.
+//
+//   k_flat_tiles<COUNT>   jellyfish count / KmerCounter::add_sequence     
+//   k_flat_tiles<LABEL>   ReadsToTranscripts bundle labelling             (§8a R3, R4)
+//   k_load_pairs          fastaToKmerCoverageStats --kmers loader         (§8a S2)
+//   k_cov_stats[_long]    compute_kmer_coverage / median / mean / stDev   (§8a S6-S9)
+//   k_assign[_long]       ReadsToTranscripts per-read vote                (§8a R5, R7-R9)
+//   k_histo, k_export     jellyfish histo / dump                          (§8a J2, J3)
+//   k_gups                random-access roofline probes                   (§8d)
+//
+// None of this is a dense contraction: no tensor cores.  The flat-tile kernels stage ASCII read tiles into
+// shared memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered), transpose them into
+// bit planes with warp ballots, and then every thread rolls 32 windows out of two plane words.
+#include "tg_internal.h"
+
+namespace tg {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+int max_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}
+
+// =========================================================================================================
+// Flat tiles: count / label
+// =========================================================================================================
+enum { MODE_COUNT = 0, MODE_LABEL = 1 };
+
+struct FlatSmem {
+    alignas(128) uint8_t ascii[2][CT_LOAD];
+    uint32_t p0[CT_THREADS + 1];
+    uint32_t p1[CT_THREADS + 1];
+    uint32_t pb[CT_THREADS + 1];
+    alignas(8) unsigned long long bar[2];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(CT_THREADS, 4)
+k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, TableView t,
+             const uint64_t* __restrict__ offs, uint64_t nrec, uint32_t first_index, uint64_t rec_base) {
+    __shared__ FlatSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned mk = kmask(k);
+    unsigned claimed = 0;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint64_t tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) {
+        mbar_arrive_expect_tx(&sm.bar[0], CT_LOAD);
+        bulk_copy_g2s(sm.ascii[0], recs + tile * CT_TILE, CT_LOAD, &sm.bar[0]);
+    }
+
+    for (unsigned it = 0; tile < ntiles; it++, tile += gridDim.x) {
+        const unsigned buf = it & 1u;
+        // prefetch the next tile into the other buffer (its previous contents were consumed before the
+        // __syncthreads that ended the previous iteration's pack step)
+        const uint64_t next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&sm.bar[buf ^ 1u], CT_LOAD);
+            bulk_copy_g2s(sm.ascii[buf ^ 1u], recs + next * CT_TILE, CT_LOAD, &sm.bar[buf ^ 1u]);
+        }
+        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+
+        // ---- ASCII -> bit planes: one ballot triple per 32-base chunk
+        const uint8_t* a = sm.ascii[buf];
+        for (int c = warp; c <= CT_THREADS; c += CT_THREADS / 32) {
+            const unsigned ch = a[c * 32 + lane];
+            const unsigned code = base_code(ch);
+            const unsigned b0 = __ballot_sync(FULL, code & 1u);
+            const unsigned b1 = __ballot_sync(FULL, code >> 1);
+            const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
+            if (lane == 0) { sm.p0[c] = b0; sm.p1[c] = b1; sm.pb[c] = bb; }
+        }
+        __syncthreads();   // planes complete; ascii[buf] is free for the TMA issued two iterations later
+
+        // ---- 32 windows per thread
+        const unsigned a0 = sm.p0[tid], a1 = sm.p1[tid], ab = sm.pb[tid];
+        const unsigned c0 = sm.p0[tid + 1], c1 = sm.p1[tid + 1], cb = sm.pb[tid + 1];
+
+        uint32_t label = 0;
+        uint64_t next_off = ~0ull;
+        const uint64_t g0 = rec_base + tile * CT_TILE + (uint64_t)tid * 32;   // in the offs[] frame
+        if (MODE == MODE_LABEL) {
+            // record index of this thread's first base: last offs[i] <= g0
+            uint64_t lo = 0, hi = nrec;   // candidates 0..nrec-1 (offs has nrec+1 entries), so lo+1 <= nrec
+            while (hi - lo > 1) {
+                uint64_t mid = (lo + hi) >> 1;
+                if (offs[mid] <= g0) lo = mid; else hi = mid;
+            }
+            label = (uint32_t)lo;
+            next_off = offs[lo + 1];
+        }
+
+        if (ab != FULL || cb != FULL) {
+#pragma unroll 1
+            for (int g = 0; g < 32; g += 4) {
+                unsigned long long key[4];
+                unsigned long long idx[4];
+                unsigned long long cur[4];
+                unsigned cnt[4];
+                uint32_t lab[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int s = g + u;
+                    const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
+                    const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+                    const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+                    unsigned long long kf = make_key(f0, f1);
+                    if (MODE == MODE_COUNT) {
+                        if (canonical) {
+                            const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                            kf = kr < kf ? kr : kf;
+                        }
+                    } else {
+                        // a valid window lies inside one record, so label < nrec whenever we advance
+                        if (!bad) while (g0 + s >= next_off) { label++; next_off = offs[label + 1]; }
+                        lab[u] = first_index + label + 1;
+                    }
+                    key[u] = bad ? 0ull : kf;
+                    cnt[u] = 1;
+                }
+                if (MODE == MODE_COUNT) {
+                    // run-length merge inside the group: homopolymer runs hit one slot once, not four times
+#pragma unroll
+                    for (int u = 1; u < 4; u++)
+                        if (key[u] != 0ull && key[u] == key[u - 1]) { cnt[u] += cnt[u - 1]; key[u - 1] = 0ull; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (key[u] != 0ull) {
+                        idx[u] = home_slot(key[u], t.cap);
+                        cur[u] = __ldcg(&t.slots[idx[u]].key);
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (key[u] != 0ull) {
+                        Slot* sl = table_upsert_slot(t, key[u], idx[u], cur[u], claimed);
+                        if (sl) {
+                            if (MODE == MODE_COUNT) atomicAdd(&sl->val, cnt[u]);
+                            else atomicMax(&sl->val, lab[u]);
+                        }
+                    }
+            }
+        }
+        __syncthreads();   // planes consumed before the next iteration overwrites them
+    }
+
+    // distinct-key accounting: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+    if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
+}
+
+static int flat_grid(const void* kern, uint64_t ntiles, int sm_count) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT_THREADS, 0);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t g = (uint64_t)per_sm * sm_count;
+    if (g > ntiles) g = ntiles;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+cudaError_t launch_count_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, TableView t,
+                               int sm_count, cudaStream_t s) {
+    if (nbytes == 0) return cudaSuccess;
+    const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
+    const int grid = flat_grid((const void*)k_flat_tiles<MODE_COUNT>, ntiles, sm_count);
+    k_flat_tiles<MODE_COUNT><<<grid, CT_THREADS, 0, s>>>(d_recs, ntiles, k, canonical, t, nullptr, 0, 0, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uint64_t* d_offs, uint64_t rec_base,
+                               uint64_t nbundles, uint32_t first_bundle_index, int k, TableView t, int sm_count,
+                               cudaStream_t s) {
+    if (nbytes == 0 || nbundles == 0) return cudaSuccess;
+    const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
+    const int grid = flat_grid((const void*)k_flat_tiles<MODE_LABEL>, ntiles, sm_count);
+    k_flat_tiles<MODE_LABEL><<<grid, CT_THREADS, 0, s>>>(d_recs, ntiles, k, 0, t, d_offs, nbundles, first_bundle_index,
+                                                    rec_base);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
+// (packed key, value) pairs and rehash
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n, int k,
+             int canonical, TableView t) {
+    unsigned claimed = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned p0, p1;
+        packed_to_planes(keys[i], k, p0, p1);
+        unsigned long long key = make_key(p0, p1);
+        if (canonical) {
+            const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
+            key = kr < key ? kr : key;
+        }
+        table_add(t, key, vals[i], claimed);
+    }
+    for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
+}
+
+cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
+                              TableView t, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_load_pairs<<<(int)blocks, 256, 0, s>>>(d_keys, d_vals, n, k, canonical, t);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label) {
+    unsigned claimed = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+        const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
+        if (key == 0ull) continue;
+        unsigned long long idx = home_slot(key, to.cap);
+        unsigned long long cur = __ldcg(&to.slots[idx].key);
+        Slot* sl = table_upsert_slot(to, key, idx, cur, claimed);
+        if (sl) { if (is_label) atomicMax(&sl->val, s.z); else atomicAdd(&sl->val, s.z); }
+    }
+    for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
+}
+
+cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, cudaStream_t s) {
+    if (from_cap == 0) return cudaSuccess;
+    uint64_t blocks = (from_cap + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_rehash<<<(int)blocks, 256, 0, s>>>(from, from_cap, to, is_label);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
+// Per-read machinery shared by stats and assign.  GS = group size: 32 (one warp per read, buffers in shared
+// memory) or LONG_THREADS (one CTA per read, buffers in global scratch).
+// =========================================================================================================
+template <int GS> __device__ __forceinline__ void gsync() {
+    if (GS == 32) __syncwarp(); else __syncthreads();
+}
+
+// planes for chunks 0..nch (chunk nch and everything past L is invalid)
+template <int GS>
+__device__ __forceinline__ void pack_read_planes(const uint8_t* __restrict__ seq, int L, int nch, uint32_t* P0,
+                                                 uint32_t* P1, uint32_t* PB, int gtid) {
+    const int lane = gtid & 31, w = gtid >> 5;
+    for (int c = w; c <= nch; c += GS / 32) {
+        const int pos = c * 32 + lane;
+        const unsigned ch = pos < L ? seq[pos] : (unsigned)'\n';
+        const unsigned code = base_code(ch);
+        const unsigned b0 = __ballot_sync(FULL, code & 1u);
+        const unsigned b1 = __ballot_sync(FULL, code >> 1);
+        const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
+        if (lane == 0) { P0[c] = b0; P1[c] = b1; PB[c] = bb; }
+    }
+}
+
+// ascending bitonic sort of buf[0..n2), n2 a power of two
+template <int GS, typename T>
+__device__ __forceinline__ void bitonic_sort(T* buf, unsigned n2, int gtid) {
+    for (unsigned kk = 2; kk <= n2; kk <<= 1) {
+        for (unsigned j = kk >> 1; j > 0; j >>= 1) {
+            for (unsigned i = gtid; i < n2; i += GS) {
+                const unsigned ixj = i ^ j;
+                if (ixj > i) {
+                    const T x = buf[i], y = buf[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((x > y) == up) { buf[i] = y; buf[ixj] = x; }
+                }
+            }
+            gsync<GS>();
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned next_pow2(unsigned n) {
+    unsigned p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+template <int GS>
+__device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v, unsigned long long* red, int gtid) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (GS == 32) return v;
+    gsync<GS>();
+    if ((gtid & 31) == 0) red[gtid >> 5] = v;
+    gsync<GS>();
+    unsigned long long tot = 0;
+    for (int w = 0; w < GS / 32; w++) tot += red[w];
+    gsync<GS>();
+    return tot;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// coverage statistics of one read (fastaToKmerCoverageStats.cpp:300-402)
+// ---------------------------------------------------------------------------------------------------------
+template <int GS>
+__device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, int L, int k, int canonical,
+                                               const Slot* __restrict__ slots, uint64_t cap, uint32_t* P0,
+                                               uint32_t* P1, uint32_t* PB, uint32_t* cov, float* sq,
+                                               unsigned long long* red, uint32_t* per_kmer, uint32_t& median,
+                                               float& mean, float& stdev, int gtid) {
+    const int nwin = L >= k ? L - k + 1 : 0;
+    if (nwin == 0) {   // S6: shorter than k -> empty vector; S7-S9 on n = 0: 0, 0, sqrt(0/-1) = -0
+        median = 0; mean = 0.0f; stdev = __int_as_float(0x80000000);
+        return;
+    }
+    const unsigned mk = kmask(k);
+    const int nch = (L + 31) >> 5;
+    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
+    gsync<GS>();
+
+    unsigned long long part = 0;
+    for (int p = gtid; p < nwin; p += GS) {
+        const int c = p >> 5, o = p & 31;
+        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+        unsigned v = 0;
+        if (!bad) {
+            const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+            const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+            unsigned long long key = make_key(f0, f1);
+            if (canonical) {
+                const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                key = kr < key ? kr : key;
+            }
+            v = table_lookup(slots, cap, key);
+        }
+        if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
+        cov[p] = v;
+        if (per_kmer) per_kmer[p] = v;
+        part += v;
+    }
+    const unsigned long long sum = group_sum_u64<GS>(part, red, gtid);   // `long` sum, exact
+    const float avg = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));
+    gsync<GS>();
+    for (int p = gtid; p < nwin; p += GS) {
+        const float d = __fsub_rn(__uint2float_rn(cov[p]), avg);
+        sq[p] = __fmul_rn(d, d);               // two roundings, no FMA (x86-64 -O2 without -march)
+    }
+    gsync<GS>();
+    float sd;
+    if (nwin == 1) {
+        sd = __int_as_float(X86_DEFAULT_NAN_BITS);   // 0/0 on SSE = default NaN with the sign bit set ("-nan")
+    } else {
+        float acc = 0.0f;
+        if (gtid == 0) {
+            for (int p = 0; p < nwin; p++) acc = __fadd_rn(acc, sq[p]);   // strict read order
+            acc = __fsqrt_rn(__fdiv_rn(acc, __int2float_rn(nwin - 1)));
+        }
+        sd = acc;
+    }
+    // median: sort ascending, odd -> middle, even -> u32 (wrapping) mean of the two middles
+    const unsigned n2 = next_pow2((unsigned)nwin);
+    for (unsigned p = nwin + gtid; p < n2; p += GS) cov[p] = 0xFFFFFFFFu;
+    gsync<GS>();
+    bitonic_sort<GS, uint32_t>(cov, n2, gtid);
+    median = (nwin & 1) ? cov[nwin / 2] : (uint32_t)(cov[(nwin - 1) / 2] + cov[nwin / 2]) / 2u;
+    mean = avg;
+    stdev = sd;    // meaningful in gtid 0 only
+}
+
+struct PerReadSmem {
+    uint32_t p0[PR_WARPS][PR_MAXCH];
+    uint32_t p1[PR_WARPS][PR_MAXCH];
+    uint32_t pb[PR_WARPS][PR_MAXCH];
+    uint32_t a[PR_WARPS][2 * PR_MAXWIN];    // stats: cov[PR_MAXWIN] + sq[PR_MAXWIN]; assign: hits[2*PR_MAXWIN]
+    unsigned int nhits[PR_WARPS];
+};
+
+__global__ void __launch_bounds__(PR_WARPS * 32)
+k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
+            int k, int canonical, const Slot* __restrict__ slots, uint64_t cap, uint32_t* __restrict__ median,
+            float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll) {
+    __shared__ PerReadSmem sm;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t r = (uint64_t)blockIdx.x * PR_WARPS + w;
+    if (r >= nreads) return;
+    const uint64_t o0 = offs[r], o1 = offs[r + 1];
+    const int L = (int)(o1 - o0 - 1);            // the record's last byte is its '\n' terminator
+    const int nwin = L >= k ? L - k + 1 : 0;
+    if (nwin > PR_MAXWIN) {
+        if (lane == 0) {
+            const unsigned slot = atomicAdd(ll.count, 1u);
+            ll.idx[slot] = (unsigned)r;
+            atomicMax(ll.max_win, (unsigned)nwin);
+        }
+        return;
+    }
+    uint32_t med; float mu, sd;
+    read_cov_stats<32>(recs + (o0 - rec_base), L, k, canonical, slots, cap, sm.p0[w], sm.p1[w], sm.pb[w], sm.a[w],
+                       reinterpret_cast<float*>(sm.a[w] + PR_MAXWIN), nullptr,
+                       per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, lane);
+    if (lane == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
+}
+
+cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                             int canonical, const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean,
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s) {
+    if (nreads == 0) return cudaSuccess;
+    const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
+    k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, cap,
+                                                           d_median, d_mean, d_stdev, d_per_kmer, ll);
+    return cudaGetLastError();
+}
+
+// scratch layout per CTA of the long path: planes 3*(nch+1) u32 | cov n2 u32 | sq n2 f32
+static inline size_t long_nch(unsigned max_win, int k) { return ((size_t)max_win + k - 1 + 31) / 32 + 2; }
+static inline size_t pow2_ge(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+static inline size_t long_scratch_words(unsigned max_win, int k, int mult) {
+    return 3 * long_nch(max_win, k) + (size_t)2 * pow2_ge((size_t)mult * max_win);
+}
+size_t cov_stats_long_scratch_bytes(unsigned max_win, int k, int nctas) {
+    return long_scratch_words(max_win, k, 1) * 4 * (size_t)nctas;
+}
+size_t assign_long_scratch_bytes(unsigned max_win, int k, int nctas) {
+    return long_scratch_words(max_win, k, 2) * 4 * (size_t)nctas;
+}
+
+__global__ void __launch_bounds__(LONG_THREADS)
+k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k,
+                 int canonical, const Slot* __restrict__ slots, uint64_t cap, uint32_t* __restrict__ median,
+                 float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer,
+                 const unsigned int* __restrict__ long_idx, unsigned int n_long, unsigned int max_win,
+                 uint32_t* scratch, size_t words_per_cta) {
+    __shared__ unsigned long long red[LONG_THREADS / 32];
+    const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
+    size_t n2max = 1; while (n2max < max_win) n2max <<= 1;
+    uint32_t* base = scratch + (size_t)blockIdx.x * words_per_cta;
+    uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
+    uint32_t* cov = PB + nchw; float* sq = reinterpret_cast<float*>(cov + n2max);
+    for (unsigned i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const uint64_t r = long_idx[i];
+        const uint64_t o0 = offs[r], o1 = offs[r + 1];
+        const int L = (int)(o1 - o0 - 1);
+        uint32_t med; float mu, sd;
+        read_cov_stats<LONG_THREADS>(recs + (o0 - rec_base), L, k, canonical, slots, cap, P0, P1, PB, cov, sq, red,
+                                     per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, threadIdx.x);
+        if (threadIdx.x == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
+                                  const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean, float* d_stdev,
+                                  uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
+                                  unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
+    if (n_long == 0) return cudaSuccess;
+    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, cap, d_median, d_mean,
+                                                    d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
+                                                    (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// read -> bundle vote of one read (ReadsToTranscripts.cc:216-274)
+// ---------------------------------------------------------------------------------------------------------
+// entropy_ok is indexed [nG][nA][nT] (26^3 bytes); nC is implied for an all-ACGT window.
+__device__ __forceinline__ bool window_entropy_ok(const uint8_t* __restrict__ lut, unsigned f0, unsigned f1, unsigned mk,
+                                                  bool rc) {
+    // codes: A=00 C=01 G=10 T=11 (bit1 = plane1, bit0 = plane0)
+    const int nG = __popc(f1 & ~f0 & mk), nA = __popc(~f1 & ~f0 & mk), nT = __popc(f1 & f0 & mk);
+    const int nC = __popc(~f1 & f0 & mk);
+    // the reference evaluates the reverse-complemented string in the same G,A,T,C slot order:
+    // its counts are (nC, nT, nA, nG) of the forward window
+    return rc ? lut[(nC * 26 + nT) * 26 + nA] != 0 : lut[(nG * 26 + nA) * 26 + nT] != 0;
+}
+
+template <int GS>
+__device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int L, int k, int strand,
+                                            const Slot* __restrict__ slots, uint64_t cap,
+                                            const uint8_t* __restrict__ lut, uint32_t* P0, uint32_t* P1, uint32_t* PB,
+                                            int32_t* hits, unsigned int* nhits_p, int32_t& best, int32_t& score,
+                                            int32_t& pct, int gtid) {
+    const int nwin = L - k + 1;        // num_kmer_pos, may be <= 0
+    best = -1; score = 0;
+    if (nwin <= 0) { pct = 0; return; }
+    const unsigned mk = kmask(k);
+    const int nch = (L + 31) >> 5;
+    if (gtid == 0) *nhits_p = 0;
+    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
+    gsync<GS>();
+    for (int p = gtid; p < nwin; p += GS) {
+        const int c = p >> 5, o = p & 31;
+        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+        if (bad) continue;              // a window with a non-ACGT character can never equal a table k-mer
+        const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+        const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+        if (window_entropy_ok(lut, f0, f1, mk, false)) {
+            const unsigned v = table_lookup(slots, cap, make_key(f0, f1));
+            if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
+        }
+        if (!strand && window_entropy_ok(lut, f0, f1, mk, true)) {
+            const unsigned v = table_lookup(slots, cap, make_key(rc_plane(f0, k), rc_plane(f1, k)));
+            if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
+        }
+    }
+    gsync<GS>();
+    const int n = (int)*nhits_p;
+    int b = -1, sc = 0;
+    if (n >= 2) {
+        const unsigned n2 = next_pow2((unsigned)n);
+        for (unsigned p = n + gtid; p < n2; p += GS) hits[p] = 0x7FFFFFFF;
+        gsync<GS>();
+        bitonic_sort<GS, int32_t>(hits, n2, gtid);
+        // a label with m hits scores m-1, the last (largest) label m-2; strict '>' while scanning ascending
+        // labels => ties go to the smaller label (ReadsToTranscripts.cc:253-268)
+        const int32_t last = hits[n - 1];
+        for (int i = gtid; i < n; i += GS) {
+            const int32_t h = hits[i];
+            if (i == n - 1 || hits[i + 1] != h) {        // end of a run: multiplicity by lower_bound
+                int lo = 0, hi = i;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid] < h) lo = mid + 1; else hi = mid; }
+                const int m = i + 1 - lo;
+                const int s = m - 1 - (h == last ? 1 : 0);
+                if (s > sc || (s == sc && s > 0 && h < b)) { sc = s; b = h; }
+            }
+        }
+        // group arg-max (score desc, label asc)
+        for (int o = 16; o > 0; o >>= 1) {
+            const int os = __shfl_xor_sync(FULL, sc, o), ob = __shfl_xor_sync(FULL, b, o);
+            if (os > sc || (os == sc && os > 0 && ob < b)) { sc = os; b = ob; }
+        }
+        if (GS > 32) {
+            __shared__ int wsc[LONG_THREADS / 32], wb[LONG_THREADS / 32];
+            gsync<GS>();
+            if ((gtid & 31) == 0) { wsc[gtid >> 5] = sc; wb[gtid >> 5] = b; }
+            gsync<GS>();
+            sc = wsc[0]; b = wb[0];
+            for (int w = 1; w < GS / 32; w++)
+                if (wsc[w] > sc || (wsc[w] == sc && wsc[w] > 0 && wb[w] < b)) { sc = wsc[w]; b = wb[w]; }
+            gsync<GS>();
+        }
+        if (sc <= 0) { b = -1; sc = 0; }
+    }
+    best = b; score = sc;
+    // pct = (int)((float)max / num_kmer_pos * 100 + 0.5): fp32 divide, fp32 multiply, double add, truncate
+    const float q = __fmul_rn(__fdiv_rn(__int2float_rn(sc), __int2float_rn(nwin)), 100.0f);
+    pct = (int)__dadd_rn((double)q, 0.5);
+}
+
+__global__ void __launch_bounds__(PR_WARPS * 32)
+k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int k,
+         int strand, const Slot* __restrict__ slots, uint64_t cap, const uint8_t* __restrict__ lut,
+         int32_t* __restrict__ best, int32_t* __restrict__ pct, int32_t* __restrict__ score, LongList ll) {
+    __shared__ PerReadSmem sm;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t r = (uint64_t)blockIdx.x * PR_WARPS + w;
+    if (r >= nreads) return;
+    const uint64_t o0 = offs[r], o1 = offs[r + 1];
+    const int L = (int)(o1 - o0 - 1);
+    const int nwin = L - k + 1;
+    if (nwin > PR_MAXWIN) {
+        if (lane == 0) {
+            const unsigned slot = atomicAdd(ll.count, 1u);
+            ll.idx[slot] = (unsigned)r;
+            atomicMax(ll.max_win, (unsigned)nwin);
+        }
+        return;
+    }
+    int32_t b, sc, pc;
+    read_assign<32>(recs + (o0 - rec_base), L, k, strand, slots, cap, lut, sm.p0[w], sm.p1[w], sm.pb[w],
+                    reinterpret_cast<int32_t*>(sm.a[w]), &sm.nhits[w], b, sc, pc, lane);
+    if (lane == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
+}
+
+cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                          int strand, const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok, int32_t* d_best,
+                          int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s) {
+    if (nreads == 0) return cudaSuccess;
+    const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
+    k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, cap,
+                                                        d_entropy_ok, d_best, d_pct, d_score, ll);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(LONG_THREADS)
+k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k, int strand,
+              const Slot* __restrict__ slots, uint64_t cap, const uint8_t* __restrict__ lut, int32_t* __restrict__ best,
+              int32_t* __restrict__ pct, int32_t* __restrict__ score, const unsigned int* __restrict__ long_idx,
+              unsigned int n_long, unsigned int max_win, uint32_t* scratch, size_t words_per_cta) {
+    __shared__ unsigned int nhits;
+    const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
+    uint32_t* base = scratch + (size_t)blockIdx.x * words_per_cta;
+    uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
+    int32_t* hits = reinterpret_cast<int32_t*>(PB + nchw);
+    for (unsigned i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const uint64_t r = long_idx[i];
+        const uint64_t o0 = offs[r], o1 = offs[r + 1];
+        const int L = (int)(o1 - o0 - 1);
+        int32_t b, sc, pc;
+        read_assign<LONG_THREADS>(recs + (o0 - rec_base), L, k, strand, slots, cap, lut, P0, P1, PB, hits, &nhits, b, sc,
+                                  pc, threadIdx.x);
+        if (threadIdx.x == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
+                               const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok, int32_t* d_best,
+                               int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
+                               unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
+    if (n_long == 0) return cudaSuccess;
+    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, cap, d_entropy_ok, d_best,
+                                                 d_pct, d_score, d_long_idx, n_long, max_win, (uint32_t*)d_scratch,
+                                                 long_scratch_words(max_win, k, 2));
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
+// Table scans: histo (jellyfish histo: bins 1..10000, 10001 = everything larger) and export (dump)
+// =========================================================================================================
+constexpr int HISTO_BINS = 10002;
+
+__global__ void __launch_bounds__(256)
+k_histo(const Slot* __restrict__ slots, uint64_t cap, unsigned long long* __restrict__ bins) {
+    __shared__ unsigned int sb[HISTO_BINS];
+    for (int i = threadIdx.x; i < HISTO_BINS; i += blockDim.x) sb[i] = 0;
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&slots[i]));
+        if ((s.x | s.y) == 0u) continue;
+        const unsigned c = s.z;
+        atomicAdd(&sb[c > 10000u ? 10001u : c], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HISTO_BINS; i += blockDim.x)
+        if (sb[i]) atomicAdd(&bins[i], (unsigned long long)sb[i]);
+}
+
+cudaError_t launch_histo(const Slot* slots, uint64_t cap, unsigned long long* d_bins, cudaStream_t s) {
+    if (cap == 0) return cudaSuccess;
+    uint64_t blocks = (cap + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_histo<<<(int)blocks, 256, 0, s>>>(slots, cap, d_bins);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+k_export(const Slot* __restrict__ slots, uint64_t cap, uint32_t min_count, uint32_t max_count, int k, int canonical_repr,
+         uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_n) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (cap + stride - 1) / stride;
+    for (uint64_t rd = 0; rd < rounds; rd++) {
+        const uint64_t i = rd * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        bool keep = false;
+        uint4 s = make_uint4(0, 0, 0, 0);
+        if (i < cap) {
+            s = __ldcs(reinterpret_cast<const uint4*>(&slots[i]));
+            keep = (s.x | s.y) != 0u && s.z >= min_count && s.z <= max_count;
+        }
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (m == 0) continue;
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(out_n, (unsigned long long)__popc(m));
+        basei = __shfl_sync(FULL, basei, 0);
+        if (keep) {
+            const uint64_t o = basei + __popc(m & ((1u << lane) - 1u));
+            if (out_keys) {
+                unsigned long long pk = planes_to_packed(s.x, s.y & 0x7FFFFFFFu, k);
+                if (canonical_repr) {           // jellyfish prints the lexicographically smaller strand (A<C<G<T)
+                    const unsigned long long rc = packed_revcomp(pk, k);
+                    pk = rc < pk ? rc : pk;
+                }
+                out_keys[o] = pk;
+                out_vals[o] = s.z;
+            }
+        }
+    }
+}
+
+cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, uint32_t max_count, int k,
+                          int canonical_repr, uint64_t* d_keys, uint32_t* d_vals, unsigned long long* d_n,
+                          cudaStream_t s) {
+    if (cap == 0) return cudaSuccess;
+    uint64_t blocks = (cap + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_export<<<(int)blocks, 256, 0, s>>>(slots, cap, min_count, max_count, k, canonical_repr, d_keys, d_vals, d_n);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
+// GUPS: the measured random-access roofline for this table geometry
+// =========================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_gups(Slot* slots, uint64_t cap, uint64_t nops, unsigned long long* sink) {
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (uint64_t i = tid; i < nops; i += 4 * stride) {
+        unsigned long long idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) idx[u] = __umul64hi(mix64(0x9E3779B97F4A7C15ull * (i + u * stride + 1)), cap);
+        if (MODE == 0) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i + u * stride < nops) v[u] = __ldcg(reinterpret_cast<const uint4*>(&slots[idx[u]]));
+                else v[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc += v[u].x + v[u].z;
+        } else {
+            unsigned long long kv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                kv[u] = 0;
+                if (i + u * stride < nops) {
+                    if (MODE == 1) kv[u] = __ldcg(&slots[idx[u]].key);
+                    else kv[u] = atomicCAS(&slots[idx[u]].key, 0ull, KEY_TAG | idx[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i + u * stride < nops) { atomicAdd(&slots[idx[u]].val, 1u); acc += kv[u]; }
+        }
+    }
+    if (acc == 0x123456789ull) *sink = acc;   // keep the loads alive
+}
+
+cudaError_t launch_gups(Slot* slots, uint64_t cap, uint64_t nops, int mode, unsigned long long* d_sink, int sm_count,
+                        cudaStream_t s) {
+    const int grid = sm_count * 8;
+    if (mode == 0) k_gups<0><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);
+    else if (mode == 1) k_gups<1><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);
+    else k_gups<2><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);
+    return cudaGetLastError();
+}
+
+}  // namespace tg
