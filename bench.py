@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- Trinity k-mer hot path on B200: 25-mers/s counted + queried.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over the whole synthetic read set: clear the table, count every canonical
+25-mer (jellyfish count stage), then per-read k-mer coverage statistics for every read
+(fastaToKmerCoverageStats).  Workload at N=1 = BASELINE.json configs[1]: 10 M PE 2x100 bp reads from a random
+20 k-transcript set (20 M reads, 2.0 Gbase; 1.52 G k-mer positions counted + 1.52 G queried per step).
+
+  value     device-resident throughput: reads already in HBM, CUDA events on the library's stream
+  e2e       the same step through the host-buffer C ABI (tg_count_reads + tg_cov_stats on pinned host
+            arrays): H2D of reads/offsets and D2H of the per-read results inside the timed region
+  roofline  dominant kernel (k_flat_tiles<COUNT>): 64 B algorithmic HBM bytes per counted position vs the measured
+            HBM peak; random_access = the same ratio against the GUPS probe measured in this run
+  cpu_baseline  the reference's own CPU tool (oracle/_ref/fastaToKmerCoverageStats, else the C oracle) on a
+            bounded sample of the same reads, timed on this box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 25
+METRIC = "25-mers/sec counted+queried"
+UNIT = "kmers/s"
+SEED = 20251017
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic transcriptome (host, numpy) -- reads themselves are generated on the device from it
+# ---------------------------------------------------------------------------------------------------------
+def make_transcriptome(ntx, seed):
+    rng = np.random.default_rng(seed)
+    lens = np.clip(np.round(rng.lognormal(np.log(1500), 0.6, ntx)), 300, 10000).astype(np.int64)
+    offs = np.zeros(ntx + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    tx = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(offs[-1]))]
+    w = rng.lognormal(0.0, 2.0, ntx) * lens          # expression x length = share of fragments
+    cum = np.cumsum(w / w.sum())
+    cum_u64 = np.minimum(cum * 2.0 ** 64, 2.0 ** 64 - 2048).astype(np.uint64)
+    cum_u64[-1] = np.uint64(2 ** 64 - 1)
+    return tx, offs, cum_u64
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU reference leg
+# ---------------------------------------------------------------------------------------------------------
+def write_sample_fasta(path, recs, read_len, nreads):
+    stride = read_len + 1
+    with open(path, "wb") as f:
+        for i in range(nreads):
+            f.write(b">r%d/1\n" % i)
+            f.write(recs[i * stride:(i + 1) * stride].tobytes())
+
+
+def cpu_reference_run(sample_recs, read_len, nreads, threads=6):
+    """Time the reference CPU tool on `nreads` reads: count (--kmers_from_reads) + stats in one process, exactly the
+    two stages of a step.  Returns (kmers_per_s, seconds, kind, cores)."""
+    positions = 2 * nreads * (read_len - K + 1)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "fastaToKmerCoverageStats")
+    if os.path.exists(ref_bin):
+        with tempfile.TemporaryDirectory() as td:
+            fa = os.path.join(td, "sample.fa")
+            write_sample_fasta(fa, sample_recs, read_len, nreads)
+            t0 = time.perf_counter()
+            with open(os.path.join(td, "out.stats"), "wb") as out:
+                subprocess.run([ref_bin, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", str(K), "--num_threads",
+                                str(threads), "--DS"], stdout=out, stderr=subprocess.DEVNULL, check=True)
+            dt = time.perf_counter() - t0
+        return positions / dt, dt, "reference", threads    # the tool caps itself at 6 threads (MAX_THREADS)
+    from oracle import oracle_py as orc
+    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(read_len + 1)
+    buf = sample_recs[: nreads * (read_len + 1)]
+    t0 = time.perf_counter()
+    kc = orc.KmerCounter(K, True)
+    kc.add_records(buf, offs)
+    kc.coverage_stats(buf, offs)
+    dt = time.perf_counter() - t0
+    return positions / dt, dt, "port", 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per GPU (configs[1]: 10 M)")
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--ntx", type=int, default=20_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gups", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    read_len, npairs = args.read_len, args.pairs
+    nreads = 2 * npairs
+    nwin = read_len - K + 1
+    positions_per_step = 2 * nreads * nwin            # counted + queried, per GPU
+    config = {"workload": f"configs[1]: synthetic {npairs / 1e6:g}M PE 2x{read_len} bp reads from a random "
+                          f"{args.ntx}-transcript set, k=25 canonical count + fastaToKmerCoverageStats, per GPU",
+              "reads_per_gpu": nreads, "k": K, "unit_definition": "k-mer window positions counted + positions queried",
+              "l2_policy": "inputs (2.0 GB reads, >=10 GB table) exceed the 126 MB L2; no flush needed",
+              "table_sharding": "per-GPU private table (reads sharded by rank)" if world > 1 else "single table"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        return run_reference_arm(args, config, world, W)
+
+    import trinityrnaseq_b200 as tg
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = tg.Context(local_rank)
+    info = ctx.info()
+    tx, tx_offs, tx_cum = make_transcriptome(args.ntx, SEED)
+    d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, npairs, read_len, seed=SEED + 7919 * rank)
+    stride = read_len + 1
+    offs_host, offs_owner = ctx.pinned((nreads + 1,), np.uint64)
+    offs_host[:] = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(stride)
+    d_offs = ctx.dev_alloc(offs_host.nbytes)
+    ctx.h2d(d_offs, offs_host)
+    d_med, d_mean, d_sd = ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads)
+
+    # table sized once from a cheap prefix estimate: errors dominate distinct k-mers (~ K novel k-mers per error)
+    expected = int(tx_offs[-1]) + int(nreads * read_len * 0.005 * K * 1.15) + (1 << 20)
+    kc = tg.KmerCounter(ctx, K, is_ds=True, expected_keys=expected)
+
+    def device_step():
+        kc.clear()
+        kc.add_records_dev(d_recs, nbytes)
+        kc.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ------------------------------------------------------------------------
+    for _ in range(W):
+        device_step()
+    tinfo = kc.info()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ctx.launch_count()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        device_step()
+    ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    if dist is not None:
+        import torch
+        tms = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * positions_per_step * args.steps / (ms / 1e3)
+
+    # dominant kernel alone (count), for the roofline block
+    kc.clear()
+    ctx.sync()
+    ctx.timer_start()
+    kc.add_records_dev(d_recs, nbytes)
+    count_ms = ctx.timer_stop()
+    ctx.timer_start()
+    kc.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
+    stats_ms = ctx.timer_stop()
+
+    # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------------
+    recs_host, recs_owner = ctx.pinned((nbytes,), np.uint8)
+    ctx.d2h(d_recs, recs_host)
+    med_h, o1 = ctx.pinned((nreads,), np.uint32)
+    mean_h, o2 = ctx.pinned((nreads,), np.float32)
+    sd_h, o3 = ctx.pinned((nreads,), np.float32)
+    from trinityrnaseq_b200 import _lib
+    L = _lib.lib()
+
+    def host_step():
+        kc.clear()
+        _lib.check(L.tg_count_reads(kc._h, recs_host.ctypes.data, nbytes, 1))
+        _lib.check(L.tg_cov_stats(kc._h, recs_host.ctypes.data, offs_host.ctypes.data, nreads, 1, med_h.ctypes.data,
+                                  mean_h.ctypes.data, sd_h.ctypes.data, None))
+
+    e2e_steps = max(1, min(args.steps, 3))
+    host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        te = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    e2e_value = world * positions_per_step * e2e_steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    # parity spot check inside the bench: device-resident and host-buffer paths must agree bit for bit
+    med_d = ctx.d2h(d_med, 4 * nreads, np.uint32)
+    sd_d = ctx.d2h(d_sd, 4 * nreads, np.uint32)
+    assert np.array_equal(med_d, med_h) and np.array_equal(sd_d, sd_h.view(np.uint32)), "device vs host path mismatch"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (dominant kernel = count) ---------------------------------------------------------------
+    peak, peak_kind = load_peaks()
+    count_positions = nreads * nwin
+    achieved = count_positions * 64 / (count_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_flat_tiles<COUNT>", "achieved": round(achieved, 1), "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "bytes_per_unit": 64, "units_per_launch": count_positions, "kernel_ms": round(count_ms, 3),
+                "stats_kernel_ms": round(stats_ms, 3),
+                "stats_achieved_gbs": round(count_positions * 32 / (stats_ms / 1e3) / 1e9, 1)}
+    if not args.no_gups:
+        slots = max(tinfo["capacity"], 1 << 29)         # >= 8 GiB of 16-B slots
+        nops = 1 << 30
+        g = {}
+        for mode, name in ((0, "load16"), (1, "load8_red"), (2, "cas_red")):
+            gms = ctx.gups(slots, nops, mode, reps=2)
+            g[name] = {"gops": round(nops / (gms / 1e3) / 1e9, 2), "ms": round(gms, 2)}
+        roofline["random_access"] = {
+            "table_gib": round(slots * 16 / 2 ** 30, 1), **g,
+            "count_frac_of_load8_red": round((count_positions / (count_ms / 1e3) / 1e9) / g["load8_red"]["gops"], 4),
+            "stats_frac_of_load16": round((count_positions / (stats_ms / 1e3) / 1e9) / g["load16"]["gops"], 4)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ns = min(args.cpu_sample_reads, nreads)
+        v, dt, kind, cores = cpu_reference_run(recs_host, read_len, ns)
+        cpu = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": kind, "seconds": round(dt, 2),
+               "sample": f"first {ns} reads of the same synthetic set: fastaToKmerCoverageStats --kmers_from_reads + "
+                         f"stats, --num_threads {cores} (the tool's own cap), host has {os.cpu_count()} cores"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u64 keys / u32 counts / f32 stats", "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * nbytes + offs_host.nbytes),
+                   "d2h_bytes_per_step": int(12 * nreads), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "table": {"capacity_slots": tinfo["capacity"], "distinct_kmers": tinfo["distinct"],
+                     "load": round(tinfo["distinct"] / tinfo["capacity"], 3)},
+           "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args, config, world, W):
+    """--impl reference: the reference's own CPU implementation of the step (count + coverage stats) on this box's
+    host cores; each step is a bounded sample of the workload.  No GPU, none of our kernels."""
+    read_len = args.read_len
+    ns = min(args.cpu_sample_reads, 2 * args.pairs)
+    # the sample is generated on the host with the test generator (same shape: reads from a weighted transcriptome)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synthdata
+    rng = np.random.default_rng(SEED)
+    txs = synthdata.transcriptome(rng, 2000)
+    reads = synthdata.reads_from(rng, txs, ns, read_len, err=0.005, n_rate=0.001)
+    reads = [r.ljust(read_len, b"N") for r in reads]
+    recs = np.frombuffer(b"".join(r + b"\n" for r in reads), dtype=np.uint8)
+    times = []
+    kind, cores = "reference", 6
+    for i in range(W + args.steps):
+        v, dt, kind, cores = cpu_reference_run(recs, read_len, ns)
+        if i >= W:
+            times.append(dt)
+    positions = 2 * ns * (read_len - K + 1)
+    total = sum(times)
+    value = positions * len(times) / total
+    sample = (f"{ns} synthetic {read_len} bp reads per step (bounded sample of the workload): "
+              f"fastaToKmerCoverageStats --kmers_from_reads + stats, --num_threads {cores}; host has {os.cpu_count()} cores")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": W, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64 keys / u32 counts / f32 stats", "data": "synthetic", "config": config,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

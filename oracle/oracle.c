@@ -344,6 +344,9 @@ static char rt_rc_char(char c) {
         default: return 0;
     }
 }
+/* exported for tests: the reference's entropy of one window */
+float orc_entropy(const char* s, int k) { return rt_entropy(s, k); }
+
 static int cmp_i32(const void* a, const void* b) {
     int x = *(const int*)a, y = *(const int*)b;
     return x < y ? -1 : x > y;

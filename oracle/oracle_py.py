@@ -47,6 +47,7 @@ def lib():
         L.orc_rt_size.restype = u64; L.orc_rt_size.argtypes = [vp]
         L.orc_rt_label.argtypes = [vp, vp, vp, u64, u32]
         L.orc_rt_assign.argtypes = [vp, vp, vp, u64, i32, C.c_float, vp, vp, vp]
+        L.orc_entropy.restype = C.c_float; L.orc_entropy.argtypes = [C.c_char_p, i32]
         _lib = L
     return _lib
 
@@ -101,6 +102,11 @@ def jf_count(recs, k=25, canonical=True, min_count=1):
     cnts = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_uint32)), shape=(max(n, 1),))[:n].copy()
     lib().orc_free(pk); lib().orc_free(pc)
     return keys, cnts
+
+
+def entropy(window):
+    w = window.encode() if isinstance(window, str) else window
+    return float(lib().orc_entropy(w, len(w)))
 
 
 def jf_histo(counts):

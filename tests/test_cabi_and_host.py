@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads and exports every symbol include/trinity_gpu.h declares; host-side logic (entropy
+table, reader restatements, formatting) without touching a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import trinityrnaseq_b200 as tg
+from trinityrnaseq_b200 import _lib
+from oracle import oracle_py as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "trinity_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libtrinity_gpu.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.tg_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _lib.lib().tg_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(tg.TrinityGpuError) as e:
+        tg.Context(0)
+    assert e.value.code == _lib.TG_ERR_NOGPU and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    """the product path must never import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "trinityrnaseq_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if any(part in ("build", "lib", "bin", "__pycache__") for part in dirpath.split(os.sep)):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "api.py" and "oracle" not in txt, (dirpath, f)
+
+
+def test_entropy_table_matches_reference_expression():
+    """tg_entropy_table (host side of R5) against the oracle's compute_entropy on an explicit window for EVERY count
+    tuple, forward slot order and reverse-complement slot order, at the default and at other thresholds"""
+    for thr in (1.5, 1.0, 1.9, 0.0):
+        ok = np.zeros(26 ** 3, np.uint8)
+        _lib.lib().tg_entropy_table(25, thr, ok.ctypes.data)
+        n = 0
+        for g in range(26):
+            for a in range(26 - g):
+                for t in range(26 - g - a):
+                    c = 25 - g - a - t
+                    e = orc.entropy("G" * g + "A" * a + "T" * t + "C" * c)
+                    assert bool(ok[(g * 26 + a) * 26 + t]) == (not (np.float32(e) < np.float32(thr))), (g, a, t, c, thr)
+                    n += 1
+        assert n == 3276
+
+
+def test_reader_restatements_edge_cases():
+    txt = b"junk before\n>a b\tc\nAC GT\nac\tgt\n\n>b\n>c\nNNNN\n>d\nACGT"
+    iw = orc.read_fasta_inchworm(txt)
+    assert [(a, s) for _, a, s in iw] == [("a", "ACGTACGT"), ("b", ""), ("c", "NNNN"), ("d", "ACGT")]
+    ds = orc.read_fasta_dnastream(txt)
+    # the line after a header is always sequence (even '>c'); the unterminated last record is dropped
+    assert ds == [(">a b\tc", "AC GTac\tgt"), (">b", ">cNNNN")]
+    assert orc.read_fasta_dnastream(b">x\nACGT\nAC") == [(">x", "ACGT")]        # later unterminated line is lost
+    assert orc.read_bundles(b">s_12 43 57\nacgtXacgt\n>s_13 1\nAC\nGT\n>s_14 2\nTTTT") == [
+        (">s_12_43_57", "ACGTXACGT"), (">s_13_1", "ACGT"), (">s_14_2", "")]
+    assert orc.format_read_name("> r name ") == ">_r_name_"
+
+
+def test_stats_line_format():
+    assert tg.format_stats_line("x/1", 67, np.float32(76.7308), np.float32(32.3844)) == "x/1\t67\t76.7308\t32.3844\tthread:0"
+    nan = np.array([0xFFC00000], np.uint32).view(np.float32)[0]
+    assert tg.format_stats_line("e", 1, np.float32(1), nan).split("\t")[3] == "-nan"
+    assert tg.format_stats_line("s", 0, np.float32(0), np.float32(-0.0)).split("\t")[3] == "-0"
+    assert tg.format_stats_line("b", 1234567, np.float32(1.33378e9), np.float32(2.30902e9)).split("\t")[2] == "1.33378e+09"
+
+
+def test_packing_roundtrip():
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        s = "".join("ACGT"[i] for i in rng.integers(0, 4, 25))
+        assert tg.packed_to_kmer(tg.kmer_to_packed(s), 25) == s
+    recs, offs = tg.records_from_sequences(["ACGT", "", "GG"])
+    assert recs.tobytes() == b"ACGT\n\nGG\n" and offs.tolist() == [0, 5, 6, 9]

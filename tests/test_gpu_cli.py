@@ -1,0 +1,157 @@
+"""GPU: the three drop-in executables against the committed outputs of the unmodified reference binaries
+(tests/golden/*.expected, produced with -t 1 / --num_threads 1 so that line order is deterministic) -- byte for byte."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import trinityrnaseq_b200 as tg
+from oracle import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+BIN = os.path.join(ROOT, "trinityrnaseq_b200", "bin")
+ENV = dict(os.environ, LC_ALL="C")
+
+
+def gold(name):
+    with open(os.path.join(GOLD, name), "rb") as f:
+        return f.read()
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, env=ENV, timeout=300, **kw)
+
+
+@pytest.mark.parametrize("tag,mode", [("", "DS"), ("", "SS"), ("_nonl", "DS"), ("_nonl", "SS")])
+def test_stats_kmers_from_reads(tag, mode):
+    fa = os.path.join(GOLD, f"reads{tag}.fa")
+    r = run([os.path.join(BIN, "fastaToKmerCoverageStats"), "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "25",
+             "--num_threads", "6", "--" + mode])
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == gold(f"stats{tag}_{mode}.expected")
+    assert b"STATS_GENERATION_TIME" in r.stderr
+
+
+def test_stats_variants():
+    fa = os.path.join(GOLD, "reads.fa")
+    exe = os.path.join(BIN, "fastaToKmerCoverageStats")
+    r = run([exe, "--reads", fa, "--kmers_from_reads", fa, "--capture_coverage_info"])
+    assert r.returncode == 0 and r.stdout == gold("stats_capture.expected")
+    r = run([exe, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "21"])
+    assert r.returncode == 0 and r.stdout == gold("stats_k21.expected")
+    r = run([exe, "--reads", fa, "--kmers", os.path.join(GOLD, "kmers_L2.fa"), "--kmer_size", "25", "--DS"])
+    assert r.returncode == 0 and r.stdout == gold("stats_kmers_L2.expected")
+    assert b"is not of length: 25" in r.stderr
+    # CLI errors (fastaToKmerCoverageStats.cpp:63-82): usage -> 1, k < 20 -> 2, unreadable file -> 1
+    assert run([exe, "--reads", fa]).returncode == 1
+    assert run([exe, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "19"]).returncode == 2
+    assert run([exe, "--reads", "/nonexistent.fa", "--kmers_from_reads", fa]).returncode == 1
+
+
+@pytest.mark.parametrize("tag,mode", [("", "ds"), ("", "strand"), ("_nonl", "ds"), ("_nonl", "strand")])
+def test_reads_to_transcripts(tmp_path, tag, mode):
+    out = tmp_path / "r2c.out"
+    cmd = [os.path.join(BIN, "ReadsToTranscripts"), "-i", os.path.join(GOLD, f"reads{tag}.fa"), "-f",
+           os.path.join(GOLD, "bundles.fa"), "-o", str(out), "-t", "8", "-max_mem_reads", "50000000", "-p", "0"]
+    if mode == "strand":
+        cmd.append("-strand")
+    r = run(cmd)
+    assert r.returncode == 0, r.stderr.decode()
+    assert out.read_bytes() == gold(f"r2t{tag}_{mode}.expected")
+    assert (tmp_path / "r2c.out.rcts.out").read_bytes() == gold(f"r2t{tag}_{mode}.expected.rcts.out")
+
+
+def test_reads_to_transcripts_chunks_and_cli(tmp_path):
+    out = tmp_path / "o"
+    exe = os.path.join(BIN, "ReadsToTranscripts")
+    r = run([exe, "-i", os.path.join(GOLD, "reads.fa"), "-f", os.path.join(GOLD, "bundles.fa"), "-o", str(out),
+             "-max_mem_reads", "100", "-p", "10"])
+    assert r.returncode == 0
+    assert out.read_bytes() == gold("r2t_p10_chunk100.expected")
+    assert (tmp_path / "o.rcts.out").read_bytes() == gold("r2t_p10_chunk100.expected.rcts.out")
+    assert run([exe, "-bogus", "1"]).returncode == 255          # exit(-1) on an unknown argument
+    assert run([exe, "-h"]).returncode == 255
+
+
+def test_jellyfish_count_dump_histo(tmp_path):
+    jf = os.path.join(BIN, "jellyfish")
+    fa = os.path.join(GOLD, "reads.fa")
+    v = run([jf, "--version"])
+    assert v.returncode == 0 and v.stdout.split()[1].startswith(b"2.")
+    # what jellyfish sees: FASTA records, line breaks inside a record do not break k-mers, blanks do
+    seqs = []
+    for line in gold("reads.fa").split(b"\n"):
+        if line.startswith(b">"):
+            seqs.append(b"")
+        elif seqs:
+            seqs[-1] += line
+    recs, _ = tg.records_from_sequences(seqs)
+    for canonical in (True, False):
+        db = tmp_path / f"mer_{int(canonical)}.jf"
+        cmd = [jf, "count", "-t", "4", "-m", "25", "-s", "100000000", "-o", str(db)] + (["--canonical"] if canonical else []) + [fa]
+        r = run(cmd)
+        assert r.returncode == 0, r.stderr.decode()
+        for L in (1, 2):
+            keys, cnts = orc.jf_count(recs, 25, canonical, L)
+            expect = "".join(">%d\n%s\n" % (c, tg.packed_to_kmer(k, 25)) for k, c in zip(keys, cnts)).encode()
+            d = run([jf, "dump", "-L", str(L), str(db)])
+            assert d.returncode == 0 and d.stdout == expect
+        keys, cnts = orc.jf_count(recs, 25, canonical, 1)
+        bins = orc.jf_histo(cnts)
+        expect = "".join("%d %d\n" % (c, bins[c]) for c in range(1, 10002) if bins[c]).encode()
+        h = run([jf, "histo", "-t", "4", "-o", str(tmp_path / "h.txt"), str(db)])
+        assert h.returncode == 0 and (tmp_path / "h.txt").read_bytes() == expect
+        c = run([jf, "dump", "-c", "-L", "3", str(db)])
+        k3, c3 = orc.jf_count(recs, 25, canonical, 3)
+        assert c.stdout == "".join("%s %d\n" % (tg.packed_to_kmer(k, 25), n) for k, n in zip(k3, c3)).encode()
+    assert run([jf, "count", "-m", "25", fa]).returncode != 0          # -s is required
+    assert run([jf, "dump", str(tmp_path / "missing.jf")]).returncode != 0
+
+
+def test_pipeline_dump_into_stats(tmp_path):
+    """The normalisation pipeline's hand-off (util/insilico_read_normalization.pl:617-846): jellyfish count --canonical
+    | dump -L 1 -> fastaToKmerCoverageStats --kmers must equal counting the reads directly, when no read has exactly
+    k bases (SURVEY §8c cross-check)."""
+    jf = os.path.join(BIN, "jellyfish")
+    stats = os.path.join(BIN, "fastaToKmerCoverageStats")
+    entries = orc.read_fasta_inchworm(gold("reads.fa"))
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(">%s\n%s\n" % (h, s) for h, _, s in entries if len(s) != 25))
+    assert run([jf, "count", "-t", "2", "-m", "25", "-s", "1000000", "--canonical", "-o", str(tmp_path / "m.jf"), str(fa)]).returncode == 0
+    d = run([jf, "dump", "-L", "1", str(tmp_path / "m.jf")])
+    (tmp_path / "k.fa").write_bytes(d.stdout)
+    a = run([stats, "--reads", str(fa), "--kmers", str(tmp_path / "k.fa"), "--kmer_size", "25", "--DS"])
+    b = run([stats, "--reads", str(fa), "--kmers_from_reads", str(fa), "--kmer_size", "25", "--DS"])
+    assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout and len(a.stdout) > 1000
+
+
+def test_against_reference_binaries_when_present(tmp_path):
+    """If the prebuilt reference binaries travelled with the snapshot, diff against them live on a fresh seeded input."""
+    ref_stats = os.path.join(orc.REF_DIR, "fastaToKmerCoverageStats")
+    ref_r2t = os.path.join(orc.REF_DIR, "ReadsToTranscripts")
+    if not (os.path.exists(ref_stats) and os.path.exists(ref_r2t)):
+        pytest.skip("oracle/_ref not present")
+    import synthdata
+    rng = np.random.default_rng(99)
+    txs = synthdata.transcriptome(rng, 80, mean_len=800, min_len=200, max_len=3000)
+    reads = synthdata.reads_from(rng, txs, 8000, 110, lower_rate=0.05, var_len=True)
+    fa = tmp_path / "reads.fa"
+    fa.write_bytes(synthdata.fasta_text([">q%d/1 x y" % i for i in range(len(reads))], reads))
+    bn, bs = synthdata.bundles_from(rng, txs)
+    bf = tmp_path / "bundles.fa"
+    bf.write_bytes(synthdata.fasta_text(bn, bs))
+    for mode in ("--DS", "--SS"):
+        a = run([ref_stats, "--reads", str(fa), "--kmers_from_reads", str(fa), "--num_threads", "1", mode])
+        b = run([os.path.join(BIN, "fastaToKmerCoverageStats"), "--reads", str(fa), "--kmers_from_reads", str(fa), mode])
+        assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout
+    for flags in ([], ["-strand"]):
+        oa, ob = tmp_path / "a.out", tmp_path / "b.out"
+        common = ["-i", str(fa), "-f", str(bf), "-max_mem_reads", "3000", "-p", "10"] + flags
+        assert run([ref_r2t, "-o", str(oa), "-t", "1"] + common).returncode == 0
+        assert run([os.path.join(BIN, "ReadsToTranscripts"), "-o", str(ob), "-t", "8"] + common).returncode == 0
+        assert oa.read_bytes() == ob.read_bytes() and len(oa.read_bytes()) > 10000
+        assert (tmp_path / "a.out.rcts.out").read_bytes() == (tmp_path / "b.out.rcts.out").read_bytes()

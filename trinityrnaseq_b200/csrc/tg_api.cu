@@ -367,8 +367,8 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
-    int rc;
-    if ((rc = tg_table_reserve(t, nbytes))) return rc;
+    // the caller sizes the table (tg_table_create / tg_table_reserve): a conservative per-byte bound would
+    // multiply the footprint.  An overflow raises the table's error flag -> TG_ERR_TABLE at tg_table_info.
     CU(launch_count_tiles((const uint8_t*)d_recs, nbytes, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
     c->launches++;
     return TG_OK;
@@ -609,8 +609,6 @@ int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const
     if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles_dev needs a TG_TABLE_LABEL table");
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
-    int rc;
-    if ((rc = tg_table_reserve(t, nbytes))) return rc;
     CU(launch_label_tiles((const uint8_t*)d_recs, nbytes, (const uint64_t*)d_offs, 0, nbundles, first_index, t->k,
                           t->view(), c->sm_count, c->stream[0]));
     c->launches++;

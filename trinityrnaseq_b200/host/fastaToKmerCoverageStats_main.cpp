@@ -1,0 +1,210 @@
+// fastaToKmerCoverageStats -- drop-in for Inchworm/bin/fastaToKmerCoverageStats (reference:
+// Inchworm/src/fastaToKmerCoverageStats.cpp).  Same argv, same stdout format, same exit codes; the k-mer table
+// and the per-read statistics run on the GPU through libtrinity_gpu.
+#include <math.h>
+#include <time.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fasta_io.hpp"
+#include "tg_loader.hpp"
+
+using namespace tgio;
+
+static const int MAX_THREADS = 6;   // kept only for the usage text / CLI compatibility
+
+// Inchworm ArgProcessor (Inchworm/src/argProcessor.cpp:5-23): every token starting with '-' is a flag and the
+// following token, whatever it is, is recorded as its value.
+struct Args {
+    std::map<std::string, std::string> val;
+    std::map<std::string, bool> set;
+    Args(int argc, char** argv) {
+        for (int i = 1; i < argc; i++)
+            if (argv[i][0] == '-') {
+                set[argv[i]] = true;
+                if (i != argc - 1) val[argv[i]] = argv[i + 1];
+            }
+    }
+    bool isSet(const char* a) const { return set.count(a) != 0; }
+    std::string str(const char* a) { return val[a]; }
+    int i(const char* a) { return atoi(val[a].c_str()); }
+};
+
+static void usage() {
+    fprintf(stderr,
+            "\n\nUsage: \n"
+            "  --reads  <str>             :fasta file containing target reads for kmer coverage stats\n"
+            "\n and source of kmers: \n"
+            "  --kmers  <str>             :fasta file containing kmers\n"
+            "      or \n"
+            "  --kmers_from_reads <str>   :fasta file containing reads as source of kmers\n"
+            "\n* optional:\n"
+            "  --kmer_size <int>          :default = 25\n"
+            "  --DS                             :double-stranded RNA-Seq mode (not strand-specific)\n"
+            "  --capture_coverage_info    :writes coverage info file.\n"
+            "  --monitor <int>            :verbose level for debugging\n"
+            "  --num_threads <int>        :number of threads\n"
+            "\n\n\n");
+}
+
+// iostream default float formatting (precision 6, %g); x86 default NaN carries the sign bit -> "-nan"
+static int fmt_float(char* out, float f) {
+    if (isnan(f)) return sprintf(out, signbit(f) ? "-nan" : "nan");
+    return sprintf(out, "%g", (double)f);
+}
+
+int main(int argc, char** argv) {
+    Args args(argc, argv);
+    if (args.isSet("--help") || !(args.isSet("--reads") && (args.isSet("--kmers") || args.isSet("--kmers_from_reads")))) {
+        usage();
+        return 1;
+    }
+    const std::string reads_file = args.str("--reads");
+    const bool is_DS = !args.isSet("--SS");           // "--DS" is accepted and ignored, like the reference (:75)
+    int K = 25;
+    if (args.isSet("--kmer_size")) {
+        K = args.i("--kmer_size");
+        if (K < 20) { fprintf(stderr, "Error, min kmer size is 20"); return 2; }
+    }
+    if (K > 32) { fprintf(stderr, "ERROR encountered: \n\nKmer length exceeds max of 32"); return 1; }
+    if (K > 31) { fprintf(stderr, "ERROR: kmer size 32 is not supported by the GPU k-mer table (max 31)\n"); return 1; }
+    const bool capture = args.isSet("--capture_coverage_info");
+
+    tg_ctx* ctx = tgh::open_device();
+    tg_table* table = nullptr;
+    std::string err;
+
+    // ---- load the k-mer table --------------------------------------------------------------------------
+    if (args.isSet("--kmers")) {
+        // populate_kmer_counter_from_kmers (:181-228): `>COUNT\nKMER` records; stop at the first record with an
+        // empty sequence; wrong-length k-mers are reported and skipped; count = atoi(header) as unsigned int
+        FileView fv;
+        if (!fv.open(args.str("--kmers"), &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
+        fprintf(stderr, "-reading Kmer occurrences...\n");
+        time_t start = time(NULL);
+        TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 32 + 1024, &table));
+        InchwormFastaReader rd(fv.data, fv.size);
+        std::vector<uint64_t> keys; std::vector<uint32_t> vals;
+        std::vector<char> seq;
+        const size_t FLUSH = 8u << 20;
+        keys.reserve(FLUSH); vals.reserve(FLUSH);
+        unsigned long parsed = 0;
+        const char* h; size_t hl;
+        for (;;) {
+            seq.clear();
+            if (!rd.next(&h, &hl, seq)) break;
+            if (seq.empty()) break;
+            parsed++;
+            if (seq.size() != (size_t)K) {
+                fprintf(stderr, "ERROR: kmer %.*s is not of length: %d\n", (int)seq.size(), seq.data(), K);
+                continue;
+            }
+            uint64_t key;
+            if (!tgh::pack_kmer(seq.data(), K, &key)) {
+                // kmer_to_intval throws on a non-GATC character (sequenceUtil.cpp:276-281) and the tool dies
+                fprintf(stderr, "\n\nerror, kmer contains nongatc: %.*s", K, seq.data());
+                return 1;
+            }
+            std::string hs(h, hl);
+            keys.push_back(key);
+            vals.push_back((uint32_t)atoi(hs.c_str()));
+            if (keys.size() == FLUSH) {
+                TGC(tg_table_load_pairs(table, keys.data(), vals.data(), keys.size(), is_DS));
+                keys.clear(); vals.clear();
+            }
+        }
+        if (!keys.empty()) TGC(tg_table_load_pairs(table, keys.data(), vals.data(), keys.size(), is_DS));
+        uint64_t cap = 0, distinct = 0;
+        TGC(tg_table_info(table, &cap, &distinct));
+        fprintf(stderr, "\n done parsing %lu Kmers, %llu added, taking %ld seconds.\n", parsed,
+                (unsigned long long)distinct, (long)(time(NULL) - start));
+    } else {
+        // populate_kmer_counter_from_reads (:230-293): reads shorter than K+1 are skipped entirely
+        FileView fv;
+        if (!fv.open(args.str("--kmers_from_reads"), &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
+        fprintf(stderr, "-storing Kmers...\n");
+        TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 4 + 1024, &table));
+        InchwormFastaReader rd(fv.data, fv.size);
+        RecordBatch rb;
+        std::vector<char> seq;
+        const char* h; size_t hl;
+        auto flush = [&]() {
+            if (rb.recs.empty()) return;
+            TGC(tg_count_reads(table, rb.recs.data(), rb.recs.size(), is_DS));
+            rb.clear();
+        };
+        while (true) {
+            seq.clear();
+            if (!rd.next(&h, &hl, seq)) break;
+            if (seq.size() < (size_t)K + 1) continue;
+            rb.recs.insert(rb.recs.end(), seq.begin(), seq.end());
+            rb.end_record();
+            if (rb.recs.size() > (256u << 20)) flush();
+        }
+        flush();
+    }
+
+    // ---- per-read statistics ----------------------------------------------------------------------------
+    FileView rv;
+    if (!rv.open(reads_file, &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
+    time_t start_time = time(NULL);
+    OutBuf out(1);
+    out.put("acc\tmedian_cov\tmean_cov\tstdev\ttid\n");
+    InchwormFastaReader rd(rv.data, rv.size);
+    RecordBatch rb;
+    std::vector<char> seq;
+    std::vector<uint32_t> median, per_kmer;
+    std::vector<float> mean, stdev;
+    bool negative = false;
+    auto flush = [&]() {
+        const size_t n = rb.count();
+        if (n == 0) return;
+        median.resize(n); mean.resize(n); stdev.resize(n);
+        if (capture) per_kmer.assign(rb.recs.size(), 0);
+        TGC(tg_cov_stats(table, rb.recs.data(), rb.offs.data(), n, is_DS, median.data(), mean.data(), stdev.data(),
+                         capture ? per_kmer.data() : nullptr));
+        char num[64];
+        for (size_t i = 0; i < n; i++) {
+            if (rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
+                fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)rb.seq_len(i), rb.seq(i), K);
+            out.put(rb.name(i), rb.name_len(i));
+            out.putc('\t'); out.put_uint(median[i]);
+            out.putc('\t'); out.put(num, (size_t)fmt_float(num, mean[i]));
+            out.putc('\t'); out.put(num, (size_t)fmt_float(num, stdev[i]));
+            out.put("\tthread:0", 9);
+            if (capture) {
+                out.putc('\t');
+                const size_t L = rb.seq_len(i);
+                const size_t nw = L >= (size_t)K ? L - K + 1 : 0;
+                for (size_t j = 0; j < nw; j++) {
+                    out.put_uint(per_kmer[rb.offs[i] + j]);
+                    if (j != nw - 1) out.putc(',');
+                }
+            }
+            out.putc('\n');
+            if (mean[i] < 0) negative = true;
+        }
+        rb.clear();
+    };
+    const char* h; size_t hl;
+    while (true) {
+        seq.clear();
+        if (!rd.next(&h, &hl, seq)) break;
+        if (seq.empty()) continue;                                       // :132-133
+        const char* acc; size_t al;
+        accession_of(h, hl, &acc, &al);
+        rb.recs.insert(rb.recs.end(), seq.begin(), seq.end());
+        rb.end_record();
+        rb.add_name(acc, al);
+        if (rb.recs.size() > (256u << 20)) flush();
+    }
+    flush();
+    if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }
+    if (negative) { fprintf(stderr, "ERROR, cannot have negative coverage!!\n"); return 1; }
+    fprintf(stderr, "STATS_GENERATION_TIME: %ld seconds.\n", (long)(time(NULL) - start_time));
+    tg_table_destroy(table);
+    tg_destroy(ctx);
+    return 0;
+}

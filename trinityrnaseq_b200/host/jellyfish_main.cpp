@@ -1,0 +1,296 @@
+// jellyfish -- drop-in for the `jellyfish count | dump | histo | --version` calls Trinity makes
+// (Trinity:2612-2632, 4065-4078; util/insilico_read_normalization.pl:617-643).  Jellyfish itself is a third-party
+// binary (gmarcais/Jellyfish 2.3.0, Docker/Dockerfile:179) that is not part of the reference tree; this tool
+// implements the same command lines and the same dump/histo text formats on top of libtrinity_gpu.
+// The .jf file is a private binary format (only our own dump/histo read it, and Trinity deletes it afterwards).
+#include <errno.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "fasta_io.hpp"
+#include "tg_loader.hpp"
+
+using namespace tgio;
+
+namespace {
+
+const char JF_MAGIC[8] = {'T', 'G', 'J', 'F', '0', '0', '1', '\n'};
+
+struct JfHeader {
+    char magic[8];
+    uint32_t k;
+    uint32_t canonical;
+    uint64_t n;
+    uint64_t histo[TG_HISTO_BINS];   // computed on the GPU at count time
+};
+
+[[noreturn]] void die_usage(const char* msg) {
+    fprintf(stderr, "jellyfish: %s\n", msg);
+    exit(1);
+}
+
+uint64_t parse_size(const std::string& s) {
+    // "100000000", "100M", "2G", "1e8"
+    char* end = nullptr;
+    double v = strtod(s.c_str(), &end);
+    if (end == s.c_str()) die_usage(("invalid size '" + s + "'").c_str());
+    switch (*end) {
+        case 'k': case 'K': v *= 1e3; break;
+        case 'm': case 'M': v *= 1e6; break;
+        case 'g': case 'G': v *= 1e9; break;
+        case 't': case 'T': v *= 1e12; break;
+        default: break;
+    }
+    return (uint64_t)v;
+}
+
+// getopt-free option scanner: supports "-m 25", "-m25", "--mer-len=25", "--mer-len 25"
+struct Opts {
+    std::vector<std::string> positional;
+    std::vector<std::pair<std::string, std::string>> kv;
+    bool has(const std::string& a, const std::string& b = "") const {
+        for (auto& p : kv) if (p.first == a || (!b.empty() && p.first == b)) return true;
+        return false;
+    }
+    std::string get(const std::string& a, const std::string& b, const std::string& def) const {
+        for (auto& p : kv) if (p.first == a || p.first == b) return p.second;
+        return def;
+    }
+};
+
+Opts scan(int argc, char** argv, int first, const std::string& short_with_val, const std::vector<std::string>& long_with_val) {
+    Opts o;
+    for (int i = first; i < argc; i++) {
+        std::string a = argv[i];
+        if (a.size() >= 2 && a[0] == '-' && a[1] == '-') {
+            size_t eq = a.find('=');
+            std::string name = eq == std::string::npos ? a : a.substr(0, eq);
+            bool takes = false;
+            for (auto& l : long_with_val) if (l == name) takes = true;
+            if (eq != std::string::npos) o.kv.push_back({name, a.substr(eq + 1)});
+            else if (takes && i + 1 < argc) o.kv.push_back({name, argv[++i]});
+            else o.kv.push_back({name, ""});
+        } else if (a.size() >= 2 && a[0] == '-') {
+            const char c = a[1];
+            if (short_with_val.find(c) != std::string::npos) {
+                if (a.size() > 2) o.kv.push_back({a.substr(0, 2), a.substr(2)});
+                else if (i + 1 < argc) o.kv.push_back({a, argv[++i]});
+                else die_usage(("option " + a + " needs a value").c_str());
+            } else {
+                for (size_t j = 1; j < a.size(); j++) o.kv.push_back({std::string("-") + a[j], ""});   // -Ct style clusters
+            }
+        } else {
+            o.positional.push_back(a);
+        }
+    }
+    return o;
+}
+
+// ---- sequence files -> record batches ----------------------------------------------------------------------
+// FASTA (multi-line allowed: line breaks inside a record do not break k-mers) and FASTQ (4-line records).
+void count_file(tg_table* table, const std::string& path, int canonical) {
+    FileView fv;
+    std::string err;
+    if (!fv.open(path, &err)) { fprintf(stderr, "jellyfish: %s\n", err.c_str()); exit(1); }
+    const char* p = fv.data; const char* end = fv.data + fv.size;
+    std::vector<char> recs;
+    const size_t FLUSH = 256u << 20;
+    recs.reserve(FLUSH + (64u << 20));
+    auto flush = [&]() {
+        if (recs.empty()) return;
+        TGC(tg_count_reads(table, recs.data(), recs.size(), canonical));
+        recs.clear();
+    };
+    while (p < end && (*p == '\n' || *p == '\r')) p++;
+    const bool fastq = p < end && *p == '@';
+    if (fastq) {
+        while (p < end) {
+            const char* nl = find_nl(p, end); p = nl < end ? nl + 1 : end;          // @name
+            if (p >= end) break;
+            nl = find_nl(p, end);
+            recs.insert(recs.end(), p, nl); recs.push_back('\n');                 // sequence
+            p = nl < end ? nl + 1 : end;
+            nl = find_nl(p, end); p = nl < end ? nl + 1 : end;                    // +
+            nl = find_nl(p, end); p = nl < end ? nl + 1 : end;                    // qualities
+            if (recs.size() > FLUSH) flush();
+        }
+    } else {
+        bool open = false;
+        while (p < end) {
+            const char* nl = find_nl(p, end);
+            if (*p == '>') {
+                if (open) recs.push_back('\n');
+                open = true;
+                if (recs.size() > FLUSH) flush();
+            } else if (open) {
+                const char* e = nl;
+                if (e > p && e[-1] == '\r') e--;
+                recs.insert(recs.end(), p, e);
+            }
+            p = nl < end ? nl + 1 : end;
+        }
+        if (open) recs.push_back('\n');
+    }
+    flush();
+}
+
+int cmd_count(int argc, char** argv) {
+    Opts o = scan(argc, argv, 2, "mstocpLUQrFd", {"--mer-len", "--size", "--threads", "--output", "--counter-len",
+                                                  "--out-counter-len", "--reprobes", "--lower-count", "--upper-count",
+                                                  "--Files", "--generator", "--shell", "--bf-size", "--bc", "--if",
+                                                  "--min-qual-char", "--quality-start", "--min-quality"});
+    if (!o.has("-m", "--mer-len")) die_usage("count: missing required option -m, --mer-len");
+    if (!o.has("-s", "--size")) die_usage("count: missing required option -s, --size");
+    const int k = atoi(o.get("-m", "--mer-len", "0").c_str());
+    if (k < 1 || k > 31) die_usage("count: mer length must be in 1..31 for the GPU k-mer table");
+    const uint64_t size_hint = parse_size(o.get("-s", "--size", "0"));
+    const std::string out_path = o.get("-o", "--output", "mer_counts.jf");
+    const int canonical = o.has("-C", "--canonical") ? 1 : 0;
+    std::vector<std::string> files = o.positional;
+    if (files.empty()) files.push_back("/dev/fd/0");
+
+    tg_ctx* ctx = tgh::open_device();
+    // -s is only an initial-size hint in jellyfish 2 (the hash grows); we additionally cap it by the input size so
+    // that thousands of tiny phase-2 invocations do not each grab gigabytes
+    uint64_t input_bytes = 0;
+    for (auto& f : files) { struct stat st; if (stat(f.c_str(), &st) == 0 && S_ISREG(st.st_mode)) input_bytes += (uint64_t)st.st_size; else input_bytes += size_hint; }
+    const uint64_t expected = std::min<uint64_t>(size_hint, input_bytes / 2 + 1024);
+    tg_table* table = nullptr;
+    TGC(tg_table_create(ctx, TG_TABLE_COUNT, k, expected, &table));
+    for (auto& f : files) count_file(table, f, canonical);
+
+    JfHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, JF_MAGIC, 8);
+    h.k = (uint32_t)k; h.canonical = (uint32_t)canonical;
+    TGC(tg_histo(table, h.histo));
+    uint64_t* keys = nullptr; uint32_t* counts = nullptr; uint64_t n = 0;
+    TGC(tg_table_export(table, 1, 0xFFFFFFFFu, /*sorted=*/1, canonical, &keys, &counts, &n));
+    h.n = n;
+    FILE* f = fopen(out_path.c_str(), "wb");
+    if (!f) { fprintf(stderr, "jellyfish: cannot open output file '%s': %s\n", out_path.c_str(), strerror(errno)); return 1; }
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    ok = ok && (n == 0 || fwrite(keys, 8, n, f) == n);
+    ok = ok && (n == 0 || fwrite(counts, 4, n, f) == n);
+    ok = (fclose(f) == 0) && ok;
+    tg_free(keys); tg_free(counts);
+    tg_table_destroy(table);
+    tg_destroy(ctx);
+    if (!ok) { fprintf(stderr, "jellyfish: write to '%s' failed\n", out_path.c_str()); unlink(out_path.c_str()); return 1; }
+    return 0;
+}
+
+struct JfFile {
+    FileView fv;
+    const JfHeader* h = nullptr;
+    const uint64_t* keys = nullptr;
+    const uint32_t* counts = nullptr;
+    void open(const std::string& path) {
+        std::string err;
+        if (!fv.open(path, &err)) { fprintf(stderr, "jellyfish: %s\n", err.c_str()); exit(1); }
+        if (fv.size < sizeof(JfHeader) || memcmp(fv.data, JF_MAGIC, 8) != 0) {
+            fprintf(stderr, "jellyfish: '%s' is not a k-mer database written by this jellyfish\n", path.c_str());
+            exit(1);
+        }
+        h = (const JfHeader*)fv.data;
+        if (fv.size < sizeof(JfHeader) + h->n * 12) { fprintf(stderr, "jellyfish: '%s' is truncated\n", path.c_str()); exit(1); }
+        keys = (const uint64_t*)(fv.data + sizeof(JfHeader));
+        counts = (const uint32_t*)(fv.data + sizeof(JfHeader) + h->n * 8);
+    }
+};
+
+int cmd_dump(int argc, char** argv) {
+    Opts o = scan(argc, argv, 2, "LUo", {"--lower-count", "--upper-count", "--output"});
+    if (o.positional.size() != 1) die_usage("dump: exactly one database argument expected");
+    const uint64_t lower = o.has("-L", "--lower-count") ? strtoull(o.get("-L", "--lower-count", "0").c_str(), nullptr, 10) : 0;
+    const uint64_t upper = o.has("-U", "--upper-count") ? strtoull(o.get("-U", "--upper-count", "0").c_str(), nullptr, 10) : ~0ull;
+    const bool column = o.has("-c", "--column"), tab = o.has("-t", "--tab");
+    JfFile jf;
+    jf.open(o.positional[0]);
+    int fd = 1;
+    if (o.has("-o", "--output")) {
+        fd = ::open(o.get("-o", "--output", "").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) { fprintf(stderr, "jellyfish: cannot open output file: %s\n", strerror(errno)); return 1; }
+    }
+    const int k = (int)jf.h->k;
+    {
+        OutBuf out(fd, 16u << 20);
+        char line[96];
+        for (uint64_t i = 0; i < jf.h->n; i++) {
+            const uint32_t c = jf.counts[i];
+            if (c < lower || c > upper) continue;
+            int n;
+            if (column) {                                       // "KMER COUNT"
+                tgh::unpack_kmer(jf.keys[i], k, line);
+                n = k;
+                line[n++] = tab ? '\t' : ' ';
+                n += sprintf(line + n, "%u\n", c);
+            } else {                                            // FASTA: ">COUNT\nKMER\n"
+                n = sprintf(line, ">%u\n", c);
+                tgh::unpack_kmer(jf.keys[i], k, line + n);
+                n += k;
+                line[n++] = '\n';
+            }
+            out.put(line, (size_t)n);
+        }
+        if (!out.flush()) { fprintf(stderr, "jellyfish: write failed: %s\n", strerror(errno)); return 1; }
+    }
+    if (fd != 1) ::close(fd);
+    return 0;
+}
+
+int cmd_histo(int argc, char** argv) {
+    Opts o = scan(argc, argv, 2, "lhito", {"--low", "--high", "--increment", "--threads", "--output"});
+    if (o.positional.size() != 1) die_usage("histo: exactly one database argument expected");
+    const uint64_t low = strtoull(o.get("-l", "--low", "1").c_str(), nullptr, 10);
+    const uint64_t high = strtoull(o.get("-h", "--high", "10000").c_str(), nullptr, 10);
+    const uint64_t inc = strtoull(o.get("-i", "--increment", "1").c_str(), nullptr, 10);
+    const bool full = o.has("-f", "--full");
+    if (inc == 0) die_usage("histo: increment must be positive");
+    if (high > 10000) die_usage("histo: --high above 10000 is not supported (bins are accumulated on the GPU up to 10000)");
+    JfFile jf;
+    jf.open(o.positional[0]);
+    // jellyfish 2 histo_main: base = low>0 ? (inc>=low ? 0 : low-inc) : 0; ceil = high+inc; bucket = (val-base)/inc,
+    // below base -> first bucket, above ceil -> last bucket; buckets printed as "base+i*inc count"
+    const uint64_t base = low > 0 ? (inc >= low ? 0 : low - inc) : 0;
+    const uint64_t ceil = high + inc;
+    const uint64_t nb = (ceil + inc - base) / inc;
+    std::vector<uint64_t> hist(nb, 0);
+    for (uint64_t c = 0; c < TG_HISTO_BINS; c++) {
+        const uint64_t m = jf.h->histo[c];
+        if (!m) continue;
+        const bool overflow = c == TG_HISTO_BINS - 1;     // every count > 10000
+        uint64_t b;
+        if (c < base) b = 0;
+        else if (overflow || c > ceil) b = nb - 1;
+        else b = (c - base) / inc;
+        if (b >= nb) b = nb - 1;
+        hist[b] += m;
+    }
+    FILE* f = stdout;
+    if (o.has("-o", "--output")) {
+        f = fopen(o.get("-o", "--output", "").c_str(), "w");
+        if (!f) { fprintf(stderr, "jellyfish: cannot open output file: %s\n", strerror(errno)); return 1; }
+    }
+    for (uint64_t i = 0; i < nb; i++)
+        if (hist[i] > 0 || full) fprintf(f, "%llu %llu\n", (unsigned long long)(base + i * inc), (unsigned long long)hist[i]);
+    if (f != stdout && fclose(f) != 0) { fprintf(stderr, "jellyfish: write failed\n"); return 1; }
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
+        printf("jellyfish 2.3.0\n");      // Trinity requires the second token to match /^2\./ (Trinity:4070-4074)
+        return 0;
+    }
+    if (argc < 2) die_usage("usage: jellyfish <count|dump|histo|--version> [options]");
+    const std::string cmd = argv[1];
+    if (cmd == "count") return cmd_count(argc, argv);
+    if (cmd == "dump") return cmd_dump(argc, argv);
+    if (cmd == "histo") return cmd_histo(argc, argv);
+    die_usage(("unknown subcommand '" + cmd + "' (supported: count, dump, histo)").c_str());
+}
