@@ -46,6 +46,11 @@ int tg_sync(tg_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
 uint64_t tg_launch_count(tg_ctx* ctx);
 
+/* tuning knobs (also read from the environment at tg_init: TG_COUNT_MODE, TG_BATCH_MB, TG_PART_MB, TG_LOG_GB,
+ * TG_REPLAY_PREFETCH): key = count_mode (auto|direct|log), batch_mb, batch_bytes, part_mb, part_bytes, log_gb,
+ * log_bytes, replay_prefetch (0|1).  None of them changes a result. */
+int tg_ctx_set(tg_ctx* ctx, const char* key, const char* value);
+
 void* tg_host_alloc(uint64_t bytes); /* pinned host memory */
 void tg_host_free(void* p);
 void tg_free(void* p); /* releases arrays returned by tg_table_export */
@@ -59,6 +64,20 @@ void tg_table_destroy(tg_table* t);
 int tg_table_reserve(tg_table* t, uint64_t additional_keys);
 int tg_table_info(tg_table* t, uint64_t* capacity_slots, uint64_t* distinct_keys);
 int tg_table_clear(tg_table* t);
+/* Geometry.  A table is `nparts` partitions of `slots_per_partition` slots; a k-mer lives in the partition its hash
+ * selects.  tg_table_create picks nparts so that one partition fits in L2.  A SHARD holds the contiguous partition
+ * range [part0, part0 + nlocal) of the global geometry -- the unit by which the table is split across GPUs
+ * (owner(k-mer) = partition / nlocal; prior art: MPIinchworm's `canonical k-mer % NUM_MPI_NODES`,
+ * Inchworm/src/mpi_deprecated/MPIinchworm.cpp:1236-1257).  The concatenation of all shards' slot arrays, in rank
+ * order, is bit-for-bit the full table (part0 = 0, nlocal = nparts). */
+int tg_table_create_sharded(tg_ctx* ctx, int kind, int k, uint64_t slots_per_partition, uint32_t nparts, uint32_t part0,
+                            uint32_t nlocal, tg_table** out);
+int tg_table_geometry(tg_table* t, uint64_t* slots_per_partition, uint32_t* nparts, uint32_t* part0, uint32_t* nlocal);
+int tg_table_resize(tg_table* t, uint64_t slots_per_partition);      /* rehash into a new partition size */
+/* raw slot array (16 B per slot) in HBM, for all-gathering shards into a full table, and the matching setter of
+ * the distinct-key counter of a table assembled that way */
+int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes);
+int tg_table_set_distinct(tg_table* t, uint64_t distinct);
 
 /* ---- stage J: jellyfish count / dump / histo ----------------------------------------------------------
  * tg_count_reads: `jellyfish count -m k [--canonical]` (Trinity:2612-2619) and
@@ -110,7 +129,19 @@ int tg_dev_records_alloc(tg_ctx* ctx, uint64_t nbytes, void** dptr); /* padded +
 int tg_dev_free(tg_ctx* ctx, void* dptr);
 int tg_memcpy_h2d(tg_ctx* ctx, void* dptr, const void* host, uint64_t bytes);
 int tg_memcpy_d2h(tg_ctx* ctx, void* host, const void* dptr, uint64_t bytes);
+int tg_memcpy_d2d(tg_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int tg_memset_dev(tg_ctx* ctx, void* dst, int value, uint64_t bytes);
 int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int canonical);
+/* Sharded counting, the two halves around the exchange (hash-sharded table across GPUs):
+ *   tg_count_partition_dev  every k-mer occurrence of the record buffer appended to bin part(k-mer) of a
+ *       caller-owned log: d_keys [nbins][cap] u64, d_cursor [nbins] u32 (zeroed by the caller).  nbins must equal
+ *       the table's global partition count, so bins [r*nlocal, (r+1)*nlocal) are exactly what rank r owns and
+ *       one equal-split all-to-all of d_keys / d_cursor routes every k-mer to its owner.  A bin overflow is
+ *       reported by the next tg_sync.
+ *   tg_table_replay_log_dev  inserts a received log [nsrc][nlocal][cap] (+ cursors [nsrc][nlocal]) into the shard. */
+int tg_count_partition_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
+                           uint32_t cap, void* d_keys, void* d_cursor);
+int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t cap);
 int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
                      void* d_median, void* d_mean, void* d_stdev);
 int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,

@@ -1,0 +1,140 @@
+"""Stand-in engine for the CPU (gloo) tests of trinityrnaseq_b200.sharded -- TEST INFRASTRUCTURE ONLY.
+
+`ShardedKmerCounter` drives an engine through a small interface (create_shard / new_log / partition / replay /
+shard_slots / full_table / ...).  The product engine is CUDA (`sharded.DeviceEngine`).  This stand-in computes the
+k-mers with the CPU oracle and keeps the shard in a dict, so that the host-side logic -- geometry, bin ownership,
+the equal-split all-to-all, the [src, lp, cap] receive layout, the all-gather of slot arrays, the reductions --
+runs on CPU tensors over gloo with world_size > 1.  It is never imported by the package.
+"""
+import numpy as np
+import torch
+
+from oracle import oracle_py as orc
+
+MASK64 = (1 << 64) - 1
+
+
+def _mix(x):
+    x &= MASK64
+    x ^= x >> 33; x = (x * 0xff51afd7ed558ccd) & MASK64
+    x ^= x >> 33; x = (x * 0xc4ceb9fe1a85ec53) & MASK64
+    x ^= x >> 33
+    return x
+
+
+def key_bin(key, nbins):
+    return ((_mix(int(key)) & 0xFFFFFFFF) * nbins) >> 32
+
+
+class StandinTable:
+    def __init__(self, k, canonical, subcap, nparts, part0, nlocal):
+        self.k, self.canonical = k, canonical
+        self.subcap, self.nparts, self.part0, self.nlocal = subcap, nparts, part0, nlocal
+        self.counts = {}
+
+    def add(self, key, n):
+        b = key_bin(key, self.nparts)
+        if not (self.part0 <= b < self.part0 + self.nlocal):
+            raise RuntimeError("k-mer routed to a shard that does not own its partition")
+        self.counts[key] = self.counts.get(key, 0) + n
+
+    # slot array: per partition the (key, count) pairs packed from its first slot, rest empty (key 0 = empty, so
+    # keys are stored +1)
+    def slots(self):
+        a = np.zeros((self.nlocal, self.subcap, 2), dtype=np.int64)
+        fill = [0] * self.nlocal
+        for key in sorted(self.counts):
+            p = key_bin(key, self.nparts) - self.part0
+            a[p, fill[p]] = (key + 1, self.counts[key])
+            fill[p] += 1
+        return a
+
+    def load_slots(self, a):
+        a = a.reshape(self.nlocal, self.subcap, 2)
+        self.counts = {}
+        for p in range(self.nlocal):
+            for key1, c in a[p]:
+                if key1:
+                    assert key_bin(int(key1) - 1, self.nparts) - self.part0 == p
+                    self.counts[int(key1) - 1] = int(c)
+
+    # what the tests compare
+    def dump(self, min_count=1):
+        ks = sorted(k for k, c in self.counts.items() if c >= min_count)
+        return np.array(ks, dtype=np.uint64), np.array([self.counts[k] for k in ks], dtype=np.uint32)
+
+    def size(self):
+        return len(self.counts)
+
+    def set_distinct(self, n):
+        assert n == len(self.counts)
+
+    def coverage_stats(self, recs, offs):
+        kc = orc.KmerCounter(self.k, self.canonical)
+        for key, c in self.counts.items():
+            kmer = "".join("ACGT"[(key >> (2 * (self.k - 1 - i))) & 3] for i in range(self.k))
+            kc.add_kmer(kmer, c)
+        return kc.coverage_stats(recs, offs)
+
+
+class StandinEngine:
+    def __init__(self, k, canonical):
+        self.k, self.canonical = k, canonical
+        self.table = None
+
+    def create_shard(self, subcap, nparts, part0, nlocal):
+        self.table = StandinTable(self.k, self.canonical, subcap, nparts, part0, nlocal)
+        return self.table
+
+    def new_log(self, nbins, cap):
+        return torch.zeros((nbins, cap), dtype=torch.int64), torch.zeros((nbins,), dtype=torch.int32)
+
+    def reset_log(self, cursor):
+        cursor.zero_()
+
+    def partition(self, recs, nbytes, keys, cursor):
+        nbins, cap = keys.shape
+        ok, oc = orc.jf_count(np.asarray(recs[:nbytes]), self.k, self.canonical, 1)
+        for key, c in zip(ok.tolist(), oc.tolist()):
+            b = key_bin(key, nbins)
+            for _ in range(c):                      # one log entry per occurrence, like the device log
+                pos = int(cursor[b])
+                assert pos < cap, "stand-in log bin overflow"
+                keys[b, pos] = key + 1
+                cursor[b] += 1
+
+    def replay(self, keys, cursor, nsrc):
+        lp = self.table.nlocal
+        keys = keys.reshape(nsrc, lp, -1)
+        cursor = cursor.reshape(nsrc, lp)
+        for s in range(nsrc):
+            for p in range(lp):
+                for e in keys[s, p, :int(cursor[s, p])].tolist():
+                    self.table.add(e - 1, 1)
+
+    def shard_slots(self):
+        return torch.from_numpy(self.table.slots().reshape(-1))
+
+    def full_table(self, subcap, nparts):
+        full = StandinTable(self.k, self.canonical, subcap, nparts, 0, nparts)
+        buf = torch.zeros(nparts * subcap * 2, dtype=torch.int64)
+        full._buf = buf
+        orig = full.set_distinct
+
+        def set_distinct(n, full=full, buf=buf, orig=orig):
+            full.load_slots(buf.numpy())
+            orig(n)
+        full.set_distinct = set_distinct
+        return full, buf
+
+    def local_distinct(self):
+        return self.table.size()
+
+    def local_histo(self):
+        return orc.jf_histo(self.table.dump()[1])
+
+    def local_dump(self, min_count=1):
+        return self.table.dump(min_count)
+
+    def scalar_tensor(self, values, dtype):
+        return torch.tensor(values, dtype=dtype)

@@ -1,0 +1,204 @@
+"""GPU parity of the partitioned (logged) count path and of the sharded table, against the CPU oracle (bit-exact).
+
+The logged path only pays on inputs far larger than a unit test, so the tests force it (count_mode=log) and shrink
+its blocking units (partition bytes, log bytes, batch bytes) until a few thousand reads exercise every branch:
+many partitions, several log flushes, bin overflow -> direct insert, growth by the sampled distinct estimate,
+homopolymer run folding, and the N-rank exchange emulated on one GPU by slicing the logs exactly as the
+equal-split all-to-all does.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import trinityrnaseq_b200 as tg
+import synthdata as synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ctx():
+    c = tg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def data():
+    rng = np.random.default_rng(424242)
+    txs = synth.transcriptome(rng, 50, mean_len=900, min_len=200, max_len=4000)
+    reads = synth.reads_from(rng, txs, 8000, 100, lower_rate=0.1, var_len=True)
+    reads += [b"A" * 120, b"T" * 77, b"A" * 25, b"ACACACACACACACACACACACACACACACACACACACAC" * 3, b"C" * 33 + b"N" + b"C" * 64,
+              b"", b"ACGT", b"N" * 60, txs[0][:25], txs[1][:26], b"acgtnACGTN" * 13] * 3
+    return txs, reads
+
+
+def _dev_records(ctx, recs):
+    d = ctx.dev_records_alloc(recs.nbytes)
+    ctx.h2d(d, recs)
+    return d
+
+
+@pytest.mark.parametrize("canonical", [True, False])
+@pytest.mark.parametrize("k", [25, 31, 17])
+def test_logged_count_host_path(ctx, oracle, data, canonical, k):
+    _, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, k, canonical, 1)
+    ctx.set("count_mode", "log")
+    ctx.set("part_bytes", 64 << 10)          # 4096-slot partitions -> dozens of partitions
+    ctx.set("batch_bytes", 100_000)          # several batches per call
+    ctx.set("log_bytes", 8 << 20)            # several flushes per call
+    with tg.KmerCounter(ctx, k, is_ds=canonical, expected_keys=2000) as kc:   # tiny hint: growth by estimate
+        kc.add_records(recs)
+        gk, gc = kc.dump()
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc, oc)
+        assert kc.size() == len(ok)
+        assert kc.geometry()[1] > 1
+        np.testing.assert_array_equal(kc.histo(), oracle.jf_histo(oc))
+        kc.add_records(recs)                 # second pass over a table that is now large enough
+        gk, gc = kc.dump()
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc, 2 * oc)
+
+
+@pytest.mark.parametrize("prefetch", [1, 0])
+def test_logged_count_device_path_and_stats(ctx, oracle, data, prefetch):
+    _, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, 25, True, 1)
+    ctx.set("count_mode", "log")
+    ctx.set("part_bytes", 128 << 10)
+    ctx.set("log_bytes", 8 << 20)            # the record buffer is replayed in several segments
+    ctx.set("replay_prefetch", prefetch)
+    d = _dev_records(ctx, recs)
+    with tg.KmerCounter(ctx, 25, is_ds=True, expected_keys=len(ok)) as kc:
+        kc.add_records_dev(d, recs.nbytes)
+        gk, gc = kc.dump()
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc, oc)
+        # statistics straight after a logged count (the log must be flushed before any lookup)
+        kc.clear()
+        kc.add_records_dev(d, recs.nbytes)
+        okc = oracle.KmerCounter(25, True)
+        for kmer, c in zip(ok, oc):
+            okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
+        om, omean, osd = okc.coverage_stats(recs, offs)
+        gm, gmean, gsd = kc.coverage_stats(recs, offs)
+        np.testing.assert_array_equal(gm, om)
+        np.testing.assert_array_equal(gmean.view(np.uint32), omean.view(np.uint32))
+        np.testing.assert_array_equal(gsd.view(np.uint32), osd.view(np.uint32))
+    ctx.dev_free(d)
+
+
+def test_logged_count_bin_overflow_counts_directly(ctx, oracle):
+    """two alternating k-mers repeated far beyond a bin's capacity: the overflow is counted straight into the table"""
+    rng = np.random.default_rng(3)
+    reads = [b"AC" * 60] * 4000 + [synth.ALPHA[rng.integers(0, 4, 90)].tobytes() for _ in range(500)]
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, 25, True, 1)
+    ctx.set("count_mode", "log")
+    ctx.set("part_bytes", 64 << 10)
+    d = _dev_records(ctx, recs)
+    with tg.KmerCounter(ctx, 25, is_ds=True, expected_keys=4 * len(ok)) as kc:
+        kc.add_records_dev(d, recs.nbytes)
+        gk, gc = kc.dump()
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc, oc)
+        assert gc.max() > 100_000
+    ctx.dev_free(d)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
+    """N ranks on one GPU: per-rank phase 1, the all-to-all done by slicing, per-rank phase 2, all-gather by copies"""
+    _, reads = data
+    k = 25
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, k, True, 1)
+    subcap, nparts, lp = tg.sharded.shard_geometry(world, len(ok) // world + 1000, part_bytes=64 << 10)
+    assert nparts == world * lp and lp > 1
+    shards = [tg.KmerCounter.sharded(ctx, k, True, subcap, nparts, r * lp, lp) for r in range(world)]
+    ranges = [tg.sharded.record_range(offs, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(reads)
+    assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+    nbytes_max = max(int(offs[r1] - offs[r0]) for r0, r1 in ranges)
+    cap = tg.sharded.log_capacity(nbytes_max, nparts)
+    logs, curs = [], []
+    for r, (r0, r1) in enumerate(ranges):
+        sub = recs[int(offs[r0]):int(offs[r1])]
+        d = _dev_records(ctx, sub)
+        keys = ctx.dev_alloc(nparts * cap * 8)
+        cur = ctx.dev_alloc(nparts * 4)
+        ctx.memset(cur, 0, nparts * 4)
+        shards[r].partition_dev(d, sub.nbytes, nparts, cap, keys, cur)
+        ctx.sync()
+        ctx.dev_free(d)
+        logs.append(keys)
+        curs.append(cur)
+    for dst in range(world):
+        rkeys = ctx.dev_alloc(nparts * cap * 8)       # [world][lp][cap]
+        rcur = ctx.dev_alloc(nparts * 4)
+        for src in range(world):
+            ctx.d2d(rkeys, logs[src], lp * cap * 8, dst_off=src * lp * cap * 8, src_off=dst * lp * cap * 8)
+            ctx.d2d(rcur, curs[src], lp * 4, dst_off=src * lp * 4, src_off=dst * lp * 4)
+        shards[dst].replay_log_dev(rkeys, rcur, world, cap)
+        ctx.sync()
+        ctx.dev_free(rkeys)
+        ctx.dev_free(rcur)
+    assert sum(s.size() for s in shards) == len(ok)
+    # every rank's dump is its part of the global dump
+    parts = [s.dump() for s in shards]
+    allk = np.concatenate([p[0] for p in parts])
+    allc = np.concatenate([p[1] for p in parts])
+    order = np.argsort(allk, kind="stable")
+    np.testing.assert_array_equal(allk[order], ok)
+    np.testing.assert_array_equal(allc[order], oc)
+    # all-gather: concatenated shard slot arrays == the full table
+    full = tg.KmerCounter.sharded(ctx, k, True, subcap, nparts, 0, nparts)
+    fp, fbytes = full.slots_dev()
+    off = 0
+    for s in shards:
+        sp, sb = s.slots_dev()
+        ctx.d2d(fp, sp, sb, dst_off=off)
+        off += sb
+    assert off == fbytes
+    full.set_distinct(len(ok))
+    gk, gc = full.dump()
+    np.testing.assert_array_equal(gk, ok)
+    np.testing.assert_array_equal(gc, oc)
+    okc = oracle.KmerCounter(k, True)
+    for kmer, c in zip(ok, oc):
+        okc.add_kmer(tg.packed_to_kmer(kmer, k), int(c))
+    om, omean, osd = okc.coverage_stats(recs, offs)
+    gm, gmean, gsd = full.coverage_stats(recs, offs)
+    np.testing.assert_array_equal(gm, om)
+    np.testing.assert_array_equal(gsd.view(np.uint32), osd.view(np.uint32))
+    # a k-mer routed to the wrong shard is an error, not a silent miss
+    with pytest.raises(tg.TrinityGpuError):
+        shards[0].add_records(recs)
+        shards[0].size()
+    for t in shards + [full]:
+        t.close()
+    for p in logs + curs:
+        ctx.dev_free(p)
+
+
+def test_partition_log_overflow_is_reported(ctx, data):
+    _, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    d = _dev_records(ctx, recs)
+    nbins, cap = 8, 64                                  # far too small
+    keys = ctx.dev_alloc(nbins * cap * 8)
+    cur = ctx.dev_alloc(nbins * 4)
+    ctx.memset(cur, 0, nbins * 4)
+    with tg.KmerCounter(ctx, 25) as kc:
+        kc.partition_dev(d, recs.nbytes, nbins, cap, keys, cur)
+        with pytest.raises(tg.TrinityGpuError) as e:
+            ctx.sync()
+        assert "overflow" in str(e.value)
+    ctx.sync()                                          # the flag is cleared once reported
+    for p in (d, keys, cur):
+        ctx.dev_free(p)

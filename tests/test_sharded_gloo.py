@@ -1,0 +1,113 @@
+"""CPU, world_size 2 and 3 over gloo: the host-side logic of the hash-sharded table (trinityrnaseq_b200.sharded) --
+geometry, read sharding by offset, bin ownership, the equal-split all-to-all and its receive layout, the all-gather
+into a full replica, the reductions -- driven through a stand-in engine (tests/standin_engine.py; the product
+engine is CUDA and is covered by tests/test_gpu_partitioned.py and the multi-GPU bench)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import synthdata as synth
+from trinityrnaseq_b200 import sharded
+from trinityrnaseq_b200.api import records_from_sequences
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _make_reads():
+    rng = np.random.default_rng(77)
+    txs = synth.transcriptome(rng, 12, mean_len=500, min_len=150, max_len=1200)
+    reads = synth.reads_from(rng, txs, 700, 80, var_len=True)
+    reads += [b"A" * 60, b"", b"ACGTN" * 12, txs[0][:25]]
+    return reads
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import oracle_py as orc
+    import standin_engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        k = 25
+        reads = _make_reads()
+        recs, offs = records_from_sequences(reads)
+        ok, oc = orc.jf_count(recs, k, True, 1)
+        r0, r1 = sharded.record_range(offs, rank, world)
+        mine = recs[int(offs[r0]):int(offs[r1])]
+        eng = standin_engine.StandinEngine(k, True)
+        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=len(ok) // world + 64, part_bytes=8 << 10)
+        assert sc.nparts == world * sc.lp and sc.lp >= 2
+        assert sc.table.part0 == rank * sc.lp and sc.table.nlocal == sc.lp
+        sc.add_records_dev(torch.from_numpy(mine.copy()) if len(mine) else torch.zeros(0, dtype=torch.uint8), len(mine))
+        assert sc.size() == len(ok)
+        np.testing.assert_array_equal(sc.histo(), orc.jf_histo(oc))
+        lk, lc = sc.dump_local()
+        # every local key belongs to this rank, and the union over ranks is the global dump
+        assert all(sc.owner_of_bin(standin_engine.key_bin(int(x), sc.nparts)) == rank for x in lk)
+        np.save(os.path.join(out_dir, f"k{rank}.npy"), lk)
+        np.save(os.path.join(out_dir, f"c{rank}.npy"), lc)
+        # second batch: counts double, the log buffers are reused
+        sc.add_records_dev(torch.from_numpy(mine.copy()) if len(mine) else torch.zeros(0, dtype=torch.uint8), len(mine))
+        full = sc.replicate()
+        fk, fc = full.dump()
+        np.testing.assert_array_equal(fk, ok)
+        np.testing.assert_array_equal(fc, 2 * oc)
+        # queries on the replica are purely local: every rank gets the single-table answer for its own reads
+        okc = orc.KmerCounter(k, True)
+        okc.add_records(recs, offs)
+        if r1 > r0:
+            sub_offs = offs[r0:r1 + 1] - offs[r0]
+            gm, gmean, gsd = full.coverage_stats(mine, sub_offs)
+            om, omean, osd = okc.coverage_stats(recs, offs)
+            # the oracle table holds single counts; the replica doubled them
+            okc2 = orc.KmerCounter(k, True)
+            for key, c in zip(ok.tolist(), oc.tolist()):
+                okc2.add_kmer("".join("ACGT"[(key >> (2 * (k - 1 - i))) & 3] for i in range(k)), 2 * c)
+            om, omean, osd = okc2.coverage_stats(recs, offs)
+            np.testing.assert_array_equal(gm, om[r0:r1])
+            np.testing.assert_array_equal(gsd.view(np.uint32), osd[r0:r1].view(np.uint32))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_counter_over_gloo(world, tmp_path):
+    port = 29500 + (os.getpid() % 400) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from oracle import oracle_py as orc
+    recs, offs = records_from_sequences(_make_reads())
+    ok, oc = orc.jf_count(recs, 25, True, 1)
+    ks = np.concatenate([np.load(tmp_path / f"k{r}.npy") for r in range(world)])
+    cs = np.concatenate([np.load(tmp_path / f"c{r}.npy") for r in range(world)])
+    order = np.argsort(ks, kind="stable")
+    np.testing.assert_array_equal(ks[order], ok)
+    np.testing.assert_array_equal(cs[order], oc)
+
+
+def test_record_range_partitions_every_record_once():
+    rng = np.random.default_rng(1)
+    lens = rng.integers(0, 200, 1000)
+    offs = np.zeros(1001, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens + 1)
+    for world in (1, 2, 3, 8):
+        rr = [sharded.record_range(offs, r, world) for r in range(world)]
+        assert rr[0][0] == 0 and rr[-1][1] == 1000
+        assert all(rr[i][1] == rr[i + 1][0] for i in range(world - 1))
+        sizes = [int(offs[b] - offs[a]) for a, b in rr]
+        assert max(sizes) - min(sizes) <= 2 * 201
+
+
+def test_shard_geometry():
+    for world in (1, 2, 4, 8):
+        subcap, nparts, lp = sharded.shard_geometry(world, 150_000_000)
+        assert nparts == world * lp and nparts <= sharded.MAX_BINS
+        assert subcap * lp >= 150_000_000 / sharded.TARGET_LOAD
+        assert subcap * 16 <= (32 << 20) or nparts * 2 > sharded.MAX_BINS

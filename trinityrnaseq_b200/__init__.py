@@ -6,3 +6,4 @@ libtrinity_gpu.so (CUDA, sm_100a) plus the drop-in executables in trinityrnaseq_
 from .api import (Context, KmerCounter, BundleKmerTable, records_from_sequences, format_stats_line,  # noqa: F401
                   packed_to_kmer, kmer_to_packed)
 from ._lib import TrinityGpuError  # noqa: F401
+from . import sharded  # noqa: F401

@@ -25,6 +25,7 @@ SIGNATURES = {
     "tg_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_u64), C.POINTER(_u64)]),
     "tg_sync": (_i32, [_vp]),
     "tg_launch_count": (_u64, [_vp]),
+    "tg_ctx_set": (_i32, [_vp, _cp, _cp]),
     "tg_host_alloc": (_vp, [_u64]),
     "tg_host_free": (None, [_vp]),
     "tg_free": (None, [_vp]),
@@ -33,6 +34,11 @@ SIGNATURES = {
     "tg_table_reserve": (_i32, [_vp, _u64]),
     "tg_table_info": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "tg_table_clear": (_i32, [_vp]),
+    "tg_table_create_sharded": (_i32, [_vp, _i32, _i32, _u64, _u32, _u32, _u32, _pp]),
+    "tg_table_geometry": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "tg_table_resize": (_i32, [_vp, _u64]),
+    "tg_table_slots_dev": (_i32, [_vp, _pp, C.POINTER(_u64)]),
+    "tg_table_set_distinct": (_i32, [_vp, _u64]),
     "tg_count_reads": (_i32, [_vp, _vp, _u64, _i32]),
     "tg_table_load_pairs": (_i32, [_vp, _vp, _vp, _u64, _i32]),
     "tg_table_export": (_i32, [_vp, _u32, _u32, _i32, _i32, _pp, _pp, C.POINTER(_u64)]),
@@ -46,7 +52,11 @@ SIGNATURES = {
     "tg_dev_free": (_i32, [_vp, _vp]),
     "tg_memcpy_h2d": (_i32, [_vp, _vp, _vp, _u64]),
     "tg_memcpy_d2h": (_i32, [_vp, _vp, _vp, _u64]),
+    "tg_memcpy_d2d": (_i32, [_vp, _vp, _vp, _u64]),
+    "tg_memset_dev": (_i32, [_vp, _vp, _i32, _u64]),
     "tg_count_reads_dev": (_i32, [_vp, _vp, _u64, _i32]),
+    "tg_count_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp]),
+    "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _u32, _u32]),
     "tg_cov_stats_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),
     "tg_label_bundles_dev": (_i32, [_vp, _vp, _u64, _vp, _u64, _u32]),
     "tg_assign_reads_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),

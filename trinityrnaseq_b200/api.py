@@ -53,6 +53,10 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def _addr(p):
+    return p.value if isinstance(p, C.c_void_p) else int(p)
+
+
 def _as_u8(recs):
     if isinstance(recs, (bytes, bytearray)):
         recs = np.frombuffer(recs, dtype=np.uint8)
@@ -89,6 +93,10 @@ class Context:
     def launch_count(self):
         return int(_lib.lib().tg_launch_count(self._h))
 
+    def set(self, key, value):
+        """tuning knob (tg_ctx_set): count_mode, batch_bytes, part_bytes, log_bytes, replay_prefetch, ..."""
+        check(_lib.lib().tg_ctx_set(self._h, str(key).encode(), str(value).encode()))
+
     # -- raw device memory (bench / tests) ------------------------------------------------------------
     def dev_alloc(self, nbytes):
         p = C.c_void_p()
@@ -115,6 +123,12 @@ class Context:
         src = C.c_void_p(dptr.value + offset)
         check(_lib.lib().tg_memcpy_d2h(self._h, _ptr(out), src, out.nbytes))
         return out
+
+    def d2d(self, dst, src, nbytes, dst_off=0, src_off=0):
+        check(_lib.lib().tg_memcpy_d2d(self._h, C.c_void_p(_addr(dst) + dst_off), C.c_void_p(_addr(src) + src_off), nbytes))
+
+    def memset(self, dst, value, nbytes):
+        check(_lib.lib().tg_memset_dev(self._h, dst, value, nbytes))
 
     def pinned(self, shape, dtype):
         """numpy array backed by pinned host memory (tg_host_alloc); keep the returned owner alive."""
@@ -169,10 +183,32 @@ class _PinnedOwner:
 class _Table:
     KIND = _lib.TG_TABLE_COUNT
 
-    def __init__(self, ctx, k=25, expected_keys=1 << 20):
+    def __init__(self, ctx, k=25, expected_keys=1 << 20, geometry=None):
         self.ctx, self.k = ctx, k
         self._h = C.c_void_p()
-        check(_lib.lib().tg_table_create(ctx._h, self.KIND, k, expected_keys, C.byref(self._h)))
+        if geometry is None:
+            check(_lib.lib().tg_table_create(ctx._h, self.KIND, k, expected_keys, C.byref(self._h)))
+        else:
+            subcap, nparts, part0, nlocal = geometry
+            check(_lib.lib().tg_table_create_sharded(ctx._h, self.KIND, k, subcap, nparts, part0, nlocal,
+                                                     C.byref(self._h)))
+
+    def geometry(self):
+        """(slots_per_partition, nparts, part0, nlocal) -- see tg_table_create_sharded"""
+        sc, n, p0, nl = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(_lib.lib().tg_table_geometry(self._h, C.byref(sc), C.byref(n), C.byref(p0), C.byref(nl)))
+        return sc.value, n.value, p0.value, nl.value
+
+    def resize(self, slots_per_partition):
+        check(_lib.lib().tg_table_resize(self._h, slots_per_partition))
+
+    def slots_dev(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().tg_table_slots_dev(self._h, C.byref(p), C.byref(n)))
+        return p, n.value
+
+    def set_distinct(self, n):
+        check(_lib.lib().tg_table_set_distinct(self._h, int(n)))
 
     def close(self):
         if self._h:
@@ -204,9 +240,24 @@ class KmerCounter(_Table):
     """k-mer -> count table.  is_ds mirrors KmerCounter(kmer_length, is_ds) (KmerCounter.cpp:13-22)."""
     KIND = _lib.TG_TABLE_COUNT
 
-    def __init__(self, ctx, k=25, is_ds=True, expected_keys=1 << 20):
-        super().__init__(ctx, k, expected_keys)
+    def __init__(self, ctx, k=25, is_ds=True, expected_keys=1 << 20, geometry=None):
+        super().__init__(ctx, k, expected_keys, geometry)
         self.is_ds = bool(is_ds)
+
+    @classmethod
+    def sharded(cls, ctx, k, is_ds, slots_per_partition, nparts, part0, nlocal):
+        """the shard holding partitions [part0, part0+nlocal) of a table of nparts partitions"""
+        return cls(ctx, k, is_ds, geometry=(slots_per_partition, nparts, part0, nlocal))
+
+    def partition_dev(self, d_recs, nbytes, nbins, cap, d_keys, d_cursor, canonical=None):
+        """phase 1 of the sharded count: k-mer occurrences -> caller-owned log bins (tg_count_partition_dev)"""
+        can = self.is_ds if canonical is None else canonical
+        check(_lib.lib().tg_count_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(can), nbins, cap, d_keys,
+                                                d_cursor))
+
+    def replay_log_dev(self, d_keys, d_cursor, nsrc, cap):
+        """phase 2: received log [nsrc][nlocal][cap] -> this shard (tg_table_replay_log_dev)"""
+        check(_lib.lib().tg_table_replay_log_dev(self._h, d_keys, d_cursor, nsrc, cap))
 
     def add_records(self, recs, canonical=None):
         """jellyfish count / KmerCounter::add_sequence over a record buffer."""

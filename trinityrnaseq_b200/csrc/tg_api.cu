@@ -72,6 +72,21 @@ struct tg_ctx {
     DevBuf lut;
     unsigned int* d_long_hdr[2] = {nullptr, nullptr};   // {count, max_win}
     unsigned int* h_long_hdr = nullptr;                 // pinned, 2 x 2
+    int* d_error = nullptr;                             // raised by table-less log appends (tg_count_partition_dev)
+    size_t part_bytes = 32ull << 20;                    // target bytes of one table partition (L2-resident unit)
+    size_t log_max_bytes = 24ull << 30;                 // most HBM the k-mer log of one table may take
+    int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
+    int replay_prefetch = 1;
+};
+
+// k-mer log of a count table (partitioned count path)
+struct KeyLog {
+    unsigned long long* keys = nullptr;
+    unsigned int* cursor = nullptr;
+    unsigned long long* chunk_start = nullptr;
+    unsigned nbins = 0, cap = 0;
+    uint64_t pending_ub = 0;          // host-side upper bound on entries appended since the last replay
+    uint64_t total_entries() const { return (uint64_t)nbins * cap; }
 };
 
 struct tg_table {
@@ -79,12 +94,31 @@ struct tg_table {
     int kind = TG_TABLE_COUNT;
     int k = 25;
     Slot* slots = nullptr;
-    uint64_t cap = 0;
+    Geo g{0, 1, 0, 1};
+    uint64_t cap = 0;                          // slots held here = g.nlocal * g.subcap
     unsigned long long* d_claimed = nullptr;   // [0] = distinct keys
     int* d_error = nullptr;
     uint64_t distinct_ub = 0;   // host-side upper bound on distinct keys (refreshed from the device at syncs)
-    TableView view() const { return TableView{slots, cap, d_claimed, d_error}; }
+    KeyLog log;
+    bool sharded() const { return g.nlocal != g.nparts; }
+    TableView view() const { return TableView{slots, g, d_claimed, d_error}; }
 };
+
+constexpr unsigned LOG_BASE_BINS = 512;
+
+// partitions for a full table of `slots` slots: a power of two up to 512, beyond that multiples of 512, so that
+// the log's bins (512 or the partition count) always nest with the partitions
+static Geo pick_geo(uint64_t slots, size_t part_bytes) {
+    const uint64_t bytes = slots * sizeof(Slot);
+    uint64_t np = 1;
+    while (np < LOG_BASE_BINS && bytes / np > part_bytes) np <<= 1;
+    if (bytes / np > part_bytes) np = LOG_BASE_BINS * ((bytes + LOG_BASE_BINS * part_bytes - 1) / (LOG_BASE_BINS * part_bytes));
+    if (np > LOG_MAX_BINS) np = LOG_MAX_BINS;
+    Geo g;
+    g.nparts = (unsigned)np; g.part0 = 0; g.nlocal = (unsigned)np;
+    g.subcap = (slots + np - 1) / np;
+    return g;
+}
 
 static int bind(tg_ctx* c) {
     CU(cudaSetDevice(c->device));
@@ -103,7 +137,9 @@ static int table_refresh(tg_table* t) {   // after a sync: read back distinct co
     CU(cudaMemcpy(&n, t->d_claimed, sizeof n, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&err, t->d_error, sizeof err, cudaMemcpyDeviceToHost));
     t->distinct_ub = n;
-    if (err) return fail(TG_ERR_TABLE, "k-mer table overflow (capacity %llu slots)", (unsigned long long)t->cap);
+    if (err == 2) return fail(TG_ERR_TABLE, "a k-mer was routed to a table shard that does not own its partition");
+    if (err) return fail(TG_ERR_TABLE, "k-mer table overflow (capacity %llu slots in %u partitions)",
+                         (unsigned long long)t->cap, t->g.nlocal);
     return TG_OK;
 }
 
@@ -158,10 +194,25 @@ int tg_init(int device, tg_ctx** out) {
     CU(cudaEventCreate(&c->t0));
     CU(cudaEventCreate(&c->t1));
     CU(cudaMallocHost(&c->h_long_hdr, 4 * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_error, sizeof(int)));
+    CU(cudaMemset(c->d_error, 0, sizeof(int)));
     if (const char* mb = getenv("TG_BATCH_MB")) {
         long v = atol(mb);
         if (v >= 1 && v <= 4096) c->batch_bytes = (size_t)v << 20;
     }
+    if (const char* mb = getenv("TG_PART_MB")) {          // bytes of one table partition (L2 blocking unit)
+        long v = atol(mb);
+        if (v >= 1 && v <= 1024) c->part_bytes = (size_t)v << 20;
+    }
+    if (const char* gb = getenv("TG_LOG_GB")) {           // HBM budget of the k-mer log
+        long v = atol(gb);
+        if (v >= 1 && v <= 160) c->log_max_bytes = (size_t)v << 30;
+    }
+    if (const char* m = getenv("TG_COUNT_MODE")) {        // auto | direct | log
+        if (!strcmp(m, "direct")) c->count_mode = 1;
+        else if (!strcmp(m, "log")) c->count_mode = 2;
+    }
+    if (const char* m = getenv("TG_REPLAY_PREFETCH")) c->replay_prefetch = atoi(m) != 0;
     *out = c;
     return TG_OK;
 }
@@ -178,6 +229,7 @@ void tg_destroy(tg_ctx* c) {
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
     c->scratch.release(); c->lut.release();
+    if (c->d_error) cudaFree(c->d_error);
     if (c->h_long_hdr) cudaFreeHost(c->h_long_hdr);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
@@ -198,10 +250,52 @@ int tg_device_info(tg_ctx* c, int* sm_count, uint64_t* free_bytes, uint64_t* tot
 int tg_sync(tg_ctx* c) {
     if (!c) return fail(TG_ERR_ARG, "null ctx");
     if (bind(c)) return TG_ERR_CUDA;
-    return sync_all(c);
+    int rc = sync_all(c);
+    if (rc) return rc;
+    int err = 0;
+    CU(cudaMemcpy(&err, c->d_error, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) {
+        CU(cudaMemset(c->d_error, 0, sizeof(int)));
+        return fail(TG_ERR_TABLE, "a k-mer log bin overflowed (tg_count_partition_dev): raise the per-bin capacity");
+    }
+    return TG_OK;
 }
 
 uint64_t tg_launch_count(tg_ctx* c) { return c ? c->launches : 0; }
+
+int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
+    if (!c || !key || !value) return fail(TG_ERR_ARG, "tg_ctx_set: null argument");
+    const long v = atol(value);
+    if (!strcmp(key, "count_mode")) {
+        if (!strcmp(value, "auto")) c->count_mode = 0;
+        else if (!strcmp(value, "direct")) c->count_mode = 1;
+        else if (!strcmp(value, "log")) c->count_mode = 2;
+        else return fail(TG_ERR_ARG, "count_mode must be auto, direct or log");
+    } else if (!strcmp(key, "batch_mb")) {
+        if (v < 1 || v > 4096) return fail(TG_ERR_ARG, "batch_mb out of range");
+        c->batch_bytes = (size_t)v << 20;
+    } else if (!strcmp(key, "batch_bytes")) {
+        if (v < 64) return fail(TG_ERR_ARG, "batch_bytes out of range");
+        c->batch_bytes = (size_t)v;
+    } else if (!strcmp(key, "part_mb")) {
+        if (v < 1 || v > 1024) return fail(TG_ERR_ARG, "part_mb out of range");
+        c->part_bytes = (size_t)v << 20;
+    } else if (!strcmp(key, "part_bytes")) {
+        if (v < 256) return fail(TG_ERR_ARG, "part_bytes out of range");
+        c->part_bytes = (size_t)v;
+    } else if (!strcmp(key, "log_gb")) {
+        if (v < 1 || v > 160) return fail(TG_ERR_ARG, "log_gb out of range");
+        c->log_max_bytes = (size_t)v << 30;
+    } else if (!strcmp(key, "log_bytes")) {
+        if (v < 4096) return fail(TG_ERR_ARG, "log_bytes out of range");
+        c->log_max_bytes = (size_t)v;
+    } else if (!strcmp(key, "replay_prefetch")) {
+        c->replay_prefetch = v != 0;
+    } else {
+        return fail(TG_ERR_ARG, "tg_ctx_set: unknown option '%s'", key);
+    }
+    return TG_OK;
+}
 
 void* tg_host_alloc(uint64_t bytes) {
     void* p = nullptr;
@@ -218,18 +312,12 @@ void tg_free(void* p) { free(p); }
 // ---------------------------------------------------------------------------------------------------------
 // tables
 // ---------------------------------------------------------------------------------------------------------
-int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table** out) {
-    if (!c || !out) return fail(TG_ERR_ARG, "tg_table_create: null argument");
-    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
-    if (kind != TG_TABLE_COUNT && kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "unknown table kind %d", kind);
-    if (bind(c)) return TG_ERR_CUDA;
+static int table_new(tg_ctx* c, int kind, int k, Geo g, tg_table** out) {
     tg_table* t = new tg_table();
-    t->ctx = c; t->kind = kind; t->k = k;
-    uint64_t slots = (uint64_t)((double)expected_keys / TARGET_LOAD) + 1;
-    if (slots < MIN_SLOTS) slots = MIN_SLOTS;
-    int rc = table_alloc(c, slots, &t->slots);
+    t->ctx = c; t->kind = kind; t->k = k; t->g = g;
+    t->cap = (uint64_t)g.nlocal * g.subcap;
+    int rc = table_alloc(c, t->cap, &t->slots);
     if (rc) { delete t; return rc; }
-    t->cap = slots;
     CU(cudaMalloc(&t->d_claimed, sizeof(unsigned long long)));
     CU(cudaMalloc(&t->d_error, sizeof(int)));
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
@@ -239,10 +327,51 @@ int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table
     return TG_OK;
 }
 
+int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table** out) {
+    if (!c || !out) return fail(TG_ERR_ARG, "tg_table_create: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (kind != TG_TABLE_COUNT && kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "unknown table kind %d", kind);
+    if (bind(c)) return TG_ERR_CUDA;
+    uint64_t slots = (uint64_t)((double)expected_keys / TARGET_LOAD) + 1;
+    if (slots < MIN_SLOTS) slots = MIN_SLOTS;
+    return table_new(c, kind, k, pick_geo(slots, c->part_bytes), out);
+}
+
+int tg_table_create_sharded(tg_ctx* c, int kind, int k, uint64_t slots_per_partition, uint32_t nparts, uint32_t part0,
+                            uint32_t nlocal, tg_table** out) {
+    if (!c || !out) return fail(TG_ERR_ARG, "tg_table_create_sharded: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (kind != TG_TABLE_COUNT && kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "unknown table kind %d", kind);
+    if (nparts == 0 || nlocal == 0 || (uint64_t)part0 + nlocal > nparts || nparts > LOG_MAX_BINS || slots_per_partition < 16)
+        return fail(TG_ERR_ARG, "tg_table_create_sharded: bad geometry (%u partitions, local %u..+%u, %llu slots each)",
+                    nparts, part0, nlocal, (unsigned long long)slots_per_partition);
+    if (bind(c)) return TG_ERR_CUDA;
+    Geo g;
+    g.subcap = slots_per_partition; g.nparts = nparts; g.part0 = part0; g.nlocal = nlocal;
+    return table_new(c, kind, k, g, out);
+}
+
+int tg_table_geometry(tg_table* t, uint64_t* slots_per_partition, uint32_t* nparts, uint32_t* part0, uint32_t* nlocal) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    if (slots_per_partition) *slots_per_partition = t->g.subcap;
+    if (nparts) *nparts = t->g.nparts;
+    if (part0) *part0 = t->g.part0;
+    if (nlocal) *nlocal = t->g.nlocal;
+    return TG_OK;
+}
+
+static void log_release(tg_table* t) {
+    if (t->log.keys) cudaFree(t->log.keys);
+    if (t->log.cursor) cudaFree(t->log.cursor);
+    if (t->log.chunk_start) cudaFree(t->log.chunk_start);
+    t->log = KeyLog();
+}
+
 void tg_table_destroy(tg_table* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaDeviceSynchronize();
+    log_release(t);
     if (t->slots) cudaFree(t->slots);
     if (t->d_claimed) cudaFree(t->d_claimed);
     if (t->d_error) cudaFree(t->d_error);
@@ -258,8 +387,51 @@ int tg_table_clear(tg_table* t) {
     CU(cudaMemsetAsync(t->slots, 0, t->cap * sizeof(Slot), c->stream[0]));
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
     CU(cudaMemsetAsync(t->d_error, 0, sizeof(int), c->stream[0]));
+    if (t->log.cursor) CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
+    t->log.pending_ub = 0;
     CU(cudaStreamSynchronize(c->stream[0]));
     t->distinct_ub = 0;
+    return TG_OK;
+}
+
+// Move the table into a new geometry (growth).  Both streams must be idle.
+static int table_regrow(tg_table* t, Geo ng) {
+    tg_ctx* c = t->ctx;
+    const uint64_t ncap = (uint64_t)ng.nlocal * ng.subcap;
+    Slot* fresh = nullptr;
+    int rc;
+    if ((rc = table_alloc(c, ncap, &fresh))) return rc;
+    CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
+    TableView nv{fresh, ng, t->d_claimed, t->d_error};
+    CU(launch_rehash(t->slots, t->cap, nv, t->kind == TG_TABLE_LABEL, c->stream[0]));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream[0]));
+    CU(cudaFree(t->slots));
+    t->slots = fresh;
+    t->cap = ncap;
+    t->g = ng;
+    return table_refresh(t);
+}
+
+// geometry for a table that must hold `keys` distinct keys at TARGET_LOAD (shards keep their partition range)
+static int grown_geo(tg_table* t, uint64_t keys, Geo* out) {
+    tg_ctx* c = t->ctx;
+    uint64_t want = (uint64_t)((double)keys / TARGET_LOAD) + 1;
+    if (want < t->cap + t->cap / 2) want = t->cap + t->cap / 2;
+    // never ask for more than the device can hold next to the old table
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    const uint64_t fit = (uint64_t)((double)fr * 0.92) / sizeof(Slot);
+    if (want > fit) want = fit;
+    if ((double)keys > 0.92 * (double)want)
+        return fail(TG_ERR_NOMEM, "k-mer table cannot grow: need room for %llu keys, device has room for %llu slots",
+                    (unsigned long long)keys, (unsigned long long)fit);
+    if (t->sharded()) {
+        *out = t->g;
+        out->subcap = (want + t->g.nlocal - 1) / t->g.nlocal;
+    } else {
+        *out = pick_geo(want, c->part_bytes);
+    }
     return TG_OK;
 }
 
@@ -280,39 +452,59 @@ int tg_table_reserve(tg_table* t, uint64_t additional) {
         t->distinct_ub += additional;
         return TG_OK;
     }
-    uint64_t want = (uint64_t)((double)(t->distinct_ub + additional) / TARGET_LOAD) + 1;
-    if (want < t->cap + t->cap / 2) want = t->cap + t->cap / 2;
-    // never ask for more than the device can hold next to the old table
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    const uint64_t fit = (uint64_t)((double)fr * 0.92) / sizeof(Slot);
-    if (want > fit) want = fit;
-    if ((double)(t->distinct_ub + additional) > 0.92 * (double)want)
-        return fail(TG_ERR_NOMEM, "k-mer table cannot grow: need room for %llu keys, device has room for %llu slots",
-                    (unsigned long long)(t->distinct_ub + additional), (unsigned long long)fit);
-    Slot* fresh = nullptr;
-    if ((rc = table_alloc(c, want, &fresh))) return rc;
-    CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
-    TableView nv{fresh, want, t->d_claimed, t->d_error};
-    CU(launch_rehash(t->slots, t->cap, nv, t->kind == TG_TABLE_LABEL, c->stream[0]));
-    c->launches++;
-    CU(cudaStreamSynchronize(c->stream[0]));
-    CU(cudaFree(t->slots));
-    t->slots = fresh;
-    t->cap = want;
-    if ((rc = table_refresh(t))) return rc;
+    Geo ng;
+    if ((rc = grown_geo(t, t->distinct_ub + additional, &ng))) return rc;
+    if ((rc = table_regrow(t, ng))) return rc;
     t->distinct_ub += additional;
     return TG_OK;
 }
 
+int tg_table_resize(tg_table* t, uint64_t slots_per_partition) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    if ((rc = table_refresh(t))) return rc;
+    if ((double)t->distinct_ub > 0.92 * (double)slots_per_partition * t->g.nlocal)
+        return fail(TG_ERR_ARG, "tg_table_resize: %llu keys do not fit %u x %llu slots", (unsigned long long)t->distinct_ub,
+                    t->g.nlocal, (unsigned long long)slots_per_partition);
+    Geo ng = t->g;
+    ng.subcap = slots_per_partition;
+    return table_regrow(t, ng);
+}
+
+static int flush_log(tg_table* t);
+
 int tg_table_info(tg_table* t, uint64_t* capacity, uint64_t* distinct) {
     if (!t) return fail(TG_ERR_ARG, "null table");
     if (bind(t->ctx)) return TG_ERR_CUDA;
-    int rc = sync_all(t->ctx);
+    int rc = flush_log(t);
     if (rc) return rc;
+    if ((rc = sync_all(t->ctx))) return rc;
     if ((rc = table_refresh(t))) return rc;
     if (capacity) *capacity = t->cap;
     if (distinct) *distinct = t->distinct_ub;
+    return TG_OK;
+}
+
+int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes) {
+    if (!t || !d_slots || !nbytes) return fail(TG_ERR_ARG, "tg_table_slots_dev: null argument");
+    if (bind(t->ctx)) return TG_ERR_CUDA;
+    int rc = flush_log(t);
+    if (rc) return rc;
+    if ((rc = sync_all(t->ctx))) return rc;
+    *d_slots = t->slots;
+    *nbytes = t->cap * sizeof(Slot);
+    return TG_OK;
+}
+
+int tg_table_set_distinct(tg_table* t, uint64_t distinct) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    if (bind(t->ctx)) return TG_ERR_CUDA;
+    unsigned long long v = distinct;
+    CU(cudaMemcpy(t->d_claimed, &v, sizeof v, cudaMemcpyHostToDevice));
+    t->distinct_ub = distinct;
     return TG_OK;
 }
 
@@ -340,24 +532,173 @@ static int upload_records(tg_ctx* c, int b, const char* src, uint64_t n) {
 // ---------------------------------------------------------------------------------------------------------
 // stage J
 // ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+// ---- k-mer log management (partitioned count path) -------------------------------------------------------
+static unsigned log_bins_for(const tg_table* t) {
+    if (t->sharded()) return t->g.nparts;                      // bins == global partitions (exchange unit)
+    return t->g.nparts > LOG_BASE_BINS ? t->g.nparts : LOG_BASE_BINS;
+}
+
+// worth logging?  The replay streams the whole table through L2 once, so the batch must be large next to it.
+static bool log_pays(const tg_table* t, uint64_t nbytes) {
+    const tg_ctx* c = t->ctx;
+    if (t->kind != TG_TABLE_COUNT || t->sharded()) return false;
+    if (c->count_mode == 1) return false;
+    if (c->count_mode == 2) return true;
+    return t->g.nparts >= 4 && nbytes * 16 >= t->cap * sizeof(Slot);
+}
+
+constexpr uint64_t LOG_BIN_SLACK = 1024;    // additive head-room per bin (hash fluctuation of small batches)
+constexpr double LOG_BIN_FACTOR = 1.2;      // multiplicative head-room per bin (hot k-mers)
+
+// entries that can be appended to an empty log without any bin expected to overflow
+static uint64_t log_room(const KeyLog& lg) {
+    if (lg.cap <= LOG_BIN_SLACK) return 0;
+    return (uint64_t)((double)(lg.cap - LOG_BIN_SLACK) / LOG_BIN_FACTOR) * lg.nbins;
+}
+
+// a log laid out for `entries` appended entries per replay (fewer if the HBM budget is smaller); *ok = false when
+// no useful log fits
+static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
+    tg_ctx* c = t->ctx;
+    *ok = false;
+    const unsigned nbins = log_bins_for(t);
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    uint64_t budget = std::min<uint64_t>(c->log_max_bytes, fr / 2);
+    if (t->log.keys) budget = std::max<uint64_t>(budget, t->log.total_entries() * 8);
+    uint64_t per_bin = (uint64_t)((double)entries / nbins * LOG_BIN_FACTOR) + LOG_BIN_SLACK;
+    per_bin = std::min<uint64_t>(per_bin, budget / 8 / nbins);
+    per_bin = std::min<uint64_t>(per_bin, 0xFFFFFF00ull);
+    if (per_bin < 2 * LOG_BIN_SLACK) return TG_OK;
+    if (t->log.keys && t->log.nbins == nbins && t->log.cap >= per_bin) { *ok = true; return TG_OK; }
+    if (t->log.pending_ub) { *ok = t->log.keys != nullptr; return TG_OK; }   // holds entries: keep its layout
+    log_release(t);
+    if (cudaMalloc(&t->log.keys, per_bin * nbins * 8) != cudaSuccess) { cudaGetLastError(); t->log.keys = nullptr; return TG_OK; }
+    CU(cudaMalloc(&t->log.cursor, nbins * sizeof(unsigned int)));
+    CU(cudaMalloc(&t->log.chunk_start, ((size_t)nbins + 1) * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(t->log.cursor, 0, nbins * sizeof(unsigned int), c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    t->log.nbins = nbins; t->log.cap = (unsigned)per_bin; t->log.pending_ub = 0;
+    *ok = true;
+    return TG_OK;
+}
+
+static LogView log_view(tg_table* t) {
+    return LogView{t->log.keys, t->log.cursor, t->log.nbins, t->log.cap, t->d_error};
+}
+
+// replay + reset on stream 0 (stream-ordered; no host sync)
+static int replay_log_async(tg_table* t) {
+    tg_ctx* c = t->ctx;
+    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, t->log.chunk_start,
+                         t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
+    c->launches += 2;
+    CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
+    t->log.pending_ub = 0;
+    return TG_OK;
+}
+
+// Distinct keys in the log, estimated from a hash-uniform sample of bins: the sample is replayed into a scratch
+// table and its exact distinct count scaled up.  Keys spread over bins by hash, so the estimate is tight whatever
+// the multiplicity skew; it counts keys already in the table too, i.e. it errs high.
+static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill, uint64_t total, uint64_t* est) {
+    tg_ctx* c = t->ctx;
+    const unsigned nbins = t->log.nbins;
+    const uint64_t mean = total / nbins + 1;
+    unsigned ns = (unsigned)std::min<uint64_t>(nbins, (4000000 + mean - 1) / mean);
+    if (ns < 1) ns = 1;
+    uint64_t sample = 0;
+    for (unsigned b = 0; b < ns; b++) sample += fill[b];
+    if (sample == 0) { *est = total; return TG_OK; }
+    Geo sg;
+    sg.subcap = sample * 2 + 1024; sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1;
+    Slot* scratch = nullptr;
+    unsigned long long* d_n = nullptr;
+    int rc;
+    if ((rc = table_alloc(c, sg.subcap, &scratch))) return rc;
+    CU(cudaMalloc(&d_n, sizeof *d_n));
+    CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, c->stream[0]));
+    TableView sv{scratch, sg, d_n, t->d_error};
+    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, ns, 0, nbins, t->log.chunk_start, sv, 0, c->sm_count,
+                         c->stream[0]));
+    c->launches += 2;
+    unsigned long long d = 0;
+    CU(cudaMemcpyAsync(&d, d_n, sizeof d, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(scratch); cudaFree(d_n);
+    *est = (uint64_t)((double)d * nbins / ns * 1.03) + 65536;
+    if (*est > total) *est = total;
+    return TG_OK;
+}
+
+// Apply every pending log entry to the table (growing it first if the log could overfill it).
+static int flush_log(tg_table* t) {
+    if (!t->log.keys || t->log.pending_ub == 0) return TG_OK;
+    tg_ctx* c = t->ctx;
+    int rc;
+    if ((rc = sync_all(c))) return rc;
+    if ((rc = table_refresh(t))) return rc;
+    std::vector<unsigned> fill(t->log.nbins);
+    CU(cudaMemcpy(fill.data(), t->log.cursor, fill.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    uint64_t total = 0;
+    for (auto& f : fill) { if (f > t->log.cap) f = t->log.cap; total += f; }
+    if ((double)(t->distinct_ub + total) > MAX_LOAD * (double)t->cap) {
+        uint64_t est = total;
+        if ((rc = estimate_log_distinct(t, fill, total, &est))) return rc;
+        if ((double)(t->distinct_ub + est) > MAX_LOAD * (double)t->cap) {
+            Geo ng;
+            if ((rc = grown_geo(t, t->distinct_ub + est, &ng))) return rc;
+            if ((rc = table_regrow(t, ng))) return rc;
+        }
+    }
+    if ((rc = replay_log_async(t))) return rc;
+    CU(cudaStreamSynchronize(c->stream[0]));
+    return table_refresh(t);
+}
+
+extern "C" {
+
 int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical) {
     if (!t || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_count_reads: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
+    // Partitioned path: append to the log batch by batch (H2D of one batch overlaps the log kernel of the other),
+    // replay when the log is full and at the end.  A table still too small to be partitioned is first grown to the
+    // size the input suggests -- only ever when the caller's hint was far below the input.
+    bool logged = false;
+    if (c->count_mode != 1 && !t->sharded() && nbytes >= (256ull << 20) && t->g.nparts < 4 && nbytes / 8 > t->cap) {
+        if ((rc = tg_table_reserve(t, nbytes / 8))) return rc;
+        t->distinct_ub -= nbytes / 8;       // it was a sizing hint, not an insertion
+    }
+    if (log_pays(t, nbytes) && (rc = ensure_log(t, nbytes, &logged))) return rc;
+    const uint64_t room = logged ? log_room(t->log) : 0;
     uint64_t pos = 0;
     for (int it = 0; pos < nbytes; it++) {
         const int b = it & 1;
         const uint64_t end = batch_end(recs, pos, nbytes, c->batch_bytes);
         const uint64_t n = end - pos;
-        if ((rc = tg_table_reserve(t, n))) return rc;     // may rehash: syncs both streams itself
+        if (logged) {
+            if (t->log.pending_ub + n > room && t->log.pending_ub) { if ((rc = flush_log(t))) return rc; }
+        } else {
+            if ((rc = tg_table_reserve(t, n))) return rc;     // may rehash: syncs both streams itself
+        }
         CU(cudaStreamSynchronize(c->stream[b]));          // staging buffer b is free again
         if ((rc = upload_records(c, b, recs + pos, n))) return rc;
-        CU(launch_count_tiles((const uint8_t*)c->recs[b].p, n, t->k, canonical, t->view(), c->sm_count, c->stream[b]));
+        if (logged) {
+            CU(launch_log_tiles((const uint8_t*)c->recs[b].p, n, t->k, canonical, log_view(t), t->view(), c->sm_count,
+                                c->stream[b]));
+            t->log.pending_ub += n;
+        } else {
+            CU(launch_count_tiles((const uint8_t*)c->recs[b].p, n, t->k, canonical, t->view(), c->sm_count, c->stream[b]));
+        }
         c->launches++;
         pos = end;
     }
+    if (logged && (rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
     return table_refresh(t);
 }
@@ -369,8 +710,53 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
     if (bind(c)) return TG_ERR_CUDA;
     // the caller sizes the table (tg_table_create / tg_table_reserve): a conservative per-byte bound would
     // multiply the footprint.  An overflow raises the table's error flag -> TG_ERR_TABLE at tg_table_info.
-    CU(launch_count_tiles((const uint8_t*)d_recs, nbytes, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
+    int rc;
+    bool logged = false;
+    if (log_pays(t, nbytes) && (rc = ensure_log(t, nbytes, &logged))) return rc;
+    if (!logged) {
+        CU(launch_count_tiles((const uint8_t*)d_recs, nbytes, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
+        c->launches++;
+        return TG_OK;
+    }
+    // segments of whole tiles, each small enough for the log; everything stays stream-ordered on stream 0
+    uint64_t seg = log_room(t->log) / CT_TILE * CT_TILE;
+    if (seg < (uint64_t)CT_TILE) seg = CT_TILE;
+    for (uint64_t pos = 0; pos < nbytes; pos += seg) {
+        const uint64_t n = std::min(seg, nbytes - pos);
+        CU(launch_log_tiles((const uint8_t*)d_recs + pos, n, t->k, canonical, log_view(t), t->view(), c->sm_count,
+                            c->stream[0]));
+        c->launches++;
+        t->log.pending_ub += n;
+        if ((rc = replay_log_async(t))) return rc;
+    }
+    return TG_OK;
+}
+
+// ---- sharded counting (multi-GPU): phase 1 into a caller-owned log, phase 2 from a caller-owned (received) log ----
+int tg_count_partition_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
+                           uint32_t cap, void* d_keys, void* d_cursor) {
+    if (!c || !d_recs || !d_keys || !d_cursor) return fail(TG_ERR_ARG, "tg_count_partition_dev: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (nbins == 0 || nbins > LOG_MAX_BINS || cap == 0) return fail(TG_ERR_ARG, "tg_count_partition_dev: bad log shape");
+    if (bind(c)) return TG_ERR_CUDA;
+    LogView lg{(unsigned long long*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error};
+    TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
+    CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
+    return TG_OK;
+}
+
+int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t cap) {
+    if (!t || !d_keys || !d_cursor || nsrc == 0 || cap == 0) return fail(TG_ERR_ARG, "tg_table_replay_log_dev: bad argument");
+    if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_table_replay_log_dev needs a TG_TABLE_COUNT table");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    const size_t need = ((size_t)nsrc * t->g.nlocal + 1) * sizeof(unsigned long long);
+    CU(c->scratch.ensure(need));
+    CU(launch_log_replay((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
+                         t->g.nparts, (unsigned long long*)c->scratch.p, t->view(), c->replay_prefetch, c->sm_count,
+                         c->stream[0]));
+    c->launches += 2;
     return TG_OK;
 }
 
@@ -379,6 +765,7 @@ int tg_table_load_pairs(tg_table* t, const uint64_t* keys, const uint32_t* vals,
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
+    if ((rc = flush_log(t))) return rc;
     const uint64_t chunk = std::max<uint64_t>(1, c->batch_bytes / 12);
     for (uint64_t pos = 0, it = 0; pos < n; pos += chunk, it++) {
         const int b = (int)(it & 1);
@@ -390,7 +777,7 @@ int tg_table_load_pairs(tg_table* t, const uint64_t* keys, const uint32_t* vals,
         CU(cudaMemcpyAsync(c->out_a[b].p, keys + pos, m * 8, cudaMemcpyHostToDevice, c->stream[b]));
         CU(cudaMemcpyAsync(c->out_b[b].p, vals + pos, m * 4, cudaMemcpyHostToDevice, c->stream[b]));
         CU(launch_load_pairs((const uint64_t*)c->out_a[b].p, (const uint32_t*)c->out_b[b].p, m, t->k, canonical,
-                             t->view(), c->stream[b]));
+                             t->view(), t->kind == TG_TABLE_LABEL, c->stream[b]));
         c->launches++;
     }
     if ((rc = sync_all(c))) return rc;
@@ -404,6 +791,7 @@ int tg_table_export(tg_table* t, uint32_t min_count, uint32_t max_count, int sor
     if (bind(c)) return TG_ERR_CUDA;
     *keys = nullptr; *counts = nullptr; *n_out = 0;
     int rc;
+    if ((rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
     if ((rc = table_refresh(t))) return rc;
     cudaStream_t s = c->stream[0];
@@ -440,6 +828,7 @@ int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]) {
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
+    if ((rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
     unsigned long long* d_bins = nullptr;
     CU(cudaMalloc(&d_bins, TG_HISTO_BINS * sizeof *d_bins));
@@ -505,6 +894,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
     if (bind(c)) return TG_ERR_CUDA;
     if (nreads == 0) return TG_OK;
     int rc;
+    if ((rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
     const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
     struct Pending { bool live = false; ReadBatch rb; } pend[2];
@@ -515,7 +905,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
         int r2 = finish_long(c, b, t->k, cov_stats_long_scratch_bytes,
             [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
                 return launch_cov_stats_long((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, t->k,
-                                             canonical, t->slots, t->cap, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p,
+                                             canonical, t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p,
                                              (float*)c->out_c[b].p, per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr,
                                              (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
                                              c->stream[b]);
@@ -545,7 +935,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
         CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
         LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
         CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
-                            t->slots, t->cap, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
+                            t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
                             per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, c->stream[b]));
         c->launches++;
         pend[b].live = true; pend[b].rb = rb;
@@ -562,17 +952,18 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_cov_stats_dev: at most 2^31 reads per call");
+    if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }
     const int b = 0;
     CU(c->long_idx[b].ensure(nreads * 4));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
     LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
-    CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->cap,
+    CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->g,
                         (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->stream[b]));
     c->launches++;
     return finish_long(c, b, t->k, cov_stats_long_scratch_bytes,
         [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
             return launch_cov_stats_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots,
-                                         t->cap, (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr,
+                                         t->g, (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr,
                                          (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
                                          c->stream[b]);
         });
@@ -642,7 +1033,7 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
         int r2 = finish_long(c, b, t->k, assign_long_scratch_bytes,
             [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
                 return launch_assign_long((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, t->k, strand,
-                                          t->slots, t->cap, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p,
+                                          t->slots, t->g, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p,
                                           (int32_t*)c->out_b[b].p, (int32_t*)c->out_c[b].p,
                                           (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
                                           c->stream[b]);
@@ -668,7 +1059,7 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
         CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
         LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
         CU(launch_assign((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, strand, t->slots,
-                         t->cap, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
+                         t->g, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
                          (int32_t*)c->out_c[b].p, ll, c->stream[b]));
         c->launches++;
         pend[b].live = true; pend[b].rb = rb;
@@ -689,12 +1080,12 @@ int tg_assign_reads_dev(tg_table* t, const void* d_recs, const void* d_offs, uin
     CU(c->long_idx[b].ensure(nreads * 4));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
     LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
-    CU(launch_assign((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, strand, t->slots, t->cap,
+    CU(launch_assign((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, strand, t->slots, t->g,
                      (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll, c->stream[b]));
     c->launches++;
     return finish_long(c, b, t->k, assign_long_scratch_bytes,
         [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
-            return launch_assign_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, strand, t->slots, t->cap,
+            return launch_assign_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, strand, t->slots, t->g,
                                       (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr,
                                       (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
                                       c->stream[b]);
@@ -762,6 +1153,21 @@ int tg_memcpy_d2h(tg_ctx* c, void* host, const void* dptr, uint64_t bytes) {
     if (bind(c)) return TG_ERR_CUDA;
     CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_memcpy_d2d(tg_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_memset_dev(tg_ctx* c, void* dst, int value, uint64_t bytes) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaMemsetAsync(dst, value, bytes, c->stream[0]));
     return TG_OK;
 }
 

@@ -26,11 +26,25 @@ struct __align__(16) Slot {
 
 constexpr unsigned long long KEY_TAG = 1ull << 63;
 
+// Table geometry.  The table is an array of `nparts` PARTITIONS of `subcap` slots each; a key lives in
+// partition part(key) (low hash word) and probes linearly, wrapping INSIDE its partition (slot from the high hash
+// word).  Partitions are what make the table shardable and cache-blockable without changing a single lookup:
+//   * one GPU: nparts is chosen so that a partition (subcap * 16 B) fits comfortably in L2; the partitioned
+//     count path replays a k-mer log partition by partition, so its CAS/RED traffic stays in L2;
+//   * N GPUs: rank r holds partitions [part0, part0 + nlocal) of the same global geometry -- owner(key) is just
+//     part(key) / nlocal -- and an all-gather of the shards IS the full table (part0 = 0, nlocal = nparts).
+struct Geo {
+    unsigned long long subcap;   // slots per partition
+    unsigned int nparts;         // partitions in the global table
+    unsigned int part0;          // first partition held by this view
+    unsigned int nlocal;         // partitions held by this view (slots[] has nlocal * subcap entries)
+};
+
 struct TableView {
     Slot* slots;
-    unsigned long long cap;           // number of slots (any size: index = mulhi64(hash, cap))
+    Geo g;
     unsigned long long* n_claimed;    // device counter of distinct keys
-    int* error;                       // device error flag (probe overflow)
+    int* error;                       // device error flag (probe overflow / key outside the local partitions)
 };
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -78,59 +92,85 @@ __host__ __device__ __forceinline__ unsigned long long packed_revcomp(unsigned l
     return r;
 }
 
-// home slot = high 64 bits of hash * capacity (any capacity, no modulo); probing is linear with wrap-around
-__device__ __forceinline__ unsigned long long home_slot(unsigned long long key, unsigned long long cap) {
-    return __umul64hi(mix64(key), cap);
+// partition of a hash: top bits of the LOW hash word (the slot uses the high word), any partition count
+__device__ __forceinline__ unsigned hash_part(unsigned long long h, unsigned nparts) {
+    return (unsigned)(((h & 0xFFFFFFFFull) * (unsigned long long)nparts) >> 32);
 }
-__device__ __forceinline__ unsigned long long next_slot(unsigned long long idx, unsigned long long cap) {
-    return (idx + 1 == cap) ? 0ull : idx + 1;
+struct Probe {
+    unsigned long long base;   // first slot of the key's partition inside this view
+    unsigned long long off;    // current slot inside the partition
+};
+// returns false when the key's partition is not held by this view
+__device__ __forceinline__ bool probe_home(const Geo& g, unsigned long long key, Probe& p) {
+    const unsigned long long h = mix64(key);
+    const unsigned part = hash_part(h, g.nparts) - g.part0;
+    p.base = (unsigned long long)part * g.subcap;
+    p.off = __umul64hi(h, g.subcap);
+    return part < g.nlocal;
 }
-// owner rank of a key when the table is sharded by hash across GPUs (low hash bits; the slot uses the high ones)
-__device__ __forceinline__ unsigned owner_rank(unsigned long long key, unsigned nranks) {
-    return (unsigned)((mix64(key) & 0xFFFFFFFFull) * (unsigned long long)nranks >> 32);
-}
+__device__ __forceinline__ void probe_next(const Geo& g, Probe& p) { p.off = (p.off + 1 == g.subcap) ? 0ull : p.off + 1; }
 
 // ---- table primitives --------------------------------------------------------------------------------
 // Keys never change once written and slots never return to empty, so a stale (L1/L2) read of a key can
 // only be "empty" where the truth is "claimed"; the CAS that follows re-validates.  ld.cg keeps random
 // sectors out of L1.
-__device__ __forceinline__ Slot* table_upsert_slot(const TableView& t, unsigned long long key,
-                                                   unsigned long long idx, unsigned long long cur,
-                                                   unsigned& claimed) {
+__device__ __forceinline__ Slot* table_upsert_slot(const TableView& t, unsigned long long key, Probe p,
+                                                   unsigned long long cur, unsigned& claimed) {
     unsigned long long probes = 0;
     while (true) {
-        if (cur == key) return &t.slots[idx];
+        Slot* sl = &t.slots[p.base + p.off];
+        if (cur == key) return sl;
         if (cur == 0ull) {
-            unsigned long long old = atomicCAS(&t.slots[idx].key, 0ull, key);
-            if (old == 0ull) { claimed++; return &t.slots[idx]; }
-            if (old == key) return &t.slots[idx];
+            unsigned long long old = atomicCAS(&sl->key, 0ull, key);
+            if (old == 0ull) { claimed++; return sl; }
+            if (old == key) return sl;
         }
-        if (++probes > t.cap) { atomicExch(t.error, 1); return nullptr; }
-        idx = next_slot(idx, t.cap);
-        cur = __ldcg(&t.slots[idx].key);
+        if (++probes > t.g.subcap) { atomicExch(t.error, 1); return nullptr; }
+        probe_next(t.g, p);
+        cur = __ldcg(&t.slots[p.base + p.off].key);
     }
 }
 
-__device__ __forceinline__ void table_add(const TableView& t, unsigned long long key, unsigned cnt,
-                                          unsigned& claimed) {
-    unsigned long long idx = home_slot(key, t.cap);
-    unsigned long long cur = __ldcg(&t.slots[idx].key);
-    Slot* s = table_upsert_slot(t, key, idx, cur, claimed);
-    if (s) atomicAdd(&s->val, cnt);
+// val += cnt (count tables) or val = max(val, cnt) (label tables)
+template <bool IS_MAX>
+__device__ __forceinline__ void table_update(const TableView& t, unsigned long long key, unsigned v, unsigned& claimed) {
+    Probe p;
+    if (!probe_home(t.g, key, p)) { atomicExch(t.error, 2); return; }
+    const unsigned long long cur = __ldcg(&t.slots[p.base + p.off].key);
+    Slot* s = table_upsert_slot(t, key, p, cur, claimed);
+    if (s) { if (IS_MAX) atomicMax(&s->val, v); else atomicAdd(&s->val, v); }
 }
 
 // read-only probe: returns val, or 0 when the key is absent.  One 16-B load fetches key and value.
-__device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, unsigned long long cap,
-                                                 unsigned long long key) {
-    unsigned long long idx = home_slot(key, cap);
-    while (true) {
-        const uint4 s = __ldcg(reinterpret_cast<const uint4*>(&slots[idx]));
+__device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, const Geo& g, unsigned long long key) {
+    Probe p;
+    if (!probe_home(g, key, p)) return 0u;
+    for (unsigned long long probes = 0; probes <= g.subcap; probes++) {   // bounded: a full partition cannot hang a lookup
+        const uint4 s = __ldcg(reinterpret_cast<const uint4*>(&slots[p.base + p.off]));
         unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
         if (k == key) return s.z;
         if (k == 0ull) return 0u;
-        idx = next_slot(idx, cap);
+        probe_next(g, p);
     }
+    return 0u;
 }
+
+// ---- k-mer log (partitioned count path) ------------------------------------------------------------------
+// Phase 1 appends every counted k-mer occurrence to the bin of its hash partition instead of touching the table;
+// phase 2 replays the log bin by bin, so the CAS/RED traffic of one bin stays inside an L2-resident group of
+// partitions.  An entry is the table key; bit 31 (never used by a key: planes are k <= 31 bits wide) marks a
+// run of LOG_RUN identical consecutive windows (homopolymers), so one entry can stand for 8 occurrences.
+constexpr unsigned long long LOG_RUN_FLAG = 1ull << 31;
+constexpr unsigned LOG_RUN = 8;
+
+struct LogView {
+    unsigned long long* keys;   // [nbins][cap]
+    unsigned int* cursor;       // [nbins] entries reserved so far; may run past cap (readers clamp, writers
+                                //         past cap insert directly / raise the overflow flag)
+    unsigned int nbins;         // bins == partitions of the geometry the log was laid out for
+    unsigned int cap;           // entries per bin
+    int* error;                 // device flag raised (3) when a bin overflows and there is no table to fall back to
+};
 
 // ---- TMA (1-D bulk async copy) + mbarrier wrappers -----------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -42,27 +42,37 @@ cudaError_t launch_count_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, in
 cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uint64_t* d_offs, uint64_t rec_base,
                                uint64_t nbundles, uint32_t first_bundle_index, int k, TableView t, int sm_count,
                                cudaStream_t s);
-// (packed key, value) pairs -> table[canon(key)] += value
+// partitioned count path, phase 1: every valid window's key appended to the log bin of its hash partition
+// (t.slots may be null: then a full bin raises lg.error instead of counting directly)
+constexpr unsigned LOG_MAX_BINS = 8192;
+cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
+                             int sm_count, cudaStream_t s);
+// phase 2: replay log segments [nsrc][nlocal][cap] (cursor [nsrc][nlocal]) bin-major into the table; the bins are
+// global bins bin0..bin0+nlocal-1 of nbins_global.  d_chunk_start: scratch of nsrc*nlocal+1 u64.
+cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                              unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
+                              TableView t, int prefetch, int sm_count, cudaStream_t s);
+// (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
-                              TableView t, cudaStream_t s);
+                              TableView t, int is_label, cudaStream_t s);
 // re-insert every live slot of `from` into `to` (growth)
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, cudaStream_t s);
 
 // per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                             int canonical, const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean,
+                             int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                              float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s);
 cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
-                                  const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean, float* d_stdev,
+                                  const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
                                   unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s);
 size_t cov_stats_long_scratch_bytes(unsigned int max_win, int k, int nctas);
 
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                          int strand, const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok,
+                          int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok,
                           int32_t* d_best, int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s);
 cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
-                               const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok, int32_t* d_best,
+                               const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                                int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
                                unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s);
 size_t assign_long_scratch_bytes(unsigned int max_win, int k, int nctas);

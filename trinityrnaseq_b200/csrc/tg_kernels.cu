@@ -20,6 +20,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 int max_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device) {
     int per_sm = 0, sms = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem);
+    if (device < 0) cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (per_sm < 1) per_sm = 1;
     return per_sm * sms;
@@ -106,7 +107,7 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
 #pragma unroll 1
             for (int g = 0; g < 32; g += 4) {
                 unsigned long long key[4];
-                unsigned long long idx[4];
+                Probe pr[4];
                 unsigned long long cur[4];
                 unsigned cnt[4];
                 uint32_t lab[4];
@@ -139,13 +140,13 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
-                        idx[u] = home_slot(key[u], t.cap);
-                        cur[u] = __ldcg(&t.slots[idx[u]].key);
+                        if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
+                        else { key[u] = 0ull; atomicExch(t.error, 2); }
                     }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
-                        Slot* sl = table_upsert_slot(t, key[u], idx[u], cur[u], claimed);
+                        Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
                         if (sl) {
                             if (MODE == MODE_COUNT) atomicAdd(&sl->val, cnt[u]);
                             else atomicMax(&sl->val, lab[u]);
@@ -192,8 +193,291 @@ cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uin
 }
 
 // =========================================================================================================
+// Partitioned count path.
+//   phase 1  k_log_tiles   reads -> canonical k-mer keys -> appended to the log bin of their hash partition
+//   phase 2  k_log_replay  bins replayed in order: all CAS/RED traffic of a bin lands in one L2-resident group of
+//                          table partitions (prefetched into L2 with a bulk prefetch one bin ahead)
+// The log costs 8 B written + 8 B read per occurrence, all of it sequential, instead of a random DRAM
+// read-modify-write per occurrence.  Multi-GPU counting uses the same two kernels with an all-to-all of the
+// bins between them (bin = global partition; rank r owns a contiguous range of bins).
+// =========================================================================================================
+constexpr int LT_TILES = 4;   // tiles per reservation round: 4 x 8 KiB of reads share one cursor reservation per bin
+
+struct LogSmem {
+    alignas(128) uint8_t ascii[2][CT_LOAD];
+    uint32_t p0[LT_TILES][CT_THREADS + 1];
+    uint32_t p1[LT_TILES][CT_THREADS + 1];
+    uint32_t pb[LT_TILES][CT_THREADS + 1];
+    alignas(8) unsigned long long bar[2];
+};
+
+// every log entry of the 32 windows starting in one thread's chunk: runs of identical consecutive keys are
+// folded (LOG_RUN at a time), the rest emitted singly.  emit(entry, bin) is called once per entry.
+template <typename Emit>
+__device__ __forceinline__ void chunk_log_entries(unsigned a0, unsigned a1, unsigned ab, unsigned c0, unsigned c1,
+                                                  unsigned cb, unsigned mk, int k, int canonical, unsigned nbins,
+                                                  Emit&& emit) {
+    if (ab == FULL) return;    // every window starting here covers at least one of this chunk's (invalid) bases
+    unsigned long long prev = 0ull;
+    unsigned run = 0;
+    auto flush = [&]() {
+        if (prev == 0ull) return;
+        const unsigned bin = hash_part(mix64(prev), nbins);
+        for (; run >= LOG_RUN; run -= LOG_RUN) emit(prev | LOG_RUN_FLAG, bin);
+        for (; run > 0; run--) emit(prev, bin);
+    };
+#pragma unroll 4
+    for (int s = 0; s < 32; s++) {
+        const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
+        unsigned long long key = 0ull;
+        if (!bad) {
+            const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+            const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+            key = make_key(f0, f1);
+            if (canonical) {
+                const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                key = kr < key ? kr : key;
+            }
+        }
+        if (key == prev) run++;
+        else { flush(); prev = key; run = 1; }
+    }
+    flush();
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 3)
+k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, LogView lg, TableView t) {
+    __shared__ LogSmem sm;
+    extern __shared__ unsigned int dyn[];          // hist[nbins] | gbase[nbins]
+    unsigned int* hist = dyn;
+    unsigned int* gbase = dyn + lg.nbins;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned mk = kmask(k);
+    unsigned claimed = 0;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // q-th tile this CTA touches: super tile (blockIdx.x + (q / LT_TILES) * gridDim.x), tile q % LT_TILES of it
+    auto tile_at = [&](uint64_t q) -> uint64_t {
+        return (blockIdx.x + (q / LT_TILES) * (uint64_t)gridDim.x) * LT_TILES + (q % LT_TILES);
+    };
+    uint64_t q = 0;
+    if (tid == 0 && tile_at(0) < ntiles) {
+        mbar_arrive_expect_tx(&sm.bar[0], CT_LOAD);
+        bulk_copy_g2s(sm.ascii[0], recs + tile_at(0) * CT_TILE, CT_LOAD, &sm.bar[0]);
+    }
+
+    for (uint64_t st = blockIdx.x; st * LT_TILES < ntiles; st += gridDim.x) {
+        const uint64_t left = ntiles - st * LT_TILES;
+        const int nt = left < (uint64_t)LT_TILES ? (int)left : LT_TILES;
+        for (unsigned b = tid; b < lg.nbins; b += CT_THREADS) hist[b] = 0;
+        // ---- pass A: planes of nt tiles + per-bin entry counts
+        for (int j = 0; j < nt; j++, q++) {
+            const unsigned buf = (unsigned)q & 1u;
+            const uint64_t next = tile_at(q + 1);
+            if (tid == 0 && next < ntiles) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&sm.bar[buf ^ 1u], CT_LOAD);
+                bulk_copy_g2s(sm.ascii[buf ^ 1u], recs + next * CT_TILE, CT_LOAD, &sm.bar[buf ^ 1u]);
+            }
+            mbar_wait(&sm.bar[buf], (unsigned)(q >> 1) & 1u);
+            const uint8_t* a = sm.ascii[buf];
+            for (int c = warp; c <= CT_THREADS; c += CT_THREADS / 32) {
+                const unsigned ch = a[c * 32 + lane];
+                const unsigned code = base_code(ch);
+                const unsigned b0 = __ballot_sync(FULL, code & 1u);
+                const unsigned b1 = __ballot_sync(FULL, code >> 1);
+                const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
+                if (lane == 0) { sm.p0[j][c] = b0; sm.p1[j][c] = b1; sm.pb[j][c] = bb; }
+            }
+            __syncthreads();   // planes of tile j complete (and hist zeroed); ascii[buf] free for the TMA after next
+            chunk_log_entries(sm.p0[j][tid], sm.p1[j][tid], sm.pb[j][tid], sm.p0[j][tid + 1], sm.p1[j][tid + 1],
+                              sm.pb[j][tid + 1], mk, k, canonical, lg.nbins,
+                              [&](unsigned long long, unsigned bin) { atomicAdd(&hist[bin], 1u); });
+        }
+        __syncthreads();
+        // ---- one cursor reservation per non-empty bin
+        for (unsigned b = tid; b < lg.nbins; b += CT_THREADS) {
+            const unsigned n = hist[b];
+            if (n) {
+                unsigned base = *reinterpret_cast<volatile unsigned int*>(&lg.cursor[b]);
+                if (base < lg.cap) base = atomicAdd(&lg.cursor[b], n);   // a full bin is never advanced again: no wrap
+                gbase[b] = base;
+                hist[b] = 0;
+            }
+        }
+        __syncthreads();
+        // ---- pass B: the same entries again, now written to their reserved places
+        for (int j = 0; j < nt; j++) {
+            chunk_log_entries(sm.p0[j][tid], sm.p1[j][tid], sm.pb[j][tid], sm.p0[j][tid + 1], sm.p1[j][tid + 1],
+                              sm.pb[j][tid + 1], mk, k, canonical, lg.nbins,
+                              [&](unsigned long long e, unsigned bin) {
+                                  const unsigned long long pos = (unsigned long long)gbase[bin] + atomicAdd(&hist[bin], 1u);
+                                  if (pos < lg.cap) {
+                                      lg.keys[(unsigned long long)bin * lg.cap + pos] = e;
+                                  } else if (t.slots) {   // bin full: count this occurrence directly
+                                      table_update<false>(t, e & ~LOG_RUN_FLAG, (e & LOG_RUN_FLAG) ? LOG_RUN : 1u, claimed);
+                                  } else {
+                                      atomicExch(lg.error, 3);
+                                  }
+                              });
+        }
+        __syncthreads();   // hist/gbase/planes consumed before the next round reuses them
+    }
+    if (t.slots) {
+        for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+        if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
+    }
+}
+
+size_t log_tiles_smem_bytes(unsigned nbins) { return (size_t)nbins * 2 * sizeof(unsigned int); }
+
+cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
+                             int sm_count, cudaStream_t s) {
+    if (nbytes == 0) return cudaSuccess;
+    const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
+    const uint64_t nsuper = (ntiles + LT_TILES - 1) / LT_TILES;
+    const size_t dyn = log_tiles_smem_bytes(lg.nbins);
+    cudaError_t e = cudaFuncSetAttribute((const void*)k_log_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_log_tiles, CT_THREADS, dyn);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)per_sm * sm_count;
+    if (grid > nsuper) grid = nsuper;
+    k_log_tiles<<<(unsigned)grid, CT_THREADS, dyn, s>>>(d_recs, ntiles, k, canonical, lg, t);
+    return cudaGetLastError();
+}
+
+// ---- phase 2 ------------------------------------------------------------------------------------------------
+constexpr int RP_THREADS = 256;
+constexpr int RP_PER_THREAD = 8;
+constexpr int RP_CHUNK = RP_THREADS * RP_PER_THREAD;
+
+// chunk_start[q] for segments in bin-major order: q = lp * nsrc + src <-> log segment src * nlocal + lp
+__global__ void __launch_bounds__(1024)
+k_log_plan(const unsigned int* __restrict__ cursor, unsigned cap, unsigned nsrc, unsigned nlocal,
+           unsigned long long* __restrict__ chunk_start) {
+    __shared__ unsigned long long part[1024];
+    const unsigned nseg = nsrc * nlocal;
+    const unsigned per = (nseg + 1023) / 1024;
+    const unsigned q0 = threadIdx.x * per, q1 = min(q0 + per, nseg);
+    unsigned long long sum = 0;
+    for (unsigned q = q0; q < q1; q++) {
+        const unsigned c = min(cursor[(q % nsrc) * nlocal + q / nsrc], cap);
+        sum += (c + RP_CHUNK - 1) / RP_CHUNK;
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long v = threadIdx.x >= o ? part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[threadIdx.x] - sum;    // exclusive prefix
+    for (unsigned q = q0; q < q1; q++) {
+        chunk_start[q] = run;
+        const unsigned c = min(cursor[(q % nsrc) * nlocal + q / nsrc], cap);
+        run += (c + RP_CHUNK - 1) / RP_CHUNK;
+    }
+    if (threadIdx.x == 1023) chunk_start[nseg] = part[1023];
+}
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(RP_THREADS, 4)
+k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
+             unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global,
+             const unsigned long long* __restrict__ chunk_start, TableView t, int prefetch) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned nseg = nsrc * nlocal;
+    const unsigned long long total = chunk_start[nseg];
+    unsigned claimed = 0;
+    unsigned q = 0, last_lp = 0xFFFFFFFFu;
+    for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
+        while (chunk_start[q + 1] <= w) q++;
+        const unsigned lp = q / nsrc, src = q % nsrc;
+        const unsigned seg = src * nlocal + lp;
+        const unsigned n = min(cursor[seg], cap);
+        const unsigned long long* base = keys + (unsigned long long)seg * cap;
+        const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
+
+        if (prefetch && lp != last_lp) {
+            // first chunk this CTA sees of bin lp: pull this CTA's slice of the NEXT bin's partitions into L2
+            last_lp = lp;
+            if (tid == 0 && lp + 1 < nlocal) {
+                const unsigned long long gb = (unsigned long long)bin0 + lp + 1;                 // global bin
+                const unsigned long long p_lo = gb * t.g.nparts / nbins_global;
+                const unsigned long long p_prev = (gb - 1) * t.g.nparts / nbins_global;
+                unsigned long long p_hi = ((gb + 1) * t.g.nparts - 1) / nbins_global;
+                if ((p_lo != p_prev || t.g.nparts >= nbins_global) && p_lo >= t.g.part0) {
+                    if (p_hi >= (unsigned long long)t.g.part0 + t.g.nlocal) p_hi = (unsigned long long)t.g.part0 + t.g.nlocal - 1;
+                    const unsigned long long r0 = (p_lo - t.g.part0) * t.g.subcap * sizeof(Slot);
+                    const unsigned long long r1 = (p_hi + 1 - t.g.part0) * t.g.subcap * sizeof(Slot);
+                    unsigned long long slice = ((r1 - r0) / gridDim.x + 127ull) & ~127ull;
+                    unsigned long long a = r0 + slice * blockIdx.x, e = a + slice;
+                    if (e > r1) e = r1;
+                    const char* tb = reinterpret_cast<const char*>(t.slots);
+                    for (; a < e; a += 16384) prefetch_l2_bulk(tb + a, (unsigned)((e - a) < 16384ull ? (e - a) : 16384ull));
+                }
+            }
+        }
+
+#pragma unroll 1
+        for (int g = 0; g < RP_PER_THREAD; g += 4) {
+            unsigned long long key[4], cur[4];
+            unsigned cnt[4];
+            Probe pr[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned i = i0 + (g + u) * RP_THREADS + tid;
+                const unsigned long long e = i < n ? __ldcs(base + i) : 0ull;
+                key[u] = e & ~LOG_RUN_FLAG;
+                cnt[u] = (e & LOG_RUN_FLAG) ? LOG_RUN : 1u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (key[u] != 0ull) {
+                    if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
+                    else { key[u] = 0ull; atomicExch(t.error, 2); }
+                }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (key[u] != 0ull) {
+                    Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
+                    if (sl) atomicAdd(&sl->val, cnt[u]);
+                }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+    if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
+}
+
+cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                              unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
+                              TableView t, int prefetch, int sm_count, cudaStream_t s) {
+    if (nsrc == 0 || nlocal == 0) return cudaSuccess;
+    k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, nlocal, d_chunk_start);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int grid = max_resident_ctas((const void*)k_log_replay, RP_THREADS, 0, -1) ;
+    k_log_replay<<<grid > 0 ? grid : sm_count, RP_THREADS, 0, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global,
+                                                                  d_chunk_start, t, prefetch);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
 // (packed key, value) pairs and rehash
 // =========================================================================================================
+template <bool IS_MAX>
 __global__ void __launch_bounds__(256)
 k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n, int k,
              int canonical, TableView t) {
@@ -206,18 +490,19 @@ k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ val
             const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
             key = kr < key ? kr : key;
         }
-        table_add(t, key, vals[i], claimed);
+        table_update<IS_MAX>(t, key, vals[i], claimed);
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
 }
 
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
-                              TableView t, cudaStream_t s) {
+                              TableView t, int is_label, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    k_load_pairs<<<(int)blocks, 256, 0, s>>>(d_keys, d_vals, n, k, canonical, t);
+    if (is_label) k_load_pairs<true><<<(int)blocks, 256, 0, s>>>(d_keys, d_vals, n, k, canonical, t);
+    else k_load_pairs<false><<<(int)blocks, 256, 0, s>>>(d_keys, d_vals, n, k, canonical, t);
     return cudaGetLastError();
 }
 
@@ -228,10 +513,7 @@ k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_
         const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
         if (key == 0ull) continue;
-        unsigned long long idx = home_slot(key, to.cap);
-        unsigned long long cur = __ldcg(&to.slots[idx].key);
-        Slot* sl = table_upsert_slot(to, key, idx, cur, claimed);
-        if (sl) { if (is_label) atomicMax(&sl->val, s.z); else atomicAdd(&sl->val, s.z); }
+        if (is_label) table_update<true>(to, key, s.z, claimed); else table_update<false>(to, key, s.z, claimed);
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
@@ -311,7 +593,7 @@ __device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v
 // ---------------------------------------------------------------------------------------------------------
 template <int GS>
 __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, int L, int k, int canonical,
-                                               const Slot* __restrict__ slots, uint64_t cap, uint32_t* P0,
+                                               const Slot* __restrict__ slots, Geo geo, uint32_t* P0,
                                                uint32_t* P1, uint32_t* PB, uint32_t* cov, float* sq,
                                                unsigned long long* red, uint32_t* per_kmer, uint32_t& median,
                                                float& mean, float& stdev, int gtid) {
@@ -338,7 +620,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
                 const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
                 key = kr < key ? kr : key;
             }
-            v = table_lookup(slots, cap, key);
+            v = table_lookup(slots, geo, key);
         }
         if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
         cov[p] = v;
@@ -384,7 +666,7 @@ struct PerReadSmem {
 
 __global__ void __launch_bounds__(PR_WARPS * 32)
 k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
-            int k, int canonical, const Slot* __restrict__ slots, uint64_t cap, uint32_t* __restrict__ median,
+            int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
             float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll) {
     __shared__ PerReadSmem sm;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -402,18 +684,18 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
         return;
     }
     uint32_t med; float mu, sd;
-    read_cov_stats<32>(recs + (o0 - rec_base), L, k, canonical, slots, cap, sm.p0[w], sm.p1[w], sm.pb[w], sm.a[w],
+    read_cov_stats<32>(recs + (o0 - rec_base), L, k, canonical, slots, geo, sm.p0[w], sm.p1[w], sm.pb[w], sm.a[w],
                        reinterpret_cast<float*>(sm.a[w] + PR_MAXWIN), nullptr,
                        per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, lane);
     if (lane == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
 }
 
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                             int canonical, const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean,
+                             int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                              float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s) {
     if (nreads == 0) return cudaSuccess;
     const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
-    k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, cap,
+    k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
                                                            d_median, d_mean, d_stdev, d_per_kmer, ll);
     return cudaGetLastError();
 }
@@ -433,7 +715,7 @@ size_t assign_long_scratch_bytes(unsigned max_win, int k, int nctas) {
 
 __global__ void __launch_bounds__(LONG_THREADS)
 k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k,
-                 int canonical, const Slot* __restrict__ slots, uint64_t cap, uint32_t* __restrict__ median,
+                 int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
                  float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer,
                  const unsigned int* __restrict__ long_idx, unsigned int n_long, unsigned int max_win,
                  uint32_t* scratch, size_t words_per_cta) {
@@ -448,7 +730,7 @@ k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ 
         const uint64_t o0 = offs[r], o1 = offs[r + 1];
         const int L = (int)(o1 - o0 - 1);
         uint32_t med; float mu, sd;
-        read_cov_stats<LONG_THREADS>(recs + (o0 - rec_base), L, k, canonical, slots, cap, P0, P1, PB, cov, sq, red,
+        read_cov_stats<LONG_THREADS>(recs + (o0 - rec_base), L, k, canonical, slots, geo, P0, P1, PB, cov, sq, red,
                                      per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, threadIdx.x);
         if (threadIdx.x == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
         __syncthreads();
@@ -456,11 +738,11 @@ k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ 
 }
 
 cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
-                                  const Slot* slots, uint64_t cap, uint32_t* d_median, float* d_mean, float* d_stdev,
+                                  const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
                                   unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
     if (n_long == 0) return cudaSuccess;
-    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, cap, d_median, d_mean,
+    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
                                                     d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
                                                     (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1));
     return cudaGetLastError();
@@ -482,7 +764,7 @@ __device__ __forceinline__ bool window_entropy_ok(const uint8_t* __restrict__ lu
 
 template <int GS>
 __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int L, int k, int strand,
-                                            const Slot* __restrict__ slots, uint64_t cap,
+                                            const Slot* __restrict__ slots, Geo geo,
                                             const uint8_t* __restrict__ lut, uint32_t* P0, uint32_t* P1, uint32_t* PB,
                                             int32_t* hits, unsigned int* nhits_p, int32_t& best, int32_t& score,
                                             int32_t& pct, int gtid) {
@@ -501,11 +783,11 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
         const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
         const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
         if (window_entropy_ok(lut, f0, f1, mk, false)) {
-            const unsigned v = table_lookup(slots, cap, make_key(f0, f1));
+            const unsigned v = table_lookup(slots, geo, make_key(f0, f1));
             if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
         }
         if (!strand && window_entropy_ok(lut, f0, f1, mk, true)) {
-            const unsigned v = table_lookup(slots, cap, make_key(rc_plane(f0, k), rc_plane(f1, k)));
+            const unsigned v = table_lookup(slots, geo, make_key(rc_plane(f0, k), rc_plane(f1, k)));
             if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
         }
     }
@@ -555,7 +837,7 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
 
 __global__ void __launch_bounds__(PR_WARPS * 32)
 k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int k,
-         int strand, const Slot* __restrict__ slots, uint64_t cap, const uint8_t* __restrict__ lut,
+         int strand, const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut,
          int32_t* __restrict__ best, int32_t* __restrict__ pct, int32_t* __restrict__ score, LongList ll) {
     __shared__ PerReadSmem sm;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -573,24 +855,24 @@ k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, ui
         return;
     }
     int32_t b, sc, pc;
-    read_assign<32>(recs + (o0 - rec_base), L, k, strand, slots, cap, lut, sm.p0[w], sm.p1[w], sm.pb[w],
+    read_assign<32>(recs + (o0 - rec_base), L, k, strand, slots, geo, lut, sm.p0[w], sm.p1[w], sm.pb[w],
                     reinterpret_cast<int32_t*>(sm.a[w]), &sm.nhits[w], b, sc, pc, lane);
     if (lane == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
 }
 
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                          int strand, const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok, int32_t* d_best,
+                          int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                           int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s) {
     if (nreads == 0) return cudaSuccess;
     const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
-    k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, cap,
+    k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, geo,
                                                         d_entropy_ok, d_best, d_pct, d_score, ll);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(LONG_THREADS)
 k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k, int strand,
-              const Slot* __restrict__ slots, uint64_t cap, const uint8_t* __restrict__ lut, int32_t* __restrict__ best,
+              const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut, int32_t* __restrict__ best,
               int32_t* __restrict__ pct, int32_t* __restrict__ score, const unsigned int* __restrict__ long_idx,
               unsigned int n_long, unsigned int max_win, uint32_t* scratch, size_t words_per_cta) {
     __shared__ unsigned int nhits;
@@ -603,7 +885,7 @@ k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
         const uint64_t o0 = offs[r], o1 = offs[r + 1];
         const int L = (int)(o1 - o0 - 1);
         int32_t b, sc, pc;
-        read_assign<LONG_THREADS>(recs + (o0 - rec_base), L, k, strand, slots, cap, lut, P0, P1, PB, hits, &nhits, b, sc,
+        read_assign<LONG_THREADS>(recs + (o0 - rec_base), L, k, strand, slots, geo, lut, P0, P1, PB, hits, &nhits, b, sc,
                                   pc, threadIdx.x);
         if (threadIdx.x == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
         __syncthreads();
@@ -611,11 +893,11 @@ k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
 }
 
 cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
-                               const Slot* slots, uint64_t cap, const uint8_t* d_entropy_ok, int32_t* d_best,
+                               const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                                int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
                                unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
     if (n_long == 0) return cudaSuccess;
-    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, cap, d_entropy_ok, d_best,
+    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
                                                  d_pct, d_score, d_long_idx, n_long, max_win, (uint32_t*)d_scratch,
                                                  long_scratch_words(max_win, k, 2));
     return cudaGetLastError();

@@ -1,0 +1,204 @@
+"""Hash-sharded k-mer counting across the GPUs of one box: one process per GPU, torch.distributed for
+the plumbing, libtrinity_gpu for every k-mer.
+
+  reads  shard by input offset: rank r counts the records starting in [r*S/n, (r+1)*S/n)  (`record_range`)
+  table  shards by hash: the global table is `nparts = world * lp` partitions; rank r holds partitions
+         [r*lp, (r+1)*lp) (tg_table_create_sharded).  Prior art for owner = f(canonical k-mer) mod n:
+         Inchworm/src/mpi_deprecated/MPIinchworm.cpp:1236-1257 -- there one blocking MPI_Send per k-mer (:519-531).
+
+  count     phase 1 on every rank appends each k-mer occurrence to the log bin of its partition
+            (tg_count_partition_dev; bins [d*lp, (d+1)*lp) are rank d's), ONE equal-split all-to-all moves the
+            bins to their owners (NCCL over NVLink), phase 2 replays the received bins into the shard
+            (tg_table_replay_log_dev).
+  queries   the shards are all-gathered once into a full replica per GPU (`replicate`), because the
+            concatenation of the shards' slot arrays IS the full table; coverage statistics / lookups then run
+            locally with no per-batch communication (SURVEY §8e "all-gather once" branch).
+
+The exchange logic is independent of where the k-mers are computed: `ShardedKmerCounter` drives an *engine*.  The
+product engine is `DeviceEngine` (CUDA).  The CPU test-suite drives the same class over gloo with a stand-in
+engine defined in tests/ -- there is no CPU engine in this package.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .api import KmerCounter
+
+TARGET_LOAD = 0.45
+MAX_BINS = 8192
+
+
+def record_range(offs_or_total, rank, world):
+    """Records [r0, r1) of rank `rank`: those whose first byte lies in [rank*S/world, (rank+1)*S/world), S = total
+    bytes.  `offs_or_total` is the offs array of a record buffer (len n+1)."""
+    offs = np.asarray(offs_or_total, dtype=np.uint64)
+    total = int(offs[-1])
+    lo = total * rank // world
+    hi = total * (rank + 1) // world
+    r0 = int(np.searchsorted(offs[:-1], lo, side="left"))
+    r1 = int(np.searchsorted(offs[:-1], hi, side="left"))
+    return r0, r1
+
+
+def shard_geometry(world, expected_keys_per_rank, part_bytes=32 << 20):
+    """-> (slots_per_partition, nparts, lp): lp partitions per rank, each about part_bytes (the L2 blocking unit)."""
+    slots = max(int(expected_keys_per_rank / TARGET_LOAD) + 1, 4096)
+    lp = 1
+    while lp * world * 2 <= MAX_BINS and slots * 16 / lp > part_bytes:
+        lp *= 2
+    subcap = (slots + lp - 1) // lp
+    return subcap, world * lp, lp
+
+
+def log_capacity(nbytes, nbins, slack=1.2):
+    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window)"""
+    return int(nbytes / nbins * slack) + 1024
+
+
+class DeviceEngine:
+    """libtrinity_gpu behind the engine interface; buffers are torch CUDA tensors (torch = device memory + NCCL)."""
+
+    def __init__(self, ctx, k, canonical):
+        import torch
+        self.torch = torch
+        self.ctx, self.k, self.canonical = ctx, k, bool(canonical)
+        self.device = torch.device("cuda", ctx.device)
+        self.table = None
+
+    # -- table shard ------------------------------------------------------------------------------------
+    def create_shard(self, subcap, nparts, part0, nlocal):
+        self.table = KmerCounter.sharded(self.ctx, self.k, self.canonical, subcap, nparts, part0, nlocal)
+        return self.table
+
+    def new_log(self, nbins, cap):
+        t = self.torch
+        keys = t.empty((nbins, cap), dtype=t.int64, device=self.device)
+        cursor = t.zeros((nbins,), dtype=t.int32, device=self.device)
+        return keys, cursor
+
+    def reset_log(self, cursor):
+        cursor.zero_()
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def partition(self, d_recs, nbytes, keys, cursor):
+        """phase 1: record buffer in HBM -> log bins"""
+        nbins, cap = keys.shape
+        check(_lib.lib().tg_count_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(self.canonical), nbins, cap,
+                                                C.c_void_p(keys.data_ptr()), C.c_void_p(cursor.data_ptr())))
+        self.ctx.sync()          # the exchange runs on torch's stream: hand over with a host sync
+
+    def replay(self, keys, cursor, nsrc):
+        """phase 2: received log [nsrc, lp, cap] -> this rank's shard"""
+        cap = keys.shape[-1]
+        self.torch.cuda.current_stream(self.device).synchronize()
+        check(_lib.lib().tg_table_replay_log_dev(self.table._h, C.c_void_p(keys.data_ptr()),
+                                                 C.c_void_p(cursor.data_ptr()), nsrc, cap))
+
+    def shard_slots(self):
+        """the shard's slot array as a flat torch uint8 tensor aliasing the table memory"""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().tg_table_slots_dev(self.table._h, C.byref(p), C.byref(n)))
+        return _alias_tensor(self.torch, p.value, n.value, self.device)
+
+    def full_table(self, subcap, nparts):
+        full = KmerCounter.sharded(self.ctx, self.k, self.canonical, subcap, nparts, 0, nparts)
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().tg_table_slots_dev(full._h, C.byref(p), C.byref(n)))
+        return full, _alias_tensor(self.torch, p.value, n.value, self.device)
+
+    def local_distinct(self):
+        return self.table.size()
+
+    def local_histo(self):
+        return self.table.histo()
+
+    def local_dump(self, min_count=1):
+        return self.table.dump(min_count=min_count)
+
+    def scalar_tensor(self, values, dtype):
+        return self.torch.tensor(values, dtype=dtype, device=self.device)
+
+
+class _CudaAlias:
+    """__cuda_array_interface__ view of raw device memory, so torch can wrap a libtrinity_gpu allocation"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _alias_tensor(torch, ptr, nbytes, device):
+    return torch.as_tensor(_CudaAlias(ptr, nbytes), device=device)
+
+
+class ShardedKmerCounter:
+    """KmerCounter whose table is sharded by hash over the ranks of a torch.distributed process group."""
+
+    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=32 << 20, dist=None):
+        if dist is None:
+            import torch.distributed as dist
+        self.dist, self.group, self.eng = dist, group, engine
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.subcap, self.nparts, self.lp = shard_geometry(self.world, expected_keys_per_rank, part_bytes)
+        self.table = engine.create_shard(self.subcap, self.nparts, self.rank * self.lp, self.lp)
+        self._log = None
+        self._recv = None
+
+    def owner_of_bin(self, b):
+        return b // self.lp
+
+    def _buffers(self, nbytes):
+        # the exchange is an equal-split all-to-all: every rank must lay its log out for the largest batch
+        m = self.eng.scalar_tensor([int(nbytes)], _int64(self.eng))
+        self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
+        cap = log_capacity(int(m.item()), self.nparts)
+        if self._log is None or self._log[0].shape[1] < cap:
+            self._log = self.eng.new_log(self.nparts, cap)
+            self._recv = self.eng.new_log(self.nparts, cap)      # same bytes, viewed [world, lp, cap]
+        else:
+            self.eng.reset_log(self._log[1])
+        return self._log, self._recv
+
+    def add_records_dev(self, d_recs, nbytes):
+        """count every k-mer of this rank's record buffer into the sharded table (collective: all ranks call it)"""
+        (keys, cur), (rkeys, rcur) = self._buffers(nbytes)
+        self.eng.partition(d_recs, nbytes, keys, cur)
+        # bins [d*lp, (d+1)*lp) go to rank d: an equal-split all-to-all over dim 0
+        self.dist.all_to_all_single(rcur, cur, group=self.group)
+        self.dist.all_to_all_single(rkeys, keys, group=self.group)
+        self.eng.replay(rkeys, rcur, self.world)
+
+    def size(self):
+        """distinct k-mers in the global table"""
+        t = self.eng.scalar_tensor([self.eng.local_distinct()], _int64(self.eng))
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def histo(self):
+        """jellyfish histo of the global table = sum of the shards' histograms"""
+        h = self.eng.local_histo()
+        t = self.eng.scalar_tensor(np.asarray(h, dtype=np.int64).tolist(), _int64(self.eng))
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def dump_local(self, min_count=1):
+        """this rank's part of `jellyfish dump` (sorted); the global dump is the merge of all ranks' parts"""
+        return self.eng.local_dump(min_count)
+
+    def replicate(self):
+        """all-gather the shards into a full table on every rank -> KmerCounter for local queries"""
+        full, full_bytes = self.eng.full_table(self.subcap, self.nparts)
+        mine = self.eng.shard_slots()
+        self.dist.all_gather_into_tensor(full_bytes, mine, group=self.group)
+        if hasattr(self.eng, "torch"):
+            self.eng.torch.cuda.current_stream(self.eng.device).synchronize()
+        full.set_distinct(self.size())
+        return full
+
+
+def _int64(eng):
+    if hasattr(eng, "torch"):
+        return eng.torch.int64
+    import torch
+    return torch.int64
