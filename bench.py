@@ -39,13 +39,13 @@ SEED = 20251017
 # ---------------------------------------------------------------------------------------------------------
 # synthetic transcriptome (host, numpy) -- reads themselves are generated on the device from it
 # ---------------------------------------------------------------------------------------------------------
-def make_transcriptome(ntx, seed):
+def make_transcriptome(ntx, seed, sigma=2.0):
     rng = np.random.default_rng(seed)
     lens = np.clip(np.round(rng.lognormal(np.log(1500), 0.6, ntx)), 300, 10000).astype(np.int64)
     offs = np.zeros(ntx + 1, dtype=np.uint64)
     offs[1:] = np.cumsum(lens)
     tx = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(offs[-1]))]
-    w = rng.lognormal(0.0, 2.0, ntx) * lens          # expression x length = share of fragments
+    w = rng.lognormal(0.0, sigma, ntx) * lens          # expression x length = share of fragments
     cum = np.cumsum(w / w.sum())
     cum_u64 = np.minimum(cum * 2.0 ** 64, 2.0 ** 64 - 2048).astype(np.uint64)
     cum_u64[-1] = np.uint64(2 ** 64 - 1)

@@ -103,7 +103,9 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
             next_off = offs[lo + 1];
         }
 
-        if (ab != FULL || cb != FULL) {
+        const bool has_windows = ab != FULL || cb != FULL;
+        const unsigned act = __ballot_sync(FULL, has_windows);   // the lanes that enter the loop below together
+        if (has_windows) {
 #pragma unroll 1
             for (int g = 0; g < 32; g += 4) {
                 unsigned long long key[4];
@@ -152,6 +154,7 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                             else atomicMax(&sl->val, lab[u]);
                         }
                     }
+                __syncwarp(act);   // lanes leave the probe loops at different times: reconverge before the next group
             }
         }
         __syncthreads();   // planes consumed before the next iteration overwrites them
@@ -455,6 +458,8 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
                     Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
                     if (sl) atomicAdd(&sl->val, cnt[u]);
                 }
+            __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
+                            // and every later log load / probe is issued once per lane subset
         }
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
@@ -608,24 +613,31 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
     gsync<GS>();
 
     unsigned long long part = 0;
-    for (int p = gtid; p < nwin; p += GS) {
-        const int c = p >> 5, o = p & 31;
-        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+    for (int pb = 0; pb < nwin; pb += GS) {     // every lane runs every iteration, so the warp can reconverge in it
+        const int p = pb + gtid;
+        const bool live = p < nwin;
         unsigned v = 0;
-        if (!bad) {
-            const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-            const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-            unsigned long long key = make_key(f0, f1);
-            if (canonical) {
-                const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
-                key = kr < key ? kr : key;
+        if (live) {
+            const int c = p >> 5, o = p & 31;
+            const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+            if (!bad) {
+                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+                unsigned long long key = make_key(f0, f1);
+                if (canonical) {
+                    const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                    key = kr < key ? kr : key;
+                }
+                v = table_lookup(slots, geo, key);
             }
-            v = table_lookup(slots, geo, key);
         }
-        if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
-        cov[p] = v;
-        if (per_kmer) per_kmer[p] = v;
-        part += v;
+        __syncwarp();                              // probe loops end at different times per lane
+        if (live) {
+            if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
+            cov[p] = v;
+            if (per_kmer) per_kmer[p] = v;
+            part += v;
+        }
     }
     const unsigned long long sum = group_sum_u64<GS>(part, red, gtid);   // `long` sum, exact
     const float avg = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));
@@ -776,20 +788,25 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
     if (gtid == 0) *nhits_p = 0;
     pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
     gsync<GS>();
-    for (int p = gtid; p < nwin; p += GS) {
-        const int c = p >> 5, o = p & 31;
-        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
-        if (bad) continue;              // a window with a non-ACGT character can never equal a table k-mer
-        const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-        const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-        if (window_entropy_ok(lut, f0, f1, mk, false)) {
-            const unsigned v = table_lookup(slots, geo, make_key(f0, f1));
-            if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
+    for (int pb = 0; pb < nwin; pb += GS) {
+        const int p = pb + gtid;
+        if (p < nwin) {
+            const int c = p >> 5, o = p & 31;
+            const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+            if (!bad) {                     // a window with a non-ACGT character can never equal a table k-mer
+                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+                if (window_entropy_ok(lut, f0, f1, mk, false)) {
+                    const unsigned v = table_lookup(slots, geo, make_key(f0, f1));
+                    if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
+                }
+                if (!strand && window_entropy_ok(lut, f0, f1, mk, true)) {
+                    const unsigned v = table_lookup(slots, geo, make_key(rc_plane(f0, k), rc_plane(f1, k)));
+                    if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
+                }
+            }
         }
-        if (!strand && window_entropy_ok(lut, f0, f1, mk, true)) {
-            const unsigned v = table_lookup(slots, geo, make_key(rc_plane(f0, k), rc_plane(f1, k)));
-            if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
-        }
+        __syncwarp();                       // probe loops end at different times per lane
     }
     gsync<GS>();
     const int n = (int)*nhits_p;
