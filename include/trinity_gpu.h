@@ -137,11 +137,16 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
  *       caller-owned log: d_keys [nbins][cap] u64, d_cursor [nbins] u32 (zeroed by the caller).  nbins must equal
  *       the table's global partition count, so bins [r*nlocal, (r+1)*nlocal) are exactly what rank r owns and
  *       one equal-split all-to-all of d_keys / d_cursor routes every k-mer to its owner.  A bin overflow is
- *       reported by the next tg_sync.
- *   tg_table_replay_log_dev  inserts a received log [nsrc][nlocal][cap] (+ cursors [nsrc][nlocal]) into the shard. */
+ *       reported by the next tg_sync.  Homopolymer windows (poly-A tails...) bypass the log: d_hpoly is 8 u64,
+ *       zeroed by the caller -- [0..3] table keys of A^k, C^k, G^k, T^k, [4..7] their occurrence counts; sum the
+ *       counts (and max the keys) over ranks before the replay.
+ *   tg_table_replay_log_dev  inserts a received log [nsrc][nlocal][cap] (+ cursors [nsrc][nlocal]) into the shard,
+ *       plus the homopolymer tallies whose partition the shard holds (d_hpoly may be NULL; its counts are
+ *       cleared). */
 int tg_count_partition_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
-                           uint32_t cap, void* d_keys, void* d_cursor);
-int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t cap);
+                           uint32_t cap, void* d_keys, void* d_cursor, void* d_hpoly);
+int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, void* d_hpoly, uint32_t nsrc,
+                            uint32_t cap);
 int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
                      void* d_median, void* d_mean, void* d_stdev);
 int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,

@@ -87,15 +87,22 @@ class StandinEngine:
         return self.table
 
     def new_log(self, nbins, cap):
-        return torch.zeros((nbins, cap), dtype=torch.int64), torch.zeros((nbins,), dtype=torch.int32)
+        return (torch.zeros((nbins, cap), dtype=torch.int64), torch.zeros((nbins,), dtype=torch.int32),
+                torch.zeros((8,), dtype=torch.int64))
 
-    def reset_log(self, cursor):
+    def reset_log(self, cursor, hpoly):
         cursor.zero_()
+        hpoly.zero_()
 
-    def partition(self, recs, nbytes, keys, cursor):
+    def partition(self, recs, nbytes, keys, cursor, hpoly):
         nbins, cap = keys.shape
         ok, oc = orc.jf_count(np.asarray(recs[:nbytes]), self.k, self.canonical, 1)
+        homo = {0: 0, (1 << (2 * self.k)) - 1: 3}      # A^k and T^k as packed k-mers -> side-channel slot
         for key, c in zip(ok.tolist(), oc.tolist()):
+            if key in homo:                         # homopolymers travel as (key, count), like on the device
+                hpoly[homo[key]] = -(key + 1)       # negative, like a device key with its tag bit
+                hpoly[4 + homo[key]] += c
+                continue
             b = key_bin(key, nbins)
             for _ in range(c):                      # one log entry per occurrence, like the device log
                 pos = int(cursor[b])
@@ -103,8 +110,16 @@ class StandinEngine:
                 keys[b, pos] = key + 1
                 cursor[b] += 1
 
-    def replay(self, keys, cursor, nsrc):
+    def replay(self, keys, cursor, hpoly, nsrc):
         lp = self.table.nlocal
+        for i in range(4):
+            n = int(hpoly[4 + i])
+            if n:
+                key = -int(hpoly[i]) - 1
+                b = key_bin(key, self.table.nparts)
+                if self.table.part0 <= b < self.table.part0 + self.table.nlocal:
+                    self.table.add(key, n)
+                hpoly[4 + i] = 0
         keys = keys.reshape(nsrc, lp, -1)
         cursor = cursor.reshape(nsrc, lp)
         for s in range(nsrc):

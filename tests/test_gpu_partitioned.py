@@ -127,25 +127,33 @@ def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
     nbytes_max = max(int(offs[r1] - offs[r0]) for r0, r1 in ranges)
     cap = tg.sharded.log_capacity(nbytes_max, nparts)
     logs, curs = [], []
+    hpoly = ctx.dev_alloc(64)
+    ctx.memset(hpoly, 0, 64)
     for r, (r0, r1) in enumerate(ranges):
         sub = recs[int(offs[r0]):int(offs[r1])]
         d = _dev_records(ctx, sub)
         keys = ctx.dev_alloc(nparts * cap * 8)
         cur = ctx.dev_alloc(nparts * 4)
         ctx.memset(cur, 0, nparts * 4)
-        shards[r].partition_dev(d, sub.nbytes, nparts, cap, keys, cur)
+        shards[r].partition_dev(d, sub.nbytes, nparts, cap, keys, cur, hpoly)
         ctx.sync()
         ctx.dev_free(d)
         logs.append(keys)
         curs.append(cur)
+    # (the homopolymer side channel accumulated over all ranks = the all-reduce of the real exchange)
+    hp_host = ctx.d2h(hpoly, 64, np.uint64)
+    assert hp_host[4] > 0 and hp_host[7] > 0          # the poly-A and poly-T reads of the fixture
     for dst in range(world):
         rkeys = ctx.dev_alloc(nparts * cap * 8)       # [world][lp][cap]
         rcur = ctx.dev_alloc(nparts * 4)
         for src in range(world):
             ctx.d2d(rkeys, logs[src], lp * cap * 8, dst_off=src * lp * cap * 8, src_off=dst * lp * cap * 8)
             ctx.d2d(rcur, curs[src], lp * 4, dst_off=src * lp * 4, src_off=dst * lp * 4)
-        shards[dst].replay_log_dev(rkeys, rcur, world, cap)
+        hp_d = ctx.dev_alloc(64)                       # every rank applies its own copy of the global tallies
+        ctx.h2d(hp_d, hp_host)
+        shards[dst].replay_log_dev(rkeys, rcur, hp_d, world, cap)
         ctx.sync()
+        ctx.dev_free(hp_d)
         ctx.dev_free(rkeys)
         ctx.dev_free(rcur)
     assert sum(s.size() for s in shards) == len(ok)
@@ -182,7 +190,7 @@ def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
         shards[0].size()
     for t in shards + [full]:
         t.close()
-    for p in logs + curs:
+    for p in logs + curs + [hpoly]:
         ctx.dev_free(p)
 
 
@@ -193,12 +201,14 @@ def test_partition_log_overflow_is_reported(ctx, data):
     nbins, cap = 8, 64                                  # far too small
     keys = ctx.dev_alloc(nbins * cap * 8)
     cur = ctx.dev_alloc(nbins * 4)
+    hp = ctx.dev_alloc(64)
     ctx.memset(cur, 0, nbins * 4)
+    ctx.memset(hp, 0, 64)
     with tg.KmerCounter(ctx, 25) as kc:
-        kc.partition_dev(d, recs.nbytes, nbins, cap, keys, cur)
+        kc.partition_dev(d, recs.nbytes, nbins, cap, keys, cur, hp)
         with pytest.raises(tg.TrinityGpuError) as e:
             ctx.sync()
         assert "overflow" in str(e.value)
     ctx.sync()                                          # the flag is cleared once reported
-    for p in (d, keys, cur):
+    for p in (d, keys, cur, hp):
         ctx.dev_free(p)

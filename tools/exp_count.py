@@ -59,17 +59,17 @@ for pm in [int(x) for x in args.parts.split(",")]:
     # phases separately through the sharded entry points (same kernels)
     subcap, nparts, p0, nl = kc.geometry()
     nbins = max(nparts, 512)
-    cap = int(nbytes / nbins * 1.2) + 1024
-    keys = ctx.dev_alloc(nbins * cap * 8); cur = ctx.dev_alloc(nbins * 4)
+    cap = tg.sharded.log_capacity(nbytes, nbins)
+    keys = ctx.dev_alloc(nbins * cap * 8); cur = ctx.dev_alloc(nbins * 4); hp = ctx.dev_alloc(64); ctx.memset(hp, 0, 64)
     def p1():
         ctx.memset(cur, 0, nbins * 4)
-        kc.partition_dev(d_recs, nbytes, nbins, cap, keys, cur)
+        kc.partition_dev(d_recs, nbytes, nbins, cap, keys, cur, hp)
     ms1 = timed(p1, 2)
     if nbins == nparts:
         kc.clear()
-        ms2 = timed(lambda: kc.replay_log_dev(keys, cur, 1, cap), 1)
+        ms2 = timed(lambda: kc.replay_log_dev(keys, cur, None, 1, cap), 1)
         kc.clear()
-        ms2 = min(ms2, timed(lambda: kc.replay_log_dev(keys, cur, 1, cap), 1))
+        ms2 = min(ms2, timed(lambda: kc.replay_log_dev(keys, cur, None, 1, cap), 1))
     else:
         ms2 = None
     curh = ctx.d2h(cur, nbins * 4, np.uint32)
@@ -79,12 +79,12 @@ for pm in [int(x) for x in args.parts.split(",")]:
     ctx.dev_free(keys); ctx.dev_free(cur)
     kc.close()
 for nb in [int(x) for x in args.p1bins.split(",") if x]:
-    cap = int(nbytes / nb * 1.2) + 1024
-    keys = ctx.dev_alloc(nb * cap * 8); cur = ctx.dev_alloc(nb * 4)
+    cap = tg.sharded.log_capacity(nbytes, nb)
+    keys = ctx.dev_alloc(nb * cap * 8); cur = ctx.dev_alloc(nb * 4); hp = ctx.dev_alloc(64); ctx.memset(hp, 0, 64)
     kc = tg.KmerCounter(ctx, K, True, expected_keys=1000)
     def p1():
         ctx.memset(cur, 0, nb * 4)
-        kc.partition_dev(d_recs, nbytes, nb, cap, keys, cur)
+        kc.partition_dev(d_recs, nbytes, nb, cap, keys, cur, hp)
     ms1 = timed(p1, 2)
     out.append({"mode": "phase1_only", "nbins": nb, "phase1_ms": ms1})
     print(json.dumps(out[-1]), flush=True)

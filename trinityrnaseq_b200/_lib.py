@@ -55,8 +55,8 @@ SIGNATURES = {
     "tg_memcpy_d2d": (_i32, [_vp, _vp, _vp, _u64]),
     "tg_memset_dev": (_i32, [_vp, _vp, _i32, _u64]),
     "tg_count_reads_dev": (_i32, [_vp, _vp, _u64, _i32]),
-    "tg_count_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp]),
-    "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _u32, _u32]),
+    "tg_count_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp, _vp]),
+    "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "tg_cov_stats_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),
     "tg_label_bundles_dev": (_i32, [_vp, _vp, _u64, _vp, _u64, _u32]),
     "tg_assign_reads_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),

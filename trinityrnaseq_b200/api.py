@@ -249,15 +249,15 @@ class KmerCounter(_Table):
         """the shard holding partitions [part0, part0+nlocal) of a table of nparts partitions"""
         return cls(ctx, k, is_ds, geometry=(slots_per_partition, nparts, part0, nlocal))
 
-    def partition_dev(self, d_recs, nbytes, nbins, cap, d_keys, d_cursor, canonical=None):
+    def partition_dev(self, d_recs, nbytes, nbins, cap, d_keys, d_cursor, d_hpoly, canonical=None):
         """phase 1 of the sharded count: k-mer occurrences -> caller-owned log bins (tg_count_partition_dev)"""
         can = self.is_ds if canonical is None else canonical
         check(_lib.lib().tg_count_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(can), nbins, cap, d_keys,
-                                                d_cursor))
+                                                d_cursor, d_hpoly))
 
-    def replay_log_dev(self, d_keys, d_cursor, nsrc, cap):
+    def replay_log_dev(self, d_keys, d_cursor, d_hpoly, nsrc, cap):
         """phase 2: received log [nsrc][nlocal][cap] -> this shard (tg_table_replay_log_dev)"""
-        check(_lib.lib().tg_table_replay_log_dev(self._h, d_keys, d_cursor, nsrc, cap))
+        check(_lib.lib().tg_table_replay_log_dev(self._h, d_keys, d_cursor, d_hpoly, nsrc, cap))
 
     def add_records(self, recs, canonical=None):
         """jellyfish count / KmerCounter::add_sequence over a record buffer."""

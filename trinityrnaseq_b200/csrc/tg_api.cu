@@ -84,6 +84,7 @@ struct KeyLog {
     unsigned long long* keys = nullptr;
     unsigned int* cursor = nullptr;
     unsigned long long* chunk_start = nullptr;
+    unsigned long long* hpoly = nullptr;   // [8] homopolymer side channel (keys, counts)
     unsigned nbins = 0, cap = 0;
     uint64_t pending_ub = 0;          // host-side upper bound on entries appended since the last replay
     uint64_t total_entries() const { return (uint64_t)nbins * cap; }
@@ -364,6 +365,7 @@ static void log_release(tg_table* t) {
     if (t->log.keys) cudaFree(t->log.keys);
     if (t->log.cursor) cudaFree(t->log.cursor);
     if (t->log.chunk_start) cudaFree(t->log.chunk_start);
+    if (t->log.hpoly) cudaFree(t->log.hpoly);
     t->log = KeyLog();
 }
 
@@ -387,7 +389,10 @@ int tg_table_clear(tg_table* t) {
     CU(cudaMemsetAsync(t->slots, 0, t->cap * sizeof(Slot), c->stream[0]));
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
     CU(cudaMemsetAsync(t->d_error, 0, sizeof(int), c->stream[0]));
-    if (t->log.cursor) CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
+    if (t->log.cursor) {
+        CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
+        CU(cudaMemsetAsync(t->log.hpoly, 0, 8 * sizeof(unsigned long long), c->stream[0]));
+    }
     t->log.pending_ub = 0;
     CU(cudaStreamSynchronize(c->stream[0]));
     t->distinct_ub = 0;
@@ -552,6 +557,9 @@ static bool log_pays(const tg_table* t, uint64_t nbytes) {
 constexpr uint64_t LOG_BIN_SLACK = 1024;    // additive head-room per bin (hash fluctuation of small batches)
 constexpr double LOG_BIN_FACTOR = 1.2;      // multiplicative head-room per bin (hot k-mers)
 
+// log entries one phase-1 launch over nbytes record bytes can take up at most: one per byte
+static uint64_t log_launch_cost(const tg_ctx*, const KeyLog&, uint64_t nbytes) { return nbytes; }
+
 // entries that can be appended to an empty log without any bin expected to overflow
 static uint64_t log_room(const KeyLog& lg) {
     if (lg.cap <= LOG_BIN_SLACK) return 0;
@@ -570,7 +578,8 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     if (t->log.keys) budget = std::max<uint64_t>(budget, t->log.total_entries() * 8);
     uint64_t per_bin = (uint64_t)((double)entries / nbins * LOG_BIN_FACTOR) + LOG_BIN_SLACK;
     per_bin = std::min<uint64_t>(per_bin, budget / 8 / nbins);
-    per_bin = std::min<uint64_t>(per_bin, 0xFFFFFF00ull);
+    per_bin = std::min<uint64_t>(per_bin, LOG_CAP_MAX);
+    per_bin = per_bin / LOG_CAP_ALIGN * LOG_CAP_ALIGN;
     if (per_bin < 2 * LOG_BIN_SLACK) return TG_OK;
     if (t->log.keys && t->log.nbins == nbins && t->log.cap >= per_bin) { *ok = true; return TG_OK; }
     if (t->log.pending_ub) { *ok = t->log.keys != nullptr; return TG_OK; }   // holds entries: keep its layout
@@ -578,7 +587,9 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     if (cudaMalloc(&t->log.keys, per_bin * nbins * 8) != cudaSuccess) { cudaGetLastError(); t->log.keys = nullptr; return TG_OK; }
     CU(cudaMalloc(&t->log.cursor, nbins * sizeof(unsigned int)));
     CU(cudaMalloc(&t->log.chunk_start, ((size_t)nbins + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&t->log.hpoly, 8 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(t->log.cursor, 0, nbins * sizeof(unsigned int), c->stream[0]));
+    CU(cudaMemsetAsync(t->log.hpoly, 0, 8 * sizeof(unsigned long long), c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[0]));
     t->log.nbins = nbins; t->log.cap = (unsigned)per_bin; t->log.pending_ub = 0;
     *ok = true;
@@ -586,14 +597,14 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
 }
 
 static LogView log_view(tg_table* t) {
-    return LogView{t->log.keys, t->log.cursor, t->log.nbins, t->log.cap, t->d_error};
+    return LogView{t->log.keys, t->log.cursor, t->log.nbins, t->log.cap, t->d_error, t->log.hpoly};
 }
 
 // replay + reset on stream 0 (stream-ordered; no host sync)
 static int replay_log_async(tg_table* t) {
     tg_ctx* c = t->ctx;
     CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, t->log.chunk_start,
-                         t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
+                         t->log.hpoly, t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
     c->launches += 2;
     CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
     t->log.pending_ub = 0;
@@ -621,8 +632,8 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     CU(cudaMalloc(&d_n, sizeof *d_n));
     CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, c->stream[0]));
     TableView sv{scratch, sg, d_n, t->d_error};
-    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, ns, 0, nbins, t->log.chunk_start, sv, 0, c->sm_count,
-                         c->stream[0]));
+    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, ns, 0, nbins, t->log.chunk_start, nullptr, sv, 0,
+                         c->sm_count, c->stream[0]));
     c->launches += 2;
     unsigned long long d = 0;
     CU(cudaMemcpyAsync(&d, d_n, sizeof d, cudaMemcpyDeviceToHost, c->stream[0]));
@@ -682,7 +693,9 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
         const uint64_t end = batch_end(recs, pos, nbytes, c->batch_bytes);
         const uint64_t n = end - pos;
         if (logged) {
-            if (t->log.pending_ub + n > room && t->log.pending_ub) { if ((rc = flush_log(t))) return rc; }
+            if (t->log.pending_ub + log_launch_cost(c, t->log, n) > room && t->log.pending_ub) {
+                if ((rc = flush_log(t))) return rc;
+            }
         } else {
             if ((rc = tg_table_reserve(t, n))) return rc;     // may rehash: syncs both streams itself
         }
@@ -691,7 +704,7 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
         if (logged) {
             CU(launch_log_tiles((const uint8_t*)c->recs[b].p, n, t->k, canonical, log_view(t), t->view(), c->sm_count,
                                 c->stream[b]));
-            t->log.pending_ub += n;
+            t->log.pending_ub += log_launch_cost(c, t->log, n);
         } else {
             CU(launch_count_tiles((const uint8_t*)c->recs[b].p, n, t->k, canonical, t->view(), c->sm_count, c->stream[b]));
         }
@@ -734,19 +747,23 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
 
 // ---- sharded counting (multi-GPU): phase 1 into a caller-owned log, phase 2 from a caller-owned (received) log ----
 int tg_count_partition_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
-                           uint32_t cap, void* d_keys, void* d_cursor) {
-    if (!c || !d_recs || !d_keys || !d_cursor) return fail(TG_ERR_ARG, "tg_count_partition_dev: null argument");
+                           uint32_t cap, void* d_keys, void* d_cursor, void* d_hpoly) {
+    if (!c || !d_recs || !d_keys || !d_cursor || !d_hpoly)
+        return fail(TG_ERR_ARG, "tg_count_partition_dev: null argument");
     if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
-    if (nbins == 0 || nbins > LOG_MAX_BINS || cap == 0) return fail(TG_ERR_ARG, "tg_count_partition_dev: bad log shape");
+    if (nbins == 0 || nbins > LOG_MAX_BINS || cap == 0 || cap > LOG_CAP_MAX)
+        return fail(TG_ERR_ARG, "tg_count_partition_dev: bad log shape (1..%u bins, capacity at most %u)", LOG_MAX_BINS,
+                    LOG_CAP_MAX);
     if (bind(c)) return TG_ERR_CUDA;
-    LogView lg{(unsigned long long*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error};
+    LogView lg{(unsigned long long*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error, (unsigned long long*)d_hpoly};
     TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
     return TG_OK;
 }
 
-int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t cap) {
+int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, void* d_hpoly, uint32_t nsrc,
+                            uint32_t cap) {
     if (!t || !d_keys || !d_cursor || nsrc == 0 || cap == 0) return fail(TG_ERR_ARG, "tg_table_replay_log_dev: bad argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_table_replay_log_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
@@ -754,8 +771,8 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
     const size_t need = ((size_t)nsrc * t->g.nlocal + 1) * sizeof(unsigned long long);
     CU(c->scratch.ensure(need));
     CU(launch_log_replay((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
-                         t->g.nparts, (unsigned long long*)c->scratch.p, t->view(), c->replay_prefetch, c->sm_count,
-                         c->stream[0]));
+                         t->g.nparts, (unsigned long long*)c->scratch.p, (unsigned long long*)d_hpoly, t->view(),
+                         c->replay_prefetch, c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;
 }

@@ -158,11 +158,8 @@ __device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots,
 // ---- k-mer log (partitioned count path) ------------------------------------------------------------------
 // Phase 1 appends every counted k-mer occurrence to the bin of its hash partition instead of touching the table;
 // phase 2 replays the log bin by bin, so the CAS/RED traffic of one bin stays inside an L2-resident group of
-// partitions.  An entry is the table key; bit 31 (never used by a key: planes are k <= 31 bits wide) marks a
-// run of LOG_RUN identical consecutive windows (homopolymers), so one entry can stand for 8 occurrences.
-constexpr unsigned long long LOG_RUN_FLAG = 1ull << 31;
-constexpr unsigned LOG_RUN = 8;
-
+// partitions.  An entry is the table key (0 = no entry).  Homopolymer windows never enter the log: they are
+// tallied per launch in hpoly[] (keys in [0..3], occurrence counts in [4..7], indexed by base code).
 struct LogView {
     unsigned long long* keys;   // [nbins][cap]
     unsigned int* cursor;       // [nbins] entries reserved so far; may run past cap (readers clamp, writers
@@ -170,6 +167,7 @@ struct LogView {
     unsigned int nbins;         // bins == partitions of the geometry the log was laid out for
     unsigned int cap;           // entries per bin
     int* error;                 // device flag raised (3) when a bin overflows and there is no table to fall back to
+    unsigned long long* hpoly;  // [8] homopolymer side channel
 };
 
 // ---- TMA (1-D bulk async copy) + mbarrier wrappers -----------------------------------------------------

@@ -45,13 +45,15 @@ cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uin
 // partitioned count path, phase 1: every valid window's key appended to the log bin of its hash partition
 // (t.slots may be null: then a full bin raises lg.error instead of counting directly)
 constexpr unsigned LOG_MAX_BINS = 8192;
+constexpr unsigned LOG_CAP_ALIGN = 16;                 // log bin capacity granularity (= entries per chunk)
+constexpr unsigned LOG_CAP_MAX = 0xF0000000u;           // per-bin cursors are 32-bit and may overshoot the capacity
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
                              int sm_count, cudaStream_t s);
 // phase 2: replay log segments [nsrc][nlocal][cap] (cursor [nsrc][nlocal]) bin-major into the table; the bins are
 // global bins bin0..bin0+nlocal-1 of nbins_global.  d_chunk_start: scratch of nsrc*nlocal+1 u64.
 cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
-                              TableView t, int prefetch, int sm_count, cudaStream_t s);
+                              unsigned long long* d_hpoly, TableView t, int prefetch, int sm_count, cudaStream_t s);
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);

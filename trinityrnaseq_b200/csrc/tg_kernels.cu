@@ -204,133 +204,194 @@ cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uin
 // read-modify-write per occurrence.  Multi-GPU counting uses the same two kernels with an all-to-all of the
 // bins between them (bin = global partition; rank r owns a contiguous range of bins).
 // =========================================================================================================
-constexpr int LT_TILES = 4;   // tiles per reservation round: 4 x 8 KiB of reads share one cursor reservation per bin
+// Phase 1 per 4 KiB tile of reads (256 threads, 16 windows each):
+//   A  every valid window: key -> bin = partition of its hash; rank = shared atomicAdd on the bin's 16-bit counter
+//      (two counters per word); (bin, rank) parked in shared memory
+//   S  exclusive scan of the counters (-> place of each bin's run in the sorted tile) and ONE global atomicAdd per
+//      non-empty bin reserving the run's place in the log -- all bins in parallel, one round trip per tile
+//   B  keys recomputed (cheap: four funnel shifts, two bit reversals) and scattered into the sorted tile
+//   W  the sorted tile streamed out: consecutive threads write consecutive entries of a run, so the stores of a
+//      warp cover a handful of sectors instead of 32
+// Homopolymer windows never enter the log (they would all hit one slot): they are tallied in registers and
+// leave through lg.hpoly as four (key, count) pairs.
+constexpr int LT_THREADS = 256;
+constexpr int LT_WIN = 16;                          // windows per thread
+constexpr int LT_TILE = LT_THREADS * LT_WIN;        // 4096 bases per tile
+constexpr int LT_LOAD = LT_TILE + CT_HALO;
+constexpr int LT_CHUNKS = LT_TILE / 32;             // 32-base plane words per tile
+static_assert(CT_TILE % LT_TILE == 0, "record buffers are padded to CT_TILE");
 
 struct LogSmem {
-    alignas(128) uint8_t ascii[2][CT_LOAD];
-    uint32_t p0[LT_TILES][CT_THREADS + 1];
-    uint32_t p1[LT_TILES][CT_THREADS + 1];
-    uint32_t pb[LT_TILES][CT_THREADS + 1];
+    alignas(128) uint8_t ascii[2][LT_LOAD];
+    uint32_t p0[LT_CHUNKS + 1];
+    uint32_t p1[LT_CHUNKS + 1];
+    uint32_t pb[LT_CHUNKS + 1];
+    uint32_t meta[LT_TILE];                         // bin << 12 | rank, ~0 = no entry
+    uint32_t wtot[LT_THREADS / 32];
+    uint32_t total;
     alignas(8) unsigned long long bar[2];
 };
 
-// every log entry of the 32 windows starting in one thread's chunk: runs of identical consecutive keys are
-// folded (LOG_RUN at a time), the rest emitted singly.  emit(entry, bin) is called once per entry.
-template <typename Emit>
-__device__ __forceinline__ void chunk_log_entries(unsigned a0, unsigned a1, unsigned ab, unsigned c0, unsigned c1,
-                                                  unsigned cb, unsigned mk, int k, int canonical, unsigned nbins,
-                                                  Emit&& emit) {
-    if (ab == FULL) return;    // every window starting here covers at least one of this chunk's (invalid) bases
-    unsigned long long prev = 0ull;
-    unsigned run = 0;
-    auto flush = [&]() {
-        if (prev == 0ull) return;
-        const unsigned bin = hash_part(mix64(prev), nbins);
-        for (; run >= LOG_RUN; run -= LOG_RUN) emit(prev | LOG_RUN_FLAG, bin);
-        for (; run > 0; run--) emit(prev, bin);
-    };
-#pragma unroll 4
-    for (int s = 0; s < 32; s++) {
-        const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
-        unsigned long long key = 0ull;
-        if (!bad) {
-            const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
-            const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-            key = make_key(f0, f1);
-            if (canonical) {
-                const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
-                key = kr < key ? kr : key;
-            }
-        }
-        if (key == prev) run++;
-        else { flush(); prev = key; run = 1; }
+__device__ __forceinline__ unsigned long long window_key(unsigned f0, unsigned f1, int k, int canonical) {
+    unsigned long long key = make_key(f0, f1);
+    if (canonical) {
+        const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+        key = kr < key ? kr : key;
     }
-    flush();
+    return key;
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 3)
+__global__ void __launch_bounds__(LT_THREADS, 2)
 k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, LogView lg, TableView t) {
     __shared__ LogSmem sm;
-    extern __shared__ unsigned int dyn[];          // hist[nbins] | gbase[nbins]
-    unsigned int* hist = dyn;
-    unsigned int* gbase = dyn + lg.nbins;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    // dynamic: skey[LT_TILE] u64 | delta[nbins] u32 | sbin[LT_TILE] u16 | cnt16[nbins2] u16 | off16[nbins2] u16
+    const unsigned nbins = lg.nbins, nbins2 = (nbins + 1u) & ~1u;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned int* delta = reinterpret_cast<unsigned int*>(skey + LT_TILE);
+    unsigned short* sbin = reinterpret_cast<unsigned short*>(delta + nbins);
+    unsigned short* cnt16 = sbin + LT_TILE;
+    unsigned short* off16 = cnt16 + nbins2;
+    unsigned int* cnt32 = reinterpret_cast<unsigned int*>(cnt16);
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mk = kmask(k);
     unsigned claimed = 0;
+    unsigned hpA = 0, hpC = 0, hpG = 0, hpT = 0;    // homopolymer windows seen by this thread, by base code
 
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
         fence_mbar_init();
     }
+    for (unsigned b = tid; b < nbins2 / 2; b += LT_THREADS) cnt32[b] = 0u;
     __syncthreads();
 
-    // q-th tile this CTA touches: super tile (blockIdx.x + (q / LT_TILES) * gridDim.x), tile q % LT_TILES of it
-    auto tile_at = [&](uint64_t q) -> uint64_t {
-        return (blockIdx.x + (q / LT_TILES) * (uint64_t)gridDim.x) * LT_TILES + (q % LT_TILES);
-    };
-    uint64_t q = 0;
-    if (tid == 0 && tile_at(0) < ntiles) {
-        mbar_arrive_expect_tx(&sm.bar[0], CT_LOAD);
-        bulk_copy_g2s(sm.ascii[0], recs + tile_at(0) * CT_TILE, CT_LOAD, &sm.bar[0]);
+    uint64_t tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) {
+        mbar_arrive_expect_tx(&sm.bar[0], LT_LOAD);
+        bulk_copy_g2s(sm.ascii[0], recs + tile * LT_TILE, LT_LOAD, &sm.bar[0]);
+    }
+    const unsigned per = (nbins + LT_THREADS - 1) / LT_THREADS;
+    for (unsigned it = 0; tile < ntiles; it++, tile += gridDim.x) {
+        const unsigned buf = it & 1u;
+        const uint64_t next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&sm.bar[buf ^ 1u], LT_LOAD);
+            bulk_copy_g2s(sm.ascii[buf ^ 1u], recs + next * LT_TILE, LT_LOAD, &sm.bar[buf ^ 1u]);
+        }
+        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+        const uint8_t* a = sm.ascii[buf];
+        for (int c = warp; c <= LT_CHUNKS; c += LT_THREADS / 32) {
+            const unsigned ch = a[c * 32 + lane];
+            const unsigned code = base_code(ch);
+            const unsigned b0 = __ballot_sync(FULL, code & 1u);
+            const unsigned b1 = __ballot_sync(FULL, code >> 1);
+            const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
+            if (lane == 0) { sm.p0[c] = b0; sm.p1[c] = b1; sm.pb[c] = bb; }
+        }
+        __syncthreads();   // planes complete; ascii[buf] is free for the TMA issued two iterations later
+
+        // ---- A: bins and ranks
+        const int c = tid >> 1, sh0 = (tid & 1) * LT_WIN;
+        const unsigned a0 = sm.p0[c], a1 = sm.p1[c], ab = sm.pb[c];
+        const unsigned c0 = sm.p0[c + 1], c1 = sm.p1[c + 1], cb = sm.pb[c + 1];
+#pragma unroll 4
+        for (int j = 0; j < LT_WIN; j++) {
+            const int s = sh0 + j;
+            const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
+            const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+            const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+            const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
+            unsigned m = 0xFFFFFFFFu;
+            if (!bad) {
+                if (homo) {
+                    const unsigned code = (f0 & 1u) | ((f1 & 1u) << 1);
+                    hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
+                } else {
+                    const unsigned bin = hash_part(mix64(window_key(f0, f1, k, canonical)), nbins);
+                    const unsigned shift = (bin & 1u) * 16u;
+                    const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
+                    m = (bin << 12) | ((old >> shift) & 0xFFFFu);
+                }
+            }
+            sm.meta[j * LT_THREADS + tid] = m;
+        }
+        __syncthreads();
+
+        // ---- S: scan the bin counters, reserve every bin's run in the log
+        {
+            const unsigned b0 = tid * per, b1 = min(b0 + per, nbins);
+            unsigned sum = 0;
+            for (unsigned b = b0; b < b1; b++) sum += cnt16[b];
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) sm.wtot[warp] = incl;
+            __syncthreads();
+            unsigned run = incl - sum;
+            for (int w = 0; w < warp; w++) run += sm.wtot[w];
+            if (tid == LT_THREADS - 1) sm.total = run + sum;
+            for (unsigned b = b0; b < b1; b++) {
+                const unsigned n = cnt16[b];
+                off16[b] = (unsigned short)run;
+                if (n) {
+                    unsigned base = *reinterpret_cast<volatile unsigned int*>(&lg.cursor[b]);
+                    if (base < lg.cap) base = atomicAdd(&lg.cursor[b], n);   // a full bin is never advanced again
+                    delta[b] = base - run;
+                    cnt16[b] = 0;
+                    run += n;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- B: keys again, into their sorted places
+#pragma unroll 4
+        for (int j = 0; j < LT_WIN; j++) {
+            const unsigned m = sm.meta[j * LT_THREADS + tid];
+            if (m != 0xFFFFFFFFu) {
+                const int s = sh0 + j;
+                const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+                const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+                const unsigned bin = m >> 12;
+                const unsigned idx = off16[bin] + (m & 0xFFFu);
+                skey[idx] = window_key(f0, f1, k, canonical);
+                sbin[idx] = (unsigned short)bin;
+            }
+        }
+        __syncthreads();
+
+        // ---- W: stream the sorted tile out
+        const unsigned total = sm.total;
+        for (unsigned i = tid; i < total; i += LT_THREADS) {
+            const unsigned bin = sbin[i];
+            const unsigned pos = delta[bin] + i;
+            const unsigned long long key = skey[i];
+            if (pos < lg.cap) {
+                lg.keys[(unsigned long long)bin * lg.cap + pos] = key;
+            } else if (t.slots) {      // bin full: count this occurrence directly
+                table_update<false>(t, key, 1u, claimed);
+            } else {
+                atomicExch(lg.error, 3);
+            }
+        }
+        __syncthreads();   // everything consumed before the next tile reuses it
     }
 
-    for (uint64_t st = blockIdx.x; st * LT_TILES < ntiles; st += gridDim.x) {
-        const uint64_t left = ntiles - st * LT_TILES;
-        const int nt = left < (uint64_t)LT_TILES ? (int)left : LT_TILES;
-        for (unsigned b = tid; b < lg.nbins; b += CT_THREADS) hist[b] = 0;
-        // ---- pass A: planes of nt tiles + per-bin entry counts
-        for (int j = 0; j < nt; j++, q++) {
-            const unsigned buf = (unsigned)q & 1u;
-            const uint64_t next = tile_at(q + 1);
-            if (tid == 0 && next < ntiles) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&sm.bar[buf ^ 1u], CT_LOAD);
-                bulk_copy_g2s(sm.ascii[buf ^ 1u], recs + next * CT_TILE, CT_LOAD, &sm.bar[buf ^ 1u]);
-            }
-            mbar_wait(&sm.bar[buf], (unsigned)(q >> 1) & 1u);
-            const uint8_t* a = sm.ascii[buf];
-            for (int c = warp; c <= CT_THREADS; c += CT_THREADS / 32) {
-                const unsigned ch = a[c * 32 + lane];
-                const unsigned code = base_code(ch);
-                const unsigned b0 = __ballot_sync(FULL, code & 1u);
-                const unsigned b1 = __ballot_sync(FULL, code >> 1);
-                const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
-                if (lane == 0) { sm.p0[j][c] = b0; sm.p1[j][c] = b1; sm.pb[j][c] = bb; }
-            }
-            __syncthreads();   // planes of tile j complete (and hist zeroed); ascii[buf] free for the TMA after next
-            chunk_log_entries(sm.p0[j][tid], sm.p1[j][tid], sm.pb[j][tid], sm.p0[j][tid + 1], sm.p1[j][tid + 1],
-                              sm.pb[j][tid + 1], mk, k, canonical, lg.nbins,
-                              [&](unsigned long long, unsigned bin) { atomicAdd(&hist[bin], 1u); });
+    // homopolymer tallies: hpoly[c] = key of the window made of base code c, hpoly[4 + c] += occurrences
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        unsigned v = c == 0 ? hpA : c == 1 ? hpC : c == 2 ? hpG : hpT;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0 && v) {
+            const unsigned f0 = (c & 1) ? mk : 0u, f1 = (c & 2) ? mk : 0u;
+            lg.hpoly[c] = window_key(f0, f1, k, canonical);
+            atomicAdd(&lg.hpoly[4 + c], (unsigned long long)v);
         }
-        __syncthreads();
-        // ---- one cursor reservation per non-empty bin
-        for (unsigned b = tid; b < lg.nbins; b += CT_THREADS) {
-            const unsigned n = hist[b];
-            if (n) {
-                unsigned base = *reinterpret_cast<volatile unsigned int*>(&lg.cursor[b]);
-                if (base < lg.cap) base = atomicAdd(&lg.cursor[b], n);   // a full bin is never advanced again: no wrap
-                gbase[b] = base;
-                hist[b] = 0;
-            }
-        }
-        __syncthreads();
-        // ---- pass B: the same entries again, now written to their reserved places
-        for (int j = 0; j < nt; j++) {
-            chunk_log_entries(sm.p0[j][tid], sm.p1[j][tid], sm.pb[j][tid], sm.p0[j][tid + 1], sm.p1[j][tid + 1],
-                              sm.pb[j][tid + 1], mk, k, canonical, lg.nbins,
-                              [&](unsigned long long e, unsigned bin) {
-                                  const unsigned long long pos = (unsigned long long)gbase[bin] + atomicAdd(&hist[bin], 1u);
-                                  if (pos < lg.cap) {
-                                      lg.keys[(unsigned long long)bin * lg.cap + pos] = e;
-                                  } else if (t.slots) {   // bin full: count this occurrence directly
-                                      table_update<false>(t, e & ~LOG_RUN_FLAG, (e & LOG_RUN_FLAG) ? LOG_RUN : 1u, claimed);
-                                  } else {
-                                      atomicExch(lg.error, 3);
-                                  }
-                              });
-        }
-        __syncthreads();   // hist/gbase/planes consumed before the next round reuses them
     }
     if (t.slots) {
         for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
@@ -338,22 +399,25 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
     }
 }
 
-size_t log_tiles_smem_bytes(unsigned nbins) { return (size_t)nbins * 2 * sizeof(unsigned int); }
+size_t log_tiles_smem_bytes(unsigned nbins) {
+    const unsigned nbins2 = (nbins + 1u) & ~1u;
+    return (size_t)LT_TILE * 8 + (size_t)nbins * 4 + (size_t)LT_TILE * 2 + (size_t)nbins2 * 2 * 2;
+}
 
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
                              int sm_count, cudaStream_t s) {
     if (nbytes == 0) return cudaSuccess;
-    const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
-    const uint64_t nsuper = (ntiles + LT_TILES - 1) / LT_TILES;
+    if (lg.nbins > LOG_MAX_BINS) return cudaErrorInvalidValue;
+    const uint64_t ntiles = (nbytes + LT_TILE - 1) / LT_TILE;
     const size_t dyn = log_tiles_smem_bytes(lg.nbins);
     cudaError_t e = cudaFuncSetAttribute((const void*)k_log_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_log_tiles, CT_THREADS, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_log_tiles, LT_THREADS, dyn);
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)per_sm * sm_count;
-    if (grid > nsuper) grid = nsuper;
-    k_log_tiles<<<(unsigned)grid, CT_THREADS, dyn, s>>>(d_recs, ntiles, k, canonical, lg, t);
+    if (grid > ntiles) grid = ntiles;
+    k_log_tiles<<<(unsigned)grid, LT_THREADS, dyn, s>>>(d_recs, ntiles, k, canonical, lg, t);
     return cudaGetLastError();
 }
 
@@ -399,11 +463,18 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
 __global__ void __launch_bounds__(RP_THREADS, 4)
 k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global,
-             const unsigned long long* __restrict__ chunk_start, TableView t, int prefetch) {
+             const unsigned long long* __restrict__ chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned nseg = nsrc * nlocal;
     const unsigned long long total = chunk_start[nseg];
     unsigned claimed = 0;
+    if (hpoly && blockIdx.x == 0 && tid < 4) {
+        // homopolymer tallies of phase 1: applied by the view that holds the key's partition, then cleared
+        const unsigned long long n = hpoly[4 + tid], key = hpoly[tid];
+        Probe p;
+        if (n && probe_home(t.g, key, p)) table_update<false>(t, key, (unsigned)n, claimed);
+        hpoly[4 + tid] = 0ull;
+    }
     unsigned q = 0, last_lp = 0xFFFFFFFFu;
     for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
         while (chunk_start[q + 1] <= w) q++;
@@ -442,9 +513,8 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const unsigned i = i0 + (g + u) * RP_THREADS + tid;
-                const unsigned long long e = i < n ? __ldcs(base + i) : 0ull;
-                key[u] = e & ~LOG_RUN_FLAG;
-                cnt[u] = (e & LOG_RUN_FLAG) ? LOG_RUN : 1u;
+                key[u] = i < n ? __ldcs(base + i) : 0ull;
+                cnt[u] = 1u;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
@@ -468,14 +538,14 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
 
 cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
-                              TableView t, int prefetch, int sm_count, cudaStream_t s) {
+                              unsigned long long* d_hpoly, TableView t, int prefetch, int sm_count, cudaStream_t s) {
     if (nsrc == 0 || nlocal == 0) return cudaSuccess;
     k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, nlocal, d_chunk_start);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int grid = max_resident_ctas((const void*)k_log_replay, RP_THREADS, 0, -1) ;
     k_log_replay<<<grid > 0 ? grid : sm_count, RP_THREADS, 0, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global,
-                                                                  d_chunk_start, t, prefetch);
+                                                                  d_chunk_start, d_hpoly, t, prefetch);
     return cudaGetLastError();
 }
 

@@ -53,8 +53,10 @@ def shard_geometry(world, expected_keys_per_rank, part_bytes=32 << 20):
 
 
 def log_capacity(nbytes, nbins, slack=1.2):
-    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window)"""
-    return int(nbytes / nbins * slack) + 1024
+    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window); the additive
+    term covers the hash fluctuation of small batches, the factor covers hot k-mers"""
+    cap = int(nbytes / nbins * slack) + 1024
+    return (cap + 15) // 16 * 16
 
 
 class DeviceEngine:
@@ -76,25 +78,28 @@ class DeviceEngine:
         t = self.torch
         keys = t.empty((nbins, cap), dtype=t.int64, device=self.device)
         cursor = t.zeros((nbins,), dtype=t.int32, device=self.device)
-        return keys, cursor
+        hpoly = t.zeros((8,), dtype=t.int64, device=self.device)    # homopolymer side channel: 4 keys, 4 counts
+        return keys, cursor, hpoly
 
-    def reset_log(self, cursor):
+    def reset_log(self, cursor, hpoly):
         cursor.zero_()
+        hpoly.zero_()
         self.torch.cuda.current_stream(self.device).synchronize()
 
-    def partition(self, d_recs, nbytes, keys, cursor):
+    def partition(self, d_recs, nbytes, keys, cursor, hpoly):
         """phase 1: record buffer in HBM -> log bins"""
         nbins, cap = keys.shape
         check(_lib.lib().tg_count_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(self.canonical), nbins, cap,
-                                                C.c_void_p(keys.data_ptr()), C.c_void_p(cursor.data_ptr())))
+                                                C.c_void_p(keys.data_ptr()), C.c_void_p(cursor.data_ptr()),
+                                                C.c_void_p(hpoly.data_ptr())))
         self.ctx.sync()          # the exchange runs on torch's stream: hand over with a host sync
 
-    def replay(self, keys, cursor, nsrc):
-        """phase 2: received log [nsrc, lp, cap] -> this rank's shard"""
+    def replay(self, keys, cursor, hpoly, nsrc):
+        """phase 2: received log [nsrc, lp, cap] (+ global homopolymer tallies) -> this rank's shard"""
         cap = keys.shape[-1]
         self.torch.cuda.current_stream(self.device).synchronize()
         check(_lib.lib().tg_table_replay_log_dev(self.table._h, C.c_void_p(keys.data_ptr()),
-                                                 C.c_void_p(cursor.data_ptr()), nsrc, cap))
+                                                 C.c_void_p(cursor.data_ptr()), C.c_void_p(hpoly.data_ptr()), nsrc, cap))
 
     def shard_slots(self):
         """the shard's slot array as a flat torch uint8 tensor aliasing the table memory"""
@@ -157,17 +162,20 @@ class ShardedKmerCounter:
             self._log = self.eng.new_log(self.nparts, cap)
             self._recv = self.eng.new_log(self.nparts, cap)      # same bytes, viewed [world, lp, cap]
         else:
-            self.eng.reset_log(self._log[1])
+            self.eng.reset_log(self._log[1], self._log[2])
         return self._log, self._recv
 
     def add_records_dev(self, d_recs, nbytes):
         """count every k-mer of this rank's record buffer into the sharded table (collective: all ranks call it)"""
-        (keys, cur), (rkeys, rcur) = self._buffers(nbytes)
-        self.eng.partition(d_recs, nbytes, keys, cur)
+        (keys, cur, hpoly), (rkeys, rcur, _) = self._buffers(nbytes)
+        self.eng.partition(d_recs, nbytes, keys, cur, hpoly)
         # bins [d*lp, (d+1)*lp) go to rank d: an equal-split all-to-all over dim 0
         self.dist.all_to_all_single(rcur, cur, group=self.group)
         self.dist.all_to_all_single(rkeys, keys, group=self.group)
-        self.eng.replay(rkeys, rcur, self.world)
+        # homopolymer tallies: every rank learns the global counts, the owner of each key applies it
+        self.dist.all_reduce(hpoly[:4], op=self.dist.ReduceOp.MIN, group=self.group)   # keys carry bit 63: negative
+        self.dist.all_reduce(hpoly[4:], op=self.dist.ReduceOp.SUM, group=self.group)
+        self.eng.replay(rkeys, rcur, hpoly, self.world)
 
     def size(self):
         """distinct k-mers in the global table"""
