@@ -11,8 +11,9 @@ A "step" = one pass of the hot path over the whole synthetic read set: clear the
   value     device-resident throughput: reads already in HBM, CUDA events on the library's stream
   e2e       the same step through the host-buffer C ABI (tg_count_reads + tg_cov_stats on pinned host
             arrays): H2D of reads/offsets and D2H of the per-read results inside the timed region
-  roofline  dominant kernel (k_flat_tiles<COUNT>): 64 B algorithmic HBM bytes per counted position vs the measured
-            HBM peak; random_access = the same ratio against the GUPS probe measured in this run
+  roofline  every kernel of one step with its CUDA-event time, algorithmic HBM bytes and fraction of the measured
+            HBM peak (the top one is reported as `roofline`); random_access = count / lookup rates against the
+            GUPS probes measured in this run
   cpu_baseline  the reference's own CPU tool (oracle/_ref/fastaToKmerCoverageStats, else the C oracle) on a
             bounded sample of the same reads, timed on this box's host cores
 """
@@ -150,6 +151,10 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gups", action="store_true")
+    ap.add_argument("--count-mode", default="auto", choices=["auto", "direct", "log"])
+    ap.add_argument("--stats-table", default="auto", choices=["auto", "min2", "full"],
+                    help="min2: statistics read the device-side `dump -L 2` table (bit-identical, see DESIGN.md); "
+                         "auto = full table on one GPU, min2 when the table is sharded (it is what gets all-gathered)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -160,11 +165,16 @@ def main():
     nreads = 2 * npairs
     nwin = read_len - K + 1
     positions_per_step = 2 * nreads * nwin            # counted + queried, per GPU
+    min_count = 2 if (args.stats_table == "min2" or (args.stats_table == "auto" and world > 1)) else 1
     config = {"workload": f"configs[1]: synthetic {npairs / 1e6:g}M PE 2x{read_len} bp reads from a random "
                           f"{args.ntx}-transcript set, k=25 canonical count + fastaToKmerCoverageStats, per GPU",
               "reads_per_gpu": nreads, "k": K, "unit_definition": "k-mer window positions counted + positions queried",
-              "l2_policy": "inputs (2.0 GB reads, >=10 GB table) exceed the 126 MB L2; no flush needed",
-              "table_sharding": "per-GPU private table (reads sharded by rank)" if world > 1 else "single table"}
+              "l2_policy": "inputs (2.0 GB reads, multi-GB table) exceed the 126 MB L2; no flush needed",
+              "table_sharding": (f"hash-sharded over {world} GPUs: k-mer log all-to-all (NCCL), shards all-gathered "
+                                 f"for the statistics") if world > 1 else "single table",
+              "stats_table": "k-mers with count >= 2 (device-side `jellyfish dump -L 2`, as the normalisation pipeline "
+                             "does; statistics bit-identical)" if min_count == 2 else "full count table",
+              "count_mode": args.count_mode}
 
     if args.impl == "reference":
         if rank != 0:
@@ -173,12 +183,14 @@ def main():
 
     import trinityrnaseq_b200 as tg
     dist = None
+    torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = tg.Context(local_rank)
+    ctx.set("count_mode", args.count_mode)
     info = ctx.info()
     tx, tx_offs, tx_cum = make_transcriptome(args.ntx, SEED)
     d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, npairs, read_len, seed=SEED + 7919 * rank)
@@ -189,24 +201,65 @@ def main():
     ctx.h2d(d_offs, offs_host)
     d_med, d_mean, d_sd = ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads)
 
-    # table sized once from a cheap prefix estimate: errors dominate distinct k-mers (~ K novel k-mers per error)
-    expected = int(tx_offs[-1]) + int(nreads * read_len * 0.005 * K * 1.15) + (1 << 20)
-    kc = tg.KmerCounter(ctx, K, is_ds=True, expected_keys=expected)
+    # table sized once from the shape of the data: the transcriptome's own k-mers are shared by all ranks, error
+    # k-mers (~ K novel k-mers per substitution) are private to each rank's reads
+    err_keys = int(nreads * read_len * 0.005 * K * 0.68)
+    expected_total = int(tx_offs[-1]) + world * err_keys + (1 << 20)
+    state = {"q": None}
+    if world == 1:
+        kc = tg.KmerCounter(ctx, K, is_ds=True, expected_keys=expected_total)
+
+        def count_dev(recs_ptr):
+            kc.clear()
+            kc.add_records_dev(recs_ptr, nbytes)
+
+        def query_table():
+            if min_count == 1:
+                return kc
+            if state["q"] is None:
+                state["q"] = kc.compacted(min_count, load=0.40)
+            else:
+                kc.compact_into(min_count, state["q"])
+            return state["q"]
+        table_info = kc.info
+    else:
+        from trinityrnaseq_b200 import sharded
+        eng = sharded.DeviceEngine(ctx, K, True)
+        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=expected_total // world + 1)
+        kc = sc.table
+
+        def count_dev(recs_ptr):
+            sc.clear()
+            sc.add_records_dev(recs_ptr, nbytes)
+
+        def query_table():
+            return sc.replicate(min_count=min_count, load=0.40)
+
+        def table_info():
+            return {"capacity": sc.subcap * sc.nparts, "distinct": sc.size()}
 
     def device_step():
-        kc.clear()
-        kc.add_records_dev(d_recs, nbytes)
-        kc.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
+        count_dev(d_recs)
+        query_table().coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
 
     def barrier():
         ctx.sync()
         if dist is not None:
+            torch.cuda.synchronize()
             dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------------------------------
     for _ in range(W):
         device_step()
-    tinfo = kc.info()
+    tinfo = table_info()
+    qinfo = query_table().info()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -220,22 +273,15 @@ def main():
     ms = ctx.timer_stop()
     barrier()
     launches = ctx.launch_count() - launches0
-    if dist is not None:
-        import torch
-        tms = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms = max_over_ranks(ms)
     value = world * positions_per_step * args.steps / (ms / 1e3)
 
-    # dominant kernel alone (count), for the roofline block
-    kc.clear()
-    ctx.sync()
-    ctx.timer_start()
-    kc.add_records_dev(d_recs, nbytes)
-    count_ms = ctx.timer_stop()
-    ctx.timer_start()
-    kc.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
-    stats_ms = ctx.timer_stop()
+    # per-kernel device times of one more step (CUDA events around every launch, on the launching stream)
+    ctx.set("kernel_timing", 1)
+    ctx.kernel_times()
+    device_step()
+    ktimes = ctx.kernel_times()
+    ctx.set("kernel_timing", 0)
 
     # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------------
     recs_host, recs_owner = ctx.pinned((nbytes,), np.uint8)
@@ -245,11 +291,17 @@ def main():
     sd_h, o3 = ctx.pinned((nreads,), np.float32)
     from trinityrnaseq_b200 import _lib
     L = _lib.lib()
+    d_stage = ctx.dev_records_alloc(nbytes) if world > 1 else None
 
     def host_step():
-        kc.clear()
-        _lib.check(L.tg_count_reads(kc._h, recs_host.ctypes.data, nbytes, 1))
-        _lib.check(L.tg_cov_stats(kc._h, recs_host.ctypes.data, offs_host.ctypes.data, nreads, 1, med_h.ctypes.data,
+        if world == 1:
+            kc.clear()
+            _lib.check(L.tg_count_reads(kc._h, recs_host.ctypes.data, nbytes, 1))
+        else:
+            ctx.h2d(d_stage, recs_host)          # the sharded count takes the rank's reads from HBM
+            count_dev(d_stage)
+        q = query_table()
+        _lib.check(L.tg_cov_stats(q._h, recs_host.ctypes.data, offs_host.ctypes.data, nreads, 1, med_h.ctypes.data,
                                   mean_h.ctypes.data, sd_h.ctypes.data, None))
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -259,12 +311,7 @@ def main():
     for _ in range(e2e_steps):
         host_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        te = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * positions_per_step * e2e_steps / e2e_s
     clocks = sampler.stop() if rank == 0 else None
 
@@ -272,32 +319,61 @@ def main():
     med_d = ctx.d2h(d_med, 4 * nreads, np.uint32)
     sd_d = ctx.d2h(d_sd, 4 * nreads, np.uint32)
     assert np.array_equal(med_d, med_h) and np.array_equal(sd_d, sd_h.view(np.uint32)), "device vs host path mismatch"
+    if min_count > 1 and world == 1:
+        # ... and the `dump -L 2` table must give exactly the statistics of the full table
+        kc.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
+        ctx.sync()
+        assert np.array_equal(ctx.d2h(d_med, 4 * nreads, np.uint32), med_h), "min2 table changed a median"
+        assert np.array_equal(ctx.d2h(d_sd, 4 * nreads, np.uint32), sd_h.view(np.uint32)), "min2 table changed a stdev"
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline (dominant kernel = count) ---------------------------------------------------------------
+    # ---- roofline: the kernel with the largest share of the step ------------------------------------------
     peak, peak_kind = load_peaks()
     count_positions = nreads * nwin
-    achieved = count_positions * 64 / (count_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_flat_tiles<COUNT>", "achieved": round(achieved, 1), "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                "bytes_per_unit": 64, "units_per_launch": count_positions, "kernel_ms": round(count_ms, 3),
-                "stats_kernel_ms": round(stats_ms, 3),
-                "stats_achieved_gbs": round(count_positions * 32 / (stats_ms / 1e3) / 1e9, 1)}
+    # algorithmic HBM bytes per k-mer position: log append 8 B written, replay 8 B read + the table
+    # streamed through L2 once (read + write-back of every 16-B slot), direct insert / lookup one 32-B sector each way
+    table_bytes = tinfo["capacity"] * 16 // world
+    alg = {"k_log_tiles": count_positions * 8 + nbytes,
+           "k_log_replay": count_positions * 8 + 2 * table_bytes,
+           "k_flat_tiles<COUNT>": count_positions * 64 + nbytes,
+           "k_cov_stats": count_positions * 32 + nbytes + 12 * nreads,
+           "k_rehash": table_bytes + qinfo["distinct"] * 64 // world}
+    kernels = []
+    step_kernel_ms = sum(v[0] for v in ktimes.values())
+    for name, (kms, n) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
+        e = {"kernel": name, "ms": round(kms, 3), "launches": n, "share": round(kms / step_kernel_ms, 3)}
+        if name in alg and kms > 0:
+            e["algorithmic_bytes"] = int(alg[name])
+            e["achieved_gbs"] = round(alg[name] / (kms / 1e3) / 1e9, 1)
+            e["frac_of_hbm_peak"] = round(e["achieved_gbs"] / peak, 4)
+        kernels.append(e)
+    top = kernels[0]
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("achieved_gbs"), "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": top.get("frac_of_hbm_peak"), "traffic": None,
+                "units_per_launch": count_positions, "kernel_ms": top["ms"], "kernels": kernels,
+                "note": "achieved = algorithmic bytes of one launch / its CUDA-event time; traffic (ncu dram bytes) is "
+                        "in profiles/README.md"}
     if not args.no_gups:
-        slots = max(tinfo["capacity"], 1 << 29)         # >= 8 GiB of 16-B slots
+        slots = max(tinfo["capacity"] // world, 1 << 29)         # >= 8 GiB of 16-B slots
         nops = 1 << 30
         g = {}
         for mode, name in ((0, "load16"), (1, "load8_red"), (2, "cas_red")):
             gms = ctx.gups(slots, nops, mode, reps=2)
             g[name] = {"gops": round(nops / (gms / 1e3) / 1e9, 2), "ms": round(gms, 2)}
-        roofline["random_access"] = {
-            "table_gib": round(slots * 16 / 2 ** 30, 1), **g,
-            "count_frac_of_load8_red": round((count_positions / (count_ms / 1e3) / 1e9) / g["load8_red"]["gops"], 4),
-            "stats_frac_of_load16": round((count_positions / (stats_ms / 1e3) / 1e9) / g["load16"]["gops"], 4)}
+        ra = {"table_gib": round(slots * 16 / 2 ** 30, 1), **g}
+        count_ms = sum(ktimes.get(n, (0, 0))[0] for n in ("k_log_tiles", "k_log_replay", "k_flat_tiles<COUNT>"))
+        stats_ms = ktimes.get("k_cov_stats", (0, 0))[0]
+        if count_ms:
+            ra["count_gkmers_s"] = round(count_positions / count_ms / 1e6, 2)
+            ra["count_vs_dram_random_rmw"] = round(count_positions / count_ms / 1e6 / g["load8_red"]["gops"], 3)
+        if stats_ms:
+            ra["stats_gkmers_s"] = round(count_positions / stats_ms / 1e6, 2)
+            ra["stats_vs_dram_random_load"] = round(count_positions / stats_ms / 1e6 / g["load16"]["gops"], 3)
+        roofline["random_access"] = ra
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -314,7 +390,8 @@ def main():
                    "d2h_bytes_per_step": int(12 * nreads), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
            "table": {"capacity_slots": tinfo["capacity"], "distinct_kmers": tinfo["distinct"],
-                     "load": round(tinfo["distinct"] / tinfo["capacity"], 3)},
+                     "load": round(tinfo["distinct"] / tinfo["capacity"], 3),
+                     "stats_table_slots": qinfo["capacity"], "stats_table_kmers": qinfo["distinct"]},
            "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
     print(json.dumps(out))
     if dist is not None:

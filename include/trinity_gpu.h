@@ -48,8 +48,11 @@ uint64_t tg_launch_count(tg_ctx* ctx);
 
 /* tuning knobs (also read from the environment at tg_init: TG_COUNT_MODE, TG_BATCH_MB, TG_PART_MB, TG_LOG_GB,
  * TG_REPLAY_PREFETCH): key = count_mode (auto|direct|log), batch_mb, batch_bytes, part_mb, part_bytes, log_gb,
- * log_bytes, replay_prefetch (0|1).  None of them changes a result. */
+ * log_bytes, replay_prefetch (0|1), kernel_timing (0|1).  None of them changes a result. */
 int tg_ctx_set(tg_ctx* ctx, const char* key, const char* value);
+/* With tg_ctx_set(ctx, "kernel_timing", "1") every kernel launch is bracketed by CUDA events on its stream;
+ * tg_kernel_times syncs, writes one line "kernel-name \t total ms \t launches" per kernel into out, and resets. */
+int tg_kernel_times(tg_ctx* ctx, char* out, uint64_t out_bytes);
 
 void* tg_host_alloc(uint64_t bytes); /* pinned host memory */
 void tg_host_free(void* p);
@@ -74,6 +77,13 @@ int tg_table_create_sharded(tg_ctx* ctx, int kind, int k, uint64_t slots_per_par
                             uint32_t nlocal, tg_table** out);
 int tg_table_geometry(tg_table* t, uint64_t* slots_per_partition, uint32_t* nparts, uint32_t* part0, uint32_t* nlocal);
 int tg_table_resize(tg_table* t, uint64_t slots_per_partition);      /* rehash into a new partition size */
+/* `jellyfish dump -L min` kept on the device: the number of k-mers with count >= min_count, and a copy of exactly
+ * those k-mers into `dst` (cleared first; same kind, k and partition range as t, any partition size).  This is the
+ * table util/insilico_read_normalization.pl feeds to fastaToKmerCoverageStats (jellyfish dump -L 2, :45,641):
+ * coverage statistics clamp every count below 1 to 1 (fastaToKmerCoverageStats.cpp:328-330), so a table without
+ * its count-1 k-mers gives bit-identical statistics while being several times smaller. */
+int tg_table_count_min(tg_table* t, uint32_t min_count, uint64_t* n);
+int tg_table_compact_into(tg_table* t, uint32_t min_count, tg_table* dst);
 /* raw slot array (16 B per slot) in HBM, for all-gathering shards into a full table, and the matching setter of
  * the distinct-key counter of a table assembled that way */
 int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes);

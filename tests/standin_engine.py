@@ -69,6 +69,9 @@ class StandinTable:
     def set_distinct(self, n):
         assert n == len(self.counts)
 
+    def clear(self):
+        self.counts = {}
+
     def coverage_stats(self, recs, offs):
         kc = orc.KmerCounter(self.k, self.canonical)
         for key, c in self.counts.items():
@@ -127,8 +130,18 @@ class StandinEngine:
                 for e in keys[s, p, :int(cursor[s, p])].tolist():
                     self.table.add(e - 1, 1)
 
-    def shard_slots(self):
-        return torch.from_numpy(self.table.slots().reshape(-1))
+    def slots_of(self, table):
+        return torch.from_numpy(table.slots().reshape(-1))
+
+    def count_min(self, min_count):
+        return sum(1 for c in self.table.counts.values() if c >= min_count)
+
+    def new_shard_like(self, subcap):
+        t = self.table
+        return StandinTable(self.k, self.canonical, subcap, t.nparts, t.part0, t.nlocal)
+
+    def compact_into(self, min_count, dst):
+        dst.counts = {k: c for k, c in self.table.counts.items() if c >= min_count}
 
     def full_table(self, subcap, nparts):
         full = StandinTable(self.k, self.canonical, subcap, nparts, 0, nparts)

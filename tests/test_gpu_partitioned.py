@@ -212,3 +212,40 @@ def test_partition_log_overflow_is_reported(ctx, data):
     ctx.sync()                                          # the flag is cleared once reported
     for p in (d, keys, cur, hp):
         ctx.dev_free(p)
+
+
+@pytest.mark.parametrize("canonical", [True, False])
+def test_compacted_min2_table_gives_identical_stats(ctx, oracle, data, canonical):
+    """`jellyfish dump -L 2` kept on the device: the table without its count-1 k-mers answers every coverage
+    query exactly like the full table (fastaToKmerCoverageStats clamps counts below 1 to 1)"""
+    _, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, 25, canonical, 1)
+    ctx.set("part_bytes", 256 << 10)
+    with tg.KmerCounter(ctx, 25, is_ds=canonical, expected_keys=len(ok)) as kc:
+        kc.add_records(recs)
+        assert kc.count_min(1) == len(ok)
+        assert kc.count_min(2) == int((oc >= 2).sum())
+        assert 0 < kc.count_min(2) < len(ok)
+        full = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+        with kc.compacted(2) as q:
+            assert q.size() == int((oc >= 2).sum())
+            k2, c2 = q.dump()
+            np.testing.assert_array_equal(k2, ok[oc >= 2])
+            np.testing.assert_array_equal(c2, oc[oc >= 2])
+            part = q.coverage_stats(recs, offs, capture_coverage_info=True)
+            for a, b in zip(full, part):
+                np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+            # refill the same destination: same content again
+            kc.compact_into(2, q)
+            assert q.size() == int((oc >= 2).sum())
+            # after more counting every k-mer has count >= 2: the old destination is too small and says so
+            kc.add_records(recs)
+            kc.compact_into(2, q)
+            with pytest.raises(tg.TrinityGpuError) as e:
+                q.size()
+            assert "overflow" in str(e.value)
+        with kc.compacted(2) as q2:
+            assert q2.size() == len(ok)
+        with kc.compacted(3) as q3:                    # -L 3 is NOT statistics-preserving: count-2 k-mers vanish
+            assert q3.size() == int((2 * oc >= 3).sum())

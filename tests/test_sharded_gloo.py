@@ -73,6 +73,20 @@ def _worker(rank, world, port, out_dir):
             om, omean, osd = okc2.coverage_stats(recs, offs)
             np.testing.assert_array_equal(gm, om[r0:r1])
             np.testing.assert_array_equal(gsd.view(np.uint32), osd[r0:r1].view(np.uint32))
+        # the `dump -L 2` replica: only k-mers seen at least twice, yet the same coverage statistics
+        rep2 = sc.replicate(min_count=2)
+        k2, c2 = rep2.dump()
+        keep = (2 * oc) >= 2
+        np.testing.assert_array_equal(k2, ok[keep])
+        rep3 = sc.replicate(min_count=3)                 # doubled counts: nothing has count 3 exactly, 2 drops out
+        k3, c3 = rep3.dump()
+        np.testing.assert_array_equal(k3, ok[(2 * oc) >= 3])
+        np.testing.assert_array_equal(c3, (2 * oc)[(2 * oc) >= 3])
+        rep2 = sc.replicate(min_count=2)
+        if r1 > r0:
+            gm2, _, gsd2 = rep2.coverage_stats(mine, sub_offs)
+            np.testing.assert_array_equal(gm2, om[r0:r1])
+            np.testing.assert_array_equal(gsd2.view(np.uint32), osd[r0:r1].view(np.uint32))
         dist.barrier()
     finally:
         dist.destroy_process_group()

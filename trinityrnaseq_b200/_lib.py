@@ -26,6 +26,7 @@ SIGNATURES = {
     "tg_sync": (_i32, [_vp]),
     "tg_launch_count": (_u64, [_vp]),
     "tg_ctx_set": (_i32, [_vp, _cp, _cp]),
+    "tg_kernel_times": (_i32, [_vp, _vp, _u64]),
     "tg_host_alloc": (_vp, [_u64]),
     "tg_host_free": (None, [_vp]),
     "tg_free": (None, [_vp]),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "tg_table_create_sharded": (_i32, [_vp, _i32, _i32, _u64, _u32, _u32, _u32, _pp]),
     "tg_table_geometry": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "tg_table_resize": (_i32, [_vp, _u64]),
+    "tg_table_count_min": (_i32, [_vp, _u32, C.POINTER(_u64)]),
+    "tg_table_compact_into": (_i32, [_vp, _u32, _vp]),
     "tg_table_slots_dev": (_i32, [_vp, _pp, C.POINTER(_u64)]),
     "tg_table_set_distinct": (_i32, [_vp, _u64]),
     "tg_count_reads": (_i32, [_vp, _vp, _u64, _i32]),

@@ -97,6 +97,16 @@ class Context:
         """tuning knob (tg_ctx_set): count_mode, batch_bytes, part_bytes, log_bytes, replay_prefetch, ..."""
         check(_lib.lib().tg_ctx_set(self._h, str(key).encode(), str(value).encode()))
 
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} since the last call; needs set("kernel_timing", 1)"""
+        buf = C.create_string_buffer(1 << 14)
+        check(_lib.lib().tg_kernel_times(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split("\t")
+            out[name] = (float(ms), int(n))
+        return out
+
     # -- raw device memory (bench / tests) ------------------------------------------------------------
     def dev_alloc(self, nbytes):
         p = C.c_void_p()
@@ -248,6 +258,25 @@ class KmerCounter(_Table):
     def sharded(cls, ctx, k, is_ds, slots_per_partition, nparts, part0, nlocal):
         """the shard holding partitions [part0, part0+nlocal) of a table of nparts partitions"""
         return cls(ctx, k, is_ds, geometry=(slots_per_partition, nparts, part0, nlocal))
+
+    def count_min(self, min_count):
+        """number of k-mers with count >= min_count (what `jellyfish dump -L min_count` would print)"""
+        n = C.c_uint64()
+        check(_lib.lib().tg_table_count_min(self._h, min_count, C.byref(n)))
+        return n.value
+
+    def compact_into(self, min_count, dst):
+        """copy the k-mers with count >= min_count into dst (`jellyfish dump -L` without leaving the device)"""
+        check(_lib.lib().tg_table_compact_into(self._h, min_count, dst._h))
+
+    def compacted(self, min_count, load=0.45):
+        """new table holding only the k-mers with count >= min_count, same partition range"""
+        n = self.count_min(min_count)
+        subcap, nparts, part0, nlocal = self.geometry()
+        sub = max(int(n / load / nlocal) + 64, 64)
+        dst = KmerCounter.sharded(self.ctx, self.k, self.is_ds, sub, nparts, part0, nlocal)
+        self.compact_into(min_count, dst)
+        return dst
 
     def partition_dev(self, d_recs, nbytes, nbins, cap, d_keys, d_cursor, d_hpoly, canonical=None):
         """phase 1 of the sharded count: k-mer occurrences -> caller-owned log bins (tg_count_partition_dev)"""

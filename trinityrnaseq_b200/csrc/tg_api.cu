@@ -75,6 +75,7 @@ struct tg_ctx {
     int* d_error = nullptr;                             // raised by table-less log appends (tg_count_partition_dev)
     size_t part_bytes = 32ull << 20;                    // target bytes of one table partition (L2-resident unit)
     size_t log_max_bytes = 24ull << 30;                 // most HBM the k-mer log of one table may take
+    KernelTimer timer;                                  // optional per-kernel event timing
     int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
     int replay_prefetch = 1;
 };
@@ -122,6 +123,7 @@ static Geo pick_geo(uint64_t slots, size_t part_bytes) {
 }
 
 static int bind(tg_ctx* c) {
+    g_kernel_timer = &c->timer;
     CU(cudaSetDevice(c->device));
     return TG_OK;
 }
@@ -292,6 +294,8 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
         c->log_max_bytes = (size_t)v;
     } else if (!strcmp(key, "replay_prefetch")) {
         c->replay_prefetch = v != 0;
+    } else if (!strcmp(key, "kernel_timing")) {
+        c->timer.on = v != 0;
     } else {
         return fail(TG_ERR_ARG, "tg_ctx_set: unknown option '%s'", key);
     }
@@ -408,7 +412,7 @@ static int table_regrow(tg_table* t, Geo ng) {
     if ((rc = table_alloc(c, ncap, &fresh))) return rc;
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
     TableView nv{fresh, ng, t->d_claimed, t->d_error};
-    CU(launch_rehash(t->slots, t->cap, nv, t->kind == TG_TABLE_LABEL, c->stream[0]));
+    CU(launch_rehash(t->slots, t->cap, nv, t->kind == TG_TABLE_LABEL, 0, c->stream[0]));
     c->launches++;
     CU(cudaStreamSynchronize(c->stream[0]));
     CU(cudaFree(t->slots));
@@ -491,6 +495,46 @@ int tg_table_info(tg_table* t, uint64_t* capacity, uint64_t* distinct) {
     if (capacity) *capacity = t->cap;
     if (distinct) *distinct = t->distinct_ub;
     return TG_OK;
+}
+
+// number of keys with value >= min_count (streams the table once)
+static int count_min(tg_table* t, uint32_t min_count, uint64_t* n) {
+    tg_ctx* c = t->ctx;
+    unsigned long long* d_n = nullptr;
+    CU(cudaMalloc(&d_n, sizeof *d_n));
+    CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, c->stream[0]));
+    CU(launch_export(t->slots, t->cap, min_count, 0xFFFFFFFFu, t->k, 0, nullptr, nullptr, d_n, c->stream[0]));
+    c->launches++;
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, d_n, sizeof v, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(d_n);
+    *n = v;
+    return TG_OK;
+}
+
+int tg_table_count_min(tg_table* t, uint32_t min_count, uint64_t* n) {
+    if (!t || !n) return fail(TG_ERR_ARG, "tg_table_count_min: null argument");
+    if (bind(t->ctx)) return TG_ERR_CUDA;
+    int rc = flush_log(t);
+    if (rc) return rc;
+    if ((rc = sync_all(t->ctx))) return rc;
+    return count_min(t, min_count, n);
+}
+
+int tg_table_compact_into(tg_table* t, uint32_t min_count, tg_table* dst) {
+    if (!t || !dst || t == dst) return fail(TG_ERR_ARG, "tg_table_compact_into: bad argument");
+    if (t->ctx != dst->ctx || t->kind != dst->kind || t->k != dst->k || t->g.nparts != dst->g.nparts ||
+        t->g.part0 != dst->g.part0 || t->g.nlocal != dst->g.nlocal)
+        return fail(TG_ERR_ARG, "tg_table_compact_into: the destination must have the source's kind, k and partition range");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = flush_log(t);
+    if (rc) return rc;
+    if ((rc = tg_table_clear(dst))) return rc;       // syncs both streams
+    CU(launch_rehash(t->slots, t->cap, dst->view(), t->kind == TG_TABLE_LABEL, min_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;                                    // stream-ordered; an overfull destination raises its error flag
 }
 
 int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes) {
@@ -1170,6 +1214,33 @@ int tg_memcpy_d2h(tg_ctx* c, void* host, const void* dptr, uint64_t bytes) {
     if (bind(c)) return TG_ERR_CUDA;
     CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[0]));
+    return TG_OK;
+}
+
+int tg_kernel_times(tg_ctx* c, char* out, uint64_t out_bytes) {
+    if (!c || !out || out_bytes == 0) return fail(TG_ERR_ARG, "tg_kernel_times: bad argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    struct Acc { const char* name; double ms; unsigned n; };
+    std::vector<Acc> acc;
+    for (auto& sp : c->timer.spans) {
+        float ms = 0;
+        if (sp.a && sp.b && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            bool found = false;
+            for (auto& a : acc) if (!strcmp(a.name, sp.name)) { a.ms += ms; a.n++; found = true; break; }
+            if (!found) acc.push_back({sp.name, ms, 1});
+        }
+        if (sp.a) cudaEventDestroy(sp.a);
+        if (sp.b) cudaEventDestroy(sp.b);
+    }
+    cudaGetLastError();
+    c->timer.spans.clear();
+    std::string txt;
+    char line[256];
+    for (auto& a : acc) { snprintf(line, sizeof line, "%s\t%.6f\t%u\n", a.name, a.ms, a.n); txt += line; }
+    if (txt.size() + 1 > out_bytes) return fail(TG_ERR_ARG, "tg_kernel_times: buffer too small (%zu bytes needed)", txt.size() + 1);
+    memcpy(out, txt.c_str(), txt.size() + 1);
     return TG_OK;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include <vector>
 #include "tg_device.cuh"
 
 namespace tg {
@@ -34,6 +35,26 @@ struct LongList {            // filled by the warp-path kernels, consumed by the
 
 int max_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device);
 
+// ---- optional per-kernel timing (tg_ctx_set "kernel_timing" 1; read back with tg_kernel_times) -------------
+// Every launch_* wrapper brackets its kernel with two CUDA events on the launching stream while a timer is bound
+// and switched on.  Off (the default) it costs one branch.
+struct KernelSpan { const char* name; cudaEvent_t a, b; };
+struct KernelTimer { bool on = false; std::vector<KernelSpan> spans; };
+extern thread_local KernelTimer* g_kernel_timer;
+struct TimedLaunch {
+    cudaStream_t s; long idx = -1;
+    TimedLaunch(const char* name, cudaStream_t stream) : s(stream) {
+        KernelTimer* kt = g_kernel_timer;
+        if (!kt || !kt->on) return;
+        KernelSpan sp{name, nullptr, nullptr};
+        if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+        cudaEventRecord(sp.a, s);
+        kt->spans.push_back(sp);
+        idx = (long)kt->spans.size() - 1;
+    }
+    ~TimedLaunch() { if (idx >= 0) cudaEventRecord(g_kernel_timer->spans[idx].b, s); }
+};
+
 // flat tiles: count every valid k-mer window of a '\n'-padded record buffer into a count table
 cudaError_t launch_count_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, TableView t,
                                int sm_count, cudaStream_t s);
@@ -57,8 +78,9 @@ cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned i
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);
-// re-insert every live slot of `from` into `to` (growth)
-cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, cudaStream_t s);
+// re-insert every live slot of `from` whose value is >= min_val into `to` (growth: min_val 0; compaction: min count)
+cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
+                          cudaStream_t s);
 
 // per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,

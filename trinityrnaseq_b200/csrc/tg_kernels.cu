@@ -17,6 +17,8 @@ namespace tg {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+thread_local KernelTimer* g_kernel_timer = nullptr;
+
 int max_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device) {
     int per_sm = 0, sms = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem);
@@ -177,6 +179,7 @@ static int flat_grid(const void* kern, uint64_t ntiles, int sm_count) {
 
 cudaError_t launch_count_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, TableView t,
                                int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_flat_tiles<COUNT>", s);
     if (nbytes == 0) return cudaSuccess;
     const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
     const int grid = flat_grid((const void*)k_flat_tiles<MODE_COUNT>, ntiles, sm_count);
@@ -187,6 +190,7 @@ cudaError_t launch_count_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, in
 cudaError_t launch_label_tiles(const uint8_t* d_recs, uint64_t nbytes, const uint64_t* d_offs, uint64_t rec_base,
                                uint64_t nbundles, uint32_t first_bundle_index, int k, TableView t, int sm_count,
                                cudaStream_t s) {
+    TimedLaunch timed("k_flat_tiles<LABEL>", s);
     if (nbytes == 0 || nbundles == 0) return cudaSuccess;
     const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
     const int grid = flat_grid((const void*)k_flat_tiles<MODE_LABEL>, ntiles, sm_count);
@@ -406,6 +410,7 @@ size_t log_tiles_smem_bytes(unsigned nbins) {
 
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
                              int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_log_tiles", s);
     if (nbytes == 0) return cudaSuccess;
     if (lg.nbins > LOG_MAX_BINS) return cudaErrorInvalidValue;
     const uint64_t ntiles = (nbytes + LT_TILE - 1) / LT_TILE;
@@ -539,6 +544,7 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
 cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
                               unsigned long long* d_hpoly, TableView t, int prefetch, int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_log_replay", s);
     if (nsrc == 0 || nlocal == 0) return cudaSuccess;
     k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, nlocal, d_chunk_start);
     cudaError_t e = cudaGetLastError();
@@ -573,6 +579,7 @@ k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ val
 
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s) {
+    TimedLaunch timed("k_load_pairs", s);
     if (n == 0) return cudaSuccess;
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
@@ -582,23 +589,25 @@ cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, ui
 }
 
 __global__ void __launch_bounds__(256)
-k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label) {
+k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val) {
     unsigned claimed = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key == 0ull) continue;
+        if (key == 0ull || s.z < min_val) continue;
         if (is_label) table_update<true>(to, key, s.z, claimed); else table_update<false>(to, key, s.z, claimed);
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
 }
 
-cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, cudaStream_t s) {
+cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
+                          cudaStream_t s) {
+    TimedLaunch timed("k_rehash", s);
     if (from_cap == 0) return cudaSuccess;
     uint64_t blocks = (from_cap + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    k_rehash<<<(int)blocks, 256, 0, s>>>(from, from_cap, to, is_label);
+    k_rehash<<<(int)blocks, 256, 0, s>>>(from, from_cap, to, is_label, min_val);
     return cudaGetLastError();
 }
 
@@ -775,6 +784,7 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                              float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s) {
+    TimedLaunch timed("k_cov_stats", s);
     if (nreads == 0) return cudaSuccess;
     const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
     k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
@@ -823,6 +833,7 @@ cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs,
                                   const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
                                   unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_cov_stats_long", s);
     if (n_long == 0) return cudaSuccess;
     k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
                                                     d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
@@ -950,6 +961,7 @@ k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, ui
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                           int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                           int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s) {
+    TimedLaunch timed("k_assign", s);
     if (nreads == 0) return cudaSuccess;
     const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
     k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, geo,
@@ -983,6 +995,7 @@ cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, ui
                                const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                                int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
                                unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_assign_long", s);
     if (n_long == 0) return cudaSuccess;
     k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
                                                  d_pct, d_score, d_long_idx, n_long, max_win, (uint32_t*)d_scratch,
@@ -1012,6 +1025,7 @@ k_histo(const Slot* __restrict__ slots, uint64_t cap, unsigned long long* __rest
 }
 
 cudaError_t launch_histo(const Slot* slots, uint64_t cap, unsigned long long* d_bins, cudaStream_t s) {
+    TimedLaunch timed("k_histo", s);
     if (cap == 0) return cudaSuccess;
     uint64_t blocks = (cap + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
@@ -1056,6 +1070,7 @@ k_export(const Slot* __restrict__ slots, uint64_t cap, uint32_t min_count, uint3
 cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, uint32_t max_count, int k,
                           int canonical_repr, uint64_t* d_keys, uint32_t* d_vals, unsigned long long* d_n,
                           cudaStream_t s) {
+    TimedLaunch timed("k_export", s);
     if (cap == 0) return cudaSuccess;
     uint64_t blocks = (cap + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -1104,6 +1119,7 @@ k_gups(Slot* slots, uint64_t cap, uint64_t nops, unsigned long long* sink) {
 
 cudaError_t launch_gups(Slot* slots, uint64_t cap, uint64_t nops, int mode, unsigned long long* d_sink, int sm_count,
                         cudaStream_t s) {
+    TimedLaunch timed("k_gups", s);
     const int grid = sm_count * 8;
     if (mode == 0) k_gups<0><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);
     else if (mode == 1) k_gups<1><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);

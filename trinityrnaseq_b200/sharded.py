@@ -101,17 +101,26 @@ class DeviceEngine:
         check(_lib.lib().tg_table_replay_log_dev(self.table._h, C.c_void_p(keys.data_ptr()),
                                                  C.c_void_p(cursor.data_ptr()), C.c_void_p(hpoly.data_ptr()), nsrc, cap))
 
-    def shard_slots(self):
-        """the shard's slot array as a flat torch uint8 tensor aliasing the table memory"""
+    def slots_of(self, table):
+        """a table's slot array as a flat torch uint8 tensor aliasing the table memory"""
         p, n = C.c_void_p(), C.c_uint64()
-        check(_lib.lib().tg_table_slots_dev(self.table._h, C.byref(p), C.byref(n)))
+        check(_lib.lib().tg_table_slots_dev(table._h, C.byref(p), C.byref(n)))
         return _alias_tensor(self.torch, p.value, n.value, self.device)
+
+    def count_min(self, min_count):
+        return self.table.count_min(min_count)
+
+    def new_shard_like(self, subcap):
+        _, nparts, part0, nlocal = self.table.geometry()
+        return KmerCounter.sharded(self.ctx, self.k, self.canonical, subcap, nparts, part0, nlocal)
+
+    def compact_into(self, min_count, dst):
+        self.table.compact_into(min_count, dst)
+        self.ctx.sync()
 
     def full_table(self, subcap, nparts):
         full = KmerCounter.sharded(self.ctx, self.k, self.canonical, subcap, nparts, 0, nparts)
-        p, n = C.c_void_p(), C.c_uint64()
-        check(_lib.lib().tg_table_slots_dev(full._h, C.byref(p), C.byref(n)))
-        return full, _alias_tensor(self.torch, p.value, n.value, self.device)
+        return full, self.slots_of(full)
 
     def local_distinct(self):
         return self.table.size()
@@ -149,6 +158,11 @@ class ShardedKmerCounter:
         self.table = engine.create_shard(self.subcap, self.nparts, self.rank * self.lp, self.lp)
         self._log = None
         self._recv = None
+        self._compact = None      # (compacted shard, its slots per partition)
+        self._full = None         # (full replica, its slot bytes as a tensor, slots per partition)
+
+    def clear(self):
+        self.table.clear()
 
     def owner_of_bin(self, b):
         return b // self.lp
@@ -194,14 +208,33 @@ class ShardedKmerCounter:
         """this rank's part of `jellyfish dump` (sorted); the global dump is the merge of all ranks' parts"""
         return self.eng.local_dump(min_count)
 
-    def replicate(self):
-        """all-gather the shards into a full table on every rank -> KmerCounter for local queries"""
-        full, full_bytes = self.eng.full_table(self.subcap, self.nparts)
-        mine = self.eng.shard_slots()
+    def replicate(self, min_count=1, load=TARGET_LOAD):
+        """All-gather the shards into a full table on every rank -> KmerCounter for local queries.  min_count > 1
+        gathers only the k-mers with at least that count (`jellyfish dump -L min_count`, what the normalisation
+        pipeline feeds fastaToKmerCoverageStats): coverage statistics are bit-identical for min_count <= 2 because
+        they clamp counts below 1 to 1, and the replica is several times smaller.  Buffers are cached, so calling
+        this once per step costs one compaction kernel and one all-gather."""
+        if min_count <= 1:
+            src, subcap = self.table, self.subcap
+        else:
+            n = self.eng.scalar_tensor([self.eng.count_min(min_count)], _int64(self.eng))
+            self.dist.all_reduce(n, op=self.dist.ReduceOp.MAX, group=self.group)
+            need = max(int(int(n.item()) / load / self.lp) + 64, 64)
+            if self._compact is None or not (need <= self._compact[1] <= 2 * need):
+                self._compact = (self.eng.new_shard_like(need), need)
+            src, subcap = self._compact
+            self.eng.compact_into(min_count, src)
+        if self._full is None or self._full[2] != subcap:
+            full, full_bytes = self.eng.full_table(subcap, self.nparts)
+            self._full = (full, full_bytes, subcap)
+        full, full_bytes, _ = self._full
+        mine = self.eng.slots_of(src)
         self.dist.all_gather_into_tensor(full_bytes, mine, group=self.group)
         if hasattr(self.eng, "torch"):
             self.eng.torch.cuda.current_stream(self.eng.device).synchronize()
-        full.set_distinct(self.size())
+        d = self.eng.scalar_tensor([src.size()], _int64(self.eng))
+        self.dist.all_reduce(d, group=self.group)
+        full.set_distinct(int(d.item()))
         return full
 
 
