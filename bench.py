@@ -53,6 +53,144 @@ def make_transcriptome(ntx, seed, sigma=2.0):
     return tx, offs, cum_u64
 
 
+def make_bundles(tx, tx_offs, seed, max_per_bundle=25):
+    """Inchworm-bundle records cut from the transcriptome (SURVEY §8d, C4 shape): contigs = consecutive pieces of
+    every transcript with length ~ lognormal(ln 500, 0.7) clipped to [100, 20000]; bundles of 1..25 consecutive
+    contigs joined by 'X' (Chrysalis/analysis/CreateIwormFastaBundle.cc:56-68).  -> (record buffer, offs, ncontigs)"""
+    rng = np.random.default_rng(seed)
+    ntx = len(tx_offs) - 1
+    pieces = []
+    for t in range(ntx):
+        a, e = int(tx_offs[t]), int(tx_offs[t + 1])
+        while a < e:
+            n = int(np.clip(round(rng.lognormal(np.log(500), 0.7)), 100, 20000))
+            if e - a - n < 100:
+                n = e - a
+            pieces.append((a, a + n))
+            a += n
+    out, offs, i = [], [0], 0
+    xs = np.frombuffer(b"X", dtype=np.uint8)
+    nl = np.frombuffer(b"\n", dtype=np.uint8)
+    while i < len(pieces):
+        m = int(rng.integers(1, max_per_bundle + 1))
+        grp = pieces[i:i + m]
+        i += m
+        n = 0
+        for j, (a, e) in enumerate(grp):
+            if j:
+                out.append(xs); n += 1
+            out.append(tx[a:e]); n += e - a
+        out.append(nl); n += 1
+        offs.append(offs[-1] + n)
+    return np.concatenate(out), np.asarray(offs, dtype=np.uint64), len(pieces)
+
+
+def r2t_cpu_reference(tx_small, offs_small, cum_small, read_len, nreads, seed, threads):
+    """oracle/_ref/ReadsToTranscripts on a small instance of the same shape (its k-mer table build -- a sort of
+    25-byte strings -- is part of the tool, so the instance is bounded on both sides).  -> reads/s or None"""
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ReadsToTranscripts")
+    if not os.path.exists(ref_bin):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synthdata
+    rng = np.random.default_rng(seed)
+    txs = [tx_small[int(offs_small[i]):int(offs_small[i + 1])].tobytes() for i in range(len(offs_small) - 1)]
+    reads = synthdata.reads_from(rng, txs, nreads, read_len, err=0.005, n_rate=0.001)
+    brecs, boffs, _ = make_bundles(tx_small, offs_small, seed)
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "reads.fa"), "wb") as f:
+            for i, r in enumerate(reads):
+                f.write(b">r%d/1\n%s\n" % (i, r))
+        with open(os.path.join(td, "bundles.fa"), "wb") as f:
+            for i in range(len(boffs) - 1):
+                f.write(b">s_%d 10\n" % i)
+                f.write(brecs[int(boffs[i]):int(boffs[i + 1])].tobytes())
+        t0 = time.perf_counter()
+        subprocess.run([ref_bin, "-i", os.path.join(td, "reads.fa"), "-f", os.path.join(td, "bundles.fa"), "-o",
+                        os.path.join(td, "out"), "-t", str(threads), "-max_mem_reads", "50000000", "-p", "10"],
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True,
+                       env={**os.environ, "OMP_NUM_THREADS": str(threads)})
+        dt = time.perf_counter() - t0
+    return nreads / dt, dt
+
+
+def bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host, nreads, read_len, steps, want_cpu):
+    """ReadsToTranscripts on the same reads (BASELINE metric, second half): label the bundle k-mers, assign every
+    read.  Device-resident and host-buffer timings; the reads are the step's 20 M reads, the bundles are cut from
+    the same transcriptome."""
+    from trinityrnaseq_b200 import _lib
+    L = _lib.lib()
+    brecs, boffs, ncontigs = make_bundles(tx, tx_offs, SEED + 1)
+    nb = len(boffs) - 1
+    d_b = ctx.dev_records_alloc(brecs.nbytes)
+    ctx.h2d(d_b, brecs)
+    d_bo = ctx.dev_alloc(boffs.nbytes)
+    ctx.h2d(d_bo, boffs)
+    d_best, d_pct = ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads)
+    bt = tg.BundleKmerTable(ctx, K, expected_keys=int(tx_offs[-1]) + (1 << 20))
+    d_lut = ctx.dev_alloc(bt.entropy_ok.nbytes)
+    ctx.h2d(d_lut, bt.entropy_ok)
+
+    def dev_step():
+        bt.clear()
+        bt.label_bundles_dev(d_b, brecs.nbytes, d_bo, nb)
+        bt.assign_reads_dev(d_recs, d_offs, nreads, d_lut, d_best, d_pct, strand=False)
+
+    dev_step()
+    ctx.sync()
+    ctx.set("kernel_timing", 1)
+    ctx.kernel_times()
+    ctx.timer_start()
+    for _ in range(steps):
+        dev_step()
+    ms = ctx.timer_stop() / steps
+    kt = ctx.kernel_times()
+    ctx.set("kernel_timing", 0)
+    best_d = ctx.d2h(d_best, 4 * nreads, np.int32)
+    pct_d = ctx.d2h(d_pct, 4 * nreads, np.int32)
+    labelled = bt.size()
+    # host-buffer C ABI (H2D of bundles + reads, D2H of the assignments inside the timed region)
+    best_h, o1 = ctx.pinned((nreads,), np.int32)
+    pct_h, o2 = ctx.pinned((nreads,), np.int32)
+    brecs_p, o3 = ctx.pinned((brecs.nbytes,), np.uint8)
+    brecs_p[:] = brecs
+
+    def host_step():
+        bt.clear()
+        _lib.check(L.tg_label_bundles(bt._h, brecs_p.ctypes.data, boffs.ctypes.data, nb, 0))
+        _lib.check(L.tg_assign_reads(bt._h, recs_host.ctypes.data, offs_host.ctypes.data, nreads, 0,
+                                     bt.entropy_ok.ctypes.data, best_h.ctypes.data, pct_h.ctypes.data, None))
+    host_step()
+    t0 = time.perf_counter()
+    host_step()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(best_d, best_h) and np.array_equal(pct_d[best_d >= 0], pct_h[best_h >= 0]), "r2t dev/host mismatch"
+    nwin = read_len - K + 1
+    lookups = 2 * nreads * nwin          # forward + reverse-complement pass (no -strand)
+    out = {"metric": "reads/sec ReadsToTranscripts", "workload": f"configs[3] shape on this step's reads: {nreads} reads x "
+           f"{read_len} bp against {ncontigs} contigs in {nb} bundles cut from the same transcriptome, double-stranded, -p 10",
+           "value": nreads / (ms / 1e3), "unit": "reads/s", "ms_per_step": ms,
+           "e2e": {"value": nreads / e2e_s, "unit": "reads/s", "ms_per_step": e2e_s * 1e3,
+                   "h2d_bytes_per_step": int(brecs.nbytes + boffs.nbytes + nbytes + offs_host.nbytes),
+                   "d2h_bytes_per_step": int(8 * nreads)},
+           "bundle_kmers": int(labelled), "reads_assigned": int((best_d >= 0).sum()),
+           "kernels": {k_: {"ms": round(v[0] / steps, 3)} for k_, v in kt.items()},
+           "lookups_per_s": lookups / (kt.get("k_assign", (ms * steps, 0))[0] / steps / 1e3)}
+    if want_cpu:
+        ntx_s = 1500
+        r = r2t_cpu_reference(tx[:int(tx_offs[ntx_s])], tx_offs[:ntx_s + 1], None, read_len, 200_000, SEED + 2,
+                              os.cpu_count() or 1)
+        if r:
+            out["cpu_baseline"] = {"value": round(r[0], 1), "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "seconds": round(r[1], 2),
+                                   "sample": f"oracle/_ref/ReadsToTranscripts -t {os.cpu_count()} on 200000 reads x {read_len} bp "
+                                             f"against the bundles of the first {ntx_s} transcripts (table build included)"}
+    for p_ in (d_b, d_bo, d_best, d_pct, d_lut):
+        ctx.dev_free(p_)
+    bt.close()
+    return out
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -151,6 +289,7 @@ def main():
     ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gups", action="store_true")
+    ap.add_argument("--no-r2t", action="store_true", help="skip the ReadsToTranscripts measurement")
     ap.add_argument("--count-mode", default="auto", choices=["auto", "direct", "log"])
     ap.add_argument("--stats-table", default="auto", choices=["auto", "min2", "full"],
                     help="min2: statistics read the device-side `dump -L 2` table (bit-identical, see DESIGN.md); "
@@ -230,7 +369,7 @@ def main():
 
         def count_dev(recs_ptr):
             sc.clear()
-            sc.add_records_dev(recs_ptr, nbytes)
+            sc.add_records_dev(recs_ptr, nbytes, max_windows=nreads * nwin)
 
         def query_table():
             return sc.replicate(min_count=min_count, load=0.40)
@@ -326,6 +465,11 @@ def main():
         assert np.array_equal(ctx.d2h(d_med, 4 * nreads, np.uint32), med_h), "min2 table changed a median"
         assert np.array_equal(ctx.d2h(d_sd, 4 * nreads, np.uint32), sd_h.view(np.uint32)), "min2 table changed a stdev"
 
+    r2t = None
+    if not args.no_r2t and world == 1:
+        r2t = bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host, nreads, read_len,
+                        max(1, min(args.steps, 3)), not args.no_cpu_baseline)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -393,6 +537,8 @@ def main():
                      "load": round(tinfo["distinct"] / tinfo["capacity"], 3),
                      "stats_table_slots": qinfo["capacity"], "stats_table_kmers": qinfo["distinct"]},
            "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
+    if r2t is not None:
+        out["reads_to_transcripts"] = r2t
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

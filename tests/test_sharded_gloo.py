@@ -124,4 +124,4 @@ def test_shard_geometry():
         subcap, nparts, lp = sharded.shard_geometry(world, 150_000_000)
         assert nparts == world * lp and nparts <= sharded.MAX_BINS
         assert subcap * lp >= 150_000_000 / sharded.TARGET_LOAD
-        assert subcap * 16 <= (32 << 20) or nparts * 2 > sharded.MAX_BINS
+        assert subcap * 16 <= (16 << 20) or nparts * 2 > sharded.MAX_BINS

@@ -15,6 +15,7 @@ ap.add_argument("--load", type=float, default=0.45)
 ap.add_argument("--parts", default="8,16,32,64")
 ap.add_argument("--sigma", type=float, default=2.0)
 ap.add_argument("--p1bins", default="")
+ap.add_argument("--groups", default="8")
 args = ap.parse_args()
 
 ctx = tg.Context(0)
@@ -65,13 +66,15 @@ for pm in [int(x) for x in args.parts.split(",")]:
         ctx.memset(cur, 0, nbins * 4)
         kc.partition_dev(d_recs, nbytes, nbins, cap, keys, cur, hp)
     ms1 = timed(p1, 2)
+    ms2 = {}
     if nbins == nparts:
-        kc.clear()
-        ms2 = timed(lambda: kc.replay_log_dev(keys, cur, None, 1, cap), 1)
-        kc.clear()
-        ms2 = min(ms2, timed(lambda: kc.replay_log_dev(keys, cur, None, 1, cap), 1))
-    else:
-        ms2 = None
+        for G in [int(x) for x in args.groups.split(",")]:
+            ctx.set("replay_groups", G)
+            kc.clear()
+            m = timed(lambda: kc.replay_log_dev(keys, cur, None, 1, cap), 1)
+            kc.clear()
+            ms2[G] = round(min(m, timed(lambda: kc.replay_log_dev(keys, cur, None, 1, cap), 1)), 2)
+            assert kc.info()["distinct"] == distinct
     curh = ctx.d2h(cur, nbins * 4, np.uint32)
     out.append({"mode": "phases", "part_mb": pm, "phase1_ms": ms1, "phase2_ms": ms2, "entries": int(curh.sum()),
                 "entries_per_pos": float(curh.sum()) / npos, "bin_fill_max_over_mean": float(curh.max() / curh.mean())})

@@ -357,6 +357,12 @@ class BundleKmerTable(_Table):
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         check(_lib.lib().tg_label_bundles(self._h, _ptr(recs), _ptr(offs), len(offs) - 1, first_index))
 
+    def label_bundles_dev(self, d_recs, nbytes, d_offs, nbundles, first_index=0):
+        check(_lib.lib().tg_label_bundles_dev(self._h, d_recs, nbytes, d_offs, nbundles, first_index))
+
+    def assign_reads_dev(self, d_recs, d_offs, nreads, d_entropy_ok, d_best, d_pct, strand=False):
+        check(_lib.lib().tg_assign_reads_dev(self._h, d_recs, d_offs, nreads, int(strand), d_entropy_ok, d_best, d_pct))
+
     def assign_reads(self, recs, offs, strand=False):
         """-> (best bundle index or -1, pct_read_mapped, max run) per record (ReadsToTranscripts.cc:216-274)."""
         recs = _as_u8(recs)

@@ -73,11 +73,12 @@ struct tg_ctx {
     unsigned int* d_long_hdr[2] = {nullptr, nullptr};   // {count, max_win}
     unsigned int* h_long_hdr = nullptr;                 // pinned, 2 x 2
     int* d_error = nullptr;                             // raised by table-less log appends (tg_count_partition_dev)
-    size_t part_bytes = 32ull << 20;                    // target bytes of one table partition (L2-resident unit)
+    size_t part_bytes = 16ull << 20;                    // target bytes of one table partition (L2-resident unit)
     size_t log_max_bytes = 24ull << 30;                 // most HBM the k-mer log of one table may take
     KernelTimer timer;                                  // optional per-kernel event timing
     int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
     int replay_prefetch = 1;
+    unsigned replay_groups = 8;                         // bins replayed concurrently (see k_log_replay)
 };
 
 // k-mer log of a count table (partitioned count path)
@@ -294,6 +295,9 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
         c->log_max_bytes = (size_t)v;
     } else if (!strcmp(key, "replay_prefetch")) {
         c->replay_prefetch = v != 0;
+    } else if (!strcmp(key, "replay_groups")) {
+        if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
+        c->replay_groups = (unsigned)v;
     } else if (!strcmp(key, "kernel_timing")) {
         c->timer.on = v != 0;
     } else {
@@ -630,7 +634,7 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     log_release(t);
     if (cudaMalloc(&t->log.keys, per_bin * nbins * 8) != cudaSuccess) { cudaGetLastError(); t->log.keys = nullptr; return TG_OK; }
     CU(cudaMalloc(&t->log.cursor, nbins * sizeof(unsigned int)));
-    CU(cudaMalloc(&t->log.chunk_start, ((size_t)nbins + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&t->log.chunk_start, log_replay_plan_words(1, nbins, 64) * sizeof(unsigned long long)));
     CU(cudaMalloc(&t->log.hpoly, 8 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(t->log.cursor, 0, nbins * sizeof(unsigned int), c->stream[0]));
     CU(cudaMemsetAsync(t->log.hpoly, 0, 8 * sizeof(unsigned long long), c->stream[0]));
@@ -647,8 +651,8 @@ static LogView log_view(tg_table* t) {
 // replay + reset on stream 0 (stream-ordered; no host sync)
 static int replay_log_async(tg_table* t) {
     tg_ctx* c = t->ctx;
-    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, t->log.chunk_start,
-                         t->log.hpoly, t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
+    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, c->replay_groups,
+                         t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
     c->launches += 2;
     CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
     t->log.pending_ub = 0;
@@ -676,7 +680,7 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     CU(cudaMalloc(&d_n, sizeof *d_n));
     CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, c->stream[0]));
     TableView sv{scratch, sg, d_n, t->d_error};
-    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, ns, 0, nbins, t->log.chunk_start, nullptr, sv, 0,
+    CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, ns, 0, nbins, 1, t->log.chunk_start, nullptr, sv, 0,
                          c->sm_count, c->stream[0]));
     c->launches += 2;
     unsigned long long d = 0;
@@ -812,11 +816,11 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_table_replay_log_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
-    const size_t need = ((size_t)nsrc * t->g.nlocal + 1) * sizeof(unsigned long long);
+    const size_t need = log_replay_plan_words(nsrc, t->g.nlocal, 64) * sizeof(unsigned long long);
     CU(c->scratch.ensure(need));
     CU(launch_log_replay((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
-                         t->g.nparts, (unsigned long long*)c->scratch.p, (unsigned long long*)d_hpoly, t->view(),
-                         c->replay_prefetch, c->sm_count, c->stream[0]));
+                         t->g.nparts, c->replay_groups, (unsigned long long*)c->scratch.p, (unsigned long long*)d_hpoly,
+                         t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;
 }

@@ -71,10 +71,13 @@ constexpr unsigned LOG_CAP_MAX = 0xF0000000u;           // per-bin cursors are 3
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
                              int sm_count, cudaStream_t s);
 // phase 2: replay log segments [nsrc][nlocal][cap] (cursor [nsrc][nlocal]) bin-major into the table; the bins are
-// global bins bin0..bin0+nlocal-1 of nbins_global.  d_chunk_start: scratch of nsrc*nlocal+1 u64.
+// global bins bin0..bin0+nlocal-1 of nbins_global, `groups` bins open at a time.  d_chunk_start: scratch of
+// log_replay_plan_words(nsrc, nlocal, groups) u64.
+size_t log_replay_plan_words(unsigned nsrc, unsigned nlocal, unsigned groups);
 cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
-                              unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
-                              unsigned long long* d_hpoly, TableView t, int prefetch, int sm_count, cudaStream_t s);
+                              unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned groups,
+                              unsigned long long* d_chunk_start, unsigned long long* d_hpoly, TableView t, int prefetch,
+                              int sm_count, cudaStream_t s);
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);

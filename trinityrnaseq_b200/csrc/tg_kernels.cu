@@ -431,19 +431,44 @@ constexpr int RP_THREADS = 256;
 constexpr int RP_PER_THREAD = 8;
 constexpr int RP_CHUNK = RP_THREADS * RP_PER_THREAD;
 
-// chunk_start[q] for segments in bin-major order: q = lp * nsrc + src <-> log segment src * nlocal + lp
+// Replay order.  Bins are dealt round-robin to G GROUPS (bin lp belongs to group lp % G); the chunk index space
+// lists group 0's bins first (in bin order, each bin's nsrc source segments together), then group 1's, ...  Every
+// group hands its chunks out in order from its own counter, and the CTAs are split evenly over the groups, so at any
+// time about G bins are being replayed, each by 1/G of the machine:
+//   * G = 1 keeps the table traffic of a whole bin inside one L2-resident partition group, but every occurrence of
+//     a hot k-mer then arrives within the few tens of microseconds its bin is open, and same-address atomics
+//     serialise in L2;
+//   * a static stride over all chunks (no counters) lets CTAs drift tens of bins apart: no hot spots, but the open
+//     partitions no longer fit in L2 (measured: 83 GB of DRAM reads for a 5.5 GB table);
+//   * G groups bound both: G partitions open, hot k-mers spread over G times the time.
+// Layout of the plan array: chunk_start[nperm + 1] (prefix over the permuted segments), then G work counters.
+__host__ __device__ __forceinline__ unsigned replay_per_group(unsigned nlocal, unsigned G) { return (nlocal + G - 1) / G; }
+
+// permuted segment index pq -> (lp, src); lp >= nlocal means "no such bin" (padding of the last groups)
+__device__ __forceinline__ void replay_segment(unsigned pq, unsigned nsrc, unsigned nlocal, unsigned G, unsigned& lp,
+                                               unsigned& src) {
+    const unsigned per = replay_per_group(nlocal, G);
+    const unsigned bp = pq / nsrc;
+    src = pq % nsrc;
+    lp = (bp % per) * G + bp / per;
+}
+
 __global__ void __launch_bounds__(1024)
-k_log_plan(const unsigned int* __restrict__ cursor, unsigned cap, unsigned nsrc, unsigned nlocal,
+k_log_plan(const unsigned int* __restrict__ cursor, unsigned cap, unsigned nsrc, unsigned nlocal, unsigned G,
            unsigned long long* __restrict__ chunk_start) {
     __shared__ unsigned long long part[1024];
-    const unsigned nseg = nsrc * nlocal;
-    const unsigned per = (nseg + 1023) / 1024;
-    const unsigned q0 = threadIdx.x * per, q1 = min(q0 + per, nseg);
+    const unsigned nperm = replay_per_group(nlocal, G) * G * nsrc;
+    const unsigned per = (nperm + 1023) / 1024;
+    const unsigned q0 = threadIdx.x * per, q1 = min(q0 + per, nperm);
+    auto chunks_of = [&](unsigned pq) -> unsigned long long {
+        unsigned lp, src;
+        replay_segment(pq, nsrc, nlocal, G, lp, src);
+        if (lp >= nlocal) return 0ull;
+        const unsigned c = min(cursor[src * nlocal + lp], cap);
+        return (c + RP_CHUNK - 1) / RP_CHUNK;
+    };
     unsigned long long sum = 0;
-    for (unsigned q = q0; q < q1; q++) {
-        const unsigned c = min(cursor[(q % nsrc) * nlocal + q / nsrc], cap);
-        sum += (c + RP_CHUNK - 1) / RP_CHUNK;
-    }
+    for (unsigned q = q0; q < q1; q++) sum += chunks_of(q);
     part[threadIdx.x] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -455,10 +480,15 @@ k_log_plan(const unsigned int* __restrict__ cursor, unsigned cap, unsigned nsrc,
     unsigned long long run = part[threadIdx.x] - sum;    // exclusive prefix
     for (unsigned q = q0; q < q1; q++) {
         chunk_start[q] = run;
-        const unsigned c = min(cursor[(q % nsrc) * nlocal + q / nsrc], cap);
-        run += (c + RP_CHUNK - 1) / RP_CHUNK;
+        run += chunks_of(q);
     }
-    if (threadIdx.x == 1023) chunk_start[nseg] = part[1023];
+    if (threadIdx.x == 1023) chunk_start[nperm] = part[1023];
+}
+
+// the counters need values written by other threads: a second tiny kernel keeps k_log_plan simple
+__global__ void k_log_plan_counters(unsigned nsrc, unsigned nlocal, unsigned G, unsigned long long* chunk_start) {
+    const unsigned nperm = replay_per_group(nlocal, G) * G * nsrc;
+    if (threadIdx.x < G) chunk_start[nperm + 1 + threadIdx.x] = chunk_start[threadIdx.x * replay_per_group(nlocal, G) * nsrc];
 }
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
@@ -467,11 +497,11 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
 
 __global__ void __launch_bounds__(RP_THREADS, 4)
 k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
-             unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global,
-             const unsigned long long* __restrict__ chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
+             unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned G,
+             unsigned long long* chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned nseg = nsrc * nlocal;
-    const unsigned long long total = chunk_start[nseg];
+    const unsigned per = replay_per_group(nlocal, G);
+    const unsigned nperm = per * G * nsrc;
     unsigned claimed = 0;
     if (hpoly && blockIdx.x == 0 && tid < 4) {
         // homopolymer tallies of phase 1: applied by the view that holds the key's partition, then cleared
@@ -480,78 +510,103 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
         if (n && probe_home(t.g, key, p)) table_update<false>(t, key, (unsigned)n, claimed);
         hpoly[4 + tid] = 0ull;
     }
-    unsigned q = 0, last_lp = 0xFFFFFFFFu;
-    for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
-        while (chunk_start[q + 1] <= w) q++;
-        const unsigned lp = q / nsrc, src = q % nsrc;
-        const unsigned seg = src * nlocal + lp;
-        const unsigned n = min(cursor[seg], cap);
-        const unsigned long long* base = keys + (unsigned long long)seg * cap;
-        const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
+    __shared__ unsigned long long s_w;
+    unsigned long long* counters = chunk_start + nperm + 1;
+    unsigned last_lp = 0xFFFFFFFFu;
+    // a CTA serves its own group first and then helps the following groups finish
+    for (unsigned gi = 0; gi < G; gi++) {
+        const unsigned g = (blockIdx.x + gi) % G;
+        const unsigned q_end = (g + 1) * per * nsrc;
+        const unsigned long long w_end = chunk_start[q_end];
+        unsigned q = g * per * nsrc;
+        while (true) {
+            __syncthreads();                       // everyone has read the previous s_w
+            if (tid == 0) s_w = atomicAdd(&counters[g], 1ull);
+            __syncthreads();
+            const unsigned long long w = s_w;
+            if (w >= w_end) break;
+            while (chunk_start[q + 1] <= w) q++;
+            unsigned lp, src;
+            replay_segment(q, nsrc, nlocal, G, lp, src);
+            const unsigned seg = src * nlocal + lp;
+            const unsigned n = min(cursor[seg], cap);
+            const unsigned long long* base = keys + (unsigned long long)seg * cap;
+            const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
 
-        if (prefetch && lp != last_lp) {
-            // first chunk this CTA sees of bin lp: pull this CTA's slice of the NEXT bin's partitions into L2
-            last_lp = lp;
-            if (tid == 0 && lp + 1 < nlocal) {
-                const unsigned long long gb = (unsigned long long)bin0 + lp + 1;                 // global bin
-                const unsigned long long p_lo = gb * t.g.nparts / nbins_global;
-                const unsigned long long p_prev = (gb - 1) * t.g.nparts / nbins_global;
-                unsigned long long p_hi = ((gb + 1) * t.g.nparts - 1) / nbins_global;
-                if ((p_lo != p_prev || t.g.nparts >= nbins_global) && p_lo >= t.g.part0) {
-                    if (p_hi >= (unsigned long long)t.g.part0 + t.g.nlocal) p_hi = (unsigned long long)t.g.part0 + t.g.nlocal - 1;
-                    const unsigned long long r0 = (p_lo - t.g.part0) * t.g.subcap * sizeof(Slot);
-                    const unsigned long long r1 = (p_hi + 1 - t.g.part0) * t.g.subcap * sizeof(Slot);
-                    unsigned long long slice = ((r1 - r0) / gridDim.x + 127ull) & ~127ull;
-                    unsigned long long a = r0 + slice * blockIdx.x, e = a + slice;
-                    if (e > r1) e = r1;
-                    const char* tb = reinterpret_cast<const char*>(t.slots);
-                    for (; a < e; a += 16384) prefetch_l2_bulk(tb + a, (unsigned)((e - a) < 16384ull ? (e - a) : 16384ull));
+            if (prefetch && lp != last_lp) {
+                // first chunk this CTA sees of bin lp: pull its slice of the group's NEXT bin's partitions into L2
+                last_lp = lp;
+                if (tid == 0 && lp + G < nlocal) {
+                    const unsigned long long gb = (unsigned long long)bin0 + lp + G;                 // global bin
+                    const unsigned long long p_lo = gb * t.g.nparts / nbins_global;
+                    unsigned long long p_hi = ((gb + 1) * t.g.nparts - 1) / nbins_global;
+                    if (p_lo >= t.g.part0 && p_lo < (unsigned long long)t.g.part0 + t.g.nlocal) {
+                        if (p_hi >= (unsigned long long)t.g.part0 + t.g.nlocal) p_hi = (unsigned long long)t.g.part0 + t.g.nlocal - 1;
+                        const unsigned long long r0 = (p_lo - t.g.part0) * t.g.subcap * sizeof(Slot);
+                        const unsigned long long r1 = (p_hi + 1 - t.g.part0) * t.g.subcap * sizeof(Slot);
+                        const unsigned ctas = gridDim.x / G ? gridDim.x / G : 1u;
+                        unsigned long long slice = ((r1 - r0) / ctas + 127ull) & ~127ull;
+                        unsigned long long a = r0 + slice * (blockIdx.x / G), e = a + slice;
+                        if (e > r1) e = r1;
+                        const char* tb = reinterpret_cast<const char*>(t.slots);
+                        for (; a < e; a += 16384) prefetch_l2_bulk(tb + a, (unsigned)((e - a) < 16384ull ? (e - a) : 16384ull));
+                    }
                 }
             }
-        }
 
 #pragma unroll 1
-        for (int g = 0; g < RP_PER_THREAD; g += 4) {
-            unsigned long long key[4], cur[4];
-            unsigned cnt[4];
-            Probe pr[4];
+            for (int gg = 0; gg < RP_PER_THREAD; gg += 4) {
+                unsigned long long key[4], cur[4];
+                Probe pr[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const unsigned i = i0 + (g + u) * RP_THREADS + tid;
-                key[u] = i < n ? __ldcs(base + i) : 0ull;
-                cnt[u] = 1u;
+                for (int u = 0; u < 4; u++) {
+                    const unsigned i = i0 + (gg + u) * RP_THREADS + tid;
+                    key[u] = i < n ? __ldcs(base + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (key[u] != 0ull) {
+                        if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
+                        else { key[u] = 0ull; atomicExch(t.error, 2); }
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (key[u] != 0ull) {
+                        Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
+                        if (sl) atomicAdd(&sl->val, 1u);
+                    }
+                __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
+                                // and every later log load / probe is issued once per lane subset
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (key[u] != 0ull) {
-                    if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
-                    else { key[u] = 0ull; atomicExch(t.error, 2); }
-                }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (key[u] != 0ull) {
-                    Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
-                    if (sl) atomicAdd(&sl->val, cnt[u]);
-                }
-            __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
-                            // and every later log load / probe is issued once per lane subset
         }
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
 }
 
+size_t log_replay_plan_words(unsigned nsrc, unsigned nlocal, unsigned G) {
+    return (size_t)replay_per_group(nlocal, G) * G * nsrc + 1 + G;
+}
+
 cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
-                              unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned long long* d_chunk_start,
-                              unsigned long long* d_hpoly, TableView t, int prefetch, int sm_count, cudaStream_t s) {
+                              unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned groups,
+                              unsigned long long* d_chunk_start, unsigned long long* d_hpoly, TableView t, int prefetch,
+                              int sm_count, cudaStream_t s) {
     TimedLaunch timed("k_log_replay", s);
     if (nsrc == 0 || nlocal == 0) return cudaSuccess;
-    k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, nlocal, d_chunk_start);
+    if (groups < 1) groups = 1;
+    if (groups > nlocal) groups = nlocal;
+    if (groups > 64) groups = 64;
+    k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, nlocal, groups, d_chunk_start);
+    k_log_plan_counters<<<1, 64, 0, s>>>(nsrc, nlocal, groups, d_chunk_start);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int grid = max_resident_ctas((const void*)k_log_replay, RP_THREADS, 0, -1) ;
-    k_log_replay<<<grid > 0 ? grid : sm_count, RP_THREADS, 0, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global,
-                                                                  d_chunk_start, d_hpoly, t, prefetch);
+    int grid = max_resident_ctas((const void*)k_log_replay, RP_THREADS, 0, -1);
+    if (grid <= 0) grid = sm_count;
+    grid = grid / (int)groups * (int)groups;           // the same number of CTAs in every group
+    if (grid < (int)groups) grid = (int)groups;
+    k_log_replay<<<grid, RP_THREADS, 0, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
+                                             d_chunk_start, d_hpoly, t, prefetch);
     return cudaGetLastError();
 }
 

@@ -42,7 +42,7 @@ def record_range(offs_or_total, rank, world):
     return r0, r1
 
 
-def shard_geometry(world, expected_keys_per_rank, part_bytes=32 << 20):
+def shard_geometry(world, expected_keys_per_rank, part_bytes=16 << 20):
     """-> (slots_per_partition, nparts, lp): lp partitions per rank, each about part_bytes (the L2 blocking unit)."""
     slots = max(int(expected_keys_per_rank / TARGET_LOAD) + 1, 4096)
     lp = 1
@@ -149,7 +149,7 @@ def _alias_tensor(torch, ptr, nbytes, device):
 class ShardedKmerCounter:
     """KmerCounter whose table is sharded by hash over the ranks of a torch.distributed process group."""
 
-    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=32 << 20, dist=None):
+    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=16 << 20, dist=None):
         if dist is None:
             import torch.distributed as dist
         self.dist, self.group, self.eng = dist, group, engine
@@ -169,6 +169,7 @@ class ShardedKmerCounter:
 
     def _buffers(self, nbytes):
         # the exchange is an equal-split all-to-all: every rank must lay its log out for the largest batch
+        # (nbytes bounds the entries of a batch: every byte starts at most one window)
         m = self.eng.scalar_tensor([int(nbytes)], _int64(self.eng))
         self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
         cap = log_capacity(int(m.item()), self.nparts)
@@ -179,9 +180,11 @@ class ShardedKmerCounter:
             self.eng.reset_log(self._log[1], self._log[2])
         return self._log, self._recv
 
-    def add_records_dev(self, d_recs, nbytes):
-        """count every k-mer of this rank's record buffer into the sharded table (collective: all ranks call it)"""
-        (keys, cur, hpoly), (rkeys, rcur, _) = self._buffers(nbytes)
+    def add_records_dev(self, d_recs, nbytes, max_windows=None):
+        """Count every k-mer of this rank's record buffer into the sharded table (collective: all ranks call it).
+        max_windows: an upper bound on the k-mer windows of the buffer when the caller knows one tighter than
+        nbytes (fixed-length reads: nreads * (L - k + 1)); it only sizes the exchange buffers."""
+        (keys, cur, hpoly), (rkeys, rcur, _) = self._buffers(nbytes if max_windows is None else min(nbytes, max_windows))
         self.eng.partition(d_recs, nbytes, keys, cur, hpoly)
         # bins [d*lp, (d+1)*lp) go to rank d: an equal-split all-to-all over dim 0
         self.dist.all_to_all_single(rcur, cur, group=self.group)
@@ -217,13 +220,29 @@ class ShardedKmerCounter:
         if min_count <= 1:
             src, subcap = self.table, self.subcap
         else:
-            n = self.eng.scalar_tensor([self.eng.count_min(min_count)], _int64(self.eng))
-            self.dist.all_reduce(n, op=self.dist.ReduceOp.MAX, group=self.group)
-            need = max(int(int(n.item()) / load / self.lp) + 64, 64)
-            if self._compact is None or not (need <= self._compact[1] <= 2 * need):
-                self._compact = (self.eng.new_shard_like(need), need)
-            src, subcap = self._compact
-            self.eng.compact_into(min_count, src)
+            # the compacted shard is sized once (one streaming count, agreed over ranks) and then refilled; a refill
+            # that outgrows it is caught by the fill check below and sized again
+            for attempt in (0, 1):
+                if self._compact is None or self._compact[2] != min_count:
+                    n = self.eng.scalar_tensor([self.eng.count_min(min_count)], _int64(self.eng))
+                    self.dist.all_reduce(n, op=self.dist.ReduceOp.MAX, group=self.group)
+                    need = max(int(int(n.item()) / load / self.lp) + 64, 64)
+                    self._compact = (self.eng.new_shard_like(need), need, min_count)
+                src, subcap, _ = self._compact
+                self.eng.compact_into(min_count, src)
+                full_flag = 0
+                try:
+                    if src.size() > 0.8 * subcap * self.lp:
+                        full_flag = 1
+                except Exception:           # overflow flag raised by the table
+                    full_flag = 1
+                f = self.eng.scalar_tensor([full_flag], _int64(self.eng))
+                self.dist.all_reduce(f, op=self.dist.ReduceOp.MAX, group=self.group)
+                if int(f.item()) == 0:
+                    break
+                if hasattr(src, "close"):
+                    src.close()
+                self._compact = None
         if self._full is None or self._full[2] != subcap:
             full, full_bytes = self.eng.full_table(subcap, self.nparts)
             self._full = (full, full_bytes, subcap)
