@@ -48,7 +48,8 @@ uint64_t tg_launch_count(tg_ctx* ctx);
 
 /* tuning knobs (also read from the environment at tg_init: TG_COUNT_MODE, TG_BATCH_MB, TG_PART_MB, TG_LOG_GB,
  * TG_REPLAY_PREFETCH): key = count_mode (auto|direct|log), batch_mb, batch_bytes, part_mb, part_bytes, log_gb,
- * log_bytes, replay_prefetch (0|1), kernel_timing (0|1).  None of them changes a result. */
+ * log_bytes, replay_prefetch (0|1), replay_groups, hot_keys (size of the L2-resident hot-k-mer table used by the
+ * coverage statistics, 0 = off), hot_force (0|1), kernel_timing (0|1).  None of them changes a result. */
 int tg_ctx_set(tg_ctx* ctx, const char* key, const char* value);
 /* With tg_ctx_set(ctx, "kernel_timing", "1") every kernel launch is bracketed by CUDA events on its stream;
  * tg_kernel_times syncs, writes one line "kernel-name \t total ms \t launches" per kernel into out, and resets. */

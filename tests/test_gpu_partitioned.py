@@ -249,3 +249,42 @@ def test_compacted_min2_table_gives_identical_stats(ctx, oracle, data, canonical
             assert q2.size() == len(ok)
         with kc.compacted(3) as q3:                    # -L 3 is NOT statistics-preserving: count-2 k-mers vanish
             assert q3.size() == int((2 * oc >= 3).sum())
+
+
+@pytest.mark.parametrize("hot_keys", [300, 5000])
+def test_hot_table_lookups_are_exact_and_never_stale(ctx, oracle, data, hot_keys):
+    """the L2-resident hot-k-mer table in front of the count table: same statistics, rebuilt after every change"""
+    _, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    half = len(reads) // 2
+    recs_a, _ = tg.records_from_sequences(reads[:half])
+    recs_b, _ = tg.records_from_sequences(reads[half:])
+    ctx.set("hot_keys", hot_keys)
+    ctx.set("hot_force", 1)
+    with tg.KmerCounter(ctx, 25, is_ds=True) as kc:
+        okc = oracle.KmerCounter(25, True)
+        for part in (recs_a, recs_b):
+            kc.add_records(part)
+            k_, c_ = kc.dump()
+            for kmer, c in zip(k_, c_):
+                pass
+            okc = oracle.KmerCounter(25, True)
+            for kmer, c in zip(k_, c_):
+                okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
+            om, omean, osd, oper = okc.coverage_stats(recs, offs, capture=True)
+            for _ in range(2):                         # second call re-uses the hot table built by the first
+                gm, gmean, gsd, gper = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+                np.testing.assert_array_equal(gper, oper)
+                np.testing.assert_array_equal(gm, om)
+                np.testing.assert_array_equal(gsd.view(np.uint32), osd.view(np.uint32))
+            d = _dev_records(ctx, recs)
+            d_offs = ctx.dev_alloc(offs.nbytes)
+            ctx.h2d(d_offs, offs)
+            n = len(offs) - 1
+            d1, d2, d3 = ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n)
+            kc.coverage_stats_dev(d, d_offs, n, d1, d2, d3)
+            ctx.sync()
+            np.testing.assert_array_equal(ctx.d2h(d1, 4 * n, np.uint32), om)
+            np.testing.assert_array_equal(ctx.d2h(d3, 4 * n, np.uint32), osd.view(np.uint32))
+            for p in (d, d_offs, d1, d2, d3):
+                ctx.dev_free(p)

@@ -79,6 +79,11 @@ struct tg_ctx {
     int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
     int replay_prefetch = 1;
     unsigned replay_groups = 8;                         // bins replayed concurrently (see k_log_replay)
+    uint64_t hot_max_keys = 0;                          // size of the L2-resident hot cache; 0 = off (the default: measured
+                                                        // no gain once the median stopped being a sort, profiles/README.md)
+    bool hot_force = false;                             // tests: build it whatever the table size / coverage
+    unsigned hot_hints = 0;                             // L2 eviction hints used with the hot table (see Geo)
+    double hot_load = 0.6;
 };
 
 // k-mer log of a count table (partitioned count path)
@@ -103,6 +108,11 @@ struct tg_table {
     int* d_error = nullptr;
     uint64_t distinct_ub = 0;   // host-side upper bound on distinct keys (refreshed from the device at syncs)
     KeyLog log;
+    Slot* hot = nullptr;        // hot table storage (g.hot_slots points here while it is valid)
+    uint64_t hot_cap = 0;
+    uint64_t hot_keys = 0;
+    uint32_t hot_min = 0;
+    bool hot_tried = false;     // a build was attempted for the current table content
     bool sharded() const { return g.nlocal != g.nparts; }
     TableView view() const { return TableView{slots, g, d_claimed, d_error}; }
 };
@@ -133,6 +143,15 @@ static int sync_all(tg_ctx* c) {
     CU(cudaStreamSynchronize(c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[1]));
     return TG_OK;
+}
+
+// the table content is about to change (or has changed behind our back): the hot copy is stale
+static void hot_invalidate(tg_table* t) {
+    t->g.hot_slots = nullptr;
+    t->g.hot_subcap = 0;
+    t->g.hot_hints = 0;
+    t->hot_keys = 0;
+    t->hot_tried = false;
 }
 
 static int table_refresh(tg_table* t) {   // after a sync: read back distinct count and the error flag
@@ -298,6 +317,16 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
     } else if (!strcmp(key, "replay_groups")) {
         if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
         c->replay_groups = (unsigned)v;
+    } else if (!strcmp(key, "hot_keys")) {
+        if (v < 0 || v > (64 << 20)) return fail(TG_ERR_ARG, "hot_keys out of range (0..64M)");
+        c->hot_max_keys = (uint64_t)v;
+    } else if (!strcmp(key, "hot_hints")) {
+        c->hot_hints = (unsigned)v & 3u;
+    } else if (!strcmp(key, "hot_load_pct")) {
+        if (v < 10 || v > 90) return fail(TG_ERR_ARG, "hot_load_pct out of range");
+        c->hot_load = v / 100.0;
+    } else if (!strcmp(key, "hot_force")) {
+        c->hot_force = v != 0;
     } else if (!strcmp(key, "kernel_timing")) {
         c->timer.on = v != 0;
     } else {
@@ -382,6 +411,7 @@ void tg_table_destroy(tg_table* t) {
     cudaSetDevice(t->ctx->device);
     cudaDeviceSynchronize();
     log_release(t);
+    if (t->hot) cudaFree(t->hot);
     if (t->slots) cudaFree(t->slots);
     if (t->d_claimed) cudaFree(t->d_claimed);
     if (t->d_error) cudaFree(t->d_error);
@@ -391,6 +421,7 @@ void tg_table_destroy(tg_table* t) {
 int tg_table_clear(tg_table* t) {
     if (!t) return fail(TG_ERR_ARG, "null table");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     int rc = sync_all(c);
     if (rc) return rc;
@@ -410,6 +441,8 @@ int tg_table_clear(tg_table* t) {
 // Move the table into a new geometry (growth).  Both streams must be idle.
 static int table_regrow(tg_table* t, Geo ng) {
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
+    ng.hot_slots = nullptr; ng.hot_subcap = 0;
     const uint64_t ncap = (uint64_t)ng.nlocal * ng.subcap;
     Slot* fresh = nullptr;
     int rc;
@@ -532,6 +565,7 @@ int tg_table_compact_into(tg_table* t, uint32_t min_count, tg_table* dst) {
         t->g.part0 != dst->g.part0 || t->g.nlocal != dst->g.nlocal)
         return fail(TG_ERR_ARG, "tg_table_compact_into: the destination must have the source's kind, k and partition range");
     tg_ctx* c = t->ctx;
+    hot_invalidate(dst);
     if (bind(c)) return TG_ERR_CUDA;
     int rc = flush_log(t);
     if (rc) return rc;
@@ -547,6 +581,7 @@ int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes) {
     int rc = flush_log(t);
     if (rc) return rc;
     if ((rc = sync_all(t->ctx))) return rc;
+    hot_invalidate(t);            // the caller may write through the pointer
     *d_slots = t->slots;
     *nbytes = t->cap * sizeof(Slot);
     return TG_OK;
@@ -555,6 +590,7 @@ int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes) {
 int tg_table_set_distinct(tg_table* t, uint64_t distinct) {
     if (!t) return fail(TG_ERR_ARG, "null table");
     if (bind(t->ctx)) return TG_ERR_CUDA;
+    hot_invalidate(t);            // called after the slots were rewritten through tg_table_slots_dev
     unsigned long long v = distinct;
     CU(cudaMemcpy(t->d_claimed, &v, sizeof v, cudaMemcpyHostToDevice));
     t->distinct_ub = distinct;
@@ -651,6 +687,7 @@ static LogView log_view(tg_table* t) {
 // replay + reset on stream 0 (stream-ordered; no host sync)
 static int replay_log_async(tg_table* t) {
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, c->replay_groups,
                          t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
     c->launches += 2;
@@ -723,6 +760,7 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
     if (!t || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_count_reads: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
     // Partitioned path: append to the log batch by batch (H2D of one batch overlaps the log kernel of the other),
@@ -768,6 +806,7 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
     if (!t || !d_recs) return fail(TG_ERR_ARG, "tg_count_reads_dev: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     // the caller sizes the table (tg_table_create / tg_table_reserve): a conservative per-byte bound would
     // multiply the footprint.  An overflow raises the table's error flag -> TG_ERR_TABLE at tg_table_info.
@@ -815,6 +854,7 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
     if (!t || !d_keys || !d_cursor || nsrc == 0 || cap == 0) return fail(TG_ERR_ARG, "tg_table_replay_log_dev: bad argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_table_replay_log_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     const size_t need = log_replay_plan_words(nsrc, t->g.nlocal, 64) * sizeof(unsigned long long);
     CU(c->scratch.ensure(need));
@@ -828,6 +868,7 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
 int tg_table_load_pairs(tg_table* t, const uint64_t* keys, const uint32_t* vals, uint64_t n, int canonical) {
     if (!t || ((!keys || !vals) && n)) return fail(TG_ERR_ARG, "tg_table_load_pairs: null argument");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
     if ((rc = flush_log(t))) return rc;
@@ -912,6 +953,59 @@ int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]) {
 // ---------------------------------------------------------------------------------------------------------
 }  // extern "C"
 
+// Build the hot table when a lookup-heavy call is about to start: the k-mers with the largest counts, as many as fit
+// the L2 budget, chosen from the count histogram.  Only worth it when they cover a good share of all occurrences
+// (expression skew) -- with a flat histogram the table is not built.  Count tables only (a label says nothing
+// about how often a k-mer is looked up).
+static int maybe_build_hot(tg_table* t, uint64_t lookups) {
+    tg_ctx* c = t->ctx;
+    if (t->g.hot_slots || t->hot_tried || t->kind != TG_TABLE_COUNT || c->hot_max_keys == 0) return TG_OK;
+    if (!c->hot_force && (t->cap * sizeof(Slot) < (256ull << 20) || lookups < (64ull << 20))) return TG_OK;
+    t->hot_tried = true;
+    unsigned long long* d_bins = nullptr;
+    CU(cudaMalloc(&d_bins, TG_HISTO_BINS * sizeof *d_bins));
+    CU(cudaMemsetAsync(d_bins, 0, TG_HISTO_BINS * sizeof *d_bins, c->stream[0]));
+    CU(launch_histo(t->slots, t->cap, d_bins, c->stream[0]));
+    c->launches++;
+    std::vector<unsigned long long> bins(TG_HISTO_BINS);
+    CU(cudaMemcpyAsync(bins.data(), d_bins, TG_HISTO_BINS * sizeof *d_bins, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(d_bins);
+    // threshold T: the smallest count such that #{count >= T} <= hot_max_keys
+    unsigned long long keys = bins[TG_HISTO_BINS - 1];
+    double covered = (double)bins[TG_HISTO_BINS - 1] * 10001.0, total = covered;
+    for (int cnt = 1; cnt <= 10000; cnt++) total += (double)bins[cnt] * cnt;
+    if (keys > c->hot_max_keys) return TG_OK;
+    uint32_t T = 10001;
+    for (int cnt = 10000; cnt >= 2; cnt--) {
+        if (keys + bins[cnt] > c->hot_max_keys) break;
+        keys += bins[cnt];
+        covered += (double)bins[cnt] * cnt;
+        T = (uint32_t)cnt;
+    }
+    if (!c->hot_force && (keys < 1024 || covered < 0.25 * total)) return TG_OK;
+    if (keys == 0) return TG_OK;
+    const uint64_t want = (uint64_t)((double)keys / c->hot_load) + 1024;
+    if (t->hot_cap < want) {
+        if (t->hot) cudaFree(t->hot);
+        t->hot = nullptr; t->hot_cap = 0;
+        if (cudaMalloc(&t->hot, want * sizeof(Slot)) != cudaSuccess) { cudaGetLastError(); return TG_OK; }
+        t->hot_cap = want;
+    }
+    CU(cudaMemsetAsync(t->hot, 0, t->hot_cap * sizeof(Slot), c->stream[0]));
+    // hottest first, so that they win the direct-mapped places
+    const uint32_t T_hi = T > 0x3FFFFFFFu ? T : T * 4u;
+    CU(launch_hot_fill(t->slots, t->cap, t->hot, t->hot_cap, T_hi, 0xFFFFFFFFu, c->stream[0]));
+    CU(launch_hot_fill(t->slots, t->cap, t->hot, t->hot_cap, T, T_hi - 1, c->stream[0]));
+    c->launches += 2;
+    CU(cudaStreamSynchronize(c->stream[0]));
+    t->hot_keys = keys; t->hot_min = T;
+    t->g.hot_slots = t->hot;
+    t->g.hot_subcap = t->hot_cap;
+    t->g.hot_hints = c->hot_hints;
+    return TG_OK;
+}
+
 struct ReadBatch { uint64_t r0, r1; };
 
 static std::vector<ReadBatch> split_reads(const uint64_t* offs, uint64_t nreads, size_t batch_bytes) {
@@ -961,6 +1055,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
     int rc;
     if ((rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
+    if ((rc = maybe_build_hot(t, offs[nreads] - offs[0]))) return rc;
     const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
     struct Pending { bool live = false; ReadBatch rb; } pend[2];
     auto drain = [&](int b) -> int {   // long-read pass + results back to the caller for the batch in flight on b
@@ -1018,6 +1113,11 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     if (bind(c)) return TG_ERR_CUDA;
     if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_cov_stats_dev: at most 2^31 reads per call");
     if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }
+    if (!t->g.hot_slots && !t->hot_tried) {
+        int rc = sync_all(c);
+        if (rc) return rc;
+        if ((rc = maybe_build_hot(t, nreads * 64))) return rc;     // reads are at least a few dozen windows each
+    }
     const int b = 0;
     CU(c->long_idx[b].ensure(nreads * 4));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
@@ -1038,6 +1138,7 @@ int tg_label_bundles(tg_table* t, const char* recs, const uint64_t* offs, uint64
     if (!t || ((!recs || !offs) && nbundles)) return fail(TG_ERR_ARG, "tg_label_bundles: null argument");
     if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles needs a TG_TABLE_LABEL table");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     if (nbundles == 0) return TG_OK;
     int rc;
@@ -1064,6 +1165,7 @@ int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const
     if (!t || !d_recs || !d_offs) return fail(TG_ERR_ARG, "tg_label_bundles_dev: null argument");
     if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles_dev needs a TG_TABLE_LABEL table");
     tg_ctx* c = t->ctx;
+    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     CU(launch_label_tiles((const uint8_t*)d_recs, nbytes, (const uint64_t*)d_offs, 0, nbundles, first_index, t->k,
                           t->view(), c->sm_count, c->stream[0]));

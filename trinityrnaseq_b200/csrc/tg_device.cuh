@@ -38,6 +38,12 @@ struct Geo {
     unsigned int nparts;         // partitions in the global table
     unsigned int part0;          // first partition held by this view
     unsigned int nlocal;         // partitions held by this view (slots[] has nlocal * subcap entries)
+    // optional HOT table (read paths only): a small, L2-resident, DIRECT-MAPPED cache of the most frequent k-mers
+    // (same slot format and hash; slot = mulhi(hash, hot_subcap)).  Lookups read it first; misses go on to the
+    // DRAM-resident table.
+    const Slot* hot_slots = nullptr;
+    unsigned long long hot_subcap = 0;
+    unsigned int hot_hints = 0;  // bit 0: big-table loads evict-first in L2, bit 1: hot-table loads evict-last
 };
 
 struct TableView {
@@ -141,18 +147,58 @@ __device__ __forceinline__ void table_update(const TableView& t, unsigned long l
     if (s) { if (IS_MAX) atomicMax(&s->val, v); else atomicAdd(&s->val, v); }
 }
 
-// read-only probe: returns val, or 0 when the key is absent.  One 16-B load fetches key and value.
-__device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, const Geo& g, unsigned long long key) {
-    Probe p;
-    if (!probe_home(g, key, p)) return 0u;
-    for (unsigned long long probes = 0; probes <= g.subcap; probes++) {   // bounded: a full partition cannot hang a lookup
-        const uint4 s = __ldcg(reinterpret_cast<const uint4*>(&slots[p.base + p.off]));
-        unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
-        if (k == key) return s.z;
-        if (k == 0ull) return 0u;
-        probe_next(g, p);
+// L2 eviction-priority hints: the hot table should stay, the one-touch sectors of the big table should go first
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_slot_hint(const Slot* p, unsigned long long policy) {
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+
+// Read-only probe: returns val, or 0 when the key is absent or !valid.  One 16-B load fetches key and value.
+// CONVERGENT: every lane of the warp must call it (lanes without a key pass valid = false).  Lanes leave the probe
+// loops at different times; the __syncwarp() between the hot-table phase and the big-table phase brings them back
+// together, so the DRAM-bound loads of a warp are issued as one request and not once per straggler group.
+__device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,
+                                                 bool valid) {
+    const unsigned long long h = mix64(key);
+    unsigned v = 0;
+    bool open = valid;
+    if (g.hot_slots) {
+        // direct-mapped: exactly one 16-B load, no probe chain; a k-mer that lost its place to another is simply
+        // not cached and is found in the big table
+        const Slot* hs = &g.hot_slots[__umul64hi(h, g.hot_subcap)];
+        const uint4 s = (g.hot_hints & 2u) ? ld_slot_hint(hs, l2_policy_evict_last())
+                                           : __ldcg(reinterpret_cast<const uint4*>(hs));
+        const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
+        if (open && k == key) { v = s.z; open = false; }
+        __syncwarp();
     }
-    return 0u;
+    const unsigned part = hash_part(h, g.nparts) - g.part0;
+    if (part >= g.nlocal) open = false;
+    const unsigned long long base = (unsigned long long)part * g.subcap;
+    unsigned long long off = __umul64hi(h, g.subcap);
+    const unsigned long long once = l2_policy_evict_first();
+    for (unsigned long long probes = 0; open && probes <= g.subcap; probes++) {   // bounded: a full partition cannot hang
+        const uint4 s = (g.hot_hints & 1u) ? ld_slot_hint(&slots[base + off], once)
+                                           : __ldcg(reinterpret_cast<const uint4*>(&slots[base + off]));
+        const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
+        if (k == key) { v = s.z; open = false; }
+        else if (k == 0ull) open = false;
+        off = (off + 1 == g.subcap) ? 0ull : off + 1;
+    }
+    __syncwarp();
+    return v;
 }
 
 // ---- k-mer log (partitioned count path) ------------------------------------------------------------------

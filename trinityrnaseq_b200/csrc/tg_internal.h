@@ -81,6 +81,9 @@ cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned i
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);
+// direct-mapped hot cache: slots of `from` with min_val <= val <= max_val -> hot[mulhi(hash, hot_cap)] when free
+cudaError_t launch_hot_fill(const Slot* from, uint64_t from_cap, Slot* hot, uint64_t hot_cap, uint32_t min_val,
+                            uint32_t max_val, cudaStream_t s);
 // re-insert every live slot of `from` whose value is >= min_val into `to` (growth: min_val 0; compaction: min count)
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
                           cudaStream_t s);

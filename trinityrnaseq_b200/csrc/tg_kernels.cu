@@ -656,6 +656,28 @@ k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
 }
 
+// direct-mapped cache fill: every live slot with val >= min_val goes to hot[mulhi(hash, hot_cap)] if that place is free
+__global__ void __launch_bounds__(256)
+k_hot_fill(const Slot* __restrict__ from, uint64_t from_cap, Slot* hot, uint64_t hot_cap, uint32_t min_val, uint32_t max_val) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+        const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
+        if (key == 0ull || s.z < min_val || s.z > max_val) continue;
+        Slot* h = &hot[__umul64hi(mix64(key), hot_cap)];
+        if (atomicCAS(&h->key, 0ull, key) == 0ull) h->val = s.z;
+    }
+}
+
+cudaError_t launch_hot_fill(const Slot* from, uint64_t from_cap, Slot* hot, uint64_t hot_cap, uint32_t min_val,
+                            uint32_t max_val, cudaStream_t s) {
+    TimedLaunch timed("k_hot_fill", s);
+    if (from_cap == 0 || hot_cap == 0) return cudaSuccess;
+    uint64_t blocks = (from_cap + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_hot_fill<<<(int)blocks, 256, 0, s>>>(from, from_cap, hot, hot_cap, min_val, max_val);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
                           cudaStream_t s) {
     TimedLaunch timed("k_rehash", s);
@@ -727,6 +749,53 @@ __device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v
     return tot;
 }
 
+// Median of n <= PR_MAXWIN u32 values held in shared memory, by one warp, WITHOUT sorting: a radix select on the bits
+// below the highest set bit of the maximum (coverage values are small: a handful of bit rounds), each round one
+// predicate per element and one redux.sync.  Returns median_coverage() of fastaToKmerCoverageStats.cpp:337-347:
+// odd n -> the middle element, even n -> the (wrapping) u32 mean of the two middle elements.
+__device__ __forceinline__ uint32_t warp_median_u32(const uint32_t* __restrict__ v, int n, int lane) {
+    constexpr int PER = PR_MAXWIN / 32;
+    unsigned x[PER];
+    unsigned mx = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int p = i * 32 + lane;
+        x[i] = p < n ? v[p] : 0u;
+        mx = max(mx, x[i]);
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
+    unsigned prefix = 0, k = k1;
+    for (int b = 31 - __clz((int)(mx | 1u)); b >= 0; b--) {
+        const unsigned hi_mask = ~((2u << b) - 1u);        // the bits above b (0 for b = 31)
+        unsigned cnt = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if (i * 32 < n) {
+                const bool live = i * 32 + lane < n;
+                cnt += (live && ((x[i] ^ prefix) & hi_mask) == 0u && !((x[i] >> b) & 1u)) ? 1u : 0u;
+            }
+        }
+        cnt = __reduce_add_sync(FULL, cnt);                // elements that share the prefix and have bit b clear
+        if (k >= cnt) { prefix |= 1u << b; k -= cnt; }
+    }
+    const unsigned x1 = prefix;                            // the element of rank k1
+    if (k1 == k2) return x1;
+    unsigned le = 0, nxt = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        if (i * 32 < n) {
+            const bool live = i * 32 + lane < n;
+            le += (live && x[i] <= x1) ? 1u : 0u;
+            if (live && x[i] > x1) nxt = min(nxt, x[i]);
+        }
+    }
+    le = __reduce_add_sync(FULL, le);
+    nxt = __reduce_min_sync(FULL, nxt);
+    const unsigned x2 = le >= k2 + 1u ? x1 : nxt;          // the element of rank k2 = k1 + 1
+    return (uint32_t)(x1 + x2) / 2u;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // coverage statistics of one read (fastaToKmerCoverageStats.cpp:300-402)
 // ---------------------------------------------------------------------------------------------------------
@@ -747,25 +816,26 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
     gsync<GS>();
 
     unsigned long long part = 0;
-    for (int pb = 0; pb < nwin; pb += GS) {     // every lane runs every iteration, so the warp can reconverge in it
+    for (int pb = 0; pb < nwin; pb += GS) {     // every lane runs every iteration: table_lookup is warp-convergent
         const int p = pb + gtid;
         const bool live = p < nwin;
-        unsigned v = 0;
+        bool ok = false;
+        unsigned long long key = 0ull;
         if (live) {
             const int c = p >> 5, o = p & 31;
             const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
             if (!bad) {
                 const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
                 const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-                unsigned long long key = make_key(f0, f1);
+                key = make_key(f0, f1);
                 if (canonical) {
                     const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
                     key = kr < key ? kr : key;
                 }
-                v = table_lookup(slots, geo, key);
+                ok = true;
             }
         }
-        __syncwarp();                              // probe loops end at different times per lane
+        unsigned v = table_lookup(slots, geo, key, ok);
         if (live) {
             if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
             cov[p] = v;
@@ -792,12 +862,16 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
         }
         sd = acc;
     }
-    // median: sort ascending, odd -> middle, even -> u32 (wrapping) mean of the two middles
-    const unsigned n2 = next_pow2((unsigned)nwin);
-    for (unsigned p = nwin + gtid; p < n2; p += GS) cov[p] = 0xFFFFFFFFu;
-    gsync<GS>();
-    bitonic_sort<GS, uint32_t>(cov, n2, gtid);
-    median = (nwin & 1) ? cov[nwin / 2] : (uint32_t)(cov[(nwin - 1) / 2] + cov[nwin / 2]) / 2u;
+    // median: odd -> middle, even -> u32 (wrapping) mean of the two middles
+    if (GS == 32) {
+        median = warp_median_u32(cov, nwin, gtid);         // selection, no sort
+    } else {
+        const unsigned n2 = next_pow2((unsigned)nwin);
+        for (unsigned p = nwin + gtid; p < n2; p += GS) cov[p] = 0xFFFFFFFFu;
+        gsync<GS>();
+        bitonic_sort<GS, uint32_t>(cov, n2, gtid);
+        median = (nwin & 1) ? cov[nwin / 2] : (uint32_t)(cov[(nwin - 1) / 2] + cov[nwin / 2]) / 2u;
+    }
     mean = avg;
     stdev = sd;    // meaningful in gtid 0 only
 }
@@ -924,30 +998,53 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
     if (gtid == 0) *nhits_p = 0;
     pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
     gsync<GS>();
-    for (int pb = 0; pb < nwin; pb += GS) {
+    for (int pb = 0; pb < nwin; pb += GS) {         // every lane runs every iteration: table_lookup is warp-convergent
         const int p = pb + gtid;
+        bool do_f = false, do_r = false;
+        unsigned f0 = 0, f1 = 0;
         if (p < nwin) {
             const int c = p >> 5, o = p & 31;
             const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
             if (!bad) {                     // a window with a non-ACGT character can never equal a table k-mer
-                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-                if (window_entropy_ok(lut, f0, f1, mk, false)) {
-                    const unsigned v = table_lookup(slots, geo, make_key(f0, f1));
-                    if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
-                }
-                if (!strand && window_entropy_ok(lut, f0, f1, mk, true)) {
-                    const unsigned v = table_lookup(slots, geo, make_key(rc_plane(f0, k), rc_plane(f1, k)));
-                    if (v) hits[atomicAdd(nhits_p, 1u)] = (int32_t)v - 1;
-                }
+                f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+                f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+                do_f = window_entropy_ok(lut, f0, f1, mk, false);
+                do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
             }
         }
-        __syncwarp();                       // probe loops end at different times per lane
+        const unsigned vf = table_lookup(slots, geo, make_key(f0, f1), do_f);
+        if (vf) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vf - 1;
+        if (!strand) {
+            const unsigned vr = table_lookup(slots, geo, make_key(rc_plane(f0, k), rc_plane(f1, k)), do_r);
+            if (vr) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vr - 1;
+        }
     }
     gsync<GS>();
     const int n = (int)*nhits_p;
     int b = -1, sc = 0;
-    if (n >= 2) {
+    if (n >= 2 && GS == 32) {
+        // The reference sorts the hits and scans the runs (ReadsToTranscripts.cc:253-268): a label with m hits scores
+        // m-1, the largest label m-2, strict '>' while ascending => ties go to the smaller label.  The same result
+        // without a sort: walk the DISTINCT labels in ascending order (almost always one or two), one warp min and
+        // one warp count per label.
+        int last = -1;
+        for (int p = gtid; p < n; p += 32) last = max(last, hits[p]);
+        last = __reduce_max_sync(FULL, last);
+        int cur = -1;
+        while (true) {
+            int mn = 0x7FFFFFFF;
+            for (int p = gtid; p < n; p += 32) { const int h = hits[p]; if (h > cur) mn = min(mn, h); }
+            const int L = __reduce_min_sync(FULL, mn);
+            if (L == 0x7FFFFFFF) break;
+            unsigned m = 0;
+            for (int p = gtid; p < n; p += 32) m += hits[p] == L ? 1u : 0u;
+            m = __reduce_add_sync(FULL, m);
+            const int s = (int)m - 1 - (L == last ? 1 : 0);
+            if (s > sc) { sc = s; b = L; }
+            cur = L;
+        }
+        if (sc <= 0) { b = -1; sc = 0; }
+    } else if (n >= 2) {
         const unsigned n2 = next_pow2((unsigned)n);
         for (unsigned p = n + gtid; p < n2; p += GS) hits[p] = 0x7FFFFFFF;
         gsync<GS>();
