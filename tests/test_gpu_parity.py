@@ -110,3 +110,43 @@ def test_assign(gpu_ctx, oracle, data, strand):
     assigned = ob >= 0
     np.testing.assert_array_equal(gp[assigned], op[assigned])
     assert assigned.sum() > 1000
+
+
+@pytest.mark.parametrize("strand", [False, True])
+@pytest.mark.parametrize("k", [25, 24])
+def test_assign_both_orientations(gpu_ctx, oracle, data, strand, k):
+    """The label table keeps one label per orientation of a canonical key: bundles that hold a sequence AND its
+    reverse complement (in different bundles, so the two orientations carry different labels), k-mers shared by
+    several bundles (highest index wins per orientation), and -- for even k -- palindromic k-mers, whose forward and
+    reverse-complement look-ups are the same table entry."""
+    txs, _ = data
+    rng = np.random.default_rng(5)
+    half = synth.ALPHA[rng.integers(0, 4, k // 2)].tobytes()
+    pal = half + synth.revcomp(half) if k % 2 == 0 else half + b"A" + synth.revcomp(half)
+    a, b, c = txs[0][:400], txs[1][:400], txs[2][:300]
+    bundles = [a + b"X" + b[:200],                    # 0
+               synth.revcomp(a)[:250] + b"X" + c,     # 1: the far end of a, reverse-complemented
+               b"G" * 5 + pal + b"C" * 7 + b"X" + b,  # 2: palindrome (even k) + all of b (re-labels bundle 0's part)
+               synth.revcomp(c) + b"X" + synth.revcomp(b)[:180],   # 3
+               pal + b"T" + a[100:180]]               # 4: the palindrome again, and a piece of a
+    brecs, boffs = tg.records_from_sequences(bundles)
+    srcs = [a, b, c, synth.revcomp(a), synth.revcomp(b), synth.revcomp(c), b"G" * 5 + pal + b"C" * 7 + b[:60],
+            synth.revcomp(b"G" * 5 + pal + b"C" * 7 + b[:60])]
+    reads = []
+    for s in srcs:
+        for off in range(0, max(1, len(s) - 60), 13):
+            reads.append(s[off:off + 60 + (off % 37)])
+    reads += [pal, pal + b"A", synth.revcomp(pal + b"A")]
+    recs, offs = tg.records_from_sequences(reads)
+    ot = oracle.BundleTable(k)
+    ot.label(brecs, boffs)
+    ob, op, osc = ot.assign(recs, offs, strand=strand)
+    with tg.BundleKmerTable(gpu_ctx, k, expected_keys=100) as bt:       # small hint: the table also has to grow
+        bt.label_bundles(brecs, boffs)
+        assert bt.size() == ot.size()
+        gb, gp, gsc = bt.assign_reads(recs, offs, strand=strand)
+    np.testing.assert_array_equal(gb, ob)
+    np.testing.assert_array_equal(gsc, osc)
+    assigned = ob >= 0
+    np.testing.assert_array_equal(gp[assigned], op[assigned])
+    assert assigned.sum() > 50 and len(set(ob[assigned].tolist())) >= 4

@@ -20,9 +20,9 @@ namespace tg {
 
 struct __align__(16) Slot {
     unsigned long long key;   // 0 = empty, else KEY_TAG | planes
-    unsigned int val;         // count (count tables) or bundle index + 1 (label tables)
-    unsigned int aux;         // unused (keeps the slot 16-B aligned inside one 32-B sector)
-};
+    unsigned int val;         // count (count tables); label tables: bundle index + 1 of the k-mer that IS the key
+    unsigned int aux;         // label tables: bundle index + 1 of the k-mer whose REVERSE COMPLEMENT is the key
+};                            // (count tables leave aux 0; it keeps the slot 16-B aligned inside one 32-B sector)
 
 constexpr unsigned long long KEY_TAG = 1ull << 63;
 
@@ -147,6 +147,23 @@ __device__ __forceinline__ void table_update(const TableView& t, unsigned long l
     if (s) { if (IS_MAX) atomicMax(&s->val, v); else atomicAdd(&s->val, v); }
 }
 
+// Label tables (ReadsToTranscripts) are keyed by the canonical form min(k-mer, reverse complement) and keep TWO
+// labels per slot: val for the bundle k-mer that equals the key, aux for the bundle k-mer whose reverse complement
+// equals the key.  The reference looks every read window up twice in a table of forward strings -- once as it is,
+// once reverse-complemented (ReadsToTranscripts.cc:236-250); here both answers sit in the one 16-B slot, so a
+// double-stranded read costs one probe per window instead of two (and the second one was nearly always a miss
+// that had to walk to an empty slot).  `rc` says which orientation the caller's k-mer has relative to the key.
+// Returns true when this call gave the (key, orientation) its first label, i.e. a new distinct forward k-mer.
+__device__ __forceinline__ bool table_label_max(const TableView& t, unsigned long long key, bool rc, unsigned lab) {
+    Probe p;
+    if (!probe_home(t.g, key, p)) { atomicExch(t.error, 2); return false; }
+    const unsigned long long cur = __ldcg(&t.slots[p.base + p.off].key);
+    unsigned dummy = 0;
+    Slot* s = table_upsert_slot(t, key, p, cur, dummy);
+    if (!s || lab == 0u) return false;
+    return atomicMax(rc ? &s->aux : &s->val, lab) == 0u;
+}
+
 // L2 eviction-priority hints: the hot table should stay, the one-touch sectors of the big table should go first
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     unsigned long long p;
@@ -169,10 +186,10 @@ __device__ __forceinline__ uint4 ld_slot_hint(const Slot* p, unsigned long long 
 // CONVERGENT: every lane of the warp must call it (lanes without a key pass valid = false).  Lanes leave the probe
 // loops at different times; the __syncwarp() between the hot-table phase and the big-table phase brings them back
 // together, so the DRAM-bound loads of a warp are issued as one request and not once per straggler group.
-__device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,
-                                                 bool valid) {
+__device__ __forceinline__ uint2 table_lookup2(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,
+                                                bool valid) {
     const unsigned long long h = mix64(key);
-    unsigned v = 0;
+    uint2 v = make_uint2(0u, 0u);   // {val, aux}
     bool open = valid;
     if (g.hot_slots) {
         // direct-mapped: exactly one 16-B load, no probe chain; a k-mer that lost its place to another is simply
@@ -181,7 +198,7 @@ __device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots,
         const uint4 s = (g.hot_hints & 2u) ? ld_slot_hint(hs, l2_policy_evict_last())
                                            : __ldcg(reinterpret_cast<const uint4*>(hs));
         const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
-        if (open && k == key) { v = s.z; open = false; }
+        if (open && k == key) { v = make_uint2(s.z, s.w); open = false; }
         __syncwarp();
     }
     const unsigned part = hash_part(h, g.nparts) - g.part0;
@@ -193,12 +210,16 @@ __device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots,
         const uint4 s = (g.hot_hints & 1u) ? ld_slot_hint(&slots[base + off], once)
                                            : __ldcg(reinterpret_cast<const uint4*>(&slots[base + off]));
         const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
-        if (k == key) { v = s.z; open = false; }
+        if (k == key) { v = make_uint2(s.z, s.w); open = false; }
         else if (k == 0ull) open = false;
         off = (off + 1 == g.subcap) ? 0ull : off + 1;
     }
     __syncwarp();
     return v;
+}
+__device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,
+                                                 bool valid) {
+    return table_lookup2(slots, g, key, valid).x;
 }
 
 // ---- k-mer log (partitioned count path) ------------------------------------------------------------------

@@ -42,7 +42,7 @@ struct FlatSmem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(CT_THREADS, 4)
+__global__ void __launch_bounds__(CT_THREADS, MODE == 0 ? 4 : 3)    // LABEL carries labels + orientation bits: no spills at 3
 k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, TableView t,
              const uint64_t* __restrict__ offs, uint64_t nrec, uint32_t first_index, uint64_t rec_base) {
     __shared__ FlatSmem sm;
@@ -115,6 +115,7 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                 unsigned long long cur[4];
                 unsigned cnt[4];
                 uint32_t lab[4];
+                unsigned rcs = 0;      // LABEL: bit u set = window u is the reverse complement of its (canonical) key
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int s = g + u;
@@ -131,6 +132,9 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                         // a valid window lies inside one record, so label < nrec whenever we advance
                         if (!bad) while (g0 + s >= next_off) { label++; next_off = offs[label + 1]; }
                         lab[u] = first_index + label + 1;
+                        // label tables are keyed canonically with one label per orientation (tg_device.cuh)
+                        const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                        if (kr < kf) { kf = kr; rcs |= 1u << u; }
                     }
                     key[u] = bad ? 0ull : kf;
                     cnt[u] = 1;
@@ -150,10 +154,14 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
-                        Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
-                        if (sl) {
-                            if (MODE == MODE_COUNT) atomicAdd(&sl->val, cnt[u]);
-                            else atomicMax(&sl->val, lab[u]);
+                        if (MODE == MODE_COUNT) {
+                            Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
+                            if (sl) atomicAdd(&sl->val, cnt[u]);
+                        } else {
+                            // `claimed` counts distinct FORWARD k-mers (NonRedKmerTable's size): first label of a field
+                            unsigned slots_claimed = 0;
+                            Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], slots_claimed);
+                            if (sl && atomicMax((rcs >> u) & 1u ? &sl->aux : &sl->val, lab[u]) == 0u) claimed++;
                         }
                     }
                 __syncwarp(act);   // lanes leave the probe loops at different times: reconverge before the next group
@@ -622,11 +630,13 @@ k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ val
         unsigned p0, p1;
         packed_to_planes(keys[i], k, p0, p1);
         unsigned long long key = make_key(p0, p1);
-        if (canonical) {
-            const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
-            key = kr < key ? kr : key;
+        const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
+        if (IS_MAX) {          // label table: (forward k-mer, bundle index + 1) -> the field of its orientation
+            if (table_label_max(t, kr < key ? kr : key, kr < key, vals[i])) claimed++;
+        } else {
+            if (canonical) key = kr < key ? kr : key;
+            table_update<false>(t, key, vals[i], claimed);
         }
-        table_update<IS_MAX>(t, key, vals[i], claimed);
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
@@ -649,8 +659,13 @@ k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key == 0ull || s.z < min_val) continue;
-        if (is_label) table_update<true>(to, key, s.z, claimed); else table_update<false>(to, key, s.z, claimed);
+        if (key == 0ull) continue;
+        if (is_label) {        // both orientations' labels move with the key
+            if (s.z && table_label_max(to, key, false, s.z)) claimed++;
+            if (s.w && table_label_max(to, key, true, s.w)) claimed++;
+        } else if (s.z >= min_val) {
+            table_update<false>(to, key, s.z, claimed);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
@@ -998,29 +1013,44 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
     if (gtid == 0) *nhits_p = 0;
     pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
     gsync<GS>();
+    unsigned nh = 0;                                // GS == 32: hits appended so far (warp-uniform)
     for (int pb = 0; pb < nwin; pb += GS) {         // every lane runs every iteration: table_lookup is warp-convergent
         const int p = pb + gtid;
-        bool do_f = false, do_r = false;
-        unsigned f0 = 0, f1 = 0;
+        bool do_f = false, do_r = false, is_rc = false, pal = false;
+        unsigned long long key = 0ull;
         if (p < nwin) {
             const int c = p >> 5, o = p & 31;
             const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
             if (!bad) {                     // a window with a non-ACGT character can never equal a table k-mer
-                f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-                f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
                 do_f = window_entropy_ok(lut, f0, f1, mk, false);
                 do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
+                const unsigned long long kf = make_key(f0, f1), kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                is_rc = kr < kf; pal = kr == kf;
+                key = is_rc ? kr : kf;
             }
         }
-        const unsigned vf = table_lookup(slots, geo, make_key(f0, f1), do_f);
-        if (vf) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vf - 1;
-        if (!strand) {
-            const unsigned vr = table_lookup(slots, geo, make_key(rc_plane(f0, k), rc_plane(f1, k)), do_r);
+        // ONE probe answers both passes of the reference (forward window, then reverse-complemented window): the slot
+        // of the canonical key holds the label of the bundle k-mer equal to the key (val) and of the bundle k-mer whose
+        // reverse complement is the key (aux).  A palindrome (even k only) is its own reverse complement.
+        const uint2 v = table_lookup2(slots, geo, key, do_f || do_r);
+        const unsigned vf = do_f ? (is_rc ? v.y : v.x) : 0u;
+        const unsigned vr = do_r ? ((is_rc || pal) ? v.x : v.y) : 0u;
+        if (GS == 32) {
+            const unsigned lt = (1u << gtid) - 1u;
+            const unsigned mf = __ballot_sync(FULL, vf != 0u), mr = __ballot_sync(FULL, vr != 0u);
+            if (vf) hits[nh + __popc(mf & lt)] = (int32_t)vf - 1;
+            nh += __popc(mf);
+            if (vr) hits[nh + __popc(mr & lt)] = (int32_t)vr - 1;
+            nh += __popc(mr);
+        } else {
+            if (vf) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vf - 1;
             if (vr) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vr - 1;
         }
     }
     gsync<GS>();
-    const int n = (int)*nhits_p;
+    const int n = GS == 32 ? (int)nh : (int)*nhits_p;
     int b = -1, sc = 0;
     if (n >= 2 && GS == 32) {
         // The reference sorts the hits and scans the runs (ReadsToTranscripts.cc:253-268): a label with m hits scores
