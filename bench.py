@@ -294,6 +294,9 @@ def main():
     ap.add_argument("--stats-table", default="auto", choices=["auto", "min2", "full"],
                     help="min2: statistics read the device-side `dump -L 2` table (bit-identical, see DESIGN.md); "
                          "auto = full table on one GPU, min2 when the table is sharded (it is what gets all-gathered)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
+                    help="multi-GPU k-mer exchange: peer = phase 1 stores into the owners' logs over NVLink (fused), "
+                         "collective = NCCL all-to-all of the bins; auto = peer when peer memory maps")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -364,7 +367,7 @@ def main():
     else:
         from trinityrnaseq_b200 import sharded
         eng = sharded.DeviceEngine(ctx, K, True)
-        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=expected_total // world + 1)
+        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=expected_total // world + 1, exchange=args.exchange)
         kc = sc.table
 
         def count_dev(recs_ptr):
@@ -422,6 +425,21 @@ def main():
     ktimes = ctx.kernel_times()
     ctx.set("kernel_timing", 0)
 
+    # multi-GPU: host-clock milliseconds per phase of one more step (a sync on both sides of every phase, so the
+    # sum exceeds the pipelined step; it says where the time goes)
+    phases = None
+    if world > 1:
+        sc.profile = {}
+        device_step()
+        barrier()
+        phases = {k_: round(max_over_ranks(v), 2) for k_, v in sorted(sc.profile.items())}
+        sc.profile = None
+        config["table_sharding"] = config["table_sharding"].replace(
+            "k-mer log all-to-all (NCCL)",
+            "k-mers stored into the owners' logs over NVLink peer memory by the partition kernel itself"
+            if sc.exchange == "peer" else "k-mer log all-to-all (NCCL)")
+        config["exchange"] = sc.exchange
+
     # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------------
     recs_host, recs_owner = ctx.pinned((nbytes,), np.uint8)
     ctx.d2h(d_recs, recs_host)
@@ -470,6 +488,8 @@ def main():
         r2t = bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host, nreads, read_len,
                         max(1, min(args.steps, 3)), not args.no_cpu_baseline)
 
+    if world > 1:
+        sc.close()                       # collective: unmap the peer logs before anybody frees its own
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -537,6 +557,8 @@ def main():
                      "load": round(tinfo["distinct"] / tinfo["capacity"], 3),
                      "stats_table_slots": qinfo["capacity"], "stats_table_kmers": qinfo["distinct"]},
            "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
+    if phases is not None:
+        out["multi_gpu"] = {"exchange": sc.exchange, "phases_ms_synced": phases, "bins": sc.nparts, "bins_per_rank": sc.lp}
     if r2t is not None:
         out["reads_to_transcripts"] = r2t
     print(json.dumps(out))

@@ -158,6 +158,24 @@ int tg_count_partition_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int
                            uint32_t cap, void* d_keys, void* d_cursor, void* d_hpoly);
 int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_cursor, void* d_hpoly, uint32_t nsrc,
                             uint32_t cap);
+/* Fused phase 1 + exchange (the path `north_star` asks for: k-mers routed to their owner GPU while counting).  One
+ * process per GPU; every rank allocates its receive log [nranks][nbins/nranks][cap] u64 with tg_dev_alloc, exports it
+ * with tg_ipc_export, and opens the other ranks' handles with tg_ipc_open (CUDA IPC; peer access over NVLink is
+ * enabled lazily).  tg_count_partition_peers_dev is tg_count_partition_dev whose entries are stored straight into
+ * segment `my_rank` of the OWNER's receive log (d_owner_keys[r] = rank r's log, the local pointer for r = my_rank):
+ * the transfer overlaps the rolling of the next tile, no send buffer and no separate all-to-all of keys.  d_cursor
+ * [nbins] stays local; after the call (and a tg_sync) the ranks exchange cursor rows -- rank r needs
+ * cursor[r*lp .. (r+1)*lp) of every rank as its [nranks][lp] cursor array for tg_table_replay_log_dev -- which is also
+ * the point after which every rank's stores have landed.  nbins/nranks must be a power of two, nranks <= 8.
+ * Replaces the exchange the reference's retired MPI build did with one blocking MPI_Send per k-mer
+ * (Inchworm/src/mpi_deprecated/MPIinchworm.cpp:519-531, owner rule :1236-1257). */
+#define TG_IPC_HANDLE_BYTES 64
+int tg_ipc_export(tg_ctx* ctx, void* dptr, uint8_t* handle /* TG_IPC_HANDLE_BYTES */);
+int tg_ipc_open(tg_ctx* ctx, const uint8_t* handle, void** dptr);
+int tg_ipc_close(tg_ctx* ctx, void* dptr);
+int tg_count_partition_peers_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
+                                 uint32_t cap, uint32_t nranks, uint32_t my_rank, void* const* d_owner_keys,
+                                 void* d_cursor, void* d_hpoly);
 int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
                      void* d_median, void* d_mean, void* d_stdev);
 int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,

@@ -80,10 +80,59 @@ class StandinTable:
         return kc.coverage_stats(recs, offs)
 
 
+class StandinPeers:
+    def __init__(self, maps, rkeys, world):
+        self.maps, self.rkeys, self.world, self.ok = maps, rkeys, world, True
+
+
 class StandinEngine:
-    def __init__(self, k, canonical):
+    """peer_dir: a directory all rank processes share; given one, the engine offers the "peer" exchange with the
+    receive logs as memory-mapped files (what CUDA IPC + NVLink stores are on the device)."""
+
+    def __init__(self, k, canonical, peer_dir=None):
         self.k, self.canonical = k, canonical
         self.table = None
+        self.peer_dir = peer_dir
+        self._gen = 0
+        if peer_dir is None:              # no shared directory: ShardedKmerCounter must pick the collective exchange
+            self.open_peer_logs = None
+
+    def sync(self):
+        pass
+
+    def open_peer_logs(self, dist, group, nbins, cap):
+        import os
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self._gen += 1
+        path = lambda r: os.path.join(self.peer_dir, f"log{self._gen}_{r}.bin")
+        mine = np.memmap(path(rank), dtype=np.int64, mode="w+", shape=(world, nbins // world, cap))
+        mine.flush()
+        dist.barrier(group=group)
+        maps = [mine if r == rank else np.memmap(path(r), dtype=np.int64, mode="r+", shape=(world, nbins // world, cap))
+                for r in range(world)]
+        return StandinPeers(maps, torch.from_numpy(mine), world)
+
+    def unmap_peer_logs(self, peers):
+        for m in peers.maps:
+            m.flush()
+        peers.maps = []
+
+    def free_peer_log(self, peers):
+        peers.rkeys = None
+
+    def new_cursors(self, nbins):
+        return (torch.zeros((nbins,), dtype=torch.int32), torch.zeros((nbins,), dtype=torch.int32),
+                torch.zeros((8,), dtype=torch.int64))
+
+    def partition_peers(self, recs, nbytes, peers, cursor, hpoly, nbins, cap, rank):
+        lp = nbins // peers.world
+        scratch = torch.zeros((nbins, cap), dtype=torch.int64)
+        self.partition(recs, nbytes, scratch, cursor, hpoly)
+        for b in range(nbins):                      # entry (bin b, pos) -> owner b // lp, segment [rank], bin b % lp
+            n = int(cursor[b])
+            peers.maps[b // lp][rank, b % lp, :n] = scratch[b, :n].numpy()
+        for m in peers.maps:
+            m.flush()
 
     def create_shard(self, subcap, nparts, part0, nlocal):
         self.table = StandinTable(self.k, self.canonical, subcap, nparts, part0, nlocal)

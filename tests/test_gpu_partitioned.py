@@ -194,6 +194,85 @@ def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
         ctx.dev_free(p)
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world):
+    """The fused phase 1 + exchange (tg_count_partition_peers_dev) with N ranks emulated on one GPU: every "rank" runs
+    phase 1 with the pointers of all N receive logs and writes segment [rank] of each; what peer memory adds on a real
+    box is only where those pointers point.  Each owner then replays its log [src][lp][cap] with the cursor rows the
+    ranks would exchange.  Result: bit-exact against the oracle, and identical to the collective exchange."""
+    _, reads = data
+    k = 25
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, k, True, 1)
+    subcap, nparts, lp = tg.sharded.shard_geometry(world, len(ok) // world + 1000, part_bytes=64 << 10)
+    assert nparts == world * lp and lp > 1 and lp & (lp - 1) == 0
+    shards = [tg.KmerCounter.sharded(ctx, k, True, subcap, nparts, r * lp, lp) for r in range(world)]
+    ranges = [tg.sharded.record_range(offs, r, world) for r in range(world)]
+    cap = tg.sharded.log_capacity(max(int(offs[r1] - offs[r0]) for r0, r1 in ranges), nparts)
+    rlogs = [ctx.dev_alloc(nparts * cap * 8) for _ in range(world)]       # rank r's receive log [world][lp][cap]
+    for p in rlogs:
+        ctx.memset(p, 0xEE, nparts * cap * 8)                             # stale bytes must never be replayed
+    curs = []
+    hpoly = ctx.dev_alloc(64)
+    ctx.memset(hpoly, 0, 64)
+    for r, (r0, r1) in enumerate(ranges):
+        sub = recs[int(offs[r0]):int(offs[r1])]
+        d = _dev_records(ctx, sub)
+        cur = ctx.dev_alloc(nparts * 4)
+        ctx.memset(cur, 0, nparts * 4)
+        shards[r].partition_peers_dev(d, sub.nbytes, nparts, cap, r, rlogs, cur, hpoly)
+        ctx.sync()
+        ctx.dev_free(d)
+        curs.append(cur)
+    hp_host = ctx.d2h(hpoly, 64, np.uint64)
+    for dst in range(world):
+        rcur = ctx.dev_alloc(nparts * 4)                                   # [world][lp]: row src = src's cursors of my bins
+        for src in range(world):
+            ctx.d2d(rcur, curs[src], lp * 4, dst_off=src * lp * 4, src_off=dst * lp * 4)
+        hp_d = ctx.dev_alloc(64)
+        ctx.h2d(hp_d, hp_host)
+        shards[dst].replay_log_dev(rlogs[dst], rcur, hp_d, world, cap)
+        ctx.sync()
+        ctx.dev_free(hp_d)
+        ctx.dev_free(rcur)
+    assert sum(s.size() for s in shards) == len(ok)
+    parts = [s.dump() for s in shards]
+    allk = np.concatenate([p[0] for p in parts])
+    allc = np.concatenate([p[1] for p in parts])
+    order = np.argsort(allk, kind="stable")
+    np.testing.assert_array_equal(allk[order], ok)
+    np.testing.assert_array_equal(allc[order], oc)
+    # argument checks: bins per rank must be a power of two, at most 8 ranks, rank inside
+    cur = curs[0]
+    with pytest.raises(tg.TrinityGpuError):
+        shards[0].partition_peers_dev(rlogs[0], 0, 3 * world, cap, 0, rlogs, cur, hpoly)
+    with pytest.raises(tg.TrinityGpuError):
+        shards[0].partition_peers_dev(rlogs[0], 0, nparts, cap, world, rlogs, cur, hpoly)
+    for t in shards:
+        t.close()
+    for p in rlogs + curs + [hpoly]:
+        ctx.dev_free(p)
+
+
+def test_ipc_handle_roundtrip_api(ctx):
+    """tg_ipc_export gives a 64-byte handle for a tg_dev_alloc allocation; opening it in the SAME process is refused by
+    CUDA (handles are for other processes) and must surface as an error, not a crash"""
+    from trinityrnaseq_b200 import _lib
+    L = _lib.lib()
+    p = ctx.dev_alloc(1 << 20)
+    h = (C.c_uint8 * _lib.TG_IPC_HANDLE_BYTES)()
+    _lib.check(L.tg_ipc_export(ctx._h, p, h))
+    assert any(bytes(h))
+    q = C.c_void_p()
+    rc = L.tg_ipc_open(ctx._h, h, C.byref(q))
+    if rc == 0:                      # some drivers allow it; then it must close cleanly
+        _lib.check(L.tg_ipc_close(ctx._h, q))
+    else:
+        assert rc == _lib.TG_ERR_CUDA
+    ctx.sync()
+    ctx.dev_free(p)
+
+
 def test_partition_log_overflow_is_reported(ctx, data):
     _, reads = data
     recs, offs = tg.records_from_sequences(reads)

@@ -1,6 +1,7 @@
 """CPU, world_size 2 and 3 over gloo: the host-side logic of the hash-sharded table (trinityrnaseq_b200.sharded) --
-geometry, read sharding by offset, bin ownership, the equal-split all-to-all and its receive layout, the all-gather
-into a full replica, the reductions -- driven through a stand-in engine (tests/standin_engine.py; the product
+geometry, read sharding by offset, bin ownership, both exchanges (the equal-split all-to-all and the "peer" exchange
+where phase 1 writes into the owners' receive logs -- memory-mapped files stand in for CUDA IPC memory) and their
+[src, lp, cap] receive layout, the all-gather into a full replica, the reductions -- driven through a stand-in engine (tests/standin_engine.py; the product
 engine is CUDA and is covered by tests/test_gpu_partitioned.py and the multi-GPU bench)."""
 import os
 import sys
@@ -26,7 +27,7 @@ def _make_reads():
     return reads
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, exchange):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import oracle_py as orc
@@ -41,8 +42,9 @@ def _worker(rank, world, port, out_dir):
         ok, oc = orc.jf_count(recs, k, True, 1)
         r0, r1 = sharded.record_range(offs, rank, world)
         mine = recs[int(offs[r0]):int(offs[r1])]
-        eng = standin_engine.StandinEngine(k, True)
+        eng = standin_engine.StandinEngine(k, True, peer_dir=out_dir if exchange == "peer" else None)
         sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=len(ok) // world + 64, part_bytes=8 << 10)
+        assert sc.exchange == exchange          # "auto" picks the peer exchange exactly when the engine offers it
         assert sc.nparts == world * sc.lp and sc.lp >= 2
         assert sc.table.part0 == rank * sc.lp and sc.table.nlocal == sc.lp
         sc.add_records_dev(torch.from_numpy(mine.copy()) if len(mine) else torch.zeros(0, dtype=torch.uint8), len(mine))
@@ -87,15 +89,16 @@ def _worker(rank, world, port, out_dir):
             gm2, _, gsd2 = rep2.coverage_stats(mine, sub_offs)
             np.testing.assert_array_equal(gm2, om[r0:r1])
             np.testing.assert_array_equal(gsd2.view(np.uint32), osd[r0:r1].view(np.uint32))
+        sc.close()
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_counter_over_gloo(world, tmp_path):
-    port = 29500 + (os.getpid() % 400) + world
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("world,exchange", [(2, "collective"), (3, "collective"), (2, "peer"), (3, "peer")])
+def test_sharded_counter_over_gloo(world, exchange, tmp_path):
+    port = 29500 + (os.getpid() % 400) + world + (10 if exchange == "peer" else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), exchange), nprocs=world, join=True)
     from oracle import oracle_py as orc
     recs, offs = records_from_sequences(_make_reads())
     ok, oc = orc.jf_count(recs, 25, True, 1)

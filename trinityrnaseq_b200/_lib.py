@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtrinity_gpu.so")
 TG_OK, TG_ERR_CUDA, TG_ERR_ARG, TG_ERR_NOMEM, TG_ERR_TABLE, TG_ERR_NOGPU = 0, -1, -2, -3, -4, -5
 TG_TABLE_COUNT, TG_TABLE_LABEL = 0, 1
 TG_HISTO_BINS = 10002
+TG_IPC_HANDLE_BYTES = 64
 
 # every symbol include/trinity_gpu.h declares: name -> (restype, argtypes)
 _u64, _u32, _i32, _vp, _cp = C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_char_p
@@ -60,6 +61,10 @@ SIGNATURES = {
     "tg_count_reads_dev": (_i32, [_vp, _vp, _u64, _i32]),
     "tg_count_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp, _vp]),
     "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32]),
+    "tg_ipc_export": (_i32, [_vp, _vp, _vp]),
+    "tg_ipc_open": (_i32, [_vp, _vp, _pp]),
+    "tg_ipc_close": (_i32, [_vp, _vp]),
+    "tg_count_partition_peers_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _u32, _u32, _pp, _vp, _vp]),
     "tg_cov_stats_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),
     "tg_label_bundles_dev": (_i32, [_vp, _vp, _u64, _vp, _u64, _u32]),
     "tg_assign_reads_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),

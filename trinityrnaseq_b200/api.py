@@ -284,6 +284,14 @@ class KmerCounter(_Table):
         check(_lib.lib().tg_count_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(can), nbins, cap, d_keys,
                                                 d_cursor, d_hpoly))
 
+    def partition_peers_dev(self, d_recs, nbytes, nbins, cap, my_rank, owner_keys, d_cursor, d_hpoly, canonical=None):
+        """phase 1 fused with the exchange: entries stored into segment [my_rank] of the owners' receive logs
+        (tg_count_partition_peers_dev); owner_keys = device pointers of every rank's log"""
+        can = self.is_ds if canonical is None else canonical
+        ptrs = (C.c_void_p * len(owner_keys))(*[_addr(p) for p in owner_keys])
+        check(_lib.lib().tg_count_partition_peers_dev(self.ctx._h, d_recs, nbytes, self.k, int(can), nbins, cap,
+                                                      len(owner_keys), my_rank, ptrs, d_cursor, d_hpoly))
+
     def replay_log_dev(self, d_keys, d_cursor, d_hpoly, nsrc, cap):
         """phase 2: received log [nsrc][nlocal][cap] -> this shard (tg_table_replay_log_dev)"""
         check(_lib.lib().tg_table_replay_log_dev(self._h, d_keys, d_cursor, d_hpoly, nsrc, cap))

@@ -680,8 +680,16 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     return TG_OK;
 }
 
+// a log held entirely by this GPU: one owner, one source segment
+static LogView local_log_view(unsigned long long* keys, unsigned int* cursor, unsigned nbins, unsigned cap, int* error,
+                              unsigned long long* hpoly) {
+    LogView lg{};
+    lg.owner[0] = keys;
+    lg.cursor = cursor; lg.nbins = nbins; lg.cap = cap; lg.lp_shift = 31; lg.src = 0; lg.error = error; lg.hpoly = hpoly;
+    return lg;
+}
 static LogView log_view(tg_table* t) {
-    return LogView{t->log.keys, t->log.cursor, t->log.nbins, t->log.cap, t->d_error, t->log.hpoly};
+    return local_log_view(t->log.keys, t->log.cursor, t->log.nbins, t->log.cap, t->d_error, t->log.hpoly);
 }
 
 // replay + reset on stream 0 (stream-ordered; no host sync)
@@ -842,10 +850,68 @@ int tg_count_partition_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k
         return fail(TG_ERR_ARG, "tg_count_partition_dev: bad log shape (1..%u bins, capacity at most %u)", LOG_MAX_BINS,
                     LOG_CAP_MAX);
     if (bind(c)) return TG_ERR_CUDA;
-    LogView lg{(unsigned long long*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error, (unsigned long long*)d_hpoly};
+    LogView lg = local_log_view((unsigned long long*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error,
+                                (unsigned long long*)d_hpoly);
     TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
+    return TG_OK;
+}
+
+// fused phase 1 + exchange: entries go straight into the owners' receive logs through peer memory
+int tg_count_partition_peers_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
+                                 uint32_t cap, uint32_t nranks, uint32_t my_rank, void* const* d_owner_keys,
+                                 void* d_cursor, void* d_hpoly) {
+    if (!c || !d_recs || !d_owner_keys || !d_cursor || !d_hpoly)
+        return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (nranks == 0 || nranks > (uint32_t)LOG_MAX_RANKS || my_rank >= nranks)
+        return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: 1..%d ranks, rank inside", LOG_MAX_RANKS);
+    if (nbins == 0 || nbins > LOG_MAX_BINS || nbins % nranks || cap == 0 || cap > LOG_CAP_MAX)
+        return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: bad log shape (bins a multiple of the ranks, at most %u)",
+                    LOG_MAX_BINS);
+    const uint32_t lp = nbins / nranks;
+    if (lp & (lp - 1)) return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: bins per rank must be a power of two");
+    if (bind(c)) return TG_ERR_CUDA;
+    LogView lg{};
+    for (uint32_t r = 0; r < nranks; r++) {
+        if (!d_owner_keys[r]) return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: null receive log for rank %u", r);
+        lg.owner[r] = (unsigned long long*)d_owner_keys[r];
+    }
+    unsigned sh = 0;
+    while ((1u << sh) < lp) sh++;
+    lg.cursor = (unsigned int*)d_cursor; lg.nbins = nbins; lg.cap = cap; lg.lp_shift = sh; lg.src = my_rank;
+    lg.error = c->d_error; lg.hpoly = (unsigned long long*)d_hpoly;
+    TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
+    CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+
+// ---- peer memory: CUDA IPC handles of allocations made with tg_dev_alloc --------------------------------------------
+int tg_ipc_export(tg_ctx* c, void* dptr, uint8_t* handle) {
+    if (!c || !dptr || !handle) return fail(TG_ERR_ARG, "tg_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TG_IPC_HANDLE_BYTES, "IPC handle size");
+    if (bind(c)) return TG_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, sizeof h);
+    return TG_OK;
+}
+
+int tg_ipc_open(tg_ctx* c, const uint8_t* handle, void** dptr) {
+    if (!c || !handle || !dptr) return fail(TG_ERR_ARG, "tg_ipc_open: null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TG_OK;
+}
+
+int tg_ipc_close(tg_ctx* c, void* dptr) {
+    if (!c || !dptr) return fail(TG_ERR_ARG, "tg_ipc_close: null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(cudaIpcCloseMemHandle(dptr));
     return TG_OK;
 }
 

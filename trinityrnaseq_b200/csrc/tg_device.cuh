@@ -227,12 +227,22 @@ __device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots,
 // phase 2 replays the log bin by bin, so the CAS/RED traffic of one bin stays inside an L2-resident group of
 // partitions.  An entry is the table key (0 = no entry).  Homopolymer windows never enter the log: they are
 // tallied per launch in hpoly[] (keys in [0..3], occurrence counts in [4..7], indexed by base code).
+//
+// Multi-GPU: the log IS the exchange.  Bin b belongs to rank b >> lp_shift (lp = bins per rank, a power of two), and
+// phase 1 stores every entry straight into the OWNER's receive log through peer memory (NVLink P2P stores, the
+// pointers come from CUDA IPC): owner[r] is rank r's receive log, laid out [nranks][lp][cap], and this rank writes
+// segment `src` of it.  The cursors stay on the writing GPU (one atomicAdd per non-empty bin per tile, all local);
+// only the 8-B keys cross NVLink, as runs of consecutive entries, while the kernel is still rolling the next tile.
+// One GPU is the same layout with one owner: owner[0] = the local log, lp_shift = 31, src = 0.
+constexpr int LOG_MAX_RANKS = 8;
 struct LogView {
-    unsigned long long* keys;   // [nbins][cap]
-    unsigned int* cursor;       // [nbins] entries reserved so far; may run past cap (readers clamp, writers
+    unsigned long long* owner[LOG_MAX_RANKS];   // receive log of each rank: [nranks][lp][cap]
+    unsigned int* cursor;       // [nbins] entries reserved so far, LOCAL; may run past cap (readers clamp, writers
                                 //         past cap insert directly / raise the overflow flag)
     unsigned int nbins;         // bins == partitions of the geometry the log was laid out for
-    unsigned int cap;           // entries per bin
+    unsigned int cap;           // entries per bin (per source segment)
+    unsigned int lp_shift;      // log2(bins per rank); 31 on one GPU
+    unsigned int src;           // this rank = the segment it writes in every owner's log
     int* error;                 // device flag raised (3) when a bin overflows and there is no table to fall back to
     unsigned long long* hpoly;  // [8] homopolymer side channel
 };

@@ -242,6 +242,7 @@ struct LogSmem {
     uint32_t wtot[LT_THREADS / 32];
     uint32_t total;
     alignas(8) unsigned long long bar[2];
+    unsigned long long* seg[LOG_MAX_RANKS];         // this rank's segment in every owner's log (dynamic index: not params)
 };
 
 __device__ __forceinline__ unsigned long long window_key(unsigned f0, unsigned f1, int k, int canonical) {
@@ -275,6 +276,9 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
         fence_mbar_init();
+#pragma unroll
+        for (int r = 0; r < LOG_MAX_RANKS; r++)
+            sm.seg[r] = lg.owner[r] ? lg.owner[r] + (((unsigned long long)lg.src << lg.lp_shift) * lg.cap) : nullptr;
     }
     for (unsigned b = tid; b < nbins2 / 2; b += LT_THREADS) cnt32[b] = 0u;
     __syncthreads();
@@ -384,7 +388,9 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
             const unsigned pos = delta[bin] + i;
             const unsigned long long key = skey[i];
             if (pos < lg.cap) {
-                lg.keys[(unsigned long long)bin * lg.cap + pos] = key;
+                // bin -> (owner, bin inside the owner); the store lands in local HBM or, over NVLink, in the owner's log
+                const unsigned o = bin >> lg.lp_shift, lb = bin - (o << lg.lp_shift);
+                sm.seg[o][(unsigned long long)lb * lg.cap + pos] = key;
             } else if (t.slots) {      // bin full: count this occurrence directly
                 table_update<false>(t, key, 1u, claimed);
             } else {

@@ -6,10 +6,17 @@ the plumbing, libtrinity_gpu for every k-mer.
          [r*lp, (r+1)*lp) (tg_table_create_sharded).  Prior art for owner = f(canonical k-mer) mod n:
          Inchworm/src/mpi_deprecated/MPIinchworm.cpp:1236-1257 -- there one blocking MPI_Send per k-mer (:519-531).
 
-  count     phase 1 on every rank appends each k-mer occurrence to the log bin of its partition
-            (tg_count_partition_dev; bins [d*lp, (d+1)*lp) are rank d's), ONE equal-split all-to-all moves the
-            bins to their owners (NCCL over NVLink), phase 2 replays the received bins into the shard
-            (tg_table_replay_log_dev).
+  count     phase 1 on every rank appends each k-mer occurrence to the log bin of its partition (bins
+            [d*lp, (d+1)*lp) are rank d's); phase 2 replays the received bins into the shard
+            (tg_table_replay_log_dev).  Between them the bins must reach their owners:
+              exchange="peer"        (default on GPUs) phase 1 IS the exchange: the kernel stores every entry straight
+                                     into segment [rank] of the OWNER's receive log through peer memory (CUDA IPC,
+                                     NVLink P2P stores; tg_count_partition_peers_dev), so the transfer overlaps the
+                                     rolling of the next tile and there is no send buffer; only the [lp] cursor rows
+                                     are exchanged afterwards (a few KB, and the "all stores have landed" point);
+              exchange="collective"  phase 1 fills a local send log (tg_count_partition_dev) and ONE equal-split
+                                     all-to-all moves the bins (NCCL over NVLink) -- the fallback when peer memory
+                                     cannot be mapped, and what the CPU test-suite runs over gloo.
   queries   the shards are all-gathered once into a full replica per GPU (`replicate`), because the
             concatenation of the shards' slot arrays IS the full table; coverage statistics / lookups then run
             locally with no per-batch communication (SURVEY §8e "all-gather once" branch).
@@ -94,6 +101,75 @@ class DeviceEngine:
                                                 C.c_void_p(hpoly.data_ptr())))
         self.ctx.sync()          # the exchange runs on torch's stream: hand over with a host sync
 
+    def sync(self):
+        self.ctx.sync()
+
+    def open_peer_logs(self, dist, group, nbins, cap):
+        """Collective.  This rank's receive log [world, lp, cap] allocated with cudaMalloc, its IPC handle exchanged,
+        every other rank's log mapped into this process.  -> PeerLogs, or None (on every rank) when any rank fails."""
+        L, t = _lib.lib(), self.torch
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = nbins * cap * 8
+        mine, handle, ok = None, b"", 1
+        try:
+            mine = self.ctx.dev_alloc(nbytes)
+            h = (C.c_uint8 * _lib.TG_IPC_HANDLE_BYTES)()
+            check(L.tg_ipc_export(self.ctx._h, mine, h))
+            handle = bytes(h)
+        except Exception:
+            ok = 0
+        handles = [None] * world
+        dist.all_gather_object(handles, (ok, handle), group=group)
+        ptrs, opened = (C.c_void_p * world)(), []
+        if all(o for o, _ in handles):
+            try:
+                for r, (_, hb) in enumerate(handles):
+                    if r == rank:
+                        ptrs[r] = mine.value
+                        continue
+                    q = C.c_void_p()
+                    check(L.tg_ipc_open(self.ctx._h, (C.c_uint8 * _lib.TG_IPC_HANDLE_BYTES).from_buffer_copy(hb), C.byref(q)))
+                    ptrs[r] = q.value
+                    opened.append(q)
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flag = self.scalar_tensor([ok], t.int64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        peers = PeerLogs(mine, ptrs, opened, None, world)
+        peers.ok = int(flag.item()) == 1
+        if peers.ok:
+            peers.rkeys = _alias_tensor(t, mine.value, nbytes, self.device).view(t.int64).view(world, nbins // world, cap)
+        return peers
+
+    # closing is two steps with a barrier between them (the caller's): every importer unmaps before any exporter frees
+    def unmap_peer_logs(self, peers):
+        for q in peers.opened:
+            try:
+                check(_lib.lib().tg_ipc_close(self.ctx._h, q))
+            except Exception:
+                pass
+        peers.opened = []
+
+    def free_peer_log(self, peers):
+        if peers.mine is not None:
+            peers.rkeys = None
+            self.ctx.dev_free(peers.mine)
+            peers.mine = None
+
+    def partition_peers(self, d_recs, nbytes, peers, cursor, hpoly, nbins, cap, rank):
+        """phase 1 fused with the exchange: entries stored into the owners' receive logs over NVLink"""
+        check(_lib.lib().tg_count_partition_peers_dev(self.ctx._h, d_recs, nbytes, self.k, int(self.canonical), nbins, cap,
+                                                      peers.world, rank, peers.ptrs, C.c_void_p(cursor.data_ptr()),
+                                                      C.c_void_p(hpoly.data_ptr())))
+        self.ctx.sync()          # kernel end = this rank's peer stores are visible system-wide
+
+    def new_cursors(self, nbins):
+        t = self.torch
+        return (t.zeros((nbins,), dtype=t.int32, device=self.device), t.zeros((nbins,), dtype=t.int32, device=self.device),
+                t.zeros((8,), dtype=t.int64, device=self.device))
+
     def replay(self, keys, cursor, hpoly, nsrc):
         """phase 2: received log [nsrc, lp, cap] (+ global homopolymer tallies) -> this rank's shard"""
         cap = keys.shape[-1]
@@ -135,6 +211,14 @@ class DeviceEngine:
         return self.torch.tensor(values, dtype=dtype, device=self.device)
 
 
+class PeerLogs:
+    """receive logs of all ranks as seen from this process (engine-specific pointers) + this rank's own as a tensor"""
+
+    def __init__(self, mine, ptrs, opened, rkeys, world):
+        self.mine, self.ptrs, self.opened, self.rkeys, self.world = mine, ptrs, opened, rkeys, world
+        self.ok = True
+
+
 class _CudaAlias:
     """__cuda_array_interface__ view of raw device memory, so torch can wrap a libtrinity_gpu allocation"""
 
@@ -149,15 +233,22 @@ def _alias_tensor(torch, ptr, nbytes, device):
 class ShardedKmerCounter:
     """KmerCounter whose table is sharded by hash over the ranks of a torch.distributed process group."""
 
-    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=16 << 20, dist=None):
+    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=16 << 20, dist=None, exchange="auto"):
         if dist is None:
             import torch.distributed as dist
+        if exchange not in ("auto", "peer", "collective"):
+            raise ValueError("exchange must be auto, peer or collective")
         self.dist, self.group, self.eng = dist, group, engine
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.subcap, self.nparts, self.lp = shard_geometry(self.world, expected_keys_per_rank, part_bytes)
         self.table = engine.create_shard(self.subcap, self.nparts, self.rank * self.lp, self.lp)
+        if exchange == "auto":
+            exchange = "peer" if (getattr(engine, "open_peer_logs", None) is not None and self.world <= 8) else "collective"
+        self.exchange = exchange
+        self.profile = None       # set to a dict to collect host-clock milliseconds per phase (syncs around each)
         self._log = None
         self._recv = None
+        self._peers = None        # (PeerLogs, cap, (cursor, rcursor, hpoly))
         self._compact = None      # (compacted shard, its slots per partition)
         self._full = None         # (full replica, its slot bytes as a tensor, slots per partition)
 
@@ -167,12 +258,51 @@ class ShardedKmerCounter:
     def owner_of_bin(self, b):
         return b // self.lp
 
-    def _buffers(self, nbytes):
-        # the exchange is an equal-split all-to-all: every rank must lay its log out for the largest batch
-        # (nbytes bounds the entries of a batch: every byte starts at most one window)
+    def _timed(self, name, fn):
+        if self.profile is None:
+            return fn()
+        import time
+        self._sync_all()
+        t0 = time.perf_counter()
+        out = fn()
+        self._sync_all()
+        self.profile[name] = self.profile.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
+
+    def _sync_all(self):
+        if hasattr(self.eng, "sync"):
+            self.eng.sync()
+        if hasattr(self.eng, "torch"):
+            self.eng.torch.cuda.current_stream(self.eng.device).synchronize()
+
+    def _agree_capacity(self, nbytes):
+        # every rank lays its log out for the largest batch (nbytes bounds the entries of a batch: every byte starts
+        # at most one window).  The reduction doubles as the barrier the peer exchange needs: a rank enters it only
+        # after its own previous replay has finished, so nobody is still reading a log that is about to be rewritten.
+        if hasattr(self.eng, "sync"):
+            self.eng.sync()
         m = self.eng.scalar_tensor([int(nbytes)], _int64(self.eng))
         self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
-        cap = log_capacity(int(m.item()), self.nparts)
+        return log_capacity(int(m.item()), self.nparts)
+
+    def _peer_buffers(self, nbytes):
+        cap = self._agree_capacity(nbytes)
+        if self._peers is not None and self._peers[1] < cap:
+            self._close_peers(self._peers[0])              # every rank is past its last replay (barrier above)
+            self._peers = None
+        if self._peers is None:
+            peers = self.eng.open_peer_logs(self.dist, self.group, self.nparts, cap)
+            if not peers.ok:
+                self._close_peers(peers)
+                return None
+            self._peers = (peers, cap, self.eng.new_cursors(self.nparts))
+        else:
+            cur, _, hpoly = self._peers[2]
+            self.eng.reset_log(cur, hpoly)
+        return self._peers
+
+    def _buffers(self, nbytes):
+        cap = self._agree_capacity(nbytes)
         if self._log is None or self._log[0].shape[1] < cap:
             self._log = self.eng.new_log(self.nparts, cap)
             self._recv = self.eng.new_log(self.nparts, cap)      # same bytes, viewed [world, lp, cap]
@@ -184,15 +314,42 @@ class ShardedKmerCounter:
         """Count every k-mer of this rank's record buffer into the sharded table (collective: all ranks call it).
         max_windows: an upper bound on the k-mer windows of the buffer when the caller knows one tighter than
         nbytes (fixed-length reads: nreads * (L - k + 1)); it only sizes the exchange buffers."""
-        (keys, cur, hpoly), (rkeys, rcur, _) = self._buffers(nbytes if max_windows is None else min(nbytes, max_windows))
-        self.eng.partition(d_recs, nbytes, keys, cur, hpoly)
-        # bins [d*lp, (d+1)*lp) go to rank d: an equal-split all-to-all over dim 0
-        self.dist.all_to_all_single(rcur, cur, group=self.group)
-        self.dist.all_to_all_single(rkeys, keys, group=self.group)
+        bound = nbytes if max_windows is None else min(nbytes, max_windows)
+        if self.exchange == "peer":
+            pb = self._timed("buffers", lambda: self._peer_buffers(bound))
+            if pb is None:
+                self.exchange = "collective"          # peer memory unavailable (agreed by all ranks): fall back for good
+        if self.exchange == "peer":
+            peers, cap, (cur, rcur, hpoly) = pb
+            # phase 1 + exchange in one kernel: this rank's entries land in segment [rank] of every owner's log
+            self._timed("partition+exchange", lambda: self.eng.partition_peers(d_recs, nbytes, peers, cur, hpoly,
+                                                                              self.nparts, cap, self.rank))
+            # cursor rows [d*lp, (d+1)*lp) go to rank d (a few KB); completing it also means every rank is past its
+            # kernel, i.e. all peer stores into this rank's log have landed
+            self._timed("cursors", lambda: self.dist.all_to_all_single(rcur, cur, group=self.group))
+            rkeys = peers.rkeys
+        else:
+            (keys, cur, hpoly), (rkeys, rcur, _) = self._timed("buffers", lambda: self._buffers(bound))
+            self._timed("partition", lambda: self.eng.partition(d_recs, nbytes, keys, cur, hpoly))
+            # bins [d*lp, (d+1)*lp) go to rank d: an equal-split all-to-all over dim 0
+            self._timed("cursors", lambda: self.dist.all_to_all_single(rcur, cur, group=self.group))
+            self._timed("exchange", lambda: self.dist.all_to_all_single(rkeys, keys, group=self.group))
         # homopolymer tallies: every rank learns the global counts, the owner of each key applies it
         self.dist.all_reduce(hpoly[:4], op=self.dist.ReduceOp.MIN, group=self.group)   # keys carry bit 63: negative
         self.dist.all_reduce(hpoly[4:], op=self.dist.ReduceOp.SUM, group=self.group)
-        self.eng.replay(rkeys, rcur, hpoly, self.world)
+        self._timed("replay", lambda: self.eng.replay(rkeys, rcur, hpoly, self.world))
+
+    def close(self):
+        """Collective: unmap / free the peer logs (the other buffers are ordinary tensors)."""
+        if self._peers is not None:
+            self._agree_capacity(0)                      # barrier: nobody still writes into or replays from a log
+            self._close_peers(self._peers[0])
+            self._peers = None
+
+    def _close_peers(self, peers):
+        self.eng.unmap_peer_logs(peers)
+        self._agree_capacity(0)                          # barrier: every importer has unmapped
+        self.eng.free_peer_log(peers)
 
     def size(self):
         """distinct k-mers in the global table"""
@@ -229,7 +386,7 @@ class ShardedKmerCounter:
                     need = max(int(int(n.item()) / load / self.lp) + 64, 64)
                     self._compact = (self.eng.new_shard_like(need), need, min_count)
                 src, subcap, _ = self._compact
-                self.eng.compact_into(min_count, src)
+                self._timed("compact", lambda: self.eng.compact_into(min_count, src))
                 full_flag = 0
                 try:
                     if src.size() > 0.8 * subcap * self.lp:
@@ -248,7 +405,7 @@ class ShardedKmerCounter:
             self._full = (full, full_bytes, subcap)
         full, full_bytes, _ = self._full
         mine = self.eng.slots_of(src)
-        self.dist.all_gather_into_tensor(full_bytes, mine, group=self.group)
+        self._timed("allgather", lambda: self.dist.all_gather_into_tensor(full_bytes, mine, group=self.group))
         if hasattr(self.eng, "torch"):
             self.eng.torch.cuda.current_stream(self.eng.device).synchronize()
         d = self.eng.scalar_tensor([src.size()], _int64(self.eng))
