@@ -169,6 +169,16 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
  * the point after which every rank's stores have landed.  nbins/nranks must be a power of two, nranks <= 8.
  * Replaces the exchange the reference's retired MPI build did with one blocking MPI_Send per k-mer
  * (Inchworm/src/mpi_deprecated/MPIinchworm.cpp:519-531, owner rule :1236-1257). */
+/* Coarse exchange bins, fine table partitions.  Phase 1 is fast only while a tile of reads scatters into a few hundred
+ * bins (runs of consecutive entries per bin; see profiles/README.md), but a big sharded table has thousands of
+ * L2-sized partitions.  So the ranks exchange COARSE bins -- nbins in the two partition calls above may be any
+ * divisor of the table's partition count that is a multiple of the rank count -- and the owner splits what it received,
+ * [nsrc][ncoarse][cap] with cursors [nsrc][ncoarse], into one segment per local partition: d_out_keys [nfine][out_cap],
+ * d_out_cursor [nfine] (zeroed by the caller), partitions fine0 .. fine0+nfine-1 of nfine_global.  Then
+ * tg_table_replay_log_dev(t, d_out_keys, d_out_cursor, hpoly, 1, out_cap).  Errors surface at the next tg_sync. */
+int tg_log_refine_dev(tg_ctx* ctx, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t ncoarse, uint32_t cap,
+                      void* d_out_keys, void* d_out_cursor, uint32_t nfine, uint32_t out_cap, uint32_t fine0,
+                      uint32_t nfine_global);
 #define TG_IPC_HANDLE_BYTES 64
 int tg_ipc_export(tg_ctx* ctx, void* dptr, uint8_t* handle /* TG_IPC_HANDLE_BYTES */);
 int tg_ipc_open(tg_ctx* ctx, const uint8_t* handle, void** dptr);

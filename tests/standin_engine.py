@@ -120,6 +120,25 @@ class StandinEngine:
     def free_peer_log(self, peers):
         peers.rkeys = None
 
+    def new_fine_log(self, nfine, cap):
+        return torch.zeros((nfine, cap), dtype=torch.int64), torch.zeros((nfine,), dtype=torch.int32)
+
+    def refine(self, rkeys, rcur, nsrc, ncoarse, fkeys, fcur, fine0, nfine_global):
+        fcur.zero_()
+        nfine, fcap = fkeys.shape
+        f = nfine // ncoarse
+        rk = rkeys.reshape(nsrc, ncoarse, -1)
+        rc = rcur.reshape(nsrc, ncoarse)
+        for cb in range(ncoarse):
+            for s_ in range(nsrc):
+                for e in rk[s_, cb, :int(rc[s_, cb])].tolist():
+                    b = key_bin(e - 1, nfine_global) - fine0
+                    assert cb * f <= b < (cb + 1) * f, "a coarse bin holds only its own partitions"
+                    pos = int(fcur[b])
+                    assert pos < fcap, "stand-in fine log overflow"
+                    fkeys[b, pos] = e
+                    fcur[b] += 1
+
     def new_cursors(self, nbins):
         return (torch.zeros((nbins,), dtype=torch.int32), torch.zeros((nbins,), dtype=torch.int32),
                 torch.zeros((8,), dtype=torch.int64))

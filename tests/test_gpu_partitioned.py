@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import trinityrnaseq_b200 as tg
+from trinityrnaseq_b200 import _lib
 import synthdata as synth
 
 pytestmark = pytest.mark.gpu
@@ -194,8 +195,8 @@ def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
         ctx.dev_free(p)
 
 
-@pytest.mark.parametrize("world", [2, 8])
-def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world):
+@pytest.mark.parametrize("world,fine_per_coarse", [(2, 1), (8, 1), (2, 4), (4, 16), (8, 2)])
+def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world, fine_per_coarse):
     """The fused phase 1 + exchange (tg_count_partition_peers_dev) with N ranks emulated on one GPU: every "rank" runs
     phase 1 with the pointers of all N receive logs and writes segment [rank] of each; what peer memory adds on a real
     box is only where those pointers point.  Each owner then replays its log [src][lp][cap] with the cursor rows the
@@ -208,8 +209,14 @@ def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world):
     assert nparts == world * lp and lp > 1 and lp & (lp - 1) == 0
     shards = [tg.KmerCounter.sharded(ctx, k, True, subcap, nparts, r * lp, lp) for r in range(world)]
     ranges = [tg.sharded.record_range(offs, r, world) for r in range(world)]
-    cap = tg.sharded.log_capacity(max(int(offs[r1] - offs[r0]) for r0, r1 in ranges), nparts)
-    rlogs = [ctx.dev_alloc(nparts * cap * 8) for _ in range(world)]       # rank r's receive log [world][lp][cap]
+    # the k-mers travel in cbins = world * c COARSE bins; fine_per_coarse > 1: the owner splits them (tg_log_refine_dev)
+    part_lp = lp
+    assert lp % fine_per_coarse == 0
+    c = lp // fine_per_coarse
+    fine_nparts, nparts, lp = nparts, world * c, c
+    bound = max(int(offs[r1] - offs[r0]) for r0, r1 in ranges)
+    cap = tg.sharded.log_capacity(bound, nparts)
+    rlogs = [ctx.dev_alloc(nparts * cap * 8) for _ in range(world)]       # rank r's receive log [world][c][cap]
     for p in rlogs:
         ctx.memset(p, 0xEE, nparts * cap * 8)                             # stale bytes must never be replayed
     curs = []
@@ -231,7 +238,23 @@ def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world):
             ctx.d2d(rcur, curs[src], lp * 4, dst_off=src * lp * 4, src_off=dst * lp * 4)
         hp_d = ctx.dev_alloc(64)
         ctx.h2d(hp_d, hp_host)
-        shards[dst].replay_log_dev(rlogs[dst], rcur, hp_d, world, cap)
+        if fine_per_coarse == 1:
+            shards[dst].replay_log_dev(rlogs[dst], rcur, hp_d, world, cap)
+        else:
+            fcap = tg.sharded.log_capacity(world * bound, part_lp, slack=1.3)
+            fkeys = ctx.dev_alloc(part_lp * fcap * 8)
+            fcur = ctx.dev_alloc(part_lp * 4)
+            ctx.memset(fkeys, 0xEE, part_lp * fcap * 8)
+            ctx.memset(fcur, 0, part_lp * 4)
+            _lib.check(_lib.lib().tg_log_refine_dev(ctx._h, rlogs[dst], rcur, world, c, cap, fkeys, fcur, part_lp, fcap,
+                                                    dst * part_lp, fine_nparts))
+            ctx.sync()
+            # nothing lost, nothing invented: the fine cursors add up to the coarse ones
+            assert int(ctx.d2h(fcur, part_lp * 4, np.uint32).sum()) == int(ctx.d2h(rcur, nparts * 4, np.uint32).sum())
+            shards[dst].replay_log_dev(fkeys, fcur, hp_d, 1, fcap)
+            ctx.sync()
+            ctx.dev_free(fkeys)
+            ctx.dev_free(fcur)
         ctx.sync()
         ctx.dev_free(hp_d)
         ctx.dev_free(rcur)
@@ -248,6 +271,21 @@ def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world):
         shards[0].partition_peers_dev(rlogs[0], 0, 3 * world, cap, 0, rlogs, cur, hpoly)
     with pytest.raises(tg.TrinityGpuError):
         shards[0].partition_peers_dev(rlogs[0], 0, nparts, cap, world, rlogs, cur, hpoly)
+    # a coarse log refined by the WRONG owner: every key is foreign, reported at the next sync
+    if fine_per_coarse > 1 and world > 1:
+        fkeys = ctx.dev_alloc(part_lp * 64 * 8)
+        fcur = ctx.dev_alloc(part_lp * 4)
+        ctx.memset(fcur, 0, part_lp * 4)
+        rcur = ctx.dev_alloc(nparts * 4)
+        for src in range(world):
+            ctx.d2d(rcur, curs[src], lp * 4, dst_off=src * lp * 4, src_off=0)
+        _lib.check(_lib.lib().tg_log_refine_dev(ctx._h, rlogs[0], rcur, world, c, cap, fkeys, fcur, part_lp, 64,
+                                                1 * part_lp, fine_nparts))
+        with pytest.raises(tg.TrinityGpuError):
+            ctx.sync()
+        ctx.sync()
+        for p in (fkeys, fcur, rcur):
+            ctx.dev_free(p)
     for t in shards:
         t.close()
     for p in rlogs + curs + [hpoly]:

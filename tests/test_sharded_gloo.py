@@ -27,7 +27,7 @@ def _make_reads():
     return reads
 
 
-def _worker(rank, world, port, out_dir, exchange):
+def _worker(rank, world, port, out_dir, exchange, coarse):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import oracle_py as orc
@@ -43,7 +43,12 @@ def _worker(rank, world, port, out_dir, exchange):
         r0, r1 = sharded.record_range(offs, rank, world)
         mine = recs[int(offs[r0]):int(offs[r1])]
         eng = standin_engine.StandinEngine(k, True, peer_dir=out_dir if exchange == "peer" else None)
-        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=len(ok) // world + 64, part_bytes=8 << 10)
+        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=len(ok) // world + 64, part_bytes=8 << 10,
+                                        max_exchange_bins=world * coarse if coarse else sharded.MAX_EXCHANGE_BINS)
+        if coarse:      # k-mers travel in `coarse` bins per rank and are split into partitions by the owner
+            assert sc.c == coarse and sc.lp > sc.c and sc.cbins == world * coarse
+        else:
+            assert sc.c == sc.lp
         assert sc.exchange == exchange          # "auto" picks the peer exchange exactly when the engine offers it
         assert sc.nparts == world * sc.lp and sc.lp >= 2
         assert sc.table.part0 == rank * sc.lp and sc.table.nlocal == sc.lp
@@ -95,10 +100,10 @@ def _worker(rank, world, port, out_dir, exchange):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,exchange", [(2, "collective"), (3, "collective"), (2, "peer"), (3, "peer")])
-def test_sharded_counter_over_gloo(world, exchange, tmp_path):
+@pytest.mark.parametrize("world,exchange,coarse", [(2, "collective", 0), (3, "collective", 2), (2, "peer", 1), (3, "peer", 0)])
+def test_sharded_counter_over_gloo(world, exchange, coarse, tmp_path):
     port = 29500 + (os.getpid() % 400) + world + (10 if exchange == "peer" else 0)
-    mp.spawn(_worker, args=(world, port, str(tmp_path), exchange), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), exchange, coarse), nprocs=world, join=True)
     from oracle import oracle_py as orc
     recs, offs = records_from_sequences(_make_reads())
     ok, oc = orc.jf_count(recs, 25, True, 1)
@@ -120,6 +125,16 @@ def test_record_range_partitions_every_record_once():
         assert all(rr[i][1] == rr[i + 1][0] for i in range(world - 1))
         sizes = [int(offs[b] - offs[a]) for a, b in rr]
         assert max(sizes) - min(sizes) <= 2 * 201
+
+
+def test_exchange_bins():
+    for world in (1, 2, 3, 4, 8):
+        for lp in (1, 2, 64, 512):
+            c = sharded.exchange_bins(world, lp)
+            assert c >= 1 and lp % c == 0 and c & (c - 1) == 0
+            assert world * c <= sharded.MAX_EXCHANGE_BINS or c == 1
+            assert c == lp or world * c * 2 > sharded.MAX_EXCHANGE_BINS
+    assert sharded.exchange_bins(8, 512) == 32 and sharded.exchange_bins(2, 512) == 128
 
 
 def test_shard_geometry():

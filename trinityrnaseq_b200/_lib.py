@@ -61,6 +61,7 @@ SIGNATURES = {
     "tg_count_reads_dev": (_i32, [_vp, _vp, _u64, _i32]),
     "tg_count_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp, _vp]),
     "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32]),
+    "tg_log_refine_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32]),
     "tg_ipc_export": (_i32, [_vp, _vp, _vp]),
     "tg_ipc_open": (_i32, [_vp, _vp, _pp]),
     "tg_ipc_close": (_i32, [_vp, _vp]),

@@ -279,7 +279,8 @@ int tg_sync(tg_ctx* c) {
     CU(cudaMemcpy(&err, c->d_error, sizeof err, cudaMemcpyDeviceToHost));
     if (err) {
         CU(cudaMemset(c->d_error, 0, sizeof(int)));
-        return fail(TG_ERR_TABLE, "a k-mer log bin overflowed (tg_count_partition_dev): raise the per-bin capacity");
+        if (err == 2) return fail(TG_ERR_TABLE, "a k-mer reached a rank that does not own its partition (tg_log_refine_dev)");
+        return fail(TG_ERR_TABLE, "a k-mer log bin overflowed (tg_count_partition_dev / tg_log_refine_dev): raise the per-bin capacity");
     }
     return TG_OK;
 }
@@ -885,6 +886,27 @@ int tg_count_partition_peers_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes,
     TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
+    return TG_OK;
+}
+
+// owner-side split of a received coarse log into the table's partitions (see k_log_refine)
+int tg_log_refine_dev(tg_ctx* c, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t ncoarse, uint32_t cap,
+                      void* d_out_keys, void* d_out_cursor, uint32_t nfine, uint32_t out_cap, uint32_t fine0,
+                      uint32_t nfine_global) {
+    if (!c || !d_keys || !d_cursor || !d_out_keys || !d_out_cursor)
+        return fail(TG_ERR_ARG, "tg_log_refine_dev: null argument");
+    if (nsrc == 0 || ncoarse == 0 || cap == 0 || nfine == 0 || out_cap == 0 || out_cap > LOG_CAP_MAX || nfine % ncoarse ||
+        (uint64_t)fine0 + nfine > nfine_global || nfine > 2048)
+        return fail(TG_ERR_ARG, "tg_log_refine_dev: bad shape (fine bins a multiple of the coarse bins, at most 2048, "
+                                "inside the global partition range)");
+    if (bind(c)) return TG_ERR_CUDA;
+    const size_t need = std::max(log_refine_plan_words(nsrc, ncoarse), log_replay_plan_words(1, nfine, 64)) *
+                        sizeof(unsigned long long);
+    CU(c->scratch.ensure(need));
+    CU(launch_log_refine((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, ncoarse,
+                         (unsigned long long*)c->scratch.p, (unsigned long long*)d_out_keys, (unsigned int*)d_out_cursor,
+                         out_cap, nfine, fine0, nfine_global, c->d_error, c->sm_count, c->stream[0]));
+    c->launches += 2;
     return TG_OK;
 }
 

@@ -598,6 +598,132 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
     if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
 }
 
+// ---- refine: coarse bins -> fine bins (owner side) ------------------------------------------------------------
+// Phase 1 is only fast while a tile's entries fall into few bins (measured, 1.5 G entries: 256 bins 14.9 ms, 512 bins
+// 17.7 ms, 1024 bins 36.6 ms, 4096 bins 63.8 ms -- a run of a bin inside a tile shrinks to one or two 8-B entries and
+// every store becomes a partial-sector write).  So the exchange uses COARSE bins (a few hundred over all GPUs: long
+// runs, efficient NVLink stores), and the owner splits each coarse bin into the f table partitions it covers with
+// this kernel: a chunk of 2048 keys of one coarse segment is counting-sorted in shared memory by fine bin (only f
+// bins occur, so runs are hundreds of entries) and streamed out; the source segments merge on the way, so the replay
+// that follows sees one segment per fine bin.  Cost: 8 B read + 8 B written per entry, all sequential.
+constexpr int RF_THREADS = 256;
+constexpr int RF_PER_THREAD = RP_CHUNK / RF_THREADS;
+static_assert(RP_CHUNK % RF_THREADS == 0, "chunk = whole rounds of the CTA");
+constexpr unsigned RF_MAX_FINE = 2048;              // fine bins (partitions) per rank
+
+__global__ void __launch_bounds__(RF_THREADS, 4)
+k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
+             unsigned nsrc, unsigned ncoarse, const unsigned long long* __restrict__ chunk_start,
+             unsigned long long* __restrict__ out_keys, unsigned int* __restrict__ out_cursor, unsigned out_cap,
+             unsigned nfine, unsigned fine0, unsigned nfine_global, int* error) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    // dynamic: skey[RP_CHUNK] u64 | cnt[nfine] u32 | delta[nfine] u32 | sbin[RP_CHUNK] u16 | off[nfine] u16
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(skey + RP_CHUNK);
+    unsigned int* delta = cnt + nfine;
+    unsigned short* sbin = reinterpret_cast<unsigned short*>(delta + nfine);
+    unsigned short* off = sbin + RP_CHUNK;
+    __shared__ unsigned wtot[RF_THREADS / 32];
+    __shared__ unsigned s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nseg = nsrc * ncoarse;
+    const unsigned long long nchunks = chunk_start[nseg];
+    const unsigned per = (nfine + RF_THREADS - 1) / RF_THREADS;
+    for (unsigned b = tid; b < nfine; b += RF_THREADS) cnt[b] = 0u;
+    __syncthreads();
+    unsigned q = 0;
+    for (unsigned long long w = blockIdx.x; w < nchunks; w += gridDim.x) {
+        while (chunk_start[q + 1] <= w) q++;                       // segments in plan order: (coarse bin, source)
+        const unsigned lb = q / nsrc, src = q % nsrc, seg = src * ncoarse + lb;
+        const unsigned n = min(cursor[seg], cap);
+        const unsigned long long* base = keys + (unsigned long long)seg * cap;
+        const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
+        // ---- A: fine bin and rank of every key
+        unsigned long long key[RF_PER_THREAD];
+        unsigned meta[RF_PER_THREAD];                              // bin << 12 | rank, ~0 = no entry
+#pragma unroll
+        for (int j = 0; j < RF_PER_THREAD; j++) {
+            const unsigned i = i0 + j * RF_THREADS + tid;
+            key[j] = i < n ? __ldcs(base + i) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < RF_PER_THREAD; j++) {
+            meta[j] = 0xFFFFFFFFu;
+            if (key[j] != 0ull) {
+                const unsigned bin = hash_part(mix64(key[j]), nfine_global) - fine0;
+                if (bin < nfine) meta[j] = (bin << 12) | atomicAdd(&cnt[bin], 1u);
+                else atomicExch(error, 2);                         // a key that does not belong to this rank
+            }
+        }
+        __syncthreads();
+        // ---- S: scan the counters, reserve every bin's run in the fine log
+        {
+            const unsigned b0 = tid * per, b1 = min(b0 + per, nfine);
+            unsigned sum = 0;
+            for (unsigned b = b0; b < b1; b++) sum += cnt[b];
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) wtot[warp] = incl;
+            __syncthreads();
+            unsigned run = incl - sum;
+            for (int ww = 0; ww < warp; ww++) run += wtot[ww];
+            if (tid == RF_THREADS - 1) s_total = run + sum;
+            for (unsigned b = b0; b < b1; b++) {
+                const unsigned c = cnt[b];
+                off[b] = (unsigned short)run;
+                if (c) {
+                    delta[b] = atomicAdd(&out_cursor[b], c) - run;
+                    cnt[b] = 0;
+                    run += c;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- B: keys into their sorted places
+#pragma unroll
+        for (int j = 0; j < RF_PER_THREAD; j++)
+            if (meta[j] != 0xFFFFFFFFu) {
+                const unsigned bin = meta[j] >> 12, idx = off[bin] + (meta[j] & 0xFFFu);
+                skey[idx] = key[j];
+                sbin[idx] = (unsigned short)bin;
+            }
+        __syncthreads();
+        // ---- W: stream the sorted chunk out
+        const unsigned total = s_total;
+        for (unsigned i = tid; i < total; i += RF_THREADS) {
+            const unsigned bin = sbin[i], pos = delta[bin] + i;
+            if (pos < out_cap) out_keys[(unsigned long long)bin * out_cap + pos] = skey[i];
+            else atomicExch(error, 3);
+        }
+        __syncthreads();
+    }
+}
+
+size_t log_refine_plan_words(unsigned nsrc, unsigned ncoarse) { return (size_t)nsrc * ncoarse + 2; }
+
+cudaError_t launch_log_refine(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                              unsigned ncoarse, unsigned long long* d_chunk_start, unsigned long long* d_out_keys,
+                              unsigned int* d_out_cursor, unsigned out_cap, unsigned nfine, unsigned fine0,
+                              unsigned nfine_global, int* d_error, int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_log_refine", s);
+    if (nsrc == 0 || ncoarse == 0 || nfine == 0) return cudaSuccess;
+    if (nfine > RF_MAX_FINE) return cudaErrorInvalidValue;
+    k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, ncoarse, 1, d_chunk_start);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t dyn = (size_t)RP_CHUNK * 8 + (size_t)nfine * 8 + (size_t)RP_CHUNK * 2 + (size_t)((nfine + 1) & ~1u) * 2;
+    e = cudaFuncSetAttribute((const void*)k_log_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    int grid = max_resident_ctas((const void*)k_log_refine, RF_THREADS, dyn, -1);
+    if (grid <= 0) grid = sm_count;
+    k_log_refine<<<grid, RF_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, ncoarse, d_chunk_start, d_out_keys, d_out_cursor,
+                                               out_cap, nfine, fine0, nfine_global, d_error);
+    return cudaGetLastError();
+}
+
 size_t log_replay_plan_words(unsigned nsrc, unsigned nlocal, unsigned G) {
     return (size_t)replay_per_group(nlocal, G) * G * nsrc + 1 + G;
 }

@@ -59,6 +59,19 @@ def shard_geometry(world, expected_keys_per_rank, part_bytes=16 << 20):
     return subcap, world * lp, lp
 
 
+MAX_EXCHANGE_BINS = 256
+
+
+def exchange_bins(world, lp, max_bins=MAX_EXCHANGE_BINS):
+    """-> c, the COARSE bins per rank the k-mers are exchanged in (a power of two dividing lp, world * c <= max_bins):
+    phase 1 and the NVLink stores are only efficient while a tile of reads scatters into a few hundred bins; the owner
+    splits each coarse bin into its lp // c table partitions afterwards (tg_log_refine_dev)."""
+    c = 1
+    while c * 2 <= lp and world * c * 2 <= max_bins:
+        c *= 2
+    return c
+
+
 def log_capacity(nbytes, nbins, slack=1.2):
     """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window); the additive
     term covers the hash fluctuation of small batches, the factor covers hot k-mers"""
@@ -165,6 +178,18 @@ class DeviceEngine:
                                                       C.c_void_p(hpoly.data_ptr())))
         self.ctx.sync()          # kernel end = this rank's peer stores are visible system-wide
 
+    def new_fine_log(self, nfine, cap):
+        t = self.torch
+        return (t.empty((nfine, cap), dtype=t.int64, device=self.device), t.zeros((nfine,), dtype=t.int32, device=self.device))
+
+    def refine(self, rkeys, rcur, nsrc, ncoarse, fkeys, fcur, fine0, nfine_global):
+        """received coarse log [nsrc, ncoarse, cap] -> fine log [nfine, fcap], one segment per local partition"""
+        fcur.zero_()
+        self.torch.cuda.current_stream(self.device).synchronize()
+        check(_lib.lib().tg_log_refine_dev(self.ctx._h, C.c_void_p(rkeys.data_ptr()), C.c_void_p(rcur.data_ptr()), nsrc,
+                                           ncoarse, rkeys.shape[-1], C.c_void_p(fkeys.data_ptr()),
+                                           C.c_void_p(fcur.data_ptr()), fkeys.shape[0], fkeys.shape[1], fine0, nfine_global))
+
     def new_cursors(self, nbins):
         t = self.torch
         return (t.zeros((nbins,), dtype=t.int32, device=self.device), t.zeros((nbins,), dtype=t.int32, device=self.device),
@@ -233,7 +258,8 @@ def _alias_tensor(torch, ptr, nbytes, device):
 class ShardedKmerCounter:
     """KmerCounter whose table is sharded by hash over the ranks of a torch.distributed process group."""
 
-    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=16 << 20, dist=None, exchange="auto"):
+    def __init__(self, engine, expected_keys_per_rank, group=None, part_bytes=16 << 20, dist=None, exchange="auto",
+                 max_exchange_bins=MAX_EXCHANGE_BINS):
         if dist is None:
             import torch.distributed as dist
         if exchange not in ("auto", "peer", "collective"):
@@ -245,6 +271,10 @@ class ShardedKmerCounter:
         if exchange == "auto":
             exchange = "peer" if (getattr(engine, "open_peer_logs", None) is not None and self.world <= 8) else "collective"
         self.exchange = exchange
+        # k-mers travel in cbins = world * c coarse bins; rank r owns coarse bins [r*c, (r+1)*c) = partitions [r*lp, (r+1)*lp)
+        self.c = exchange_bins(self.world, self.lp, max_exchange_bins)
+        self.cbins = self.world * self.c
+        self._fine = None         # (fine keys [lp, cap], fine cursors [lp]) when lp > c
         self.profile = None       # set to a dict to collect host-clock milliseconds per phase (syncs around each)
         self._log = None
         self._recv = None
@@ -256,6 +286,7 @@ class ShardedKmerCounter:
         self.table.clear()
 
     def owner_of_bin(self, b):
+        """rank that owns table partition b"""
         return b // self.lp
 
     def _timed(self, name, fn):
@@ -283,7 +314,8 @@ class ShardedKmerCounter:
             self.eng.sync()
         m = self.eng.scalar_tensor([int(nbytes)], _int64(self.eng))
         self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
-        return log_capacity(int(m.item()), self.nparts)
+        self._bound = int(m.item())
+        return log_capacity(self._bound, self.cbins)
 
     def _peer_buffers(self, nbytes):
         cap = self._agree_capacity(nbytes)
@@ -291,11 +323,11 @@ class ShardedKmerCounter:
             self._close_peers(self._peers[0])              # every rank is past its last replay (barrier above)
             self._peers = None
         if self._peers is None:
-            peers = self.eng.open_peer_logs(self.dist, self.group, self.nparts, cap)
+            peers = self.eng.open_peer_logs(self.dist, self.group, self.cbins, cap)
             if not peers.ok:
                 self._close_peers(peers)
                 return None
-            self._peers = (peers, cap, self.eng.new_cursors(self.nparts))
+            self._peers = (peers, cap, self.eng.new_cursors(self.cbins))
         else:
             cur, _, hpoly = self._peers[2]
             self.eng.reset_log(cur, hpoly)
@@ -304,8 +336,8 @@ class ShardedKmerCounter:
     def _buffers(self, nbytes):
         cap = self._agree_capacity(nbytes)
         if self._log is None or self._log[0].shape[1] < cap:
-            self._log = self.eng.new_log(self.nparts, cap)
-            self._recv = self.eng.new_log(self.nparts, cap)      # same bytes, viewed [world, lp, cap]
+            self._log = self.eng.new_log(self.cbins, cap)
+            self._recv = self.eng.new_log(self.cbins, cap)       # same bytes, viewed [world, c, cap]
         else:
             self.eng.reset_log(self._log[1], self._log[2])
         return self._log, self._recv
@@ -323,7 +355,7 @@ class ShardedKmerCounter:
             peers, cap, (cur, rcur, hpoly) = pb
             # phase 1 + exchange in one kernel: this rank's entries land in segment [rank] of every owner's log
             self._timed("partition+exchange", lambda: self.eng.partition_peers(d_recs, nbytes, peers, cur, hpoly,
-                                                                              self.nparts, cap, self.rank))
+                                                                              self.cbins, cap, self.rank))
             # cursor rows [d*lp, (d+1)*lp) go to rank d (a few KB); completing it also means every rank is past its
             # kernel, i.e. all peer stores into this rank's log have landed
             self._timed("cursors", lambda: self.dist.all_to_all_single(rcur, cur, group=self.group))
@@ -337,7 +369,17 @@ class ShardedKmerCounter:
         # homopolymer tallies: every rank learns the global counts, the owner of each key applies it
         self.dist.all_reduce(hpoly[:4], op=self.dist.ReduceOp.MIN, group=self.group)   # keys carry bit 63: negative
         self.dist.all_reduce(hpoly[4:], op=self.dist.ReduceOp.SUM, group=self.group)
-        self._timed("replay", lambda: self.eng.replay(rkeys, rcur, hpoly, self.world))
+        if self.lp > self.c:
+            # the owner splits its coarse bins into table partitions; the source segments merge on the way
+            fcap = log_capacity(self._bound, self.lp, slack=1.3)
+            if self._fine is None or self._fine[0].shape[1] < fcap:
+                self._fine = self.eng.new_fine_log(self.lp, fcap)
+            fkeys, fcur = self._fine
+            self._timed("refine", lambda: self.eng.refine(rkeys, rcur, self.world, self.c, fkeys, fcur,
+                                                          self.rank * self.lp, self.nparts))
+            self._timed("replay", lambda: self.eng.replay(fkeys, fcur, hpoly, 1))
+        else:
+            self._timed("replay", lambda: self.eng.replay(rkeys, rcur, hpoly, self.world))
 
     def close(self):
         """Collective: unmap / free the peer logs (the other buffers are ordinary tensors)."""
