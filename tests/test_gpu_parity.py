@@ -150,3 +150,79 @@ def test_assign_both_orientations(gpu_ctx, oracle, data, strand, k):
     assigned = ob >= 0
     np.testing.assert_array_equal(gp[assigned], op[assigned])
     assert assigned.sum() > 50 and len(set(ob[assigned].tolist())) >= 4
+
+
+def test_device_resident_entry_points_with_long_reads(gpu_ctx, oracle, data):
+    """tg_cov_stats_dev / tg_assign_reads_dev never synchronise with the host: the CTA-per-read kernel for reads beyond
+    the warp path is launched unconditionally and finds the long reads itself.  Same results as the host-buffer entry
+    points (which are checked against the oracle above), and a read that outgrows the scratch budget is an error at
+    the next sync, never a wrong answer."""
+    txs, reads = data
+    rng = np.random.default_rng(99)
+    giant = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 150_000))
+    reads = list(reads) + [txs[3][:2500] * 3, giant[:40_000]]
+    recs, offs = tg.records_from_sequences(reads)
+    n = len(reads)
+    ctx = gpu_ctx
+    d_recs = ctx.dev_records_alloc(recs.nbytes)
+    ctx.h2d(d_recs, recs)
+    d_offs = ctx.dev_alloc(offs.nbytes)
+    ctx.h2d(d_offs, offs)
+    d1, d2, d3 = ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n)
+    with tg.KmerCounter(ctx, 25, is_ds=True) as kc:
+        kc.add_records(recs)
+        hm, hmean, hsd = kc.coverage_stats(recs, offs)
+        for _ in range(2):                                   # twice: the long-read list is reset per call
+            kc.coverage_stats_dev(d_recs, d_offs, n, d1, d2, d3)
+        ctx.sync()
+        np.testing.assert_array_equal(ctx.d2h(d1, 4 * n, np.uint32), hm)
+        np.testing.assert_array_equal(ctx.d2h(d2, 4 * n, np.uint32), _f32_bits(hmean))
+        np.testing.assert_array_equal(ctx.d2h(d3, 4 * n, np.uint32), _f32_bits(hsd))
+        om, omean, osd = _oracle_stats(oracle, recs, offs)
+        np.testing.assert_array_equal(hm, om)
+        np.testing.assert_array_equal(_f32_bits(hsd), _f32_bits(osd))
+    names, bundles = synth.bundles_from(rng, txs)
+    brecs, boffs = tg.records_from_sequences(bundles)
+    with tg.BundleKmerTable(ctx, 25) as bt:
+        bt.label_bundles(brecs, boffs)
+        hb, hp, _ = bt.assign_reads(recs, offs, strand=False)
+        d_lut = ctx.dev_alloc(bt.entropy_ok.nbytes)
+        ctx.h2d(d_lut, bt.entropy_ok)
+        bt.assign_reads_dev(d_recs, d_offs, n, d_lut, d1, d2, strand=False)
+        ctx.sync()
+        np.testing.assert_array_equal(ctx.d2h(d1, 4 * n, np.int32), hb)
+        np.testing.assert_array_equal(ctx.d2h(d2, 4 * n, np.int32)[hb >= 0], hp[hb >= 0])
+        ctx.dev_free(d_lut)
+    # a 150 kb read against a 1 MiB scratch budget
+    recs2, offs2 = tg.records_from_sequences([giant, reads[0]])
+    with tg.Context(ctx.device) as small:
+        small.set("long_scratch_mb", 1)
+        d_r3 = small.dev_records_alloc(recs2.nbytes)
+        small.h2d(d_r3, recs2)
+        d_o3 = small.dev_alloc(offs2.nbytes)
+        small.h2d(d_o3, offs2)
+        e1, e2, e3 = small.dev_alloc(8), small.dev_alloc(8), small.dev_alloc(8)
+        with tg.KmerCounter(small, 25, is_ds=True) as kc:
+            kc.add_records(recs2)
+            kc.coverage_stats_dev(d_r3, d_o3, 2, e1, e2, e3)
+            with pytest.raises(tg.TrinityGpuError) as e:
+                small.sync()
+            assert "too long" in str(e.value)
+            small.sync()
+            # the host-buffer entry point sizes its scratch from the data and handles the same read
+            gm, _, _ = kc.coverage_stats(recs2, offs2)
+            assert gm[0] >= 1
+    for p in (d_recs, d_offs, d1, d2, d3):
+        ctx.dev_free(p)
+
+
+def _oracle_stats(oracle, recs, offs):
+    okc = oracle.KmerCounter(25, True)
+    okc.add_records(recs, offs)
+    # KmerCounter.add_records follows the reference loader (reads of exactly k bases skipped); the GPU table above counted
+    # them, so add them back for an apples-to-apples comparison
+    for i in range(len(offs) - 1):
+        seq = bytes(recs[int(offs[i]):int(offs[i + 1]) - 1])
+        if len(seq) == 25 and all(ch in b"ACGTacgt" for ch in seq):
+            okc.add_kmer(seq.decode().upper(), 1)
+    return okc.coverage_stats(recs, offs)

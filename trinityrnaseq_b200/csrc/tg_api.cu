@@ -70,6 +70,9 @@ struct tg_ctx {
     // per-stream staging for the host-buffer entry points
     DevBuf recs[2], offs[2], out_a[2], out_b[2], out_c[2], per_kmer[2], long_idx[2], scratch;
     DevBuf lut;
+    DevBuf long_scratch;                                // fixed budget of the device-driven CTA-per-read kernels (*_dev entry points)
+    size_t long_scratch_bytes = 64ull << 20;            // reads up to ~2 M windows; longer ones: host-buffer entry points
+    cudaEvent_t order[2] = {nullptr, nullptr};          // cross-stream ordering without host syncs
     unsigned int* d_long_hdr[2] = {nullptr, nullptr};   // {count, max_win}
     unsigned int* h_long_hdr = nullptr;                 // pinned, 2 x 2
     int* d_error = nullptr;                             // raised by table-less log appends (tg_count_partition_dev)
@@ -119,6 +122,9 @@ struct tg_table {
 
 constexpr unsigned LOG_BASE_BINS = 512;
 
+// partitions are whole 64-B buckets (tg_device.cuh: BUCKET_SLOTS)
+static inline uint64_t whole_buckets(uint64_t slots) { return (slots + BUCKET_SLOTS - 1) / BUCKET_SLOTS * BUCKET_SLOTS; }
+
 // partitions for a full table of `slots` slots: a power of two up to 512, beyond that multiples of 512, so that
 // the log's bins (512 or the partition count) always nest with the partitions
 static Geo pick_geo(uint64_t slots, size_t part_bytes) {
@@ -129,7 +135,7 @@ static Geo pick_geo(uint64_t slots, size_t part_bytes) {
     if (np > LOG_MAX_BINS) np = LOG_MAX_BINS;
     Geo g;
     g.nparts = (unsigned)np; g.part0 = 0; g.nlocal = (unsigned)np;
-    g.subcap = (slots + np - 1) / np;
+    g.subcap = whole_buckets((slots + np - 1) / np);
     return g;
 }
 
@@ -251,9 +257,10 @@ void tg_destroy(tg_ctx* c) {
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
-    c->scratch.release(); c->lut.release();
+    c->scratch.release(); c->lut.release(); c->long_scratch.release();
     if (c->d_error) cudaFree(c->d_error);
     if (c->h_long_hdr) cudaFreeHost(c->h_long_hdr);
+    for (int i = 0; i < 2; i++) if (c->order[i]) cudaEventDestroy(c->order[i]);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     delete c;
@@ -279,6 +286,9 @@ int tg_sync(tg_ctx* c) {
     CU(cudaMemcpy(&err, c->d_error, sizeof err, cudaMemcpyDeviceToHost));
     if (err) {
         CU(cudaMemset(c->d_error, 0, sizeof(int)));
+        if (err == 4) return fail(TG_ERR_ARG, "a read is too long for the scratch of the device-resident entry points "
+                                              "(tg_cov_stats_dev / tg_assign_reads_dev): use the host-buffer entry points "
+                                              "or raise long_scratch_mb");
         if (err == 2) return fail(TG_ERR_TABLE, "a k-mer reached a rank that does not own its partition (tg_log_refine_dev)");
         return fail(TG_ERR_TABLE, "a k-mer log bin overflowed (tg_count_partition_dev / tg_log_refine_dev): raise the per-bin capacity");
     }
@@ -315,6 +325,9 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
         c->log_max_bytes = (size_t)v;
     } else if (!strcmp(key, "replay_prefetch")) {
         c->replay_prefetch = v != 0;
+    } else if (!strcmp(key, "long_scratch_mb")) {
+        if (v < 1 || v > (64 << 10)) return fail(TG_ERR_ARG, "long_scratch_mb out of range (1..65536)");
+        c->long_scratch_bytes = (size_t)v << 20;
     } else if (!strcmp(key, "replay_groups")) {
         if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
         c->replay_groups = (unsigned)v;
@@ -386,7 +399,7 @@ int tg_table_create_sharded(tg_ctx* c, int kind, int k, uint64_t slots_per_parti
                     nparts, part0, nlocal, (unsigned long long)slots_per_partition);
     if (bind(c)) return TG_ERR_CUDA;
     Geo g;
-    g.subcap = slots_per_partition; g.nparts = nparts; g.part0 = part0; g.nlocal = nlocal;
+    g.subcap = whole_buckets(slots_per_partition); g.nparts = nparts; g.part0 = part0; g.nlocal = nlocal;
     return table_new(c, kind, k, g, out);
 }
 
@@ -424,8 +437,14 @@ int tg_table_clear(tg_table* t) {
     tg_ctx* c = t->ctx;
     hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
-    int rc = sync_all(c);
-    if (rc) return rc;
+    // stream-ordered, no host synchronisation (a host stall must not idle the GPU): stream 0 waits for whatever stream 1
+    // still does with the table, clears, and stream 1 waits for the clear
+    if (!c->order[0]) {
+        CU(cudaEventCreateWithFlags(&c->order[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->order[1], cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(c->order[1], c->stream[1]));
+    CU(cudaStreamWaitEvent(c->stream[0], c->order[1], 0));
     CU(cudaMemsetAsync(t->slots, 0, t->cap * sizeof(Slot), c->stream[0]));
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
     CU(cudaMemsetAsync(t->d_error, 0, sizeof(int), c->stream[0]));
@@ -434,7 +453,8 @@ int tg_table_clear(tg_table* t) {
         CU(cudaMemsetAsync(t->log.hpoly, 0, 8 * sizeof(unsigned long long), c->stream[0]));
     }
     t->log.pending_ub = 0;
-    CU(cudaStreamSynchronize(c->stream[0]));
+    CU(cudaEventRecord(c->order[0], c->stream[0]));
+    CU(cudaStreamWaitEvent(c->stream[1], c->order[0], 0));
     t->distinct_ub = 0;
     return TG_OK;
 }
@@ -475,7 +495,7 @@ static int grown_geo(tg_table* t, uint64_t keys, Geo* out) {
                     (unsigned long long)keys, (unsigned long long)fit);
     if (t->sharded()) {
         *out = t->g;
-        out->subcap = (want + t->g.nlocal - 1) / t->g.nlocal;
+        out->subcap = whole_buckets((want + t->g.nlocal - 1) / t->g.nlocal);
     } else {
         *out = pick_geo(want, c->part_bytes);
     }
@@ -517,7 +537,7 @@ int tg_table_resize(tg_table* t, uint64_t slots_per_partition) {
         return fail(TG_ERR_ARG, "tg_table_resize: %llu keys do not fit %u x %llu slots", (unsigned long long)t->distinct_ub,
                     t->g.nlocal, (unsigned long long)slots_per_partition);
     Geo ng = t->g;
-    ng.subcap = slots_per_partition;
+    ng.subcap = whole_buckets(slots_per_partition);
     return table_regrow(t, ng);
 }
 
@@ -657,11 +677,16 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     tg_ctx* c = t->ctx;
     *ok = false;
     const unsigned nbins = log_bins_for(t);
+    const uint64_t want = (uint64_t)((double)entries / nbins * LOG_BIN_FACTOR) + LOG_BIN_SLACK;
+    if (t->log.keys && t->log.nbins == nbins && t->log.cap >= std::min<uint64_t>(want, LOG_CAP_MAX) / LOG_CAP_ALIGN * LOG_CAP_ALIGN) {
+        *ok = true;                                     // the common case costs no driver call (cudaMemGetInfo may block)
+        return TG_OK;
+    }
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
     uint64_t budget = std::min<uint64_t>(c->log_max_bytes, fr / 2);
     if (t->log.keys) budget = std::max<uint64_t>(budget, t->log.total_entries() * 8);
-    uint64_t per_bin = (uint64_t)((double)entries / nbins * LOG_BIN_FACTOR) + LOG_BIN_SLACK;
+    uint64_t per_bin = want;
     per_bin = std::min<uint64_t>(per_bin, budget / 8 / nbins);
     per_bin = std::min<uint64_t>(per_bin, LOG_CAP_MAX);
     per_bin = per_bin / LOG_CAP_ALIGN * LOG_CAP_ALIGN;
@@ -718,7 +743,7 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     for (unsigned b = 0; b < ns; b++) sample += fill[b];
     if (sample == 0) { *est = total; return TG_OK; }
     Geo sg;
-    sg.subcap = sample * 2 + 1024; sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1;
+    sg.subcap = whole_buckets(sample * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1;
     Slot* scratch = nullptr;
     unsigned long long* d_n = nullptr;
     int rc;
@@ -1201,25 +1226,24 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     if (bind(c)) return TG_ERR_CUDA;
     if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_cov_stats_dev: at most 2^31 reads per call");
     if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }
-    if (!t->g.hot_slots && !t->hot_tried) {
+    if (c->hot_max_keys && !t->g.hot_slots && !t->hot_tried) {
         int rc = sync_all(c);
         if (rc) return rc;
         if ((rc = maybe_build_hot(t, nreads * 64))) return rc;     // reads are at least a few dozen windows each
     }
+    // everything below is stream-ordered: no host synchronisation (see launch_cov_stats_long_auto)
     const int b = 0;
     CU(c->long_idx[b].ensure(nreads * 4));
+    CU(c->long_scratch.ensure(c->long_scratch_bytes));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
     LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
     CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->g,
                         (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->stream[b]));
-    c->launches++;
-    return finish_long(c, b, t->k, cov_stats_long_scratch_bytes,
-        [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
-            return launch_cov_stats_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots,
-                                         t->g, (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr,
-                                         (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
-                                         c->stream[b]);
-        });
+    CU(launch_cov_stats_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots, t->g,
+                                  (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->long_scratch.p,
+                                  c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[b]));
+    c->launches += 2;
+    return TG_OK;
 }
 
 int tg_label_bundles(tg_table* t, const char* recs, const uint64_t* offs, uint64_t nbundles, uint32_t first_index) {
@@ -1335,16 +1359,14 @@ int tg_assign_reads_dev(tg_table* t, const void* d_recs, const void* d_offs, uin
     CU(c->long_idx[b].ensure(nreads * 4));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
     LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+    CU(c->long_scratch.ensure(c->long_scratch_bytes));
     CU(launch_assign((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, strand, t->slots, t->g,
                      (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll, c->stream[b]));
-    c->launches++;
-    return finish_long(c, b, t->k, assign_long_scratch_bytes,
-        [&](unsigned n_long, unsigned max_win, void* scratch, int nctas) {
-            return launch_assign_long((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, strand, t->slots, t->g,
-                                      (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr,
-                                      (const unsigned int*)c->long_idx[b].p, n_long, max_win, scratch, nctas,
-                                      c->stream[b]);
-        });
+    CU(launch_assign_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, strand, t->slots, t->g,
+                               (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll,
+                               c->long_scratch.p, c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[b]));
+    c->launches += 2;
+    return TG_OK;
 }
 
 // compute_entropy(string&) of Chrysalis/analysis/sequenceUtil.cc:326-355, evaluated for every count tuple:

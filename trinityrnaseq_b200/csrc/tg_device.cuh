@@ -12,6 +12,11 @@
 //    (first base most significant, A<C<G<T) that the C-ABI speaks is produced/consumed by
 //    planes_to_packed()/packed_to_planes() at the boundary (export, load_pairs).
 //  * slot = 16 B {u64 key, u32 val, u32 aux}: key and value share one 32-B DRAM sector.
+//  * BUCKETS: a key's probe sequence starts at the first slot of a 64-B bucket (4 slots, one DRAM access granule:
+//    ncu shows ~80 B of DRAM traffic per random 16-B load, i.e. the neighbours come along anyway) and then walks
+//    linearly.  Inserts claim the first free slot of that walk, so a bucket fills front to back and a lookup settles
+//    a key with ONE round of two 256-bit loads (LDG.E.ENL2.256) unless the whole bucket is taken -- the dependent
+//    probe rounds that a warp-convergent lookup pays as max-over-lanes shrink from 3-4 to ~1.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -25,6 +30,7 @@ struct __align__(16) Slot {
 };                            // (count tables leave aux 0; it keeps the slot 16-B aligned inside one 32-B sector)
 
 constexpr unsigned long long KEY_TAG = 1ull << 63;
+constexpr unsigned BUCKET_SLOTS = 4;          // 64 B; every partition is a whole number of buckets
 
 // Table geometry.  The table is an array of `nparts` PARTITIONS of `subcap` slots each; a key lives in
 // partition part(key) (low hash word) and probes linearly, wrapping INSIDE its partition (slot from the high hash
@@ -111,7 +117,7 @@ __device__ __forceinline__ bool probe_home(const Geo& g, unsigned long long key,
     const unsigned long long h = mix64(key);
     const unsigned part = hash_part(h, g.nparts) - g.part0;
     p.base = (unsigned long long)part * g.subcap;
-    p.off = __umul64hi(h, g.subcap);
+    p.off = __umul64hi(h, g.subcap / BUCKET_SLOTS) * BUCKET_SLOTS;      // first slot of the home bucket
     return part < g.nlocal;
 }
 __device__ __forceinline__ void probe_next(const Geo& g, Probe& p) { p.off = (p.off + 1 == g.subcap) ? 0ull : p.off + 1; }
@@ -182,7 +188,13 @@ __device__ __forceinline__ uint4 ld_slot_hint(const Slot* p, unsigned long long 
     return v;
 }
 
-// Read-only probe: returns val, or 0 when the key is absent or !valid.  One 16-B load fetches key and value.
+// two adjacent slots (32 B, one sector) in one 256-bit load: {key, val | aux << 32} twice
+__device__ __forceinline__ void ld_slot_pair(const Slot* p, unsigned long long& k0, unsigned long long& w0,
+                                             unsigned long long& k1, unsigned long long& w1) {
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(w0), "=l"(k1), "=l"(w1) : "l"(p));
+}
+
+// Read-only probe: returns {val, aux}, or 0 when the key is absent or !valid.  One round = one 64-B bucket.
 // CONVERGENT: every lane of the warp must call it (lanes without a key pass valid = false).  Lanes leave the probe
 // loops at different times; the __syncwarp() between the hot-table phase and the big-table phase brings them back
 // together, so the DRAM-bound loads of a warp are issued as one request and not once per straggler group.
@@ -204,15 +216,19 @@ __device__ __forceinline__ uint2 table_lookup2(const Slot* __restrict__ slots, c
     const unsigned part = hash_part(h, g.nparts) - g.part0;
     if (part >= g.nlocal) open = false;
     const unsigned long long base = (unsigned long long)part * g.subcap;
-    unsigned long long off = __umul64hi(h, g.subcap);
-    const unsigned long long once = l2_policy_evict_first();
-    for (unsigned long long probes = 0; open && probes <= g.subcap; probes++) {   // bounded: a full partition cannot hang
-        const uint4 s = (g.hot_hints & 1u) ? ld_slot_hint(&slots[base + off], once)
-                                           : __ldcg(reinterpret_cast<const uint4*>(&slots[base + off]));
-        const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
-        if (k == key) { v = make_uint2(s.z, s.w); open = false; }
-        else if (k == 0ull) open = false;
-        off = (off + 1 == g.subcap) ? 0ull : off + 1;
+    unsigned long long off = __umul64hi(h, g.subcap / BUCKET_SLOTS) * BUCKET_SLOTS;
+    // one bucket per round: both halves of the 64-B line requested at once, the four slots examined in fill order
+    for (unsigned long long probes = 0; open && probes <= g.subcap; probes += BUCKET_SLOTS) {   // bounded: a full partition cannot hang
+        const Slot* b = &slots[base + off];
+        unsigned long long k0, w0, k1, w1, k2, w2, k3, w3;
+        ld_slot_pair(b, k0, w0, k1, w1);
+        ld_slot_pair(b + 2, k2, w2, k3, w3);
+        unsigned long long w = 0ull;
+        bool hit = true;
+        if (k0 == key) w = w0; else if (k1 == key) w = w1; else if (k2 == key) w = w2; else if (k3 == key) w = w3; else hit = false;
+        if (hit) { v = make_uint2((unsigned)w, (unsigned)(w >> 32)); open = false; }
+        else if (k0 == 0ull || k1 == 0ull || k2 == 0ull || k3 == 0ull) open = false;     // a free slot ends the walk
+        off = (off + BUCKET_SLOTS == g.subcap) ? 0ull : off + BUCKET_SLOTS;
     }
     __syncwarp();
     return v;

@@ -106,6 +106,12 @@ cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
                                   unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s);
 size_t cov_stats_long_scratch_bytes(unsigned int max_win, int k, int nctas);
+// device-driven twin: launched unconditionally, reads {count, max_win} from ll itself, lays out the given scratch budget
+// (error 4 in *d_error when one read does not fit), returns at once when there is no long read.  No host sync.
+cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k,
+                                       int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
+                                       float* d_stdev, uint32_t* d_per_kmer, LongList ll, void* d_scratch,
+                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s);
 
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                           int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok,
@@ -115,6 +121,10 @@ cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, ui
                                int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
                                unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s);
 size_t assign_long_scratch_bytes(unsigned int max_win, int k, int nctas);
+cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
+                                    const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
+                                    int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
+                                    int* d_error, int nctas, cudaStream_t s);
 
 // table scans
 cudaError_t launch_histo(const Slot* slots, uint64_t cap, unsigned long long* d_bins /*10002*/, cudaStream_t s);

@@ -570,22 +570,30 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
 
 #pragma unroll 1
             for (int gg = 0; gg < RP_PER_THREAD; gg += 4) {
-                unsigned long long key[4], cur[4];
+                unsigned long long key[4], cur[4], cur1[4];
                 Probe pr[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const unsigned i = i0 + (gg + u) * RP_THREADS + tid;
                     key[u] = i < n ? __ldcs(base + i) : 0ull;
                 }
+                // the first TWO slots of the home bucket in one 256-bit load: buckets fill front to back, so most keys
+                // that are not in slot 0 are in slot 1 and need no second (dependent) round trip to L2
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
-                        if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
-                        else { key[u] = 0ull; atomicExch(t.error, 2); }
+                        if (probe_home(t.g, key[u], pr[u])) {
+                            unsigned long long w0, w1;
+                            ld_slot_pair(&t.slots[pr[u].base + pr[u].off], cur[u], w0, cur1[u], w1);
+                        } else { key[u] = 0ull; atomicExch(t.error, 2); }
                     }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
+                        if (cur[u] != key[u] && cur[u] != 0ull) {      // slot 0 holds another key: go on from slot 1
+                            probe_next(t.g, pr[u]);
+                            cur[u] = cur1[u];
+                        }
                         Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
                         if (sl) atomicAdd(&sl->val, 1u);
                     }
@@ -896,51 +904,61 @@ __device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v
     return tot;
 }
 
-// Median of n <= PR_MAXWIN u32 values held in shared memory, by one warp, WITHOUT sorting: a radix select on the bits
-// below the highest set bit of the maximum (coverage values are small: a handful of bit rounds), each round one
-// predicate per element and one redux.sync.  Returns median_coverage() of fastaToKmerCoverageStats.cpp:337-347:
-// odd n -> the middle element, even n -> the (wrapping) u32 mean of the two middle elements.
-__device__ __forceinline__ uint32_t warp_median_u32(const uint32_t* __restrict__ v, int n, int lane) {
-    constexpr int PER = PR_MAXWIN / 32;
+// Median of n <= PR_MAXWIN u32 values held in shared memory, by one warp, WITHOUT sorting: a bisection on the VALUE
+// between the warp minimum and maximum (coverage values of one read sit in a narrow band, so a handful of rounds),
+// each round one compare per element and one redux.sync.  PER = elements per lane = ceil(n / 32), a template
+// parameter so that a 100-bp read (76 windows, PER = 3) does not pay for the 256-window maximum.  Returns
+// median_coverage() of fastaToKmerCoverageStats.cpp:337-347: odd n -> the middle element, even n -> the (wrapping)
+// u32 mean of the two middle elements.
+template <int PER>
+__device__ __forceinline__ uint32_t warp_median_per(const uint32_t* __restrict__ v, int n, int lane) {
     unsigned x[PER];
-    unsigned mx = 0;
+    const bool tail_live = (PER - 1) * 32 + lane < n;      // only the last element of a lane can lie past n
+    unsigned mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const int p = i * 32 + lane;
-        x[i] = p < n ? v[p] : 0u;
-        mx = max(mx, x[i]);
+        const bool live = i < PER - 1 || tail_live;
+        x[i] = live ? v[i * 32 + lane] : 0u;
+        if (live) { mn = min(mn, x[i]); mx = max(mx, x[i]); }
     }
-    mx = __reduce_max_sync(FULL, mx);
+    unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
     const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
-    unsigned prefix = 0, k = k1;
-    for (int b = 31 - __clz((int)(mx | 1u)); b >= 0; b--) {
-        const unsigned hi_mask = ~((2u << b) - 1u);        // the bits above b (0 for b = 31)
+    // smallest value with at least k1 + 1 elements <= it = the element of rank k1
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
         unsigned cnt = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) {
-            if (i * 32 < n) {
-                const bool live = i * 32 + lane < n;
-                cnt += (live && ((x[i] ^ prefix) & hi_mask) == 0u && !((x[i] >> b) & 1u)) ? 1u : 0u;
-            }
-        }
-        cnt = __reduce_add_sync(FULL, cnt);                // elements that share the prefix and have bit b clear
-        if (k >= cnt) { prefix |= 1u << b; k -= cnt; }
+        for (int i = 0; i < PER; i++) cnt += ((i < PER - 1 || tail_live) && x[i] <= mid) ? 1u : 0u;
+        cnt = __reduce_add_sync(FULL, cnt);
+        if (cnt >= k1 + 1u) hi = mid; else lo = mid + 1u;
     }
-    const unsigned x1 = prefix;                            // the element of rank k1
+    const unsigned x1 = lo;
     if (k1 == k2) return x1;
     unsigned le = 0, nxt = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        if (i * 32 < n) {
-            const bool live = i * 32 + lane < n;
-            le += (live && x[i] <= x1) ? 1u : 0u;
-            if (live && x[i] > x1) nxt = min(nxt, x[i]);
-        }
+        const bool live = i < PER - 1 || tail_live;
+        le += (live && x[i] <= x1) ? 1u : 0u;
+        if (live && x[i] > x1) nxt = min(nxt, x[i]);
     }
     le = __reduce_add_sync(FULL, le);
     nxt = __reduce_min_sync(FULL, nxt);
     const unsigned x2 = le >= k2 + 1u ? x1 : nxt;          // the element of rank k2 = k1 + 1
     return (uint32_t)(x1 + x2) / 2u;
+}
+
+__device__ __forceinline__ uint32_t warp_median_u32(const uint32_t* __restrict__ v, int n, int lane) {
+    static_assert(PR_MAXWIN == 256, "dispatch below covers 1..8 elements per lane");
+    switch ((n + 31) >> 5) {           // exact: warp_median_per assumes only a lane's LAST element can lie past n
+        case 0: case 1: return warp_median_per<1>(v, n, lane);
+        case 2: return warp_median_per<2>(v, n, lane);
+        case 3: return warp_median_per<3>(v, n, lane);
+        case 4: return warp_median_per<4>(v, n, lane);
+        case 5: return warp_median_per<5>(v, n, lane);
+        case 6: return warp_median_per<6>(v, n, lane);
+        case 7: return warp_median_per<7>(v, n, lane);
+        default: return warp_median_per<8>(v, n, lane);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1004,7 +1022,14 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
     } else {
         float acc = 0.0f;
         if (gtid == 0) {
-            for (int p = 0; p < nwin; p++) acc = __fadd_rn(acc, sq[p]);   // strict read order
+            // strict read order; four squares per load where sq is 16-B aligned (always on the warp path)
+            const float4* sq4 = reinterpret_cast<const float4*>(sq);
+            int p = 0;
+            for (; (reinterpret_cast<unsigned long long>(sq) & 15ull) == 0ull && p + 4 <= nwin; p += 4) {
+                const float4 q = sq4[p >> 2];
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q.x), q.y), q.z), q.w);
+            }
+            for (; p < nwin; p++) acc = __fadd_rn(acc, sq[p]);
             acc = __fsqrt_rn(__fdiv_rn(acc, __int2float_rn(nwin - 1)));
         }
         sd = acc;
@@ -1023,7 +1048,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
     stdev = sd;    // meaningful in gtid 0 only
 }
 
-struct PerReadSmem {
+struct alignas(16) PerReadSmem {
     uint32_t p0[PR_WARPS][PR_MAXCH];
     uint32_t p1[PR_WARPS][PR_MAXCH];
     uint32_t pb[PR_WARPS][PR_MAXCH];
@@ -1031,7 +1056,7 @@ struct PerReadSmem {
     unsigned int nhits[PR_WARPS];
 };
 
-__global__ void __launch_bounds__(PR_WARPS * 32)
+__global__ void __launch_bounds__(PR_WARPS * 32, 6)
 k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
             int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
             float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll) {
@@ -1069,10 +1094,32 @@ cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint
 }
 
 // scratch layout per CTA of the long path: planes 3*(nch+1) u32 | cov n2 u32 | sq n2 f32
-static inline size_t long_nch(unsigned max_win, int k) { return ((size_t)max_win + k - 1 + 31) / 32 + 2; }
-static inline size_t pow2_ge(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
-static inline size_t long_scratch_words(unsigned max_win, int k, int mult) {
+__host__ __device__ static inline size_t long_nch(unsigned max_win, int k) { return ((size_t)max_win + k - 1 + 31) / 32 + 2; }
+__host__ __device__ static inline size_t pow2_ge(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+__host__ __device__ static inline size_t long_scratch_words(unsigned max_win, int k, int mult) {
     return 3 * long_nch(max_win, k) + (size_t)2 * pow2_ge((size_t)mult * max_win);
+}
+
+// The CTA-per-read kernels run in one of two ways.  Host-driven (the host-buffer entry points, which synchronise
+// anyway): the host has read {count, max_win}, sized the scratch and passes them.  Device-driven (the *_dev entry
+// points, which must not synchronise -- a host stall would leave the GPU idle): the kernel is launched unconditionally
+// behind the warp-path kernel, reads {count, max_win} from `hdr` itself, lays the fixed scratch budget out and leaves
+// at once when there is no long read.  A read too long for the budget raises error 4 instead of a wrong answer.
+struct LongPlan { unsigned n_long, max_win, stride; size_t words_per_cta; };
+__device__ __forceinline__ bool long_plan(const unsigned int* hdr, unsigned n_long, unsigned max_win, size_t words_per_cta,
+                                          unsigned long long scratch_words, int k, int mult, int* error, LongPlan& pl) {
+    pl.n_long = n_long; pl.max_win = max_win; pl.words_per_cta = words_per_cta; pl.stride = gridDim.x;
+    if (!hdr) return true;
+    pl.n_long = hdr[0]; pl.max_win = hdr[1];
+    if (pl.n_long == 0) return false;
+    pl.words_per_cta = long_scratch_words(pl.max_win, k, mult);
+    const unsigned long long fit = scratch_words / pl.words_per_cta;
+    if (fit == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(error, 4);
+        return false;
+    }
+    pl.stride = (unsigned)min((unsigned long long)gridDim.x, fit);
+    return blockIdx.x < pl.stride;
 }
 size_t cov_stats_long_scratch_bytes(unsigned max_win, int k, int nctas) {
     return long_scratch_words(max_win, k, 1) * 4 * (size_t)nctas;
@@ -1085,15 +1132,19 @@ __global__ void __launch_bounds__(LONG_THREADS)
 k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k,
                  int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
                  float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer,
-                 const unsigned int* __restrict__ long_idx, unsigned int n_long, unsigned int max_win,
-                 uint32_t* scratch, size_t words_per_cta) {
+                 const unsigned int* __restrict__ long_idx, unsigned int n_long_h, unsigned int max_win_h,
+                 uint32_t* scratch, size_t words_per_cta_h, const unsigned int* __restrict__ hdr,
+                 unsigned long long scratch_words, int* error) {
     __shared__ unsigned long long red[LONG_THREADS / 32];
+    LongPlan pl;
+    if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 1, error, pl)) return;
+    const unsigned n_long = pl.n_long, max_win = pl.max_win;
     const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
     size_t n2max = 1; while (n2max < max_win) n2max <<= 1;
-    uint32_t* base = scratch + (size_t)blockIdx.x * words_per_cta;
+    uint32_t* base = scratch + (size_t)blockIdx.x * pl.words_per_cta;
     uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
     uint32_t* cov = PB + nchw; float* sq = reinterpret_cast<float*>(cov + n2max);
-    for (unsigned i = blockIdx.x; i < n_long; i += gridDim.x) {
+    for (unsigned i = blockIdx.x; i < n_long; i += pl.stride) {
         const uint64_t r = long_idx[i];
         const uint64_t o0 = offs[r], o1 = offs[r + 1];
         const int L = (int)(o1 - o0 - 1);
@@ -1113,7 +1164,19 @@ cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs,
     if (n_long == 0) return cudaSuccess;
     k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
                                                     d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
-                                                    (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1));
+                                                    (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1), nullptr, 0,
+                                                    nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k,
+                                       int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
+                                       float* d_stdev, uint32_t* d_per_kmer, LongList ll, void* d_scratch,
+                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_cov_stats_long", s);
+    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
+                                                    d_stdev, d_per_kmer, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
+                                                    scratch_bytes / 4, d_error);
     return cudaGetLastError();
 }
 
@@ -1287,13 +1350,17 @@ __global__ void __launch_bounds__(LONG_THREADS)
 k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k, int strand,
               const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut, int32_t* __restrict__ best,
               int32_t* __restrict__ pct, int32_t* __restrict__ score, const unsigned int* __restrict__ long_idx,
-              unsigned int n_long, unsigned int max_win, uint32_t* scratch, size_t words_per_cta) {
+              unsigned int n_long_h, unsigned int max_win_h, uint32_t* scratch, size_t words_per_cta_h,
+              const unsigned int* __restrict__ hdr, unsigned long long scratch_words, int* error) {
     __shared__ unsigned int nhits;
+    LongPlan pl;
+    if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 2, error, pl)) return;
+    const unsigned n_long = pl.n_long, max_win = pl.max_win;
     const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
-    uint32_t* base = scratch + (size_t)blockIdx.x * words_per_cta;
+    uint32_t* base = scratch + (size_t)blockIdx.x * pl.words_per_cta;
     uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
     int32_t* hits = reinterpret_cast<int32_t*>(PB + nchw);
-    for (unsigned i = blockIdx.x; i < n_long; i += gridDim.x) {
+    for (unsigned i = blockIdx.x; i < n_long; i += pl.stride) {
         const uint64_t r = long_idx[i];
         const uint64_t o0 = offs[r], o1 = offs[r + 1];
         const int L = (int)(o1 - o0 - 1);
@@ -1313,7 +1380,18 @@ cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, ui
     if (n_long == 0) return cudaSuccess;
     k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
                                                  d_pct, d_score, d_long_idx, n_long, max_win, (uint32_t*)d_scratch,
-                                                 long_scratch_words(max_win, k, 2));
+                                                 long_scratch_words(max_win, k, 2), nullptr, 0, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
+                                    const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
+                                    int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
+                                    int* d_error, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_assign_long", s);
+    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
+                                                 d_pct, d_score, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
+                                                 scratch_bytes / 4, d_error);
     return cudaGetLastError();
 }
 
