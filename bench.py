@@ -297,6 +297,8 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="multi-GPU k-mer exchange: peer = phase 1 stores into the owners' logs over NVLink (fused), "
                          "collective = NCCL all-to-all of the bins; auto = peer when peer memory maps")
+    ap.add_argument("--replay-fold", type=int, default=-1, help="fold duplicate k-mers per replay chunk (-1 = auto: 4+ GPUs)")
+    ap.add_argument("--exchange-bins", type=int, default=0, help="coarse bins the k-mers are exchanged in (0 = default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -333,6 +335,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = tg.Context(local_rank)
     ctx.set("count_mode", args.count_mode)
+    if args.replay_fold >= 0 and world == 1:
+        ctx.set("replay_fold", args.replay_fold)
     info = ctx.info()
     tx, tx_offs, tx_cum = make_transcriptome(args.ntx, SEED)
     d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, npairs, read_len, seed=SEED + 7919 * rank)
@@ -367,7 +371,9 @@ def main():
     else:
         from trinityrnaseq_b200 import sharded
         eng = sharded.DeviceEngine(ctx, K, True)
-        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=expected_total // world + 1, exchange=args.exchange)
+        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=expected_total // world + 1, exchange=args.exchange,
+                                        max_exchange_bins=args.exchange_bins or sharded.MAX_EXCHANGE_BINS,
+                                        replay_fold=None if args.replay_fold < 0 else bool(args.replay_fold))
         kc = sc.table
 
         def count_dev(recs_ptr):
@@ -558,7 +564,8 @@ def main():
                      "stats_table_slots": qinfo["capacity"], "stats_table_kmers": qinfo["distinct"]},
            "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
     if phases is not None:
-        out["multi_gpu"] = {"exchange": sc.exchange, "phases_ms_synced": phases, "bins": sc.nparts, "bins_per_rank": sc.lp}
+        out["multi_gpu"] = {"exchange": sc.exchange, "phases_ms_synced": phases, "partitions": sc.nparts, "partitions_per_rank": sc.lp,
+                            "exchange_bins": sc.cbins, "replay_fold": sc.replay_fold}
     if r2t is not None:
         out["reads_to_transcripts"] = r2t
     print(json.dumps(out))

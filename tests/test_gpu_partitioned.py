@@ -65,14 +65,15 @@ def test_logged_count_host_path(ctx, oracle, data, canonical, k):
         np.testing.assert_array_equal(gc, 2 * oc)
 
 
-@pytest.mark.parametrize("prefetch", [1, 0])
-def test_logged_count_device_path_and_stats(ctx, oracle, data, prefetch):
+@pytest.mark.parametrize("prefetch,fold", [(1, 0), (0, 0), (1, 1)])
+def test_logged_count_device_path_and_stats(ctx, oracle, data, prefetch, fold):
     _, reads = data
     recs, offs = tg.records_from_sequences(reads)
     ok, oc = oracle.jf_count(recs, 25, True, 1)
     ctx.set("count_mode", "log")
     ctx.set("part_bytes", 128 << 10)
     ctx.set("log_bytes", 8 << 20)            # the record buffer is replayed in several segments
+    ctx.set("replay_fold", fold)          # duplicates of a chunk folded in shared memory before the table
     ctx.set("replay_prefetch", prefetch)
     d = _dev_records(ctx, recs)
     with tg.KmerCounter(ctx, 25, is_ds=True, expected_keys=len(ok)) as kc:

@@ -134,7 +134,7 @@ def test_exchange_bins():
             assert c >= 1 and lp % c == 0 and c & (c - 1) == 0
             assert world * c <= sharded.MAX_EXCHANGE_BINS or c == 1
             assert c == lp or world * c * 2 > sharded.MAX_EXCHANGE_BINS
-    assert sharded.exchange_bins(8, 512) == 32 and sharded.exchange_bins(2, 512) == 128
+    assert sharded.exchange_bins(8, 512) == 16 and sharded.exchange_bins(2, 512) == 64
 
 
 def test_shard_geometry():

@@ -81,6 +81,9 @@ struct tg_ctx {
     KernelTimer timer;                                  // optional per-kernel event timing
     int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
     int replay_prefetch = 1;
+    bool replay_fold = false;                           // fold a chunk's duplicate keys in shared memory before the table
+                                                        // (pays when many GPUs send their copies of the same hot k-mers to
+                                                        // one owner; costs ~12 ms per 1.5 G entries otherwise)
     unsigned replay_groups = 8;                         // bins replayed concurrently (see k_log_replay)
     uint64_t hot_max_keys = 0;                          // size of the L2-resident hot cache; 0 = off (the default: measured
                                                         // no gain once the median stopped being a sort, profiles/README.md)
@@ -328,6 +331,8 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
     } else if (!strcmp(key, "long_scratch_mb")) {
         if (v < 1 || v > (64 << 10)) return fail(TG_ERR_ARG, "long_scratch_mb out of range (1..65536)");
         c->long_scratch_bytes = (size_t)v << 20;
+    } else if (!strcmp(key, "replay_fold")) {
+        c->replay_fold = v != 0;
     } else if (!strcmp(key, "replay_groups")) {
         if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
         c->replay_groups = (unsigned)v;
@@ -723,7 +728,7 @@ static int replay_log_async(tg_table* t) {
     tg_ctx* c = t->ctx;
     hot_invalidate(t);
     CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, c->replay_groups,
-                         t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
+                         t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
     c->launches += 2;
     CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
     t->log.pending_ub = 0;
@@ -973,7 +978,7 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
     CU(c->scratch.ensure(need));
     CU(launch_log_replay((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
                          t->g.nparts, c->replay_groups, (unsigned long long*)c->scratch.p, (unsigned long long*)d_hpoly,
-                         t->view(), c->replay_prefetch, c->sm_count, c->stream[0]));
+                         t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;
 }

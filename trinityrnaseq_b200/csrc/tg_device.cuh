@@ -217,12 +217,19 @@ __device__ __forceinline__ uint2 table_lookup2(const Slot* __restrict__ slots, c
     if (part >= g.nlocal) open = false;
     const unsigned long long base = (unsigned long long)part * g.subcap;
     unsigned long long off = __umul64hi(h, g.subcap / BUCKET_SLOTS) * BUCKET_SLOTS;
-    // one bucket per round: both halves of the 64-B line requested at once, the four slots examined in fill order
+    // one bucket per round, the four slots examined in fill order
     for (unsigned long long probes = 0; open && probes <= g.subcap; probes += BUCKET_SLOTS) {   // bounded: a full partition cannot hang
         const Slot* b = &slots[base + off];
         unsigned long long k0, w0, k1, w1, k2, w2, k3, w3;
         ld_slot_pair(b, k0, w0, k1, w1);
         ld_slot_pair(b + 2, k2, w2, k3, w3);
+        // Short-circuit on purpose: ptxas sinks the second load behind the outcome of the first pair, so a lookup settled by
+        // slots 0-1 (97 % in a count table at load 0.34) requests ONE sector.  Measured the other way (both halves always
+        // requested, branch-free match): k_cov_stats 35 -> 58 ms -- the second request is not free even though DRAM
+        // delivers the whole 64 B.  In a `dump -L 2` table a third of the lookups (absent singletons, slots 2-3) pay a
+        // second dependent round: 43 ms instead of 35 ms.  (Also measured and dropped: the lookups of a whole read -- three
+        // groups of 32 windows -- in flight together; it needs 64 registers, and the lost occupancy costs more than the
+        // saved round trips: 35 -> 38-40 ms.  The kernel is throughput-bound: 69 % issue slots, 66 % of DRAM peak.)
         unsigned long long w = 0ull;
         bool hit = true;
         if (k0 == key) w = w0; else if (k1 == key) w = w1; else if (k2 == key) w = w2; else if (k3 == key) w = w3; else hit = false;

@@ -444,6 +444,9 @@ cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int 
 constexpr int RP_THREADS = 256;
 constexpr int RP_PER_THREAD = 8;
 constexpr int RP_CHUNK = RP_THREADS * RP_PER_THREAD;
+constexpr int RP_FOLD = RP_CHUNK;                   // slots of the per-chunk fold table; entries that do not find a
+constexpr int RP_FOLD_PROBES = 8;                   // place within a few probes go to the table directly
+static_assert((RP_FOLD & (RP_FOLD - 1)) == 0 && (RP_FOLD / RP_THREADS) % 4 == 0, "fold table geometry");
 
 // Replay order.  Bins are dealt round-robin to G GROUPS (bin lp belongs to group lp % G); the chunk index space
 // lists group 0's bins first (in bin order, each bin's nsrc source segments together), then group 1's, ...  Every
@@ -509,6 +512,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+template <bool FOLD>
 __global__ void __launch_bounds__(RP_THREADS, 4)
 k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned G,
@@ -525,6 +529,10 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
         hpoly[4 + tid] = 0ull;
     }
     __shared__ unsigned long long s_w;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    unsigned long long* f_key = reinterpret_cast<unsigned long long*>(dyn);      // fold table of one chunk:
+    unsigned int* f_cnt = reinterpret_cast<unsigned int*>(f_key + RP_FOLD);      // key -> occurrences, open addressing
+    if (FOLD) for (int i = tid; i < RP_FOLD; i += RP_THREADS) { f_key[i] = 0ull; f_cnt[i] = 0u; }
     unsigned long long* counters = chunk_start + nperm + 1;
     unsigned last_lp = 0xFFFFFFFFu;
     // a CTA serves its own group first and then helps the following groups finish
@@ -568,14 +576,43 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
                 }
             }
 
+            // ---- the chunk's duplicates folded in shared memory first.  An expressed transcript's k-mers arrive hundreds
+            // of times per bin (and N GPUs send N times as many to the one owner): folded here, a key costs ONE global
+            // atomic per chunk instead of one per occurrence, and same-address atomics stop serialising in L2.
+#pragma unroll
+            for (int u = 0; FOLD && u < RP_PER_THREAD; u++) {
+                const unsigned i = i0 + u * RP_THREADS + tid;
+                const unsigned long long key = i < n ? __ldcs(base + i) : 0ull;
+                if (key != 0ull) {
+                    // bits 40..: every key of a bin shares the top bits of the LOW hash word (they are the partition)
+                    unsigned h = (unsigned)(mix64(key) >> 40) & (RP_FOLD - 1);
+                    int tries = 0;
+                    for (; tries < RP_FOLD_PROBES; tries++) {
+                        const unsigned long long old = atomicCAS(&f_key[h], 0ull, key);
+                        if (old == 0ull || old == key) { atomicAdd(&f_cnt[h], 1u); break; }
+                        h = (h + 1) & (RP_FOLD - 1);
+                    }
+                    if (tries == RP_FOLD_PROBES) table_update<false>(t, key, 1u, claimed);      // crowded corner: unfolded
+                }
+            }
+            if (FOLD) __syncthreads();
 #pragma unroll 1
             for (int gg = 0; gg < RP_PER_THREAD; gg += 4) {
                 unsigned long long key[4], cur[4], cur1[4];
+                unsigned cnt[4];
                 Probe pr[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const unsigned i = i0 + (gg + u) * RP_THREADS + tid;
-                    key[u] = i < n ? __ldcs(base + i) : 0ull;
+                    if (FOLD) {
+                        const unsigned sidx = (gg + u) * RP_THREADS + tid;
+                        key[u] = f_key[sidx];
+                        cnt[u] = f_cnt[sidx];
+                        if (key[u] != 0ull) { f_key[sidx] = 0ull; f_cnt[sidx] = 0u; }     // clean for the next chunk
+                    } else {
+                        const unsigned i = i0 + (gg + u) * RP_THREADS + tid;
+                        key[u] = i < n ? __ldcs(base + i) : 0ull;
+                        cnt[u] = 1u;
+                    }
                 }
                 // the first TWO slots of the home bucket in one 256-bit load: buckets fill front to back, so most keys
                 // that are not in slot 0 are in slot 1 and need no second (dependent) round trip to L2
@@ -595,7 +632,7 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
                             cur[u] = cur1[u];
                         }
                         Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
-                        if (sl) atomicAdd(&sl->val, 1u);
+                        if (sl) atomicAdd(&sl->val, cnt[u]);
                     }
                 __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
                                 // and every later log load / probe is issued once per lane subset
@@ -749,12 +786,19 @@ cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned i
     k_log_plan_counters<<<1, 64, 0, s>>>(nsrc, nlocal, groups, d_chunk_start);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int grid = max_resident_ctas((const void*)k_log_replay, RP_THREADS, 0, -1);
+    const bool fold = (prefetch & 2) != 0;             // bit 1 of the flags word: fold duplicates per chunk
+    const size_t dyn = fold ? (size_t)RP_FOLD * 12 : 0;
+    const void* kern = fold ? (const void*)k_log_replay<true> : (const void*)k_log_replay<false>;
+    int grid = max_resident_ctas(kern, RP_THREADS, dyn, -1);
     if (grid <= 0) grid = sm_count;
     grid = grid / (int)groups * (int)groups;           // the same number of CTAs in every group
     if (grid < (int)groups) grid = (int)groups;
-    k_log_replay<<<grid, RP_THREADS, 0, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
-                                             d_chunk_start, d_hpoly, t, prefetch);
+    if (fold)
+        k_log_replay<true><<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
+                                                       d_chunk_start, d_hpoly, t, prefetch & 1);
+    else
+        k_log_replay<false><<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
+                                                        d_chunk_start, d_hpoly, t, prefetch & 1);
     return cudaGetLastError();
 }
 
