@@ -293,7 +293,7 @@ def main():
     ap.add_argument("--count-mode", default="auto", choices=["auto", "direct", "log"])
     ap.add_argument("--stats-table", default="auto", choices=["auto", "min2", "full"],
                     help="min2: statistics read the device-side `dump -L 2` table (bit-identical, see DESIGN.md); "
-                         "auto = full table on one GPU, min2 when the table is sharded (it is what gets all-gathered)")
+                         "auto = full table on 1-2 GPUs, min2 from 4 GPUs on (it is what gets all-gathered)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="multi-GPU k-mer exchange: peer = phase 1 stores into the owners' logs over NVLink (fused), "
                          "collective = NCCL all-to-all of the bins; auto = peer when peer memory maps")
@@ -309,7 +309,9 @@ def main():
     nreads = 2 * npairs
     nwin = read_len - K + 1
     positions_per_step = 2 * nreads * nwin            # counted + queried, per GPU
-    min_count = 2 if (args.stats_table == "min2" or (args.stats_table == "auto" and world > 1)) else 1
+    # auto: the full shards are all-gathered on 2 GPUs (6.7 GB received, cheaper than compacting first and the statistics
+    # kernel is faster on the full table); from 4 GPUs on the `dump -L 2` shards are (a quarter of the bytes)
+    min_count = 2 if (args.stats_table == "min2" or (args.stats_table == "auto" and world >= 4)) else 1
     config = {"workload": f"configs[1]: synthetic {npairs / 1e6:g}M PE 2x{read_len} bp reads from a random "
                           f"{args.ntx}-transcript set, k=25 canonical count + fastaToKmerCoverageStats, per GPU",
               "reads_per_gpu": nreads, "k": K, "unit_definition": "k-mer window positions counted + positions queried",
@@ -522,11 +524,16 @@ def main():
             e["frac_of_hbm_peak"] = round(e["achieved_gbs"] / peak, 4)
         kernels.append(e)
     top = kernels[0]
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures of exactly
+    # this workload, profiles/r01_ncu_full_v3_count_stats_raw.csv; null for any other shape
+    ncu_traffic = {"k_cov_stats": 152.1e9, "k_log_replay": 33.6e9, "k_log_tiles": 13.9e9}
+    default_shape = (world == 1 and npairs == 10_000_000 and read_len == 100 and args.ntx == 20_000 and min_count == 1)
+    traffic = ncu_traffic.get(top["kernel"]) if default_shape else None
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("achieved_gbs"), "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": top.get("frac_of_hbm_peak"), "traffic": None,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": top.get("frac_of_hbm_peak"), "traffic": traffic,
                 "units_per_launch": count_positions, "kernel_ms": top["ms"], "kernels": kernels,
-                "note": "achieved = algorithmic bytes of one launch / its CUDA-event time; traffic (ncu dram bytes) is "
-                        "in profiles/README.md"}
+                "note": "achieved = algorithmic bytes of one launch / its CUDA-event time; traffic = ncu DRAM bytes of "
+                        "one launch of the same workload (profiles/README.md), bytes"}
     if not args.no_gups:
         slots = max(tinfo["capacity"] // world, 1 << 29)         # >= 8 GiB of 16-B slots
         nops = 1 << 30
