@@ -114,7 +114,8 @@ def r2t_cpu_reference(tx_small, offs_small, cum_small, read_len, nreads, seed, t
     return nreads / dt, dt
 
 
-def bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host, nreads, read_len, steps, want_cpu):
+def bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host, nreads, read_len, steps, want_cpu,
+              world=1, max_over_ranks=lambda x: x):
     """ReadsToTranscripts on the same reads (BASELINE metric, second half): label the bundle k-mers, assign every
     read.  Device-resident and host-buffer timings; the reads are the step's 20 M reads, the bundles are cut from
     the same transcriptome."""
@@ -143,7 +144,7 @@ def bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host
     ctx.timer_start()
     for _ in range(steps):
         dev_step()
-    ms = ctx.timer_stop() / steps
+    ms = max_over_ranks(ctx.timer_stop() / steps)
     kt = ctx.kernel_times()
     ctx.set("kernel_timing", 0)
     best_d = ctx.d2h(d_best, 4 * nreads, np.int32)
@@ -163,14 +164,16 @@ def bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host
     host_step()
     t0 = time.perf_counter()
     host_step()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     assert np.array_equal(best_d, best_h) and np.array_equal(pct_d[best_d >= 0], pct_h[best_h >= 0]), "r2t dev/host mismatch"
     nwin = read_len - K + 1
     lookups = 2 * nreads * nwin          # forward + reverse-complement pass (no -strand)
     out = {"metric": "reads/sec ReadsToTranscripts", "workload": f"configs[3] shape on this step's reads: {nreads} reads x "
-           f"{read_len} bp against {ncontigs} contigs in {nb} bundles cut from the same transcriptome, double-stranded, -p 10",
-           "value": nreads / (ms / 1e3), "unit": "reads/s", "ms_per_step": ms,
-           "e2e": {"value": nreads / e2e_s, "unit": "reads/s", "ms_per_step": e2e_s * 1e3,
+           f"{read_len} bp against {ncontigs} contigs in {nb} bundles cut from the same transcriptome, double-stranded, -p 10"
+           + (f"; per GPU, {world} GPUs, reads sharded by rank, the 1.2 GB label table built on every GPU (replicas only: "
+              f"the path has no exchange step)" if world > 1 else ""),
+           "value": world * nreads / (ms / 1e3), "unit": "reads/s", "ms_per_step": ms, "n_gpus": world,
+           "e2e": {"value": world * nreads / e2e_s, "unit": "reads/s", "ms_per_step": e2e_s * 1e3,
                    "h2d_bytes_per_step": int(brecs.nbytes + boffs.nbytes + nbytes + offs_host.nbytes),
                    "d2h_bytes_per_step": int(8 * nreads)},
            "bundle_kmers": int(labelled), "reads_assigned": int((best_d >= 0).sum()),
@@ -492,9 +495,11 @@ def main():
         assert np.array_equal(ctx.d2h(d_sd, 4 * nreads, np.uint32), sd_h.view(np.uint32)), "min2 table changed a stdev"
 
     r2t = None
-    if not args.no_r2t and world == 1:
+    if not args.no_r2t:
+        if world > 1:
+            barrier()
         r2t = bench_r2t(ctx, tg, tx, tx_offs, d_recs, nbytes, d_offs, offs_host, recs_host, nreads, read_len,
-                        max(1, min(args.steps, 3)), not args.no_cpu_baseline)
+                        max(1, min(args.steps, 3)), (not args.no_cpu_baseline) and rank == 0, world, max_over_ranks)
 
     if world > 1:
         sc.close()                       # collective: unmap the peer logs before anybody frees its own
