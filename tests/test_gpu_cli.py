@@ -155,3 +155,57 @@ def test_against_reference_binaries_when_present(tmp_path):
         assert run([os.path.join(BIN, "ReadsToTranscripts"), "-o", str(ob), "-t", "8"] + common).returncode == 0
         assert oa.read_bytes() == ob.read_bytes() and len(oa.read_bytes()) > 10000
         assert (tmp_path / "a.out.rcts.out").read_bytes() == (tmp_path / "b.out.rcts.out").read_bytes()
+
+
+def test_dump_sidecar_binary_handoff(tmp_path):
+    """`jellyfish dump > kmers.fa` leaves kmers.fa.tgk (packed pairs) next to the FASTA, and
+    fastaToKmerCoverageStats --kmers loads it instead of re-parsing the text -- only while it provably describes that
+    FASTA (length + content hash).  Output identical either way; any change to the FASTA falls back to the text."""
+    jf = os.path.join(BIN, "jellyfish")
+    stats = os.path.join(BIN, "fastaToKmerCoverageStats")
+    fa = os.path.join(GOLD, "reads.fa")
+    db = tmp_path / "m.jf"
+    assert run([jf, "count", "-t", "2", "-m", "25", "-s", "1000000", "--canonical", "-o", str(db), fa]).returncode == 0
+    kfa = tmp_path / "k.fa"
+    with open(kfa, "wb") as out:
+        r = subprocess.run([jf, "dump", "-L", "2", str(db)], stdout=out, stderr=subprocess.PIPE, env=ENV, timeout=300)
+    assert r.returncode == 0
+    side = tmp_path / "k.fa.tgk"
+    assert side.exists() and not (tmp_path / "k.fa.tgk.tmp").exists()
+    piped = run([jf, "dump", "-L", "2", str(db)])                       # same text through a pipe: no file to sit next to
+    assert piped.stdout == kfa.read_bytes()
+    nrec = kfa.read_bytes().count(b">")
+    assert side.stat().st_size == 40 + 12 * nrec
+
+    cmd = [stats, "--reads", fa, "--kmers", str(kfa), "--kmer_size", "25", "--DS"]
+    with_side = run(cmd)
+    assert with_side.returncode == 0 and len(with_side.stdout) > 1000
+    no_side = subprocess.run(cmd, capture_output=True, env=dict(ENV, TRINITY_GPU_NO_SIDECAR="1"), timeout=300)
+    assert no_side.returncode == 0 and no_side.stdout == with_side.stdout
+    done = [l for l in with_side.stderr.split(b"\n") if b"done parsing" in l]
+    done2 = [l for l in no_side.stderr.split(b"\n") if b"done parsing" in l]
+    assert done and done[0].split(b", taking")[0] == done2[0].split(b", taking")[0]      # same "N Kmers, M added"
+
+    # the FASTA edited in place (same length: one count digit changed) -> the hash no longer matches -> text is parsed
+    text = bytearray(kfa.read_bytes())
+    first_nl = text.index(b"\n")
+    assert text[1:first_nl].isdigit()
+    text[first_nl - 1] = ord("9") if text[first_nl - 1] != ord("9") else ord("8")
+    kfa.write_bytes(bytes(text))
+    edited = run(cmd)
+    edited_text = subprocess.run(cmd, capture_output=True, env=dict(ENV, TRINITY_GPU_NO_SIDECAR="1"), timeout=300)
+    assert edited.returncode == 0 and edited.stdout == edited_text.stdout and edited.stdout != with_side.stdout
+    # ... and grown by a record -> length mismatch -> text again
+    kfa.write_bytes(bytes(text) + b">7\n" + b"ACGT" * 6 + b"A\n")
+    grown = run(cmd)
+    grown_text = subprocess.run(cmd, capture_output=True, env=dict(ENV, TRINITY_GPU_NO_SIDECAR="1"), timeout=300)
+    assert grown.returncode == 0 and grown.stdout == grown_text.stdout
+
+    # -o writes a sidecar as well; the switch turns the writer off; column format never gets one
+    assert run([jf, "dump", "-L", "1", "-o", str(tmp_path / "o.fa"), str(db)]).returncode == 0
+    assert (tmp_path / "o.fa.tgk").exists()
+    r = subprocess.run([jf, "dump", "-o", str(tmp_path / "n.fa"), str(db)], capture_output=True,
+                       env=dict(ENV, TRINITY_GPU_NO_SIDECAR="1"), timeout=300)
+    assert r.returncode == 0 and not (tmp_path / "n.fa.tgk").exists()
+    assert run([jf, "dump", "-c", "-o", str(tmp_path / "c.txt"), str(db)]).returncode == 0
+    assert not (tmp_path / "c.txt.tgk").exists()

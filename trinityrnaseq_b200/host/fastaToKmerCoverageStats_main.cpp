@@ -4,12 +4,14 @@
 #include <math.h>
 #include <time.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "fasta_io.hpp"
 #include "tg_loader.hpp"
+#include "tg_sidecar.hpp"
 
 using namespace tgio;
 
@@ -85,7 +87,35 @@ int main(int argc, char** argv) {
         fprintf(stderr, "-reading Kmer occurrences...\n");
         time_t start = time(NULL);
         TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 32 + 1024, &table));
-        InchwormFastaReader rd(fv.data, fv.size);
+        // Binary hand-off (tg_sidecar.hpp): if our `jellyfish dump` left `<kmers>.tgk` and it provably describes THIS
+        // file (length + content hash), load the packed pairs and skip the text parse.  Same records, same
+        // `table[canon] += count` as populate_kmer_counter_from_kmers, same diagnostics.
+        bool from_sidecar = false;
+        if (!tgside::disabled()) {
+            FileView sv;
+            std::string serr;
+            if (sv.open(args.str("--kmers") + ".tgk", &serr) && sv.size >= sizeof(tgside::TgkHeader)) {
+                const tgside::TgkHeader* sh = (const tgside::TgkHeader*)sv.data;
+                if (memcmp(sh->magic, tgside::TGK_MAGIC, 8) == 0 && sh->k == (uint32_t)K && sh->text_bytes == fv.size &&
+                    sv.size == sizeof(tgside::TgkHeader) + sh->n * 12) {
+                    tgside::TextHash th;
+                    th.update(fv.data, fv.size);
+                    if (th.digest() == sh->text_hash) {
+                        const uint64_t* sk = (const uint64_t*)(sv.data + sizeof(tgside::TgkHeader));
+                        const uint32_t* sc = (const uint32_t*)(sv.data + sizeof(tgside::TgkHeader) + sh->n * 8);
+                        const uint64_t STEP = 32u << 20;
+                        for (uint64_t i = 0; i < sh->n; i += STEP)
+                            TGC(tg_table_load_pairs(table, sk + i, sc + i, std::min<uint64_t>(STEP, sh->n - i), is_DS));
+                        uint64_t cap = 0, distinct = 0;
+                        TGC(tg_table_info(table, &cap, &distinct));
+                        fprintf(stderr, "\n done parsing %lu Kmers, %llu added, taking %ld seconds.\n", (unsigned long)sh->n,
+                                (unsigned long long)distinct, (long)(time(NULL) - start));
+                        from_sidecar = true;
+                    }
+                }
+            }
+        }
+        InchwormFastaReader rd(fv.data, from_sidecar ? 0 : fv.size);      // nothing left to parse after a sidecar load
         std::vector<uint64_t> keys; std::vector<uint32_t> vals;
         std::vector<char> seq;
         const size_t FLUSH = 8u << 20;
@@ -116,10 +146,12 @@ int main(int argc, char** argv) {
             }
         }
         if (!keys.empty()) TGC(tg_table_load_pairs(table, keys.data(), vals.data(), keys.size(), is_DS));
-        uint64_t cap = 0, distinct = 0;
-        TGC(tg_table_info(table, &cap, &distinct));
-        fprintf(stderr, "\n done parsing %lu Kmers, %llu added, taking %ld seconds.\n", parsed,
-                (unsigned long long)distinct, (long)(time(NULL) - start));
+        if (!from_sidecar) {
+            uint64_t cap = 0, distinct = 0;
+            TGC(tg_table_info(table, &cap, &distinct));
+            fprintf(stderr, "\n done parsing %lu Kmers, %llu added, taking %ld seconds.\n", parsed,
+                    (unsigned long long)distinct, (long)(time(NULL) - start));
+        }
     } else {
         // populate_kmer_counter_from_reads (:230-293): reads shorter than K+1 are skipped entirely
         FileView fv;

@@ -11,6 +11,7 @@
 
 #include "fasta_io.hpp"
 #include "tg_loader.hpp"
+#include "tg_sidecar.hpp"
 
 using namespace tgio;
 
@@ -215,9 +216,21 @@ int cmd_dump(int argc, char** argv) {
         if (fd < 0) { fprintf(stderr, "jellyfish: cannot open output file: %s\n", strerror(errno)); return 1; }
     }
     const int k = (int)jf.h->k;
+    // Binary hand-off (tg_sidecar.hpp): a FASTA dump that lands in a regular file gets `<file>.tgk` next to it with the
+    // same records as packed pairs, so fastaToKmerCoverageStats --kmers need not re-parse ~31 B of text per k-mer.
+    const std::string text_path = (!column && !tgside::disabled()) ? tgside::regular_file_behind(fd) : "";
+    std::vector<uint64_t> side_keys;
+    std::vector<uint32_t> side_counts;
+    tgside::TextHash hash;
     {
         OutBuf out(fd, 16u << 20);
         char line[96];
+        auto put_uint = [](char* dst, uint32_t v) {             // decimal without sprintf: this loop runs 10^8 times
+            char tmp[12]; int n = 0;
+            do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+            for (int i = 0; i < n; i++) dst[i] = tmp[n - 1 - i];
+            return n;
+        };
         for (uint64_t i = 0; i < jf.h->n; i++) {
             const uint32_t c = jf.counts[i];
             if (c < lower || c > upper) continue;
@@ -226,18 +239,42 @@ int cmd_dump(int argc, char** argv) {
                 tgh::unpack_kmer(jf.keys[i], k, line);
                 n = k;
                 line[n++] = tab ? '\t' : ' ';
-                n += sprintf(line + n, "%u\n", c);
+                n += put_uint(line + n, c);
+                line[n++] = '\n';
             } else {                                            // FASTA: ">COUNT\nKMER\n"
-                n = sprintf(line, ">%u\n", c);
+                line[0] = '>';
+                n = 1 + put_uint(line + 1, c);
+                line[n++] = '\n';
                 tgh::unpack_kmer(jf.keys[i], k, line + n);
                 n += k;
                 line[n++] = '\n';
             }
             out.put(line, (size_t)n);
+            if (!text_path.empty()) {
+                hash.update(line, (size_t)n);
+                side_keys.push_back(jf.keys[i]);
+                side_counts.push_back(c);
+            }
         }
         if (!out.flush()) { fprintf(stderr, "jellyfish: write failed: %s\n", strerror(errno)); return 1; }
     }
     if (fd != 1) ::close(fd);
+    if (!text_path.empty()) {
+        // best effort: a sidecar that cannot be written is simply absent (the FASTA is complete either way)
+        const std::string side = text_path + ".tgk", tmp = side + ".tmp";
+        tgside::TgkHeader h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, tgside::TGK_MAGIC, 8);
+        h.k = (uint32_t)k; h.n = side_keys.size(); h.text_bytes = hash.total; h.text_hash = hash.digest();
+        FILE* f = fopen(tmp.c_str(), "wb");
+        bool ok = f != nullptr;
+        ok = ok && fwrite(&h, sizeof h, 1, f) == 1;
+        ok = ok && (h.n == 0 || fwrite(side_keys.data(), 8, h.n, f) == h.n);
+        ok = ok && (h.n == 0 || fwrite(side_counts.data(), 4, h.n, f) == h.n);
+        if (f) ok = (fclose(f) == 0) && ok;
+        if (ok) ok = rename(tmp.c_str(), side.c_str()) == 0;
+        if (!ok) unlink(tmp.c_str());
+    }
     return 0;
 }
 
