@@ -65,6 +65,49 @@ def test_logged_count_host_path(ctx, oracle, data, canonical, k):
         np.testing.assert_array_equal(gc, 2 * oc)
 
 
+@pytest.mark.parametrize("path", ["host", "device", "device_fine_overflow"])
+def test_logged_count_more_partitions_than_log_bins_is_refined(ctx, oracle, data, path):
+    """A table with more partitions than the 512 log bins phase 1 is fast with (on one GPU: tables beyond ~8 GB; here
+    4 KiB partitions): phase 1 fills 512 COARSE bins and the replay first splits them into one segment per partition
+    (k_log_refine).  A repeat k-mer that overflows its fine segment is counted directly.  Bit-exact either way."""
+    _, reads = data
+    reads = list(reads) + [b"ACACACACACACACACACACACACACACACACACACACACACACACACAGACACACACACACACACACACACACACACACACACACACACACACACACACAC"] * 900
+    if path == "device_fine_overflow":
+        # 40 MB of N: no k-mers, but the log is laid out for the input size, so the coarse bin now HOLDS the repeat
+        # (no direct insert in phase 1) and it is its fine segment (1/11 of the coarse bin) that overflows in the refine
+        reads = reads + [b"N" * 1_000_000] * 40
+    recs, offs = tg.records_from_sequences(reads)
+    k = 25
+    ok, oc = oracle.jf_count(recs, k, True, 1)
+    assert oc.max() > 20000                                  # the repeat: tens of thousands of occurrences of two k-mers
+    ctx.set("count_mode", "log")
+    ctx.set("part_bytes", 4 << 10)                           # 256-slot partitions -> thousands of partitions
+    ctx.set("kernel_timing", 1)
+    ctx.kernel_times()
+    with tg.KmerCounter(ctx, k, is_ds=True, expected_keys=len(ok)) as kc:
+        nparts = kc.geometry()[1]
+        assert nparts > 512 and nparts % 512 == 0
+        if path == "host":
+            kc.add_records(recs)
+        else:
+            d = _dev_records(ctx, recs)
+            kc.add_records_dev(d, recs.nbytes)
+        gk, gc = kc.dump()
+        kt = ctx.kernel_times()
+        assert "k_log_refine" in kt and "k_log_replay" in kt and "k_log_tiles" in kt
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc, oc)
+        assert kc.size() == len(ok)
+        if path != "host":
+            kc.add_records_dev(d, recs.nbytes)               # buffers reused, counts double
+            gk, gc = kc.dump()
+            np.testing.assert_array_equal(gc, 2 * oc)
+            ctx.dev_free(d)
+    ctx.set("kernel_timing", 0)
+    ctx.set("part_bytes", 16 << 20)
+    ctx.set("count_mode", "auto")
+
+
 @pytest.mark.parametrize("prefetch,fold", [(1, 0), (0, 0), (1, 1)])
 def test_logged_count_device_path_and_stats(ctx, oracle, data, prefetch, fold):
     _, reads = data

@@ -10,8 +10,11 @@ from bench import make_transcriptome, SEED, K
 ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=10_000_000)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--part-mb", type=int, default=0, help="table partition size (0 = default 16)")
 a = ap.parse_args()
 ctx = tg.Context(0)
+if a.part_mb:
+    ctx.set("part_mb", a.part_mb)
 tx, tx_offs, tx_cum = make_transcriptome(20000, SEED)
 d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, a.pairs, 100, seed=SEED)
 nreads = 2 * a.pairs
@@ -43,4 +46,4 @@ for rep in range(a.reps):
     kt = ctx.kernel_times()
     print(json.dumps({"rep": rep, "clear_ms": round(t_clear, 2), "count_ms": round(t_count, 2), "stats_ms": round(t_stats, 2),
                       "step_event_ms": round(t_step, 2), "kernels": {k: round(v[0], 2) for k, v in kt.items()},
-                      "info": kc.info()}), flush=True)
+                      "info": kc.info(), "geometry": kc.geometry()}), flush=True)

@@ -99,6 +99,11 @@ struct KeyLog {
     unsigned long long* chunk_start = nullptr;
     unsigned long long* hpoly = nullptr;   // [8] homopolymer side channel (keys, counts)
     unsigned nbins = 0, cap = 0;
+    // tables with more partitions than LOG_BASE_BINS: phase 1 fills `nbins` COARSE bins (long runs per tile) and the
+    // replay first splits them into one segment per partition (k_log_refine)
+    unsigned long long* fine_keys = nullptr;
+    unsigned int* fine_cursor = nullptr;
+    unsigned fine_bins = 0, fine_cap = 0, plan_bins = 0;
     uint64_t pending_ub = 0;          // host-side upper bound on entries appended since the last replay
     uint64_t total_entries() const { return (uint64_t)nbins * cap; }
 };
@@ -421,6 +426,8 @@ static void log_release(tg_table* t) {
     if (t->log.keys) cudaFree(t->log.keys);
     if (t->log.cursor) cudaFree(t->log.cursor);
     if (t->log.chunk_start) cudaFree(t->log.chunk_start);
+    if (t->log.fine_keys) cudaFree(t->log.fine_keys);
+    if (t->log.fine_cursor) cudaFree(t->log.fine_cursor);
     if (t->log.hpoly) cudaFree(t->log.hpoly);
     t->log = KeyLog();
 }
@@ -650,9 +657,16 @@ static int upload_records(tg_ctx* c, int b, const char* src, uint64_t n) {
 }  // extern "C"
 
 // ---- k-mer log management (partitioned count path) -------------------------------------------------------
+// can a log of `nbins` coarse bins be split into the table's partitions at replay time?
+static bool log_refines(const tg_table* t, unsigned nbins) {
+    const unsigned np = t->g.nparts;
+    return !t->sharded() && nbins < np && np % nbins == 0 && np / nbins <= log_refine_max_split();
+}
+
 static unsigned log_bins_for(const tg_table* t) {
     if (t->sharded()) return t->g.nparts;                      // bins == global partitions (exchange unit)
-    return t->g.nparts > LOG_BASE_BINS ? t->g.nparts : LOG_BASE_BINS;
+    if (t->g.nparts <= LOG_BASE_BINS || log_refines(t, LOG_BASE_BINS)) return LOG_BASE_BINS;
+    return t->g.nparts;
 }
 
 // worth logging?  The replay streams the whole table through L2 once, so the batch must be large next to it.
@@ -690,6 +704,7 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
     uint64_t budget = std::min<uint64_t>(c->log_max_bytes, fr / 2);
+    if (log_refines(t, nbins)) budget /= 2;                  // the other half is the fine log of the replay
     if (t->log.keys) budget = std::max<uint64_t>(budget, t->log.total_entries() * 8);
     uint64_t per_bin = want;
     per_bin = std::min<uint64_t>(per_bin, budget / 8 / nbins);
@@ -702,6 +717,7 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     if (cudaMalloc(&t->log.keys, per_bin * nbins * 8) != cudaSuccess) { cudaGetLastError(); t->log.keys = nullptr; return TG_OK; }
     CU(cudaMalloc(&t->log.cursor, nbins * sizeof(unsigned int)));
     CU(cudaMalloc(&t->log.chunk_start, log_replay_plan_words(1, nbins, 64) * sizeof(unsigned long long)));
+    t->log.plan_bins = nbins;
     CU(cudaMalloc(&t->log.hpoly, 8 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(t->log.cursor, 0, nbins * sizeof(unsigned int), c->stream[0]));
     CU(cudaMemsetAsync(t->log.hpoly, 0, 8 * sizeof(unsigned long long), c->stream[0]));
@@ -724,9 +740,52 @@ static LogView log_view(tg_table* t) {
 }
 
 // replay + reset on stream 0 (stream-ordered; no host sync)
+// coarse log -> one segment per partition (stream-ordered); false when the fine log cannot be had (then the coarse bins
+// are replayed as they are: correct, but a bin's partitions no longer fit in L2)
+static bool refine_log_async(tg_table* t) {
+    tg_ctx* c = t->ctx;
+    KeyLog& lg = t->log;
+    if (!log_refines(t, lg.nbins)) return false;
+    const unsigned np = t->g.nparts;
+    uint64_t fcap = (uint64_t)((double)lg.cap * lg.nbins / np * 1.3) + 2048;
+    fcap = (fcap + LOG_CAP_ALIGN - 1) / LOG_CAP_ALIGN * LOG_CAP_ALIGN;
+    if (fcap > LOG_CAP_MAX) return false;
+    if (lg.fine_bins != np || lg.fine_cap < fcap) {
+        if (lg.fine_keys) cudaFree(lg.fine_keys);
+        if (lg.fine_cursor) cudaFree(lg.fine_cursor);
+        lg.fine_keys = nullptr; lg.fine_cursor = nullptr; lg.fine_bins = 0; lg.fine_cap = 0;
+        if (cudaMalloc(&lg.fine_keys, (uint64_t)np * fcap * 8) != cudaSuccess) { cudaGetLastError(); lg.fine_keys = nullptr; return false; }
+        if (cudaMalloc(&lg.fine_cursor, np * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(lg.fine_keys); lg.fine_keys = nullptr; lg.fine_cursor = nullptr; return false;
+        }
+        lg.fine_bins = np; lg.fine_cap = (unsigned)fcap;
+    }
+    if (lg.plan_bins < np) {
+        unsigned long long* p = nullptr;
+        if (cudaMalloc(&p, log_replay_plan_words(1, np, 64) * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaStreamSynchronize(c->stream[0]);
+        cudaFree(lg.chunk_start);
+        lg.chunk_start = p; lg.plan_bins = np;
+    }
+    if (cudaMemsetAsync(lg.fine_cursor, 0, np * sizeof(unsigned int), c->stream[0]) != cudaSuccess) return false;
+    if (launch_log_refine(lg.keys, lg.cursor, lg.cap, 1, lg.nbins, lg.chunk_start, lg.fine_keys, lg.fine_cursor, lg.fine_cap, np,
+                          0, np, t->d_error, t->view(), c->sm_count, c->stream[0]) != cudaSuccess) return false;
+    c->launches += 2;
+    return true;
+}
+
 static int replay_log_async(tg_table* t) {
     tg_ctx* c = t->ctx;
     hot_invalidate(t);
+    if (refine_log_async(t)) {
+        CU(launch_log_replay(t->log.fine_keys, t->log.fine_cursor, t->log.fine_cap, 1, t->log.fine_bins, 0, t->log.fine_bins,
+                             c->replay_groups, t->log.chunk_start, t->log.hpoly, t->view(),
+                             c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
+        c->launches += 2;
+        CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
+        t->log.pending_ub = 0;
+        return TG_OK;
+    }
     CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, c->replay_groups,
                          t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
     c->launches += 2;
@@ -926,16 +985,17 @@ int tg_log_refine_dev(tg_ctx* c, const void* d_keys, const void* d_cursor, uint3
     if (!c || !d_keys || !d_cursor || !d_out_keys || !d_out_cursor)
         return fail(TG_ERR_ARG, "tg_log_refine_dev: null argument");
     if (nsrc == 0 || ncoarse == 0 || cap == 0 || nfine == 0 || out_cap == 0 || out_cap > LOG_CAP_MAX || nfine % ncoarse ||
-        (uint64_t)fine0 + nfine > nfine_global || nfine > 2048)
-        return fail(TG_ERR_ARG, "tg_log_refine_dev: bad shape (fine bins a multiple of the coarse bins, at most 2048, "
-                                "inside the global partition range)");
+        (uint64_t)fine0 + nfine > nfine_global || nfine / ncoarse > log_refine_max_split() || nfine > LOG_MAX_BINS)
+        return fail(TG_ERR_ARG, "tg_log_refine_dev: bad shape (fine bins a multiple of the coarse bins, at most %u per "
+                                "coarse bin, inside the global partition range)", log_refine_max_split());
     if (bind(c)) return TG_ERR_CUDA;
     const size_t need = std::max(log_refine_plan_words(nsrc, ncoarse), log_replay_plan_words(1, nfine, 64)) *
                         sizeof(unsigned long long);
     CU(c->scratch.ensure(need));
     CU(launch_log_refine((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, ncoarse,
                          (unsigned long long*)c->scratch.p, (unsigned long long*)d_out_keys, (unsigned int*)d_out_cursor,
-                         out_cap, nfine, fine0, nfine_global, c->d_error, c->sm_count, c->stream[0]));
+                         out_cap, nfine, fine0, nfine_global, c->d_error, TableView{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr},
+                         c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;
 }

@@ -80,13 +80,14 @@ cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned i
                               int sm_count, cudaStream_t s);
 // owner-side refinement of a received COARSE log [nsrc][ncoarse][cap] into a FINE log [nfine][out_cap] (one segment per
 // fine bin = table partition fine0 + bin of nfine_global): see k_log_refine.  d_out_cursor zeroed by the caller;
-// d_chunk_start: scratch of log_refine_plan_words(nsrc, ncoarse) u64.  Errors (2 = foreign key, 3 = fine bin full) are
-// raised in *d_error.
+// d_chunk_start: scratch of log_refine_plan_words(nsrc, ncoarse) u64.  A full fine bin counts its overflow directly into
+// overflow_table when that has slots, else raises error 3 in *d_error; a foreign key raises error 2.
 size_t log_refine_plan_words(unsigned nsrc, unsigned ncoarse);
+unsigned log_refine_max_split();      // most table partitions one coarse bin may cover
 cudaError_t launch_log_refine(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned ncoarse, unsigned long long* d_chunk_start, unsigned long long* d_out_keys,
                               unsigned int* d_out_cursor, unsigned out_cap, unsigned nfine, unsigned fine0,
-                              unsigned nfine_global, int* d_error, int sm_count, cudaStream_t s);
+                              unsigned nfine_global, int* d_error, TableView overflow_table, int sm_count, cudaStream_t s);
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);

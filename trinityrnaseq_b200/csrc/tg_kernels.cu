@@ -654,27 +654,25 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
 constexpr int RF_THREADS = 256;
 constexpr int RF_PER_THREAD = RP_CHUNK / RF_THREADS;
 static_assert(RP_CHUNK % RF_THREADS == 0, "chunk = whole rounds of the CTA");
-constexpr unsigned RF_MAX_FINE = 2048;              // fine bins (partitions) per rank
+constexpr unsigned RF_MAX_SPLIT = RF_THREADS;       // table partitions per coarse bin: one counter per thread
 
 __global__ void __launch_bounds__(RF_THREADS, 4)
 k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned ncoarse, const unsigned long long* __restrict__ chunk_start,
              unsigned long long* __restrict__ out_keys, unsigned int* __restrict__ out_cursor, unsigned out_cap,
-             unsigned nfine, unsigned fine0, unsigned nfine_global, int* error) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    // dynamic: skey[RP_CHUNK] u64 | cnt[nfine] u32 | delta[nfine] u32 | sbin[RP_CHUNK] u16 | off[nfine] u16
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dyn);
-    unsigned int* cnt = reinterpret_cast<unsigned int*>(skey + RP_CHUNK);
-    unsigned int* delta = cnt + nfine;
-    unsigned short* sbin = reinterpret_cast<unsigned short*>(delta + nfine);
-    unsigned short* off = sbin + RP_CHUNK;
+             unsigned nfine, unsigned fine0, unsigned nfine_global, int* error, TableView t) {
+    unsigned claimed = 0;
+    // a chunk belongs to ONE coarse bin, so only its f = nfine / ncoarse fine bins can occur: all bookkeeping is per f
+    __shared__ unsigned long long skey[RP_CHUNK];
+    __shared__ unsigned short sbin[RP_CHUNK];
+    __shared__ unsigned int cnt[RF_MAX_SPLIT], delta[RF_MAX_SPLIT], off[RF_MAX_SPLIT];
     __shared__ unsigned wtot[RF_THREADS / 32];
     __shared__ unsigned s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned f = nfine / ncoarse;
     const unsigned nseg = nsrc * ncoarse;
     const unsigned long long nchunks = chunk_start[nseg];
-    const unsigned per = (nfine + RF_THREADS - 1) / RF_THREADS;
-    for (unsigned b = tid; b < nfine; b += RF_THREADS) cnt[b] = 0u;
+    cnt[tid] = 0u;
     __syncthreads();
     unsigned q = 0;
     for (unsigned long long w = blockIdx.x; w < nchunks; w += gridDim.x) {
@@ -683,7 +681,8 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
         const unsigned n = min(cursor[seg], cap);
         const unsigned long long* base = keys + (unsigned long long)seg * cap;
         const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
-        // ---- A: fine bin and rank of every key
+        const unsigned first = fine0 + lb * f;                     // global index of this coarse bin's first partition
+        // ---- A: fine bin (inside the coarse bin) and rank of every key
         unsigned long long key[RF_PER_THREAD];
         unsigned meta[RF_PER_THREAD];                              // bin << 12 | rank, ~0 = no entry
 #pragma unroll
@@ -695,36 +694,28 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
         for (int j = 0; j < RF_PER_THREAD; j++) {
             meta[j] = 0xFFFFFFFFu;
             if (key[j] != 0ull) {
-                const unsigned bin = hash_part(mix64(key[j]), nfine_global) - fine0;
-                if (bin < nfine) meta[j] = (bin << 12) | atomicAdd(&cnt[bin], 1u);
-                else atomicExch(error, 2);                         // a key that does not belong to this rank
+                const unsigned bin = hash_part(mix64(key[j]), nfine_global) - first;
+                if (bin < f) meta[j] = (bin << 12) | atomicAdd(&cnt[bin], 1u);
+                else atomicExch(error, 2);                         // a key that does not belong to this coarse bin
             }
         }
         __syncthreads();
-        // ---- S: scan the counters, reserve every bin's run in the fine log
+        // ---- S: scan the f counters (one per thread), reserve every bin's run in the fine log
         {
-            const unsigned b0 = tid * per, b1 = min(b0 + per, nfine);
-            unsigned sum = 0;
-            for (unsigned b = b0; b < b1; b++) sum += cnt[b];
-            unsigned incl = sum;
+            const unsigned c = (unsigned)tid < f ? cnt[tid] : 0u;
+            unsigned incl = c;
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned v = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += v;
             }
             if (lane == 31) wtot[warp] = incl;
             __syncthreads();
-            unsigned run = incl - sum;
+            unsigned run = incl - c;
             for (int ww = 0; ww < warp; ww++) run += wtot[ww];
-            if (tid == RF_THREADS - 1) s_total = run + sum;
-            for (unsigned b = b0; b < b1; b++) {
-                const unsigned c = cnt[b];
-                off[b] = (unsigned short)run;
-                if (c) {
-                    delta[b] = atomicAdd(&out_cursor[b], c) - run;
-                    cnt[b] = 0;
-                    run += c;
-                }
-            }
+            if (tid == RF_THREADS - 1) s_total = run + c;
+            off[tid] = run;
+            if (c) delta[tid] = atomicAdd(&out_cursor[lb * f + tid], c) - run;
+            cnt[tid] = 0u;
         }
         __syncthreads();
         // ---- B: keys into their sorted places
@@ -736,36 +727,39 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
                 sbin[idx] = (unsigned short)bin;
             }
         __syncthreads();
-        // ---- W: stream the sorted chunk out
+        // ---- W: stream the sorted chunk out: runs of hundreds of entries per fine bin
         const unsigned total = s_total;
         for (unsigned i = tid; i < total; i += RF_THREADS) {
             const unsigned bin = sbin[i], pos = delta[bin] + i;
-            if (pos < out_cap) out_keys[(unsigned long long)bin * out_cap + pos] = skey[i];
+            if (pos < out_cap) out_keys[(unsigned long long)(lb * f + bin) * out_cap + pos] = skey[i];
+            else if (t.slots) table_update<false>(t, skey[i], 1u, claimed);      // fine bin full (a repeat k-mer): count directly
             else atomicExch(error, 3);
         }
         __syncthreads();
     }
+    if (t.slots) {
+        for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+        if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
+    }
 }
 
 size_t log_refine_plan_words(unsigned nsrc, unsigned ncoarse) { return (size_t)nsrc * ncoarse + 2; }
+unsigned log_refine_max_split() { return RF_MAX_SPLIT; }
 
 cudaError_t launch_log_refine(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned ncoarse, unsigned long long* d_chunk_start, unsigned long long* d_out_keys,
                               unsigned int* d_out_cursor, unsigned out_cap, unsigned nfine, unsigned fine0,
-                              unsigned nfine_global, int* d_error, int sm_count, cudaStream_t s) {
+                              unsigned nfine_global, int* d_error, TableView t, int sm_count, cudaStream_t s) {
     TimedLaunch timed("k_log_refine", s);
     if (nsrc == 0 || ncoarse == 0 || nfine == 0) return cudaSuccess;
-    if (nfine > RF_MAX_FINE) return cudaErrorInvalidValue;
+    if (nfine % ncoarse || nfine / ncoarse > RF_MAX_SPLIT) return cudaErrorInvalidValue;
     k_log_plan<<<1, 1024, 0, s>>>(d_cursor, cap, nsrc, ncoarse, 1, d_chunk_start);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const size_t dyn = (size_t)RP_CHUNK * 8 + (size_t)nfine * 8 + (size_t)RP_CHUNK * 2 + (size_t)((nfine + 1) & ~1u) * 2;
-    e = cudaFuncSetAttribute((const void*)k_log_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    int grid = max_resident_ctas((const void*)k_log_refine, RF_THREADS, dyn, -1);
+    int grid = max_resident_ctas((const void*)k_log_refine, RF_THREADS, 0, -1);
     if (grid <= 0) grid = sm_count;
-    k_log_refine<<<grid, RF_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, ncoarse, d_chunk_start, d_out_keys, d_out_cursor,
-                                               out_cap, nfine, fine0, nfine_global, d_error);
+    k_log_refine<<<grid, RF_THREADS, 0, s>>>(d_keys, d_cursor, cap, nsrc, ncoarse, d_chunk_start, d_out_keys, d_out_cursor,
+                                             out_cap, nfine, fine0, nfine_global, d_error, t);
     return cudaGetLastError();
 }
 
