@@ -90,3 +90,15 @@ def test_packing_roundtrip():
         assert tg.packed_to_kmer(tg.kmer_to_packed(s), 25) == s
     recs, offs = tg.records_from_sequences(["ACGT", "", "GG"])
     assert recs.tobytes() == b"ACGT\n\nGG\n" and offs.tolist() == [0, 5, 6, 9]
+
+
+def test_sidecar_content_hash_cpp(tmp_path):
+    """host/tg_sidecar.hpp (binary hand-off between `jellyfish dump` and the stats tool): the content hash is independent
+    of the writer's chunking and notices single-byte edits and truncation -- compiled and run on the CPU."""
+    import subprocess
+    exe = tmp_path / "sidecar_hash_test"
+    src = os.path.join(ROOT, "tests", "cpp", "sidecar_hash_test.cpp")
+    inc = os.path.join(ROOT, "trinityrnaseq_b200", "host")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), src], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr

@@ -444,6 +444,13 @@ cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int 
 constexpr int RP_THREADS = 256;
 constexpr int RP_PER_THREAD = 8;
 constexpr int RP_CHUNK = RP_THREADS * RP_PER_THREAD;
+#ifndef RP_GROUP
+#define RP_GROUP 4                                  // entries per thread whose probes are in flight together
+#endif
+#ifndef RP_MIN_CTAS
+#define RP_MIN_CTAS 4
+#endif
+static_assert(RP_PER_THREAD % RP_GROUP == 0, "groups tile a thread's entries");
 constexpr int RP_FOLD = RP_CHUNK;                   // slots of the per-chunk fold table; entries that do not find a
 constexpr int RP_FOLD_PROBES = 8;                   // place within a few probes go to the table directly
 static_assert((RP_FOLD & (RP_FOLD - 1)) == 0 && (RP_FOLD / RP_THREADS) % 4 == 0, "fold table geometry");
@@ -513,7 +520,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
 }
 
 template <bool FOLD>
-__global__ void __launch_bounds__(RP_THREADS, 4)
+__global__ void __launch_bounds__(RP_THREADS, RP_MIN_CTAS)
 k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned G,
              unsigned long long* chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
@@ -597,12 +604,12 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
             }
             if (FOLD) __syncthreads();
 #pragma unroll 1
-            for (int gg = 0; gg < RP_PER_THREAD; gg += 4) {
-                unsigned long long key[4], cur[4], cur1[4];
-                unsigned cnt[4];
-                Probe pr[4];
+            for (int gg = 0; gg < RP_PER_THREAD; gg += RP_GROUP) {
+                unsigned long long key[RP_GROUP], cur[RP_GROUP], cur1[RP_GROUP];
+                unsigned cnt[RP_GROUP];
+                Probe pr[RP_GROUP];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RP_GROUP; u++) {
                     if (FOLD) {
                         const unsigned sidx = (gg + u) * RP_THREADS + tid;
                         key[u] = f_key[sidx];
@@ -617,7 +624,7 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
                 // the first TWO slots of the home bucket in one 256-bit load: buckets fill front to back, so most keys
                 // that are not in slot 0 are in slot 1 and need no second (dependent) round trip to L2
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < RP_GROUP; u++)
                     if (key[u] != 0ull) {
                         if (probe_home(t.g, key[u], pr[u])) {
                             unsigned long long w0, w1;
@@ -625,7 +632,7 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
                         } else { key[u] = 0ull; atomicExch(t.error, 2); }
                     }
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < RP_GROUP; u++)
                     if (key[u] != 0ull) {
                         if (cur[u] != key[u] && cur[u] != 0ull) {      // slot 0 holds another key: go on from slot 1
                             probe_next(t.g, pr[u]);
