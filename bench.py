@@ -279,6 +279,49 @@ def cpu_reference_run(sample_recs, read_len, nreads, threads=6):
     return positions / dt, dt, "port", 1
 
 
+def _stats_cols(out_bytes):
+    """what downstream reads of a stats file: columns acc / median / mean / stdev, sorted"""
+    rows = [l.split(b"\t")[:4] for l in out_bytes.split(b"\n") if l and not l.startswith(b"acc\t")]
+    return sorted(rows)
+
+
+def cli_end_to_end(sample_recs, read_len, n_small, n_large):
+    """The drop-in executable, whole process, file in / file out (SURVEY §8d "end-to-end rate"): (1) on the CPU-baseline
+    sample our tool and the reference tool must print the same statistics (columns 1-4, sorted: the reference's line
+    order and tid depend on its threads); (2) wall clock of our tool on a larger file.  CUDA context creation, FASTA
+    parsing and text formatting are all inside."""
+    ours = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "fastaToKmerCoverageStats")
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "fastaToKmerCoverageStats")
+    if not os.path.exists(ours):
+        return None
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        def run(tool, fa, threads=None):
+            cmd = [tool, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", str(K), "--DS"]
+            if threads:
+                cmd += ["--num_threads", str(threads)]
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+            return r.stdout, time.perf_counter() - t0
+        fa = os.path.join(td, "small.fa")
+        write_sample_fasta(fa, sample_recs, read_len, n_small)
+        mine, t_mine = run(ours, fa)
+        out["sample_reads"] = n_small
+        out["ours_seconds"] = round(t_mine, 3)
+        if os.path.exists(ref_bin):
+            theirs, t_ref = run(ref_bin, fa, 6)
+            out["reference_seconds"] = round(t_ref, 3)
+            out["identical_cols_1_4_sorted"] = _stats_cols(mine) == _stats_cols(theirs)
+        if n_large > n_small:
+            fa2 = os.path.join(td, "large.fa")
+            write_sample_fasta(fa2, sample_recs, read_len, n_large)
+            big, t_big = run(ours, fa2)
+            positions = 2 * n_large * (read_len - K + 1)
+            out["large"] = {"reads": n_large, "seconds": round(t_big, 3), "value": round(positions / t_big, 1), "unit": UNIT,
+                            "fasta_bytes": os.path.getsize(fa2), "output_bytes": len(big)}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -291,6 +334,7 @@ def main():
     ap.add_argument("--ntx", type=int, default=20_000)
     ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cli-reads", type=int, default=4_000_000, help="reads in the file the drop-in executable is timed on")
     ap.add_argument("--no-gups", action="store_true")
     ap.add_argument("--no-r2t", action="store_true", help="skip the ReadsToTranscripts measurement")
     ap.add_argument("--count-mode", default="auto", choices=["auto", "direct", "log"])
@@ -565,6 +609,10 @@ def main():
                "sample": f"first {ns} reads of the same synthetic set: fastaToKmerCoverageStats --kmers_from_reads + "
                          f"stats, --num_threads {cores} (the tool's own cap), host has {os.cpu_count()} cores"}
 
+    cli = None
+    if not args.no_cpu_baseline and world == 1:
+        cli = cli_end_to_end(recs_host, read_len, min(args.cpu_sample_reads, nreads), min(args.cli_reads, nreads))
+
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u64 keys / u32 counts / f32 stats", "data": "synthetic", "config": config, "clocks": clocks,
@@ -575,6 +623,8 @@ def main():
                      "load": round(tinfo["distinct"] / tinfo["capacity"], 3),
                      "stats_table_slots": qinfo["capacity"], "stats_table_kmers": qinfo["distinct"]},
            "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
+    if cli is not None:
+        out["cli_end_to_end"] = cli
     if phases is not None:
         out["multi_gpu"] = {"exchange": sc.exchange, "phases_ms_synced": phases, "partitions": sc.nparts, "partitions_per_rank": sc.lp,
                             "exchange_bins": sc.cbins, "replay_fold": sc.replay_fold}

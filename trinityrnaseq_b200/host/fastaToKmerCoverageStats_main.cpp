@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <map>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,7 @@
 using namespace tgio;
 
 static const int MAX_THREADS = 6;   // kept only for the usage text / CLI compatibility
+static const unsigned FORMAT_THREADS = 8;
 
 // Inchworm ArgProcessor (Inchworm/src/argProcessor.cpp:5-23): every token starting with '-' is a flag and the
 // following token, whatever it is, is recorded as its value.
@@ -168,10 +170,9 @@ int main(int argc, char** argv) {
             rb.clear();
         };
         while (true) {
-            seq.clear();
-            if (!rd.next(&h, &hl, seq)) break;
-            if (seq.size() < (size_t)K + 1) continue;
-            rb.recs.insert(rb.recs.end(), seq.begin(), seq.end());
+            const size_t before = rb.recs.size();
+            if (!rd.next(&h, &hl, rb.recs)) break;          // the cleaned sequence lands in the batch directly
+            if (rb.recs.size() - before < (size_t)K + 1) { rb.recs.resize(before); continue; }
             rb.end_record();
             if (rb.recs.size() > (256u << 20)) flush();
         }
@@ -197,37 +198,55 @@ int main(int argc, char** argv) {
         if (capture) per_kmer.assign(rb.recs.size(), 0);
         TGC(tg_cov_stats(table, rb.recs.data(), rb.offs.data(), n, is_DS, median.data(), mean.data(), stdev.data(),
                          capture ? per_kmer.data() : nullptr));
-        char num[64];
-        for (size_t i = 0; i < n; i++) {
+        for (size_t i = 0; i < n; i++)
             if (rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
                 fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)rb.seq_len(i), rb.seq(i), K);
-            out.put(rb.name(i), rb.name_len(i));
-            out.putc('\t'); out.put_uint(median[i]);
-            out.putc('\t'); out.put(num, (size_t)fmt_float(num, mean[i]));
-            out.putc('\t'); out.put(num, (size_t)fmt_float(num, stdev[i]));
-            out.put("\tthread:0", 9);
-            if (capture) {
-                out.putc('\t');
-                const size_t L = rb.seq_len(i);
-                const size_t nw = L >= (size_t)K ? L - K + 1 : 0;
-                for (size_t j = 0; j < nw; j++) {
-                    out.put_uint(per_kmer[rb.offs[i] + j]);
-                    if (j != nw - 1) out.putc(',');
+        // the lines are formatted by a few threads, each into its own buffer, and written in read order: two %g
+        // conversions per read are the most expensive thing left on the host once the statistics come from the GPU
+        auto format_range = [&](size_t a, size_t b, std::vector<char>& buf, bool* neg) {
+            char num[64];
+            auto put = [&](const char* p, size_t m) { buf.insert(buf.end(), p, p + m); };
+            auto put_uint = [&](uint32_t v) { char t[12]; int m = 0; do { t[m++] = (char)('0' + v % 10); v /= 10; } while (v); while (m) buf.push_back(t[--m]); };
+            for (size_t i = a; i < b; i++) {
+                put(rb.name(i), rb.name_len(i));
+                buf.push_back('\t'); put_uint(median[i]);
+                buf.push_back('\t'); put(num, (size_t)fmt_float(num, mean[i]));
+                buf.push_back('\t'); put(num, (size_t)fmt_float(num, stdev[i]));
+                put("\tthread:0", 9);
+                if (capture) {
+                    buf.push_back('\t');
+                    const size_t L = rb.seq_len(i);
+                    const size_t nw = L >= (size_t)K ? L - K + 1 : 0;
+                    for (size_t j = 0; j < nw; j++) {
+                        put_uint(per_kmer[rb.offs[i] + j]);
+                        if (j != nw - 1) buf.push_back(',');
+                    }
                 }
+                buf.push_back('\n');
+                if (mean[i] < 0) *neg = true;
             }
-            out.putc('\n');
-            if (mean[i] < 0) negative = true;
+        };
+        const size_t nthreads = n < 4096 ? 1 : (size_t)std::min<unsigned>(FORMAT_THREADS, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::vector<char>> bufs(nthreads);
+        std::vector<char> negs(nthreads, 0);
+        std::vector<std::thread> workers;
+        for (size_t w = 1; w < nthreads; w++)
+            workers.emplace_back([&, w] { bool ng = false; format_range(n * w / nthreads, n * (w + 1) / nthreads, bufs[w], &ng); negs[w] = ng; });
+        { bool ng = false; format_range(0, n / nthreads, bufs[0], &ng); negs[0] = ng; }
+        for (auto& th : workers) th.join();
+        for (size_t w = 0; w < nthreads; w++) {
+            out.put(bufs[w].data(), bufs[w].size());
+            if (negs[w]) negative = true;
         }
         rb.clear();
     };
     const char* h; size_t hl;
     while (true) {
-        seq.clear();
-        if (!rd.next(&h, &hl, seq)) break;
-        if (seq.empty()) continue;                                       // :132-133
+        const size_t before = rb.recs.size();
+        if (!rd.next(&h, &hl, rb.recs)) break;                           // the cleaned sequence lands in the batch directly
+        if (rb.recs.size() == before) continue;                          // :132-133
         const char* acc; size_t al;
         accession_of(h, hl, &acc, &al);
-        rb.recs.insert(rb.recs.end(), seq.begin(), seq.end());
         rb.end_record();
         rb.add_name(acc, al);
         if (rb.recs.size() > (256u << 20)) flush();

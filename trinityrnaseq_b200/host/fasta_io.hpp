@@ -110,16 +110,21 @@ public:
     size_t consumed(const char* base) const { return (size_t)(p_ - base); }
 private:
     static void append_clean(const char* a, const char* b, std::vector<char>& out) {
-        size_t o = out.size();
-        out.resize(o + (size_t)(b - a));
+        const size_t o = out.size(), n = (size_t)(b - a);
+        out.resize(o + n);
         char* w = out.data() + o;
-        for (const char* q = a; q < b; q++) {
-            char c = *q;
-            if (c == ' ' || c == '\t') continue;
-            if (c >= 'a' && c <= 'z') c = (char)(c - 32);
-            *w++ = c;
+        // branch-free upper-casing copy (vectorises); blanks are counted and squeezed out only if there were any
+        size_t blanks = 0;
+        for (size_t i = 0; i < n; i++) {
+            const unsigned char c = (unsigned char)a[i];
+            blanks += (size_t)((c == ' ') | (c == '\t'));
+            w[i] = (char)(c - (((unsigned char)(c - 'a') < 26) << 5));
         }
-        out.resize((size_t)(w - out.data()));
+        if (blanks) {
+            char* d = w;
+            for (size_t i = 0; i < n; i++) if (w[i] != ' ' && w[i] != '\t') *d++ = w[i];
+            out.resize((size_t)(d - out.data()));
+        }
     }
     const char* p_;
     const char* end_;
