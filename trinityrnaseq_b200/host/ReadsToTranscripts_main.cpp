@@ -156,7 +156,6 @@ int main(int argc, char** argv) {
 
     unsigned long read_count = 0, total_reads_read = 0;
     RecordBatch rb;
-    std::vector<char> seq;
     std::vector<int32_t> best, pct;
     std::vector<uint32_t> order, bucket_start;
     std::string nm;
@@ -170,9 +169,7 @@ int main(int argc, char** argv) {
         long got = 0;
         const char* name; size_t name_len;
         while (got < max_mem_reads) {
-            seq.clear();
-            if (!rd.next(&name, &name_len, seq)) { more = false; break; }
-            rb.recs.insert(rb.recs.end(), seq.begin(), seq.end());
+            if (!rd.next(&name, &name_len, rb.recs)) { more = false; break; }   // sequence lands in the batch directly
             rb.end_record();
             rb.add_name(name, name_len);
             got++;
