@@ -48,8 +48,11 @@ uint64_t tg_launch_count(tg_ctx* ctx);
 
 /* tuning knobs (also read from the environment at tg_init: TG_COUNT_MODE, TG_BATCH_MB, TG_PART_MB, TG_LOG_GB,
  * TG_REPLAY_PREFETCH): key = count_mode (auto|direct|log), batch_mb, batch_bytes, part_mb, part_bytes, log_gb,
- * log_bytes, replay_prefetch (0|1), replay_groups, hot_keys (size of the L2-resident hot-k-mer table used by the
- * coverage statistics, 0 = off), hot_force (0|1), kernel_timing (0|1).  None of them changes a result. */
+ * log_bytes, replay_prefetch (0|1), replay_groups, replay_fold (0|1: fold a replay chunk's duplicate k-mers in shared
+ * memory before the table; pays when several GPUs send their copies of the same k-mers to one owner), long_scratch_mb
+ * (scratch budget of the device-resident entry points for reads beyond the warp path), hot_keys (size of the
+ * L2-resident hot-k-mer table used by the coverage statistics, 0 = off), hot_force (0|1), kernel_timing (0|1).
+ * None of them changes a result. */
 int tg_ctx_set(tg_ctx* ctx, const char* key, const char* value);
 /* With tg_ctx_set(ctx, "kernel_timing", "1") every kernel launch is bracketed by CUDA events on its stream;
  * tg_kernel_times syncs, writes one line "kernel-name \t total ms \t launches" per kernel into out, and resets. */
@@ -67,9 +70,10 @@ int tg_table_create(tg_ctx* ctx, int kind, int k, uint64_t expected_keys, tg_tab
 void tg_table_destroy(tg_table* t);
 int tg_table_reserve(tg_table* t, uint64_t additional_keys);
 int tg_table_info(tg_table* t, uint64_t* capacity_slots, uint64_t* distinct_keys);
-int tg_table_clear(tg_table* t);
+int tg_table_clear(tg_table* t);     /* stream-ordered (see the device-resident section): no host synchronisation */
 /* Geometry.  A table is `nparts` partitions of `slots_per_partition` slots; a k-mer lives in the partition its hash
- * selects.  tg_table_create picks nparts so that one partition fits in L2.  A SHARD holds the contiguous partition
+ * selects, and probes linearly from the first slot of a 64-byte bucket (4 slots) inside it; slots_per_partition is
+ * rounded up to whole buckets.  tg_table_create picks nparts so that one partition fits in L2.  A SHARD holds the contiguous partition
  * range [part0, part0 + nlocal) of the global geometry -- the unit by which the table is split across GPUs
  * (owner(k-mer) = partition / nlocal; prior art: MPIinchworm's `canonical k-mer % NUM_MPI_NODES`,
  * Inchworm/src/mpi_deprecated/MPIinchworm.cpp:1236-1257).  The concatenation of all shards' slot arrays, in rank
@@ -134,7 +138,13 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
  * (Chrysalis/analysis/sequenceUtil.cc:326-355); host-side, evaluated with the reference's fp32 expression. */
 void tg_entropy_table(int k, float min_entropy, uint8_t* entropy_ok /* 26*26*26 */);
 
-/* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ---------------------- */
+/* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ----------------------
+ * These calls (and tg_table_clear) are STREAM-ORDERED and never synchronise with the host: they return once the work is
+ * queued, results and error flags are valid after tg_sync (or any host-buffer call on the same table).  A caller can
+ * therefore queue clear -> count -> statistics for several batches back to back; a stalled host thread then never
+ * idles the GPU.  Reads with more than 256 windows are handled by a second kernel that is launched unconditionally and
+ * sizes itself from device memory; a read too long for its scratch budget (tg_ctx_set "long_scratch_mb", default 64)
+ * is reported by tg_sync -- the host-buffer entry points have no such limit. */
 int tg_dev_alloc(tg_ctx* ctx, uint64_t bytes, void** dptr);
 int tg_dev_records_alloc(tg_ctx* ctx, uint64_t nbytes, void** dptr); /* padded + '\n'-filled for the tile kernels */
 int tg_dev_free(tg_ctx* ctx, void* dptr);
@@ -145,9 +155,10 @@ int tg_memset_dev(tg_ctx* ctx, void* dst, int value, uint64_t bytes);
 int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int canonical);
 /* Sharded counting, the two halves around the exchange (hash-sharded table across GPUs):
  *   tg_count_partition_dev  every k-mer occurrence of the record buffer appended to bin part(k-mer) of a
- *       caller-owned log: d_keys [nbins][cap] u64, d_cursor [nbins] u32 (zeroed by the caller).  nbins must equal
- *       the table's global partition count, so bins [r*nlocal, (r+1)*nlocal) are exactly what rank r owns and
- *       one equal-split all-to-all of d_keys / d_cursor routes every k-mer to its owner.  A bin overflow is
+ *       caller-owned log: d_keys [nbins][cap] u64, d_cursor [nbins] u32 (zeroed by the caller).  nbins is the
+ *       table's global partition count or a divisor of it that is a multiple of the rank count (coarse bins, see
+ *       tg_log_refine_dev), so bins [r*nbins/ranks, (r+1)*nbins/ranks) are exactly what rank r owns and one
+ *       equal-split all-to-all of d_keys / d_cursor routes every k-mer to its owner.  A bin overflow is
  *       reported by the next tg_sync.  Homopolymer windows (poly-A tails...) bypass the log: d_hpoly is 8 u64,
  *       zeroed by the caller -- [0..3] table keys of A^k, C^k, G^k, T^k, [4..7] their occurrence counts; sum the
  *       counts (and max the keys) over ranks before the replay.
