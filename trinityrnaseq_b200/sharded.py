@@ -6,20 +6,25 @@ the plumbing, libtrinity_gpu for every k-mer.
          [r*lp, (r+1)*lp) (tg_table_create_sharded).  Prior art for owner = f(canonical k-mer) mod n:
          Inchworm/src/mpi_deprecated/MPIinchworm.cpp:1236-1257 -- there one blocking MPI_Send per k-mer (:519-531).
 
-  count     phase 1 on every rank appends each k-mer occurrence to the log bin of its partition (bins
-            [d*lp, (d+1)*lp) are rank d's); phase 2 replays the received bins into the shard
-            (tg_table_replay_log_dev).  Between them the bins must reach their owners:
+  count     phase 1 on every rank appends each k-mer occurrence to the log bin of its partition; phase 2 replays the
+            received bins into the shard (tg_table_replay_log_dev).  The k-mers travel in COARSE bins -- `cbins =
+            world * c` of them (c = exchange_bins(): 128 in total by default), rank d owning bins [d*c, (d+1)*c) --
+            because phase 1 and the NVLink stores are only fast with long runs per bin; the owner then splits each
+            coarse bin into its lp / c table partitions (tg_log_refine_dev) and, from FOLD_FROM_WORLD GPUs on, folds a
+            chunk's duplicate k-mers in shared memory before touching the table.  Between phase 1 and the owner the
+            bins must travel:
               exchange="peer"        (default on GPUs) phase 1 IS the exchange: the kernel stores every entry straight
                                      into segment [rank] of the OWNER's receive log through peer memory (CUDA IPC,
                                      NVLink P2P stores; tg_count_partition_peers_dev), so the transfer overlaps the
-                                     rolling of the next tile and there is no send buffer; only the [lp] cursor rows
+                                     rolling of the next tile and there is no send buffer; only the [c] cursor rows
                                      are exchanged afterwards (a few KB, and the "all stores have landed" point);
               exchange="collective"  phase 1 fills a local send log (tg_count_partition_dev) and ONE equal-split
                                      all-to-all moves the bins (NCCL over NVLink) -- the fallback when peer memory
                                      cannot be mapped, and what the CPU test-suite runs over gloo.
   queries   the shards are all-gathered once into a full replica per GPU (`replicate`), because the
             concatenation of the shards' slot arrays IS the full table; coverage statistics / lookups then run
-            locally with no per-batch communication (SURVEY §8e "all-gather once" branch).
+            locally with no per-batch communication (SURVEY §8e "all-gather once" branch).  min_count = 2 gathers the
+            device-side `jellyfish dump -L 2` of every shard instead (a quarter of the bytes, identical statistics).
 
 The exchange logic is independent of where the k-mers are computed: `ShardedKmerCounter` drives an *engine*.  The
 product engine is `DeviceEngine` (CUDA).  The CPU test-suite drives the same class over gloo with a stand-in
