@@ -102,3 +102,41 @@ def test_sidecar_content_hash_cpp(tmp_path):
     subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), src], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_host_fasta_readers_cpp_match_the_oracle_restatements(tmp_path):
+    """The C++ readers the executables use (host/fasta_io.hpp) against the oracle's restatements of the reference's three
+    readers, on the edge cases the survey probed (blank lines, blanks and lower case inside sequences, headers with
+    tabs/spaces, '>' right after a header, unterminated last lines, CRLF-free multi-line records) and on a seeded random
+    soup of such lines -- compiled and run on the CPU."""
+    import subprocess
+    exe = tmp_path / "readers_dump"
+    src = os.path.join(ROOT, "tests", "cpp", "readers_dump.cpp")
+    inc = os.path.join(ROOT, "trinityrnaseq_b200", "host")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), src], check=True)
+
+    def dump(mode, data):
+        f = tmp_path / "in.fa"
+        f.write_bytes(data)
+        r = subprocess.run([str(exe), mode, str(f)], capture_output=True, check=True)
+        return [tuple(line.split(b"\x01")) for line in r.stdout.split(b"\n") if line]
+
+    rng = np.random.default_rng(5)
+    pieces = [b">r1 x\ty", b">r2", b">", b"> lead", b"ACGT", b"acgtn", b"AC GT", b"A\tC", b"", b" ", b">s_7 1 2", b"NNNN",
+              b"ACGTXACGT", b"acgtxacgt tail", b"junk"]
+    cases = [b"junk before\n>a b\tc\nAC GT\nac\tgt\n\n>b\n>c\nNNNN\n>d\nACGT",
+             b">x\nACGT\nAC", b"", b"\n\n", b">only", b">only\n", b">a\nAC\n>b\nGT\n",
+             b">s_12 43 57\nacgtXacgt\n>s_13 1\nAC\nGT\n>s_14 2\nTTTT"]
+    for _ in range(60):
+        n = int(rng.integers(1, 12))
+        body = b"\n".join(pieces[int(i)] for i in rng.integers(0, len(pieces), n))
+        cases.append(body + (b"\n" if rng.integers(0, 2) else b""))
+    for data in cases:
+        iw = [(a.encode(), s.encode()) for _, a, s in orc.read_fasta_inchworm(data)]
+        assert dump("inchworm", data) == iw, data
+        ds = orc.read_fasta_dnastream(data)
+        got = dump("dnastream", data)
+        assert [(g[0].split(b"\x02")[0], g[1]) for g in got] == [(n.encode(), s.encode()) for n, s in ds], data
+        assert [g[0].split(b"\x02")[1] for g in got] == [orc.format_read_name(n).encode() for n, _ in ds], data
+        bd = [(n.encode(), s.encode()) for n, s in orc.read_bundles(data)]
+        assert dump("bundles", data) == bd, data
