@@ -140,3 +140,37 @@ def test_host_fasta_readers_cpp_match_the_oracle_restatements(tmp_path):
         assert [g[0].split(b"\x02")[1] for g in got] == [orc.format_read_name(n).encode() for n, _ in ds], data
         bd = [(n.encode(), s.encode()) for n, s in orc.read_bundles(data)]
         assert dump("bundles", data) == bd, data
+
+
+def test_jellyfish_sequence_file_parser_cpp(tmp_path):
+    """host/seq_file.hpp: FASTA records are joined across line breaks (a k-mer may span them), FASTQ records give their
+    second line, CR is dropped, text before the first header is ignored, batches are cut at record boundaries."""
+    import subprocess
+    exe = tmp_path / "seqfile_dump"
+    src = os.path.join(ROOT, "tests", "cpp", "seqfile_dump.cpp")
+    inc = os.path.join(ROOT, "trinityrnaseq_b200", "host")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), src], check=True)
+
+    def parse(data, flush=1 << 30):
+        f = tmp_path / "in.txt"
+        f.write_bytes(data)
+        r = subprocess.run([str(exe), str(f), str(flush)], capture_output=True, check=True)
+        n, _, body = r.stdout.partition(b"\n")
+        return int(n), body
+
+    assert parse(b">a\nACGT\nAC\n>b desc\n\nGG\r\nTT\n>c\n>d\nNN")[1] == b"ACGTAC\nGGTT\n\nNN\n"
+    assert parse(b"junk\nmore junk\n>a\nAC\n")[1] == b"AC\n"
+    assert parse(b"")[1] == b"" and parse(b"\n\n")[1] == b"" and parse(b"no header at all\n")[1] == b""
+    fq = b"@r1 x\nACGTN\n+\nIIIII\n@r2\nGG\r\n+r2\n@@\n@r3\nTTT"
+    assert parse(fq)[1] == b"ACGTN\nGG\nTTT\n"            # a quality line may start with '@': records are 4 lines
+    assert parse(b"\n\n" + fq)[1] == b"ACGTN\nGG\nTTT\n"
+    # batches: many records, tiny threshold -> several flushes, same bytes, each cut after a terminator
+    rng = np.random.default_rng(3)
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), int(rng.integers(0, 90)))) for _ in range(300)]
+    fa = b"".join(b">s%d\n" % i + b"\n".join(s[j:j + 30] for j in range(0, len(s), 30)) + b"\n" for i, s in enumerate(seqs))
+    want = b"".join(s + b"\n" for s in seqs)
+    n1, body1 = parse(fa)
+    n2, body2 = parse(fa, flush=500)
+    assert body1 == want and body2 == want and n1 == 1 and n2 > 5
+    fqs = b"".join(b"@q%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(seqs))
+    assert parse(fqs, flush=500)[1] == want

@@ -209,3 +209,21 @@ def test_dump_sidecar_binary_handoff(tmp_path):
     assert r.returncode == 0 and not (tmp_path / "n.fa.tgk").exists()
     assert run([jf, "dump", "-c", "-o", str(tmp_path / "c.txt"), str(db)]).returncode == 0
     assert not (tmp_path / "c.txt.tgk").exists()
+
+
+def test_jellyfish_count_fastq_equals_fasta(tmp_path):
+    """`jellyfish count` on a 4-line FASTQ counts what it counts on the same sequences as FASTA (Trinity hands it FASTA;
+    FASTQ is what users run it on by hand)."""
+    jf = os.path.join(BIN, "jellyfish")
+    entries = orc.read_fasta_inchworm(gold("reads.fa"))
+    fa, fq = tmp_path / "r.fa", tmp_path / "r.fq"
+    fa.write_text("".join(">%s\n%s\n" % (h, s) for h, _, s in entries))
+    fq.write_text("".join("@%s\n%s\n+\n%s\n" % (h, s, "@" * len(s)) for h, _, s in entries))
+    outs = []
+    for src in (fa, fq):
+        db = tmp_path / (src.name + ".jf")
+        assert run([jf, "count", "-m", "25", "-s", "1000000", "-C", "-o", str(db), str(src)]).returncode == 0
+        d = run([jf, "dump", str(db)])
+        assert d.returncode == 0 and len(d.stdout) > 1000
+        outs.append(d.stdout)
+    assert outs[0] == outs[1]

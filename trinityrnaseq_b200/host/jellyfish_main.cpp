@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fasta_io.hpp"
+#include "seq_file.hpp"
 #include "tg_loader.hpp"
 #include "tg_sidecar.hpp"
 
@@ -95,46 +96,14 @@ void count_file(tg_table* table, const std::string& path, int canonical) {
     FileView fv;
     std::string err;
     if (!fv.open(path, &err)) { fprintf(stderr, "jellyfish: %s\n", err.c_str()); exit(1); }
-    const char* p = fv.data; const char* end = fv.data + fv.size;
     std::vector<char> recs;
     const size_t FLUSH = 256u << 20;
     recs.reserve(FLUSH + (64u << 20));
-    auto flush = [&]() {
+    parse_sequence_file(fv.data, fv.data + fv.size, recs, FLUSH, [&]() {
         if (recs.empty()) return;
         TGC(tg_count_reads(table, recs.data(), recs.size(), canonical));
         recs.clear();
-    };
-    while (p < end && (*p == '\n' || *p == '\r')) p++;
-    const bool fastq = p < end && *p == '@';
-    if (fastq) {
-        while (p < end) {
-            const char* nl = find_nl(p, end); p = nl < end ? nl + 1 : end;          // @name
-            if (p >= end) break;
-            nl = find_nl(p, end);
-            recs.insert(recs.end(), p, nl); recs.push_back('\n');                 // sequence
-            p = nl < end ? nl + 1 : end;
-            nl = find_nl(p, end); p = nl < end ? nl + 1 : end;                    // +
-            nl = find_nl(p, end); p = nl < end ? nl + 1 : end;                    // qualities
-            if (recs.size() > FLUSH) flush();
-        }
-    } else {
-        bool open = false;
-        while (p < end) {
-            const char* nl = find_nl(p, end);
-            if (*p == '>') {
-                if (open) recs.push_back('\n');
-                open = true;
-                if (recs.size() > FLUSH) flush();
-            } else if (open) {
-                const char* e = nl;
-                if (e > p && e[-1] == '\r') e--;
-                recs.insert(recs.end(), p, e);
-            }
-            p = nl < end ? nl + 1 : end;
-        }
-        if (open) recs.push_back('\n');
-    }
-    flush();
+    });
 }
 
 int cmd_count(int argc, char** argv) {
