@@ -227,3 +227,14 @@ def test_jellyfish_count_fastq_equals_fasta(tmp_path):
         assert d.returncode == 0 and len(d.stdout) > 1000
         outs.append(d.stdout)
     assert outs[0] == outs[1]
+
+
+def test_stats_from_real_jellyfish_dump():
+    """fastaToKmerCoverageStats --kmers on REAL jellyfish output (the reference tree's own fixture, see
+    tests/golden/make_golden_real_jf.py) against the unmodified reference tool's output, byte for byte."""
+    exe = os.path.join(BIN, "fastaToKmerCoverageStats")
+    r = run([exe, "--reads", os.path.join(GOLD, "real_jf_reads.fa"), "--kmers", os.path.join(GOLD, "real_jf_dump_head.fa"),
+             "--kmer_size", "25", "--DS"])
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == gold("stats_real_jf.expected")
+    assert b"done parsing 3000 Kmers, 3000 added" in r.stderr

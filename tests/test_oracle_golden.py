@@ -194,3 +194,29 @@ def test_survey_md5_vectors(tmp_path):
         st = oracle_stats_text(both, ds=ds).decode().splitlines()[1:]
         cut = "".join("\t".join(l.split("\t")[:4]) + "\n" for l in st).encode()
         assert sorted_md5(cut, []) == md5
+
+
+def test_real_jellyfish_dump_fixture_pins_format_representative_and_loader():
+    """The one piece of REAL jellyfish output in the reference tree (trinity_ext_sample_data/test_Inchworm/
+    jellyfish.kmers.fa.gz; first 3000 records committed verbatim by tests/golden/make_golden_real_jf.py):
+      * format: `>COUNT\\nKMER\\n`, 25 upper-case bases -- exactly what the J restatement prints;
+      * representative: every k-mer is the lexicographically smaller (A<C<G<T) of itself and its reverse complement --
+        rule (1) of the restatement (SURVEY §8c), on 3000 of 3000 records (chance: 2^-3000);
+      * order: jellyfish's own hash order, NOT sorted -- nothing downstream may rely on ours being sorted;
+      * loader: the oracle restatement of fastaToKmerCoverageStats --kmers reproduces the reference binary's output on
+        reads whose coverage is decided by those counts."""
+    text = gold("real_jf_dump_head.fa")
+    lines = text.split(b"\n")
+    assert lines[-1] == b"" and len(lines) == 6001
+    counts, kmers = lines[0:6000:2], lines[1:6000:2]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for c, km in zip(counts, kmers):
+        assert c[:1] == b">" and c[1:].isdigit() and int(c[1:]) >= 1
+        assert len(km) == 25 and set(km) <= set(b"ACGT")
+        assert km <= km.translate(comp)[::-1]
+    assert kmers != sorted(kmers) and len(set(kmers)) == len(kmers)
+    # the restatement's own dump text of these (k-mer, count) pairs, in this order, is the file
+    ours = b"".join(b">%d\n%s\n" % (int(c[1:]), tg.packed_to_kmer(tg.kmer_to_packed(km.decode()), 25).encode())
+                    for c, km in zip(counts, kmers))
+    assert ours == text
+    assert oracle_stats_text(gold("real_jf_reads.fa"), kmers_text=text) == gold("stats_real_jf.expected")
