@@ -13,7 +13,10 @@
  *     installed here.  orc_jf_* restates its published semantics and is anchored on the
  *     reference's own equivalent counter: orc_jf_count must agree with the Inchworm KmerCounter restatement
  *     (and, through `fastaToKmerCoverageStats --kmers <dump>` vs `--kmers_from_reads`, with the real
- *     reference binary) -- see tests/test_oracle_golden.py::test_dump_feeds_reference_stats.
+ *     reference binary) -- see tests/test_oracle_golden.py::test_dump_feeds_reference_stats.  The one real jellyfish
+ *     dump in the reference tree (trinity_ext_sample_data/test_Inchworm/jellyfish.kmers.fa.gz, head committed under
+ *     tests/golden/) additionally pins the dump format, the printed representative (lexicographic minimum of k-mer
+ *     and reverse complement) and the --kmers loader: ::test_real_jellyfish_dump_fixture_pins_*.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (no -march, like the reference's -O2 build, so fp32
  * expressions are evaluated exactly as in Inchworm/Chrysalis: no FMA, one rounding per operation).
