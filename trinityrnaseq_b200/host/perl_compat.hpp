@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
 
 #include <string>
 #include <vector>
@@ -69,7 +70,18 @@ inline PerlNum classify(const std::string& s) {
     }
     return r;
 }
+inline bool plain_positive(const std::string& s) {       // digits[.digits][e[+-]digits], first char a digit 1-9 or "0." ...
+    if (s.empty() || s[0] < '0' || s[0] > '9') return false;
+    bool nonzero = false;
+    for (char c : s) {
+        if (c >= '1' && c <= '9') nonzero = true;
+        else if (!(c == '0' || c == '.' || c == 'e' || c == 'E' || c == '+' || c == '-')) return false;
+    }
+    return nonzero;
+}
 inline double perl_add(const std::string& a, const std::string& b) {
+    // ordinary positive numbers: integer and floating addition agree (below 2^53) and no zero can result
+    if (a.size() <= 15 && b.size() <= 15 && plain_positive(a) && plain_positive(b)) return strtod(a.c_str(), nullptr) + strtod(b.c_str(), nullptr);
     const PerlNum A = classify(a), B = classify(b);
     if (B.ivable && A.ivable) {
         long long sum;
@@ -142,14 +154,13 @@ public:
     }
 private:
     bool getline(std::string& out) {
-        out.clear();
-        char buf[65536];
-        while (fgets(buf, sizeof buf, f_)) {
-            out += buf;
-            if (!out.empty() && out.back() == '\n') return true;
-        }
-        return !out.empty();
+        const ssize_t n = ::getline(&buf_, &cap_, f_);          // POSIX getline: one pass, reused buffer
+        if (n <= 0) { out.clear(); return false; }
+        out.assign(buf_, (size_t)n);
+        return true;
     }
+    char* buf_ = nullptr;
+    size_t cap_ = 0;
     FILE* f_;
     void (*fatal_)(const std::string&);
 };
