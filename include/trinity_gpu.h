@@ -15,7 +15,7 @@
  *     offs[n] the end of the last terminator; record i has offs[i+1]-offs[i]-1 bases.  Bases are
  *     case-insensitive; any byte other than ACGTacgt is "not a base" and breaks every k-mer window over it.
  *   - "packed k-mer": 2 bits per base, A=0 C=1 G=2 T=3, first base most significant, in the low 2k bits of
- *     a uint64_t (so integer order == lexicographic order).  1 <= k <= 31.
+ *     a uint64_t (so integer order == lexicographic order).  1 <= k <= 31 (the partitioned / sharded count path: 8 <= k).
  *   - host buffers may be pageable; buffers from tg_host_alloc (pinned) are copied at full PCIe speed.
  *   - a tg_ctx owns one device and its streams; calls on one ctx must not overlap in time.
  */
@@ -43,6 +43,11 @@ int tg_init(int device, tg_ctx** ctx);
 void tg_destroy(tg_ctx* ctx);
 int tg_device_info(tg_ctx* ctx, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes);
 int tg_sync(tg_ctx* ctx);
+/* tg_sync for the table-less log appends of the sharded count (tg_count_partition[_peers]_dev, tg_log_refine_dev): a full
+ * bin -- a k-mer or minimizer far hotter than the per-bin head-room allowed for -- is not an error but *overflowed = 1
+ * (flag cleared): entries were dropped, so the caller repeats the batch with a larger per-bin capacity.  Every other
+ * pending error is returned as by tg_sync. */
+int tg_log_overflow_check(tg_ctx* ctx, int* overflowed);
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
 uint64_t tg_launch_count(tg_ctx* ctx);
 
@@ -50,8 +55,7 @@ uint64_t tg_launch_count(tg_ctx* ctx);
  * TG_REPLAY_PREFETCH): key = count_mode (auto|direct|log), batch_mb, batch_bytes, part_mb, part_bytes, log_gb,
  * log_bytes, replay_prefetch (0|1), replay_groups, replay_fold (0|1: fold a replay chunk's duplicate k-mers in shared
  * memory before the table; pays when several GPUs send their copies of the same k-mers to one owner), long_scratch_mb
- * (scratch budget of the device-resident entry points for reads beyond the warp path), hot_keys (size of the
- * L2-resident hot-k-mer table used by the coverage statistics, 0 = off), hot_force (0|1), kernel_timing (0|1).
+ * (scratch budget of the device-resident entry points for reads beyond the warp path), kernel_timing (0|1).
  * None of them changes a result. */
 int tg_ctx_set(tg_ctx* ctx, const char* key, const char* value);
 /* With tg_ctx_set(ctx, "kernel_timing", "1") every kernel launch is bracketed by CUDA events on its stream;
@@ -71,8 +75,10 @@ void tg_table_destroy(tg_table* t);
 int tg_table_reserve(tg_table* t, uint64_t additional_keys);
 int tg_table_info(tg_table* t, uint64_t* capacity_slots, uint64_t* distinct_keys);
 int tg_table_clear(tg_table* t);     /* stream-ordered (see the device-resident section): no host synchronisation */
-/* Geometry.  A table is `nparts` partitions of `slots_per_partition` slots; a k-mer lives in the partition its hash
- * selects, and probes linearly from the first slot of a 64-byte bucket (4 slots) inside it; slots_per_partition is
+/* Geometry.  A table is `nparts` partitions of `slots_per_partition` slots.  A k-mer lives in the partition chosen by the
+ * hash of its MINIMIZER (the smallest-hash (k-7)-mer inside it): its home is slot j of a 128-byte bucket of 8 slots, j = the
+ * minimizer's position in the k-mer, so that the consecutive windows of a read fall into neighbouring slots of one bucket;
+ * a k-mer whose home slot is taken is placed by its own hash inside the same partition.  slots_per_partition is
  * rounded up to whole buckets.  tg_table_create picks nparts so that one partition fits in L2.  A SHARD holds the contiguous partition
  * range [part0, part0 + nlocal) of the global geometry -- the unit by which the table is split across GPUs
  * (owner(k-mer) = partition / nlocal; prior art: MPIinchworm's `canonical k-mer % NUM_MPI_NODES`,
@@ -155,7 +161,7 @@ int tg_memset_dev(tg_ctx* ctx, void* dst, int value, uint64_t bytes);
 int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int canonical);
 /* Sharded counting, the two halves around the exchange (hash-sharded table across GPUs):
  *   tg_count_partition_dev  every k-mer occurrence of the record buffer appended to bin part(k-mer) of a
- *       caller-owned log: d_keys [nbins][cap] u64, d_cursor [nbins] u32 (zeroed by the caller).  nbins is the
+ *       caller-owned log: d_keys [nbins][cap] entries of tg_log_entry_bytes(), d_cursor [nbins] u32 (zeroed by the caller).  nbins is the
  *       table's global partition count or a divisor of it that is a multiple of the rank count (coarse bins, see
  *       tg_log_refine_dev), so bins [r*nbins/ranks, (r+1)*nbins/ranks) are exactly what rank r owns and one
  *       equal-split all-to-all of d_keys / d_cursor routes every k-mer to its owner.  A bin overflow is
@@ -190,6 +196,9 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
 int tg_log_refine_dev(tg_ctx* ctx, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t ncoarse, uint32_t cap,
                       void* d_out_keys, void* d_out_cursor, uint32_t nfine, uint32_t out_cap, uint32_t fine0,
                       uint32_t nfine_global);
+/* bytes of one k-mer log entry (16: the table key and the packed home of the k-mer): every `d_keys` / `d_owner_keys` /
+ * `d_out_keys` log of the sharded-count calls holds bins * cap entries of this size */
+uint32_t tg_log_entry_bytes(void);
 #define TG_IPC_HANDLE_BYTES 64
 int tg_ipc_export(tg_ctx* ctx, void* dptr, uint8_t* handle /* TG_IPC_HANDLE_BYTES */);
 int tg_ipc_open(tg_ctx* ctx, const uint8_t* handle, void** dptr);

@@ -129,15 +129,19 @@ class StandinEngine:
         f = nfine // ncoarse
         rk = rkeys.reshape(nsrc, ncoarse, -1)
         rc = rcur.reshape(nsrc, ncoarse)
+        overflow = False
         for cb in range(ncoarse):
             for s_ in range(nsrc):
                 for e in rk[s_, cb, :int(rc[s_, cb])].tolist():
                     b = key_bin(e - 1, nfine_global) - fine0
                     assert cb * f <= b < (cb + 1) * f, "a coarse bin holds only its own partitions"
                     pos = int(fcur[b])
-                    assert pos < fcap, "stand-in fine log overflow"
+                    if pos >= fcap:                 # like the device: the entry is dropped, the caller repeats with more room
+                        overflow = True
+                        continue
                     fkeys[b, pos] = e
                     fcur[b] += 1
+        return overflow
 
     def new_cursors(self, nbins):
         return (torch.zeros((nbins,), dtype=torch.int32), torch.zeros((nbins,), dtype=torch.int32),
@@ -146,12 +150,13 @@ class StandinEngine:
     def partition_peers(self, recs, nbytes, peers, cursor, hpoly, nbins, cap, rank):
         lp = nbins // peers.world
         scratch = torch.zeros((nbins, cap), dtype=torch.int64)
-        self.partition(recs, nbytes, scratch, cursor, hpoly)
+        overflow = self.partition(recs, nbytes, scratch, cursor, hpoly)
         for b in range(nbins):                      # entry (bin b, pos) -> owner b // lp, segment [rank], bin b % lp
             n = int(cursor[b])
             peers.maps[b // lp][rank, b % lp, :n] = scratch[b, :n].numpy()
         for m in peers.maps:
             m.flush()
+        return overflow
 
     def create_shard(self, subcap, nparts, part0, nlocal):
         self.table = StandinTable(self.k, self.canonical, subcap, nparts, part0, nlocal)
@@ -169,6 +174,7 @@ class StandinEngine:
         nbins, cap = keys.shape
         ok, oc = orc.jf_count(np.asarray(recs[:nbytes]), self.k, self.canonical, 1)
         homo = {0: 0, (1 << (2 * self.k)) - 1: 3}      # A^k and T^k as packed k-mers -> side-channel slot
+        overflow = False
         for key, c in zip(ok.tolist(), oc.tolist()):
             if key in homo:                         # homopolymers travel as (key, count), like on the device
                 hpoly[homo[key]] = -(key + 1)       # negative, like a device key with its tag bit
@@ -177,9 +183,12 @@ class StandinEngine:
             b = key_bin(key, nbins)
             for _ in range(c):                      # one log entry per occurrence, like the device log
                 pos = int(cursor[b])
-                assert pos < cap, "stand-in log bin overflow"
+                if pos >= cap:                      # like the device: dropped, reported, the batch is repeated
+                    overflow = True
+                    break
                 keys[b, pos] = key + 1
                 cursor[b] += 1
+        return overflow
 
     def replay(self, keys, cursor, hpoly, nsrc):
         lp = self.table.nlocal

@@ -174,3 +174,16 @@ def test_jellyfish_sequence_file_parser_cpp(tmp_path):
     assert body1 == want and body2 == want and n1 == 1 and n2 > 5
     fqs = b"".join(b"@q%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(seqs))
     assert parse(fqs, flush=500)[1] == want
+
+
+def test_minimizer_fast_path_equals_slow_path(tmp_path):
+    """trinityrnaseq_b200/csrc/tg_minimizer.cuh is host+device code: the sliding-minimum fast path the kernels use for the
+    windows of a read must give exactly the home (minimizer hash, slot) that the per-key slow path gives -- every k, every
+    strip width, both strands, tie-heavy reads (tests/cpp/test_minimizer.cpp)."""
+    import subprocess
+    exe = tmp_path / "test_minimizer"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "cpp", "test_minimizer.cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "fast == slow" in r.stdout

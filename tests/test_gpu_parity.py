@@ -226,3 +226,29 @@ def _oracle_stats(oracle, recs, offs):
         if len(seq) == 25 and all(ch in b"ACGTacgt" for ch in seq):
             okc.add_kmer(seq.decode().upper(), 1)
     return okc.coverage_stats(recs, offs)
+
+
+@pytest.mark.parametrize("k", [5, 7, 8, 9])
+def test_short_kmers_use_the_slow_homes(gpu_ctx, oracle, k):
+    """k < 8 has fewer than 8 m-mers per k-mer: count and statistics go through the per-key home computation (and the
+    CTA-per-read kernel); k = 8, 9 are the first lengths of the fast paths.  Same answers as the oracle."""
+    rng = np.random.default_rng(k)
+    txs = synth.transcriptome(rng, 5, mean_len=300, min_len=100, max_len=600)
+    reads = synth.reads_from(rng, txs, 400, 60, var_len=True) + [b"A" * 40, b"ACGTN" * 9, b"", b"AC"]
+    recs, offs = tg.records_from_sequences(reads)
+    for canonical in (True, False):
+        ok, oc = oracle.jf_count(recs, k, canonical, 1)
+        with tg.KmerCounter(gpu_ctx, k, is_ds=canonical, expected_keys=len(ok) + 16) as kc:
+            kc.add_records(recs)
+            gk, gc = kc.dump()
+            np.testing.assert_array_equal(gk, ok)
+            np.testing.assert_array_equal(gc, oc)
+            okc = oracle.KmerCounter(k, canonical)
+            for kmer, c in zip(ok, oc):
+                okc.add_kmer(tg.packed_to_kmer(kmer, k), int(c))
+            om, omean, osd, oper = okc.coverage_stats(recs, offs, capture=True)
+            gm, gmean, gsd, gper = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+            np.testing.assert_array_equal(gper, oper)
+            np.testing.assert_array_equal(gm, om)
+            np.testing.assert_array_equal(gmean.view(np.uint32), omean.view(np.uint32))
+            np.testing.assert_array_equal(gsd.view(np.uint32), osd.view(np.uint32))

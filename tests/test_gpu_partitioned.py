@@ -17,6 +17,8 @@ import synthdata as synth
 
 pytestmark = pytest.mark.gpu
 
+LOG_ENTRY = _lib.lib().tg_log_entry_bytes()      # bytes of one k-mer log entry (key + packed home)
+
 
 @pytest.fixture()
 def ctx():
@@ -177,7 +179,7 @@ def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
     for r, (r0, r1) in enumerate(ranges):
         sub = recs[int(offs[r0]):int(offs[r1])]
         d = _dev_records(ctx, sub)
-        keys = ctx.dev_alloc(nparts * cap * 8)
+        keys = ctx.dev_alloc(nparts * cap * LOG_ENTRY)
         cur = ctx.dev_alloc(nparts * 4)
         ctx.memset(cur, 0, nparts * 4)
         shards[r].partition_dev(d, sub.nbytes, nparts, cap, keys, cur, hpoly)
@@ -189,10 +191,10 @@ def test_sharded_count_exchange_emulated(ctx, oracle, data, world):
     hp_host = ctx.d2h(hpoly, 64, np.uint64)
     assert hp_host[4] > 0 and hp_host[7] > 0          # the poly-A and poly-T reads of the fixture
     for dst in range(world):
-        rkeys = ctx.dev_alloc(nparts * cap * 8)       # [world][lp][cap]
+        rkeys = ctx.dev_alloc(nparts * cap * LOG_ENTRY)       # [world][lp][cap]
         rcur = ctx.dev_alloc(nparts * 4)
         for src in range(world):
-            ctx.d2d(rkeys, logs[src], lp * cap * 8, dst_off=src * lp * cap * 8, src_off=dst * lp * cap * 8)
+            ctx.d2d(rkeys, logs[src], lp * cap * LOG_ENTRY, dst_off=src * lp * cap * LOG_ENTRY, src_off=dst * lp * cap * LOG_ENTRY)
             ctx.d2d(rcur, curs[src], lp * 4, dst_off=src * lp * 4, src_off=dst * lp * 4)
         hp_d = ctx.dev_alloc(64)                       # every rank applies its own copy of the global tallies
         ctx.h2d(hp_d, hp_host)
@@ -260,9 +262,9 @@ def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world, fine_per
     fine_nparts, nparts, lp = nparts, world * c, c
     bound = max(int(offs[r1] - offs[r0]) for r0, r1 in ranges)
     cap = tg.sharded.log_capacity(bound, nparts)
-    rlogs = [ctx.dev_alloc(nparts * cap * 8) for _ in range(world)]       # rank r's receive log [world][c][cap]
+    rlogs = [ctx.dev_alloc(nparts * cap * LOG_ENTRY) for _ in range(world)]       # rank r's receive log [world][c][cap]
     for p in rlogs:
-        ctx.memset(p, 0xEE, nparts * cap * 8)                             # stale bytes must never be replayed
+        ctx.memset(p, 0xEE, nparts * cap * LOG_ENTRY)                             # stale bytes must never be replayed
     curs = []
     hpoly = ctx.dev_alloc(64)
     ctx.memset(hpoly, 0, 64)
@@ -286,9 +288,9 @@ def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world, fine_per
             shards[dst].replay_log_dev(rlogs[dst], rcur, hp_d, world, cap)
         else:
             fcap = tg.sharded.log_capacity(world * bound, part_lp, slack=1.3)
-            fkeys = ctx.dev_alloc(part_lp * fcap * 8)
+            fkeys = ctx.dev_alloc(part_lp * fcap * LOG_ENTRY)
             fcur = ctx.dev_alloc(part_lp * 4)
-            ctx.memset(fkeys, 0xEE, part_lp * fcap * 8)
+            ctx.memset(fkeys, 0xEE, part_lp * fcap * LOG_ENTRY)
             ctx.memset(fcur, 0, part_lp * 4)
             _lib.check(_lib.lib().tg_log_refine_dev(ctx._h, rlogs[dst], rcur, world, c, cap, fkeys, fcur, part_lp, fcap,
                                                     dst * part_lp, fine_nparts))
@@ -317,7 +319,7 @@ def test_sharded_count_peer_exchange_emulated(ctx, oracle, data, world, fine_per
         shards[0].partition_peers_dev(rlogs[0], 0, nparts, cap, world, rlogs, cur, hpoly)
     # a coarse log refined by the WRONG owner: every key is foreign, reported at the next sync
     if fine_per_coarse > 1 and world > 1:
-        fkeys = ctx.dev_alloc(part_lp * 64 * 8)
+        fkeys = ctx.dev_alloc(part_lp * 64 * LOG_ENTRY)
         fcur = ctx.dev_alloc(part_lp * 4)
         ctx.memset(fcur, 0, part_lp * 4)
         rcur = ctx.dev_alloc(nparts * 4)
@@ -360,7 +362,7 @@ def test_partition_log_overflow_is_reported(ctx, data):
     recs, offs = tg.records_from_sequences(reads)
     d = _dev_records(ctx, recs)
     nbins, cap = 8, 64                                  # far too small
-    keys = ctx.dev_alloc(nbins * cap * 8)
+    keys = ctx.dev_alloc(nbins * cap * LOG_ENTRY)
     cur = ctx.dev_alloc(nbins * 4)
     hp = ctx.dev_alloc(64)
     ctx.memset(cur, 0, nbins * 4)
@@ -412,40 +414,46 @@ def test_compacted_min2_table_gives_identical_stats(ctx, oracle, data, canonical
             assert q3.size() == int((2 * oc >= 3).sum())
 
 
-@pytest.mark.parametrize("hot_keys", [300, 5000])
-def test_hot_table_lookups_are_exact_and_never_stale(ctx, oracle, data, hot_keys):
-    """the L2-resident hot-k-mer table in front of the count table: same statistics, rebuilt after every change"""
-    _, reads = data
+def test_displaced_keys_are_found(ctx, oracle):
+    """Minimizer placement under pressure: every single-base variant of a few sequences shares minimizers -- and hence home
+    slots -- with the original, so most variant k-mers are DISPLACED into the key-hashed walk of their partition; absent
+    variants land on flagged home slots too.  Counts, dumps and statistics must stay exact, on a table tight enough that
+    walks are long, through the direct and the logged count path."""
+    rng = np.random.default_rng(99)
+    base = [synth.ALPHA[rng.integers(0, 4, 120)].tobytes() for _ in range(6)]
+    reads = []
+    for b in base:
+        for rep in range(3):
+            reads.append(b)
+        for i in range(len(b)):
+            for alt in b"ACGT":
+                if alt != b[i]:
+                    reads.append(b[:i] + bytes([alt]) + b[i + 1:])
+    probes = list(reads)
+    for b in base:                               # absent double variants: looked up, never counted
+        for i in range(0, len(b) - 3, 7):
+            v = bytearray(b)
+            v[i] = ord("A") if v[i] != ord("A") else ord("C")
+            v[i + 3] = ord("G") if v[i + 3] != ord("G") else ord("T")
+            probes.append(bytes(v))
     recs, offs = tg.records_from_sequences(reads)
-    half = len(reads) // 2
-    recs_a, _ = tg.records_from_sequences(reads[:half])
-    recs_b, _ = tg.records_from_sequences(reads[half:])
-    ctx.set("hot_keys", hot_keys)
-    ctx.set("hot_force", 1)
-    with tg.KmerCounter(ctx, 25, is_ds=True) as kc:
-        okc = oracle.KmerCounter(25, True)
-        for part in (recs_a, recs_b):
-            kc.add_records(part)
-            k_, c_ = kc.dump()
-            for kmer, c in zip(k_, c_):
-                pass
-            okc = oracle.KmerCounter(25, True)
-            for kmer, c in zip(k_, c_):
-                okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
-            om, omean, osd, oper = okc.coverage_stats(recs, offs, capture=True)
-            for _ in range(2):                         # second call re-uses the hot table built by the first
-                gm, gmean, gsd, gper = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+    precs, poffs = tg.records_from_sequences(probes)
+    for mode in ("direct", "log"):
+        for canonical in (True, False):
+            ok, oc = oracle.jf_count(recs, 25, canonical, 1)
+            ctx.set("count_mode", mode)
+            ctx.set("part_bytes", 64 << 10)
+            with tg.KmerCounter(ctx, 25, is_ds=canonical, expected_keys=int(len(ok) * 0.7)) as kc:     # load ~0.65
+                kc.add_records(recs)
+                gk, gc = kc.dump()
+                np.testing.assert_array_equal(gk, ok)
+                np.testing.assert_array_equal(gc, oc)
+                okc = oracle.KmerCounter(25, canonical)
+                for kmer, c in zip(ok, oc):
+                    okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
+                om, omean, osd, oper = okc.coverage_stats(precs, poffs, capture=True)
+                gm, gmean, gsd, gper = kc.coverage_stats(precs, poffs, capture_coverage_info=True)
                 np.testing.assert_array_equal(gper, oper)
                 np.testing.assert_array_equal(gm, om)
                 np.testing.assert_array_equal(gsd.view(np.uint32), osd.view(np.uint32))
-            d = _dev_records(ctx, recs)
-            d_offs = ctx.dev_alloc(offs.nbytes)
-            ctx.h2d(d_offs, offs)
-            n = len(offs) - 1
-            d1, d2, d3 = ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n)
-            kc.coverage_stats_dev(d, d_offs, n, d1, d2, d3)
-            ctx.sync()
-            np.testing.assert_array_equal(ctx.d2h(d1, 4 * n, np.uint32), om)
-            np.testing.assert_array_equal(ctx.d2h(d3, 4 * n, np.uint32), osd.view(np.uint32))
-            for p in (d, d_offs, d1, d2, d3):
-                ctx.dev_free(p)
+    ctx.set("count_mode", "auto")

@@ -114,6 +114,54 @@ def test_sharded_counter_over_gloo(world, exchange, coarse, tmp_path):
     np.testing.assert_array_equal(cs[order], oc)
 
 
+def _skew_worker(rank, world, port, out_dir):
+    """one k-mer carried by a large share of the reads: its log bin overflows the even-spread head-room, the ranks agree,
+    double the head-room and repeat the batch (the sharded path used to abort here)"""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import oracle_py as orc
+    import standin_engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        k = 25
+        rng = np.random.default_rng(5)
+        txs = synth.transcriptome(rng, 6, mean_len=400, min_len=150, max_len=800)
+        hot = b"AGATCGGAAGAGCACACGTCTGAAC"                       # exactly one 25-mer
+        # a few thousand spread-out windows plus 8000 copies of one k-mer: with the exact window count as the bound a bin
+        # has room for ~1500 entries, the hot k-mer alone brings 4000 per rank
+        reads = synth.reads_from(rng, txs, 120, 60, var_len=True) + [hot] * 8000
+        recs, offs = records_from_sequences(reads)
+        ok, oc = orc.jf_count(recs, k, True, 1)
+        assert oc.max() >= 3000
+        r0, r1 = sharded.record_range(offs, rank, world)
+        mine = recs[int(offs[r0]):int(offs[r1])]
+        eng = standin_engine.StandinEngine(k, True, peer_dir=out_dir)
+        sc = sharded.ShardedKmerCounter(eng, expected_keys_per_rank=len(ok) // world + 64, part_bytes=2 << 10, max_exchange_bins=32)
+        assert sc.lp > sc.c                               # coarse exchange bins + owner-side refine: both can overflow
+        nwin = sum(max(0, len(r) - k + 1) for r in reads[r0:r1])
+        sc.add_records_dev(torch.from_numpy(mine.copy()), len(mine), max_windows=nwin)
+        assert sc.overflow_retries >= 1 and sc._grow >= 2
+        assert sc.size() == len(ok)
+        np.testing.assert_array_equal(sc.histo(), orc.jf_histo(oc))
+        retries = sc.overflow_retries
+        sc.add_records_dev(torch.from_numpy(mine.copy()), len(mine), max_windows=nwin)       # the head-room is remembered
+        assert sc.overflow_retries == retries
+        fk, fc = sc.replicate().dump()
+        np.testing.assert_array_equal(fk, ok)
+        np.testing.assert_array_equal(fc, 2 * oc)
+        sc.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_counter_survives_a_hot_kmer(tmp_path):
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_skew_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
 def test_record_range_partitions_every_record_once():
     rng = np.random.default_rng(1)
     lens = rng.integers(0, 200, 1000)

@@ -25,6 +25,7 @@ SIGNATURES = {
     "tg_destroy": (None, [_vp]),
     "tg_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_u64), C.POINTER(_u64)]),
     "tg_sync": (_i32, [_vp]),
+    "tg_log_overflow_check": (_i32, [_vp, C.POINTER(_i32)]),
     "tg_launch_count": (_u64, [_vp]),
     "tg_ctx_set": (_i32, [_vp, _cp, _cp]),
     "tg_kernel_times": (_i32, [_vp, _vp, _u64]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "tg_count_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp, _vp]),
     "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "tg_log_refine_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32]),
+    "tg_log_entry_bytes": (_u32, []),
     "tg_ipc_export": (_i32, [_vp, _vp, _vp]),
     "tg_ipc_open": (_i32, [_vp, _vp, _pp]),
     "tg_ipc_close": (_i32, [_vp, _vp]),

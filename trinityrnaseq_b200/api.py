@@ -90,6 +90,12 @@ class Context:
     def sync(self):
         check(_lib.lib().tg_sync(self._h))
 
+    def log_overflow_check(self):
+        """sync; True when a table-less log append overflowed a bin since the last check (flag cleared)"""
+        f = C.c_int(0)
+        check(_lib.lib().tg_log_overflow_check(self._h, C.byref(f)))
+        return bool(f.value)
+
     def launch_count(self):
         return int(_lib.lib().tg_launch_count(self._h))
 

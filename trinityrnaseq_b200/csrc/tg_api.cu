@@ -77,7 +77,7 @@ struct tg_ctx {
     unsigned int* h_long_hdr = nullptr;                 // pinned, 2 x 2
     int* d_error = nullptr;                             // raised by table-less log appends (tg_count_partition_dev)
     size_t part_bytes = 16ull << 20;                    // target bytes of one table partition (L2-resident unit)
-    size_t log_max_bytes = 24ull << 30;                 // most HBM the k-mer log of one table may take
+    size_t log_max_bytes = 48ull << 30;                 // most HBM the k-mer log of one table may take
     KernelTimer timer;                                  // optional per-kernel event timing
     int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
     int replay_prefetch = 1;
@@ -85,23 +85,18 @@ struct tg_ctx {
                                                         // (pays when many GPUs send their copies of the same hot k-mers to
                                                         // one owner; costs ~12 ms per 1.5 G entries otherwise)
     unsigned replay_groups = 8;                         // bins replayed concurrently (see k_log_replay)
-    uint64_t hot_max_keys = 0;                          // size of the L2-resident hot cache; 0 = off (the default: measured
-                                                        // no gain once the median stopped being a sort, profiles/README.md)
-    bool hot_force = false;                             // tests: build it whatever the table size / coverage
-    unsigned hot_hints = 0;                             // L2 eviction hints used with the hot table (see Geo)
-    double hot_load = 0.6;
 };
 
 // k-mer log of a count table (partitioned count path)
 struct KeyLog {
-    unsigned long long* keys = nullptr;
+    LogEntry* keys = nullptr;                  // [nbins][cap] 16-B entries (key + packed home)
     unsigned int* cursor = nullptr;
     unsigned long long* chunk_start = nullptr;
     unsigned long long* hpoly = nullptr;   // [8] homopolymer side channel (keys, counts)
     unsigned nbins = 0, cap = 0;
     // tables with more partitions than LOG_BASE_BINS: phase 1 fills `nbins` COARSE bins (long runs per tile) and the
     // replay first splits them into one segment per partition (k_log_refine)
-    unsigned long long* fine_keys = nullptr;
+    LogEntry* fine_keys = nullptr;
     unsigned int* fine_cursor = nullptr;
     unsigned fine_bins = 0, fine_cap = 0, plan_bins = 0;
     uint64_t pending_ub = 0;          // host-side upper bound on entries appended since the last replay
@@ -113,17 +108,12 @@ struct tg_table {
     int kind = TG_TABLE_COUNT;
     int k = 25;
     Slot* slots = nullptr;
-    Geo g{0, 1, 0, 1};
+    Geo g{0, 1, 0, 1, 25};
     uint64_t cap = 0;                          // slots held here = g.nlocal * g.subcap
     unsigned long long* d_claimed = nullptr;   // [0] = distinct keys
     int* d_error = nullptr;
     uint64_t distinct_ub = 0;   // host-side upper bound on distinct keys (refreshed from the device at syncs)
     KeyLog log;
-    Slot* hot = nullptr;        // hot table storage (g.hot_slots points here while it is valid)
-    uint64_t hot_cap = 0;
-    uint64_t hot_keys = 0;
-    uint32_t hot_min = 0;
-    bool hot_tried = false;     // a build was attempted for the current table content
     bool sharded() const { return g.nlocal != g.nparts; }
     TableView view() const { return TableView{slots, g, d_claimed, d_error}; }
 };
@@ -144,6 +134,7 @@ static Geo pick_geo(uint64_t slots, size_t part_bytes) {
     Geo g;
     g.nparts = (unsigned)np; g.part0 = 0; g.nlocal = (unsigned)np;
     g.subcap = whole_buckets((slots + np - 1) / np);
+    g.k = 0;            // set by table_new / table_regrow
     return g;
 }
 
@@ -157,15 +148,6 @@ static int sync_all(tg_ctx* c) {
     CU(cudaStreamSynchronize(c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[1]));
     return TG_OK;
-}
-
-// the table content is about to change (or has changed behind our back): the hot copy is stale
-static void hot_invalidate(tg_table* t) {
-    t->g.hot_slots = nullptr;
-    t->g.hot_subcap = 0;
-    t->g.hot_hints = 0;
-    t->hot_keys = 0;
-    t->hot_tried = false;
 }
 
 static int table_refresh(tg_table* t) {   // after a sync: read back distinct count and the error flag
@@ -192,7 +174,8 @@ static int table_alloc(tg_ctx* c, uint64_t slots, Slot** out) {
 
 extern "C" {
 
-int tg_version(void) { return 100; }
+int tg_version(void) { return 200; }
+uint32_t tg_log_entry_bytes(void) { return (uint32_t)sizeof(LogEntry); }
 const char* tg_last_error(void) { return g_err.c_str(); }
 
 int tg_device_count(void) {
@@ -303,6 +286,22 @@ int tg_sync(tg_ctx* c) {
     return TG_OK;
 }
 
+int tg_log_overflow_check(tg_ctx* c, int* overflowed) {
+    if (!c || !overflowed) return fail(TG_ERR_ARG, "tg_log_overflow_check: null argument");
+    *overflowed = 0;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    int err = 0;
+    CU(cudaMemcpy(&err, c->d_error, sizeof err, cudaMemcpyDeviceToHost));
+    if (err == 3) {                      // a bin was full: the caller lays the log out again and repeats the batch
+        CU(cudaMemset(c->d_error, 0, sizeof(int)));
+        *overflowed = 1;
+        return TG_OK;
+    }
+    return tg_sync(c);                   // anything else is reported (and cleared) the usual way
+}
+
 uint64_t tg_launch_count(tg_ctx* c) { return c ? c->launches : 0; }
 
 int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
@@ -341,16 +340,6 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
     } else if (!strcmp(key, "replay_groups")) {
         if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
         c->replay_groups = (unsigned)v;
-    } else if (!strcmp(key, "hot_keys")) {
-        if (v < 0 || v > (64 << 20)) return fail(TG_ERR_ARG, "hot_keys out of range (0..64M)");
-        c->hot_max_keys = (uint64_t)v;
-    } else if (!strcmp(key, "hot_hints")) {
-        c->hot_hints = (unsigned)v & 3u;
-    } else if (!strcmp(key, "hot_load_pct")) {
-        if (v < 10 || v > 90) return fail(TG_ERR_ARG, "hot_load_pct out of range");
-        c->hot_load = v / 100.0;
-    } else if (!strcmp(key, "hot_force")) {
-        c->hot_force = v != 0;
     } else if (!strcmp(key, "kernel_timing")) {
         c->timer.on = v != 0;
     } else {
@@ -376,6 +365,7 @@ void tg_free(void* p) { free(p); }
 // ---------------------------------------------------------------------------------------------------------
 static int table_new(tg_ctx* c, int kind, int k, Geo g, tg_table** out) {
     tg_table* t = new tg_table();
+    g.k = k;
     t->ctx = c; t->kind = kind; t->k = k; t->g = g;
     t->cap = (uint64_t)g.nlocal * g.subcap;
     int rc = table_alloc(c, t->cap, &t->slots);
@@ -409,7 +399,7 @@ int tg_table_create_sharded(tg_ctx* c, int kind, int k, uint64_t slots_per_parti
                     nparts, part0, nlocal, (unsigned long long)slots_per_partition);
     if (bind(c)) return TG_ERR_CUDA;
     Geo g;
-    g.subcap = whole_buckets(slots_per_partition); g.nparts = nparts; g.part0 = part0; g.nlocal = nlocal;
+    g.subcap = whole_buckets(slots_per_partition); g.nparts = nparts; g.part0 = part0; g.nlocal = nlocal; g.k = k;
     return table_new(c, kind, k, g, out);
 }
 
@@ -437,7 +427,6 @@ void tg_table_destroy(tg_table* t) {
     cudaSetDevice(t->ctx->device);
     cudaDeviceSynchronize();
     log_release(t);
-    if (t->hot) cudaFree(t->hot);
     if (t->slots) cudaFree(t->slots);
     if (t->d_claimed) cudaFree(t->d_claimed);
     if (t->d_error) cudaFree(t->d_error);
@@ -447,7 +436,6 @@ void tg_table_destroy(tg_table* t) {
 int tg_table_clear(tg_table* t) {
     if (!t) return fail(TG_ERR_ARG, "null table");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     // stream-ordered, no host synchronisation (a host stall must not idle the GPU): stream 0 waits for whatever stream 1
     // still does with the table, clears, and stream 1 waits for the clear
@@ -474,8 +462,7 @@ int tg_table_clear(tg_table* t) {
 // Move the table into a new geometry (growth).  Both streams must be idle.
 static int table_regrow(tg_table* t, Geo ng) {
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
-    ng.hot_slots = nullptr; ng.hot_subcap = 0;
+    ng.k = t->k;
     const uint64_t ncap = (uint64_t)ng.nlocal * ng.subcap;
     Slot* fresh = nullptr;
     int rc;
@@ -598,7 +585,6 @@ int tg_table_compact_into(tg_table* t, uint32_t min_count, tg_table* dst) {
         t->g.part0 != dst->g.part0 || t->g.nlocal != dst->g.nlocal)
         return fail(TG_ERR_ARG, "tg_table_compact_into: the destination must have the source's kind, k and partition range");
     tg_ctx* c = t->ctx;
-    hot_invalidate(dst);
     if (bind(c)) return TG_ERR_CUDA;
     int rc = flush_log(t);
     if (rc) return rc;
@@ -614,7 +600,6 @@ int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes) {
     int rc = flush_log(t);
     if (rc) return rc;
     if ((rc = sync_all(t->ctx))) return rc;
-    hot_invalidate(t);            // the caller may write through the pointer
     *d_slots = t->slots;
     *nbytes = t->cap * sizeof(Slot);
     return TG_OK;
@@ -623,7 +608,6 @@ int tg_table_slots_dev(tg_table* t, void** d_slots, uint64_t* nbytes) {
 int tg_table_set_distinct(tg_table* t, uint64_t distinct) {
     if (!t) return fail(TG_ERR_ARG, "null table");
     if (bind(t->ctx)) return TG_ERR_CUDA;
-    hot_invalidate(t);            // called after the slots were rewritten through tg_table_slots_dev
     unsigned long long v = distinct;
     CU(cudaMemcpy(t->d_claimed, &v, sizeof v, cudaMemcpyHostToDevice));
     t->distinct_ub = distinct;
@@ -672,7 +656,7 @@ static unsigned log_bins_for(const tg_table* t) {
 // worth logging?  The replay streams the whole table through L2 once, so the batch must be large next to it.
 static bool log_pays(const tg_table* t, uint64_t nbytes) {
     const tg_ctx* c = t->ctx;
-    if (t->kind != TG_TABLE_COUNT || t->sharded()) return false;
+    if (t->kind != TG_TABLE_COUNT || t->sharded() || t->k < MIN_FAST_K) return false;
     if (c->count_mode == 1) return false;
     if (c->count_mode == 2) return true;
     return t->g.nparts >= 4 && nbytes * 16 >= t->cap * sizeof(Slot);
@@ -681,8 +665,10 @@ static bool log_pays(const tg_table* t, uint64_t nbytes) {
 constexpr uint64_t LOG_BIN_SLACK = 1024;    // additive head-room per bin (hash fluctuation of small batches)
 constexpr double LOG_BIN_FACTOR = 1.2;      // multiplicative head-room per bin (hot k-mers)
 
-// log entries one phase-1 launch over nbytes record bytes can take up at most: one per byte
-static uint64_t log_launch_cost(const tg_ctx*, const KeyLog&, uint64_t nbytes) { return nbytes; }
+// log entries a phase-1 launch over nbytes record bytes is laid out for.  An entry is a run of up to 8 windows that share
+// a minimizer (typically ~3.5 windows, i.e. ~0.2 entries per byte); one entry per two bytes leaves 2x head-room, and a
+// bin that fills up all the same counts its overflow directly (correct, only slower).
+static uint64_t log_launch_cost(const tg_ctx*, const KeyLog&, uint64_t nbytes) { return nbytes / 2 + 4096; }
 
 // entries that can be appended to an empty log without any bin expected to overflow
 static uint64_t log_room(const KeyLog& lg) {
@@ -705,16 +691,16 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     CU(cudaMemGetInfo(&fr, &tot));
     uint64_t budget = std::min<uint64_t>(c->log_max_bytes, fr / 2);
     if (log_refines(t, nbins)) budget /= 2;                  // the other half is the fine log of the replay
-    if (t->log.keys) budget = std::max<uint64_t>(budget, t->log.total_entries() * 8);
+    if (t->log.keys) budget = std::max<uint64_t>(budget, t->log.total_entries() * sizeof(LogEntry));
     uint64_t per_bin = want;
-    per_bin = std::min<uint64_t>(per_bin, budget / 8 / nbins);
+    per_bin = std::min<uint64_t>(per_bin, budget / sizeof(LogEntry) / nbins);
     per_bin = std::min<uint64_t>(per_bin, LOG_CAP_MAX);
     per_bin = per_bin / LOG_CAP_ALIGN * LOG_CAP_ALIGN;
     if (per_bin < 2 * LOG_BIN_SLACK) return TG_OK;
     if (t->log.keys && t->log.nbins == nbins && t->log.cap >= per_bin) { *ok = true; return TG_OK; }
     if (t->log.pending_ub) { *ok = t->log.keys != nullptr; return TG_OK; }   // holds entries: keep its layout
     log_release(t);
-    if (cudaMalloc(&t->log.keys, per_bin * nbins * 8) != cudaSuccess) { cudaGetLastError(); t->log.keys = nullptr; return TG_OK; }
+    if (cudaMalloc(&t->log.keys, per_bin * nbins * sizeof(LogEntry)) != cudaSuccess) { cudaGetLastError(); t->log.keys = nullptr; return TG_OK; }
     CU(cudaMalloc(&t->log.cursor, nbins * sizeof(unsigned int)));
     CU(cudaMalloc(&t->log.chunk_start, log_replay_plan_words(1, nbins, 64) * sizeof(unsigned long long)));
     t->log.plan_bins = nbins;
@@ -728,7 +714,7 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
 }
 
 // a log held entirely by this GPU: one owner, one source segment
-static LogView local_log_view(unsigned long long* keys, unsigned int* cursor, unsigned nbins, unsigned cap, int* error,
+static LogView local_log_view(LogEntry* keys, unsigned int* cursor, unsigned nbins, unsigned cap, int* error,
                               unsigned long long* hpoly) {
     LogView lg{};
     lg.owner[0] = keys;
@@ -754,7 +740,7 @@ static bool refine_log_async(tg_table* t) {
         if (lg.fine_keys) cudaFree(lg.fine_keys);
         if (lg.fine_cursor) cudaFree(lg.fine_cursor);
         lg.fine_keys = nullptr; lg.fine_cursor = nullptr; lg.fine_bins = 0; lg.fine_cap = 0;
-        if (cudaMalloc(&lg.fine_keys, (uint64_t)np * fcap * 8) != cudaSuccess) { cudaGetLastError(); lg.fine_keys = nullptr; return false; }
+        if (cudaMalloc(&lg.fine_keys, (uint64_t)np * fcap * sizeof(LogEntry)) != cudaSuccess) { cudaGetLastError(); lg.fine_keys = nullptr; return false; }
         if (cudaMalloc(&lg.fine_cursor, np * sizeof(unsigned int)) != cudaSuccess) {
             cudaGetLastError(); cudaFree(lg.fine_keys); lg.fine_keys = nullptr; lg.fine_cursor = nullptr; return false;
         }
@@ -776,7 +762,6 @@ static bool refine_log_async(tg_table* t) {
 
 static int replay_log_async(tg_table* t) {
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (refine_log_async(t)) {
         CU(launch_log_replay(t->log.fine_keys, t->log.fine_cursor, t->log.fine_cap, 1, t->log.fine_bins, 0, t->log.fine_bins,
                              c->replay_groups, t->log.chunk_start, t->log.hpoly, t->view(),
@@ -805,9 +790,10 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     if (ns < 1) ns = 1;
     uint64_t sample = 0;
     for (unsigned b = 0; b < ns; b++) sample += fill[b];
-    if (sample == 0) { *est = total; return TG_OK; }
+    const uint64_t per_entry = (uint64_t)le_max_run(t->k);
+    if (sample == 0) { *est = total * per_entry; return TG_OK; }
     Geo sg;
-    sg.subcap = whole_buckets(sample * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1;
+    sg.subcap = whole_buckets(sample * per_entry * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1; sg.k = t->k;
     Slot* scratch = nullptr;
     unsigned long long* d_n = nullptr;
     int rc;
@@ -823,7 +809,7 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     CU(cudaStreamSynchronize(c->stream[0]));
     cudaFree(scratch); cudaFree(d_n);
     *est = (uint64_t)((double)d * nbins / ns * 1.03) + 65536;
-    if (*est > total) *est = total;
+    if (*est > total * per_entry) *est = total * per_entry;
     return TG_OK;
 }
 
@@ -838,8 +824,9 @@ static int flush_log(tg_table* t) {
     CU(cudaMemcpy(fill.data(), t->log.cursor, fill.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
     uint64_t total = 0;
     for (auto& f : fill) { if (f > t->log.cap) f = t->log.cap; total += f; }
-    if ((double)(t->distinct_ub + total) > MAX_LOAD * (double)t->cap) {
-        uint64_t est = total;
+    const uint64_t kmers_ub = total * (uint64_t)le_max_run(t->k);          // an entry holds up to that many k-mers
+    if ((double)(t->distinct_ub + kmers_ub) > MAX_LOAD * (double)t->cap) {
+        uint64_t est = kmers_ub;
         if ((rc = estimate_log_distinct(t, fill, total, &est))) return rc;
         if ((double)(t->distinct_ub + est) > MAX_LOAD * (double)t->cap) {
             Geo ng;
@@ -858,7 +845,6 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
     if (!t || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_count_reads: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
     // Partitioned path: append to the log batch by batch (H2D of one batch overlaps the log kernel of the other),
@@ -869,7 +855,7 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
         if ((rc = tg_table_reserve(t, nbytes / 8))) return rc;
         t->distinct_ub -= nbytes / 8;       // it was a sizing hint, not an insertion
     }
-    if (log_pays(t, nbytes) && (rc = ensure_log(t, nbytes, &logged))) return rc;
+    if (log_pays(t, nbytes) && (rc = ensure_log(t, log_launch_cost(c, t->log, nbytes), &logged))) return rc;
     const uint64_t room = logged ? log_room(t->log) : 0;
     uint64_t pos = 0;
     for (int it = 0; pos < nbytes; it++) {
@@ -904,27 +890,26 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
     if (!t || !d_recs) return fail(TG_ERR_ARG, "tg_count_reads_dev: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     // the caller sizes the table (tg_table_create / tg_table_reserve): a conservative per-byte bound would
     // multiply the footprint.  An overflow raises the table's error flag -> TG_ERR_TABLE at tg_table_info.
     int rc;
     bool logged = false;
-    if (log_pays(t, nbytes) && (rc = ensure_log(t, nbytes, &logged))) return rc;
+    if (log_pays(t, nbytes) && (rc = ensure_log(t, log_launch_cost(c, t->log, nbytes), &logged))) return rc;
     if (!logged) {
         CU(launch_count_tiles((const uint8_t*)d_recs, nbytes, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
         c->launches++;
         return TG_OK;
     }
     // segments of whole tiles, each small enough for the log; everything stays stream-ordered on stream 0
-    uint64_t seg = log_room(t->log) / CT_TILE * CT_TILE;
+    uint64_t seg = log_room(t->log) * 2 / CT_TILE * CT_TILE;        // bytes whose entries the log is laid out for
     if (seg < (uint64_t)CT_TILE) seg = CT_TILE;
     for (uint64_t pos = 0; pos < nbytes; pos += seg) {
         const uint64_t n = std::min(seg, nbytes - pos);
         CU(launch_log_tiles((const uint8_t*)d_recs + pos, n, t->k, canonical, log_view(t), t->view(), c->sm_count,
                             c->stream[0]));
         c->launches++;
-        t->log.pending_ub += n;
+        t->log.pending_ub += log_launch_cost(c, t->log, n);
         if ((rc = replay_log_async(t))) return rc;
     }
     return TG_OK;
@@ -935,14 +920,14 @@ int tg_count_partition_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k
                            uint32_t cap, void* d_keys, void* d_cursor, void* d_hpoly) {
     if (!c || !d_recs || !d_keys || !d_cursor || !d_hpoly)
         return fail(TG_ERR_ARG, "tg_count_partition_dev: null argument");
-    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (k < MIN_FAST_K || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported by the partitioned path (%d..31)", k, MIN_FAST_K);
     if (nbins == 0 || nbins > LOG_MAX_BINS || cap == 0 || cap > LOG_CAP_MAX)
         return fail(TG_ERR_ARG, "tg_count_partition_dev: bad log shape (1..%u bins, capacity at most %u)", LOG_MAX_BINS,
                     LOG_CAP_MAX);
     if (bind(c)) return TG_ERR_CUDA;
-    LogView lg = local_log_view((unsigned long long*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error,
+    LogView lg = local_log_view((LogEntry*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error,
                                 (unsigned long long*)d_hpoly);
-    TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
+    TableView none{nullptr, Geo{0, 1, 0, 1, k}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
     return TG_OK;
@@ -954,7 +939,7 @@ int tg_count_partition_peers_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes,
                                  void* d_cursor, void* d_hpoly) {
     if (!c || !d_recs || !d_owner_keys || !d_cursor || !d_hpoly)
         return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: null argument");
-    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (k < MIN_FAST_K || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported by the partitioned path (%d..31)", k, MIN_FAST_K);
     if (nranks == 0 || nranks > (uint32_t)LOG_MAX_RANKS || my_rank >= nranks)
         return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: 1..%d ranks, rank inside", LOG_MAX_RANKS);
     if (nbins == 0 || nbins > LOG_MAX_BINS || nbins % nranks || cap == 0 || cap > LOG_CAP_MAX)
@@ -966,13 +951,13 @@ int tg_count_partition_peers_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes,
     LogView lg{};
     for (uint32_t r = 0; r < nranks; r++) {
         if (!d_owner_keys[r]) return fail(TG_ERR_ARG, "tg_count_partition_peers_dev: null receive log for rank %u", r);
-        lg.owner[r] = (unsigned long long*)d_owner_keys[r];
+        lg.owner[r] = (LogEntry*)d_owner_keys[r];
     }
     unsigned sh = 0;
     while ((1u << sh) < lp) sh++;
     lg.cursor = (unsigned int*)d_cursor; lg.nbins = nbins; lg.cap = cap; lg.lp_shift = sh; lg.src = my_rank;
     lg.error = c->d_error; lg.hpoly = (unsigned long long*)d_hpoly;
-    TableView none{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr};
+    TableView none{nullptr, Geo{0, 1, 0, 1, k}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
     return TG_OK;
@@ -992,9 +977,9 @@ int tg_log_refine_dev(tg_ctx* c, const void* d_keys, const void* d_cursor, uint3
     const size_t need = std::max(log_refine_plan_words(nsrc, ncoarse), log_replay_plan_words(1, nfine, 64)) *
                         sizeof(unsigned long long);
     CU(c->scratch.ensure(need));
-    CU(launch_log_refine((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, ncoarse,
-                         (unsigned long long*)c->scratch.p, (unsigned long long*)d_out_keys, (unsigned int*)d_out_cursor,
-                         out_cap, nfine, fine0, nfine_global, c->d_error, TableView{nullptr, Geo{0, 1, 0, 1}, nullptr, nullptr},
+    CU(launch_log_refine((const LogEntry*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, ncoarse,
+                         (unsigned long long*)c->scratch.p, (LogEntry*)d_out_keys, (unsigned int*)d_out_cursor,
+                         out_cap, nfine, fine0, nfine_global, c->d_error, TableView{nullptr, Geo{0, 1, 0, 1, 0}, nullptr, nullptr},
                          c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;
@@ -1032,11 +1017,10 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
     if (!t || !d_keys || !d_cursor || nsrc == 0 || cap == 0) return fail(TG_ERR_ARG, "tg_table_replay_log_dev: bad argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_table_replay_log_dev needs a TG_TABLE_COUNT table");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     const size_t need = log_replay_plan_words(nsrc, t->g.nlocal, 64) * sizeof(unsigned long long);
     CU(c->scratch.ensure(need));
-    CU(launch_log_replay((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
+    CU(launch_log_replay((const LogEntry*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
                          t->g.nparts, c->replay_groups, (unsigned long long*)c->scratch.p, (unsigned long long*)d_hpoly,
                          t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
     c->launches += 2;
@@ -1046,7 +1030,6 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
 int tg_table_load_pairs(tg_table* t, const uint64_t* keys, const uint32_t* vals, uint64_t n, int canonical) {
     if (!t || ((!keys || !vals) && n)) return fail(TG_ERR_ARG, "tg_table_load_pairs: null argument");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     int rc;
     if ((rc = flush_log(t))) return rc;
@@ -1131,59 +1114,6 @@ int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]) {
 // ---------------------------------------------------------------------------------------------------------
 }  // extern "C"
 
-// Build the hot table when a lookup-heavy call is about to start: the k-mers with the largest counts, as many as fit
-// the L2 budget, chosen from the count histogram.  Only worth it when they cover a good share of all occurrences
-// (expression skew) -- with a flat histogram the table is not built.  Count tables only (a label says nothing
-// about how often a k-mer is looked up).
-static int maybe_build_hot(tg_table* t, uint64_t lookups) {
-    tg_ctx* c = t->ctx;
-    if (t->g.hot_slots || t->hot_tried || t->kind != TG_TABLE_COUNT || c->hot_max_keys == 0) return TG_OK;
-    if (!c->hot_force && (t->cap * sizeof(Slot) < (256ull << 20) || lookups < (64ull << 20))) return TG_OK;
-    t->hot_tried = true;
-    unsigned long long* d_bins = nullptr;
-    CU(cudaMalloc(&d_bins, TG_HISTO_BINS * sizeof *d_bins));
-    CU(cudaMemsetAsync(d_bins, 0, TG_HISTO_BINS * sizeof *d_bins, c->stream[0]));
-    CU(launch_histo(t->slots, t->cap, d_bins, c->stream[0]));
-    c->launches++;
-    std::vector<unsigned long long> bins(TG_HISTO_BINS);
-    CU(cudaMemcpyAsync(bins.data(), d_bins, TG_HISTO_BINS * sizeof *d_bins, cudaMemcpyDeviceToHost, c->stream[0]));
-    CU(cudaStreamSynchronize(c->stream[0]));
-    cudaFree(d_bins);
-    // threshold T: the smallest count such that #{count >= T} <= hot_max_keys
-    unsigned long long keys = bins[TG_HISTO_BINS - 1];
-    double covered = (double)bins[TG_HISTO_BINS - 1] * 10001.0, total = covered;
-    for (int cnt = 1; cnt <= 10000; cnt++) total += (double)bins[cnt] * cnt;
-    if (keys > c->hot_max_keys) return TG_OK;
-    uint32_t T = 10001;
-    for (int cnt = 10000; cnt >= 2; cnt--) {
-        if (keys + bins[cnt] > c->hot_max_keys) break;
-        keys += bins[cnt];
-        covered += (double)bins[cnt] * cnt;
-        T = (uint32_t)cnt;
-    }
-    if (!c->hot_force && (keys < 1024 || covered < 0.25 * total)) return TG_OK;
-    if (keys == 0) return TG_OK;
-    const uint64_t want = (uint64_t)((double)keys / c->hot_load) + 1024;
-    if (t->hot_cap < want) {
-        if (t->hot) cudaFree(t->hot);
-        t->hot = nullptr; t->hot_cap = 0;
-        if (cudaMalloc(&t->hot, want * sizeof(Slot)) != cudaSuccess) { cudaGetLastError(); return TG_OK; }
-        t->hot_cap = want;
-    }
-    CU(cudaMemsetAsync(t->hot, 0, t->hot_cap * sizeof(Slot), c->stream[0]));
-    // hottest first, so that they win the direct-mapped places
-    const uint32_t T_hi = T > 0x3FFFFFFFu ? T : T * 4u;
-    CU(launch_hot_fill(t->slots, t->cap, t->hot, t->hot_cap, T_hi, 0xFFFFFFFFu, c->stream[0]));
-    CU(launch_hot_fill(t->slots, t->cap, t->hot, t->hot_cap, T, T_hi - 1, c->stream[0]));
-    c->launches += 2;
-    CU(cudaStreamSynchronize(c->stream[0]));
-    t->hot_keys = keys; t->hot_min = T;
-    t->g.hot_slots = t->hot;
-    t->g.hot_subcap = t->hot_cap;
-    t->g.hot_hints = c->hot_hints;
-    return TG_OK;
-}
-
 struct ReadBatch { uint64_t r0, r1; };
 
 static std::vector<ReadBatch> split_reads(const uint64_t* offs, uint64_t nreads, size_t batch_bytes) {
@@ -1199,6 +1129,23 @@ static std::vector<ReadBatch> split_reads(const uint64_t* offs, uint64_t nreads,
         r0 = r1;
     }
     return v;
+}
+
+// largest window count among reads [r0, r1) (at least 1, so that scratch sizes are never zero)
+static unsigned batch_max_windows(const uint64_t* offs, uint64_t r0, uint64_t r1, int k) {
+    uint64_t mx = 1;
+    for (uint64_t r = r0; r < r1; r++) {
+        const uint64_t L = offs[r + 1] - offs[r] - 1;
+        if (L >= (uint64_t)k && L - k + 1 > mx) mx = L - k + 1;
+    }
+    return (unsigned)std::min<uint64_t>(mx, 0xFFFFFFF0ull);
+}
+template <typename ScratchBytes>
+static void long_launch_shape(tg_ctx* c, unsigned n_long, unsigned max_win, int k, ScratchBytes scratch_bytes, int* nctas,
+                              size_t* need) {
+    *nctas = (int)std::min<unsigned>(std::max(n_long, 1u), (unsigned)c->sm_count * 2);
+    *need = scratch_bytes(max_win, k, *nctas);
+    while (*nctas > 1 && *need > (1ull << 30)) { *nctas = (*nctas + 1) / 2; *need = scratch_bytes(max_win, k, *nctas); }
 }
 
 // after the warp-path kernel of batch b: run the CTA-per-read kernel if any read was too long for it
@@ -1233,7 +1180,6 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
     int rc;
     if ((rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
-    if ((rc = maybe_build_hot(t, offs[nreads] - offs[0]))) return rc;
     const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
     struct Pending { bool live = false; ReadBatch rb; } pend[2];
     auto drain = [&](int b) -> int {   // long-read pass + results back to the caller for the batch in flight on b
@@ -1272,9 +1218,22 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
         CU(cudaMemcpyAsync(c->offs[b].p, offs + rb.r0, (m + 1) * 8, cudaMemcpyHostToDevice, c->stream[b]));
         CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
         LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
-        CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
-                            t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
-                            per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, c->stream[b]));
+        if (t->k >= MIN_FAST_K) {
+            CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
+                                t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
+                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, c->stream[b]));
+        } else {
+            // k-mers shorter than the warp path's 8 m-mers per k-mer: every read through the CTA-per-read kernel
+            int nctas = 0; size_t need = 0;
+            const unsigned max_win = batch_max_windows(offs, rb.r0, rb.r1, t->k);
+            long_launch_shape(c, (unsigned)m, max_win, t->k, cov_stats_long_scratch_bytes, &nctas, &need);
+            CU(cudaStreamSynchronize(c->stream[b ^ 1]));      // the scratch buffer is shared by both streams
+            CU(c->scratch.ensure(need));
+            CU(launch_cov_stats_long((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, t->k, canonical,
+                                     t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
+                                     per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, nullptr, (unsigned)m, max_win,
+                                     c->scratch.p, nctas, c->stream[b]));
+        }
         c->launches++;
         pend[b].live = true; pend[b].rb = rb;
     }
@@ -1290,12 +1249,8 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_cov_stats_dev: at most 2^31 reads per call");
+    if (t->k < MIN_FAST_K) return fail(TG_ERR_ARG, "tg_cov_stats_dev: k >= %d (shorter k-mers: the host-buffer entry point)", MIN_FAST_K);
     if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }
-    if (c->hot_max_keys && !t->g.hot_slots && !t->hot_tried) {
-        int rc = sync_all(c);
-        if (rc) return rc;
-        if ((rc = maybe_build_hot(t, nreads * 64))) return rc;     // reads are at least a few dozen windows each
-    }
     // everything below is stream-ordered: no host synchronisation (see launch_cov_stats_long_auto)
     const int b = 0;
     CU(c->long_idx[b].ensure(nreads * 4));
@@ -1315,7 +1270,6 @@ int tg_label_bundles(tg_table* t, const char* recs, const uint64_t* offs, uint64
     if (!t || ((!recs || !offs) && nbundles)) return fail(TG_ERR_ARG, "tg_label_bundles: null argument");
     if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles needs a TG_TABLE_LABEL table");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     if (nbundles == 0) return TG_OK;
     int rc;
@@ -1342,7 +1296,6 @@ int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const
     if (!t || !d_recs || !d_offs) return fail(TG_ERR_ARG, "tg_label_bundles_dev: null argument");
     if (t->kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "tg_label_bundles_dev needs a TG_TABLE_LABEL table");
     tg_ctx* c = t->ctx;
-    hot_invalidate(t);
     if (bind(c)) return TG_ERR_CUDA;
     CU(launch_label_tiles((const uint8_t*)d_recs, nbytes, (const uint64_t*)d_offs, 0, nbundles, first_index, t->k,
                           t->view(), c->sm_count, c->stream[0]));
@@ -1402,9 +1355,20 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
         CU(cudaMemcpyAsync(c->offs[b].p, offs + rb.r0, (m + 1) * 8, cudaMemcpyHostToDevice, c->stream[b]));
         CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
         LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
-        CU(launch_assign((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, strand, t->slots,
-                         t->g, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
-                         (int32_t*)c->out_c[b].p, ll, c->stream[b]));
+        if (t->k >= MIN_FAST_K) {
+            CU(launch_assign((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, strand, t->slots,
+                             t->g, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
+                             (int32_t*)c->out_c[b].p, ll, c->stream[b]));
+        } else {
+            int nctas = 0; size_t need = 0;
+            const unsigned max_win = batch_max_windows(offs, rb.r0, rb.r1, t->k);
+            long_launch_shape(c, (unsigned)m, max_win, t->k, assign_long_scratch_bytes, &nctas, &need);
+            CU(cudaStreamSynchronize(c->stream[b ^ 1]));
+            CU(c->scratch.ensure(need));
+            CU(launch_assign_long((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, t->k, strand, t->slots,
+                                  t->g, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
+                                  (int32_t*)c->out_c[b].p, nullptr, (unsigned)m, max_win, c->scratch.p, nctas, c->stream[b]));
+        }
         c->launches++;
         pend[b].live = true; pend[b].rb = rb;
     }
@@ -1420,6 +1384,7 @@ int tg_assign_reads_dev(tg_table* t, const void* d_recs, const void* d_offs, uin
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_assign_reads_dev: at most 2^31 reads per call");
+    if (t->k < MIN_FAST_K) return fail(TG_ERR_ARG, "tg_assign_reads_dev: k >= %d (shorter k-mers: the host-buffer entry point)", MIN_FAST_K);
     const int b = 0;
     CU(c->long_idx[b].ensure(nreads * 4));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));

@@ -74,7 +74,7 @@ cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int 
 // global bins bin0..bin0+nlocal-1 of nbins_global, `groups` bins open at a time.  d_chunk_start: scratch of
 // log_replay_plan_words(nsrc, nlocal, groups) u64.
 size_t log_replay_plan_words(unsigned nsrc, unsigned nlocal, unsigned groups);
-cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+cudaError_t launch_log_replay(const LogEntry* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned groups,
                               unsigned long long* d_chunk_start, unsigned long long* d_hpoly, TableView t, int prefetch,
                               int sm_count, cudaStream_t s);
@@ -84,16 +84,13 @@ cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned i
 // overflow_table when that has slots, else raises error 3 in *d_error; a foreign key raises error 2.
 size_t log_refine_plan_words(unsigned nsrc, unsigned ncoarse);
 unsigned log_refine_max_split();      // most table partitions one coarse bin may cover
-cudaError_t launch_log_refine(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
-                              unsigned ncoarse, unsigned long long* d_chunk_start, unsigned long long* d_out_keys,
+cudaError_t launch_log_refine(const LogEntry* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                              unsigned ncoarse, unsigned long long* d_chunk_start, LogEntry* d_out_keys,
                               unsigned int* d_out_cursor, unsigned out_cap, unsigned nfine, unsigned fine0,
                               unsigned nfine_global, int* d_error, TableView overflow_table, int sm_count, cudaStream_t s);
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);
-// direct-mapped hot cache: slots of `from` with min_val <= val <= max_val -> hot[mulhi(hash, hot_cap)] when free
-cudaError_t launch_hot_fill(const Slot* from, uint64_t from_cap, Slot* hot, uint64_t hot_cap, uint32_t min_val,
-                            uint32_t max_val, cudaStream_t s);
 // re-insert every live slot of `from` whose value is >= min_val into `to` (growth: min_val 0; compaction: min count)
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
                           cudaStream_t s);

@@ -111,8 +111,6 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
 #pragma unroll 1
             for (int g = 0; g < 32; g += 4) {
                 unsigned long long key[4];
-                Probe pr[4];
-                unsigned long long cur[4];
                 unsigned cnt[4];
                 uint32_t lab[4];
                 unsigned rcs = 0;      // LABEL: bit u set = window u is the reverse complement of its (canonical) key
@@ -145,23 +143,17 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                     for (int u = 1; u < 4; u++)
                         if (key[u] != 0ull && key[u] == key[u - 1]) { cnt[u] += cnt[u - 1]; key[u - 1] = 0ull; }
                 }
+                // homes by the slow path (8 m-mer hashes per key): this kernel serves inputs that are small next to the
+                // table -- the bundle records, short batches, the overflow of a full log bin
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
-                        if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
-                        else { key[u] = 0ull; atomicExch(t.error, 2); }
-                    }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (key[u] != 0ull) {
+                        const unsigned hj = key_home_packed(key[u], k);
                         if (MODE == MODE_COUNT) {
-                            Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
-                            if (sl) atomicAdd(&sl->val, cnt[u]);
+                            table_add(t, key[u], hj, cnt[u], claimed);
                         } else {
                             // `claimed` counts distinct FORWARD k-mers (NonRedKmerTable's size): first label of a field
-                            unsigned slots_claimed = 0;
-                            Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], slots_claimed);
-                            if (sl && atomicMax((rcs >> u) & 1u ? &sl->aux : &sl->val, lab[u]) == 0u) claimed++;
+                            if (table_label_max(t, key[u], hj, (rcs >> u) & 1u, lab[u])) claimed++;
                         }
                     }
                 __syncwarp(act);   // lanes leave the probe loops at different times: reconverge before the next group
@@ -235,14 +227,18 @@ static_assert(CT_TILE % LT_TILE == 0, "record buffers are padded to CT_TILE");
 
 struct LogSmem {
     alignas(128) uint8_t ascii[2][LT_LOAD];
-    uint32_t p0[LT_CHUNKS + 1];
-    uint32_t p1[LT_CHUNKS + 1];
-    uint32_t pb[LT_CHUNKS + 1];
-    uint32_t meta[LT_TILE];                         // bin << 12 | rank, ~0 = no entry
+    uint32_t p0[LT_CHUNKS + 2];                     // + halo chunk + one word the funnel shifts of the halo may touch
+    uint32_t p1[LT_CHUNKS + 2];
+    uint32_t pb[LT_CHUNKS + 2];
+    // entry descriptors, row e = the thread's e-th entry (phase A -> B): minimizer hash / packed home, rank inside its bin
+    // in this tile, and first window | (n - 1) << 4 | q0 << 7 | explicit << 10
+    uint32_t eh[LT_TILE];
+    uint16_t erank[LT_TILE];
+    uint16_t einfo[LT_TILE];
     uint32_t wtot[LT_THREADS / 32];
     uint32_t total;
     alignas(8) unsigned long long bar[2];
-    unsigned long long* seg[LOG_MAX_RANKS];         // this rank's segment in every owner's log (dynamic index: not params)
+    LogEntry* seg[LOG_MAX_RANKS];                   // this rank's segment in every owner's log (dynamic index: not params)
 };
 
 __device__ __forceinline__ unsigned long long window_key(unsigned f0, unsigned f1, int k, int canonical) {
@@ -258,17 +254,22 @@ __global__ void __launch_bounds__(LT_THREADS, 2)
 k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, LogView lg, TableView t) {
     __shared__ LogSmem sm;
     extern __shared__ __align__(16) unsigned char dyn[];
-    // dynamic: skey[LT_TILE] u64 | delta[nbins] u32 | sbin[LT_TILE] u16 | cnt16[nbins2] u16 | off16[nbins2] u16
+    // dynamic: sent[LT_TILE] 16-B entries (the m-mer hashes of phases H/A share its memory) | delta[nbins] u32 |
+    //          cnt16[nbins2] u16 | off16[nbins2] u16
     const unsigned nbins = lg.nbins, nbins2 = (nbins + 1u) & ~1u;
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dyn);
-    unsigned int* delta = reinterpret_cast<unsigned int*>(skey + LT_TILE);
-    unsigned short* sbin = reinterpret_cast<unsigned short*>(delta + nbins);
-    unsigned short* cnt16 = sbin + LT_TILE;
+    LogEntry* sent = reinterpret_cast<LogEntry*>(dyn);
+    unsigned int* hx = reinterpret_cast<unsigned int*>(dyn);
+    static_assert((LT_TILE + HOME_SLOTS) * 17 / 16 * 4 <= LT_TILE * 16, "the hash array fits the sorted-tile buffer");
+    unsigned int* delta = reinterpret_cast<unsigned int*>(sent + LT_TILE);
+    unsigned short* cnt16 = reinterpret_cast<unsigned short*>(delta + nbins);
     unsigned short* off16 = cnt16 + nbins2;
     unsigned int* cnt32 = reinterpret_cast<unsigned int*>(cnt16);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mk = kmask(k);
+    const int m = mm_len(k);
+    const unsigned mm = kmask(m);
+    const unsigned nmax = (unsigned)le_max_run(k);
     unsigned claimed = 0;
     unsigned hpA = 0, hpC = 0, hpG = 0, hpT = 0;    // homopolymer windows seen by this thread, by base code
 
@@ -279,6 +280,7 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
 #pragma unroll
         for (int r = 0; r < LOG_MAX_RANKS; r++)
             sm.seg[r] = lg.owner[r] ? lg.owner[r] + (((unsigned long long)lg.src << lg.lp_shift) * lg.cap) : nullptr;
+        sm.p0[LT_CHUNKS + 1] = 0u; sm.p1[LT_CHUNKS + 1] = 0u; sm.pb[LT_CHUNKS + 1] = 0xFFFFFFFFu;
     }
     for (unsigned b = tid; b < nbins2 / 2; b += LT_THREADS) cnt32[b] = 0u;
     __syncthreads();
@@ -309,31 +311,81 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
         }
         __syncthreads();   // planes complete; ascii[buf] is free for the TMA issued two iterations later
 
-        // ---- A: bins and ranks
+        // ---- H: strand-symmetric hash of the m-mer at every position of the tile (+7 past its end).  Padded by one
+        // word per 16 so that the strips below (thread t reads positions 16 t ..) are bank-conflict free.
+        for (int pos = tid; pos < LT_TILE + HOME_SLOTS - 1; pos += LT_THREADS) {
+            const int hc = pos >> 5, ho = pos & 31;
+            unsigned x = 0xFFFFFFFFu;
+            if (!(__funnelshift_r(sm.pb[hc], sm.pb[hc + 1], ho) & mm))
+                x = mmer_hash(__funnelshift_r(sm.p0[hc], sm.p0[hc + 1], ho) & mm, __funnelshift_r(sm.p1[hc], sm.p1[hc + 1], ho) & mm, m);
+            hx[pos + (pos >> 4)] = x;
+        }
+        __syncthreads();
+
+        // ---- A: super-k-mers.  The thread walks its 16 windows; consecutive valid windows whose minimizer is the same
+        // m-mer occurrence (same absolute position, unique smallest hash in the window) form one run = one entry, whose
+        // bin is the partition of the minimizer hash.  A window whose smallest hash occurs twice travels alone, with the
+        // home its own orientation dictates.
         const int c = tid >> 1, sh0 = (tid & 1) * LT_WIN;
         const unsigned a0 = sm.p0[c], a1 = sm.p1[c], ab = sm.pb[c];
         const unsigned c0 = sm.p0[c + 1], c1 = sm.p1[c + 1], cb = sm.pb[c + 1];
-#pragma unroll 4
-        for (int j = 0; j < LT_WIN; j++) {
-            const int s = sh0 + j;
-            const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
-            const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
-            const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-            const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
-            unsigned m = 0xFFFFFFFFu;
-            if (!bad) {
-                if (homo) {
-                    const unsigned code = (f0 & 1u) | ((f1 & 1u) << 1);
-                    hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
+        unsigned ne = 0;                                  // entries of this thread
+        unsigned run_n = 0, run_start = 0, run_abs = 0;   // the open run: windows, first window, minimizer position (strip)
+        auto emit = [&](unsigned h_or_hj, unsigned info) {
+            const unsigned bin = home_part(h_or_hj, nbins);
+            const unsigned shift = (bin & 1u) * 16u;
+            const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
+            sm.eh[ne * LT_THREADS + tid] = h_or_hj;
+            sm.erank[ne * LT_THREADS + tid] = (unsigned short)((old >> shift) & 0xFFFFu);     // < LT_TILE = 4096
+            sm.einfo[ne * LT_THREADS + tid] = (unsigned short)info;
+            ne++;
+        };
+        auto close_run = [&]() {
+            if (run_n) {
+                const int pos = tid * LT_WIN + (int)run_abs;
+                emit(hx[pos + (pos >> 4)], run_start | ((run_n - 1u) << 4) | ((run_abs - run_start) << 7));
+                run_n = 0;
+            }
+        };
+#pragma unroll 1
+        for (int half = 0; half < LT_WIN / HOME_SLOTS; half++) {
+            const int b0 = tid * LT_WIN + half * HOME_SLOTS;          // first position of this strip of 8 windows
+            unsigned strip[2 * HOME_SLOTS - 1], vl[HOME_SLOTS], vr[HOME_SLOTS];
+#pragma unroll
+            for (int q = 0; q < 2 * HOME_SLOTS - 1; q++) strip[q] = hx[b0 + q + ((b0 + q) >> 4)];
+            strip_minimizers<HOME_SLOTS>(strip, vl, vr);
+#pragma unroll
+            for (int i = 0; i < HOME_SLOTS; i++) {
+                const unsigned j = (unsigned)(half * HOME_SLOTS + i);
+                const int s = sh0 + (int)j;
+                const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
+                const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+                const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+                const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
+                if (bad || homo) {
+                    close_run();
+                    if (!bad) {
+                        const unsigned code = (f0 & 1u) | ((f1 & 1u) << 1);
+                        hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
+                    }
+                    continue;
+                }
+                const unsigned sl = vl[i] & ORD_POS_MASK, sr = ORD_POS_MASK - (vr[i] & ORD_POS_MASK);   // in the half strip
+                const unsigned abs_l = (unsigned)(half * HOME_SLOTS) + sl;
+                if (sl == sr) {
+                    if (run_n && abs_l == run_abs && run_n < nmax) { run_n++; continue; }
+                    close_run();
+                    run_n = 1; run_start = j; run_abs = abs_l;
                 } else {
-                    const unsigned bin = hash_part(mix64(window_key(f0, f1, k, canonical)), nbins);
-                    const unsigned shift = (bin & 1u) * 16u;
-                    const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
-                    m = (bin << 12) | ((old >> shift) & 0xFFFFu);
+                    close_run();
+                    const bool is_rc = canonical && make_key(rc_plane(f0, k), rc_plane(f1, k)) < make_key(f0, f1);
+                    unsigned jj;
+                    const unsigned sp = strip_pick(vl[i], vr[i], i, is_rc, jj);
+                    emit(pack_home(hx[b0 + sp + ((b0 + sp) >> 4)], jj), j | (1u << 10));
                 }
             }
-            sm.meta[j * LT_THREADS + tid] = m;
         }
+        close_run();
         __syncthreads();
 
         // ---- S: scan the bin counters, reserve every bin's run in the log
@@ -363,36 +415,41 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // (also: every thread is done with the hashes, the sorted tile may overwrite them)
 
-        // ---- B: keys again, into their sorted places
-#pragma unroll 4
-        for (int j = 0; j < LT_WIN; j++) {
-            const unsigned m = sm.meta[j * LT_THREADS + tid];
-            if (m != 0xFFFFFFFFu) {
-                const int s = sh0 + j;
-                const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
-                const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-                const unsigned bin = m >> 12;
-                const unsigned idx = off16[bin] + (m & 0xFFFu);
-                skey[idx] = window_key(f0, f1, k, canonical);
-                sbin[idx] = (unsigned short)bin;
+        // ---- B: the entries, into their sorted places (bases straight from the plane words: two funnel shifts)
+        for (unsigned e = 0; e < ne; e++) {
+            const unsigned h = sm.eh[e * LT_THREADS + tid], info = sm.einfo[e * LT_THREADS + tid];
+            const int s = sh0 + (int)(info & 15u);
+            const unsigned idx = off16[home_part(h, nbins)] + sm.erank[e * LT_THREADS + tid];
+            LogEntry le;
+            le.h = h;
+            if (info & (1u << 10)) {          // a single window with its own home: the (canonical) key itself
+                const unsigned long long key = window_key(__funnelshift_r(a0, c0, s) & mk, __funnelshift_r(a1, c1, s) & mk, k, canonical);
+                le.b0 = key_p0(key); le.b1 = key_p1(key);
+                le.meta = LE_VALID | LE_EXPLICIT | 1u;
+            } else {
+                const unsigned n = ((info >> 4) & 7u) + 1u, q0 = (info >> 7) & 7u;
+                const unsigned lm = kmask(k + (int)n - 1);
+                le.b0 = __funnelshift_r(a0, c0, s) & lm; le.b1 = __funnelshift_r(a1, c1, s) & lm;
+                le.meta = LE_VALID | n | (q0 << 4) | (canonical ? LE_CANONICAL : 0u);
             }
+            sent[idx] = le;
         }
         __syncthreads();
 
         // ---- W: stream the sorted tile out
         const unsigned total = sm.total;
         for (unsigned i = tid; i < total; i += LT_THREADS) {
-            const unsigned bin = sbin[i];
+            const LogEntry e = sent[i];
+            const unsigned bin = home_part(e.h, nbins);
             const unsigned pos = delta[bin] + i;
-            const unsigned long long key = skey[i];
             if (pos < lg.cap) {
                 // bin -> (owner, bin inside the owner); the store lands in local HBM or, over NVLink, in the owner's log
                 const unsigned o = bin >> lg.lp_shift, lb = bin - (o << lg.lp_shift);
-                sm.seg[o][(unsigned long long)lb * lg.cap + pos] = key;
-            } else if (t.slots) {      // bin full: count this occurrence directly
-                table_update<false>(t, key, 1u, claimed);
+                sm.seg[o][(unsigned long long)lb * lg.cap + pos] = e;
+            } else if (t.slots) {      // bin full: count these occurrences directly
+                le_apply(t, e, 1u, claimed);
             } else {
                 atomicExch(lg.error, 3);
             }
@@ -419,7 +476,7 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
 
 size_t log_tiles_smem_bytes(unsigned nbins) {
     const unsigned nbins2 = (nbins + 1u) & ~1u;
-    return (size_t)LT_TILE * 8 + (size_t)nbins * 4 + (size_t)LT_TILE * 2 + (size_t)nbins2 * 2 * 2;
+    return (size_t)LT_TILE * sizeof(LogEntry) + (size_t)nbins * 4 + (size_t)nbins2 * 2 * 2;
 }
 
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
@@ -519,27 +576,42 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// one log entry, streamed (read once)
+__device__ __forceinline__ LogEntry ld_entry(const LogEntry* p) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+    LogEntry e;
+    e.b0 = v.x; e.b1 = v.y; e.h = v.z; e.meta = v.w;
+    return e;
+}
+
 template <bool FOLD>
 __global__ void __launch_bounds__(RP_THREADS, RP_MIN_CTAS)
-k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
+k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned G,
              unsigned long long* chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned per = replay_per_group(nlocal, G);
     const unsigned nperm = per * G * nsrc;
+    const int k = t.g.k;
+    const unsigned mk = kmask(k);
     unsigned claimed = 0;
     if (hpoly && blockIdx.x == 0 && tid < 4) {
         // homopolymer tallies of phase 1: applied by the view that holds the key's partition, then cleared
         const unsigned long long n = hpoly[4 + tid], key = hpoly[tid];
-        Probe p;
-        if (n && probe_home(t.g, key, p)) table_update<false>(t, key, (unsigned)n, claimed);
+        if (n) {
+            const unsigned hj = key_home_packed(key, t.g.k);
+            if (home_part(hj, t.g.nparts) - t.g.part0 < t.g.nlocal) table_add(t, key, hj, (unsigned)n, claimed);
+        }
         hpoly[4 + tid] = 0ull;
     }
     __shared__ unsigned long long s_w;
     extern __shared__ __align__(16) unsigned char dyn[];
-    unsigned long long* f_key = reinterpret_cast<unsigned long long*>(dyn);      // fold table of one chunk:
-    unsigned int* f_cnt = reinterpret_cast<unsigned int*>(f_key + RP_FOLD);      // key -> occurrences, open addressing
-    if (FOLD) for (int i = tid; i < RP_FOLD; i += RP_THREADS) { f_key[i] = 0ull; f_cnt[i] = 0u; }
+    // fold table of one chunk, open addressing: (bases, minimizer hash, meta) of an entry -> occurrences.  The bases of an
+    // entry are never all-A (those windows are homopolymers and bypass the log), so 0 marks a free place.
+    unsigned long long* f_key = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned long long* f_hm = f_key + RP_FOLD;                                  // h | meta << 32, written by the claimer
+    unsigned int* f_cnt = reinterpret_cast<unsigned int*>(f_hm + RP_FOLD);
+    if (FOLD) for (int i = tid; i < RP_FOLD; i += RP_THREADS) { f_key[i] = 0ull; f_hm[i] = 0ull; f_cnt[i] = 0u; }
     unsigned long long* counters = chunk_start + nperm + 1;
     unsigned last_lp = 0xFFFFFFFFu;
     // a CTA serves its own group first and then helps the following groups finish
@@ -559,7 +631,7 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
             replay_segment(q, nsrc, nlocal, G, lp, src);
             const unsigned seg = src * nlocal + lp;
             const unsigned n = min(cursor[seg], cap);
-            const unsigned long long* base = keys + (unsigned long long)seg * cap;
+            const LogEntry* kbase = keys + (unsigned long long)seg * cap;
             const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
 
             if (prefetch && lp != last_lp) {
@@ -589,58 +661,83 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
 #pragma unroll
             for (int u = 0; FOLD && u < RP_PER_THREAD; u++) {
                 const unsigned i = i0 + u * RP_THREADS + tid;
-                const unsigned long long key = i < n ? __ldcs(base + i) : 0ull;
-                if (key != 0ull) {
-                    // bits 40..: every key of a bin shares the top bits of the LOW hash word (they are the partition)
-                    unsigned h = (unsigned)(mix64(key) >> 40) & (RP_FOLD - 1);
+                LogEntry e;
+                e.meta = 0u;
+                if (i < n) e = ld_entry(kbase + i);
+                if (e.meta != 0u) {
+                    const unsigned long long bases = ((unsigned long long)e.b1 << 32) | e.b0;
+                    const unsigned long long hm = ((unsigned long long)e.meta << 32) | e.h;
+                    unsigned h = (unsigned)(mix64(bases ^ hm) >> 40) & (RP_FOLD - 1);
                     int tries = 0;
                     for (; tries < RP_FOLD_PROBES; tries++) {
-                        const unsigned long long old = atomicCAS(&f_key[h], 0ull, key);
-                        if (old == 0ull || old == key) { atomicAdd(&f_cnt[h], 1u); break; }
+                        const unsigned long long old = atomicCAS(&f_key[h], 0ull, bases);
+                        if (old == 0ull) {
+                            // the claimer publishes the rest.  A twin racing ahead of that store sees 0, takes it for a
+                            // different entry and moves on: the entry then sits in two places, which only folds less.
+                            *reinterpret_cast<volatile unsigned long long*>(&f_hm[h]) = hm;
+                            atomicAdd(&f_cnt[h], 1u);
+                            break;
+                        }
+                        if (old == bases && *reinterpret_cast<volatile unsigned long long*>(&f_hm[h]) == hm) {
+                            atomicAdd(&f_cnt[h], 1u);
+                            break;
+                        }
                         h = (h + 1) & (RP_FOLD - 1);
                     }
-                    if (tries == RP_FOLD_PROBES) table_update<false>(t, key, 1u, claimed);      // crowded corner: unfolded
+                    if (tries == RP_FOLD_PROBES) le_apply(t, e, 1u, claimed);          // crowded corner: unfolded
                 }
             }
             if (FOLD) __syncthreads();
 #pragma unroll 1
-            for (int gg = 0; gg < RP_PER_THREAD; gg += RP_GROUP) {
-                unsigned long long key[RP_GROUP], cur[RP_GROUP], cur1[RP_GROUP];
-                unsigned cnt[RP_GROUP];
-                Probe pr[RP_GROUP];
-#pragma unroll
-                for (int u = 0; u < RP_GROUP; u++) {
-                    if (FOLD) {
-                        const unsigned sidx = (gg + u) * RP_THREADS + tid;
-                        key[u] = f_key[sidx];
-                        cnt[u] = f_cnt[sidx];
-                        if (key[u] != 0ull) { f_key[sidx] = 0ull; f_cnt[sidx] = 0u; }     // clean for the next chunk
+            for (int gg = 0; gg < RP_PER_THREAD; gg++) {
+                LogEntry e;
+                unsigned cnt = 1u;
+                e.meta = 0u;
+                if (FOLD) {
+                    const unsigned sidx = gg * RP_THREADS + tid;
+                    const unsigned long long bases = f_key[sidx];
+                    if (bases != 0ull) {
+                        const unsigned long long hm = f_hm[sidx];
+                        e.b0 = (unsigned)bases; e.b1 = (unsigned)(bases >> 32); e.h = (unsigned)hm; e.meta = (unsigned)(hm >> 32);
+                        cnt = f_cnt[sidx];
+                        f_key[sidx] = 0ull; f_hm[sidx] = 0ull; f_cnt[sidx] = 0u;          // clean for the next chunk
+                    }
+                } else {
+                    const unsigned i = i0 + gg * RP_THREADS + tid;
+                    if (i < n) e = ld_entry(kbase + i);
+                }
+                if (e.meta != 0u) {
+                    if (e.meta & LE_EXPLICIT) {
+                        table_add(t, make_key(e.b0, e.b1), e.h, cnt, claimed);
                     } else {
-                        const unsigned i = i0 + (gg + u) * RP_THREADS + tid;
-                        key[u] = i < n ? __ldcs(base + i) : 0ull;
-                        cnt[u] = 1u;
+                        // all windows of the run live in ONE bucket: address it once, have the home-slot loads of up to
+                        // four windows in flight, settle them, then the rest
+                        unsigned long long base, home0;
+                        if (!home_of(t.g, pack_home(e.h, 0u), base, home0)) { atomicExch(t.error, 2); }
+                        else {
+                            const unsigned nw = le_n(e.meta);
+#pragma unroll 1
+                            for (unsigned w0 = 0; w0 < nw; w0 += 4) {
+                                unsigned long long key[4], cur[4];
+                                unsigned slot[4];
+#pragma unroll
+                                for (unsigned u = 0; u < 4; u++)
+                                    if (w0 + u < nw) {
+                                        unsigned hj;
+                                        le_window(e, w0 + u, k, mk, key[u], hj);
+                                        slot[u] = home_slot(hj);
+                                        cur[u] = __ldcg(&t.slots[home0 + slot[u]].key);
+                                    }
+#pragma unroll
+                                for (unsigned u = 0; u < 4; u++)
+                                    if (w0 + u < nw) {
+                                        Slot* sl = table_upsert_finish(t, key[u], base, home0 + slot[u], cur[u], claimed);
+                                        if (sl) atomicAdd(&sl->val, cnt);
+                                    }
+                            }
+                        }
                     }
                 }
-                // the first TWO slots of the home bucket in one 256-bit load: buckets fill front to back, so most keys
-                // that are not in slot 0 are in slot 1 and need no second (dependent) round trip to L2
-#pragma unroll
-                for (int u = 0; u < RP_GROUP; u++)
-                    if (key[u] != 0ull) {
-                        if (probe_home(t.g, key[u], pr[u])) {
-                            unsigned long long w0, w1;
-                            ld_slot_pair(&t.slots[pr[u].base + pr[u].off], cur[u], w0, cur1[u], w1);
-                        } else { key[u] = 0ull; atomicExch(t.error, 2); }
-                    }
-#pragma unroll
-                for (int u = 0; u < RP_GROUP; u++)
-                    if (key[u] != 0ull) {
-                        if (cur[u] != key[u] && cur[u] != 0ull) {      // slot 0 holds another key: go on from slot 1
-                            probe_next(t.g, pr[u]);
-                            cur[u] = cur1[u];
-                        }
-                        Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
-                        if (sl) atomicAdd(&sl->val, cnt[u]);
-                    }
                 __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
                                 // and every later log load / probe is issued once per lane subset
             }
@@ -664,14 +761,13 @@ static_assert(RP_CHUNK % RF_THREADS == 0, "chunk = whole rounds of the CTA");
 constexpr unsigned RF_MAX_SPLIT = RF_THREADS;       // table partitions per coarse bin: one counter per thread
 
 __global__ void __launch_bounds__(RF_THREADS, 4)
-k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
+k_log_refine(const LogEntry* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned ncoarse, const unsigned long long* __restrict__ chunk_start,
-             unsigned long long* __restrict__ out_keys, unsigned int* __restrict__ out_cursor, unsigned out_cap,
+             LogEntry* __restrict__ out_keys, unsigned int* __restrict__ out_cursor, unsigned out_cap,
              unsigned nfine, unsigned fine0, unsigned nfine_global, int* error, TableView t) {
     unsigned claimed = 0;
     // a chunk belongs to ONE coarse bin, so only its f = nfine / ncoarse fine bins can occur: all bookkeeping is per f
-    __shared__ unsigned long long skey[RP_CHUNK];
-    __shared__ unsigned short sbin[RP_CHUNK];
+    __shared__ LogEntry sent[RP_CHUNK];
     __shared__ unsigned int cnt[RF_MAX_SPLIT], delta[RF_MAX_SPLIT], off[RF_MAX_SPLIT];
     __shared__ unsigned wtot[RF_THREADS / 32];
     __shared__ unsigned s_total;
@@ -686,24 +782,25 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
         while (chunk_start[q + 1] <= w) q++;                       // segments in plan order: (coarse bin, source)
         const unsigned lb = q / nsrc, src = q % nsrc, seg = src * ncoarse + lb;
         const unsigned n = min(cursor[seg], cap);
-        const unsigned long long* base = keys + (unsigned long long)seg * cap;
+        const LogEntry* base = keys + (unsigned long long)seg * cap;
         const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
         const unsigned first = fine0 + lb * f;                     // global index of this coarse bin's first partition
-        // ---- A: fine bin (inside the coarse bin) and rank of every key
-        unsigned long long key[RF_PER_THREAD];
+        // ---- A: fine bin (inside the coarse bin) and rank of every entry
+        LogEntry ent[RF_PER_THREAD];
         unsigned meta[RF_PER_THREAD];                              // bin << 12 | rank, ~0 = no entry
 #pragma unroll
         for (int j = 0; j < RF_PER_THREAD; j++) {
             const unsigned i = i0 + j * RF_THREADS + tid;
-            key[j] = i < n ? __ldcs(base + i) : 0ull;
+            ent[j].meta = 0u;
+            if (i < n) ent[j] = ld_entry(base + i);
         }
 #pragma unroll
         for (int j = 0; j < RF_PER_THREAD; j++) {
             meta[j] = 0xFFFFFFFFu;
-            if (key[j] != 0ull) {
-                const unsigned bin = hash_part(mix64(key[j]), nfine_global) - first;
+            if (ent[j].meta != 0u) {
+                const unsigned bin = home_part(ent[j].h, nfine_global) - first;
                 if (bin < f) meta[j] = (bin << 12) | atomicAdd(&cnt[bin], 1u);
-                else atomicExch(error, 2);                         // a key that does not belong to this coarse bin
+                else atomicExch(error, 2);                         // an entry that does not belong to this coarse bin
             }
         }
         __syncthreads();
@@ -730,16 +827,16 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
         for (int j = 0; j < RF_PER_THREAD; j++)
             if (meta[j] != 0xFFFFFFFFu) {
                 const unsigned bin = meta[j] >> 12, idx = off[bin] + (meta[j] & 0xFFFu);
-                skey[idx] = key[j];
-                sbin[idx] = (unsigned short)bin;
+                sent[idx] = ent[j];
             }
         __syncthreads();
         // ---- W: stream the sorted chunk out: runs of hundreds of entries per fine bin
         const unsigned total = s_total;
         for (unsigned i = tid; i < total; i += RF_THREADS) {
-            const unsigned bin = sbin[i], pos = delta[bin] + i;
-            if (pos < out_cap) out_keys[(unsigned long long)(lb * f + bin) * out_cap + pos] = skey[i];
-            else if (t.slots) table_update<false>(t, skey[i], 1u, claimed);      // fine bin full (a repeat k-mer): count directly
+            const LogEntry e = sent[i];
+            const unsigned bin = home_part(e.h, nfine_global) - first, pos = delta[bin] + i;
+            if (pos < out_cap) out_keys[(unsigned long long)(lb * f + bin) * out_cap + pos] = e;
+            else if (t.slots) le_apply(t, e, 1u, claimed);                       // fine bin full (a repeat k-mer): count directly
             else atomicExch(error, 3);
         }
         __syncthreads();
@@ -753,8 +850,8 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
 size_t log_refine_plan_words(unsigned nsrc, unsigned ncoarse) { return (size_t)nsrc * ncoarse + 2; }
 unsigned log_refine_max_split() { return RF_MAX_SPLIT; }
 
-cudaError_t launch_log_refine(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
-                              unsigned ncoarse, unsigned long long* d_chunk_start, unsigned long long* d_out_keys,
+cudaError_t launch_log_refine(const LogEntry* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                              unsigned ncoarse, unsigned long long* d_chunk_start, LogEntry* d_out_keys,
                               unsigned int* d_out_cursor, unsigned out_cap, unsigned nfine, unsigned fine0,
                               unsigned nfine_global, int* d_error, TableView t, int sm_count, cudaStream_t s) {
     TimedLaunch timed("k_log_refine", s);
@@ -774,7 +871,7 @@ size_t log_replay_plan_words(unsigned nsrc, unsigned nlocal, unsigned G) {
     return (size_t)replay_per_group(nlocal, G) * G * nsrc + 1 + G;
 }
 
-cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+cudaError_t launch_log_replay(const LogEntry* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned groups,
                               unsigned long long* d_chunk_start, unsigned long long* d_hpoly, TableView t, int prefetch,
                               int sm_count, cudaStream_t s) {
@@ -788,7 +885,7 @@ cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned i
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const bool fold = (prefetch & 2) != 0;             // bit 1 of the flags word: fold duplicates per chunk
-    const size_t dyn = fold ? (size_t)RP_FOLD * 12 : 0;
+    const size_t dyn = fold ? (size_t)RP_FOLD * 20 : 0;
     const void* kern = fold ? (const void*)k_log_replay<true> : (const void*)k_log_replay<false>;
     int grid = max_resident_ctas(kern, RP_THREADS, dyn, -1);
     if (grid <= 0) grid = sm_count;
@@ -817,10 +914,12 @@ k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ val
         unsigned long long key = make_key(p0, p1);
         const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
         if (IS_MAX) {          // label table: (forward k-mer, bundle index + 1) -> the field of its orientation
-            if (table_label_max(t, kr < key ? kr : key, kr < key, vals[i])) claimed++;
+            const bool rc = kr < key;
+            if (rc) key = kr;
+            if (table_label_max(t, key, key_home_packed(key, k), rc, vals[i])) claimed++;
         } else {
             if (canonical) key = kr < key ? kr : key;
-            table_update<false>(t, key, vals[i], claimed);
+            table_add(t, key, key_home_packed(key, k), vals[i], claimed);
         }
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
@@ -846,36 +945,16 @@ k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
         if (key == 0ull) continue;
         if (is_label) {        // both orientations' labels move with the key
-            if (s.z && table_label_max(to, key, false, s.z)) claimed++;
-            if (s.w && table_label_max(to, key, true, s.w)) claimed++;
+            const unsigned aux = s.w & AUX_LABEL_MASK;
+            const unsigned hj = key_home_packed(key, to.g.k);
+            if (s.z && table_label_max(to, key, hj, false, s.z)) claimed++;
+            if (aux && table_label_max(to, key, hj, true, aux)) claimed++;
         } else if (s.z >= min_val) {
-            table_update<false>(to, key, s.z, claimed);
+            table_add(to, key, key_home_packed(key, to.g.k), s.z, claimed);
         }
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
-}
-
-// direct-mapped cache fill: every live slot with val >= min_val goes to hot[mulhi(hash, hot_cap)] if that place is free
-__global__ void __launch_bounds__(256)
-k_hot_fill(const Slot* __restrict__ from, uint64_t from_cap, Slot* hot, uint64_t hot_cap, uint32_t min_val, uint32_t max_val) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
-        const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key == 0ull || s.z < min_val || s.z > max_val) continue;
-        Slot* h = &hot[__umul64hi(mix64(key), hot_cap)];
-        if (atomicCAS(&h->key, 0ull, key) == 0ull) h->val = s.z;
-    }
-}
-
-cudaError_t launch_hot_fill(const Slot* from, uint64_t from_cap, Slot* hot, uint64_t hot_cap, uint32_t min_val,
-                            uint32_t max_val, cudaStream_t s) {
-    TimedLaunch timed("k_hot_fill", s);
-    if (from_cap == 0 || hot_cap == 0) return cudaSuccess;
-    uint64_t blocks = (from_cap + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    k_hot_fill<<<(int)blocks, 256, 0, s>>>(from, from_cap, hot, hot_cap, min_val, max_val);
-    return cudaGetLastError();
 }
 
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
@@ -885,558 +964,6 @@ cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int
     uint64_t blocks = (from_cap + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     k_rehash<<<(int)blocks, 256, 0, s>>>(from, from_cap, to, is_label, min_val);
-    return cudaGetLastError();
-}
-
-// =========================================================================================================
-// Per-read machinery shared by stats and assign.  GS = group size: 32 (one warp per read, buffers in shared
-// memory) or LONG_THREADS (one CTA per read, buffers in global scratch).
-// =========================================================================================================
-template <int GS> __device__ __forceinline__ void gsync() {
-    if (GS == 32) __syncwarp(); else __syncthreads();
-}
-
-// planes for chunks 0..nch (chunk nch and everything past L is invalid)
-template <int GS>
-__device__ __forceinline__ void pack_read_planes(const uint8_t* __restrict__ seq, int L, int nch, uint32_t* P0,
-                                                 uint32_t* P1, uint32_t* PB, int gtid) {
-    const int lane = gtid & 31, w = gtid >> 5;
-    for (int c = w; c <= nch; c += GS / 32) {
-        const int pos = c * 32 + lane;
-        const unsigned ch = pos < L ? seq[pos] : (unsigned)'\n';
-        const unsigned code = base_code(ch);
-        const unsigned b0 = __ballot_sync(FULL, code & 1u);
-        const unsigned b1 = __ballot_sync(FULL, code >> 1);
-        const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
-        if (lane == 0) { P0[c] = b0; P1[c] = b1; PB[c] = bb; }
-    }
-}
-
-// ascending bitonic sort of buf[0..n2), n2 a power of two
-template <int GS, typename T>
-__device__ __forceinline__ void bitonic_sort(T* buf, unsigned n2, int gtid) {
-    for (unsigned kk = 2; kk <= n2; kk <<= 1) {
-        for (unsigned j = kk >> 1; j > 0; j >>= 1) {
-            for (unsigned i = gtid; i < n2; i += GS) {
-                const unsigned ixj = i ^ j;
-                if (ixj > i) {
-                    const T x = buf[i], y = buf[ixj];
-                    const bool up = (i & kk) == 0;
-                    if ((x > y) == up) { buf[i] = y; buf[ixj] = x; }
-                }
-            }
-            gsync<GS>();
-        }
-    }
-}
-
-__device__ __forceinline__ unsigned next_pow2(unsigned n) {
-    unsigned p = 1;
-    while (p < n) p <<= 1;
-    return p;
-}
-
-template <int GS>
-__device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v, unsigned long long* red, int gtid) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    if (GS == 32) return v;
-    gsync<GS>();
-    if ((gtid & 31) == 0) red[gtid >> 5] = v;
-    gsync<GS>();
-    unsigned long long tot = 0;
-    for (int w = 0; w < GS / 32; w++) tot += red[w];
-    gsync<GS>();
-    return tot;
-}
-
-// Median of n <= PR_MAXWIN u32 values held in shared memory, by one warp, WITHOUT sorting: a bisection on the VALUE
-// between the warp minimum and maximum (coverage values of one read sit in a narrow band, so a handful of rounds),
-// each round one compare per element and one redux.sync.  PER = elements per lane = ceil(n / 32), a template
-// parameter so that a 100-bp read (76 windows, PER = 3) does not pay for the 256-window maximum.  Returns
-// median_coverage() of fastaToKmerCoverageStats.cpp:337-347: odd n -> the middle element, even n -> the (wrapping)
-// u32 mean of the two middle elements.
-template <int PER>
-__device__ __forceinline__ uint32_t warp_median_per(const uint32_t* __restrict__ v, int n, int lane) {
-    unsigned x[PER];
-    const bool tail_live = (PER - 1) * 32 + lane < n;      // only the last element of a lane can lie past n
-    unsigned mn = 0xFFFFFFFFu, mx = 0u;
-#pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const bool live = i < PER - 1 || tail_live;
-        x[i] = live ? v[i * 32 + lane] : 0u;
-        if (live) { mn = min(mn, x[i]); mx = max(mx, x[i]); }
-    }
-    unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
-    const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
-    // smallest value with at least k1 + 1 elements <= it = the element of rank k1
-    while (lo < hi) {
-        const unsigned mid = lo + ((hi - lo) >> 1);
-        unsigned cnt = 0;
-#pragma unroll
-        for (int i = 0; i < PER; i++) cnt += ((i < PER - 1 || tail_live) && x[i] <= mid) ? 1u : 0u;
-        cnt = __reduce_add_sync(FULL, cnt);
-        if (cnt >= k1 + 1u) hi = mid; else lo = mid + 1u;
-    }
-    const unsigned x1 = lo;
-    if (k1 == k2) return x1;
-    unsigned le = 0, nxt = 0xFFFFFFFFu;
-#pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const bool live = i < PER - 1 || tail_live;
-        le += (live && x[i] <= x1) ? 1u : 0u;
-        if (live && x[i] > x1) nxt = min(nxt, x[i]);
-    }
-    le = __reduce_add_sync(FULL, le);
-    nxt = __reduce_min_sync(FULL, nxt);
-    const unsigned x2 = le >= k2 + 1u ? x1 : nxt;          // the element of rank k2 = k1 + 1
-    return (uint32_t)(x1 + x2) / 2u;
-}
-
-__device__ __forceinline__ uint32_t warp_median_u32(const uint32_t* __restrict__ v, int n, int lane) {
-    static_assert(PR_MAXWIN == 256, "dispatch below covers 1..8 elements per lane");
-    switch ((n + 31) >> 5) {           // exact: warp_median_per assumes only a lane's LAST element can lie past n
-        case 0: case 1: return warp_median_per<1>(v, n, lane);
-        case 2: return warp_median_per<2>(v, n, lane);
-        case 3: return warp_median_per<3>(v, n, lane);
-        case 4: return warp_median_per<4>(v, n, lane);
-        case 5: return warp_median_per<5>(v, n, lane);
-        case 6: return warp_median_per<6>(v, n, lane);
-        case 7: return warp_median_per<7>(v, n, lane);
-        default: return warp_median_per<8>(v, n, lane);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// coverage statistics of one read (fastaToKmerCoverageStats.cpp:300-402)
-// ---------------------------------------------------------------------------------------------------------
-template <int GS>
-__device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, int L, int k, int canonical,
-                                               const Slot* __restrict__ slots, Geo geo, uint32_t* P0,
-                                               uint32_t* P1, uint32_t* PB, uint32_t* cov, float* sq,
-                                               unsigned long long* red, uint32_t* per_kmer, uint32_t& median,
-                                               float& mean, float& stdev, int gtid) {
-    const int nwin = L >= k ? L - k + 1 : 0;
-    if (nwin == 0) {   // S6: shorter than k -> empty vector; S7-S9 on n = 0: 0, 0, sqrt(0/-1) = -0
-        median = 0; mean = 0.0f; stdev = __int_as_float(0x80000000);
-        return;
-    }
-    const unsigned mk = kmask(k);
-    const int nch = (L + 31) >> 5;
-    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
-    gsync<GS>();
-
-    unsigned long long part = 0;
-    for (int pb = 0; pb < nwin; pb += GS) {     // every lane runs every iteration: table_lookup is warp-convergent
-        const int p = pb + gtid;
-        const bool live = p < nwin;
-        bool ok = false;
-        unsigned long long key = 0ull;
-        if (live) {
-            const int c = p >> 5, o = p & 31;
-            const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
-            if (!bad) {
-                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-                key = make_key(f0, f1);
-                if (canonical) {
-                    const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
-                    key = kr < key ? kr : key;
-                }
-                ok = true;
-            }
-        }
-        unsigned v = table_lookup(slots, geo, key, ok);
-        if (live) {
-            if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
-            cov[p] = v;
-            if (per_kmer) per_kmer[p] = v;
-            part += v;
-        }
-    }
-    const unsigned long long sum = group_sum_u64<GS>(part, red, gtid);   // `long` sum, exact
-    const float avg = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));
-    gsync<GS>();
-    for (int p = gtid; p < nwin; p += GS) {
-        const float d = __fsub_rn(__uint2float_rn(cov[p]), avg);
-        sq[p] = __fmul_rn(d, d);               // two roundings, no FMA (x86-64 -O2 without -march)
-    }
-    gsync<GS>();
-    float sd;
-    if (nwin == 1) {
-        sd = __int_as_float(X86_DEFAULT_NAN_BITS);   // 0/0 on SSE = default NaN with the sign bit set ("-nan")
-    } else {
-        float acc = 0.0f;
-        if (gtid == 0) {
-            // strict read order; four squares per load where sq is 16-B aligned (always on the warp path)
-            const float4* sq4 = reinterpret_cast<const float4*>(sq);
-            int p = 0;
-            for (; (reinterpret_cast<unsigned long long>(sq) & 15ull) == 0ull && p + 4 <= nwin; p += 4) {
-                const float4 q = sq4[p >> 2];
-                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q.x), q.y), q.z), q.w);
-            }
-            for (; p < nwin; p++) acc = __fadd_rn(acc, sq[p]);
-            acc = __fsqrt_rn(__fdiv_rn(acc, __int2float_rn(nwin - 1)));
-        }
-        sd = acc;
-    }
-    // median: odd -> middle, even -> u32 (wrapping) mean of the two middles
-    if (GS == 32) {
-        median = warp_median_u32(cov, nwin, gtid);         // selection, no sort
-    } else {
-        const unsigned n2 = next_pow2((unsigned)nwin);
-        for (unsigned p = nwin + gtid; p < n2; p += GS) cov[p] = 0xFFFFFFFFu;
-        gsync<GS>();
-        bitonic_sort<GS, uint32_t>(cov, n2, gtid);
-        median = (nwin & 1) ? cov[nwin / 2] : (uint32_t)(cov[(nwin - 1) / 2] + cov[nwin / 2]) / 2u;
-    }
-    mean = avg;
-    stdev = sd;    // meaningful in gtid 0 only
-}
-
-struct alignas(16) PerReadSmem {
-    uint32_t p0[PR_WARPS][PR_MAXCH];
-    uint32_t p1[PR_WARPS][PR_MAXCH];
-    uint32_t pb[PR_WARPS][PR_MAXCH];
-    uint32_t a[PR_WARPS][2 * PR_MAXWIN];    // stats: cov[PR_MAXWIN] + sq[PR_MAXWIN]; assign: hits[2*PR_MAXWIN]
-    unsigned int nhits[PR_WARPS];
-};
-
-__global__ void __launch_bounds__(PR_WARPS * 32, 6)
-k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
-            int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
-            float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll) {
-    __shared__ PerReadSmem sm;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t r = (uint64_t)blockIdx.x * PR_WARPS + w;
-    if (r >= nreads) return;
-    const uint64_t o0 = offs[r], o1 = offs[r + 1];
-    const int L = (int)(o1 - o0 - 1);            // the record's last byte is its '\n' terminator
-    const int nwin = L >= k ? L - k + 1 : 0;
-    if (nwin > PR_MAXWIN) {
-        if (lane == 0) {
-            const unsigned slot = atomicAdd(ll.count, 1u);
-            ll.idx[slot] = (unsigned)r;
-            atomicMax(ll.max_win, (unsigned)nwin);
-        }
-        return;
-    }
-    uint32_t med; float mu, sd;
-    read_cov_stats<32>(recs + (o0 - rec_base), L, k, canonical, slots, geo, sm.p0[w], sm.p1[w], sm.pb[w], sm.a[w],
-                       reinterpret_cast<float*>(sm.a[w] + PR_MAXWIN), nullptr,
-                       per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, lane);
-    if (lane == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
-}
-
-cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                             int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s) {
-    TimedLaunch timed("k_cov_stats", s);
-    if (nreads == 0) return cudaSuccess;
-    const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
-    k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
-                                                           d_median, d_mean, d_stdev, d_per_kmer, ll);
-    return cudaGetLastError();
-}
-
-// scratch layout per CTA of the long path: planes 3*(nch+1) u32 | cov n2 u32 | sq n2 f32
-__host__ __device__ static inline size_t long_nch(unsigned max_win, int k) { return ((size_t)max_win + k - 1 + 31) / 32 + 2; }
-__host__ __device__ static inline size_t pow2_ge(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
-__host__ __device__ static inline size_t long_scratch_words(unsigned max_win, int k, int mult) {
-    return 3 * long_nch(max_win, k) + (size_t)2 * pow2_ge((size_t)mult * max_win);
-}
-
-// The CTA-per-read kernels run in one of two ways.  Host-driven (the host-buffer entry points, which synchronise
-// anyway): the host has read {count, max_win}, sized the scratch and passes them.  Device-driven (the *_dev entry
-// points, which must not synchronise -- a host stall would leave the GPU idle): the kernel is launched unconditionally
-// behind the warp-path kernel, reads {count, max_win} from `hdr` itself, lays the fixed scratch budget out and leaves
-// at once when there is no long read.  A read too long for the budget raises error 4 instead of a wrong answer.
-struct LongPlan { unsigned n_long, max_win, stride; size_t words_per_cta; };
-__device__ __forceinline__ bool long_plan(const unsigned int* hdr, unsigned n_long, unsigned max_win, size_t words_per_cta,
-                                          unsigned long long scratch_words, int k, int mult, int* error, LongPlan& pl) {
-    pl.n_long = n_long; pl.max_win = max_win; pl.words_per_cta = words_per_cta; pl.stride = gridDim.x;
-    if (!hdr) return true;
-    pl.n_long = hdr[0]; pl.max_win = hdr[1];
-    if (pl.n_long == 0) return false;
-    pl.words_per_cta = long_scratch_words(pl.max_win, k, mult);
-    const unsigned long long fit = scratch_words / pl.words_per_cta;
-    if (fit == 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(error, 4);
-        return false;
-    }
-    pl.stride = (unsigned)min((unsigned long long)gridDim.x, fit);
-    return blockIdx.x < pl.stride;
-}
-size_t cov_stats_long_scratch_bytes(unsigned max_win, int k, int nctas) {
-    return long_scratch_words(max_win, k, 1) * 4 * (size_t)nctas;
-}
-size_t assign_long_scratch_bytes(unsigned max_win, int k, int nctas) {
-    return long_scratch_words(max_win, k, 2) * 4 * (size_t)nctas;
-}
-
-__global__ void __launch_bounds__(LONG_THREADS)
-k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k,
-                 int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
-                 float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer,
-                 const unsigned int* __restrict__ long_idx, unsigned int n_long_h, unsigned int max_win_h,
-                 uint32_t* scratch, size_t words_per_cta_h, const unsigned int* __restrict__ hdr,
-                 unsigned long long scratch_words, int* error) {
-    __shared__ unsigned long long red[LONG_THREADS / 32];
-    LongPlan pl;
-    if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 1, error, pl)) return;
-    const unsigned n_long = pl.n_long, max_win = pl.max_win;
-    const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
-    size_t n2max = 1; while (n2max < max_win) n2max <<= 1;
-    uint32_t* base = scratch + (size_t)blockIdx.x * pl.words_per_cta;
-    uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
-    uint32_t* cov = PB + nchw; float* sq = reinterpret_cast<float*>(cov + n2max);
-    for (unsigned i = blockIdx.x; i < n_long; i += pl.stride) {
-        const uint64_t r = long_idx[i];
-        const uint64_t o0 = offs[r], o1 = offs[r + 1];
-        const int L = (int)(o1 - o0 - 1);
-        uint32_t med; float mu, sd;
-        read_cov_stats<LONG_THREADS>(recs + (o0 - rec_base), L, k, canonical, slots, geo, P0, P1, PB, cov, sq, red,
-                                     per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, threadIdx.x);
-        if (threadIdx.x == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
-        __syncthreads();
-    }
-}
-
-cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
-                                  const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
-                                  uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
-                                  unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
-    TimedLaunch timed("k_cov_stats_long", s);
-    if (n_long == 0) return cudaSuccess;
-    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
-                                                    d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
-                                                    (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1), nullptr, 0,
-                                                    nullptr);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k,
-                                       int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                                       float* d_stdev, uint32_t* d_per_kmer, LongList ll, void* d_scratch,
-                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s) {
-    TimedLaunch timed("k_cov_stats_long", s);
-    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
-                                                    d_stdev, d_per_kmer, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
-                                                    scratch_bytes / 4, d_error);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// read -> bundle vote of one read (ReadsToTranscripts.cc:216-274)
-// ---------------------------------------------------------------------------------------------------------
-// entropy_ok is indexed [nG][nA][nT] (26^3 bytes); nC is implied for an all-ACGT window.
-__device__ __forceinline__ bool window_entropy_ok(const uint8_t* __restrict__ lut, unsigned f0, unsigned f1, unsigned mk,
-                                                  bool rc) {
-    // codes: A=00 C=01 G=10 T=11 (bit1 = plane1, bit0 = plane0)
-    const int nG = __popc(f1 & ~f0 & mk), nA = __popc(~f1 & ~f0 & mk), nT = __popc(f1 & f0 & mk);
-    const int nC = __popc(~f1 & f0 & mk);
-    // the reference evaluates the reverse-complemented string in the same G,A,T,C slot order:
-    // its counts are (nC, nT, nA, nG) of the forward window
-    return rc ? lut[(nC * 26 + nT) * 26 + nA] != 0 : lut[(nG * 26 + nA) * 26 + nT] != 0;
-}
-
-template <int GS>
-__device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int L, int k, int strand,
-                                            const Slot* __restrict__ slots, Geo geo,
-                                            const uint8_t* __restrict__ lut, uint32_t* P0, uint32_t* P1, uint32_t* PB,
-                                            int32_t* hits, unsigned int* nhits_p, int32_t& best, int32_t& score,
-                                            int32_t& pct, int gtid) {
-    const int nwin = L - k + 1;        // num_kmer_pos, may be <= 0
-    best = -1; score = 0;
-    if (nwin <= 0) { pct = 0; return; }
-    const unsigned mk = kmask(k);
-    const int nch = (L + 31) >> 5;
-    if (gtid == 0) *nhits_p = 0;
-    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
-    gsync<GS>();
-    unsigned nh = 0;                                // GS == 32: hits appended so far (warp-uniform)
-    for (int pb = 0; pb < nwin; pb += GS) {         // every lane runs every iteration: table_lookup is warp-convergent
-        const int p = pb + gtid;
-        bool do_f = false, do_r = false, is_rc = false, pal = false;
-        unsigned long long key = 0ull;
-        if (p < nwin) {
-            const int c = p >> 5, o = p & 31;
-            const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
-            if (!bad) {                     // a window with a non-ACGT character can never equal a table k-mer
-                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-                do_f = window_entropy_ok(lut, f0, f1, mk, false);
-                do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
-                const unsigned long long kf = make_key(f0, f1), kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
-                is_rc = kr < kf; pal = kr == kf;
-                key = is_rc ? kr : kf;
-            }
-        }
-        // ONE probe answers both passes of the reference (forward window, then reverse-complemented window): the slot
-        // of the canonical key holds the label of the bundle k-mer equal to the key (val) and of the bundle k-mer whose
-        // reverse complement is the key (aux).  A palindrome (even k only) is its own reverse complement.
-        const uint2 v = table_lookup2(slots, geo, key, do_f || do_r);
-        const unsigned vf = do_f ? (is_rc ? v.y : v.x) : 0u;
-        const unsigned vr = do_r ? ((is_rc || pal) ? v.x : v.y) : 0u;
-        if (GS == 32) {
-            const unsigned lt = (1u << gtid) - 1u;
-            const unsigned mf = __ballot_sync(FULL, vf != 0u), mr = __ballot_sync(FULL, vr != 0u);
-            if (vf) hits[nh + __popc(mf & lt)] = (int32_t)vf - 1;
-            nh += __popc(mf);
-            if (vr) hits[nh + __popc(mr & lt)] = (int32_t)vr - 1;
-            nh += __popc(mr);
-        } else {
-            if (vf) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vf - 1;
-            if (vr) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vr - 1;
-        }
-    }
-    gsync<GS>();
-    const int n = GS == 32 ? (int)nh : (int)*nhits_p;
-    int b = -1, sc = 0;
-    if (n >= 2 && GS == 32) {
-        // The reference sorts the hits and scans the runs (ReadsToTranscripts.cc:253-268): a label with m hits scores
-        // m-1, the largest label m-2, strict '>' while ascending => ties go to the smaller label.  The same result
-        // without a sort: walk the DISTINCT labels in ascending order (almost always one or two), one warp min and
-        // one warp count per label.
-        int last = -1;
-        for (int p = gtid; p < n; p += 32) last = max(last, hits[p]);
-        last = __reduce_max_sync(FULL, last);
-        int cur = -1;
-        while (true) {
-            int mn = 0x7FFFFFFF;
-            for (int p = gtid; p < n; p += 32) { const int h = hits[p]; if (h > cur) mn = min(mn, h); }
-            const int L = __reduce_min_sync(FULL, mn);
-            if (L == 0x7FFFFFFF) break;
-            unsigned m = 0;
-            for (int p = gtid; p < n; p += 32) m += hits[p] == L ? 1u : 0u;
-            m = __reduce_add_sync(FULL, m);
-            const int s = (int)m - 1 - (L == last ? 1 : 0);
-            if (s > sc) { sc = s; b = L; }
-            cur = L;
-        }
-        if (sc <= 0) { b = -1; sc = 0; }
-    } else if (n >= 2) {
-        const unsigned n2 = next_pow2((unsigned)n);
-        for (unsigned p = n + gtid; p < n2; p += GS) hits[p] = 0x7FFFFFFF;
-        gsync<GS>();
-        bitonic_sort<GS, int32_t>(hits, n2, gtid);
-        // a label with m hits scores m-1, the last (largest) label m-2; strict '>' while scanning ascending
-        // labels => ties go to the smaller label (ReadsToTranscripts.cc:253-268)
-        const int32_t last = hits[n - 1];
-        for (int i = gtid; i < n; i += GS) {
-            const int32_t h = hits[i];
-            if (i == n - 1 || hits[i + 1] != h) {        // end of a run: multiplicity by lower_bound
-                int lo = 0, hi = i;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid] < h) lo = mid + 1; else hi = mid; }
-                const int m = i + 1 - lo;
-                const int s = m - 1 - (h == last ? 1 : 0);
-                if (s > sc || (s == sc && s > 0 && h < b)) { sc = s; b = h; }
-            }
-        }
-        // group arg-max (score desc, label asc)
-        for (int o = 16; o > 0; o >>= 1) {
-            const int os = __shfl_xor_sync(FULL, sc, o), ob = __shfl_xor_sync(FULL, b, o);
-            if (os > sc || (os == sc && os > 0 && ob < b)) { sc = os; b = ob; }
-        }
-        if (GS > 32) {
-            __shared__ int wsc[LONG_THREADS / 32], wb[LONG_THREADS / 32];
-            gsync<GS>();
-            if ((gtid & 31) == 0) { wsc[gtid >> 5] = sc; wb[gtid >> 5] = b; }
-            gsync<GS>();
-            sc = wsc[0]; b = wb[0];
-            for (int w = 1; w < GS / 32; w++)
-                if (wsc[w] > sc || (wsc[w] == sc && wsc[w] > 0 && wb[w] < b)) { sc = wsc[w]; b = wb[w]; }
-            gsync<GS>();
-        }
-        if (sc <= 0) { b = -1; sc = 0; }
-    }
-    best = b; score = sc;
-    // pct = (int)((float)max / num_kmer_pos * 100 + 0.5): fp32 divide, fp32 multiply, double add, truncate
-    const float q = __fmul_rn(__fdiv_rn(__int2float_rn(sc), __int2float_rn(nwin)), 100.0f);
-    pct = (int)__dadd_rn((double)q, 0.5);
-}
-
-__global__ void __launch_bounds__(PR_WARPS * 32)
-k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int k,
-         int strand, const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut,
-         int32_t* __restrict__ best, int32_t* __restrict__ pct, int32_t* __restrict__ score, LongList ll) {
-    __shared__ PerReadSmem sm;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t r = (uint64_t)blockIdx.x * PR_WARPS + w;
-    if (r >= nreads) return;
-    const uint64_t o0 = offs[r], o1 = offs[r + 1];
-    const int L = (int)(o1 - o0 - 1);
-    const int nwin = L - k + 1;
-    if (nwin > PR_MAXWIN) {
-        if (lane == 0) {
-            const unsigned slot = atomicAdd(ll.count, 1u);
-            ll.idx[slot] = (unsigned)r;
-            atomicMax(ll.max_win, (unsigned)nwin);
-        }
-        return;
-    }
-    int32_t b, sc, pc;
-    read_assign<32>(recs + (o0 - rec_base), L, k, strand, slots, geo, lut, sm.p0[w], sm.p1[w], sm.pb[w],
-                    reinterpret_cast<int32_t*>(sm.a[w]), &sm.nhits[w], b, sc, pc, lane);
-    if (lane == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
-}
-
-cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                          int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
-                          int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s) {
-    TimedLaunch timed("k_assign", s);
-    if (nreads == 0) return cudaSuccess;
-    const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
-    k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, geo,
-                                                        d_entropy_ok, d_best, d_pct, d_score, ll);
-    return cudaGetLastError();
-}
-
-__global__ void __launch_bounds__(LONG_THREADS)
-k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k, int strand,
-              const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut, int32_t* __restrict__ best,
-              int32_t* __restrict__ pct, int32_t* __restrict__ score, const unsigned int* __restrict__ long_idx,
-              unsigned int n_long_h, unsigned int max_win_h, uint32_t* scratch, size_t words_per_cta_h,
-              const unsigned int* __restrict__ hdr, unsigned long long scratch_words, int* error) {
-    __shared__ unsigned int nhits;
-    LongPlan pl;
-    if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 2, error, pl)) return;
-    const unsigned n_long = pl.n_long, max_win = pl.max_win;
-    const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
-    uint32_t* base = scratch + (size_t)blockIdx.x * pl.words_per_cta;
-    uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
-    int32_t* hits = reinterpret_cast<int32_t*>(PB + nchw);
-    for (unsigned i = blockIdx.x; i < n_long; i += pl.stride) {
-        const uint64_t r = long_idx[i];
-        const uint64_t o0 = offs[r], o1 = offs[r + 1];
-        const int L = (int)(o1 - o0 - 1);
-        int32_t b, sc, pc;
-        read_assign<LONG_THREADS>(recs + (o0 - rec_base), L, k, strand, slots, geo, lut, P0, P1, PB, hits, &nhits, b, sc,
-                                  pc, threadIdx.x);
-        if (threadIdx.x == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
-        __syncthreads();
-    }
-}
-
-cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
-                               const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
-                               int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
-                               unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
-    TimedLaunch timed("k_assign_long", s);
-    if (n_long == 0) return cudaSuccess;
-    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
-                                                 d_pct, d_score, d_long_idx, n_long, max_win, (uint32_t*)d_scratch,
-                                                 long_scratch_words(max_win, k, 2), nullptr, 0, nullptr);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
-                                    const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
-                                    int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
-                                    int* d_error, int nctas, cudaStream_t s) {
-    TimedLaunch timed("k_assign_long", s);
-    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
-                                                 d_pct, d_score, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
-                                                 scratch_bytes / 4, d_error);
     return cudaGetLastError();
 }
 

@@ -80,7 +80,7 @@ TG_HD unsigned mmer_hash(unsigned f0, unsigned f1, int m) {
 TG_HD unsigned ord_left(unsigned x, unsigned pos) { return (x & ~ORD_POS_MASK) | pos; }
 TG_HD unsigned ord_right(unsigned x, unsigned pos) { return (x & ~ORD_POS_MASK) | (ORD_POS_MASK - pos); }
 
-// home of a table key given as k-bit planes (SLOW path: 8 m-mer hashes; loaders, rehash, replay of plain keys)
+// home of a table key given as k-bit planes (SLOW path: 8 m-mer hashes; loaders, rehash, long reads)
 TG_HD void key_home(unsigned p0, unsigned p1, int k, unsigned& h, unsigned& j) {
     const int m = mm_len(k), w = mm_win(k);
     const unsigned mm = bits_mask(m);
@@ -94,10 +94,13 @@ TG_HD void key_home(unsigned p0, unsigned p1, int k, unsigned& h, unsigned& j) {
     j = best & ORD_POS_MASK;
 }
 
-// partition and bucket of a home hash
-TG_HD unsigned home_part(unsigned h, unsigned nparts) { return (unsigned)(((unsigned long long)h * nparts) >> 32); }
-TG_HD unsigned home_bucket(unsigned h, unsigned nbuckets) {
-    unsigned x = h * 0xB5297A4Du;
+// A home travels as ONE word: hj = (hash & ~7) | slot.  Partition and bucket use the hash with its low three bits cleared,
+// so that every holder of an hj (log entries, queued walks) addresses exactly like the code that computed it.
+TG_HD unsigned pack_home(unsigned h, unsigned j) { return (h & ~7u) | j; }
+TG_HD unsigned home_slot(unsigned hj) { return hj & 7u; }
+TG_HD unsigned home_part(unsigned hj, unsigned nparts) { return (unsigned)(((unsigned long long)(hj & ~7u) * nparts) >> 32); }
+TG_HD unsigned home_bucket(unsigned hj, unsigned nbuckets) {
+    unsigned x = (hj & ~7u) * 0xB5297A4Du;
     x ^= x >> 15;
     x *= 0x68E31DA5u;
     x ^= x >> 14;

@@ -1,0 +1,835 @@
+// Per-read kernels of the Trinity k-mer hot path (sm_100a):
+//
+//   k_cov_stats[_long]    compute_kmer_coverage / median / mean / stDev   
+//   k_assign[_long]       ReadsToTranscripts per-read vote                (§8a R5, R7-R9)
+//
+// Warp path (reads up to PR_MAXWIN windows): one warp per read, and every lane owns a STRIP of PER consecutive windows
+// (PER = ceil(windows / 32)).  The front end is the same for both kernels:
+//   1. ballot transpose of the read into bit planes (shared memory);
+//   2. H pass: strand-symmetric hash of the m-mer at every position (one position per lane and round);
+//   3. per strip: sliding minimum over the PER + 7 hashes -> minimizer (leftmost and rightmost) of every window
+//      (tg_minimizer.cuh), canonical key, home slot = (bucket of the minimizer hash, slot = minimizer position);
+//   4. ONE 16-byte load per window from the home slot.  Windows that share a minimizer read neighbouring slots of one
+//      128-byte bucket, so the load instruction of the warp covers ~1/5 of the DRAM granules a key-hashed table needs.
+//   5. the few windows whose home slot holds another key with the DISPLACED flag are queued in shared memory and settled
+//      by a key-hashed walk afterwards, one queued window per lane, all walks in flight together -- instead of the whole
+//      warp waiting on a rare lane in every round.
+// Statistics then need the sequential fp32 sum of squares (the reference's evaluation order is observable in the last
+// bits, S9).  A warp keeps the coverage vectors of a BATCH of consecutive reads in its shared-memory arena and runs the
+// sequential sums of the whole batch at once, one read per lane: the 76 dependent adds of a 100-bp read are issued once
+// per batch instead of once per read.
+//
+// Long path (CTA per read, planes and buffers in global scratch): the slow lookup (home computed from the key alone).
+#include "tg_internal.h"
+
+namespace tg {
+
+namespace {
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int PR_HX = PR_MAXWIN + HOME_SLOTS;     // m-mer positions of the longest warp-path read
+constexpr int WQ = 32;                            // queued walks per warp (one ballot can add at most 32)
+}
+
+// =========================================================================================================
+// shared pieces
+// =========================================================================================================
+template <int GS> __device__ __forceinline__ void gsync() {
+    if (GS == 32) __syncwarp(); else __syncthreads();
+}
+
+// planes for chunks 0..nch (chunk nch and everything past L is invalid)
+template <int GS>
+__device__ __forceinline__ void pack_read_planes(const uint8_t* __restrict__ seq, int L, int nch, uint32_t* P0,
+                                                 uint32_t* P1, uint32_t* PB, int gtid) {
+    const int lane = gtid & 31, w = gtid >> 5;
+    for (int c = w; c <= nch; c += GS / 32) {
+        const int pos = c * 32 + lane;
+        const unsigned ch = pos < L ? seq[pos] : (unsigned)'\n';
+        const unsigned code = base_code(ch);
+        const unsigned b0 = __ballot_sync(FULL, code & 1u);
+        const unsigned b1 = __ballot_sync(FULL, code >> 1);
+        const unsigned bb = __ballot_sync(FULL, !base_valid(ch));
+        if (lane == 0) { P0[c] = b0; P1[c] = b1; PB[c] = bb; }
+    }
+}
+
+// ascending bitonic sort of buf[0..n2), n2 a power of two
+template <int GS, typename T>
+__device__ __forceinline__ void bitonic_sort(T* buf, unsigned n2, int gtid) {
+    for (unsigned kk = 2; kk <= n2; kk <<= 1) {
+        for (unsigned j = kk >> 1; j > 0; j >>= 1) {
+            for (unsigned i = gtid; i < n2; i += GS) {
+                const unsigned ixj = i ^ j;
+                if (ixj > i) {
+                    const T x = buf[i], y = buf[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((x > y) == up) { buf[i] = y; buf[ixj] = x; }
+                }
+            }
+            gsync<GS>();
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned next_pow2(unsigned n) {
+    unsigned p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+template <int GS>
+__device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v, unsigned long long* red, int gtid) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (GS == 32) return v;
+    gsync<GS>();
+    if ((gtid & 31) == 0) red[gtid >> 5] = v;
+    gsync<GS>();
+    unsigned long long tot = 0;
+    for (int w = 0; w < GS / 32; w++) tot += red[w];
+    gsync<GS>();
+    return tot;
+}
+
+// planes, m-mer hashes and the deferred-walk queue of one warp
+struct WarpFront {
+    uint32_t p0[PR_MAXCH], p1[PR_MAXCH], pb[PR_MAXCH];
+    uint32_t hx[PR_HX];
+    unsigned long long qkey[WQ];
+    uint32_t qh[WQ];
+    uint32_t qx[WQ];          // stats: index of the window in the arena; assign: orientation flags
+};
+
+// steps 1-2 of the front end for one read (whole warp)
+__device__ __forceinline__ void front_planes_hashes(WarpFront& f, const uint8_t* __restrict__ seq, int L, int m, unsigned mm,
+                                                    int lane) {
+    const int nch = (L + 31) >> 5;
+    pack_read_planes<32>(seq, L, nch, f.p0, f.p1, f.pb, lane);
+    __syncwarp();
+    const int nmm = L - m + 1;
+    for (int q = lane; q < nmm; q += 32) {
+        const int c = q >> 5, o = q & 31;
+        unsigned x = 0xFFFFFFFFu;
+        if (!(__funnelshift_r(f.pb[c], f.pb[c + 1], o) & mm))
+            x = mmer_hash(__funnelshift_r(f.p0[c], f.p0[c + 1], o) & mm, __funnelshift_r(f.p1[c], f.p1[c + 1], o) & mm, m);
+        f.hx[q] = x;
+    }
+    __syncwarp();
+}
+
+// one window of a strip: planes -> canonical key (or the forward one), orientation, home (h, j)
+struct Window { unsigned long long key; unsigned hj, f0, f1; bool valid, is_rc, pal; };
+__device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nwin, int k, unsigned mk, bool canonical, int s0,
+                                               int i, unsigned vl, unsigned vr) {
+    Window w;
+    w.valid = false; w.is_rc = false; w.pal = false; w.key = 0ull; w.hj = 0u; w.f0 = 0u; w.f1 = 0u;
+    if (p < nwin) {
+        const int c = p >> 5, o = p & 31;
+        if (!(__funnelshift_r(f.pb[c], f.pb[c + 1], o) & mk)) {
+            w.f0 = __funnelshift_r(f.p0[c], f.p0[c + 1], o) & mk;
+            w.f1 = __funnelshift_r(f.p1[c], f.p1[c + 1], o) & mk;
+            const unsigned long long kf = make_key(w.f0, w.f1), kr = make_key(rc_plane(w.f0, k), rc_plane(w.f1, k));
+            w.is_rc = canonical && kr < kf;
+            w.pal = kr == kf;
+            w.key = w.is_rc ? kr : kf;
+            unsigned j;
+            const unsigned sp = strip_pick(vl, vr, i, w.is_rc, j);
+            w.hj = pack_home(f.hx[s0 + (int)sp], j);
+            w.valid = true;
+        }
+    }
+    return w;
+}
+
+// =========================================================================================================
+// coverage statistics
+// =========================================================================================================
+constexpr int ST_ARENA = 1024;        // coverage words per warp: the reads of one batch
+constexpr int ST_BATCH = 16;          // reads per batch at most
+constexpr int ST_RPW = 16;            // consecutive reads handled by one warp
+
+struct StatsWarp {
+    WarpFront f;
+    uint32_t cov[ST_ARENA];
+    uint32_t b_off[ST_BATCH], b_n[ST_BATCH], b_rr[ST_BATCH];
+    float b_avg[ST_BATCH];
+};
+
+__device__ __forceinline__ void stats_drain(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, unsigned nq, int lane) {
+    __syncwarp();
+    for (unsigned e = lane; e < nq; e += 32) {
+        const unsigned long long key = sw.f.qkey[e];
+        const unsigned h = sw.f.qh[e];
+        const unsigned long long base = (unsigned long long)(home_part(h, geo.nparts) - geo.part0) * geo.subcap;
+        unsigned v = table_walk_find(slots, geo, base, key).x;
+        if (v < 1) v = 1;
+        sw.cov[sw.f.qx[e]] = v;
+    }
+    __syncwarp();
+}
+
+// Median of the n values a warp holds in registers (lane l owns x[0..PER) = values PER*l .., live where < n), WITHOUT
+// sorting: a bisection on the VALUE between the warp minimum and maximum (coverage values of one read sit in a narrow
+// band, so a handful of rounds), each round one compare per element and one redux.sync.  Returns median_coverage() of
+// fastaToKmerCoverageStats.cpp:337-347: odd n -> the middle element, even n -> the (wrapping) u32 mean of the two middle
+// elements.
+template <int PER>
+__device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], int n, int lane, unsigned lo, unsigned hi) {
+    const int s0 = PER * lane;
+    const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
+    // smallest value with at least k1 + 1 elements <= it = the element of rank k1
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        unsigned cnt = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) cnt += (s0 + i < n && x[i] <= mid) ? 1u : 0u;
+        cnt = __reduce_add_sync(FULL, cnt);
+        if (cnt >= k1 + 1u) hi = mid; else lo = mid + 1u;
+    }
+    const unsigned x1 = lo;
+    if (k1 == k2) return x1;
+    unsigned le = 0, nxt = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const bool live = s0 + i < n;
+        le += (live && x[i] <= x1) ? 1u : 0u;
+        if (live && x[i] > x1) nxt = min(nxt, x[i]);
+    }
+    le = __reduce_add_sync(FULL, le);
+    nxt = __reduce_min_sync(FULL, nxt);
+    const unsigned x2 = le >= k2 + 1u ? x1 : nxt;          // the element of rank k2 = k1 + 1
+    return (uint32_t)(x1 + x2) / 2u;
+}
+
+// steps 3-5 for one read + sum, mean, median; the coverage vector is left in sw.cov[used .. used + nwin)
+template <int PER>
+__device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, int nwin, int k,
+                                           unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean) {
+    const int s0 = PER * lane;
+    unsigned strip[PER + HOME_SLOTS - 1], vl[PER], vr[PER];
+#pragma unroll
+    for (int q = 0; q < PER + HOME_SLOTS - 1; q++) strip[q] = sw.f.hx[s0 + q];
+    strip_minimizers<PER>(strip, vl, vr);
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned nq = 0;                               // queued walks (warp-uniform)
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int p = s0 + i;
+        const Window w = front_window(sw.f, p, nwin, k, mk, canonical, s0, i, vl[i], vr[i]);
+        unsigned v = 0;
+        bool need = false;
+        if (w.valid) {
+            const HomeProbe pr = table_home_find(slots, geo, w.key, w.hj);
+            v = pr.v.x;
+            need = pr.walk;
+        }
+        if (v < 1) v = 1;                          // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
+        if (p < nwin) sw.cov[used + p] = v;
+        const unsigned mq = __ballot_sync(FULL, need);
+        if (mq) {
+            if (nq + __popc(mq) > WQ) { stats_drain(sw, slots, geo, nq, lane); nq = 0; }
+            if (need) {
+                const unsigned e = nq + __popc(mq & lt);
+                sw.f.qkey[e] = w.key; sw.f.qh[e] = w.hj; sw.f.qx[e] = used + p;
+            }
+            nq += __popc(mq);
+        }
+    }
+    if (nq) stats_drain(sw, slots, geo, nq, lane); else __syncwarp();
+    // the lane's values back in registers (the walks may have changed them)
+    unsigned x[PER];
+    unsigned mn = 0xFFFFFFFFu, mx = 0u;
+    unsigned long long part = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const bool live = s0 + i < nwin;
+        x[i] = live ? sw.cov[used + s0 + i] : 0u;
+        if (live) { mn = min(mn, x[i]); mx = max(mx, x[i]); part += x[i]; }
+    }
+    const unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
+    unsigned long long sum;
+    if (hi < (1u << 19)) {                         // 256 windows x 2^19 < 2^32: one redux instead of a 64-bit butterfly
+        sum = __reduce_add_sync(FULL, (unsigned)part);
+    } else {
+        sum = part;
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    }
+    mean = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));   // `long` sum, exact
+    median = warp_median_regs<PER>(x, nwin, lane, lo, hi);
+}
+
+// sequential fp32 sums of squares of a batch, one read per lane (fastaToKmerCoverageStats.cpp:389-402): strict read order,
+// two roundings per term, no FMA (x86-64 -O2 without -march)
+__device__ __forceinline__ void stats_flush(StatsWarp& sw, unsigned nb, uint64_t r0, float* __restrict__ stdev, int lane) {
+    __syncwarp();
+    if ((unsigned)lane < nb) {
+        const unsigned n = sw.b_n[lane];
+        const uint32_t* c = sw.cov + sw.b_off[lane];
+        const float avg = sw.b_avg[lane];
+        float sd;
+        if (n == 1) {
+            sd = __int_as_float(X86_DEFAULT_NAN_BITS);   // 0/0 on SSE = default NaN with the sign bit set ("-nan")
+        } else {
+            float acc = 0.0f;
+            unsigned i = 0;
+            for (; i + 4 <= n; i += 4) {
+                const float d0 = __fsub_rn(__uint2float_rn(c[i]), avg), d1 = __fsub_rn(__uint2float_rn(c[i + 1]), avg);
+                const float d2 = __fsub_rn(__uint2float_rn(c[i + 2]), avg), d3 = __fsub_rn(__uint2float_rn(c[i + 3]), avg);
+                acc = __fadd_rn(acc, __fmul_rn(d0, d0));
+                acc = __fadd_rn(acc, __fmul_rn(d1, d1));
+                acc = __fadd_rn(acc, __fmul_rn(d2, d2));
+                acc = __fadd_rn(acc, __fmul_rn(d3, d3));
+            }
+            for (; i < n; i++) {
+                const float d = __fsub_rn(__uint2float_rn(c[i]), avg);
+                acc = __fadd_rn(acc, __fmul_rn(d, d));
+            }
+            sd = __fsqrt_rn(__fdiv_rn(acc, __int2float_rn((int)n - 1)));
+        }
+        stdev[r0 + sw.b_rr[lane]] = sd;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(PR_WARPS * 32, 4)
+k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
+            int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
+            float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    StatsWarp& sw = reinterpret_cast<StatsWarp*>(dyn)[w];
+    const uint64_t r0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * ST_RPW;
+    if (r0 >= nreads) return;
+    const unsigned mk = kmask(k);
+    const int m = mm_len(k);
+    const unsigned mm = kmask(m);
+    // offsets of the warp's reads: one load per lane, handed round by shuffles
+    const uint64_t my_off = offs[min(r0 + (uint64_t)lane, nreads)];
+    unsigned nb = 0, used = 0;
+    for (int rr = 0; rr < ST_RPW && r0 + rr < nreads; rr++) {
+        const uint64_t o0 = __shfl_sync(FULL, my_off, rr), o1 = __shfl_sync(FULL, my_off, rr + 1);
+        const uint64_t r = r0 + rr;
+        const int L = (int)(o1 - o0 - 1);            // the record's last byte is its '\n' terminator
+        const int nwin = L >= k ? L - k + 1 : 0;
+        if (nwin > PR_MAXWIN) {
+            if (lane == 0) {
+                const unsigned slot = atomicAdd(ll.count, 1u);
+                ll.idx[slot] = (unsigned)r;
+                atomicMax(ll.max_win, (unsigned)nwin);
+            }
+            continue;
+        }
+        if (nwin == 0) {   // S6: shorter than k -> empty vector; S7-S9 on n = 0: 0, 0, sqrt(0/-1) = -0
+            if (lane == 0) { median[r] = 0u; mean[r] = 0.0f; stdev[r] = __int_as_float(0x80000000); }
+            continue;
+        }
+        if (nb == ST_BATCH || used + nwin > ST_ARENA) { stats_flush(sw, nb, r0, stdev, lane); nb = 0; used = 0; }
+        const uint8_t* seq = recs + (o0 - rec_base);
+        front_planes_hashes(sw.f, seq, L, m, mm, lane);
+        uint32_t med; float mu;
+        switch ((nwin + 31) >> 5) {
+            case 1: stats_read<1>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 2: stats_read<2>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 3: stats_read<3>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 4: stats_read<4>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 5: stats_read<5>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 6: stats_read<6>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 7: stats_read<7>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            default: stats_read<8>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+        }
+        if (per_kmer) {
+            uint32_t* out = per_kmer + (o0 - rec_base);
+            for (int p = lane; p < nwin; p += 32) out[p] = sw.cov[used + p];
+        }
+        if (lane == 0) {
+            median[r] = med; mean[r] = mu;
+            sw.b_off[nb] = used; sw.b_n[nb] = (unsigned)nwin; sw.b_rr[nb] = (unsigned)rr; sw.b_avg[nb] = mu;
+        }
+        nb++;
+        used += (unsigned)nwin;
+    }
+    stats_flush(sw, nb, r0, stdev, lane);
+}
+
+cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                             int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s) {
+    TimedLaunch timed("k_cov_stats", s);
+    if (nreads == 0) return cudaSuccess;
+    if (k < MIN_FAST_K) return cudaErrorInvalidValue;      // callers route shorter k-mers through the long kernel
+    const size_t dyn = sizeof(StatsWarp) * PR_WARPS;
+    cudaError_t e = cudaFuncSetAttribute((const void*)k_cov_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    const uint64_t per_cta = (uint64_t)PR_WARPS * ST_RPW;
+    const uint64_t blocks = (nreads + per_cta - 1) / per_cta;
+    k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
+                                                             d_median, d_mean, d_stdev, d_per_kmer, ll);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// long path: one CTA per read (fastaToKmerCoverageStats.cpp:300-402)
+// ---------------------------------------------------------------------------------------------------------
+template <int GS>
+__device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, int L, int k, int canonical,
+                                               const Slot* __restrict__ slots, Geo geo, uint32_t* P0,
+                                               uint32_t* P1, uint32_t* PB, uint32_t* cov, float* sq,
+                                               unsigned long long* red, uint32_t* per_kmer, uint32_t& median,
+                                               float& mean, float& stdev, int gtid) {
+    const int nwin = L >= k ? L - k + 1 : 0;
+    if (nwin == 0) {   // S6: shorter than k -> empty vector; S7-S9 on n = 0: 0, 0, sqrt(0/-1) = -0
+        median = 0; mean = 0.0f; stdev = __int_as_float(0x80000000);
+        return;
+    }
+    const unsigned mk = kmask(k);
+    const int nch = (L + 31) >> 5;
+    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
+    gsync<GS>();
+
+    unsigned long long part = 0;
+    for (int p = gtid; p < nwin; p += GS) {
+        const int c = p >> 5, o = p & 31;
+        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+        unsigned v = 0;
+        if (!bad) {
+            const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+            const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+            unsigned long long key = make_key(f0, f1);
+            if (canonical) {
+                const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                key = kr < key ? kr : key;
+            }
+            v = table_find_key(slots, geo, key).x;
+        }
+        if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
+        cov[p] = v;
+        if (per_kmer) per_kmer[p] = v;
+        part += v;
+    }
+    const unsigned long long sum = group_sum_u64<GS>(part, red, gtid);   // `long` sum, exact
+    const float avg = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));
+    gsync<GS>();
+    for (int p = gtid; p < nwin; p += GS) {
+        const float d = __fsub_rn(__uint2float_rn(cov[p]), avg);
+        sq[p] = __fmul_rn(d, d);               // two roundings, no FMA (x86-64 -O2 without -march)
+    }
+    gsync<GS>();
+    float sd;
+    if (nwin == 1) {
+        sd = __int_as_float(X86_DEFAULT_NAN_BITS);   // 0/0 on SSE = default NaN with the sign bit set ("-nan")
+    } else {
+        float acc = 0.0f;
+        if (gtid == 0) {
+            for (int p = 0; p < nwin; p++) acc = __fadd_rn(acc, sq[p]);     // strict read order
+            acc = __fsqrt_rn(__fdiv_rn(acc, __int2float_rn(nwin - 1)));
+        }
+        sd = acc;
+    }
+    // median: odd -> middle, even -> u32 (wrapping) mean of the two middles
+    const unsigned n2 = next_pow2((unsigned)nwin);
+    for (unsigned p = nwin + gtid; p < n2; p += GS) cov[p] = 0xFFFFFFFFu;
+    gsync<GS>();
+    bitonic_sort<GS, uint32_t>(cov, n2, gtid);
+    median = (nwin & 1) ? cov[nwin / 2] : (uint32_t)(cov[(nwin - 1) / 2] + cov[nwin / 2]) / 2u;
+    mean = avg;
+    stdev = sd;    // meaningful in gtid 0 only
+}
+
+// scratch layout per CTA of the long path: planes 3*(nch+1) u32 | cov n2 u32 | sq n2 f32
+__host__ __device__ static inline size_t long_nch(unsigned max_win, int k) { return ((size_t)max_win + k - 1 + 31) / 32 + 2; }
+__host__ __device__ static inline size_t pow2_ge(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+__host__ __device__ static inline size_t long_scratch_words(unsigned max_win, int k, int mult) {
+    return 3 * long_nch(max_win, k) + (size_t)2 * pow2_ge((size_t)mult * max_win);
+}
+
+// The CTA-per-read kernels run in one of two ways.  Host-driven (the host-buffer entry points, which synchronise
+// anyway): the host has read {count, max_win}, sized the scratch and passes them.  Device-driven (the *_dev entry
+// points, which must not synchronise -- a host stall would leave the GPU idle): the kernel is launched unconditionally
+// behind the warp-path kernel, reads {count, max_win} from `hdr` itself, lays the fixed scratch budget out and leaves
+// at once when there is no long read.  A read too long for the budget raises error 4 instead of a wrong answer.
+// all_reads != 0 (k-mers shorter than the fast path's 8): every read 0 .. n_long-1 goes through this kernel.
+struct LongPlan { unsigned n_long, max_win, stride; size_t words_per_cta; };
+__device__ __forceinline__ bool long_plan(const unsigned int* hdr, unsigned n_long, unsigned max_win, size_t words_per_cta,
+                                          unsigned long long scratch_words, int k, int mult, int* error, LongPlan& pl) {
+    pl.n_long = n_long; pl.max_win = max_win; pl.words_per_cta = words_per_cta; pl.stride = gridDim.x;
+    if (!hdr) return true;
+    pl.n_long = hdr[0]; pl.max_win = hdr[1];
+    if (pl.n_long == 0) return false;
+    pl.words_per_cta = long_scratch_words(pl.max_win, k, mult);
+    const unsigned long long fit = scratch_words / pl.words_per_cta;
+    if (fit == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(error, 4);
+        return false;
+    }
+    pl.stride = (unsigned)min((unsigned long long)gridDim.x, fit);
+    return blockIdx.x < pl.stride;
+}
+size_t cov_stats_long_scratch_bytes(unsigned max_win, int k, int nctas) {
+    return long_scratch_words(max_win, k, 1) * 4 * (size_t)nctas;
+}
+size_t assign_long_scratch_bytes(unsigned max_win, int k, int nctas) {
+    return long_scratch_words(max_win, k, 2) * 4 * (size_t)nctas;
+}
+
+__global__ void __launch_bounds__(LONG_THREADS)
+k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k,
+                 int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
+                 float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer,
+                 const unsigned int* __restrict__ long_idx, unsigned int n_long_h, unsigned int max_win_h,
+                 uint32_t* scratch, size_t words_per_cta_h, const unsigned int* __restrict__ hdr,
+                 unsigned long long scratch_words, int* error) {
+    __shared__ unsigned long long red[LONG_THREADS / 32];
+    LongPlan pl;
+    if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 1, error, pl)) return;
+    const unsigned n_long = pl.n_long, max_win = pl.max_win;
+    const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
+    size_t n2max = 1; while (n2max < max_win) n2max <<= 1;
+    uint32_t* base = scratch + (size_t)blockIdx.x * pl.words_per_cta;
+    uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
+    uint32_t* cov = PB + nchw; float* sq = reinterpret_cast<float*>(cov + n2max);
+    for (unsigned i = blockIdx.x; i < n_long; i += pl.stride) {
+        const uint64_t r = long_idx ? long_idx[i] : i;
+        const uint64_t o0 = offs[r], o1 = offs[r + 1];
+        const int L = (int)(o1 - o0 - 1);
+        uint32_t med; float mu, sd;
+        read_cov_stats<LONG_THREADS>(recs + (o0 - rec_base), L, k, canonical, slots, geo, P0, P1, PB, cov, sq, red,
+                                     per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, threadIdx.x);
+        if (threadIdx.x == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
+                                  const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
+                                  uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
+                                  unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_cov_stats_long", s);
+    if (n_long == 0) return cudaSuccess;
+    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
+                                                    d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
+                                                    (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1), nullptr, 0,
+                                                    nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k,
+                                       int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
+                                       float* d_stdev, uint32_t* d_per_kmer, LongList ll, void* d_scratch,
+                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_cov_stats_long", s);
+    k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
+                                                    d_stdev, d_per_kmer, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
+                                                    scratch_bytes / 4, d_error);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
+// read -> bundle vote (ReadsToTranscripts.cc:216-274)
+// =========================================================================================================
+// entropy_ok is indexed [nG][nA][nT] (26^3 bytes); nC is implied for an all-ACGT window.
+__device__ __forceinline__ bool window_entropy_ok(const uint8_t* __restrict__ lut, unsigned f0, unsigned f1, unsigned mk,
+                                                  bool rc) {
+    // codes: A=00 C=01 G=10 T=11 (bit1 = plane1, bit0 = plane0)
+    const int nG = __popc(f1 & ~f0 & mk), nA = __popc(~f1 & ~f0 & mk), nT = __popc(f1 & f0 & mk);
+    const int nC = __popc(~f1 & f0 & mk);
+    // the reference evaluates the reverse-complemented string in the same G,A,T,C slot order:
+    // its counts are (nC, nT, nA, nG) of the forward window
+    return rc ? lut[(nC * 26 + nT) * 26 + nA] != 0 : lut[(nG * 26 + nA) * 26 + nT] != 0;
+}
+
+// labels of a settled lookup -> the reference's two lookups (forward window, reverse-complemented window):
+// the slot of the canonical key holds the label of the bundle k-mer equal to the key (val) and of the bundle k-mer whose
+// reverse complement is the key (aux).  A palindrome (even k only) is its own reverse complement.
+__device__ __forceinline__ void labels_of(uint2 v, bool do_f, bool do_r, bool is_rc, bool pal, unsigned& vf, unsigned& vr) {
+    vf = do_f ? (is_rc ? v.y : v.x) : 0u;
+    vr = do_r ? ((is_rc || pal) ? v.x : v.y) : 0u;
+}
+
+// The reference sorts the hits and scans the runs (ReadsToTranscripts.cc:253-268): a label with m hits scores m-1, the
+// largest label m-2, strict '>' while ascending => ties go to the smaller label.  The same result without a sort: walk
+// the DISTINCT labels in ascending order (almost always one or two), one warp min and one warp count per label.
+__device__ __forceinline__ void warp_vote(const int32_t* hits, int n, int lane, int& best, int& score) {
+    int b = -1, sc = 0;
+    if (n >= 2) {
+        int last = -1;
+        for (int p = lane; p < n; p += 32) last = max(last, hits[p]);
+        last = __reduce_max_sync(FULL, last);
+        int cur = -1;
+        while (true) {
+            int mn = 0x7FFFFFFF;
+            for (int p = lane; p < n; p += 32) { const int h = hits[p]; if (h > cur) mn = min(mn, h); }
+            const int lab = __reduce_min_sync(FULL, mn);
+            if (lab == 0x7FFFFFFF) break;
+            unsigned m = 0;
+            for (int p = lane; p < n; p += 32) m += hits[p] == lab ? 1u : 0u;
+            m = __reduce_add_sync(FULL, m);
+            const int s = (int)m - 1 - (lab == last ? 1 : 0);
+            if (s > sc) { sc = s; b = lab; }
+            cur = lab;
+        }
+        if (sc <= 0) { b = -1; sc = 0; }
+    }
+    best = b; score = sc;
+}
+
+struct AssignWarp {
+    WarpFront f;
+    int32_t hits[2 * PR_MAXWIN];
+};
+
+// append the labels the warp's lanes hold (0 = none) to the hit list; nh is warp-uniform
+__device__ __forceinline__ void push_hits(int32_t* hits, unsigned& nh, unsigned vf, unsigned vr, int lane) {
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned mf = __ballot_sync(FULL, vf != 0u), mr = __ballot_sync(FULL, vr != 0u);
+    if (vf) hits[nh + __popc(mf & lt)] = (int32_t)vf - 1;
+    nh += __popc(mf);
+    if (vr) hits[nh + __popc(mr & lt)] = (int32_t)vr - 1;
+    nh += __popc(mr);
+}
+
+__device__ __forceinline__ void assign_drain(AssignWarp& aw, const Slot* __restrict__ slots, const Geo& geo, unsigned nq,
+                                             unsigned& nh, int lane) {
+    __syncwarp();
+    for (unsigned e0 = 0; e0 < nq; e0 += 32) {        // nq <= WQ = 32: one round
+        const unsigned e = e0 + lane;
+        unsigned vf = 0, vr = 0;
+        if (e < nq) {
+            const unsigned long long key = aw.f.qkey[e];
+            const unsigned h = aw.f.qh[e], fl = aw.f.qx[e];
+            const unsigned long long base = (unsigned long long)(home_part(h, geo.nparts) - geo.part0) * geo.subcap;
+            const uint2 v = table_walk_find(slots, geo, base, key);
+            labels_of(v, fl & 1u, fl & 2u, fl & 4u, fl & 8u, vf, vr);
+        }
+        push_hits(aw.hits, nh, vf, vr, lane);
+    }
+    __syncwarp();
+}
+
+template <int PER>
+__device__ __forceinline__ void assign_read(AssignWarp& aw, const Slot* __restrict__ slots, const Geo& geo,
+                                            const uint8_t* __restrict__ lut, int nwin, int k, unsigned mk, int strand, int lane,
+                                            unsigned& nh_out) {
+    const int s0 = PER * lane;
+    unsigned strip[PER + HOME_SLOTS - 1], vl[PER], vr[PER];
+#pragma unroll
+    for (int q = 0; q < PER + HOME_SLOTS - 1; q++) strip[q] = aw.f.hx[s0 + q];
+    strip_minimizers<PER>(strip, vl, vr);
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned nq = 0, nh = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int p = s0 + i;
+        // label tables are keyed canonically whatever the library type: the strand flag only drops the second lookup
+        const Window w = front_window(aw.f, p, nwin, k, mk, true, s0, i, vl[i], vr[i]);
+        bool do_f = false, do_r = false, need = false;
+        uint2 v = make_uint2(0u, 0u);
+        if (w.valid) {                     // a window with a non-ACGT character can never equal a table k-mer
+            do_f = window_entropy_ok(lut, w.f0, w.f1, mk, false);
+            do_r = !strand && window_entropy_ok(lut, w.f0, w.f1, mk, true);
+            if (do_f || do_r) {
+                const HomeProbe pr = table_home_find(slots, geo, w.key, w.hj);
+                v = pr.v;
+                need = pr.walk;
+            }
+        }
+        unsigned vf, vr2;
+        labels_of(v, do_f, do_r, w.is_rc, w.pal, vf, vr2);
+        push_hits(aw.hits, nh, vf, vr2, lane);
+        const unsigned mq = __ballot_sync(FULL, need);
+        if (mq) {
+            if (nq + __popc(mq) > WQ) { assign_drain(aw, slots, geo, nq, nh, lane); nq = 0; }
+            if (need) {
+                const unsigned e = nq + __popc(mq & lt);
+                aw.f.qkey[e] = w.key; aw.f.qh[e] = w.hj;
+                aw.f.qx[e] = (do_f ? 1u : 0u) | (do_r ? 2u : 0u) | (w.is_rc ? 4u : 0u) | (w.pal ? 8u : 0u);
+            }
+            nq += __popc(mq);
+        }
+    }
+    if (nq) assign_drain(aw, slots, geo, nq, nh, lane); else __syncwarp();
+    nh_out = nh;
+}
+
+// pct = (int)((float)max / num_kmer_pos * 100 + 0.5): fp32 divide, fp32 multiply, double add, truncate
+__device__ __forceinline__ int assign_pct(int score, int nwin) {
+    const float q = __fmul_rn(__fdiv_rn(__int2float_rn(score), __int2float_rn(nwin)), 100.0f);
+    return (int)__dadd_rn((double)q, 0.5);
+}
+
+__global__ void __launch_bounds__(PR_WARPS * 32, 4)
+k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int k,
+         int strand, const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut,
+         int32_t* __restrict__ best, int32_t* __restrict__ pct, int32_t* __restrict__ score, LongList ll) {
+    __shared__ AssignWarp smw[PR_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    AssignWarp& aw = smw[w];
+    const uint64_t r = (uint64_t)blockIdx.x * PR_WARPS + w;
+    if (r >= nreads) return;
+    const uint64_t o0 = offs[r], o1 = offs[r + 1];
+    const int L = (int)(o1 - o0 - 1);
+    const int nwin = L - k + 1;        // num_kmer_pos, may be <= 0
+    if (nwin > PR_MAXWIN) {
+        if (lane == 0) {
+            const unsigned slot = atomicAdd(ll.count, 1u);
+            ll.idx[slot] = (unsigned)r;
+            atomicMax(ll.max_win, (unsigned)nwin);
+        }
+        return;
+    }
+    int b = -1, sc = 0, pc = 0;
+    if (nwin > 0) {
+        const unsigned mk = kmask(k);
+        const int m = mm_len(k);
+        front_planes_hashes(aw.f, recs + (o0 - rec_base), L, m, kmask(m), lane);
+        unsigned nh = 0;
+        switch ((nwin + 31) >> 5) {
+            case 1: assign_read<1>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            case 2: assign_read<2>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            case 3: assign_read<3>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            case 4: assign_read<4>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            case 5: assign_read<5>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            case 6: assign_read<6>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            case 7: assign_read<7>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+            default: assign_read<8>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
+        }
+        warp_vote(aw.hits, (int)nh, lane, b, sc);
+        pc = assign_pct(sc, nwin);
+    }
+    if (lane == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
+}
+
+cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                          int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
+                          int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s) {
+    TimedLaunch timed("k_assign", s);
+    if (nreads == 0) return cudaSuccess;
+    if (k < MIN_FAST_K) return cudaErrorInvalidValue;
+    const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
+    k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, geo,
+                                                        d_entropy_ok, d_best, d_pct, d_score, ll);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// long path: one CTA per read
+// ---------------------------------------------------------------------------------------------------------
+template <int GS>
+__device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int L, int k, int strand,
+                                            const Slot* __restrict__ slots, Geo geo,
+                                            const uint8_t* __restrict__ lut, uint32_t* P0, uint32_t* P1, uint32_t* PB,
+                                            int32_t* hits, unsigned int* nhits_p, int32_t& best, int32_t& score,
+                                            int32_t& pct, int gtid) {
+    const int nwin = L - k + 1;        // num_kmer_pos, may be <= 0
+    best = -1; score = 0;
+    if (nwin <= 0) { pct = 0; return; }
+    const unsigned mk = kmask(k);
+    const int nch = (L + 31) >> 5;
+    if (gtid == 0) *nhits_p = 0;
+    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
+    gsync<GS>();
+    for (int p = gtid; p < nwin; p += GS) {
+        const int c = p >> 5, o = p & 31;
+        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+        if (bad) continue;                 // a window with a non-ACGT character can never equal a table k-mer
+        const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+        const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+        const bool do_f = window_entropy_ok(lut, f0, f1, mk, false);
+        const bool do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
+        if (!do_f && !do_r) continue;
+        const unsigned long long kf = make_key(f0, f1), kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+        const bool is_rc = kr < kf, pal = kr == kf;
+        const uint2 v = table_find_key(slots, geo, is_rc ? kr : kf);
+        unsigned vf, vr;
+        labels_of(v, do_f, do_r, is_rc, pal, vf, vr);
+        if (vf) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vf - 1;
+        if (vr) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vr - 1;
+    }
+    gsync<GS>();
+    const int n = (int)*nhits_p;
+    int b = -1, sc = 0;
+    if (n >= 2) {
+        const unsigned n2 = next_pow2((unsigned)n);
+        for (unsigned p = n + gtid; p < n2; p += GS) hits[p] = 0x7FFFFFFF;
+        gsync<GS>();
+        bitonic_sort<GS, int32_t>(hits, n2, gtid);
+        // a label with m hits scores m-1, the last (largest) label m-2; strict '>' while scanning ascending
+        // labels => ties go to the smaller label (ReadsToTranscripts.cc:253-268)
+        const int32_t last = hits[n - 1];
+        for (int i = gtid; i < n; i += GS) {
+            const int32_t h = hits[i];
+            if (i == n - 1 || hits[i + 1] != h) {        // end of a run: multiplicity by lower_bound
+                int lo = 0, hi = i;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid] < h) lo = mid + 1; else hi = mid; }
+                const int m = i + 1 - lo;
+                const int s = m - 1 - (h == last ? 1 : 0);
+                if (s > sc || (s == sc && s > 0 && h < b)) { sc = s; b = h; }
+            }
+        }
+        // group arg-max (score desc, label asc)
+        for (int o = 16; o > 0; o >>= 1) {
+            const int os = __shfl_xor_sync(FULL, sc, o), ob = __shfl_xor_sync(FULL, b, o);
+            if (os > sc || (os == sc && os > 0 && ob < b)) { sc = os; b = ob; }
+        }
+        __shared__ int wsc[LONG_THREADS / 32], wb[LONG_THREADS / 32];
+        gsync<GS>();
+        if ((gtid & 31) == 0) { wsc[gtid >> 5] = sc; wb[gtid >> 5] = b; }
+        gsync<GS>();
+        sc = wsc[0]; b = wb[0];
+        for (int w = 1; w < GS / 32; w++)
+            if (wsc[w] > sc || (wsc[w] == sc && wsc[w] > 0 && wb[w] < b)) { sc = wsc[w]; b = wb[w]; }
+        gsync<GS>();
+        if (sc <= 0) { b = -1; sc = 0; }
+    }
+    best = b; score = sc;
+    pct = assign_pct(sc, nwin);
+}
+
+__global__ void __launch_bounds__(LONG_THREADS)
+k_assign_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, int k, int strand,
+              const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut, int32_t* __restrict__ best,
+              int32_t* __restrict__ pct, int32_t* __restrict__ score, const unsigned int* __restrict__ long_idx,
+              unsigned int n_long_h, unsigned int max_win_h, uint32_t* scratch, size_t words_per_cta_h,
+              const unsigned int* __restrict__ hdr, unsigned long long scratch_words, int* error) {
+    __shared__ unsigned int nhits;
+    LongPlan pl;
+    if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 2, error, pl)) return;
+    const unsigned n_long = pl.n_long, max_win = pl.max_win;
+    const size_t nchw = ((size_t)max_win + k - 1 + 31) / 32 + 2;
+    uint32_t* base = scratch + (size_t)blockIdx.x * pl.words_per_cta;
+    uint32_t* P0 = base; uint32_t* P1 = P0 + nchw; uint32_t* PB = P1 + nchw;
+    int32_t* hits = reinterpret_cast<int32_t*>(PB + nchw);
+    for (unsigned i = blockIdx.x; i < n_long; i += pl.stride) {
+        const uint64_t r = long_idx ? long_idx[i] : i;
+        const uint64_t o0 = offs[r], o1 = offs[r + 1];
+        const int L = (int)(o1 - o0 - 1);
+        int32_t b, sc, pc;
+        read_assign<LONG_THREADS>(recs + (o0 - rec_base), L, k, strand, slots, geo, lut, P0, P1, PB, hits, &nhits, b, sc,
+                                  pc, threadIdx.x);
+        if (threadIdx.x == 0) { best[r] = b; pct[r] = pc; if (score) score[r] = sc; }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
+                               const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
+                               int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
+                               unsigned int max_win, void* d_scratch, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_assign_long", s);
+    if (n_long == 0) return cudaSuccess;
+    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
+                                                 d_pct, d_score, d_long_idx, n_long, max_win, (uint32_t*)d_scratch,
+                                                 long_scratch_words(max_win, k, 2), nullptr, 0, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
+                                    const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
+                                    int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
+                                    int* d_error, int nctas, cudaStream_t s) {
+    TimedLaunch timed("k_assign_long", s);
+    k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
+                                                 d_pct, d_score, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
+                                                 scratch_bytes / 4, d_error);
+    return cudaGetLastError();
+}
+
+}  // namespace tg

@@ -188,8 +188,19 @@ int cmd_dump(int argc, char** argv) {
     // Binary hand-off (tg_sidecar.hpp): a FASTA dump that lands in a regular file gets `<file>.tgk` next to it with the
     // same records as packed pairs, so fastaToKmerCoverageStats --kmers need not re-parse ~31 B of text per k-mer.
     const std::string text_path = (!column && !tgside::disabled()) ? tgside::regular_file_behind(fd) : "";
-    std::vector<uint64_t> side_keys;
-    std::vector<uint32_t> side_counts;
+    // The sidecar is streamed like the text (O(1) memory, whatever the table size): header placeholder, the packed k-mers as
+    // they are printed, then -- in a second pass over the memory-mapped counts with the same filter -- the counts, and last the
+    // real header.  Best effort: a sidecar that cannot be written is simply absent (the FASTA is complete either way).
+    const std::string side = text_path + ".tgk", side_tmp = side + ".tmp";
+    FILE* sf = text_path.empty() ? nullptr : fopen(side_tmp.c_str(), "wb");
+    bool side_ok = sf != nullptr;
+    uint64_t side_n = 0;
+    tgside::TgkHeader sh;
+    memset(&sh, 0, sizeof sh);
+    if (sf) {
+        setvbuf(sf, nullptr, _IOFBF, 4u << 20);
+        side_ok = fwrite(&sh, sizeof sh, 1, sf) == 1;
+    }
     tgside::TextHash hash;
     {
         OutBuf out(fd, 16u << 20);
@@ -219,30 +230,27 @@ int cmd_dump(int argc, char** argv) {
                 line[n++] = '\n';
             }
             out.put(line, (size_t)n);
-            if (!text_path.empty()) {
+            if (sf) {
                 hash.update(line, (size_t)n);
-                side_keys.push_back(jf.keys[i]);
-                side_counts.push_back(c);
+                side_ok = side_ok && fwrite(&jf.keys[i], 8, 1, sf) == 1;
+                side_n++;
             }
         }
-        if (!out.flush()) { fprintf(stderr, "jellyfish: write failed: %s\n", strerror(errno)); return 1; }
+        if (!out.flush()) { fprintf(stderr, "jellyfish: write failed: %s\n", strerror(errno)); if (sf) { fclose(sf); unlink(side_tmp.c_str()); } return 1; }
     }
     if (fd != 1) ::close(fd);
-    if (!text_path.empty()) {
-        // best effort: a sidecar that cannot be written is simply absent (the FASTA is complete either way)
-        const std::string side = text_path + ".tgk", tmp = side + ".tmp";
-        tgside::TgkHeader h;
-        memset(&h, 0, sizeof h);
-        memcpy(h.magic, tgside::TGK_MAGIC, 8);
-        h.k = (uint32_t)k; h.n = side_keys.size(); h.text_bytes = hash.total; h.text_hash = hash.digest();
-        FILE* f = fopen(tmp.c_str(), "wb");
-        bool ok = f != nullptr;
-        ok = ok && fwrite(&h, sizeof h, 1, f) == 1;
-        ok = ok && (h.n == 0 || fwrite(side_keys.data(), 8, h.n, f) == h.n);
-        ok = ok && (h.n == 0 || fwrite(side_counts.data(), 4, h.n, f) == h.n);
-        if (f) ok = (fclose(f) == 0) && ok;
-        if (ok) ok = rename(tmp.c_str(), side.c_str()) == 0;
-        if (!ok) unlink(tmp.c_str());
+    if (sf) {
+        for (uint64_t i = 0; side_ok && i < jf.h->n; i++) {
+            const uint32_t c = jf.counts[i];
+            if (c < lower || c > upper) continue;
+            side_ok = fwrite(&c, 4, 1, sf) == 1;
+        }
+        memcpy(sh.magic, tgside::TGK_MAGIC, 8);
+        sh.k = (uint32_t)k; sh.n = side_n; sh.text_bytes = hash.total; sh.text_hash = hash.digest();
+        side_ok = side_ok && fseek(sf, 0, SEEK_SET) == 0 && fwrite(&sh, sizeof sh, 1, sf) == 1;
+        side_ok = (fclose(sf) == 0) && side_ok;
+        if (side_ok) side_ok = rename(side_tmp.c_str(), side.c_str()) == 0;
+        if (!side_ok) unlink(side_tmp.c_str());
     }
     return 0;
 }
@@ -256,6 +264,9 @@ int cmd_histo(int argc, char** argv) {
     const bool full = o.has("-f", "--full");
     if (inc == 0) die_usage("histo: increment must be positive");
     if (high > 10000) die_usage("histo: --high above 10000 is not supported (bins are accumulated on the GPU up to 10000)");
+    // counts above 10000 are one bin here; that is exact only while they all fall into the LAST bucket, i.e. while the
+    // ceiling high + increment does not pass 10001 (the defaults -h 10000 -i 1 are exactly that)
+    if (high + inc > 10001) die_usage("histo: --high + --increment above 10001 is not supported (counts above 10000 are one bin)");
     JfFile jf;
     jf.open(o.positional[0]);
     // jellyfish 2 histo_main: base = low>0 ? (inc>=low ? 0 : low-inc) : 0; ceil = high+inc; bucket = (val-base)/inc,

@@ -13,7 +13,12 @@ static const char* USAGE =
     "#  --min_cov <int>           : minimum coverage\n#\n#  --max_CV <int>            : maximum coeff. var.\n#\n#\n"
     "#############################################################\n\n";
 
+// accessions selected so far: Perl flushes STDOUT when it dies, so a malformed row late in the table must not swallow them
+static std::string g_out;
+
 static void fatal(const std::string& msg) {
+    fwrite(g_out.data(), 1, g_out.size(), stdout);
+    fflush(stdout);
     fprintf(stderr, "%s\n", msg.c_str());
     exit(255);
 }
@@ -38,7 +43,7 @@ int main(int argc, char** argv) {
     perlc::Drand48 rng(12345);
     unsigned long long total = 0, selected = 0, aberrant = 0, below = 0;
     std::vector<std::string> row;
-    std::string out;
+    std::string& out = g_out;
     out.reserve(1 << 20);
     while (rd.next(row)) {
         total++;

@@ -80,10 +80,14 @@ def exchange_bins(world, lp, max_bins=MAX_EXCHANGE_BINS):
     return c
 
 
+ENTRIES_PER_WINDOW = 0.5      # a log entry is a run of up to 8 windows sharing a minimizer (typically ~3.5 windows per entry)
+
+
 def log_capacity(nbytes, nbins, slack=1.2):
-    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window); the additive
-    term covers the hash fluctuation of small batches, the factor covers hot k-mers"""
-    cap = int(nbytes / nbins * slack) + 1024
+    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window, an entry holds ~3.5
+    windows: laid out for one entry per two windows); the additive term covers the hash fluctuation of small batches, the
+    factor covers hot minimizers.  A bin that overflows all the same makes the caller double the head-room and repeat."""
+    cap = int(nbytes * ENTRIES_PER_WINDOW / nbins * slack) + 1024
     return (cap + 15) // 16 * 16
 
 
@@ -102,9 +106,12 @@ class DeviceEngine:
         self.table = KmerCounter.sharded(self.ctx, self.k, self.canonical, subcap, nparts, part0, nlocal)
         return self.table
 
+    # a log entry is 16 bytes on the device (key + packed home of the k-mer): two int64 words
+    ENTRY_WORDS = 2
+
     def new_log(self, nbins, cap):
         t = self.torch
-        keys = t.empty((nbins, cap), dtype=t.int64, device=self.device)
+        keys = t.empty((nbins, cap, self.ENTRY_WORDS), dtype=t.int64, device=self.device)
         cursor = t.zeros((nbins,), dtype=t.int32, device=self.device)
         hpoly = t.zeros((8,), dtype=t.int64, device=self.device)    # homopolymer side channel: 4 keys, 4 counts
         return keys, cursor, hpoly
@@ -116,11 +123,11 @@ class DeviceEngine:
 
     def partition(self, d_recs, nbytes, keys, cursor, hpoly):
         """phase 1: record buffer in HBM -> log bins"""
-        nbins, cap = keys.shape
+        nbins, cap = keys.shape[0], keys.shape[1]
         check(_lib.lib().tg_count_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(self.canonical), nbins, cap,
                                                 C.c_void_p(keys.data_ptr()), C.c_void_p(cursor.data_ptr()),
                                                 C.c_void_p(hpoly.data_ptr())))
-        self.ctx.sync()          # the exchange runs on torch's stream: hand over with a host sync
+        return self.ctx.log_overflow_check()          # (a sync: the exchange runs on torch's stream)
 
     def sync(self):
         self.ctx.sync()
@@ -130,7 +137,7 @@ class DeviceEngine:
         every other rank's log mapped into this process.  -> PeerLogs, or None (on every rank) when any rank fails."""
         L, t = _lib.lib(), self.torch
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        nbytes = nbins * cap * 8
+        nbytes = nbins * cap * 8 * self.ENTRY_WORDS
         mine, handle, ok = None, b"", 1
         try:
             mine = self.ctx.dev_alloc(nbytes)
@@ -161,7 +168,8 @@ class DeviceEngine:
         peers = PeerLogs(mine, ptrs, opened, None, world)
         peers.ok = int(flag.item()) == 1
         if peers.ok:
-            peers.rkeys = _alias_tensor(t, mine.value, nbytes, self.device).view(t.int64).view(world, nbins // world, cap)
+            peers.rkeys = _alias_tensor(t, mine.value, nbytes, self.device).view(t.int64).view(world, nbins // world, cap,
+                                                                                                self.ENTRY_WORDS)
         return peers
 
     # closing is two steps with a barrier between them (the caller's): every importer unmaps before any exporter frees
@@ -184,19 +192,21 @@ class DeviceEngine:
         check(_lib.lib().tg_count_partition_peers_dev(self.ctx._h, d_recs, nbytes, self.k, int(self.canonical), nbins, cap,
                                                       peers.world, rank, peers.ptrs, C.c_void_p(cursor.data_ptr()),
                                                       C.c_void_p(hpoly.data_ptr())))
-        self.ctx.sync()          # kernel end = this rank's peer stores are visible system-wide
+        return self.ctx.log_overflow_check()          # kernel end = this rank's peer stores are visible system-wide
 
     def new_fine_log(self, nfine, cap):
         t = self.torch
-        return (t.empty((nfine, cap), dtype=t.int64, device=self.device), t.zeros((nfine,), dtype=t.int32, device=self.device))
+        return (t.empty((nfine, cap, self.ENTRY_WORDS), dtype=t.int64, device=self.device),
+                t.zeros((nfine,), dtype=t.int32, device=self.device))
 
     def refine(self, rkeys, rcur, nsrc, ncoarse, fkeys, fcur, fine0, nfine_global):
         """received coarse log [nsrc, ncoarse, cap] -> fine log [nfine, fcap], one segment per local partition"""
         fcur.zero_()
         self.torch.cuda.current_stream(self.device).synchronize()
         check(_lib.lib().tg_log_refine_dev(self.ctx._h, C.c_void_p(rkeys.data_ptr()), C.c_void_p(rcur.data_ptr()), nsrc,
-                                           ncoarse, rkeys.shape[-1], C.c_void_p(fkeys.data_ptr()),
+                                           ncoarse, rkeys.shape[-2], C.c_void_p(fkeys.data_ptr()),
                                            C.c_void_p(fcur.data_ptr()), fkeys.shape[0], fkeys.shape[1], fine0, nfine_global))
+        return self.ctx.log_overflow_check()
 
     def new_cursors(self, nbins):
         t = self.torch
@@ -208,7 +218,7 @@ class DeviceEngine:
 
     def replay(self, keys, cursor, hpoly, nsrc):
         """phase 2: received log [nsrc, lp, cap] (+ global homopolymer tallies) -> this rank's shard"""
-        cap = keys.shape[-1]
+        cap = keys.shape[-2]
         self.torch.cuda.current_stream(self.device).synchronize()
         check(_lib.lib().tg_table_replay_log_dev(self.table._h, C.c_void_p(keys.data_ptr()),
                                                  C.c_void_p(cursor.data_ptr()), C.c_void_p(hpoly.data_ptr()), nsrc, cap))
@@ -294,6 +304,9 @@ class ShardedKmerCounter:
         self.profile = None       # set to a dict to collect host-clock milliseconds per phase (syncs around each)
         self._log = None
         self._recv = None
+        self._grow = 1            # per-bin head-room multiplier: doubled whenever a batch overflowed a bin (hot k-mers / minimizers)
+        self._fine_grow = 1
+        self.overflow_retries = 0
         self._peers = None        # (PeerLogs, cap, (cursor, rcursor, hpoly))
         self._compact = None      # (compacted shard, its slots per partition)
         self._full = None         # (full replica, its slot bytes as a tensor, slots per partition)
@@ -331,7 +344,7 @@ class ShardedKmerCounter:
         m = self.eng.scalar_tensor([int(nbytes)], _int64(self.eng))
         self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
         self._bound = int(m.item())
-        return log_capacity(self._bound, self.cbins)
+        return log_capacity(self._bound, self.cbins) * self._grow
 
     def _peer_buffers(self, nbytes):
         cap = self._agree_capacity(nbytes)
@@ -358,27 +371,47 @@ class ShardedKmerCounter:
             self.eng.reset_log(self._log[1], self._log[2])
         return self._log, self._recv
 
+    def _any(self, flag):
+        """collective OR of a per-rank flag"""
+        f = self.eng.scalar_tensor([1 if flag else 0], _int64(self.eng))
+        self.dist.all_reduce(f, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(f.item()) != 0
+
     def add_records_dev(self, d_recs, nbytes, max_windows=None):
         """Count every k-mer of this rank's record buffer into the sharded table (collective: all ranks call it).
         max_windows: an upper bound on the k-mer windows of the buffer when the caller knows one tighter than
-        nbytes (fixed-length reads: nreads * (L - k + 1)); it only sizes the exchange buffers."""
+        nbytes (fixed-length reads: nreads * (L - k + 1)); it only sizes the exchange buffers.
+
+        Bins are laid out for an even spread plus head-room.  A k-mer (or minimizer) hot enough to overfill its bin on
+        any rank -- an adapter dimer in a tenth of the reads, say -- does not fail the batch: the ranks agree that a bin
+        overflowed, double the head-room (kept for later batches) and repeat the partition step; nothing has touched the
+        table at that point."""
         bound = nbytes if max_windows is None else min(nbytes, max_windows)
+        while True:
+            if self.exchange == "peer":
+                pb = self._timed("buffers", lambda: self._peer_buffers(bound))
+                if pb is None:
+                    self.exchange = "collective"          # peer memory unavailable (agreed by all ranks): fall back for good
+            if self.exchange == "peer":
+                peers, cap, (cur, rcur, hpoly) = pb
+                # phase 1 + exchange in one kernel: this rank's entries land in segment [rank] of every owner's log
+                ovf = self._timed("partition+exchange", lambda: self.eng.partition_peers(d_recs, nbytes, peers, cur, hpoly,
+                                                                                        self.cbins, cap, self.rank))
+            else:
+                (keys, cur, hpoly), (rkeys, rcur, _) = self._timed("buffers", lambda: self._buffers(bound))
+                ovf = self._timed("partition", lambda: self.eng.partition(d_recs, nbytes, keys, cur, hpoly))
+            if not self._any(ovf):
+                break
+            if self._grow >= 64:
+                raise RuntimeError("k-mer log bin still overflows at 64x head-room")
+            self._grow *= 2
+            self.overflow_retries += 1
         if self.exchange == "peer":
-            pb = self._timed("buffers", lambda: self._peer_buffers(bound))
-            if pb is None:
-                self.exchange = "collective"          # peer memory unavailable (agreed by all ranks): fall back for good
-        if self.exchange == "peer":
-            peers, cap, (cur, rcur, hpoly) = pb
-            # phase 1 + exchange in one kernel: this rank's entries land in segment [rank] of every owner's log
-            self._timed("partition+exchange", lambda: self.eng.partition_peers(d_recs, nbytes, peers, cur, hpoly,
-                                                                              self.cbins, cap, self.rank))
             # cursor rows [d*lp, (d+1)*lp) go to rank d (a few KB); completing it also means every rank is past its
             # kernel, i.e. all peer stores into this rank's log have landed
             self._timed("cursors", lambda: self.dist.all_to_all_single(rcur, cur, group=self.group))
             rkeys = peers.rkeys
         else:
-            (keys, cur, hpoly), (rkeys, rcur, _) = self._timed("buffers", lambda: self._buffers(bound))
-            self._timed("partition", lambda: self.eng.partition(d_recs, nbytes, keys, cur, hpoly))
             # bins [d*lp, (d+1)*lp) go to rank d: an equal-split all-to-all over dim 0
             self._timed("cursors", lambda: self.dist.all_to_all_single(rcur, cur, group=self.group))
             self._timed("exchange", lambda: self.dist.all_to_all_single(rkeys, keys, group=self.group))
@@ -387,12 +420,19 @@ class ShardedKmerCounter:
         self.dist.all_reduce(hpoly[4:], op=self.dist.ReduceOp.SUM, group=self.group)
         if self.lp > self.c:
             # the owner splits its coarse bins into table partitions; the source segments merge on the way
-            fcap = log_capacity(self._bound, self.lp, slack=1.3)
-            if self._fine is None or self._fine[0].shape[1] < fcap:
-                self._fine = self.eng.new_fine_log(self.lp, fcap)
-            fkeys, fcur = self._fine
-            self._timed("refine", lambda: self.eng.refine(rkeys, rcur, self.world, self.c, fkeys, fcur,
-                                                          self.rank * self.lp, self.nparts))
+            while True:
+                fcap = log_capacity(self._bound, self.lp, slack=1.3) * self._fine_grow
+                if self._fine is None or self._fine[0].shape[1] < fcap:
+                    self._fine = self.eng.new_fine_log(self.lp, fcap)
+                fkeys, fcur = self._fine
+                ovf = self._timed("refine", lambda: self.eng.refine(rkeys, rcur, self.world, self.c, fkeys, fcur,
+                                                                    self.rank * self.lp, self.nparts))
+                if not self._any(ovf):
+                    break
+                if self._fine_grow >= 64:
+                    raise RuntimeError("fine k-mer log bin still overflows at 64x head-room")
+                self._fine_grow *= 2
+                self.overflow_retries += 1
             self._timed("replay", lambda: self.eng.replay(fkeys, fcur, hpoly, 1))
         else:
             self._timed("replay", lambda: self.eng.replay(rkeys, rcur, hpoly, self.world))
