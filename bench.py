@@ -4,8 +4,8 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A "step" = one pass of the hot path over the whole synthetic read set: clear the table, count every canonical
-25-mer (jellyfish count stage), then per-read k-mer coverage statistics for every read
-(fastaToKmerCoverageStats).  Workload at N=1 = BASELINE.json configs[1]: 10 M PE 2x100 bp reads from a random
+25-mer (jellyfish count stage), keep the k-mers seen at least twice (`jellyfish dump -L 2`, on the device), then per-read
+k-mer coverage statistics for every read against that table (fastaToKmerCoverageStats).  Workload at N=1 = BASELINE.json configs[1]: 10 M PE 2x100 bp reads from a random
 20 k-transcript set (20 M reads, 2.0 Gbase; 1.52 G k-mer positions counted + 1.52 G queried per step).
 
   value     device-resident throughput: reads already in HBM, CUDA events on the library's stream
@@ -30,6 +30,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch on the default workload, from the committed `ncu --set full`
+# captures (profiles/README.md); filled in when a capture of the current kernels exists
+NCU_TRAFFIC_BYTES = {}
 
 K = 25
 METRIC = "25-mers/sec counted+queried"
@@ -345,8 +349,10 @@ def main():
     ap.add_argument("--no-r2t", action="store_true", help="skip the ReadsToTranscripts measurement")
     ap.add_argument("--count-mode", default="auto", choices=["auto", "direct", "log"])
     ap.add_argument("--stats-table", default="auto", choices=["auto", "min2", "full"],
-                    help="min2: statistics read the device-side `dump -L 2` table (bit-identical, see DESIGN.md); "
-                         "auto = full table on 1-2 GPUs, min2 from 4 GPUs on (it is what gets all-gathered)")
+                    help="min2: statistics read the device-side `jellyfish dump -L 2` table -- what the normalisation pipeline "
+                         "feeds fastaToKmerCoverageStats (util/insilico_read_normalization.pl:45,641); its build is part of the "
+                         "timed step; full: the count table itself (bit-identical statistics, see DESIGN.md); auto = min2 at "
+                         "every GPU count")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="multi-GPU k-mer exchange: peer = phase 1 stores into the owners' logs over NVLink (fused), "
                          "collective = NCCL all-to-all of the bins; auto = peer when peer memory maps")
@@ -362,9 +368,8 @@ def main():
     nreads = 2 * npairs
     nwin = read_len - K + 1
     positions_per_step = 2 * nreads * nwin            # counted + queried, per GPU
-    # auto: the full shards are all-gathered on 2 GPUs (6.7 GB received, cheaper than compacting first and the statistics
-    # kernel is faster on the full table); from 4 GPUs on the `dump -L 2` shards are (a quarter of the bytes)
-    min_count = 2 if (args.stats_table == "min2" or (args.stats_table == "auto" and world >= 4)) else 1
+    # the step follows the pipeline at every GPU count: count -> `dump -L 2` (kept on the device) -> statistics on that table
+    min_count = 1 if args.stats_table == "full" else 2
     config = {"workload": f"configs[1]: synthetic {npairs / 1e6:g}M PE 2x{read_len} bp reads from a random "
                           f"{args.ntx}-transcript set, k=25 canonical count + fastaToKmerCoverageStats, per GPU",
               "reads_per_gpu": nreads, "k": K, "unit_definition": "k-mer window positions counted + positions queried",
@@ -558,37 +563,51 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline: the kernel with the largest share of the step ------------------------------------------
+    # ---- roofline ---------------------------------------------------------------------------------------------
+    # Algorithmic HBM bytes are SURVEY §8(d)'s per-unit figures: counting = one 16-B slot read-modify-write
+    # per k-mer occurrence = 64 B; a lookup = one 32-B sector; `dump -L 2` = the count table read once (16 B/slot) + 64 B
+    # per kept k-mer.  Counting is two kernels (k_log_tiles: reads -> super-k-mer log; k_log_replay: log -> table, plus
+    # k_log_refine beyond 512 partitions) that only make sense together, so the figure is attributed to the STAGE and the
+    # stage's time is the sum of its kernels' CUDA-event times.  `roofline` reports the stage with the largest time.
     peak, peak_kind = load_peaks()
     count_positions = nreads * nwin
-    # algorithmic HBM bytes per k-mer position: log append 8 B written, replay 8 B read + the table
-    # streamed through L2 once (read + write-back of every 16-B slot), direct insert / lookup one 32-B sector each way
     table_bytes = tinfo["capacity"] * 16 // world
-    alg = {"k_log_tiles": count_positions * 8 + nbytes,
-           "k_log_replay": count_positions * 8 + 2 * table_bytes,
-           "k_flat_tiles<COUNT>": count_positions * 64 + nbytes,
-           "k_cov_stats": count_positions * 32 + nbytes + 12 * nreads,
-           "k_rehash": table_bytes + qinfo["distinct"] * 64 // world}
-    kernels = []
+    stage_of = {"k_log_tiles": "count", "k_log_replay": "count", "k_log_refine": "count", "k_flat_tiles<COUNT>": "count",
+                "k_log_plan": "count", "k_rehash": "dump_L2", "k_cov_stats": "stats", "k_cov_stats_long": "stats"}
+    stage_bytes = {"count": count_positions * 64 + nbytes,
+                   "dump_L2": table_bytes + qinfo["distinct"] * 64 // world,
+                   "stats": count_positions * 32 + nbytes + 12 * nreads}
+    stage_units = {"count": count_positions, "dump_L2": tinfo["capacity"] // world, "stats": count_positions}
+    kernels, stages = [], {}
     step_kernel_ms = sum(v[0] for v in ktimes.values())
     for name, (kms, n) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
-        e = {"kernel": name, "ms": round(kms, 3), "launches": n, "share": round(kms / step_kernel_ms, 3)}
-        if name in alg and kms > 0:
-            e["algorithmic_bytes"] = int(alg[name])
-            e["achieved_gbs"] = round(alg[name] / (kms / 1e3) / 1e9, 1)
+        st = stage_of.get(name, "other")
+        kernels.append({"kernel": name, "stage": st, "ms": round(kms, 3), "launches": n, "share": round(kms / step_kernel_ms, 3)})
+        stages.setdefault(st, {"ms": 0.0, "kernels": []})
+        stages[st]["ms"] += kms
+        stages[st]["kernels"].append(name)
+    for st, e in stages.items():
+        e["ms"] = round(e["ms"], 3)
+        e["share"] = round(e["ms"] / step_kernel_ms, 3)
+        if st in stage_bytes and e["ms"] > 0:
+            e["units"] = int(stage_units[st])
+            e["algorithmic_bytes"] = int(stage_bytes[st])
+            e["achieved_gbs"] = round(stage_bytes[st] / (e["ms"] / 1e3) / 1e9, 1)
             e["frac_of_hbm_peak"] = round(e["achieved_gbs"] / peak, 4)
-        kernels.append(e)
-    top = kernels[0]
-    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures of exactly
-    # this workload, profiles/r01_ncu_full_v3_count_stats_raw.csv; null for any other shape
-    ncu_traffic = {"k_cov_stats": 152.1e9, "k_log_replay": 33.6e9, "k_log_tiles": 13.9e9}
-    default_shape = (world == 1 and npairs == 10_000_000 and read_len == 100 and args.ntx == 20_000 and min_count == 1)
-    traffic = ncu_traffic.get(top["kernel"]) if default_shape else None
-    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("achieved_gbs"), "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": top.get("frac_of_hbm_peak"), "traffic": traffic,
-                "units_per_launch": count_positions, "kernel_ms": top["ms"], "kernels": kernels,
-                "note": "achieved = algorithmic bytes of one launch / its CUDA-event time; traffic = ncu DRAM bytes of "
-                        "one launch of the same workload (profiles/README.md), bytes"}
+    top_name = max((st for st in stages if st in stage_bytes), key=lambda st: stages[st]["ms"])
+    top = stages[top_name]
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the stage's kernels from the `ncu --set full`
+    # capture of exactly this workload (profiles/README.md names the file); null for any other shape
+    ncu_traffic = NCU_TRAFFIC_BYTES
+    default_shape = (world == 1 and npairs == 10_000_000 and read_len == 100 and args.ntx == 20_000 and min_count == 2)
+    traffic = None
+    if default_shape and all(k_ in ncu_traffic for k_ in top["kernels"] if not k_.startswith("k_log_plan")):
+        traffic = sum(ncu_traffic[k_] for k_ in top["kernels"] if not k_.startswith("k_log_plan"))
+    roofline = {"bound": "hbm", "kernel": " + ".join(top["kernels"]), "stage": top_name, "achieved": top.get("achieved_gbs"),
+                "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": top.get("frac_of_hbm_peak"), "traffic": traffic,
+                "units_per_launch": top.get("units"), "kernel_ms": top["ms"], "stages": stages, "kernels": kernels,
+                "note": "achieved = algorithmic bytes of the stage (SURVEY 8d per-unit figure x units) / sum of its kernels' "
+                        "CUDA-event times in one step; traffic = ncu DRAM bytes of the same kernels, one launch each, bytes"}
     if not args.no_gups:
         slots = max(tinfo["capacity"] // world, 1 << 29)         # >= 8 GiB of 16-B slots
         nops = 1 << 30
@@ -597,7 +616,7 @@ def main():
             gms = ctx.gups(slots, nops, mode, reps=2)
             g[name] = {"gops": round(nops / (gms / 1e3) / 1e9, 2), "ms": round(gms, 2)}
         ra = {"table_gib": round(slots * 16 / 2 ** 30, 1), **g}
-        count_ms = sum(ktimes.get(n, (0, 0))[0] for n in ("k_log_tiles", "k_log_replay", "k_flat_tiles<COUNT>"))
+        count_ms = stages.get("count", {}).get("ms", 0)
         stats_ms = ktimes.get("k_cov_stats", (0, 0))[0]
         if count_ms:
             ra["count_gkmers_s"] = round(count_positions / count_ms / 1e6, 2)

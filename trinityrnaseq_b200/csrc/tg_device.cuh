@@ -34,6 +34,7 @@ struct __align__(16) Slot {
 constexpr unsigned long long KEY_TAG = 1ull << 63;
 constexpr unsigned BUCKET_SLOTS = HOME_SLOTS; // 128 B home bucket; every partition is a whole number of buckets
 constexpr unsigned WALK_SLOTS = 4;            // the key-hashed walk starts at a 64-B group boundary (two 256-bit loads)
+constexpr unsigned long long WALK_LIMIT = 1ull << 16;   // slots an insert walks before it declares its partition full
 constexpr unsigned AUX_DISPLACED = 0x80000000u;
 constexpr unsigned AUX_LABEL_MASK = 0x7FFFFFFFu;
 
@@ -151,7 +152,11 @@ __device__ __forceinline__ Slot* table_upsert_finish(const TableView& t, unsigne
     // the home slot belongs to another key: leave a note there and go by the key's own hash
     if (!(__ldcg(&hs->aux) & AUX_DISPLACED)) atomicOr(&hs->aux, AUX_DISPLACED);
     unsigned long long off = walk_start(t.g, key);
-    for (unsigned long long probes = 0; probes <= t.g.subcap; probes++) {
+    // A walk is a handful of slots at the loads the host keeps (<= 0.7).  WALK_LIMIT slots without a free one means the
+    // partition is full: raise the overflow flag and give up -- and once it is up every other insert gives up at once, so an
+    // undersized table fails in milliseconds instead of walking millions of slots per key.
+    const unsigned long long limit = t.g.subcap < WALK_LIMIT ? t.g.subcap : WALK_LIMIT;
+    for (unsigned long long probes = 0; probes <= limit; probes++) {
         Slot* sl = &t.slots[base + off];
         cur = __ldcg(&sl->key);
         if (cur == key) return sl;
@@ -160,6 +165,7 @@ __device__ __forceinline__ Slot* table_upsert_finish(const TableView& t, unsigne
             if (old == 0ull) { claimed++; return sl; }
             if (old == key) return sl;
         }
+        if ((probes & 63ull) == 63ull && *reinterpret_cast<volatile int*>(t.error) != 0) return nullptr;
         off = walk_next(t.g, off);
     }
     atomicExch(t.error, 1);
@@ -215,7 +221,8 @@ __device__ __forceinline__ bool table_label_max(const TableView& t, unsigned lon
 __device__ __forceinline__ uint2 table_walk_find(const Slot* __restrict__ slots, const Geo& g, unsigned long long base,
                                                   unsigned long long key) {
     unsigned long long off = walk_start(g, key);
-    for (unsigned long long probes = 0; probes <= g.subcap; probes += WALK_SLOTS) {     // bounded: a full partition cannot hang
+    const unsigned long long limit = g.subcap < WALK_LIMIT ? g.subcap : WALK_LIMIT;     // an insert never went further
+    for (unsigned long long probes = 0; probes <= limit; probes += WALK_SLOTS) {
         const Slot* b = &slots[base + off];
         unsigned long long k0, w0, k1, w1, k2, w2, k3, w3;
         ld_slot_pair(b, k0, w0, k1, w1);

@@ -1045,28 +1045,34 @@ cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, u
 // =========================================================================================================
 // GUPS: the measured random-access roofline for this table geometry
 // =========================================================================================================
+// Every thread keeps GUPS_FLIGHT independent accesses in flight (a dependent chain per thread would measure latency, not
+// the memory system): mode 0 = 256-bit loads of two adjacent slots (one 32-B sector, what a lookup of the key-hashed walk
+// issues), 1 = 8-B load + RED.add on the same slot (steady-state count), 2 = CAS + RED.add.
+constexpr int GUPS_FLIGHT = 8;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_gups(Slot* slots, uint64_t cap, uint64_t nops, unsigned long long* sink) {
     const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long acc = 0;
-    for (uint64_t i = tid; i < nops; i += 4 * stride) {
-        unsigned long long idx[4];
+    for (uint64_t i = tid; i < nops; i += GUPS_FLIGHT * stride) {
+        unsigned long long idx[GUPS_FLIGHT];
 #pragma unroll
-        for (int u = 0; u < 4; u++) idx[u] = __umul64hi(mix64(0x9E3779B97F4A7C15ull * (i + u * stride + 1)), cap);
+        for (int u = 0; u < GUPS_FLIGHT; u++)
+            idx[u] = __umul64hi(mix64(0x9E3779B97F4A7C15ull * (i + u * stride + 1)), cap / 2) * 2;     // a sector-aligned pair
         if (MODE == 0) {
-            uint4 v[4];
+            unsigned long long k0[GUPS_FLIGHT], w0[GUPS_FLIGHT], k1[GUPS_FLIGHT], w1[GUPS_FLIGHT];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (i + u * stride < nops) v[u] = __ldcg(reinterpret_cast<const uint4*>(&slots[idx[u]]));
-                else v[u] = make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < GUPS_FLIGHT; u++) {
+                k0[u] = w0[u] = k1[u] = w1[u] = 0ull;
+                if (i + u * stride < nops) ld_slot_pair(&slots[idx[u]], k0[u], w0[u], k1[u], w1[u]);
+            }
 #pragma unroll
-            for (int u = 0; u < 4; u++) acc += v[u].x + v[u].z;
+            for (int u = 0; u < GUPS_FLIGHT; u++) acc += k0[u] + w0[u] + k1[u] + w1[u];
         } else {
-            unsigned long long kv[4];
+            unsigned long long kv[GUPS_FLIGHT];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < GUPS_FLIGHT; u++) {
                 kv[u] = 0;
                 if (i + u * stride < nops) {
                     if (MODE == 1) kv[u] = __ldcg(&slots[idx[u]].key);
@@ -1074,7 +1080,7 @@ k_gups(Slot* slots, uint64_t cap, uint64_t nops, unsigned long long* sink) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < GUPS_FLIGHT; u++)
                 if (i + u * stride < nops) { atomicAdd(&slots[idx[u]].val, 1u); acc += kv[u]; }
         }
     }
@@ -1084,7 +1090,7 @@ k_gups(Slot* slots, uint64_t cap, uint64_t nops, unsigned long long* sink) {
 cudaError_t launch_gups(Slot* slots, uint64_t cap, uint64_t nops, int mode, unsigned long long* d_sink, int sm_count,
                         cudaStream_t s) {
     TimedLaunch timed("k_gups", s);
-    const int grid = sm_count * 8;
+    const int grid = sm_count * 6;
     if (mode == 0) k_gups<0><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);
     else if (mode == 1) k_gups<1><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);
     else k_gups<2><<<grid, 256, 0, s>>>(slots, cap, nops, d_sink);

@@ -94,16 +94,26 @@ TG_HD void key_home(unsigned p0, unsigned p1, int k, unsigned& h, unsigned& j) {
     j = best & ORD_POS_MASK;
 }
 
-// A home travels as ONE word: hj = (hash & ~7) | slot.  Partition and bucket use the hash with its low three bits cleared,
-// so that every holder of an hj (log entries, queued walks) addresses exactly like the code that computed it.
+// A home travels as ONE word: hj = (hash & ~7) | slot.  Partition and bucket are taken from a bijective REMIX of the hash with
+// its low three bits cleared -- never from the hash itself: a minimizer is the SMALLEST of eight hashes, so its value is far
+// from uniform (an eighth of all minimizers fall into the lowest 1/64 of the range), while its remix is uniform over the
+// distinct minimizers.  Every holder of an hj (log entries, queued walks) addresses exactly like the code that computed it.
 TG_HD unsigned pack_home(unsigned h, unsigned j) { return (h & ~7u) | j; }
 TG_HD unsigned home_slot(unsigned hj) { return hj & 7u; }
-TG_HD unsigned home_part(unsigned hj, unsigned nparts) { return (unsigned)(((unsigned long long)(hj & ~7u) * nparts) >> 32); }
+TG_HD unsigned home_mix(unsigned hj) {
+    unsigned x = (hj & ~7u) * 0x9E3779B1u;
+    x ^= x >> 16;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 13;
+    return x;
+}
+TG_HD unsigned home_part(unsigned hj, unsigned nparts) { return (unsigned)(((unsigned long long)home_mix(hj) * nparts) >> 32); }
+// (inside a partition the top bits of the remix are fixed: the bucket takes a second remix)
 TG_HD unsigned home_bucket(unsigned hj, unsigned nbuckets) {
-    unsigned x = (hj & ~7u) * 0xB5297A4Du;
+    unsigned x = home_mix(hj) * 0xC2B2AE35u;
     x ^= x >> 15;
-    x *= 0x68E31DA5u;
-    x ^= x >> 14;
+    x *= 0x27D4EB2Fu;
+    x ^= x >> 16;
     return (unsigned)(((unsigned long long)x * nbuckets) >> 32);
 }
 
