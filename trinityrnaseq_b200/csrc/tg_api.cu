@@ -673,7 +673,7 @@ static uint64_t log_launch_cost(const tg_ctx*, const KeyLog&, uint64_t nbytes) {
 // entries that can be appended to an empty log without any bin expected to overflow
 static uint64_t log_room(const KeyLog& lg) {
     if (lg.cap <= LOG_BIN_SLACK) return 0;
-    return (uint64_t)((double)(lg.cap - LOG_BIN_SLACK) / LOG_BIN_FACTOR) * lg.nbins;
+    return (uint64_t)((double)(lg.cap - LOG_BIN_SLACK) / LOG_BIN_FACTOR * lg.nbins) + lg.nbins;     // (+ rounding of cap)
 }
 
 // a log laid out for `entries` appended entries per replay (fewer if the HBM budget is smaller); *ok = false when
@@ -682,7 +682,7 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     tg_ctx* c = t->ctx;
     *ok = false;
     const unsigned nbins = log_bins_for(t);
-    const uint64_t want = (uint64_t)((double)entries / nbins * LOG_BIN_FACTOR) + LOG_BIN_SLACK;
+    const uint64_t want = ((uint64_t)((double)entries / nbins * LOG_BIN_FACTOR) + LOG_BIN_SLACK + LOG_CAP_ALIGN) / LOG_CAP_ALIGN * LOG_CAP_ALIGN;
     if (t->log.keys && t->log.nbins == nbins && t->log.cap >= std::min<uint64_t>(want, LOG_CAP_MAX) / LOG_CAP_ALIGN * LOG_CAP_ALIGN) {
         *ok = true;                                     // the common case costs no driver call (cudaMemGetInfo may block)
         return TG_OK;
@@ -696,7 +696,7 @@ static int ensure_log(tg_table* t, uint64_t entries, bool* ok) {
     per_bin = std::min<uint64_t>(per_bin, budget / sizeof(LogEntry) / nbins);
     per_bin = std::min<uint64_t>(per_bin, LOG_CAP_MAX);
     per_bin = per_bin / LOG_CAP_ALIGN * LOG_CAP_ALIGN;
-    if (per_bin < 2 * LOG_BIN_SLACK) return TG_OK;
+    if (per_bin < want && per_bin < 2 * LOG_BIN_SLACK) return TG_OK;    // budget-limited down to a useless size
     if (t->log.keys && t->log.nbins == nbins && t->log.cap >= per_bin) { *ok = true; return TG_OK; }
     if (t->log.pending_ub) { *ok = t->log.keys != nullptr; return TG_OK; }   // holds entries: keep its layout
     log_release(t);
@@ -902,7 +902,10 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
         return TG_OK;
     }
     // segments of whole tiles, each small enough for the log; everything stays stream-ordered on stream 0
-    uint64_t seg = log_room(t->log) * 2 / CT_TILE * CT_TILE;        // bytes whose entries the log is laid out for
+    // one segment when the log was laid out for this input (the usual case); else equal segments of whole tiles
+    const uint64_t room = std::max<uint64_t>(log_room(t->log), 1);
+    const uint64_t nseg = (log_launch_cost(c, t->log, nbytes) + room - 1) / room;
+    uint64_t seg = ((nbytes + nseg - 1) / nseg + CT_TILE - 1) / CT_TILE * CT_TILE;
     if (seg < (uint64_t)CT_TILE) seg = CT_TILE;
     for (uint64_t pos = 0; pos < nbytes; pos += seg) {
         const uint64_t n = std::min(seg, nbytes - pos);

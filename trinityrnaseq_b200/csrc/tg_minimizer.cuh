@@ -149,6 +149,19 @@ TG_HD void strip_minimizers(const unsigned (&hx)[PER + HOME_SLOTS - 1], unsigned
         vr[i] = sr[i] < pr ? sr[i] : pr;
     }
 }
+// one window on its own: hx[0..7] are the hashes of its eight m-mers
+TG_HD void window_minimizers(const unsigned (&hx)[HOME_SLOTS], unsigned& vl, unsigned& vr) {
+    unsigned a = ord_left(hx[0], 0u), b = ord_right(hx[0], 0u);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 1; q < HOME_SLOTS; q++) {
+        const unsigned l = ord_left(hx[q], (unsigned)q), r = ord_right(hx[q], (unsigned)q);
+        a = l < a ? l : a;
+        b = r < b ? r : b;
+    }
+    vl = a; vr = b;
+}
 // position (relative to the strip start) of the m-mer that is the KEY's minimizer, and its slot j in key orientation;
 // i = window index inside the strip, is_rc = the key is the reverse complement of the window
 TG_HD unsigned strip_pick(unsigned vl, unsigned vr, int i, bool is_rc, unsigned& j) {

@@ -3,14 +3,14 @@
 //   k_cov_stats[_long]    compute_kmer_coverage / median / mean / stDev   
 //   k_assign[_long]       ReadsToTranscripts per-read vote                (§8a R5, R7-R9)
 //
-// Warp path (reads up to PR_MAXWIN windows): one warp per read, and every lane owns a STRIP of PER consecutive windows
-// (PER = ceil(windows / 32)).  The front end is the same for both kernels:
+// Warp path (reads up to PR_MAXWIN windows): one warp per read; in round i lane l handles window 32 i + l, so that one
+// load instruction of the warp covers 32 CONSECUTIVE windows.  The front end is the same for both kernels:
 //   1. ballot transpose of the read into bit planes (shared memory);
 //   2. H pass: strand-symmetric hash of the m-mer at every position (one position per lane and round);
-//   3. per strip: sliding minimum over the PER + 7 hashes -> minimizer (leftmost and rightmost) of every window
-//      (tg_minimizer.cuh), canonical key, home slot = (bucket of the minimizer hash, slot = minimizer position);
+//   3. per window: minimum over its 8 m-mer hashes -> minimizer (leftmost and rightmost, tg_minimizer.cuh), canonical key,
+//      home slot = (bucket of the minimizer hash, slot = minimizer position);
 //   4. ONE 16-byte load per window from the home slot.  Windows that share a minimizer read neighbouring slots of one
-//      128-byte bucket, so the load instruction of the warp covers ~1/5 of the DRAM granules a key-hashed table needs.
+//      128-byte bucket, so the 32 loads of a round fall into ~7 buckets instead of 32 random DRAM granules.
 //   5. the few windows whose home slot holds another key with the DISPLACED flag are queued in shared memory and settled
 //      by a key-hashed walk afterwards, one queued window per lane, all walks in flight together -- instead of the whole
 //      warp waiting on a rare lane in every round.
@@ -116,10 +116,9 @@ __device__ __forceinline__ void front_planes_hashes(WarpFront& f, const uint8_t*
     __syncwarp();
 }
 
-// one window of a strip: planes -> canonical key (or the forward one), orientation, home (h, j)
+// one window: planes -> canonical key (or the forward one), orientation, packed home
 struct Window { unsigned long long key; unsigned hj, f0, f1; bool valid, is_rc, pal; };
-__device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nwin, int k, unsigned mk, bool canonical, int s0,
-                                               int i, unsigned vl, unsigned vr) {
+__device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nwin, int k, unsigned mk, bool canonical) {
     Window w;
     w.valid = false; w.is_rc = false; w.pal = false; w.key = 0ull; w.hj = 0u; w.f0 = 0u; w.f1 = 0u;
     if (p < nwin) {
@@ -131,9 +130,12 @@ __device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nw
             w.is_rc = canonical && kr < kf;
             w.pal = kr == kf;
             w.key = w.is_rc ? kr : kf;
-            unsigned j;
-            const unsigned sp = strip_pick(vl, vr, i, w.is_rc, j);
-            w.hj = pack_home(f.hx[s0 + (int)sp], j);
+            unsigned hx[HOME_SLOTS], vl, vr, j;
+#pragma unroll
+            for (int q = 0; q < HOME_SLOTS; q++) hx[q] = f.hx[p + q];
+            window_minimizers(hx, vl, vr);
+            const unsigned sp = strip_pick(vl, vr, 0, w.is_rc, j);
+            w.hj = pack_home(f.hx[p + (int)sp], j);
             w.valid = true;
         }
     }
@@ -167,21 +169,20 @@ __device__ __forceinline__ void stats_drain(StatsWarp& sw, const Slot* __restric
     __syncwarp();
 }
 
-// Median of the n values a warp holds in registers (lane l owns x[0..PER) = values PER*l .., live where < n), WITHOUT
+// Median of the n values a warp holds in registers (lane l owns x[i] = value 32 i + l, live where < n), WITHOUT
 // sorting: a bisection on the VALUE between the warp minimum and maximum (coverage values of one read sit in a narrow
 // band, so a handful of rounds), each round one compare per element and one redux.sync.  Returns median_coverage() of
 // fastaToKmerCoverageStats.cpp:337-347: odd n -> the middle element, even n -> the (wrapping) u32 mean of the two middle
 // elements.
 template <int PER>
 __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], int n, int lane, unsigned lo, unsigned hi) {
-    const int s0 = PER * lane;
     const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
     // smallest value with at least k1 + 1 elements <= it = the element of rank k1
     while (lo < hi) {
         const unsigned mid = lo + ((hi - lo) >> 1);
         unsigned cnt = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) cnt += (s0 + i < n && x[i] <= mid) ? 1u : 0u;
+        for (int i = 0; i < PER; i++) cnt += (32 * i + lane < n && x[i] <= mid) ? 1u : 0u;
         cnt = __reduce_add_sync(FULL, cnt);
         if (cnt >= k1 + 1u) hi = mid; else lo = mid + 1u;
     }
@@ -190,7 +191,7 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
     unsigned le = 0, nxt = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const bool live = s0 + i < n;
+        const bool live = 32 * i + lane < n;
         le += (live && x[i] <= x1) ? 1u : 0u;
         if (live && x[i] > x1) nxt = min(nxt, x[i]);
     }
@@ -204,17 +205,12 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
 template <int PER>
 __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, int nwin, int k,
                                            unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean) {
-    const int s0 = PER * lane;
-    unsigned strip[PER + HOME_SLOTS - 1], vl[PER], vr[PER];
-#pragma unroll
-    for (int q = 0; q < PER + HOME_SLOTS - 1; q++) strip[q] = sw.f.hx[s0 + q];
-    strip_minimizers<PER>(strip, vl, vr);
     const unsigned lt = (1u << lane) - 1u;
     unsigned nq = 0;                               // queued walks (warp-uniform)
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const int p = s0 + i;
-        const Window w = front_window(sw.f, p, nwin, k, mk, canonical, s0, i, vl[i], vr[i]);
+        const int p = 32 * i + lane;
+        const Window w = front_window(sw.f, p, nwin, k, mk, canonical);
         unsigned v = 0;
         bool need = false;
         if (w.valid) {
@@ -241,8 +237,8 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
     unsigned long long part = 0;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const bool live = s0 + i < nwin;
-        x[i] = live ? sw.cov[used + s0 + i] : 0u;
+        const bool live = 32 * i + lane < nwin;
+        x[i] = live ? sw.cov[used + 32 * i + lane] : 0u;
         if (live) { mn = min(mn, x[i]); mx = max(mx, x[i]); part += x[i]; }
     }
     const unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
@@ -608,18 +604,13 @@ template <int PER>
 __device__ __forceinline__ void assign_read(AssignWarp& aw, const Slot* __restrict__ slots, const Geo& geo,
                                             const uint8_t* __restrict__ lut, int nwin, int k, unsigned mk, int strand, int lane,
                                             unsigned& nh_out) {
-    const int s0 = PER * lane;
-    unsigned strip[PER + HOME_SLOTS - 1], vl[PER], vr[PER];
-#pragma unroll
-    for (int q = 0; q < PER + HOME_SLOTS - 1; q++) strip[q] = aw.f.hx[s0 + q];
-    strip_minimizers<PER>(strip, vl, vr);
     const unsigned lt = (1u << lane) - 1u;
     unsigned nq = 0, nh = 0;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const int p = s0 + i;
+        const int p = 32 * i + lane;
         // label tables are keyed canonically whatever the library type: the strand flag only drops the second lookup
-        const Window w = front_window(aw.f, p, nwin, k, mk, true, s0, i, vl[i], vr[i]);
+        const Window w = front_window(aw.f, p, nwin, k, mk, true);
         bool do_f = false, do_r = false, need = false;
         uint2 v = make_uint2(0u, 0u);
         if (w.valid) {                     // a window with a non-ACGT character can never equal a table k-mer
