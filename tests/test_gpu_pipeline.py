@@ -44,7 +44,7 @@ def _run(home, outdir, left, right):
     env = dict(os.environ, LC_ALL="C", PATH=BIN + os.pathsep + os.environ["PATH"])      # our jellyfish first on $PATH
     cmd = ["perl", os.path.join(home, "util", "insilico_read_normalization.pl"), "--seqType", "fa", "--JM", "1G", "--max_cov", "200",
            "--min_cov", "1", "--CPU", "4", "--output", outdir, "--max_CV", "10000", "--left", left, "--right", right,
-           "--pairs_together", "--PARALLEL_STATS"]
+           "--pairs_together", "--PARALLEL_STATS", "--no_cleanup"]        # keep tmp_normalized_reads/ (the .accs list)
     r = subprocess.run(cmd, capture_output=True, env=env, timeout=1200)
     assert r.returncode == 0, (r.stdout.decode()[-2000:], r.stderr.decode()[-4000:])
     out = {}

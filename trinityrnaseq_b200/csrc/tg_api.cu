@@ -108,7 +108,7 @@ struct tg_table {
     int kind = TG_TABLE_COUNT;
     int k = 25;
     Slot* slots = nullptr;
-    Geo g{0, 1, 0, 1, 25};
+    Geo g{0, 1, 0, 1, 25, 0u};
     uint64_t cap = 0;                          // slots held here = g.nlocal * g.subcap
     unsigned long long* d_claimed = nullptr;   // [0] = distinct keys
     int* d_error = nullptr;
@@ -134,7 +134,7 @@ static Geo pick_geo(uint64_t slots, size_t part_bytes) {
     Geo g;
     g.nparts = (unsigned)np; g.part0 = 0; g.nlocal = (unsigned)np;
     g.subcap = whole_buckets((slots + np - 1) / np);
-    g.k = 0;            // set by table_new / table_regrow
+    g.k = 0; g.filter = 0;            // set by table_new / table_regrow
     return g;
 }
 
@@ -365,7 +365,7 @@ void tg_free(void* p) { free(p); }
 // ---------------------------------------------------------------------------------------------------------
 static int table_new(tg_ctx* c, int kind, int k, Geo g, tg_table** out) {
     tg_table* t = new tg_table();
-    g.k = k;
+    g.k = k; g.filter = kind == TG_TABLE_COUNT ? 1u : 0u;
     t->ctx = c; t->kind = kind; t->k = k; t->g = g;
     t->cap = (uint64_t)g.nlocal * g.subcap;
     int rc = table_alloc(c, t->cap, &t->slots);
@@ -459,18 +459,37 @@ int tg_table_clear(tg_table* t) {
     return TG_OK;
 }
 
+// Re-insert the k-mers of t with count >= min_count into `to` (growth, `dump -L n` on the device).  Who comes first keeps
+// its home slot, and a k-mer that is looked up a thousand times per step should not lose it to one of its own error
+// variants (same minimizer, same slot, a count of 2): count tables go in three passes, the most frequent k-mers first.
+static int rehash_by_priority(tg_table* t, TableView to, uint32_t min_count) {
+    tg_ctx* c = t->ctx;
+    if (t->kind == TG_TABLE_LABEL) {
+        CU(launch_rehash(t->slots, t->cap, to, 1, 0, 0xFFFFFFFFu, c->stream[0]));
+        c->launches++;
+        return TG_OK;
+    }
+    const uint32_t lo_of[3] = {64u, 8u, 0u}, hi_of[3] = {0xFFFFFFFFu, 63u, 7u};
+    for (int pass = 0; pass < 3; pass++) {
+        const uint32_t lo = std::max(lo_of[pass], min_count), hi = hi_of[pass];
+        if (lo > hi) continue;
+        CU(launch_rehash(t->slots, t->cap, to, 0, lo, hi, c->stream[0]));
+        c->launches++;
+    }
+    return TG_OK;
+}
+
 // Move the table into a new geometry (growth).  Both streams must be idle.
 static int table_regrow(tg_table* t, Geo ng) {
     tg_ctx* c = t->ctx;
-    ng.k = t->k;
+    ng.k = t->k; ng.filter = t->g.filter;
     const uint64_t ncap = (uint64_t)ng.nlocal * ng.subcap;
     Slot* fresh = nullptr;
     int rc;
     if ((rc = table_alloc(c, ncap, &fresh))) return rc;
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
     TableView nv{fresh, ng, t->d_claimed, t->d_error};
-    CU(launch_rehash(t->slots, t->cap, nv, t->kind == TG_TABLE_LABEL, 0, c->stream[0]));
-    c->launches++;
+    if (int rc2 = rehash_by_priority(t, nv, 0)) { cudaFree(fresh); return rc2; }
     CU(cudaStreamSynchronize(c->stream[0]));
     CU(cudaFree(t->slots));
     t->slots = fresh;
@@ -589,8 +608,7 @@ int tg_table_compact_into(tg_table* t, uint32_t min_count, tg_table* dst) {
     int rc = flush_log(t);
     if (rc) return rc;
     if ((rc = tg_table_clear(dst))) return rc;       // syncs both streams
-    CU(launch_rehash(t->slots, t->cap, dst->view(), t->kind == TG_TABLE_LABEL, min_count, c->stream[0]));
-    c->launches++;
+    if ((rc = rehash_by_priority(t, dst->view(), min_count))) return rc;
     return TG_OK;                                    // stream-ordered; an overfull destination raises its error flag
 }
 
@@ -793,7 +811,7 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     const uint64_t per_entry = (uint64_t)le_max_run(t->k);
     if (sample == 0) { *est = total * per_entry; return TG_OK; }
     Geo sg;
-    sg.subcap = whole_buckets(sample * per_entry * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1; sg.k = t->k;
+    sg.subcap = whole_buckets(sample * per_entry * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1; sg.k = t->k; sg.filter = 1u;
     Slot* scratch = nullptr;
     unsigned long long* d_n = nullptr;
     int rc;
@@ -930,7 +948,7 @@ int tg_count_partition_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k
     if (bind(c)) return TG_ERR_CUDA;
     LogView lg = local_log_view((LogEntry*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error,
                                 (unsigned long long*)d_hpoly);
-    TableView none{nullptr, Geo{0, 1, 0, 1, k}, nullptr, nullptr};
+    TableView none{nullptr, Geo{0, 1, 0, 1, k, 0u}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
     return TG_OK;
@@ -960,7 +978,7 @@ int tg_count_partition_peers_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes,
     while ((1u << sh) < lp) sh++;
     lg.cursor = (unsigned int*)d_cursor; lg.nbins = nbins; lg.cap = cap; lg.lp_shift = sh; lg.src = my_rank;
     lg.error = c->d_error; lg.hpoly = (unsigned long long*)d_hpoly;
-    TableView none{nullptr, Geo{0, 1, 0, 1, k}, nullptr, nullptr};
+    TableView none{nullptr, Geo{0, 1, 0, 1, k, 0u}, nullptr, nullptr};
     CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
     c->launches++;
     return TG_OK;
@@ -982,7 +1000,7 @@ int tg_log_refine_dev(tg_ctx* c, const void* d_keys, const void* d_cursor, uint3
     CU(c->scratch.ensure(need));
     CU(launch_log_refine((const LogEntry*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, ncoarse,
                          (unsigned long long*)c->scratch.p, (LogEntry*)d_out_keys, (unsigned int*)d_out_cursor,
-                         out_cap, nfine, fine0, nfine_global, c->d_error, TableView{nullptr, Geo{0, 1, 0, 1, 0}, nullptr, nullptr},
+                         out_cap, nfine, fine0, nfine_global, c->d_error, TableView{nullptr, Geo{0, 1, 0, 1, 0, 0u}, nullptr, nullptr},
                          c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;

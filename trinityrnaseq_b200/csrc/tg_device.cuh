@@ -37,6 +37,14 @@ constexpr unsigned WALK_SLOTS = 4;            // the key-hashed walk starts at a
 constexpr unsigned long long WALK_LIMIT = 1ull << 16;   // slots an insert walks before it declares its partition full
 constexpr unsigned AUX_DISPLACED = 0x80000000u;
 constexpr unsigned AUX_LABEL_MASK = 0x7FFFFFFFu;
+// Count tables have no use for the low 31 bits of aux, so they make the DISPLACED note selective: a key that loses its home
+// slot also sets bit aux_filter_bit(key) there, and a lookup goes on to the key-hashed walk only when ITS bit is set.  The
+// error variants of an expressed k-mer share its minimizer and so its home slot; most of them occur once and are not in a
+// `dump -L 2` table at all -- without the filter every one of their lookups would walk for nothing.
+__device__ __forceinline__ unsigned aux_filter_bit(unsigned long long key) {
+    unsigned v = ((unsigned)key * 0x9E3779B1u + (unsigned)(key >> 32) * 0x85EBCA77u) >> 27;      // 0..31
+    return 1u << (v == 31u ? 0u : v);
+}
 
 // Table geometry.  The table is an array of `nparts` PARTITIONS of `subcap` slots each; a key lives in the partition
 // chosen by the top bits of its home hash and never leaves it (both its home bucket and its key-hashed walk are inside).
@@ -51,6 +59,7 @@ struct Geo {
     unsigned int part0;          // first partition held by this view
     unsigned int nlocal;         // partitions held by this view (slots[] has nlocal * subcap entries)
     int k;                       // k-mer length of the keys (the home of a key depends on it)
+    unsigned int filter;         // 1 = count table: the low 31 bits of aux are a filter of the slot's displaced keys
 };
 
 struct TableView {
@@ -139,18 +148,22 @@ __device__ __forceinline__ void ld_slot_pair(const Slot* p, unsigned long long& 
 //
 // The slot of `key` (claimed if new; claimed++ then), or nullptr on a full partition / a foreign key (error raised).
 // Split in two so that a caller can have the home-slot loads of several keys in flight before it settles any of them:
-// `cur` is the key read from t.slots[home] (ld.cg).
+// `cur` is the whole home slot read with ld.cg ({key lo, key hi, val, aux}).
+__device__ __forceinline__ uint4 ld_slot(const Slot* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ Slot* table_upsert_finish(const TableView& t, unsigned long long key, unsigned long long base,
-                                                     unsigned long long home, unsigned long long cur, unsigned& claimed) {
+                                                     unsigned long long home, uint4 cur4, unsigned& claimed) {
     Slot* hs = &t.slots[home];
+    unsigned long long cur = ((unsigned long long)cur4.y << 32) | cur4.x;
     if (cur == key) return hs;
     if (cur == 0ull) {
         const unsigned long long old = atomicCAS(&hs->key, 0ull, key);
         if (old == 0ull) { claimed++; return hs; }
         if (old == key) return hs;
+        cur4.w = 0u;                      // the slot was claimed under our eyes: its note cannot be trusted
     }
-    // the home slot belongs to another key: leave a note there and go by the key's own hash
-    if (!(__ldcg(&hs->aux) & AUX_DISPLACED)) atomicOr(&hs->aux, AUX_DISPLACED);
+    // the home slot belongs to another key: leave a note there (once) and go by the key's own hash
+    const unsigned note = AUX_DISPLACED | (t.g.filter ? aux_filter_bit(key) : 0u);
+    if ((cur4.w & note) != note) atomicOr(&hs->aux, note);
     unsigned long long off = walk_start(t.g, key);
     // A walk is a handful of slots at the loads the host keeps (<= 0.7).  WALK_LIMIT slots without a free one means the
     // partition is full: raise the overflow flag and give up -- and once it is up every other insert gives up at once, so an
@@ -174,7 +187,7 @@ __device__ __forceinline__ Slot* table_upsert_finish(const TableView& t, unsigne
 __device__ __forceinline__ Slot* table_upsert(const TableView& t, unsigned long long key, unsigned hj, unsigned& claimed) {
     unsigned long long base, home;
     if (!home_of(t.g, hj, base, home)) { atomicExch(t.error, 2); return nullptr; }
-    return table_upsert_finish(t, key, base, home, __ldcg(&t.slots[home].key), claimed);
+    return table_upsert_finish(t, key, base, home, ld_slot(&t.slots[home]), claimed);
 }
 
 // val += cnt (count tables)
@@ -217,7 +230,8 @@ __device__ __forceinline__ bool table_label_max(const TableView& t, unsigned lon
 }
 
 // Key-hashed walk of a read-only lookup (the home slot held another key and its DISPLACED flag was set): one 64-B group
-// per round, the four slots examined in fill order; a free slot ends the walk.  Returns {val, aux} or 0.
+// per round, the four slots examined in fill order; a free slot ends the walk.  Returns {val, aux} or 0 (aux is only
+// meaningful in label tables: in count tables it is the note of the slot the key was found in).
 __device__ __forceinline__ uint2 table_walk_find(const Slot* __restrict__ slots, const Geo& g, unsigned long long base,
                                                   unsigned long long key) {
     unsigned long long off = walk_start(g, key);
@@ -249,8 +263,11 @@ __device__ __forceinline__ HomeProbe table_home_find(const Slot* __restrict__ sl
     if (!home_of(g, hj, r.base, home)) return r;                 // a shard that does not hold the partition: absent
     const uint4 s = __ldcg(reinterpret_cast<const uint4*>(&slots[home]));
     const unsigned long long sk = ((unsigned long long)s.y << 32) | s.x;
-    if (sk == key) { r.v = make_uint2(s.z, s.w & AUX_LABEL_MASK); r.found = true; }
-    else r.walk = sk != 0ull && (s.w & AUX_DISPLACED) != 0u;
+    if (sk == key) { r.v = make_uint2(s.z, g.filter ? 0u : s.w & AUX_LABEL_MASK); r.found = true; }
+    else {
+        const unsigned note = AUX_DISPLACED | (g.filter ? aux_filter_bit(key) : 0u);
+        r.walk = sk != 0ull && (s.w & note) == note;
+    }
     return r;
 }
 // complete single-thread lookup from a key alone (slow path: long reads, tests)

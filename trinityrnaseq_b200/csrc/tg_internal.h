@@ -91,9 +91,9 @@ cudaError_t launch_log_refine(const LogEntry* d_keys, const unsigned int* d_curs
 // (packed key, value) pairs -> table[canon(key)] += value (count tables) / max= (label tables)
 cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int k, int canonical,
                               TableView t, int is_label, cudaStream_t s);
-// re-insert every live slot of `from` whose value is >= min_val into `to` (growth: min_val 0; compaction: min count)
+// re-insert every live slot of `from` whose value is in [min_val, max_val] into `to` (label tables: every slot)
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
-                          cudaStream_t s);
+                          uint32_t max_val, cudaStream_t s);
 
 // per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,

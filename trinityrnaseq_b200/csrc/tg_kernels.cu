@@ -505,7 +505,7 @@ constexpr int RP_CHUNK = RP_THREADS * RP_PER_THREAD;
 #define RP_GROUP 4                                  // entries per thread whose probes are in flight together
 #endif
 #ifndef RP_MIN_CTAS
-#define RP_MIN_CTAS 4
+#define RP_MIN_CTAS 3
 #endif
 static_assert(RP_PER_THREAD % RP_GROUP == 0, "groups tile a thread's entries");
 constexpr int RP_FOLD = RP_CHUNK;                   // slots of the per-chunk fold table; entries that do not find a
@@ -688,11 +688,27 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
                 }
             }
             if (FOLD) __syncthreads();
-#pragma unroll 1
+            // the thread's entries are streamed from DRAM two ahead of the one being applied
+            LogEntry ahead[2];
+            ahead[0].meta = 0u; ahead[1].meta = 0u;
+            if (!FOLD) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const unsigned i = i0 + a * RP_THREADS + tid;
+                    if (i < n) ahead[a] = ld_entry(kbase + i);
+                }
+            }
+#pragma unroll 2
             for (int gg = 0; gg < RP_PER_THREAD; gg++) {
                 LogEntry e;
                 unsigned cnt = 1u;
                 e.meta = 0u;
+                if (!FOLD) {
+                    e = ahead[gg & 1];
+                    ahead[gg & 1].meta = 0u;
+                    const unsigned i = i0 + (gg + 2) * RP_THREADS + tid;
+                    if (gg + 2 < RP_PER_THREAD && i < n) ahead[gg & 1] = ld_entry(kbase + i);
+                }
                 if (FOLD) {
                     const unsigned sidx = gg * RP_THREADS + tid;
                     const unsigned long long bases = f_key[sidx];
@@ -702,9 +718,6 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
                         cnt = f_cnt[sidx];
                         f_key[sidx] = 0ull; f_hm[sidx] = 0ull; f_cnt[sidx] = 0u;          // clean for the next chunk
                     }
-                } else {
-                    const unsigned i = i0 + gg * RP_THREADS + tid;
-                    if (i < n) e = ld_entry(kbase + i);
                 }
                 if (e.meta != 0u) {
                     if (e.meta & LE_EXPLICIT) {
@@ -718,7 +731,8 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
                             const unsigned nw = le_n(e.meta);
 #pragma unroll 1
                             for (unsigned w0 = 0; w0 < nw; w0 += 4) {
-                                unsigned long long key[4], cur[4];
+                                unsigned long long key[4];
+                                uint4 cur[4];
                                 unsigned slot[4];
 #pragma unroll
                                 for (unsigned u = 0; u < 4; u++)
@@ -726,7 +740,7 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
                                         unsigned hj;
                                         le_window(e, w0 + u, k, mk, key[u], hj);
                                         slot[u] = home_slot(hj);
-                                        cur[u] = __ldcg(&t.slots[home0 + slot[u]].key);
+                                        cur[u] = ld_slot(&t.slots[home0 + slot[u]]);
                                     }
 #pragma unroll
                                 for (unsigned u = 0; u < 4; u++)
@@ -937,33 +951,61 @@ cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, ui
     return cudaGetLastError();
 }
 
+// Only a fraction of the slots pass the filter of a compaction pass, and finding a key's home again costs ~300 instructions
+// (8 m-mer hashes): the survivors of a warp's 32 slots are queued in shared memory and re-inserted 32 at a time, so that
+// the expensive part always runs on full warps.
 __global__ void __launch_bounds__(256)
-k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val) {
-    unsigned claimed = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val, uint32_t max_val) {
+    __shared__ uint4 queue[8][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned claimed = 0, nq = 0;
+    auto insert = [&](const uint4 s) {
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key == 0ull) continue;
+        const unsigned hj = key_home_packed(key, to.g.k);
         if (is_label) {        // both orientations' labels move with the key
             const unsigned aux = s.w & AUX_LABEL_MASK;
-            const unsigned hj = key_home_packed(key, to.g.k);
             if (s.z && table_label_max(to, key, hj, false, s.z)) claimed++;
             if (aux && table_label_max(to, key, hj, true, aux)) claimed++;
-        } else if (s.z >= min_val) {
-            table_add(to, key, key_home_packed(key, to.g.k), s.z, claimed);
+        } else {
+            table_add(to, key, hj, s.z, claimed);
+        }
+    };
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (from_cap + stride - 1) / stride;
+    for (uint64_t rd = 0; rd < rounds; rd++) {
+        const uint64_t i = rd * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        uint4 s = make_uint4(0u, 0u, 0u, 0u);
+        if (i < from_cap) s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+        const bool keep = (s.x | s.y) != 0u && (is_label || (s.z >= min_val && s.z <= max_val));
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) queue[w][nq + __popc(m & lt)] = s;
+        nq += __popc(m);
+        __syncwarp();
+        if (nq >= 32u) {
+            insert(queue[w][lane]);
+            __syncwarp();
+            nq -= 32u;
+            const bool mv = (unsigned)lane < nq;               // the leftovers move to the front
+            uint4 t2 = make_uint4(0u, 0u, 0u, 0u);
+            if (mv) t2 = queue[w][32 + lane];
+            __syncwarp();
+            if (mv) queue[w][lane] = t2;
+            __syncwarp();
         }
     }
+    if ((unsigned)lane < nq) insert(queue[w][lane]);
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
-    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
+    if (lane == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
 }
 
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,
-                          cudaStream_t s) {
+                          uint32_t max_val, cudaStream_t s) {
     TimedLaunch timed("k_rehash", s);
     if (from_cap == 0) return cudaSuccess;
     uint64_t blocks = (from_cap + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    k_rehash<<<(int)blocks, 256, 0, s>>>(from, from_cap, to, is_label, min_val);
+    k_rehash<<<(int)blocks, 256, 0, s>>>(from, from_cap, to, is_label, min_val, max_val);
     return cudaGetLastError();
 }
 

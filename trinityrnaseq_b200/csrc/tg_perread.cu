@@ -169,20 +169,21 @@ __device__ __forceinline__ void stats_drain(StatsWarp& sw, const Slot* __restric
     __syncwarp();
 }
 
-// Median of the n values a warp holds in registers (lane l owns x[i] = value 32 i + l, live where < n), WITHOUT
+// Median of the n values a warp holds in registers (lane l owns x[i] = value 32 i + l; elements past n hold 0xFFFFFFFF,
+// which no pivot below the maximum reaches -- if every value IS 0xFFFFFFFF the answer is that value either way), WITHOUT
 // sorting: a bisection on the VALUE between the warp minimum and maximum (coverage values of one read sit in a narrow
 // band, so a handful of rounds), each round one compare per element and one redux.sync.  Returns median_coverage() of
 // fastaToKmerCoverageStats.cpp:337-347: odd n -> the middle element, even n -> the (wrapping) u32 mean of the two middle
 // elements.
 template <int PER>
-__device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], int n, int lane, unsigned lo, unsigned hi) {
+__device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], int n, unsigned lo, unsigned hi) {
     const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
     // smallest value with at least k1 + 1 elements <= it = the element of rank k1
     while (lo < hi) {
         const unsigned mid = lo + ((hi - lo) >> 1);
         unsigned cnt = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) cnt += (32 * i + lane < n && x[i] <= mid) ? 1u : 0u;
+        for (int i = 0; i < PER; i++) cnt += x[i] <= mid ? 1u : 0u;          // (dead elements are 0xFFFFFFFF > mid)
         cnt = __reduce_add_sync(FULL, cnt);
         if (cnt >= k1 + 1u) hi = mid; else lo = mid + 1u;
     }
@@ -191,9 +192,8 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
     unsigned le = 0, nxt = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const bool live = 32 * i + lane < n;
-        le += (live && x[i] <= x1) ? 1u : 0u;
-        if (live && x[i] > x1) nxt = min(nxt, x[i]);
+        le += x[i] <= x1 ? 1u : 0u;
+        if (x[i] > x1) nxt = min(nxt, x[i]);
     }
     le = __reduce_add_sync(FULL, le);
     nxt = __reduce_min_sync(FULL, nxt);
@@ -238,7 +238,7 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         const bool live = 32 * i + lane < nwin;
-        x[i] = live ? sw.cov[used + 32 * i + lane] : 0u;
+        x[i] = live ? sw.cov[used + 32 * i + lane] : 0xFFFFFFFFu;
         if (live) { mn = min(mn, x[i]); mx = max(mx, x[i]); part += x[i]; }
     }
     const unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
@@ -250,7 +250,7 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     }
     mean = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));   // `long` sum, exact
-    median = warp_median_regs<PER>(x, nwin, lane, lo, hi);
+    median = warp_median_regs<PER>(x, nwin, lo, hi);
 }
 
 // sequential fp32 sums of squares of a batch, one read per lane (fastaToKmerCoverageStats.cpp:389-402): strict read order,
@@ -546,21 +546,29 @@ __device__ __forceinline__ void labels_of(uint2 v, bool do_f, bool do_r, bool is
 __device__ __forceinline__ void warp_vote(const int32_t* hits, int n, int lane, int& best, int& score) {
     int b = -1, sc = 0;
     if (n >= 2) {
+        // nearly every read hits ONE bundle: one pass settles it (that label is also the largest: m - 2)
+        const int first = hits[0];
+        unsigned same = 0;
         int last = -1;
-        for (int p = lane; p < n; p += 32) last = max(last, hits[p]);
-        last = __reduce_max_sync(FULL, last);
-        int cur = -1;
-        while (true) {
-            int mn = 0x7FFFFFFF;
-            for (int p = lane; p < n; p += 32) { const int h = hits[p]; if (h > cur) mn = min(mn, h); }
-            const int lab = __reduce_min_sync(FULL, mn);
-            if (lab == 0x7FFFFFFF) break;
-            unsigned m = 0;
-            for (int p = lane; p < n; p += 32) m += hits[p] == lab ? 1u : 0u;
-            m = __reduce_add_sync(FULL, m);
-            const int s = (int)m - 1 - (lab == last ? 1 : 0);
-            if (s > sc) { sc = s; b = lab; }
-            cur = lab;
+        for (int p = lane; p < n; p += 32) { const int h = hits[p]; same += h == first ? 1u : 0u; last = max(last, h); }
+        same = __reduce_add_sync(FULL, same);
+        if ((int)same == n) {
+            sc = n - 2; b = first;
+        } else {
+            last = __reduce_max_sync(FULL, last);
+            int cur = -1;
+            while (true) {
+                int mn = 0x7FFFFFFF;
+                for (int p = lane; p < n; p += 32) { const int h = hits[p]; if (h > cur) mn = min(mn, h); }
+                const int lab = __reduce_min_sync(FULL, mn);
+                if (lab == 0x7FFFFFFF) break;
+                unsigned m = 0;
+                for (int p = lane; p < n; p += 32) m += hits[p] == lab ? 1u : 0u;
+                m = __reduce_add_sync(FULL, m);
+                const int s = (int)m - 1 - (lab == last ? 1 : 0);
+                if (s > sc) { sc = s; b = lab; }
+                cur = lab;
+            }
         }
         if (sc <= 0) { b = -1; sc = 0; }
     }
