@@ -322,70 +322,94 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
         }
         __syncthreads();
 
-        // ---- A: super-k-mers.  The thread walks its 16 windows; consecutive valid windows whose minimizer is the same
-        // m-mer occurrence (same absolute position, unique smallest hash in the window) form one run = one entry, whose
-        // bin is the partition of the minimizer hash.  A window whose smallest hash occurs twice travels alone, with the
-        // home its own orientation dictates.
+        // ---- A: super-k-mers.  Consecutive valid windows whose minimizer is the same m-mer occurrence (same absolute
+        // position, unique smallest hash in the window) form one run = one entry, whose bin is the partition of the
+        // minimizer hash.  A window whose smallest hash occurs twice travels alone, with the home its own orientation
+        // dictates.  Two steps, so that the per-window part has no data-dependent branches: (1) every window is classified
+        // into three 16-bit masks (first window of a run / lone window / homopolymer) plus its minimizer position, packed
+        // 5 bits per window; (2) one loop over the set bits emits the entries.
         const int c = tid >> 1, sh0 = (tid & 1) * LT_WIN;
         const unsigned a0 = sm.p0[c], a1 = sm.p1[c], ab = sm.pb[c];
         const unsigned c0 = sm.p0[c + 1], c1 = sm.p1[c + 1], cb = sm.pb[c + 1];
-        unsigned ne = 0;                                  // entries of this thread
-        unsigned run_n = 0, run_start = 0, run_abs = 0;   // the open run: windows, first window, minimizer position (strip)
-        auto emit = [&](unsigned h_or_hj, unsigned info) {
-            const unsigned bin = home_part(h_or_hj, nbins);
-            const unsigned shift = (bin & 1u) * 16u;
-            const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
-            sm.eh[ne * LT_THREADS + tid] = h_or_hj;
-            sm.erank[ne * LT_THREADS + tid] = (unsigned short)((old >> shift) & 0xFFFFu);     // < LT_TILE = 4096
-            sm.einfo[ne * LT_THREADS + tid] = (unsigned short)info;
-            ne++;
-        };
-        auto close_run = [&]() {
-            if (run_n) {
-                const int pos = tid * LT_WIN + (int)run_abs;
-                emit(hx[pos + (pos >> 4)], run_start | ((run_n - 1u) << 4) | ((run_abs - run_start) << 7));
-                run_n = 0;
-            }
-        };
-#pragma unroll 1
-        for (int half = 0; half < LT_WIN / HOME_SLOTS; half++) {
-            const int b0 = tid * LT_WIN + half * HOME_SLOTS;          // first position of this strip of 8 windows
-            unsigned strip[2 * HOME_SLOTS - 1], vl[HOME_SLOTS], vr[HOME_SLOTS];
+        unsigned m_run = 0, m_lone = 0, m_homo = 0, m_ok = 0;      // bit j = window j of this thread
+        unsigned long long pos_lo = 0, pos_hi = 0;                 // minimizer position (0..22) of windows 0..11 / 12..15
+        {
+            unsigned prev_abs = 0xFFu, run_len = 0;               // the run that window j - 1 belongs to (0xFF = none)
 #pragma unroll
-            for (int q = 0; q < 2 * HOME_SLOTS - 1; q++) strip[q] = hx[b0 + q + ((b0 + q) >> 4)];
-            strip_minimizers<HOME_SLOTS>(strip, vl, vr);
+            for (int half = 0; half < LT_WIN / HOME_SLOTS; half++) {
+                const int b0 = tid * LT_WIN + half * HOME_SLOTS;   // first position of this strip of 8 windows
+                unsigned strip[2 * HOME_SLOTS - 1], vl[HOME_SLOTS], vr[HOME_SLOTS];
 #pragma unroll
-            for (int i = 0; i < HOME_SLOTS; i++) {
-                const unsigned j = (unsigned)(half * HOME_SLOTS + i);
-                const int s = sh0 + (int)j;
-                const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
-                const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
-                const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-                const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
-                if (bad || homo) {
-                    close_run();
-                    if (!bad) {
-                        const unsigned code = (f0 & 1u) | ((f1 & 1u) << 1);
-                        hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
-                    }
-                    continue;
-                }
-                const unsigned sl = vl[i] & ORD_POS_MASK, sr = ORD_POS_MASK - (vr[i] & ORD_POS_MASK);   // in the half strip
-                const unsigned abs_l = (unsigned)(half * HOME_SLOTS) + sl;
-                if (sl == sr) {
-                    if (run_n && abs_l == run_abs && run_n < nmax) { run_n++; continue; }
-                    close_run();
-                    run_n = 1; run_start = j; run_abs = abs_l;
-                } else {
-                    close_run();
-                    const bool is_rc = canonical && make_key(rc_plane(f0, k), rc_plane(f1, k)) < make_key(f0, f1);
-                    unsigned jj;
-                    const unsigned sp = strip_pick(vl[i], vr[i], i, is_rc, jj);
-                    emit(pack_home(hx[b0 + sp + ((b0 + sp) >> 4)], jj), j | (1u << 10));
+                for (int q = 0; q < 2 * HOME_SLOTS - 1; q++) strip[q] = hx[b0 + q + ((b0 + q) >> 4)];
+                strip_minimizers<HOME_SLOTS>(strip, vl, vr);
+#pragma unroll
+                for (int i = 0; i < HOME_SLOTS; i++) {
+                    const int j = half * HOME_SLOTS + i;
+                    const int s = sh0 + j;
+                    const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
+                    const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+                    const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+                    const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
+                    const bool ok = bad == 0u && !homo;
+                    const unsigned sl = vl[i] & ORD_POS_MASK, sr = ORD_POS_MASK - (vr[i] & ORD_POS_MASK);
+                    const unsigned abs_l = (unsigned)(half * HOME_SLOTS) + sl;
+                    const bool uniq = ok && sl == sr;
+                    const bool cont = uniq && abs_l == prev_abs && run_len < nmax;
+                    run_len = cont ? run_len + 1u : 1u;
+                    prev_abs = uniq ? abs_l : 0xFFu;
+                    m_run |= (uniq && !cont ? 1u : 0u) << j;
+                    m_lone |= (ok && !uniq ? 1u : 0u) << j;
+                    m_homo |= (bad == 0u && homo ? 1u : 0u) << j;
+                    m_ok |= (uniq ? 1u : 0u) << j;
+                    if (j < 12) pos_lo |= (unsigned long long)abs_l << (5 * j);
+                    else pos_hi |= (unsigned long long)abs_l << (5 * (j - 12));
                 }
             }
         }
-        close_run();
+        unsigned ne = 0;                                  // entries of this thread
+        {
+            // homopolymer windows (rare): tallied by base code
+            for (unsigned m = m_homo; m; m &= m - 1u) {
+                const int s = sh0 + (__ffs(m) - 1);
+                const unsigned code = (__funnelshift_r(a0, c0, s) & 1u) | ((__funnelshift_r(a1, c1, s) & 1u) << 1);
+                hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
+            }
+            // a run ends where the next one starts, or at the first window that does not continue it
+            const unsigned stops = m_run | ~m_ok;
+            for (unsigned m = m_run | m_lone; m; m &= m - 1u) {
+                const unsigned j = (unsigned)__ffs(m) - 1u;
+                unsigned h, info;
+                if ((m_lone >> j) & 1u) {
+                    const int s = sh0 + (int)j;
+                    const unsigned f0 = __funnelshift_r(a0, c0, s) & mk, f1 = __funnelshift_r(a1, c1, s) & mk;
+                    const bool is_rc = canonical && make_key(rc_plane(f0, k), rc_plane(f1, k)) < make_key(f0, f1);
+                    // the window's eight hashes again: its leftmost / rightmost smallest
+                    unsigned wx[HOME_SLOTS], vl1, vr1, jj;
+                    const int p0w = tid * LT_WIN + (int)j;
+#pragma unroll
+                    for (int q = 0; q < HOME_SLOTS; q++) wx[q] = hx[p0w + q + ((p0w + q) >> 4)];
+                    window_minimizers(wx, vl1, vr1);
+                    const unsigned sp = strip_pick(vl1, vr1, 0, is_rc, jj);
+                    const int pp = p0w + (int)sp;
+                    h = pack_home(hx[pp + (pp >> 4)], jj);
+                    info = j | (1u << 10);
+                } else {
+                    const unsigned rest = (stops >> (j + 1u)) | (1u << (LT_WIN - 1u - j));      // a stop at the strip end at the latest
+                    const unsigned n = (unsigned)__ffs(rest);                                    // windows j .. j + n - 1
+                    const unsigned abs_l = (unsigned)((j < 12u ? pos_lo >> (5u * j) : pos_hi >> (5u * (j - 12u))) & 31ull);
+                    const int pp = tid * LT_WIN + (int)abs_l;
+                    h = hx[pp + (pp >> 4)];
+                    info = j | ((n - 1u) << 4) | ((abs_l - j) << 7);
+                }
+                const unsigned bin = home_part(h, nbins);
+                const unsigned shift = (bin & 1u) * 16u;
+                const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
+                sm.eh[ne * LT_THREADS + tid] = h;
+                sm.erank[ne * LT_THREADS + tid] = (unsigned short)((old >> shift) & 0xFFFFu);     // < LT_TILE = 4096
+                sm.einfo[ne * LT_THREADS + tid] = (unsigned short)info;
+                ne++;
+            }
+        }
         __syncthreads();
 
         // ---- S: scan the bin counters, reserve every bin's run in the log
