@@ -50,7 +50,7 @@ def _run(home, outdir, left, right):
     out = {}
     for root, _, files in os.walk(outdir):
         for f in files:
-            if f.endswith(".accs") or ".normalized_" in f or f.endswith(".stats.sort"):
+            if f.endswith(".accs") or (".normalized_" in f and not f.endswith(".ok")):
                 p = os.path.join(root, f)
                 if os.path.islink(p):
                     p = os.path.realpath(p)

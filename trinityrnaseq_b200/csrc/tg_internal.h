@@ -24,7 +24,7 @@ inline uint64_t padded_record_bytes(uint64_t nbytes) {
 // ---- geometry of the per-read kernels (stats / assign) ------------------------------------------------
 constexpr int PR_WARPS = 8;          // warps (= reads in flight) per CTA
 constexpr int PR_MAXWIN = 256;       // windows per read handled by the warp path (reads up to 256+k-1 bases)
-constexpr int PR_MAXCH = (PR_MAXWIN + 32) / 32 + 2;  // plane chunks per read incl. sentinel
+constexpr int PR_MAXCH = ((PR_MAXWIN + 32) / 32 + 2 + 3) / 4 * 4;  // plane chunks per read incl. sentinel (whole groups of 4)
 constexpr int LONG_THREADS = 256;    // CTA-per-read path for longer reads
 
 struct LongList {            // filled by the warp-path kernels, consumed by the CTA-per-read kernels

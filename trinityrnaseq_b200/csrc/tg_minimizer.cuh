@@ -62,17 +62,15 @@ TG_HD unsigned funnel_r(unsigned lo, unsigned hi, unsigned o) {
 #endif
 }
 
-// strand-symmetric hash of an m-mer given as two m-bit planes
+// strand-symmetric hash of an m-mer given as two m-bit planes: both strands are hashed (two multiply-adds each) and the
+// smaller hash goes through the finalizer -- no 64-bit compare-and-select to find the canonical m-mer first
 TG_HD unsigned mmer_hash(unsigned f0, unsigned f1, int m) {
     const unsigned r0 = rc_plane_n(f0, m), r1 = rc_plane_n(f1, m);
-    const bool rev = r1 < f1 || (r1 == f1 && r0 < f0);       // the smaller of (f1:f0) and (r1:r0)
-    const unsigned c0 = rev ? r0 : f0, c1 = rev ? r1 : f1;
-    unsigned x = c0 * 0x9E3779B1u + c1 * 0x85EBCA77u;
+    const unsigned a = f0 * 0x9E3779B1u + f1 * 0x85EBCA77u, b = r0 * 0x9E3779B1u + r1 * 0x85EBCA77u;
+    unsigned x = a < b ? a : b;
     x ^= x >> 15;
     x *= 0x2C1B3C6Du;
     x ^= x >> 13;
-    x *= 0x297A2D39u;
-    x ^= x >> 16;
     return x;
 }
 
@@ -110,10 +108,7 @@ TG_HD unsigned home_mix(unsigned hj) {
 TG_HD unsigned home_part(unsigned hj, unsigned nparts) { return (unsigned)(((unsigned long long)home_mix(hj) * nparts) >> 32); }
 // (inside a partition the top bits of the remix are fixed: the bucket takes a second remix)
 TG_HD unsigned home_bucket(unsigned hj, unsigned nbuckets) {
-    unsigned x = home_mix(hj) * 0xC2B2AE35u;
-    x ^= x >> 15;
-    x *= 0x27D4EB2Fu;
-    x ^= x >> 16;
+    const unsigned x = home_mix(hj) * 0xC2B2AE35u;          // the high bits of the product depend on every bit of the remix
     return (unsigned)(((unsigned long long)x * nbuckets) >> 32);
 }
 

@@ -90,6 +90,45 @@ __device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v
     return tot;
 }
 
+// The warp path's transpose: FOUR bases per lane and round (128 bases per round: one round for a 100-bp read instead of
+// four ballot rounds).  Lane l holds bases 4l .. 4l+3 of the round as one 32-bit word; code bits and validity are computed
+// for the four bytes at once (SWAR), gathered into nibbles, and the eight lanes that share a 32-base plane word OR their
+// nibbles together with a segmented redux.  Bytes are read as aligned words (two per lane, funnel-shifted by the record's
+// misalignment); nothing past the record's terminator is touched beyond the padding every device record buffer carries.
+__device__ __forceinline__ unsigned swar_zero_bytes(unsigned z) {          // bit 7 of every byte of z that is 0
+    return ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u;
+}
+__device__ __forceinline__ unsigned swar_gather(unsigned x) {             // bits 0, 8, 16, 24 -> bits 0..3
+    return ((x & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ void pack_read_planes_warp(const uint8_t* __restrict__ seq, int L, int nch, uint32_t* P0,
+                                                      uint32_t* P1, uint32_t* PB, int lane) {
+    const unsigned long long a0 = reinterpret_cast<unsigned long long>(seq);
+    const int sh = (int)(a0 & 3ull);
+    const unsigned* words = reinterpret_cast<const unsigned*>(a0 - (unsigned long long)sh);
+    const unsigned grp = 0xFFu << (lane & 24);                              // the 8 lanes of this lane's plane word
+    for (int g = 0; 4 * g <= nch; g++) {
+        const int first = 128 * g + 4 * lane;                               // index of this lane's first base
+        // aligned words covering bytes [first - sh, first - sh + 8)
+        const unsigned w0 = first - sh < L ? words[32 * g + lane] : 0x0A0A0A0Au;
+        const unsigned w1 = first - sh + 4 < L ? words[32 * g + lane + 1] : 0x0A0A0A0Au;
+        const unsigned w = __funnelshift_r(w0, w1, 8 * sh);
+        const unsigned cc = (w >> 1) ^ (w >> 2);                            // code = bits 0-1 of every byte
+        const unsigned u = w & 0xDFDFDFDFu;                                 // upper case
+        const unsigned ok = swar_zero_bytes(u ^ 0x41414141u) | swar_zero_bytes(u ^ 0x43434343u) |
+                            swar_zero_bytes(u ^ 0x47474747u) | swar_zero_bytes(u ^ 0x54545454u);
+        const int live = L - first;                                         // bases of this lane inside the record
+        const unsigned lm = live >= 4 ? 0xFu : live <= 0 ? 0u : (1u << live) - 1u;
+        const unsigned n0 = swar_gather(cc), n1 = swar_gather(cc >> 1);
+        const unsigned nb = ~(swar_gather(ok >> 7) & lm) & 0xFu;           // invalid: not ACGT, or past the record
+        const int pos = 4 * (lane & 7);
+        const unsigned b0 = __reduce_or_sync(grp, n0 << pos);
+        const unsigned b1 = __reduce_or_sync(grp, n1 << pos);
+        const unsigned bb = __reduce_or_sync(grp, nb << pos);
+        if ((lane & 7) == 0) { const int c = 4 * g + (lane >> 3); P0[c] = b0; P1[c] = b1; PB[c] = bb; }
+    }
+}
+
 // planes, m-mer hashes and the deferred-walk queue of one warp
 struct WarpFront {
     uint32_t p0[PR_MAXCH], p1[PR_MAXCH], pb[PR_MAXCH];
@@ -103,7 +142,7 @@ struct WarpFront {
 __device__ __forceinline__ void front_planes_hashes(WarpFront& f, const uint8_t* __restrict__ seq, int L, int m, unsigned mm,
                                                     int lane) {
     const int nch = (L + 31) >> 5;
-    pack_read_planes<32>(seq, L, nch, f.p0, f.p1, f.pb, lane);
+    pack_read_planes_warp(seq, L, nch, f.p0, f.p1, f.pb, lane);
     __syncwarp();
     const int nmm = L - m + 1;
     for (int q = lane; q < nmm; q += 32) {
