@@ -118,6 +118,16 @@ int tg_table_export(tg_table* t, uint32_t min_count, uint32_t max_count, int sor
 /* tg_histo: `jellyfish histo` (Trinity:2630): bins[c] = number of distinct k-mers with count c. */
 int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]);
 
+/* ---- one upload for several calls ----------------------------------------------------------------------
+ * The reference tools read the same reads twice when `--kmers_from_reads` names the `--reads` file (count, then
+ * statistics: Inchworm/src/fastaToKmerCoverageStats.cpp:230-293, :122-172), and so do the two halves of a bench step.
+ * tg_records_hold declares a host record buffer IMMUTABLE until tg_records_release (or the next hold): the library keeps
+ * one device copy of it (uploaded during the first call that uses it, overlapped with that call's kernels) and every
+ * later tg_count_reads / tg_cov_stats / tg_assign_reads given the same pointer and length (offs[nreads] for the per-read
+ * calls) works on that copy.  Results are identical with or without it. */
+int tg_records_hold(tg_ctx* ctx, const char* recs, uint64_t nbytes);
+int tg_records_release(tg_ctx* ctx);
+
 /* ---- stage S: fastaToKmerCoverageStats ------------------------------------------------------------------
  * compute_kmer_coverage + median_coverage + mean + stDev (Inchworm/src/fastaToKmerCoverageStats.cpp:300-402)
  * for every record: per window c = max(1, table[canon(w)]) (0 -> 1 also for windows with a non-base);

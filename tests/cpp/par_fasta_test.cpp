@@ -1,0 +1,74 @@
+// CPU check of host/par_fasta.hpp: chunked, multi-threaded parsing hands out exactly the records of a serial parse, in
+// file order, for FASTA texts with every reader quirk (multi-line records, blank lines, blanks inside lines, lower case,
+// '>' inside a sequence line, text before the first header, no trailing newline, empty records, tiny chunk sizes).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include "par_fasta.hpp"
+
+using namespace tgio;
+
+static void parse_all(const char* d, size_t n, RecordBatch& rb) {
+    InchwormFastaReader rd(d, n);
+    const char* h; size_t hl;
+    while (true) {
+        const size_t before = rb.recs.size();
+        if (!rd.next(&h, &hl, rb.recs)) break;
+        if (rb.recs.size() == before) continue;
+        const char* acc; size_t al;
+        accession_of(h, hl, &acc, &al);
+        rb.end_record();
+        rb.add_name(acc, al);
+    }
+}
+
+int main() {
+    srand(7);
+    long checked = 0;
+    for (int trial = 0; trial < 300; trial++) {
+        std::string t;
+        if (trial % 5 == 0) t += "junk before the first header\nmore junk\n";
+        const int nrec = rand() % 40;
+        for (int r = 0; r < nrec; r++) {
+            t += ">r" + std::to_string(r) + (rand() % 3 ? " desc text" : "") + "\n";
+            const int lines = rand() % 4;
+            for (int l = 0; l < lines; l++) {
+                const int len = rand() % 70;
+                for (int i = 0; i < len; i++) {
+                    const int x = rand() % 40;
+                    t += x == 0 ? ' ' : x == 1 ? '\t' : x == 2 ? '>' : x == 3 ? 'n' : "ACGTacgt"[rand() & 7];
+                }
+                // a '>' may appear INSIDE a line, never at its start here (that would be a header by definition)
+                if (!t.empty() && t.back() == '\n') {}
+                t += "\n";
+                if (rand() % 9 == 0) t += "\n";
+            }
+        }
+        // make sure no sequence line starts with '>' (our generator could have produced one): prefix with 'A'
+        for (size_t i = 1; i + 1 < t.size(); i++)
+            if (t[i] == '>' && t[i - 1] == '\n' && !(t[i + 1] == 'r')) t[i] = 'A';
+        if (trial % 4 == 0 && !t.empty() && t.back() == '\n') t.pop_back();      // no trailing newline
+        RecordBatch serial;
+        parse_all(t.data(), t.size(), serial);
+        for (size_t target : {size_t(1), size_t(17), size_t(200), size_t(100000)}) {
+            for (unsigned threads : {1u, 3u, 8u}) {
+                OrderedChunkParser p(t.data(), t.size(), target, threads, 3, parse_all);
+                RecordBatch all, rb;
+                while (p.next(rb)) {
+                    for (size_t i = 0; i < rb.count(); i++) {
+                        all.recs.insert(all.recs.end(), rb.seq(i), rb.seq(i) + rb.seq_len(i));
+                        all.end_record();
+                        all.add_name(rb.name(i), rb.name_len(i));
+                    }
+                }
+                if (all.recs != serial.recs || all.offs != serial.offs || all.names != serial.names || all.name_offs != serial.name_offs) {
+                    fprintf(stderr, "MISMATCH trial %d target %zu threads %u\n", trial, target, threads);
+                    return 1;
+                }
+                checked += (long)all.count();
+            }
+        }
+    }
+    printf("parallel parse == serial parse on %ld records\n", checked);
+    return 0;
+}

@@ -187,3 +187,16 @@ def test_minimizer_fast_path_equals_slow_path(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "fast == slow" in r.stdout
+
+
+def test_parallel_fasta_parser_equals_serial(tmp_path):
+    """host/par_fasta.hpp: chunked multi-threaded parsing == serial parsing, record for record, in file order, for FASTA
+    texts with every reader quirk and chunk sizes down to one byte (tests/cpp/par_fasta_test.cpp)."""
+    import subprocess
+    exe = tmp_path / "par_fasta_test"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", "-I",
+                    os.path.join(ROOT, "trinityrnaseq_b200", "host"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "cpp", "par_fasta_test.cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "parallel parse == serial parse" in r.stdout

@@ -252,3 +252,47 @@ def test_short_kmers_use_the_slow_homes(gpu_ctx, oracle, k):
             np.testing.assert_array_equal(gm, om)
             np.testing.assert_array_equal(gmean.view(np.uint32), omean.view(np.uint32))
             np.testing.assert_array_equal(gsd.view(np.uint32), osd.view(np.uint32))
+
+
+def test_held_records_one_upload_same_results(gpu_ctx, oracle, data):
+    """tg_records_hold: count + statistics + assignment on ONE device copy of the reads give exactly what the separate
+    uploads give (and what the oracle gives), in either order of first use, with a long read falling back to the batched
+    path, and after release / a new hold."""
+    txs, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, 25, True, 1)
+    okc = oracle.KmerCounter(25, True)
+    for kmer, c in zip(ok, oc):
+        okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
+    om, omean, osd = okc.coverage_stats(recs, offs)
+    pinned, owner = gpu_ctx.pinned((recs.nbytes,), np.uint8)
+    pinned[:] = recs
+    for first in ("count", "stats"):
+        gpu_ctx.records_hold(pinned)
+        with tg.KmerCounter(gpu_ctx, 25, is_ds=True, expected_keys=len(ok)) as kc:
+            if first == "stats":            # the statistics call uploads; the table is still empty: every coverage is 1
+                m0, _, _ = kc.coverage_stats(pinned, offs)
+                assert int(m0.max()) <= 1
+            kc.add_records(pinned)
+            gk, gc = kc.dump()
+            np.testing.assert_array_equal(gk, ok)
+            np.testing.assert_array_equal(gc, oc)
+            gm, gmean, gsd = kc.coverage_stats(pinned, offs)
+            np.testing.assert_array_equal(gm, om)
+            np.testing.assert_array_equal(_f32_bits(gmean), _f32_bits(omean))
+            np.testing.assert_array_equal(_f32_bits(gsd), _f32_bits(osd))
+            # a different array with the same content takes the ordinary path: same answers
+            gm2, _, gsd2 = kc.coverage_stats(recs, offs)
+            np.testing.assert_array_equal(gm2, om)
+            np.testing.assert_array_equal(_f32_bits(gsd2), _f32_bits(osd))
+        names, bundles = synth.bundles_from(np.random.default_rng(3), txs)
+        brecs, boffs = tg.records_from_sequences(bundles)
+        with tg.BundleKmerTable(gpu_ctx, 25) as bt:
+            bt.label_bundles(brecs, boffs)
+            hb, hp, hs = bt.assign_reads(pinned, offs, strand=False)
+            gpu_ctx.records_release()
+            b2, p2, s2 = bt.assign_reads(pinned, offs, strand=False)
+            np.testing.assert_array_equal(hb, b2)
+            np.testing.assert_array_equal(hp, p2)
+            np.testing.assert_array_equal(hs, s2)
+    gpu_ctx.records_release()

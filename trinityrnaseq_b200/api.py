@@ -96,6 +96,17 @@ class Context:
         check(_lib.lib().tg_log_overflow_check(self._h, C.byref(f)))
         return bool(f.value)
 
+    def records_hold(self, recs):
+        """declare `recs` (a uint8 array, e.g. from pinned()) immutable until records_release: ONE upload shared by the
+        count / statistics / assignment calls that are given this same array"""
+        a = _as_u8(recs)
+        check(_lib.lib().tg_records_hold(self._h, _ptr(a), a.nbytes))
+        self._held = a
+
+    def records_release(self):
+        check(_lib.lib().tg_records_release(self._h))
+        self._held = None
+
     def launch_count(self):
         return int(_lib.lib().tg_launch_count(self._h))
 

@@ -78,6 +78,15 @@ struct tg_ctx {
     int* d_error = nullptr;                             // raised by table-less log appends (tg_count_partition_dev)
     size_t part_bytes = 16ull << 20;                    // target bytes of one table partition (L2-resident unit)
     size_t log_max_bytes = 48ull << 30;                 // most HBM the k-mer log of one table may take
+    // a host record buffer the caller declared immutable (tg_records_hold): its ONE device copy, shared by every call that
+    // is given the same pointer and length
+    struct Held {
+        const char* host = nullptr; uint64_t nbytes = 0;
+        DevBuf dev; bool uploaded = false;
+        DevBuf offs, out_a, out_b, out_c, long_idx;
+        cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+    } held;
+    size_t held_chunk_bytes = 64ull << 20;              // upload granularity of a held buffer (whole tiles)
     KernelTimer timer;                                  // optional per-kernel event timing
     int count_mode = 0;                                 // 0 auto, 1 always direct, 2 always logged
     int replay_prefetch = 1;
@@ -249,6 +258,9 @@ void tg_destroy(tg_ctx* c) {
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
     c->scratch.release(); c->lut.release(); c->long_scratch.release();
+    c->held.dev.release(); c->held.offs.release(); c->held.out_a.release(); c->held.out_b.release(); c->held.out_c.release();
+    c->held.long_idx.release();
+    for (int i = 0; i < 2; i++) if (c->held.chunk_done[i]) cudaEventDestroy(c->held.chunk_done[i]);
     if (c->d_error) cudaFree(c->d_error);
     if (c->h_long_hdr) cudaFreeHost(c->h_long_hdr);
     for (int i = 0; i < 2; i++) if (c->order[i]) cudaEventDestroy(c->order[i]);
@@ -859,6 +871,73 @@ static int flush_log(tg_table* t) {
 
 extern "C" {
 
+int tg_records_hold(tg_ctx* c, const char* recs, uint64_t nbytes) {
+    if (!c || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_records_hold: null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    c->held.host = nullptr; c->held.nbytes = 0; c->held.uploaded = false;
+    if (nbytes == 0) return TG_OK;
+    CU(c->held.dev.ensure(padded_record_bytes(nbytes)));
+    for (int i = 0; i < 2; i++)
+        if (!c->held.chunk_done[i]) CU(cudaEventCreateWithFlags(&c->held.chunk_done[i], cudaEventDisableTiming));
+    c->held.host = recs; c->held.nbytes = nbytes;
+    return TG_OK;
+}
+
+int tg_records_release(tg_ctx* c) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    c->held.host = nullptr; c->held.nbytes = 0; c->held.uploaded = false;
+    return rc;
+}
+
+}  // extern "C"
+
+static bool is_held(const tg_ctx* c, const char* recs, uint64_t nbytes) {
+    return c->held.host && recs == c->held.host && nbytes == c->held.nbytes;
+}
+
+// First use of a held buffer: upload it in chunks of whole tiles on stream 1 while `consume(device pointer, bytes)` works on
+// the chunks behind on stream 0.  A chunk's kernel reads a few bytes past its end (the halo of its last tile), so chunk i is
+// consumed only after chunk i + 1 has arrived; the tail of the buffer is '\n' padding.  Later uses find the copy in place.
+template <typename Consume>
+static int held_stream(tg_ctx* c, Consume consume) {
+    auto& h = c->held;
+    char* dev = (char*)h.dev.p;
+    const uint64_t chunk = std::max<uint64_t>(c->held_chunk_bytes, CT_TILE) / CT_TILE * CT_TILE;
+    if (h.uploaded) {
+        for (uint64_t pos = 0; pos < h.nbytes; pos += chunk) {
+            int rc = consume(dev + pos, std::min(chunk, h.nbytes - pos));
+            if (rc) return rc;
+        }
+        return TG_OK;
+    }
+    const uint64_t padded = padded_record_bytes(h.nbytes);
+    CU(cudaMemsetAsync(dev + h.nbytes, '\n', padded - h.nbytes, c->stream[1]));
+    const uint64_t nchunks = (h.nbytes + chunk - 1) / chunk;
+    for (uint64_t i = 0; i <= nchunks; i++) {
+        if (i < nchunks) {
+            const uint64_t pos = i * chunk, n = std::min(chunk, h.nbytes - pos);
+            CU(cudaMemcpyAsync(dev + pos, h.host + pos, n, cudaMemcpyHostToDevice, c->stream[1]));
+            CU(cudaEventRecord(h.chunk_done[i & 1], c->stream[1]));
+        }
+        if (i >= 1) {           // chunk i - 1 is complete together with its halo (chunk i, or the padding after the last one)
+            if (i < nchunks) CU(cudaStreamWaitEvent(c->stream[0], h.chunk_done[i & 1], 0));
+            else CU(cudaStreamWaitEvent(c->stream[0], h.chunk_done[(i - 1) & 1], 0));
+            const uint64_t pos = (i - 1) * chunk;
+            int rc = consume(dev + pos, std::min(chunk, h.nbytes - pos));
+            if (rc) return rc;
+            // (the event slot is re-recorded two uploads later; a wait refers to the record that preceded it)
+        }
+    }
+    h.uploaded = true;
+    return TG_OK;
+}
+
+extern "C" {
+
 int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical) {
     if (!t || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_count_reads: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_reads needs a TG_TABLE_COUNT table");
@@ -875,6 +954,28 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
     }
     if (log_pays(t, nbytes) && (rc = ensure_log(t, log_launch_cost(c, t->log, nbytes), &logged))) return rc;
     const uint64_t room = logged ? log_room(t->log) : 0;
+    if (is_held(c, recs, nbytes)) {
+        // the caller promised the buffer does not change: one device copy, uploaded here (or found in place) and left for
+        // the statistics call that follows
+        if ((rc = sync_all(c))) return rc;
+        rc = held_stream(c, [&](const char* d, uint64_t n) -> int {
+            int r2;
+            if (logged) {
+                if (t->log.pending_ub + log_launch_cost(c, t->log, n) > room && t->log.pending_ub && (r2 = flush_log(t))) return r2;
+                CU(launch_log_tiles((const uint8_t*)d, n, t->k, canonical, log_view(t), t->view(), c->sm_count, c->stream[0]));
+                t->log.pending_ub += log_launch_cost(c, t->log, n);
+            } else {
+                if ((r2 = tg_table_reserve(t, n))) return r2;
+                CU(launch_count_tiles((const uint8_t*)d, n, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
+            }
+            c->launches++;
+            return TG_OK;
+        });
+        if (rc) return rc;
+        if (logged && (rc = flush_log(t))) return rc;
+        if ((rc = sync_all(c))) return rc;
+        return table_refresh(t);
+    }
     uint64_t pos = 0;
     for (int it = 0; pos < nbytes; it++) {
         const int b = it & 1;
@@ -1135,6 +1236,34 @@ int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]) {
 // ---------------------------------------------------------------------------------------------------------
 }  // extern "C"
 
+// One per-read pass over a held record buffer: offsets up, kernels on the device copy, three 4-byte results per read down.
+// *done = false (and nothing written) when a read was too long for the fixed scratch of the device-driven long kernels.
+template <typename Launch, typename A, typename B, typename C3>
+static int held_pass(tg_ctx* c, const uint64_t* offs, uint64_t nreads, bool* done, Launch launch, A* out_a, B* out_b, C3* out_c) {
+    auto& h = c->held;
+    *done = false;
+    int rc;
+    if (!h.uploaded && (rc = held_stream(c, [](const char*, uint64_t) -> int { return TG_OK; }))) return rc;
+    CU(h.offs.ensure((nreads + 1) * 8));
+    CU(h.out_a.ensure(nreads * 4)); CU(h.out_b.ensure(nreads * 4)); CU(h.out_c.ensure(nreads * 4));
+    CU(h.long_idx.ensure(nreads * 4));
+    CU(c->long_scratch.ensure(c->long_scratch_bytes));
+    CU(cudaMemcpyAsync(h.offs.p, offs, (nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaMemsetAsync(c->d_long_hdr[0], 0, 2 * sizeof(unsigned int), c->stream[0]));
+    LongList ll{c->d_long_hdr[0], c->d_long_hdr[0] + 1, (unsigned int*)h.long_idx.p};
+    if ((rc = launch((const uint8_t*)h.dev.p, (const uint64_t*)h.offs.p, ll))) return rc;
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, c->d_error, sizeof err, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    if (err == 4) { CU(cudaMemset(c->d_error, 0, sizeof(int))); return TG_OK; }
+    CU(cudaMemcpyAsync(out_a, h.out_a.p, nreads * 4, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaMemcpyAsync(out_b, h.out_b.p, nreads * 4, cudaMemcpyDeviceToHost, c->stream[0]));
+    if (out_c) CU(cudaMemcpyAsync(out_c, h.out_c.p, nreads * 4, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    *done = true;
+    return TG_OK;
+}
+
 struct ReadBatch { uint64_t r0, r1; };
 
 static std::vector<ReadBatch> split_reads(const uint64_t* offs, uint64_t nreads, size_t batch_bytes) {
@@ -1201,6 +1330,20 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
     int rc;
     if ((rc = flush_log(t))) return rc;
     if ((rc = sync_all(c))) return rc;
+    if (!per_kmer && t->k >= MIN_FAST_K && nreads <= 0x7FFFFFF0ull && is_held(c, recs, offs[nreads])) {
+        // held records: the device copy is there already (or goes up once, now); one pass over all reads, no staging
+        bool done = false;
+        if ((rc = held_pass(c, offs, nreads, &done, [&](const uint8_t* d, const uint64_t* d_offs, LongList ll) -> int {
+                CU(launch_cov_stats(d, d_offs, 0, nreads, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
+                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, c->stream[0]));
+                CU(launch_cov_stats_long_auto(d, d_offs, 0, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
+                                              (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, c->long_scratch.p,
+                                              c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[0]));
+                c->launches += 2;
+                return TG_OK;
+            }, median, mean, stdev))) return rc;
+        if (done) return TG_OK;                    // else: a read too long for the fixed scratch -- the batched path below
+    }
     const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
     struct Pending { bool live = false; ReadBatch rb; } pend[2];
     auto drain = [&](int b) -> int {   // long-read pass + results back to the caller for the batch in flight on b
@@ -1342,6 +1485,19 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
     int rc;
     if ((rc = sync_all(c))) return rc;
     if ((rc = ensure_lut(c, entropy_ok))) return rc;
+    if (t->k >= MIN_FAST_K && nreads <= 0x7FFFFFF0ull && is_held(c, recs, offs[nreads])) {
+        bool done = false;
+        if ((rc = held_pass(c, offs, nreads, &done, [&](const uint8_t* d, const uint64_t* d_offs, LongList ll) -> int {
+                CU(launch_assign(d, d_offs, 0, nreads, t->k, strand, t->slots, t->g, (const uint8_t*)c->lut.p,
+                                 (int32_t*)c->held.out_a.p, (int32_t*)c->held.out_b.p, (int32_t*)c->held.out_c.p, ll, c->stream[0]));
+                CU(launch_assign_long_auto(d, d_offs, 0, t->k, strand, t->slots, t->g, (const uint8_t*)c->lut.p,
+                                           (int32_t*)c->held.out_a.p, (int32_t*)c->held.out_b.p, (int32_t*)c->held.out_c.p, ll,
+                                           c->long_scratch.p, c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[0]));
+                c->launches += 2;
+                return TG_OK;
+            }, best, pct, score))) return rc;
+        if (done) return TG_OK;
+    }
     const std::vector<ReadBatch> batches = split_reads(offs, nreads, c->batch_bytes);
     struct Pending { bool live = false; ReadBatch rb; } pend[2];
     auto drain = [&](int b) -> int {

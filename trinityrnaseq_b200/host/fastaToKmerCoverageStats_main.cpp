@@ -11,13 +11,15 @@
 #include <vector>
 
 #include "fasta_io.hpp"
+#include "par_fasta.hpp"
 #include "tg_loader.hpp"
 #include "tg_sidecar.hpp"
 
 using namespace tgio;
 
 static const int MAX_THREADS = 6;   // kept only for the usage text / CLI compatibility
-static const unsigned FORMAT_THREADS = 8;
+static const unsigned HOST_THREADS_CAP = 32;      // parse / format threads (TRINITY_GPU_HOST_THREADS overrides the core count)
+static const size_t CHUNK_BYTES = 48u << 20;        // FASTA bytes per parsed batch
 
 // Inchworm ArgProcessor (Inchworm/src/argProcessor.cpp:5-23): every token starting with '-' is a flag and the
 // following token, whatever it is, is recorded as its value.
@@ -160,23 +162,21 @@ int main(int argc, char** argv) {
         if (!fv.open(args.str("--kmers_from_reads"), &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
         fprintf(stderr, "-storing Kmers...\n");
         TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 4 + 1024, &table));
-        InchwormFastaReader rd(fv.data, fv.size);
+        // chunks of the file are parsed by a pool of threads and counted in file order (par_fasta.hpp)
+        OrderedChunkParser parser(fv.data, fv.size, CHUNK_BYTES, host_threads(HOST_THREADS_CAP), 4,
+            [K](const char* d, size_t n, RecordBatch& rb) {
+                InchwormFastaReader rd(d, n);
+                const char* h; size_t hl;
+                while (true) {
+                    const size_t before = rb.recs.size();
+                    if (!rd.next(&h, &hl, rb.recs)) break;          // the cleaned sequence lands in the batch directly
+                    if (rb.recs.size() - before < (size_t)K + 1) { rb.recs.resize(before); continue; }
+                    rb.end_record();
+                }
+            });
         RecordBatch rb;
-        std::vector<char> seq;
-        const char* h; size_t hl;
-        auto flush = [&]() {
-            if (rb.recs.empty()) return;
-            TGC(tg_count_reads(table, rb.recs.data(), rb.recs.size(), is_DS));
-            rb.clear();
-        };
-        while (true) {
-            const size_t before = rb.recs.size();
-            if (!rd.next(&h, &hl, rb.recs)) break;          // the cleaned sequence lands in the batch directly
-            if (rb.recs.size() - before < (size_t)K + 1) { rb.recs.resize(before); continue; }
-            rb.end_record();
-            if (rb.recs.size() > (256u << 20)) flush();
-        }
-        flush();
+        while (parser.next(rb))
+            if (!rb.recs.empty()) TGC(tg_count_reads(table, rb.recs.data(), rb.recs.size(), is_DS));
     }
 
     // ---- per-read statistics ----------------------------------------------------------------------------
@@ -185,73 +185,93 @@ int main(int argc, char** argv) {
     time_t start_time = time(NULL);
     OutBuf out(1);
     out.put("acc\tmedian_cov\tmean_cov\tstdev\ttid\n");
-    InchwormFastaReader rd(rv.data, rv.size);
-    RecordBatch rb;
-    std::vector<char> seq;
-    std::vector<uint32_t> median, per_kmer;
-    std::vector<float> mean, stdev;
+    // Pipeline (all in file order): a pool of threads parses chunks of the file; the main thread runs the statistics of
+    // batch i on the GPU while the lines of batch i - 1 are being formatted by the pool's cores, and writes them out.
+    const unsigned nthreads_host = host_threads(HOST_THREADS_CAP);
+    OrderedChunkParser parser(rv.data, rv.size, CHUNK_BYTES, nthreads_host, 4,
+        [](const char* d, size_t n, RecordBatch& rb) {
+            InchwormFastaReader rd(d, n);
+            const char* h; size_t hl;
+            while (true) {
+                const size_t before = rb.recs.size();
+                if (!rd.next(&h, &hl, rb.recs)) break;                       // the cleaned sequence lands in the batch directly
+                if (rb.recs.size() == before) continue;                      // :132-133
+                const char* acc; size_t al;
+                accession_of(h, hl, &acc, &al);
+                rb.end_record();
+                rb.add_name(acc, al);
+            }
+        });
+    struct Job {
+        RecordBatch rb;
+        std::vector<uint32_t> median, per_kmer;
+        std::vector<float> mean, stdev;
+        std::vector<std::vector<char>> bufs;
+        std::vector<char> negs;
+        std::thread formatter;
+    } jobs[2];
     bool negative = false;
-    auto flush = [&]() {
+    auto format_job = [&](Job& jb) {
+        const RecordBatch& rb = jb.rb;
         const size_t n = rb.count();
-        if (n == 0) return;
-        median.resize(n); mean.resize(n); stdev.resize(n);
-        if (capture) per_kmer.assign(rb.recs.size(), 0);
-        TGC(tg_cov_stats(table, rb.recs.data(), rb.offs.data(), n, is_DS, median.data(), mean.data(), stdev.data(),
-                         capture ? per_kmer.data() : nullptr));
-        for (size_t i = 0; i < n; i++)
-            if (rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
-                fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)rb.seq_len(i), rb.seq(i), K);
-        // the lines are formatted by a few threads, each into its own buffer, and written in read order: two %g
-        // conversions per read are the most expensive thing left on the host once the statistics come from the GPU
-        auto format_range = [&](size_t a, size_t b, std::vector<char>& buf, bool* neg) {
+        const size_t nt = n < 4096 ? 1 : nthreads_host;
+        jb.bufs.assign(nt, std::vector<char>());
+        jb.negs.assign(nt, 0);
+        // two %g conversions per read are the most expensive thing left on the host once the statistics come from the GPU
+        parallel_for_threads((unsigned)nt, [&](unsigned w) {
+            std::vector<char>& buf = jb.bufs[w];
+            const size_t a = n * w / nt, b = n * (w + 1) / nt;
+            buf.reserve((b - a) * 48);
             char num[64];
             auto put = [&](const char* p, size_t m) { buf.insert(buf.end(), p, p + m); };
             auto put_uint = [&](uint32_t v) { char t[12]; int m = 0; do { t[m++] = (char)('0' + v % 10); v /= 10; } while (v); while (m) buf.push_back(t[--m]); };
             for (size_t i = a; i < b; i++) {
                 put(rb.name(i), rb.name_len(i));
-                buf.push_back('\t'); put_uint(median[i]);
-                buf.push_back('\t'); put(num, (size_t)fmt_float(num, mean[i]));
-                buf.push_back('\t'); put(num, (size_t)fmt_float(num, stdev[i]));
+                buf.push_back('\t'); put_uint(jb.median[i]);
+                buf.push_back('\t'); put(num, (size_t)fmt_float(num, jb.mean[i]));
+                buf.push_back('\t'); put(num, (size_t)fmt_float(num, jb.stdev[i]));
                 put("\tthread:0", 9);
                 if (capture) {
                     buf.push_back('\t');
                     const size_t L = rb.seq_len(i);
                     const size_t nw = L >= (size_t)K ? L - K + 1 : 0;
                     for (size_t j = 0; j < nw; j++) {
-                        put_uint(per_kmer[rb.offs[i] + j]);
+                        put_uint(jb.per_kmer[rb.offs[i] + j]);
                         if (j != nw - 1) buf.push_back(',');
                     }
                 }
                 buf.push_back('\n');
-                if (mean[i] < 0) *neg = true;
+                if (jb.mean[i] < 0) jb.negs[w] = 1;
             }
-        };
-        const size_t nthreads = n < 4096 ? 1 : (size_t)std::min<unsigned>(FORMAT_THREADS, std::max(1u, std::thread::hardware_concurrency()));
-        std::vector<std::vector<char>> bufs(nthreads);
-        std::vector<char> negs(nthreads, 0);
-        std::vector<std::thread> workers;
-        for (size_t w = 1; w < nthreads; w++)
-            workers.emplace_back([&, w] { bool ng = false; format_range(n * w / nthreads, n * (w + 1) / nthreads, bufs[w], &ng); negs[w] = ng; });
-        { bool ng = false; format_range(0, n / nthreads, bufs[0], &ng); negs[0] = ng; }
-        for (auto& th : workers) th.join();
-        for (size_t w = 0; w < nthreads; w++) {
-            out.put(bufs[w].data(), bufs[w].size());
-            if (negs[w]) negative = true;
-        }
-        rb.clear();
+        });
     };
-    const char* h; size_t hl;
-    while (true) {
-        const size_t before = rb.recs.size();
-        if (!rd.next(&h, &hl, rb.recs)) break;                           // the cleaned sequence lands in the batch directly
-        if (rb.recs.size() == before) continue;                          // :132-133
-        const char* acc; size_t al;
-        accession_of(h, hl, &acc, &al);
-        rb.end_record();
-        rb.add_name(acc, al);
-        if (rb.recs.size() > (256u << 20)) flush();
+    auto finish_job = [&](Job& jb) {           // wait for its lines and write them
+        if (!jb.formatter.joinable()) return;
+        jb.formatter.join();
+        for (size_t w = 0; w < jb.bufs.size(); w++) {
+            out.put(jb.bufs[w].data(), jb.bufs[w].size());
+            if (jb.negs[w]) negative = true;
+        }
+        jb.bufs.clear();
+    };
+    for (unsigned it = 0;; it++) {
+        Job& jb = jobs[it & 1];
+        finish_job(jb);                          // the job that used this slot two batches ago
+        if (!parser.next(jb.rb)) break;
+        const size_t n = jb.rb.count();
+        if (n == 0) continue;
+        jb.median.resize(n); jb.mean.resize(n); jb.stdev.resize(n);
+        if (capture) jb.per_kmer.assign(jb.rb.recs.size(), 0);
+        TGC(tg_cov_stats(table, jb.rb.recs.data(), jb.rb.offs.data(), n, is_DS, jb.median.data(), jb.mean.data(), jb.stdev.data(),
+                         capture ? jb.per_kmer.data() : nullptr));
+        for (size_t i = 0; i < n; i++)
+            if (jb.rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
+                fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)jb.rb.seq_len(i), jb.rb.seq(i), K);
+        finish_job(jobs[(it & 1) ^ 1]);          // the previous batch's lines go out before this batch's (file order)
+        jb.formatter = std::thread([&format_job, &jb] { format_job(jb); });
     }
-    flush();
+    finish_job(jobs[0]);
+    finish_job(jobs[1]);
     if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }
     if (negative) { fprintf(stderr, "ERROR, cannot have negative coverage!!\n"); return 1; }
     fprintf(stderr, "STATS_GENERATION_TIME: %ld seconds.\n", (long)(time(NULL) - start_time));
