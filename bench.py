@@ -253,11 +253,19 @@ def load_peaks():
 # CPU reference leg
 # ---------------------------------------------------------------------------------------------------------
 def write_sample_fasta(path, recs, read_len, nreads):
+    """`>r<8 digits>/1` + sequence, one line each, straight from the record buffer (vectorised: 20 M records in seconds)"""
     stride = read_len + 1
     with open(path, "wb") as f:
-        for i in range(nreads):
-            f.write(b">r%d/1\n" % i)
-            f.write(recs[i * stride:(i + 1) * stride].tobytes())
+        for a in range(0, nreads, 2_000_000):
+            n = min(2_000_000, nreads - a)
+            rows = np.empty((n, 13 + stride), dtype=np.uint8)
+            rows[:, 0] = ord(">"); rows[:, 1] = ord("r")
+            idx = np.arange(a, a + n, dtype=np.int64)
+            for d in range(8):
+                rows[:, 9 - d] = (idx // 10 ** d % 10 + ord("0")).astype(np.uint8)
+            rows[:, 10] = ord("/"); rows[:, 11] = ord("1"); rows[:, 12] = ord("\n")
+            rows[:, 13:] = recs[a * stride:(a + n) * stride].reshape(n, stride)
+            rows.tofile(f)
 
 
 def cpu_reference_run(sample_recs, read_len, nreads, threads=6):
@@ -344,7 +352,7 @@ def main():
     ap.add_argument("--ntx", type=int, default=20_000)
     ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cli-reads", type=int, default=4_000_000, help="reads in the file the drop-in executable is timed on")
+    ap.add_argument("--cli-reads", type=int, default=20_000_000, help="reads in the file the drop-in executable is timed on")
     ap.add_argument("--no-gups", action="store_true")
     ap.add_argument("--no-r2t", action="store_true", help="skip the ReadsToTranscripts measurement")
     ap.add_argument("--count-mode", default="auto", choices=["auto", "direct", "log"])
@@ -506,6 +514,36 @@ def main():
             if sc.exchange == "peer" else "k-mer log all-to-all (NCCL)")
         config["exchange"] = sc.exchange
 
+    # ---- parity inside the bench (at the full size, on however many GPUs) ----------------------------------------
+    # (1) conservation: the sum of all counts in the (sharded) table == the number of valid 25-mer windows of all reads,
+    #     counted by an independent kernel straight from the ASCII; (2) on 2 GPUs: the all-reduced histogram of the table
+    #     sharded over NVLink == the histogram of ONE single-GPU table counting both ranks' reads.
+    count_dev(d_recs)
+    barrier()
+    local_sum = kc.count_sum()
+    local_valid = ctx.valid_windows_dev(d_recs, nbytes, K)
+    if dist is not None:
+        t2 = torch.tensor([local_sum, local_valid], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t2)
+        total_sum, total_valid = int(t2[0].item()), int(t2[1].item())
+    else:
+        total_sum, total_valid = local_sum, local_valid
+    assert total_sum == total_valid, f"conservation violated: {total_sum} counted vs {total_valid} valid windows"
+    parity = {"sum_of_counts": total_sum, "valid_windows": total_valid}
+    if world == 2:
+        sharded_histo = sc.histo()
+        if rank == 0:
+            with tg.KmerCounter(ctx, K, is_ds=True, expected_keys=expected_total) as one:
+                for r_ in range(world):
+                    d_o, nb_o = ctx.synth_reads_dev(tx, tx_offs, tx_cum, npairs, read_len, seed=SEED + 7919 * r_)
+                    one.add_records_dev(d_o, nb_o)
+                    ctx.sync()
+                    ctx.dev_free(d_o)
+                single_histo = one.histo()
+            assert np.array_equal(np.asarray(sharded_histo), np.asarray(single_histo)), "sharded histogram != single-GPU histogram"
+            parity["histogram_2gpu_equals_1gpu"] = True
+        barrier()
+
     # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------------
     recs_host, recs_owner = ctx.pinned((nbytes,), np.uint8)
     ctx.d2h(d_recs, recs_host)
@@ -660,6 +698,7 @@ def main():
                      "load": round(tinfo["distinct"] / tinfo["capacity"], 3),
                      "stats_table_slots": qinfo["capacity"], "stats_table_kmers": qinfo["distinct"]},
            "device": {"sm_count": info["sm_count"], "hbm_total_gb": round(info["total_bytes"] / 1e9, 1)}}
+    out["parity_checks"] = parity
     if cli is not None:
         out["cli_end_to_end"] = cli
     if phases is not None:

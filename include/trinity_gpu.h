@@ -117,6 +117,11 @@ int tg_table_export(tg_table* t, uint32_t min_count, uint32_t max_count, int sor
                     uint64_t** packed_keys, uint32_t** counts, uint64_t* n);
 /* tg_histo: `jellyfish histo` (Trinity:2630): bins[c] = number of distinct k-mers with count c. */
 int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]);
+/* Conservation check used by the tests and the bench at sizes where no dump can be compared: the sum of all counts of a
+ * count table must equal the number of valid k-mer windows of the reads counted into it.  tg_valid_windows_dev counts those
+ * windows straight from the ASCII record buffer (device memory), sharing nothing with the counting kernels. */
+int tg_table_count_sum(tg_table* t, uint64_t* sum);
+int tg_valid_windows_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, uint64_t* n);
 
 /* ---- one upload for several calls ----------------------------------------------------------------------
  * The reference tools read the same reads twice when `--kmers_from_reads` names the `--reads` file (count, then

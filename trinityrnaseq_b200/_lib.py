@@ -64,6 +64,8 @@ SIGNATURES = {
     "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "tg_log_refine_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32]),
     "tg_log_entry_bytes": (_u32, []),
+    "tg_table_count_sum": (_i32, [_vp, C.POINTER(_u64)]),
+    "tg_valid_windows_dev": (_i32, [_vp, _vp, _u64, _i32, C.POINTER(_u64)]),
     "tg_records_hold": (_i32, [_vp, _vp, _u64]),
     "tg_records_release": (_i32, [_vp]),
     "tg_ipc_export": (_i32, [_vp, _vp, _vp]),

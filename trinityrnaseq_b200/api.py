@@ -96,6 +96,12 @@ class Context:
         check(_lib.lib().tg_log_overflow_check(self._h, C.byref(f)))
         return bool(f.value)
 
+    def valid_windows_dev(self, d_recs, nbytes, k):
+        """number of k-mer windows without a non-ACGT byte in a device record buffer (independent of the count kernels)"""
+        n = C.c_uint64(0)
+        check(_lib.lib().tg_valid_windows_dev(self._h, d_recs, nbytes, k, C.byref(n)))
+        return int(n.value)
+
     def records_hold(self, recs):
         """declare `recs` (a uint8 array, e.g. from pinned()) immutable until records_release: ONE upload shared by the
         count / statistics / assignment calls that are given this same array"""
@@ -343,6 +349,12 @@ class KmerCounter(_Table):
             _lib.lib().tg_free(pk)
             _lib.lib().tg_free(pc)
         return keys, cnts
+
+    def count_sum(self):
+        """sum of the counts of every k-mer in the table"""
+        v = C.c_uint64(0)
+        check(_lib.lib().tg_table_count_sum(self._h, C.byref(v)))
+        return int(v.value)
 
     def histo(self):
         bins = np.zeros(_lib.TG_HISTO_BINS, dtype=np.uint64)

@@ -1212,6 +1212,42 @@ int tg_table_export(tg_table* t, uint32_t min_count, uint32_t max_count, int sor
     return TG_OK;
 }
 
+int tg_table_count_sum(tg_table* t, uint64_t* sum) {
+    if (!t || !sum) return fail(TG_ERR_ARG, "tg_table_count_sum: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    if ((rc = flush_log(t))) return rc;
+    if ((rc = sync_all(c))) return rc;
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof *d));
+    CU(cudaMemsetAsync(d, 0, sizeof *d, c->stream[0]));
+    CU(launch_table_sum(t->slots, t->cap, d, c->stream[0]));
+    c->launches++;
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(d);
+    *sum = v;
+    return TG_OK;
+}
+
+int tg_valid_windows_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k, uint64_t* n) {
+    if (!c || !d_recs || !n || k < 1 || k > 32) return fail(TG_ERR_ARG, "tg_valid_windows_dev: bad argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof *d));
+    CU(cudaMemsetAsync(d, 0, sizeof *d, c->stream[0]));
+    CU(launch_valid_windows((const uint8_t*)d_recs, nbytes, k, d, c->stream[0]));
+    c->launches++;
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(d);
+    *n = v;
+    return TG_OK;
+}
+
 int tg_histo(tg_table* t, uint64_t bins[TG_HISTO_BINS]) {
     if (!t || !bins) return fail(TG_ERR_ARG, "tg_histo: null argument");
     tg_ctx* c = t->ctx;

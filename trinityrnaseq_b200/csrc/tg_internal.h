@@ -129,6 +129,9 @@ cudaError_t launch_histo(const Slot* slots, uint64_t cap, unsigned long long* d_
 cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, uint32_t max_count, int k,
                           int canonical_repr, uint64_t* d_keys, uint32_t* d_vals, unsigned long long* d_n,
                           cudaStream_t s);
+// conservation checks: sum of the counts of a table; valid k-mer windows of a record buffer (independent of the count path)
+cudaError_t launch_table_sum(const Slot* slots, uint64_t cap, unsigned long long* d_out, cudaStream_t s);
+cudaError_t launch_valid_windows(const uint8_t* d_recs, uint64_t nbytes, int k, unsigned long long* d_out, cudaStream_t s);
 // tg_sort.cu: in-place ascending sort of (key,value) pairs on the low 2k bits (CUB radix sort)
 cudaError_t sort_pairs(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, int k, cudaStream_t s);
 

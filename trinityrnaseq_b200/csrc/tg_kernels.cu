@@ -1109,6 +1109,53 @@ cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, u
 }
 
 // =========================================================================================================
+// Conservation checks (tests, bench): sum of all counts in a table; number of valid k-mer windows of a record buffer.
+// The second one shares nothing with the counting kernels (one thread per window, straight from the ASCII), so
+// "sum of counts == valid windows" is an independent end-to-end check at any size and on any number of GPUs.
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+k_table_sum(const Slot* __restrict__ slots, uint64_t cap, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&slots[i]));
+        if ((s.x | s.y) != 0u) acc += s.z;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+__global__ void __launch_bounds__(256)
+k_valid_windows(const uint8_t* __restrict__ recs, uint64_t nbytes, int k, unsigned long long* __restrict__ out) {
+    // thread t owns positions [64 t, 64 t + 64): it walks 64 + k - 1 bytes keeping the length of the current run of bases
+    unsigned long long acc = 0;
+    const uint64_t nstrips = (nbytes + 63) / 64;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < nstrips; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = t * 64, e = min(nbytes, a + 64 + (uint64_t)k - 1);
+        unsigned run = 0;
+        for (uint64_t i = a; i < e; i++) {
+            run = base_valid(recs[i]) ? run + 1u : 0u;
+            // a window ENDS at i and starts at i - k + 1: counted by the strip that owns its start
+            if (run >= (unsigned)k && i + 1 >= a + (uint64_t)k && i + 1 - k < a + 64) acc++;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+cudaError_t launch_table_sum(const Slot* slots, uint64_t cap, unsigned long long* d_out, cudaStream_t s) {
+    TimedLaunch timed("k_table_sum", s);
+    if (cap == 0) return cudaSuccess;
+    k_table_sum<<<148 * 8, 256, 0, s>>>(slots, cap, d_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_valid_windows(const uint8_t* d_recs, uint64_t nbytes, int k, unsigned long long* d_out, cudaStream_t s) {
+    TimedLaunch timed("k_valid_windows", s);
+    if (nbytes == 0) return cudaSuccess;
+    k_valid_windows<<<148 * 8, 256, 0, s>>>(d_recs, nbytes, k, d_out);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
 // GUPS: the measured random-access roofline for this table geometry
 // =========================================================================================================
 // Every thread keeps GUPS_FLIGHT independent accesses in flight (a dependent chain per thread would measure latency, not
