@@ -15,6 +15,7 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--stats-load", type=float, default=0.40)
 ap.add_argument("--no-r2t", action="store_true")
 ap.add_argument("--set", action="append", default=[], help="ctx knob key=value")
+ap.add_argument("--count-variants", default="", help="';'-separated lists of knobs (k=v,k=v): the count is timed once per list")
 a = ap.parse_args()
 ctx = tg.Context(0)
 for kv in a.set:
@@ -30,6 +31,22 @@ d_offs = ctx.dev_alloc(offs.nbytes); ctx.h2d(d_offs, offs)
 d1, d2, d3 = ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads)
 q = None
 out = {}
+if a.count_variants:
+    out["count_variants"] = {}
+    for var in a.count_variants.split(";"):
+        for kv in var.split(","):
+            k_, v_ = kv.split("=")
+            ctx.set(k_, v_)
+        best = None
+        for rep in range(2):
+            ctx.set("kernel_timing", 1); ctx.kernel_times()
+            kc.clear()
+            kc.add_records_dev(d_recs, nbytes)
+            ctx.sync()
+            kt = {k_: round(v[0], 3) for k_, v in ctx.kernel_times().items()}
+            if best is None or sum(kt.values()) < sum(best.values()):
+                best = kt
+        out["count_variants"][var] = best
 for rep in range(a.reps):
     ctx.set("kernel_timing", 1); ctx.kernel_times()
     kc.clear()

@@ -608,8 +608,8 @@ __device__ __forceinline__ LogEntry ld_entry(const LogEntry* p) {
     return e;
 }
 
-template <bool FOLD>
-__global__ void __launch_bounds__(RP_THREADS, RP_MIN_CTAS)
+template <bool FOLD, int MINB>
+__global__ void __launch_bounds__(RP_THREADS, MINB)
 k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned G,
              unsigned long long* chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
@@ -629,6 +629,9 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
         hpoly[4 + tid] = 0ull;
     }
     __shared__ unsigned long long s_w;
+    __shared__ LogEntry s_ent[RP_THREADS / 32][32];             // per warp: the 32 entries being applied,
+    __shared__ unsigned int s_cnt[RP_THREADS / 32][32];         //           their multiplicities (fold),
+    __shared__ unsigned char s_idx[RP_THREADS / 32][256];       //           and (entry << 3 | window) of every k-mer of theirs
     extern __shared__ __align__(16) unsigned char dyn[];
     // fold table of one chunk, open addressing: (bases, minimizer hash, meta) of an entry -> occurrences.  The bases of an
     // entry are never all-A (those windows are homopolymers and bypass the log), so 0 marks a free place.
@@ -712,72 +715,70 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
                 }
             }
             if (FOLD) __syncthreads();
-            // the thread's entries are streamed from DRAM two ahead of the one being applied
-            LogEntry ahead[2];
-            ahead[0].meta = 0u; ahead[1].meta = 0u;
-            if (!FOLD) {
-#pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    const unsigned i = i0 + a * RP_THREADS + tid;
-                    if (i < n) ahead[a] = ld_entry(kbase + i);
-                }
-            }
-#pragma unroll 2
-            for (int gg = 0; gg < RP_PER_THREAD; gg++) {
+            // ---- apply.  A warp takes 32 entries at a time (one per lane, coalesced from the log or from the fold table),
+            // spreads their k-mers -- 1 to 8 each -- over ALL lanes through shared memory, and then every lane settles one k-mer
+            // per round, four rounds in flight: no lane waits for a neighbour's longer run, and the home-slot loads of 128
+            // k-mers of the warp are outstanding together.
+            const int wq = tid >> 5;
+            for (int sub = 0; sub < RP_PER_THREAD; sub++) {
                 LogEntry e;
                 unsigned cnt = 1u;
                 e.meta = 0u;
-                if (!FOLD) {
-                    e = ahead[gg & 1];
-                    ahead[gg & 1].meta = 0u;
-                    const unsigned i = i0 + (gg + 2) * RP_THREADS + tid;
-                    if (gg + 2 < RP_PER_THREAD && i < n) ahead[gg & 1] = ld_entry(kbase + i);
-                }
+                const unsigned slot_i = (unsigned)(wq * (RP_CHUNK / (RP_THREADS / 32)) + sub * 32 + lane);      // entry of the chunk
                 if (FOLD) {
-                    const unsigned sidx = gg * RP_THREADS + tid;
-                    const unsigned long long bases = f_key[sidx];
+                    const unsigned long long bases = f_key[slot_i];
                     if (bases != 0ull) {
-                        const unsigned long long hm = f_hm[sidx];
+                        const unsigned long long hm = f_hm[slot_i];
                         e.b0 = (unsigned)bases; e.b1 = (unsigned)(bases >> 32); e.h = (unsigned)hm; e.meta = (unsigned)(hm >> 32);
-                        cnt = f_cnt[sidx];
-                        f_key[sidx] = 0ull; f_hm[sidx] = 0ull; f_cnt[sidx] = 0u;          // clean for the next chunk
+                        cnt = f_cnt[slot_i];
+                        f_key[slot_i] = 0ull; f_hm[slot_i] = 0ull; f_cnt[slot_i] = 0u;          // clean for the next chunk
                     }
+                } else {
+                    const unsigned i = i0 + slot_i;
+                    if (i < n) e = ld_entry(kbase + i);
                 }
-                if (e.meta != 0u) {
-                    if (e.meta & LE_EXPLICIT) {
-                        table_add(t, make_key(e.b0, e.b1), e.h, cnt, claimed);
-                    } else {
-                        // all windows of the run live in ONE bucket: address it once, have the home-slot loads of up to
-                        // four windows in flight, settle them, then the rest
-                        unsigned long long base, home0;
-                        if (!home_of(t.g, pack_home(e.h, 0u), base, home0)) { atomicExch(t.error, 2); }
-                        else {
-                            const unsigned nw = le_n(e.meta);
+                const unsigned nw = e.meta == 0u ? 0u : (e.meta & LE_EXPLICIT) ? 1u : le_n(e.meta);
+                // exclusive prefix of the window counts -> where this entry's k-mers sit in the warp's list
+                unsigned incl = nw;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const unsigned total = __shfl_sync(FULL, incl, 31), first = incl - nw;
+                s_ent[wq][lane] = e;
+                s_cnt[wq][lane] = cnt;
+                for (unsigned w = 0; w < nw; w++) s_idx[wq][first + w] = (unsigned char)((lane << 3) | w);
+                __syncwarp();
 #pragma unroll 1
-                            for (unsigned w0 = 0; w0 < nw; w0 += 4) {
-                                unsigned long long key[4];
-                                uint4 cur[4];
-                                unsigned slot[4];
+                for (unsigned r0 = 0; r0 < total; r0 += 128) {
+                    unsigned long long key[4], base[4], home[4];
+                    uint4 cur[4];
+                    unsigned kc[4];
 #pragma unroll
-                                for (unsigned u = 0; u < 4; u++)
-                                    if (w0 + u < nw) {
-                                        unsigned hj;
-                                        le_window(e, w0 + u, k, mk, key[u], hj);
-                                        slot[u] = home_slot(hj);
-                                        cur[u] = ld_slot(&t.slots[home0 + slot[u]]);
-                                    }
-#pragma unroll
-                                for (unsigned u = 0; u < 4; u++)
-                                    if (w0 + u < nw) {
-                                        Slot* sl = table_upsert_finish(t, key[u], base, home0 + slot[u], cur[u], claimed);
-                                        if (sl) atomicAdd(&sl->val, cnt);
-                                    }
-                            }
+                    for (int u = 0; u < 4; u++) {
+                        const unsigned i = r0 + u * 32 + lane;
+                        key[u] = 0ull;
+                        if (i < total) {
+                            const unsigned id = s_idx[wq][i];
+                            const LogEntry& se = s_ent[wq][id >> 3];
+                            unsigned hj;
+                            if (se.meta & LE_EXPLICIT) { key[u] = make_key(se.b0, se.b1); hj = se.h; }
+                            else le_window(se, id & 7u, k, mk, key[u], hj);
+                            kc[u] = s_cnt[wq][id >> 3];
+                            if (home_of(t.g, hj, base[u], home[u])) cur[u] = ld_slot(&t.slots[home[u]]);
+                            else { key[u] = 0ull; atomicExch(t.error, 2); }
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (key[u] != 0ull) {
+                            Slot* sl = table_upsert_finish(t, key[u], base[u], home[u], cur[u], claimed);
+                            if (sl) atomicAdd(&sl->val, kc[u]);
+                        }
+                    __syncwarp();   // lanes leave the probe loops at different times: reconverge before the next round
                 }
-                __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
-                                // and every later log load / probe is issued once per lane subset
+                __syncwarp();       // the warp's lists are rewritten by the next 32 entries
             }
         }
     }
@@ -923,18 +924,18 @@ cudaError_t launch_log_replay(const LogEntry* d_keys, const unsigned int* d_curs
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const bool fold = (prefetch & 2) != 0;             // bit 1 of the flags word: fold duplicates per chunk
+    const bool dense = (prefetch & 4) != 0;            // bit 2: 4 CTAs per SM (64 registers) instead of 3
     const size_t dyn = fold ? (size_t)RP_FOLD * 20 : 0;
-    const void* kern = fold ? (const void*)k_log_replay<true> : (const void*)k_log_replay<false>;
-    int grid = max_resident_ctas(kern, RP_THREADS, dyn, -1);
+    using Kern = void (*)(const LogEntry*, const unsigned int*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                          unsigned long long*, unsigned long long*, TableView, int);
+    const Kern kern = fold ? (dense ? (Kern)k_log_replay<true, 4> : (Kern)k_log_replay<true, 3>)
+                           : (dense ? (Kern)k_log_replay<false, 4> : (Kern)k_log_replay<false, 3>);
+    int grid = max_resident_ctas((const void*)kern, RP_THREADS, dyn, -1);
     if (grid <= 0) grid = sm_count;
     grid = grid / (int)groups * (int)groups;           // the same number of CTAs in every group
     if (grid < (int)groups) grid = (int)groups;
-    if (fold)
-        k_log_replay<true><<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
-                                                       d_chunk_start, d_hpoly, t, prefetch & 1);
-    else
-        k_log_replay<false><<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
-                                                        d_chunk_start, d_hpoly, t, prefetch & 1);
+    kern<<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups, d_chunk_start, d_hpoly, t,
+                                       prefetch & 1);
     return cudaGetLastError();
 }
 
