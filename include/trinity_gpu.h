@@ -159,6 +159,21 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
  * (Chrysalis/analysis/sequenceUtil.cc:326-355); host-side, evaluated with the reference's fp32 expression. */
 void tg_entropy_table(int k, float min_entropy, uint8_t* entropy_ok /* 26*26*26 */);
 
+/* ---- next row: GraphFromFasta weldmer counting ----------------------------------------
+ * NonRedKmerTable::SetUp(crossover) + AddData(DNAStringStreamFast&) (Chrysalis/analysis/GraphFromFasta.cc:1412-1424,
+ * NonRedKmerTable.cc:12-96,162-200): `weldmers` holds n candidate strings of kk characters back to back (33 <= kk <= 48; the
+ * reference's default -kk is 48).  Every window of kk bases of every record that EQUALS a candidate -- forward strand only,
+ * case-insensitive, no canonicalisation -- adds one to that candidate's counter.  tg_weld_counts returns the counters in
+ * input order (duplicate candidates share one counter, like the reference's unique-sorted table; a candidate with a
+ * non-ACGT character can match no read window and stays 0).  Counts are what GetCount(weldmer, 0) returns to the weld
+ * decisions (GraphFromFasta.cc:538,584). */
+typedef struct tg_weld tg_weld;
+int tg_weld_create(tg_ctx* ctx, int kk, const char* weldmers, uint64_t n, tg_weld** out);
+void tg_weld_destroy(tg_weld* w);
+int tg_weld_count_reads(tg_weld* w, const char* recs, uint64_t nbytes);
+int tg_weld_count_reads_dev(tg_weld* w, const void* d_recs, uint64_t nbytes);
+int tg_weld_counts(tg_weld* w, int32_t* counts /* n */);
+
 /* ---- device-resident variants (inputs already in HBM; used for kernel-only timing) ----------------------
  * These calls (and tg_table_clear) are STREAM-ORDERED and never synchronise with the host: they return once the work is
  * queued, results and error flags are valid after tg_sync (or any host-buffer call on the same table).  A caller can

@@ -21,6 +21,7 @@
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (no -march, like the reference's -O2 build, so fp32
  * expressions are evaluated exactly as in Inchworm/Chrysalis: no FMA, one rounding per operation).
  */
+#include <ctype.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -404,4 +405,54 @@ void orc_rt_assign(orc_rt* t, const char* recs, const uint64_t* offs, uint64_t n
         if (score_out) score_out[r] = max;
     }
     free(d); free(dd); free(comp);
+}
+
+/* =========================================================================================================
+ * GraphFromFasta weldmer counting
+ *   NonRedKmerTable::SetUp(templ)  Chrysalis/analysis/NonRedKmerTable.cc:12-96   the candidates, sorted and made unique
+ *   NonRedKmerTable::AddData(DNAStringStreamFast&)  :162-200   every read upper-cased; every window of m_k characters is
+ *       looked up by binary search over the sorted STRINGS (exact match: forward strand, no canonicalisation) and bumps
+ *       the counter of the candidate it equals
+ *   NonRedKmerTable::GetCount  NonRedKmerTable.h:50-55          the counter, 0 for a string that is not a candidate
+ * counts[i] = counter of candidate i after all records (duplicate candidates share one counter).
+ * ========================================================================================================= */
+static int g_weld_kk;
+static const char* g_weld_base;
+static int weld_cmp_idx(const void* a, const void* b) {
+    return memcmp(g_weld_base + *(const uint64_t*)a * (uint64_t)g_weld_kk, g_weld_base + *(const uint64_t*)b * (uint64_t)g_weld_kk,
+                  (size_t)g_weld_kk);
+}
+void orc_weld_count(const char* weldmers, uint64_t n, int kk, const char* recs, const uint64_t* offs, uint64_t nreads,
+                    int32_t* counts) {
+    uint64_t* order = (uint64_t*)malloc((n ? n : 1) * sizeof *order);
+    int32_t* cnt = (int32_t*)calloc(n ? n : 1, sizeof *cnt);             /* counter of the candidate at sorted position i */
+    for (uint64_t i = 0; i < n; i++) order[i] = i;
+    g_weld_kk = kk; g_weld_base = weldmers;
+    qsort(order, n, sizeof *order, weld_cmp_idx);                          /* UniqueSort: equal strings end up adjacent */
+    char* win = (char*)malloc((size_t)kk + 1);
+    for (uint64_t r = 0; r < nreads; r++) {
+        const char* s = recs + offs[r];
+        const int64_t len = (int64_t)(offs[r + 1] - offs[r]) - 1;
+        for (int64_t j = 0; j <= len - kk; j++) {
+            for (int x = 0; x < kk; x++) win[x] = (char)toupper((unsigned char)s[j + x]);
+            /* BinSearch: first sorted position whose string is >= the window */
+            uint64_t lo = 0, hi = n;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (memcmp(weldmers + order[mid] * (uint64_t)kk, win, (size_t)kk) < 0) lo = mid + 1; else hi = mid;
+            }
+            if (lo < n && memcmp(weldmers + order[lo] * (uint64_t)kk, win, (size_t)kk) == 0) cnt[lo]++;
+        }
+    }
+    /* every input candidate reports the counter of the first sorted position holding its string */
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t lo = 0, hi = n;
+        const char* w = weldmers + i * (uint64_t)kk;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) / 2;
+            if (memcmp(weldmers + order[mid] * (uint64_t)kk, w, (size_t)kk) < 0) lo = mid + 1; else hi = mid;
+        }
+        counts[i] = cnt[lo];
+    }
+    free(win); free(cnt); free(order);
 }

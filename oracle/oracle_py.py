@@ -48,6 +48,7 @@ def lib():
         L.orc_rt_label.argtypes = [vp, vp, vp, u64, u32]
         L.orc_rt_assign.argtypes = [vp, vp, vp, u64, i32, C.c_float, vp, vp, vp]
         L.orc_entropy.restype = C.c_float; L.orc_entropy.argtypes = [C.c_char_p, i32]
+        L.orc_weld_count.argtypes = [vp, u64, i32, vp, vp, u64, vp]
         _lib = L
     return _lib
 
@@ -244,3 +245,14 @@ def format_read_name(name):
     while name[-1:] == " ":
         name = name[:-1]
     return name
+
+
+def weld_count(weldmers, kk, recs, offs):
+    """GraphFromFasta weldmer counting restated (oracle.c: orc_weld_count): weldmers = list of kk-character strings;
+    -> int32 counts in input order"""
+    blob = np.frombuffer(b"".join(w if isinstance(w, bytes) else w.encode() for w in weldmers), dtype=np.uint8)
+    assert blob.size == len(weldmers) * kk
+    recs = _u8(recs); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    out = np.zeros(len(weldmers), np.int32)
+    lib().orc_weld_count(_p(blob) if blob.size else None, len(weldmers), kk, _p(recs), _p(offs), len(offs) - 1, _p(out))
+    return out

@@ -411,3 +411,41 @@ class BundleKmerTable(_Table):
         check(_lib.lib().tg_assign_reads(self._h, _ptr(recs), _ptr(offs), n, int(strand), _ptr(self.entropy_ok),
                                          _ptr(best), _ptr(pct), _ptr(score)))
         return best, pct, score
+
+
+class WeldmerTable:
+    """NonRedKmerTable of GraphFromFasta's weldmer candidates (Chrysalis/analysis/GraphFromFasta.cc:1412-1424): a fixed set of
+    kk-mers (33..48 bases), the forward windows of the reads that equal one are counted."""
+
+    def __init__(self, ctx, weldmers, kk=48):
+        blob = b"".join(w if isinstance(w, bytes) else w.encode() for w in weldmers)
+        if len(blob) != len(weldmers) * kk:
+            raise ValueError("every weldmer must have exactly kk characters")
+        self.ctx, self.kk, self.n = ctx, kk, len(weldmers)
+        self._blob = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(0, np.uint8)
+        h = C.c_void_p()
+        check(_lib.lib().tg_weld_create(ctx._h, kk, _ptr(self._blob) if self.n else None, self.n, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().tg_weld_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def add_records(self, recs):
+        a = _as_u8(recs)
+        check(_lib.lib().tg_weld_count_reads(self._h, _ptr(a), a.nbytes))
+
+    def add_records_dev(self, d_recs, nbytes):
+        check(_lib.lib().tg_weld_count_reads_dev(self._h, d_recs, nbytes))
+
+    def counts(self):
+        out = np.zeros(self.n, np.int32)
+        check(_lib.lib().tg_weld_counts(self._h, _ptr(out) if self.n else None))
+        return out

@@ -1637,6 +1637,111 @@ void tg_entropy_table(int k, float min_entropy, uint8_t* ok) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// GraphFromFasta weldmer counting
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace tg { unsigned long long weld_hash_host(unsigned long long lo, unsigned hi); }
+
+struct tg_weld {
+    tg_ctx* ctx = nullptr;
+    int kk = 48;
+    uint64_t n = 0, cap = 0;
+    WeldSlot* d_slots = nullptr;
+    std::vector<int64_t> slot_of;        // table slot of input weldmer i, -1 = unmatchable (a non-ACGT character)
+};
+
+extern "C" {
+
+int tg_weld_create(tg_ctx* c, int kk, const char* weldmers, uint64_t n, tg_weld** out) {
+    if (!c || !out || (!weldmers && n)) return fail(TG_ERR_ARG, "tg_weld_create: null argument");
+    if (kk < 33 || kk > 48) return fail(TG_ERR_ARG, "weldmer length %d unsupported (33..48; GraphFromFasta's default -kk is 48)", kk);
+    if (bind(c)) return TG_ERR_CUDA;
+    tg_weld* w = new tg_weld();
+    w->ctx = c; w->kk = kk; w->n = n;
+    uint64_t cap = 1024;
+    while (cap < 4 * n) cap <<= 1;                       // load <= 0.25: a miss settles on the first slot three times out of four
+    w->cap = cap;
+    std::vector<WeldSlot> host(cap);
+    memset(host.data(), 0, cap * sizeof(WeldSlot));
+    w->slot_of.assign(n, -1);
+    for (uint64_t i = 0; i < n; i++) {
+        const char* s = weldmers + i * (uint64_t)kk;
+        unsigned long long p0 = 0, p1 = 0;
+        bool ok = true;
+        for (int b = 0; b < kk && ok; b++) {
+            const unsigned ch = (unsigned char)s[b];
+            if (!base_valid(ch)) { ok = false; break; }
+            const unsigned code = base_code(ch);
+            p0 |= (unsigned long long)(code & 1u) << b;
+            p1 |= (unsigned long long)(code >> 1) << b;
+        }
+        if (!ok) continue;                               // can never equal a window of read bases
+        const unsigned long long lo = p0 | (p1 << 48);
+        const unsigned hi = (unsigned)(p1 >> 16);
+        uint64_t at = weld_hash_host(lo, hi) & (cap - 1);
+        while ((host[at].cnt & WELD_OCCUPIED) && !(host[at].lo == lo && host[at].hi == hi)) at = (at + 1) & (cap - 1);
+        host[at].lo = lo; host[at].hi = hi; host[at].cnt = WELD_OCCUPIED;
+        w->slot_of[i] = (int64_t)at;
+    }
+    cudaError_t e = cudaMalloc(&w->d_slots, cap * sizeof(WeldSlot));
+    if (e != cudaSuccess) { delete w; CU(e); }
+    CU(cudaMemcpyAsync(w->d_slots, host.data(), cap * sizeof(WeldSlot), cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    *out = w;
+    return TG_OK;
+}
+
+void tg_weld_destroy(tg_weld* w) {
+    if (!w) return;
+    cudaSetDevice(w->ctx->device);
+    cudaDeviceSynchronize();
+    if (w->d_slots) cudaFree(w->d_slots);
+    delete w;
+}
+
+int tg_weld_count_reads_dev(tg_weld* w, const void* d_recs, uint64_t nbytes) {
+    if (!w || !d_recs) return fail(TG_ERR_ARG, "tg_weld_count_reads_dev: null argument");
+    tg_ctx* c = w->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(launch_weld_tiles((const uint8_t*)d_recs, nbytes, w->kk, w->d_slots, w->cap - 1, c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+
+int tg_weld_count_reads(tg_weld* w, const char* recs, uint64_t nbytes) {
+    if (!w || (!recs && nbytes)) return fail(TG_ERR_ARG, "tg_weld_count_reads: null argument");
+    tg_ctx* c = w->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc;
+    uint64_t pos = 0;
+    for (int it = 0; pos < nbytes; it++) {
+        const int b = it & 1;
+        const uint64_t end = batch_end(recs, pos, nbytes, c->batch_bytes);
+        const uint64_t n = end - pos;
+        CU(cudaStreamSynchronize(c->stream[b]));          // staging buffer b is free again
+        if ((rc = upload_records(c, b, recs + pos, n))) return rc;
+        CU(launch_weld_tiles((const uint8_t*)c->recs[b].p, n, w->kk, w->d_slots, w->cap - 1, c->sm_count, c->stream[b]));
+        c->launches++;
+        pos = end;
+    }
+    return sync_all(c);
+}
+
+int tg_weld_counts(tg_weld* w, int32_t* counts) {
+    if (!w || (!counts && w->n)) return fail(TG_ERR_ARG, "tg_weld_counts: null argument");
+    tg_ctx* c = w->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    std::vector<WeldSlot> host(w->cap);
+    CU(cudaMemcpy(host.data(), w->d_slots, w->cap * sizeof(WeldSlot), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < w->n; i++)
+        counts[i] = w->slot_of[i] < 0 ? 0 : (int32_t)(host[(size_t)w->slot_of[i]].cnt & ~WELD_OCCUPIED);
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // device memory + timing + measurement utilities
 // ---------------------------------------------------------------------------------------------------------
 int tg_dev_alloc(tg_ctx* c, uint64_t bytes, void** dptr) {

@@ -13,12 +13,14 @@ constexpr int CT_THREADS = 256;
 constexpr int CT_TILE = CT_THREADS * 32;   // bases per tile: one 32-base chunk per thread
 constexpr int CT_HALO = 32;                // one extra chunk so windows may run past the tile end (k <= 32)
 constexpr int CT_LOAD = CT_TILE + CT_HALO; // bytes per TMA bulk copy (multiple of 16)
+constexpr int REC_PAD = 64;                // '\n' bytes behind the last tile of a device record buffer: the weldmer kernel's
+                                           // windows (up to 48 bases) read two chunks past a tile
 
 // bytes a device record buffer of nbytes must be allocated (and '\n'-padded) to
 inline uint64_t padded_record_bytes(uint64_t nbytes) {
     uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
     if (ntiles == 0) ntiles = 1;
-    return ntiles * CT_TILE + CT_HALO;
+    return ntiles * CT_TILE + REC_PAD;
 }
 
 // ---- geometry of the per-read kernels (stats / assign) ------------------------------------------------
@@ -124,6 +126,16 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
                                     int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
                                     int* d_error, int nctas, cudaStream_t s);
 
+// ---- GraphFromFasta weldmer counting: a read-only set of kk-mers (33 <= kk <= 48), every FORWARD
+// window of every read that equals one of them bumps its counter (NonRedKmerTable::AddData, NonRedKmerTable.cc:162-200)
+struct __align__(16) WeldSlot {
+    unsigned long long lo;    // plane0 (kk bits) | low 16 bits of plane1 << 48
+    unsigned int hi;          // plane1 >> 16
+    unsigned int cnt;         // WELD_OCCUPIED | occurrences
+};
+constexpr unsigned WELD_OCCUPIED = 0x80000000u;
+cudaError_t launch_weld_tiles(const uint8_t* d_recs, uint64_t nbytes, int kk, WeldSlot* slots, uint64_t cap_mask, int sm_count,
+                              cudaStream_t s);
 // table scans
 cudaError_t launch_histo(const Slot* slots, uint64_t cap, unsigned long long* d_bins /*10002*/, cudaStream_t s);
 cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, uint32_t max_count, int k,
