@@ -176,19 +176,6 @@ def test_jellyfish_sequence_file_parser_cpp(tmp_path):
     assert parse(fqs, flush=500)[1] == want
 
 
-def test_minimizer_fast_path_equals_slow_path(tmp_path):
-    """trinityrnaseq_b200/csrc/tg_minimizer.cuh is host+device code: the sliding-minimum fast path the kernels use for the
-    windows of a read must give exactly the home (minimizer hash, slot) that the per-key slow path gives -- every k, every
-    strip width, both strands, tie-heavy reads (tests/cpp/test_minimizer.cpp)."""
-    import subprocess
-    exe = tmp_path / "test_minimizer"
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", str(exe),
-                    os.path.join(ROOT, "tests", "cpp", "test_minimizer.cpp")], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    assert "fast == slow" in r.stdout
-
-
 def test_parallel_fasta_parser_equals_serial(tmp_path):
     """host/par_fasta.hpp: chunked multi-threaded parsing == serial parsing, record for record, in file order, for FASTA
     texts with every reader quirk and chunk sizes down to one byte (tests/cpp/par_fasta_test.cpp)."""

@@ -70,6 +70,9 @@ struct tg_ctx {
     // per-stream staging for the host-buffer entry points
     DevBuf recs[2], offs[2], out_a[2], out_b[2], out_c[2], per_kmer[2], long_idx[2], scratch;
     DevBuf lut;
+    DevBuf locus[2];                                    // per stream: signatures, indices, sort scratch of the locus order
+    bool locus_order = true;                            // per-read kernels visit the reads in locus order (tg_perread.cu)
+    uint64_t locus_min_reads = 1ull << 15;              // ... when a launch has at least this many reads
     DevBuf long_scratch;                                // fixed budget of the device-driven CTA-per-read kernels (*_dev entry points)
     size_t long_scratch_bytes = 64ull << 20;            // reads up to ~2 M windows; longer ones: host-buffer entry points
     cudaEvent_t order[2] = {nullptr, nullptr};          // cross-stream ordering without host syncs
@@ -99,7 +102,7 @@ struct tg_ctx {
 
 // k-mer log of a count table (partitioned count path)
 struct KeyLog {
-    LogEntry* keys = nullptr;                  // [nbins][cap] 16-B entries (key + packed home)
+    LogEntry* keys = nullptr;                  // [nbins][cap] entries
     unsigned int* cursor = nullptr;
     unsigned long long* chunk_start = nullptr;
     unsigned long long* hpoly = nullptr;   // [8] homopolymer side channel (keys, counts)
@@ -258,7 +261,7 @@ void tg_destroy(tg_ctx* c) {
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
-    c->scratch.release(); c->lut.release(); c->long_scratch.release();
+    c->scratch.release(); c->lut.release(); c->long_scratch.release(); c->locus[0].release(); c->locus[1].release();
     c->held.dev.release(); c->held.offs.release(); c->held.out_a.release(); c->held.out_b.release(); c->held.out_c.release();
     c->held.long_idx.release();
     for (int i = 0; i < 2; i++) if (c->held.chunk_done[i]) cudaEventDestroy(c->held.chunk_done[i]);
@@ -355,6 +358,11 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
     } else if (!strcmp(key, "replay_groups")) {
         if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
         c->replay_groups = (unsigned)v;
+    } else if (!strcmp(key, "locus_order")) {
+        c->locus_order = v != 0;
+    } else if (!strcmp(key, "locus_min_reads")) {
+        if (v < 0) return fail(TG_ERR_ARG, "locus_min_reads out of range");
+        c->locus_min_reads = (uint64_t)v;
     } else if (!strcmp(key, "kernel_timing")) {
         c->timer.on = v != 0;
     } else {
@@ -474,23 +482,11 @@ int tg_table_clear(tg_table* t) {
     return TG_OK;
 }
 
-// Re-insert the k-mers of t with count >= min_count into `to` (growth, `dump -L n` on the device).  Who comes first keeps
-// its home slot, and a k-mer that is looked up a thousand times per step should not lose it to one of its own error
-// variants (same minimizer, same slot, a count of 2): count tables go in three passes, the most frequent k-mers first.
+// Re-insert the k-mers of t with count >= min_count into `to` (growth, `dump -L n` on the device).
 static int rehash_by_priority(tg_table* t, TableView to, uint32_t min_count) {
     tg_ctx* c = t->ctx;
-    if (t->kind == TG_TABLE_LABEL) {
-        CU(launch_rehash(t->slots, t->cap, to, 1, 0, 0xFFFFFFFFu, c->stream[0]));
-        c->launches++;
-        return TG_OK;
-    }
-    const uint32_t lo_of[3] = {64u, 8u, 0u}, hi_of[3] = {0xFFFFFFFFu, 63u, 7u};
-    for (int pass = 0; pass < 3; pass++) {
-        const uint32_t lo = std::max(lo_of[pass], min_count), hi = hi_of[pass];
-        if (lo > hi) continue;
-        CU(launch_rehash(t->slots, t->cap, to, 0, lo, hi, c->stream[0]));
-        c->launches++;
-    }
+    CU(launch_rehash(t->slots, t->cap, to, t->kind == TG_TABLE_LABEL, min_count, 0xFFFFFFFFu, c->stream[0]));
+    c->launches++;
     return TG_OK;
 }
 
@@ -698,10 +694,8 @@ static bool log_pays(const tg_table* t, uint64_t nbytes) {
 constexpr uint64_t LOG_BIN_SLACK = 1024;    // additive head-room per bin (hash fluctuation of small batches)
 constexpr double LOG_BIN_FACTOR = 1.2;      // multiplicative head-room per bin (hot k-mers)
 
-// log entries a phase-1 launch over nbytes record bytes is laid out for.  An entry is a run of up to 8 windows that share
-// a minimizer (typically ~3.5 windows, i.e. ~0.2 entries per byte); one entry per two bytes leaves 2x head-room, and a
-// bin that fills up all the same counts its overflow directly (correct, only slower).
-static uint64_t log_launch_cost(const tg_ctx*, const KeyLog&, uint64_t nbytes) { return nbytes / 2 + 4096; }
+// log entries one phase-1 launch over nbytes record bytes can take up at most: one per byte
+static uint64_t log_launch_cost(const tg_ctx*, const KeyLog&, uint64_t nbytes) { return nbytes; }
 
 // entries that can be appended to an empty log without any bin expected to overflow
 static uint64_t log_room(const KeyLog& lg) {
@@ -1303,6 +1297,21 @@ static int held_pass(tg_ctx* c, const uint64_t* offs, uint64_t nreads, bool* don
     return TG_OK;
 }
 
+// Locus order of the reads [0, nreads) of a device record buffer, queued on stream b: *d_order = u32[nreads], or nullptr
+// when the launch is too small to pay for it (or the knob is off).  Stream-ordered, no host synchronisation.
+static int locus_order_async(tg_ctx* c, int b, const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads,
+                             int k, const uint32_t** d_order) {
+    *d_order = nullptr;
+    if (!c->locus_order || nreads < c->locus_min_reads || nreads > 0x7FFFFFF0ull) return TG_OK;
+    const size_t need = locus_sort_bytes(nreads);
+    CU(c->locus[b].ensure(need));
+    uint32_t* sig = (uint32_t*)c->locus[b].p;
+    CU(launch_read_locus(d_recs, d_offs, rec_base, nreads, k, sig, sig + nreads, c->stream[b]));
+    CU(locus_sort(c->locus[b].p, need, nreads, d_order, c->stream[b]));
+    c->launches += 2;
+    return TG_OK;
+}
+
 struct ReadBatch { uint64_t r0, r1; };
 
 static std::vector<ReadBatch> split_reads(const uint64_t* offs, uint64_t nreads, size_t batch_bytes) {
@@ -1373,8 +1382,10 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
         // held records: the device copy is there already (or goes up once, now); one pass over all reads, no staging
         bool done = false;
         if ((rc = held_pass(c, offs, nreads, &done, [&](const uint8_t* d, const uint64_t* d_offs, LongList ll) -> int {
+                const uint32_t* ord = nullptr;
+                if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord)) return r3;
                 CU(launch_cov_stats(d, d_offs, 0, nreads, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
-                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, c->stream[0]));
+                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, ord, c->stream[0]));
                 CU(launch_cov_stats_long_auto(d, d_offs, 0, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
                                               (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, c->long_scratch.p,
                                               c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[0]));
@@ -1422,9 +1433,11 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
         CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
         LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
         if (t->k >= MIN_FAST_K) {
+            const uint32_t* ord = nullptr;
+            if ((rc = locus_order_async(c, b, (const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, &ord))) return rc;
             CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
                                 t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
-                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, c->stream[b]));
+                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, ord, c->stream[b]));
         } else {
             // k-mers shorter than the warp path's 8 m-mers per k-mer: every read through the CTA-per-read kernel
             int nctas = 0; size_t need = 0;
@@ -1460,8 +1473,10 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     CU(c->long_scratch.ensure(c->long_scratch_bytes));
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
     LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+    const uint32_t* ord = nullptr;
+    if (int rc = locus_order_async(c, b, (const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, &ord)) return rc;
     CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->g,
-                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->stream[b]));
+                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, ord, c->stream[b]));
     CU(launch_cov_stats_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots, t->g,
                                   (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->long_scratch.p,
                                   c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[b]));
@@ -1527,8 +1542,10 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
     if (t->k >= MIN_FAST_K && nreads <= 0x7FFFFFF0ull && is_held(c, recs, offs[nreads])) {
         bool done = false;
         if ((rc = held_pass(c, offs, nreads, &done, [&](const uint8_t* d, const uint64_t* d_offs, LongList ll) -> int {
+                const uint32_t* ord = nullptr;
+                if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord)) return r3;
                 CU(launch_assign(d, d_offs, 0, nreads, t->k, strand, t->slots, t->g, (const uint8_t*)c->lut.p,
-                                 (int32_t*)c->held.out_a.p, (int32_t*)c->held.out_b.p, (int32_t*)c->held.out_c.p, ll, c->stream[0]));
+                                 (int32_t*)c->held.out_a.p, (int32_t*)c->held.out_b.p, (int32_t*)c->held.out_c.p, ll, ord, c->stream[0]));
                 CU(launch_assign_long_auto(d, d_offs, 0, t->k, strand, t->slots, t->g, (const uint8_t*)c->lut.p,
                                            (int32_t*)c->held.out_a.p, (int32_t*)c->held.out_b.p, (int32_t*)c->held.out_c.p, ll,
                                            c->long_scratch.p, c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[0]));
@@ -1572,9 +1589,11 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
         CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
         LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
         if (t->k >= MIN_FAST_K) {
+            const uint32_t* ord = nullptr;
+            if ((rc = locus_order_async(c, b, (const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, &ord))) return rc;
             CU(launch_assign((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, strand, t->slots,
                              t->g, (const uint8_t*)c->lut.p, (int32_t*)c->out_a[b].p, (int32_t*)c->out_b[b].p,
-                             (int32_t*)c->out_c[b].p, ll, c->stream[b]));
+                             (int32_t*)c->out_c[b].p, ll, ord, c->stream[b]));
         } else {
             int nctas = 0; size_t need = 0;
             const unsigned max_win = batch_max_windows(offs, rb.r0, rb.r1, t->k);
@@ -1606,8 +1625,10 @@ int tg_assign_reads_dev(tg_table* t, const void* d_recs, const void* d_offs, uin
     CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
     LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
     CU(c->long_scratch.ensure(c->long_scratch_bytes));
+    const uint32_t* ord = nullptr;
+    if (int rc = locus_order_async(c, b, (const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, &ord)) return rc;
     CU(launch_assign((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, strand, t->slots, t->g,
-                     (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll, c->stream[b]));
+                     (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll, ord, c->stream[b]));
     CU(launch_assign_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, strand, t->slots, t->g,
                                (const uint8_t*)d_entropy_ok, (int32_t*)d_best, (int32_t*)d_pct, nullptr, ll,
                                c->long_scratch.p, c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[b]));

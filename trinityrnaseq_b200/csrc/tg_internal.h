@@ -100,7 +100,7 @@ cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int
 // per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s);
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, cudaStream_t s);
 cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
                                   const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
@@ -115,7 +115,7 @@ cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_
 
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                           int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok,
-                          int32_t* d_best, int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s);
+                          int32_t* d_best, int32_t* d_pct, int32_t* d_score, LongList ll, const uint32_t* d_order, cudaStream_t s);
 cudaError_t launch_assign_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int strand,
                                const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                                int32_t* d_pct, int32_t* d_score, const unsigned int* d_long_idx, unsigned int n_long,
@@ -125,6 +125,12 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
                                     const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
                                     int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
                                     int* d_error, int nctas, cudaStream_t s);
+
+// locus order of the reads (tg_perread.cu, tg_sort.cu): signature per read, then a radix sort of (signature, index)
+cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                              uint32_t* d_sig, uint32_t* d_idx, cudaStream_t s);
+size_t locus_sort_bytes(uint64_t n);
+cudaError_t locus_sort(void* work, size_t work_bytes, uint64_t n, const uint32_t** d_sorted, cudaStream_t s);
 
 // ---- GraphFromFasta weldmer counting: a read-only set of kk-mers (33 <= kk <= 48), every FORWARD
 // window of every read that equals one of them bumps its counter (NonRedKmerTable::AddData, NonRedKmerTable.cc:162-200)

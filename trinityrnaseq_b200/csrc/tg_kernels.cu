@@ -111,6 +111,8 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
 #pragma unroll 1
             for (int g = 0; g < 32; g += 4) {
                 unsigned long long key[4];
+                Probe pr[4];
+                unsigned long long cur[4];
                 unsigned cnt[4];
                 uint32_t lab[4];
                 unsigned rcs = 0;      // LABEL: bit u set = window u is the reverse complement of its (canonical) key
@@ -143,17 +145,23 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                     for (int u = 1; u < 4; u++)
                         if (key[u] != 0ull && key[u] == key[u - 1]) { cnt[u] += cnt[u - 1]; key[u - 1] = 0ull; }
                 }
-                // homes by the slow path (8 m-mer hashes per key): this kernel serves inputs that are small next to the
-                // table -- the bundle records, short batches, the overflow of a full log bin
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                     if (key[u] != 0ull) {
-                        const unsigned hj = key_home_packed(key[u], k);
+                        if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
+                        else { key[u] = 0ull; atomicExch(t.error, 2); }
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (key[u] != 0ull) {
                         if (MODE == MODE_COUNT) {
-                            table_add(t, key[u], hj, cnt[u], claimed);
+                            Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
+                            if (sl) atomicAdd(&sl->val, cnt[u]);
                         } else {
                             // `claimed` counts distinct FORWARD k-mers (NonRedKmerTable's size): first label of a field
-                            if (table_label_max(t, key[u], hj, (rcs >> u) & 1u, lab[u])) claimed++;
+                            unsigned slots_claimed = 0;
+                            Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], slots_claimed);
+                            if (sl && atomicMax((rcs >> u) & 1u ? &sl->aux : &sl->val, lab[u]) == 0u) claimed++;
                         }
                     }
                 __syncwarp(act);   // lanes leave the probe loops at different times: reconverge before the next group
@@ -227,18 +235,14 @@ static_assert(CT_TILE % LT_TILE == 0, "record buffers are padded to CT_TILE");
 
 struct LogSmem {
     alignas(128) uint8_t ascii[2][LT_LOAD];
-    uint32_t p0[LT_CHUNKS + 2];                     // + halo chunk + one word the funnel shifts of the halo may touch
-    uint32_t p1[LT_CHUNKS + 2];
-    uint32_t pb[LT_CHUNKS + 2];
-    // entry descriptors, row e = the thread's e-th entry (phase A -> B): minimizer hash / packed home, rank inside its bin
-    // in this tile, and first window | (n - 1) << 4 | q0 << 7 | explicit << 10
-    uint32_t eh[LT_TILE];
-    uint16_t erank[LT_TILE];
-    uint16_t einfo[LT_TILE];
+    uint32_t p0[LT_CHUNKS + 1];
+    uint32_t p1[LT_CHUNKS + 1];
+    uint32_t pb[LT_CHUNKS + 1];
+    uint32_t meta[LT_TILE];                         // bin << 12 | rank, ~0 = no entry
     uint32_t wtot[LT_THREADS / 32];
     uint32_t total;
     alignas(8) unsigned long long bar[2];
-    LogEntry* seg[LOG_MAX_RANKS];                   // this rank's segment in every owner's log (dynamic index: not params)
+    unsigned long long* seg[LOG_MAX_RANKS];         // this rank's segment in every owner's log (dynamic index: not params)
 };
 
 __device__ __forceinline__ unsigned long long window_key(unsigned f0, unsigned f1, int k, int canonical) {
@@ -254,22 +258,17 @@ __global__ void __launch_bounds__(LT_THREADS, 2)
 k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, LogView lg, TableView t) {
     __shared__ LogSmem sm;
     extern __shared__ __align__(16) unsigned char dyn[];
-    // dynamic: sent[LT_TILE] 16-B entries (the m-mer hashes of phases H/A share its memory) | delta[nbins] u32 |
-    //          cnt16[nbins2] u16 | off16[nbins2] u16
+    // dynamic: skey[LT_TILE] u64 | delta[nbins] u32 | sbin[LT_TILE] u16 | cnt16[nbins2] u16 | off16[nbins2] u16
     const unsigned nbins = lg.nbins, nbins2 = (nbins + 1u) & ~1u;
-    LogEntry* sent = reinterpret_cast<LogEntry*>(dyn);
-    unsigned int* hx = reinterpret_cast<unsigned int*>(dyn);
-    static_assert((LT_TILE + HOME_SLOTS) * 17 / 16 * 4 <= LT_TILE * 16, "the hash array fits the sorted-tile buffer");
-    unsigned int* delta = reinterpret_cast<unsigned int*>(sent + LT_TILE);
-    unsigned short* cnt16 = reinterpret_cast<unsigned short*>(delta + nbins);
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned int* delta = reinterpret_cast<unsigned int*>(skey + LT_TILE);
+    unsigned short* sbin = reinterpret_cast<unsigned short*>(delta + nbins);
+    unsigned short* cnt16 = sbin + LT_TILE;
     unsigned short* off16 = cnt16 + nbins2;
     unsigned int* cnt32 = reinterpret_cast<unsigned int*>(cnt16);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mk = kmask(k);
-    const int m = mm_len(k);
-    const unsigned mm = kmask(m);
-    const unsigned nmax = (unsigned)le_max_run(k);
     unsigned claimed = 0;
     unsigned hpA = 0, hpC = 0, hpG = 0, hpT = 0;    // homopolymer windows seen by this thread, by base code
 
@@ -280,7 +279,6 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
 #pragma unroll
         for (int r = 0; r < LOG_MAX_RANKS; r++)
             sm.seg[r] = lg.owner[r] ? lg.owner[r] + (((unsigned long long)lg.src << lg.lp_shift) * lg.cap) : nullptr;
-        sm.p0[LT_CHUNKS + 1] = 0u; sm.p1[LT_CHUNKS + 1] = 0u; sm.pb[LT_CHUNKS + 1] = 0xFFFFFFFFu;
     }
     for (unsigned b = tid; b < nbins2 / 2; b += LT_THREADS) cnt32[b] = 0u;
     __syncthreads();
@@ -311,104 +309,30 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
         }
         __syncthreads();   // planes complete; ascii[buf] is free for the TMA issued two iterations later
 
-        // ---- H: strand-symmetric hash of the m-mer at every position of the tile (+7 past its end).  Padded by one
-        // word per 16 so that the strips below (thread t reads positions 16 t ..) are bank-conflict free.
-        for (int pos = tid; pos < LT_TILE + HOME_SLOTS - 1; pos += LT_THREADS) {
-            const int hc = pos >> 5, ho = pos & 31;
-            unsigned x = 0xFFFFFFFFu;
-            if (!(__funnelshift_r(sm.pb[hc], sm.pb[hc + 1], ho) & mm))
-                x = mmer_hash(__funnelshift_r(sm.p0[hc], sm.p0[hc + 1], ho) & mm, __funnelshift_r(sm.p1[hc], sm.p1[hc + 1], ho) & mm, m);
-            hx[pos + (pos >> 4)] = x;
-        }
-        __syncthreads();
-
-        // ---- A: super-k-mers.  Consecutive valid windows whose minimizer is the same m-mer occurrence (same absolute
-        // position, unique smallest hash in the window) form one run = one entry, whose bin is the partition of the
-        // minimizer hash.  A window whose smallest hash occurs twice travels alone, with the home its own orientation
-        // dictates.  Two steps, so that the per-window part has no data-dependent branches: (1) every window is classified
-        // into three 16-bit masks (first window of a run / lone window / homopolymer) plus its minimizer position, packed
-        // 5 bits per window; (2) one loop over the set bits emits the entries.
+        // ---- A: bins and ranks
         const int c = tid >> 1, sh0 = (tid & 1) * LT_WIN;
         const unsigned a0 = sm.p0[c], a1 = sm.p1[c], ab = sm.pb[c];
         const unsigned c0 = sm.p0[c + 1], c1 = sm.p1[c + 1], cb = sm.pb[c + 1];
-        unsigned m_run = 0, m_lone = 0, m_homo = 0, m_ok = 0;      // bit j = window j of this thread
-        unsigned long long pos_lo = 0, pos_hi = 0;                 // minimizer position (0..22) of windows 0..11 / 12..15
-        {
-            unsigned prev_abs = 0xFFu, run_len = 0;               // the run that window j - 1 belongs to (0xFF = none)
-#pragma unroll
-            for (int half = 0; half < LT_WIN / HOME_SLOTS; half++) {
-                const int b0 = tid * LT_WIN + half * HOME_SLOTS;   // first position of this strip of 8 windows
-                unsigned strip[2 * HOME_SLOTS - 1], vl[HOME_SLOTS], vr[HOME_SLOTS];
-#pragma unroll
-                for (int q = 0; q < 2 * HOME_SLOTS - 1; q++) strip[q] = hx[b0 + q + ((b0 + q) >> 4)];
-                strip_minimizers<HOME_SLOTS>(strip, vl, vr);
-#pragma unroll
-                for (int i = 0; i < HOME_SLOTS; i++) {
-                    const int j = half * HOME_SLOTS + i;
-                    const int s = sh0 + j;
-                    const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
-                    const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
-                    const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-                    const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
-                    const bool ok = bad == 0u && !homo;
-                    const unsigned sl = vl[i] & ORD_POS_MASK, sr = ORD_POS_MASK - (vr[i] & ORD_POS_MASK);
-                    const unsigned abs_l = (unsigned)(half * HOME_SLOTS) + sl;
-                    const bool uniq = ok && sl == sr;
-                    const bool cont = uniq && abs_l == prev_abs && run_len < nmax;
-                    run_len = cont ? run_len + 1u : 1u;
-                    prev_abs = uniq ? abs_l : 0xFFu;
-                    m_run |= (uniq && !cont ? 1u : 0u) << j;
-                    m_lone |= (ok && !uniq ? 1u : 0u) << j;
-                    m_homo |= (bad == 0u && homo ? 1u : 0u) << j;
-                    m_ok |= (uniq ? 1u : 0u) << j;
-                    if (j < 12) pos_lo |= (unsigned long long)abs_l << (5 * j);
-                    else pos_hi |= (unsigned long long)abs_l << (5 * (j - 12));
-                }
-            }
-        }
-        unsigned ne = 0;                                  // entries of this thread
-        {
-            // homopolymer windows (rare): tallied by base code
-            for (unsigned m = m_homo; m; m &= m - 1u) {
-                const int s = sh0 + (__ffs(m) - 1);
-                const unsigned code = (__funnelshift_r(a0, c0, s) & 1u) | ((__funnelshift_r(a1, c1, s) & 1u) << 1);
-                hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
-            }
-            // a run ends where the next one starts, or at the first window that does not continue it
-            const unsigned stops = m_run | ~m_ok;
-            for (unsigned m = m_run | m_lone; m; m &= m - 1u) {
-                const unsigned j = (unsigned)__ffs(m) - 1u;
-                unsigned h, info;
-                if ((m_lone >> j) & 1u) {
-                    const int s = sh0 + (int)j;
-                    const unsigned f0 = __funnelshift_r(a0, c0, s) & mk, f1 = __funnelshift_r(a1, c1, s) & mk;
-                    const bool is_rc = canonical && make_key(rc_plane(f0, k), rc_plane(f1, k)) < make_key(f0, f1);
-                    // the window's eight hashes again: its leftmost / rightmost smallest
-                    unsigned wx[HOME_SLOTS], vl1, vr1, jj;
-                    const int p0w = tid * LT_WIN + (int)j;
-#pragma unroll
-                    for (int q = 0; q < HOME_SLOTS; q++) wx[q] = hx[p0w + q + ((p0w + q) >> 4)];
-                    window_minimizers(wx, vl1, vr1);
-                    const unsigned sp = strip_pick(vl1, vr1, 0, is_rc, jj);
-                    const int pp = p0w + (int)sp;
-                    h = pack_home(hx[pp + (pp >> 4)], jj);
-                    info = j | (1u << 10);
+#pragma unroll 4
+        for (int j = 0; j < LT_WIN; j++) {
+            const int s = sh0 + j;
+            const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
+            const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+            const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+            const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
+            unsigned m = 0xFFFFFFFFu;
+            if (!bad) {
+                if (homo) {
+                    const unsigned code = (f0 & 1u) | ((f1 & 1u) << 1);
+                    hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
                 } else {
-                    const unsigned rest = (stops >> (j + 1u)) | (1u << (LT_WIN - 1u - j));      // a stop at the strip end at the latest
-                    const unsigned n = (unsigned)__ffs(rest);                                    // windows j .. j + n - 1
-                    const unsigned abs_l = (unsigned)((j < 12u ? pos_lo >> (5u * j) : pos_hi >> (5u * (j - 12u))) & 31ull);
-                    const int pp = tid * LT_WIN + (int)abs_l;
-                    h = hx[pp + (pp >> 4)];
-                    info = j | ((n - 1u) << 4) | ((abs_l - j) << 7);
+                    const unsigned bin = hash_part(mix64(window_key(f0, f1, k, canonical)), nbins);
+                    const unsigned shift = (bin & 1u) * 16u;
+                    const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
+                    m = (bin << 12) | ((old >> shift) & 0xFFFFu);
                 }
-                const unsigned bin = home_part(h, nbins);
-                const unsigned shift = (bin & 1u) * 16u;
-                const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
-                sm.eh[ne * LT_THREADS + tid] = h;
-                sm.erank[ne * LT_THREADS + tid] = (unsigned short)((old >> shift) & 0xFFFFu);     // < LT_TILE = 4096
-                sm.einfo[ne * LT_THREADS + tid] = (unsigned short)info;
-                ne++;
             }
+            sm.meta[j * LT_THREADS + tid] = m;
         }
         __syncthreads();
 
@@ -439,41 +363,36 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
                 }
             }
         }
-        __syncthreads();   // (also: every thread is done with the hashes, the sorted tile may overwrite them)
+        __syncthreads();
 
-        // ---- B: the entries, into their sorted places (bases straight from the plane words: two funnel shifts)
-        for (unsigned e = 0; e < ne; e++) {
-            const unsigned h = sm.eh[e * LT_THREADS + tid], info = sm.einfo[e * LT_THREADS + tid];
-            const int s = sh0 + (int)(info & 15u);
-            const unsigned idx = off16[home_part(h, nbins)] + sm.erank[e * LT_THREADS + tid];
-            LogEntry le;
-            le.h = h;
-            if (info & (1u << 10)) {          // a single window with its own home: the (canonical) key itself
-                const unsigned long long key = window_key(__funnelshift_r(a0, c0, s) & mk, __funnelshift_r(a1, c1, s) & mk, k, canonical);
-                le.b0 = key_p0(key); le.b1 = key_p1(key);
-                le.meta = LE_VALID | LE_EXPLICIT | 1u;
-            } else {
-                const unsigned n = ((info >> 4) & 7u) + 1u, q0 = (info >> 7) & 7u;
-                const unsigned lm = kmask(k + (int)n - 1);
-                le.b0 = __funnelshift_r(a0, c0, s) & lm; le.b1 = __funnelshift_r(a1, c1, s) & lm;
-                le.meta = LE_VALID | n | (q0 << 4) | (canonical ? LE_CANONICAL : 0u);
+        // ---- B: keys again, into their sorted places
+#pragma unroll 4
+        for (int j = 0; j < LT_WIN; j++) {
+            const unsigned m = sm.meta[j * LT_THREADS + tid];
+            if (m != 0xFFFFFFFFu) {
+                const int s = sh0 + j;
+                const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
+                const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
+                const unsigned bin = m >> 12;
+                const unsigned idx = off16[bin] + (m & 0xFFFu);
+                skey[idx] = window_key(f0, f1, k, canonical);
+                sbin[idx] = (unsigned short)bin;
             }
-            sent[idx] = le;
         }
         __syncthreads();
 
         // ---- W: stream the sorted tile out
         const unsigned total = sm.total;
         for (unsigned i = tid; i < total; i += LT_THREADS) {
-            const LogEntry e = sent[i];
-            const unsigned bin = home_part(e.h, nbins);
+            const unsigned bin = sbin[i];
             const unsigned pos = delta[bin] + i;
+            const unsigned long long key = skey[i];
             if (pos < lg.cap) {
                 // bin -> (owner, bin inside the owner); the store lands in local HBM or, over NVLink, in the owner's log
                 const unsigned o = bin >> lg.lp_shift, lb = bin - (o << lg.lp_shift);
-                sm.seg[o][(unsigned long long)lb * lg.cap + pos] = e;
-            } else if (t.slots) {      // bin full: count these occurrences directly
-                le_apply(t, e, 1u, claimed);
+                sm.seg[o][(unsigned long long)lb * lg.cap + pos] = key;
+            } else if (t.slots) {      // bin full: count this occurrence directly
+                table_update<false>(t, key, 1u, claimed);
             } else {
                 atomicExch(lg.error, 3);
             }
@@ -500,7 +419,7 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
 
 size_t log_tiles_smem_bytes(unsigned nbins) {
     const unsigned nbins2 = (nbins + 1u) & ~1u;
-    return (size_t)LT_TILE * sizeof(LogEntry) + (size_t)nbins * 4 + (size_t)nbins2 * 2 * 2;
+    return (size_t)LT_TILE * 8 + (size_t)nbins * 4 + (size_t)LT_TILE * 2 + (size_t)nbins2 * 2 * 2;
 }
 
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
@@ -529,7 +448,7 @@ constexpr int RP_CHUNK = RP_THREADS * RP_PER_THREAD;
 #define RP_GROUP 4                                  // entries per thread whose probes are in flight together
 #endif
 #ifndef RP_MIN_CTAS
-#define RP_MIN_CTAS 3
+#define RP_MIN_CTAS 4
 #endif
 static_assert(RP_PER_THREAD % RP_GROUP == 0, "groups tile a thread's entries");
 constexpr int RP_FOLD = RP_CHUNK;                   // slots of the per-chunk fold table; entries that do not find a
@@ -600,45 +519,27 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// one log entry, streamed (read once)
-__device__ __forceinline__ LogEntry ld_entry(const LogEntry* p) {
-    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
-    LogEntry e;
-    e.b0 = v.x; e.b1 = v.y; e.h = v.z; e.meta = v.w;
-    return e;
-}
-
-template <bool FOLD, int MINB>
-__global__ void __launch_bounds__(RP_THREADS, MINB)
-k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
+template <bool FOLD>
+__global__ void __launch_bounds__(RP_THREADS, RP_MIN_CTAS)
+k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned G,
              unsigned long long* chunk_start, unsigned long long* hpoly, TableView t, int prefetch) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned per = replay_per_group(nlocal, G);
     const unsigned nperm = per * G * nsrc;
-    const int k = t.g.k;
-    const unsigned mk = kmask(k);
     unsigned claimed = 0;
     if (hpoly && blockIdx.x == 0 && tid < 4) {
         // homopolymer tallies of phase 1: applied by the view that holds the key's partition, then cleared
         const unsigned long long n = hpoly[4 + tid], key = hpoly[tid];
-        if (n) {
-            const unsigned hj = key_home_packed(key, t.g.k);
-            if (home_part(hj, t.g.nparts) - t.g.part0 < t.g.nlocal) table_add(t, key, hj, (unsigned)n, claimed);
-        }
+        Probe p;
+        if (n && probe_home(t.g, key, p)) table_update<false>(t, key, (unsigned)n, claimed);
         hpoly[4 + tid] = 0ull;
     }
     __shared__ unsigned long long s_w;
-    __shared__ LogEntry s_ent[RP_THREADS / 32][32];             // per warp: the 32 entries being applied,
-    __shared__ unsigned int s_cnt[RP_THREADS / 32][32];         //           their multiplicities (fold),
-    __shared__ unsigned char s_idx[RP_THREADS / 32][256];       //           and (entry << 3 | window) of every k-mer of theirs
     extern __shared__ __align__(16) unsigned char dyn[];
-    // fold table of one chunk, open addressing: (bases, minimizer hash, meta) of an entry -> occurrences.  The bases of an
-    // entry are never all-A (those windows are homopolymers and bypass the log), so 0 marks a free place.
-    unsigned long long* f_key = reinterpret_cast<unsigned long long*>(dyn);
-    unsigned long long* f_hm = f_key + RP_FOLD;                                  // h | meta << 32, written by the claimer
-    unsigned int* f_cnt = reinterpret_cast<unsigned int*>(f_hm + RP_FOLD);
-    if (FOLD) for (int i = tid; i < RP_FOLD; i += RP_THREADS) { f_key[i] = 0ull; f_hm[i] = 0ull; f_cnt[i] = 0u; }
+    unsigned long long* f_key = reinterpret_cast<unsigned long long*>(dyn);      // fold table of one chunk:
+    unsigned int* f_cnt = reinterpret_cast<unsigned int*>(f_key + RP_FOLD);      // key -> occurrences, open addressing
+    if (FOLD) for (int i = tid; i < RP_FOLD; i += RP_THREADS) { f_key[i] = 0ull; f_cnt[i] = 0u; }
     unsigned long long* counters = chunk_start + nperm + 1;
     unsigned last_lp = 0xFFFFFFFFu;
     // a CTA serves its own group first and then helps the following groups finish
@@ -658,7 +559,7 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
             replay_segment(q, nsrc, nlocal, G, lp, src);
             const unsigned seg = src * nlocal + lp;
             const unsigned n = min(cursor[seg], cap);
-            const LogEntry* kbase = keys + (unsigned long long)seg * cap;
+            const unsigned long long* base = keys + (unsigned long long)seg * cap;
             const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
 
             if (prefetch && lp != last_lp) {
@@ -688,97 +589,60 @@ k_log_replay(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
 #pragma unroll
             for (int u = 0; FOLD && u < RP_PER_THREAD; u++) {
                 const unsigned i = i0 + u * RP_THREADS + tid;
-                LogEntry e;
-                e.meta = 0u;
-                if (i < n) e = ld_entry(kbase + i);
-                if (e.meta != 0u) {
-                    const unsigned long long bases = ((unsigned long long)e.b1 << 32) | e.b0;
-                    const unsigned long long hm = ((unsigned long long)e.meta << 32) | e.h;
-                    unsigned h = (unsigned)(mix64(bases ^ hm) >> 40) & (RP_FOLD - 1);
+                const unsigned long long key = i < n ? __ldcs(base + i) : 0ull;
+                if (key != 0ull) {
+                    // bits 40..: every key of a bin shares the top bits of the LOW hash word (they are the partition)
+                    unsigned h = (unsigned)(mix64(key) >> 40) & (RP_FOLD - 1);
                     int tries = 0;
                     for (; tries < RP_FOLD_PROBES; tries++) {
-                        const unsigned long long old = atomicCAS(&f_key[h], 0ull, bases);
-                        if (old == 0ull) {
-                            // the claimer publishes the rest.  A twin racing ahead of that store sees 0, takes it for a
-                            // different entry and moves on: the entry then sits in two places, which only folds less.
-                            *reinterpret_cast<volatile unsigned long long*>(&f_hm[h]) = hm;
-                            atomicAdd(&f_cnt[h], 1u);
-                            break;
-                        }
-                        if (old == bases && *reinterpret_cast<volatile unsigned long long*>(&f_hm[h]) == hm) {
-                            atomicAdd(&f_cnt[h], 1u);
-                            break;
-                        }
+                        const unsigned long long old = atomicCAS(&f_key[h], 0ull, key);
+                        if (old == 0ull || old == key) { atomicAdd(&f_cnt[h], 1u); break; }
                         h = (h + 1) & (RP_FOLD - 1);
                     }
-                    if (tries == RP_FOLD_PROBES) le_apply(t, e, 1u, claimed);          // crowded corner: unfolded
+                    if (tries == RP_FOLD_PROBES) table_update<false>(t, key, 1u, claimed);      // crowded corner: unfolded
                 }
             }
             if (FOLD) __syncthreads();
-            // ---- apply.  A warp takes 32 entries at a time (one per lane, coalesced from the log or from the fold table),
-            // spreads their k-mers -- 1 to 8 each -- over ALL lanes through shared memory, and then every lane settles one k-mer
-            // per round, four rounds in flight: no lane waits for a neighbour's longer run, and the home-slot loads of 128
-            // k-mers of the warp are outstanding together.
-            const int wq = tid >> 5;
-            for (int sub = 0; sub < RP_PER_THREAD; sub++) {
-                LogEntry e;
-                unsigned cnt = 1u;
-                e.meta = 0u;
-                const unsigned slot_i = (unsigned)(wq * (RP_CHUNK / (RP_THREADS / 32)) + sub * 32 + lane);      // entry of the chunk
-                if (FOLD) {
-                    const unsigned long long bases = f_key[slot_i];
-                    if (bases != 0ull) {
-                        const unsigned long long hm = f_hm[slot_i];
-                        e.b0 = (unsigned)bases; e.b1 = (unsigned)(bases >> 32); e.h = (unsigned)hm; e.meta = (unsigned)(hm >> 32);
-                        cnt = f_cnt[slot_i];
-                        f_key[slot_i] = 0ull; f_hm[slot_i] = 0ull; f_cnt[slot_i] = 0u;          // clean for the next chunk
-                    }
-                } else {
-                    const unsigned i = i0 + slot_i;
-                    if (i < n) e = ld_entry(kbase + i);
-                }
-                const unsigned nw = e.meta == 0u ? 0u : (e.meta & LE_EXPLICIT) ? 1u : le_n(e.meta);
-                // exclusive prefix of the window counts -> where this entry's k-mers sit in the warp's list
-                unsigned incl = nw;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const unsigned total = __shfl_sync(FULL, incl, 31), first = incl - nw;
-                s_ent[wq][lane] = e;
-                s_cnt[wq][lane] = cnt;
-                for (unsigned w = 0; w < nw; w++) s_idx[wq][first + w] = (unsigned char)((lane << 3) | w);
-                __syncwarp();
 #pragma unroll 1
-                for (unsigned r0 = 0; r0 < total; r0 += 128) {
-                    unsigned long long key[4], base[4], home[4];
-                    uint4 cur[4];
-                    unsigned kc[4];
+            for (int gg = 0; gg < RP_PER_THREAD; gg += RP_GROUP) {
+                unsigned long long key[RP_GROUP], cur[RP_GROUP], cur1[RP_GROUP];
+                unsigned cnt[RP_GROUP];
+                Probe pr[RP_GROUP];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const unsigned i = r0 + u * 32 + lane;
-                        key[u] = 0ull;
-                        if (i < total) {
-                            const unsigned id = s_idx[wq][i];
-                            const LogEntry& se = s_ent[wq][id >> 3];
-                            unsigned hj;
-                            if (se.meta & LE_EXPLICIT) { key[u] = make_key(se.b0, se.b1); hj = se.h; }
-                            else le_window(se, id & 7u, k, mk, key[u], hj);
-                            kc[u] = s_cnt[wq][id >> 3];
-                            if (home_of(t.g, hj, base[u], home[u])) cur[u] = ld_slot(&t.slots[home[u]]);
-                            else { key[u] = 0ull; atomicExch(t.error, 2); }
-                        }
+                for (int u = 0; u < RP_GROUP; u++) {
+                    if (FOLD) {
+                        const unsigned sidx = (gg + u) * RP_THREADS + tid;
+                        key[u] = f_key[sidx];
+                        cnt[u] = f_cnt[sidx];
+                        if (key[u] != 0ull) { f_key[sidx] = 0ull; f_cnt[sidx] = 0u; }     // clean for the next chunk
+                    } else {
+                        const unsigned i = i0 + (gg + u) * RP_THREADS + tid;
+                        key[u] = i < n ? __ldcs(base + i) : 0ull;
+                        cnt[u] = 1u;
+                    }
+                }
+                // the first TWO slots of the home bucket in one 256-bit load: buckets fill front to back, so most keys
+                // that are not in slot 0 are in slot 1 and need no second (dependent) round trip to L2
+#pragma unroll
+                for (int u = 0; u < RP_GROUP; u++)
+                    if (key[u] != 0ull) {
+                        if (probe_home(t.g, key[u], pr[u])) {
+                            unsigned long long w0, w1;
+                            ld_slot_pair(&t.slots[pr[u].base + pr[u].off], cur[u], w0, cur1[u], w1);
+                        } else { key[u] = 0ull; atomicExch(t.error, 2); }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (key[u] != 0ull) {
-                            Slot* sl = table_upsert_finish(t, key[u], base[u], home[u], cur[u], claimed);
-                            if (sl) atomicAdd(&sl->val, kc[u]);
+                for (int u = 0; u < RP_GROUP; u++)
+                    if (key[u] != 0ull) {
+                        if (cur[u] != key[u] && cur[u] != 0ull) {      // slot 0 holds another key: go on from slot 1
+                            probe_next(t.g, pr[u]);
+                            cur[u] = cur1[u];
                         }
-                    __syncwarp();   // lanes leave the probe loops at different times: reconverge before the next round
-                }
-                __syncwarp();       // the warp's lists are rewritten by the next 32 entries
+                        Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
+                        if (sl) atomicAdd(&sl->val, cnt[u]);
+                    }
+                __syncwarp();   // lanes leave the probe loops at different times: without this the warp stays split
+                                // and every later log load / probe is issued once per lane subset
             }
         }
     }
@@ -800,13 +664,14 @@ static_assert(RP_CHUNK % RF_THREADS == 0, "chunk = whole rounds of the CTA");
 constexpr unsigned RF_MAX_SPLIT = RF_THREADS;       // table partitions per coarse bin: one counter per thread
 
 __global__ void __launch_bounds__(RF_THREADS, 4)
-k_log_refine(const LogEntry* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
+k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap,
              unsigned nsrc, unsigned ncoarse, const unsigned long long* __restrict__ chunk_start,
-             LogEntry* __restrict__ out_keys, unsigned int* __restrict__ out_cursor, unsigned out_cap,
+             unsigned long long* __restrict__ out_keys, unsigned int* __restrict__ out_cursor, unsigned out_cap,
              unsigned nfine, unsigned fine0, unsigned nfine_global, int* error, TableView t) {
     unsigned claimed = 0;
     // a chunk belongs to ONE coarse bin, so only its f = nfine / ncoarse fine bins can occur: all bookkeeping is per f
-    __shared__ LogEntry sent[RP_CHUNK];
+    __shared__ unsigned long long skey[RP_CHUNK];
+    __shared__ unsigned short sbin[RP_CHUNK];
     __shared__ unsigned int cnt[RF_MAX_SPLIT], delta[RF_MAX_SPLIT], off[RF_MAX_SPLIT];
     __shared__ unsigned wtot[RF_THREADS / 32];
     __shared__ unsigned s_total;
@@ -821,25 +686,24 @@ k_log_refine(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
         while (chunk_start[q + 1] <= w) q++;                       // segments in plan order: (coarse bin, source)
         const unsigned lb = q / nsrc, src = q % nsrc, seg = src * ncoarse + lb;
         const unsigned n = min(cursor[seg], cap);
-        const LogEntry* base = keys + (unsigned long long)seg * cap;
+        const unsigned long long* base = keys + (unsigned long long)seg * cap;
         const unsigned i0 = (unsigned)(w - chunk_start[q]) * RP_CHUNK;
         const unsigned first = fine0 + lb * f;                     // global index of this coarse bin's first partition
-        // ---- A: fine bin (inside the coarse bin) and rank of every entry
-        LogEntry ent[RF_PER_THREAD];
+        // ---- A: fine bin (inside the coarse bin) and rank of every key
+        unsigned long long key[RF_PER_THREAD];
         unsigned meta[RF_PER_THREAD];                              // bin << 12 | rank, ~0 = no entry
 #pragma unroll
         for (int j = 0; j < RF_PER_THREAD; j++) {
             const unsigned i = i0 + j * RF_THREADS + tid;
-            ent[j].meta = 0u;
-            if (i < n) ent[j] = ld_entry(base + i);
+            key[j] = i < n ? __ldcs(base + i) : 0ull;
         }
 #pragma unroll
         for (int j = 0; j < RF_PER_THREAD; j++) {
             meta[j] = 0xFFFFFFFFu;
-            if (ent[j].meta != 0u) {
-                const unsigned bin = home_part(ent[j].h, nfine_global) - first;
+            if (key[j] != 0ull) {
+                const unsigned bin = hash_part(mix64(key[j]), nfine_global) - first;
                 if (bin < f) meta[j] = (bin << 12) | atomicAdd(&cnt[bin], 1u);
-                else atomicExch(error, 2);                         // an entry that does not belong to this coarse bin
+                else atomicExch(error, 2);                         // a key that does not belong to this coarse bin
             }
         }
         __syncthreads();
@@ -866,16 +730,16 @@ k_log_refine(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
         for (int j = 0; j < RF_PER_THREAD; j++)
             if (meta[j] != 0xFFFFFFFFu) {
                 const unsigned bin = meta[j] >> 12, idx = off[bin] + (meta[j] & 0xFFFu);
-                sent[idx] = ent[j];
+                skey[idx] = key[j];
+                sbin[idx] = (unsigned short)bin;
             }
         __syncthreads();
         // ---- W: stream the sorted chunk out: runs of hundreds of entries per fine bin
         const unsigned total = s_total;
         for (unsigned i = tid; i < total; i += RF_THREADS) {
-            const LogEntry e = sent[i];
-            const unsigned bin = home_part(e.h, nfine_global) - first, pos = delta[bin] + i;
-            if (pos < out_cap) out_keys[(unsigned long long)(lb * f + bin) * out_cap + pos] = e;
-            else if (t.slots) le_apply(t, e, 1u, claimed);                       // fine bin full (a repeat k-mer): count directly
+            const unsigned bin = sbin[i], pos = delta[bin] + i;
+            if (pos < out_cap) out_keys[(unsigned long long)(lb * f + bin) * out_cap + pos] = skey[i];
+            else if (t.slots) table_update<false>(t, skey[i], 1u, claimed);      // fine bin full (a repeat k-mer): count directly
             else atomicExch(error, 3);
         }
         __syncthreads();
@@ -889,8 +753,8 @@ k_log_refine(const LogEntry* __restrict__ keys, const unsigned int* __restrict__
 size_t log_refine_plan_words(unsigned nsrc, unsigned ncoarse) { return (size_t)nsrc * ncoarse + 2; }
 unsigned log_refine_max_split() { return RF_MAX_SPLIT; }
 
-cudaError_t launch_log_refine(const LogEntry* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
-                              unsigned ncoarse, unsigned long long* d_chunk_start, LogEntry* d_out_keys,
+cudaError_t launch_log_refine(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                              unsigned ncoarse, unsigned long long* d_chunk_start, unsigned long long* d_out_keys,
                               unsigned int* d_out_cursor, unsigned out_cap, unsigned nfine, unsigned fine0,
                               unsigned nfine_global, int* d_error, TableView t, int sm_count, cudaStream_t s) {
     TimedLaunch timed("k_log_refine", s);
@@ -910,7 +774,7 @@ size_t log_replay_plan_words(unsigned nsrc, unsigned nlocal, unsigned G) {
     return (size_t)replay_per_group(nlocal, G) * G * nsrc + 1 + G;
 }
 
-cudaError_t launch_log_replay(const LogEntry* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+cudaError_t launch_log_replay(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
                               unsigned nlocal, unsigned bin0, unsigned nbins_global, unsigned groups,
                               unsigned long long* d_chunk_start, unsigned long long* d_hpoly, TableView t, int prefetch,
                               int sm_count, cudaStream_t s) {
@@ -924,18 +788,18 @@ cudaError_t launch_log_replay(const LogEntry* d_keys, const unsigned int* d_curs
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const bool fold = (prefetch & 2) != 0;             // bit 1 of the flags word: fold duplicates per chunk
-    const bool dense = (prefetch & 4) != 0;            // bit 2: 4 CTAs per SM (64 registers) instead of 3
-    const size_t dyn = fold ? (size_t)RP_FOLD * 20 : 0;
-    using Kern = void (*)(const LogEntry*, const unsigned int*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
-                          unsigned long long*, unsigned long long*, TableView, int);
-    const Kern kern = fold ? (dense ? (Kern)k_log_replay<true, 4> : (Kern)k_log_replay<true, 3>)
-                           : (dense ? (Kern)k_log_replay<false, 4> : (Kern)k_log_replay<false, 3>);
-    int grid = max_resident_ctas((const void*)kern, RP_THREADS, dyn, -1);
+    const size_t dyn = fold ? (size_t)RP_FOLD * 12 : 0;
+    const void* kern = fold ? (const void*)k_log_replay<true> : (const void*)k_log_replay<false>;
+    int grid = max_resident_ctas(kern, RP_THREADS, dyn, -1);
     if (grid <= 0) grid = sm_count;
     grid = grid / (int)groups * (int)groups;           // the same number of CTAs in every group
     if (grid < (int)groups) grid = (int)groups;
-    kern<<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups, d_chunk_start, d_hpoly, t,
-                                       prefetch & 1);
+    if (fold)
+        k_log_replay<true><<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
+                                                       d_chunk_start, d_hpoly, t, prefetch & 1);
+    else
+        k_log_replay<false><<<grid, RP_THREADS, dyn, s>>>(d_keys, d_cursor, cap, nsrc, nlocal, bin0, nbins_global, groups,
+                                                        d_chunk_start, d_hpoly, t, prefetch & 1);
     return cudaGetLastError();
 }
 
@@ -953,12 +817,10 @@ k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ val
         unsigned long long key = make_key(p0, p1);
         const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
         if (IS_MAX) {          // label table: (forward k-mer, bundle index + 1) -> the field of its orientation
-            const bool rc = kr < key;
-            if (rc) key = kr;
-            if (table_label_max(t, key, key_home_packed(key, k), rc, vals[i])) claimed++;
+            if (table_label_max(t, kr < key ? kr : key, kr < key, vals[i])) claimed++;
         } else {
             if (canonical) key = kr < key ? kr : key;
-            table_add(t, key, key_home_packed(key, k), vals[i], claimed);
+            table_update<false>(t, key, vals[i], claimed);
         }
     }
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
@@ -976,52 +838,22 @@ cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, ui
     return cudaGetLastError();
 }
 
-// Only a fraction of the slots pass the filter of a compaction pass, and finding a key's home again costs ~300 instructions
-// (8 m-mer hashes): the survivors of a warp's 32 slots are queued in shared memory and re-inserted 32 at a time, so that
-// the expensive part always runs on full warps.
 __global__ void __launch_bounds__(256)
 k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val, uint32_t max_val) {
-    __shared__ uint4 queue[8][64];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned claimed = 0, nq = 0;
-    auto insert = [&](const uint4 s) {
+    unsigned claimed = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        const unsigned hj = key_home_packed(key, to.g.k);
+        if (key == 0ull) continue;
         if (is_label) {        // both orientations' labels move with the key
-            const unsigned aux = s.w & AUX_LABEL_MASK;
-            if (s.z && table_label_max(to, key, hj, false, s.z)) claimed++;
-            if (aux && table_label_max(to, key, hj, true, aux)) claimed++;
-        } else {
-            table_add(to, key, hj, s.z, claimed);
-        }
-    };
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (from_cap + stride - 1) / stride;
-    for (uint64_t rd = 0; rd < rounds; rd++) {
-        const uint64_t i = rd * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-        uint4 s = make_uint4(0u, 0u, 0u, 0u);
-        if (i < from_cap) s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
-        const bool keep = (s.x | s.y) != 0u && (is_label || (s.z >= min_val && s.z <= max_val));
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) queue[w][nq + __popc(m & lt)] = s;
-        nq += __popc(m);
-        __syncwarp();
-        if (nq >= 32u) {
-            insert(queue[w][lane]);
-            __syncwarp();
-            nq -= 32u;
-            const bool mv = (unsigned)lane < nq;               // the leftovers move to the front
-            uint4 t2 = make_uint4(0u, 0u, 0u, 0u);
-            if (mv) t2 = queue[w][32 + lane];
-            __syncwarp();
-            if (mv) queue[w][lane] = t2;
-            __syncwarp();
+            if (s.z && table_label_max(to, key, false, s.z)) claimed++;
+            if (s.w && table_label_max(to, key, true, s.w)) claimed++;
+        } else if (s.z >= min_val && s.z <= max_val) {
+            table_update<false>(to, key, s.z, claimed);
         }
     }
-    if ((unsigned)lane < nq) insert(queue[w][lane]);
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
-    if (lane == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
 }
 
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,

@@ -2,32 +2,32 @@
 //
 //   k_cov_stats[_long]    compute_kmer_coverage / median / mean / stDev   
 //   k_assign[_long]       ReadsToTranscripts per-read vote                (§8a R5, R7-R9)
+//   k_read_locus          one 32-bit LOCUS signature per read (smallest strand-symmetric m-mer hash of the read)
 //
-// Warp path (reads up to PR_MAXWIN windows): one warp per read; in round i lane l handles window 32 i + l, so that one
-// load instruction of the warp covers 32 CONSECUTIVE windows.  The front end is the same for both kernels:
-//   1. ballot transpose of the read into bit planes (shared memory);
-//   2. H pass: strand-symmetric hash of the m-mer at every position (one position per lane and round);
-//   3. per window: minimum over its 8 m-mer hashes -> minimizer (leftmost and rightmost, tg_minimizer.cuh), canonical key,
-//      home slot = (bucket of the minimizer hash, slot = minimizer position);
-//   4. ONE 16-byte load per window from the home slot.  Windows that share a minimizer read neighbouring slots of one
-//      128-byte bucket, so the 32 loads of a round fall into ~7 buckets instead of 32 random DRAM granules.
-//   5. the few windows whose home slot holds another key with the DISPLACED flag are queued in shared memory and settled
-//      by a key-hashed walk afterwards, one queued window per lane, all walks in flight together -- instead of the whole
-//      warp waiting on a rare lane in every round.
-// Statistics then need the sequential fp32 sum of squares (the reference's evaluation order is observable in the last
-// bits, S9).  A warp keeps the coverage vectors of a BATCH of consecutive reads in its shared-memory arena and runs the
+// Warp path (reads up to PR_MAXWIN windows): one warp per read; in round i lane l handles window 32 i + l.
+//   1. SWAR transpose of the read into bit planes (shared memory), four bases per lane and round;
+//   2. per window: canonical key -> home bucket -> one warp-convergent bucket lookup (tg_device.cuh);
+//   3. statistics straight from the registers that hold the lane's coverage values.
+// Statistics need the sequential fp32 sum of squares (the reference's evaluation order is observable in the last bits,
+// S9).  A warp keeps the coverage vectors of a BATCH of consecutive reads in its shared-memory arena and runs the
 // sequential sums of the whole batch at once, one read per lane: the 76 dependent adds of a 100-bp read are issued once
 // per batch instead of once per read.
 //
-// Long path (CTA per read, planes and buffers in global scratch): the slow lookup (home computed from the key alone).
+// LOCUS ORDER.  Both kernels take an optional permutation `order`: the i-th read processed is read order[i], results go
+// to the read's own index.  The callers pass the reads sorted by k_read_locus.  Reads that overlap the same stretch of a
+// transcript share their smallest m-mer with high probability, so they become neighbours in that order, and an RNA-seq
+// library covers every expressed position tens to thousands of times: the table buckets one read touches are the ones
+// its neighbours touched microseconds earlier, and the lookups are served by L2 (and L1) instead of one random DRAM
+// granule each (measured: profiles/README.md).  The order changes nothing but the timing -- every read is still looked
+// up window by window in the same table.
+//
+// Long path (CTA per read, planes and buffers in global scratch): same per-window code, bitonic sort for the median.
 #include "tg_internal.h"
 
 namespace tg {
 
 namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int PR_HX = PR_MAXWIN + HOME_SLOTS;     // m-mer positions of the longest warp-path read
-constexpr int WQ = 32;                            // queued walks per warp (one ballot can add at most 32)
 }
 
 // =========================================================================================================
@@ -129,37 +129,21 @@ __device__ __forceinline__ void pack_read_planes_warp(const uint8_t* __restrict_
     }
 }
 
-// planes, m-mer hashes and the deferred-walk queue of one warp
+// planes of one warp's current read
 struct WarpFront {
     uint32_t p0[PR_MAXCH], p1[PR_MAXCH], pb[PR_MAXCH];
-    uint32_t hx[PR_HX];
-    unsigned long long qkey[WQ];
-    uint32_t qh[WQ];
-    uint32_t qx[WQ];          // stats: index of the window in the arena; assign: orientation flags
 };
 
-// steps 1-2 of the front end for one read (whole warp)
-__device__ __forceinline__ void front_planes_hashes(WarpFront& f, const uint8_t* __restrict__ seq, int L, int m, unsigned mm,
-                                                    int lane) {
-    const int nch = (L + 31) >> 5;
-    pack_read_planes_warp(seq, L, nch, f.p0, f.p1, f.pb, lane);
-    __syncwarp();
-    const int nmm = L - m + 1;
-    for (int q = lane; q < nmm; q += 32) {
-        const int c = q >> 5, o = q & 31;
-        unsigned x = 0xFFFFFFFFu;
-        if (!(__funnelshift_r(f.pb[c], f.pb[c + 1], o) & mm))
-            x = mmer_hash(__funnelshift_r(f.p0[c], f.p0[c + 1], o) & mm, __funnelshift_r(f.p1[c], f.p1[c + 1], o) & mm, m);
-        f.hx[q] = x;
-    }
+__device__ __forceinline__ void front_planes(WarpFront& f, const uint8_t* __restrict__ seq, int L, int lane) {
+    pack_read_planes_warp(seq, L, (L + 31) >> 5, f.p0, f.p1, f.pb, lane);
     __syncwarp();
 }
 
-// one window: planes -> canonical key (or the forward one), orientation, packed home
-struct Window { unsigned long long key; unsigned hj, f0, f1; bool valid, is_rc, pal; };
+// one window: planes -> canonical key (or the forward one) and orientation
+struct Window { unsigned long long key; unsigned f0, f1; bool valid, is_rc, pal; };
 __device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nwin, int k, unsigned mk, bool canonical) {
     Window w;
-    w.valid = false; w.is_rc = false; w.pal = false; w.key = 0ull; w.hj = 0u; w.f0 = 0u; w.f1 = 0u;
+    w.valid = false; w.is_rc = false; w.pal = false; w.key = 0ull; w.f0 = 0u; w.f1 = 0u;
     if (p < nwin) {
         const int c = p >> 5, o = p & 31;
         if (!(__funnelshift_r(f.pb[c], f.pb[c + 1], o) & mk)) {
@@ -169,12 +153,6 @@ __device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nw
             w.is_rc = canonical && kr < kf;
             w.pal = kr == kf;
             w.key = w.is_rc ? kr : kf;
-            unsigned hx[HOME_SLOTS], vl, vr, j;
-#pragma unroll
-            for (int q = 0; q < HOME_SLOTS; q++) hx[q] = f.hx[p + q];
-            window_minimizers(hx, vl, vr);
-            const unsigned sp = strip_pick(vl, vr, 0, w.is_rc, j);
-            w.hj = pack_home(f.hx[p + (int)sp], j);
             w.valid = true;
         }
     }
@@ -191,22 +169,9 @@ constexpr int ST_RPW = 16;            // consecutive reads handled by one warp
 struct StatsWarp {
     WarpFront f;
     uint32_t cov[ST_ARENA];
-    uint32_t b_off[ST_BATCH], b_n[ST_BATCH], b_rr[ST_BATCH];
+    uint32_t b_off[ST_BATCH], b_n[ST_BATCH], b_r[ST_BATCH];
     float b_avg[ST_BATCH];
 };
-
-__device__ __forceinline__ void stats_drain(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, unsigned nq, int lane) {
-    __syncwarp();
-    for (unsigned e = lane; e < nq; e += 32) {
-        const unsigned long long key = sw.f.qkey[e];
-        const unsigned h = sw.f.qh[e];
-        const unsigned long long base = (unsigned long long)(home_part(h, geo.nparts) - geo.part0) * geo.subcap;
-        unsigned v = table_walk_find(slots, geo, base, key).x;
-        if (v < 1) v = 1;
-        sw.cov[sw.f.qx[e]] = v;
-    }
-    __syncwarp();
-}
 
 // Median of the n values a warp holds in registers (lane l owns x[i] = value 32 i + l; elements past n hold 0xFFFFFFFF,
 // which no pivot below the maximum reaches -- if every value IS 0xFFFFFFFF the answer is that value either way), WITHOUT
@@ -240,45 +205,22 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
     return (uint32_t)(x1 + x2) / 2u;
 }
 
-// steps 3-5 for one read + sum, mean, median; the coverage vector is left in sw.cov[used .. used + nwin)
+// lookups of one read + sum, mean, median; the coverage vector is left in sw.cov[used .. used + nwin)
 template <int PER>
 __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, int nwin, int k,
                                            unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean) {
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned nq = 0;                               // queued walks (warp-uniform)
-#pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const int p = 32 * i + lane;
-        const Window w = front_window(sw.f, p, nwin, k, mk, canonical);
-        unsigned v = 0;
-        bool need = false;
-        if (w.valid) {
-            const HomeProbe pr = table_home_find(slots, geo, w.key, w.hj);
-            v = pr.v.x;
-            need = pr.walk;
-        }
-        if (v < 1) v = 1;                          // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
-        if (p < nwin) sw.cov[used + p] = v;
-        const unsigned mq = __ballot_sync(FULL, need);
-        if (mq) {
-            if (nq + __popc(mq) > WQ) { stats_drain(sw, slots, geo, nq, lane); nq = 0; }
-            if (need) {
-                const unsigned e = nq + __popc(mq & lt);
-                sw.f.qkey[e] = w.key; sw.f.qh[e] = w.hj; sw.f.qx[e] = used + p;
-            }
-            nq += __popc(mq);
-        }
-    }
-    if (nq) stats_drain(sw, slots, geo, nq, lane); else __syncwarp();
-    // the lane's values back in registers (the walks may have changed them)
     unsigned x[PER];
     unsigned mn = 0xFFFFFFFFu, mx = 0u;
     unsigned long long part = 0;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-        const bool live = 32 * i + lane < nwin;
-        x[i] = live ? sw.cov[used + 32 * i + lane] : 0xFFFFFFFFu;
-        if (live) { mn = min(mn, x[i]); mx = max(mx, x[i]); part += x[i]; }
+        const int p = 32 * i + lane;
+        const Window w = front_window(sw.f, p, nwin, k, mk, canonical);
+        unsigned v = table_lookup(slots, geo, w.key, w.valid);          // warp-convergent: every lane calls it
+        if (v < 1) v = 1;                          // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
+        const bool live = p < nwin;
+        x[i] = live ? v : 0xFFFFFFFFu;
+        if (live) { sw.cov[used + p] = v; mn = min(mn, v); mx = max(mx, v); part += v; }
     }
     const unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
     unsigned long long sum;
@@ -294,7 +236,7 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
 
 // sequential fp32 sums of squares of a batch, one read per lane (fastaToKmerCoverageStats.cpp:389-402): strict read order,
 // two roundings per term, no FMA (x86-64 -O2 without -march)
-__device__ __forceinline__ void stats_flush(StatsWarp& sw, unsigned nb, uint64_t r0, float* __restrict__ stdev, int lane) {
+__device__ __forceinline__ void stats_flush(StatsWarp& sw, unsigned nb, float* __restrict__ stdev, int lane) {
     __syncwarp();
     if ((unsigned)lane < nb) {
         const unsigned n = sw.b_n[lane];
@@ -320,7 +262,7 @@ __device__ __forceinline__ void stats_flush(StatsWarp& sw, unsigned nb, uint64_t
             }
             sd = __fsqrt_rn(__fdiv_rn(acc, __int2float_rn((int)n - 1)));
         }
-        stdev[r0 + sw.b_rr[lane]] = sd;
+        stdev[sw.b_r[lane]] = sd;
     }
     __syncwarp();
 }
@@ -328,21 +270,25 @@ __device__ __forceinline__ void stats_flush(StatsWarp& sw, unsigned nb, uint64_t
 __global__ void __launch_bounds__(PR_WARPS * 32, 4)
 k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
             int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
-            float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll) {
+            float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll,
+            const uint32_t* __restrict__ order) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     StatsWarp& sw = reinterpret_cast<StatsWarp*>(dyn)[w];
-    const uint64_t r0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * ST_RPW;
-    if (r0 >= nreads) return;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * ST_RPW;      // position in processing order
+    if (i0 >= nreads) return;
     const unsigned mk = kmask(k);
-    const int m = mm_len(k);
-    const unsigned mm = kmask(m);
-    // offsets of the warp's reads: one load per lane, handed round by shuffles
-    const uint64_t my_off = offs[min(r0 + (uint64_t)lane, nreads)];
+    // the warp's reads: lane rr holds the index and the two offsets of the rr-th one, handed round by shuffles
+    static_assert(ST_RPW <= 32, "one read per lane");
+    uint64_t my_r = 0, my_o0 = 0, my_o1 = 0;
+    if (lane < ST_RPW && i0 + lane < nreads) {
+        my_r = order ? (uint64_t)order[i0 + lane] : i0 + lane;
+        my_o0 = offs[my_r]; my_o1 = offs[my_r + 1];
+    }
     unsigned nb = 0, used = 0;
-    for (int rr = 0; rr < ST_RPW && r0 + rr < nreads; rr++) {
-        const uint64_t o0 = __shfl_sync(FULL, my_off, rr), o1 = __shfl_sync(FULL, my_off, rr + 1);
-        const uint64_t r = r0 + rr;
+    for (int rr = 0; rr < ST_RPW && i0 + rr < nreads; rr++) {
+        const uint64_t r = __shfl_sync(FULL, my_r, rr);
+        const uint64_t o0 = __shfl_sync(FULL, my_o0, rr), o1 = __shfl_sync(FULL, my_o1, rr);
         const int L = (int)(o1 - o0 - 1);            // the record's last byte is its '\n' terminator
         const int nwin = L >= k ? L - k + 1 : 0;
         if (nwin > PR_MAXWIN) {
@@ -357,9 +303,9 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
             if (lane == 0) { median[r] = 0u; mean[r] = 0.0f; stdev[r] = __int_as_float(0x80000000); }
             continue;
         }
-        if (nb == ST_BATCH || used + nwin > ST_ARENA) { stats_flush(sw, nb, r0, stdev, lane); nb = 0; used = 0; }
+        if (nb == ST_BATCH || used + nwin > ST_ARENA) { stats_flush(sw, nb, stdev, lane); nb = 0; used = 0; }
         const uint8_t* seq = recs + (o0 - rec_base);
-        front_planes_hashes(sw.f, seq, L, m, mm, lane);
+        front_planes(sw.f, seq, L, lane);
         uint32_t med; float mu;
         switch ((nwin + 31) >> 5) {
             case 1: stats_read<1>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
@@ -372,32 +318,32 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
             default: stats_read<8>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
         }
         if (per_kmer) {
+            __syncwarp();
             uint32_t* out = per_kmer + (o0 - rec_base);
             for (int p = lane; p < nwin; p += 32) out[p] = sw.cov[used + p];
         }
         if (lane == 0) {
             median[r] = med; mean[r] = mu;
-            sw.b_off[nb] = used; sw.b_n[nb] = (unsigned)nwin; sw.b_rr[nb] = (unsigned)rr; sw.b_avg[nb] = mu;
+            sw.b_off[nb] = used; sw.b_n[nb] = (unsigned)nwin; sw.b_r[nb] = (unsigned)r; sw.b_avg[nb] = mu;
         }
         nb++;
         used += (unsigned)nwin;
     }
-    stats_flush(sw, nb, r0, stdev, lane);
+    stats_flush(sw, nb, stdev, lane);
 }
 
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, cudaStream_t s) {
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, cudaStream_t s) {
     TimedLaunch timed("k_cov_stats", s);
     if (nreads == 0) return cudaSuccess;
-    if (k < MIN_FAST_K) return cudaErrorInvalidValue;      // callers route shorter k-mers through the long kernel
     const size_t dyn = sizeof(StatsWarp) * PR_WARPS;
     cudaError_t e = cudaFuncSetAttribute((const void*)k_cov_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     const uint64_t per_cta = (uint64_t)PR_WARPS * ST_RPW;
     const uint64_t blocks = (nreads + per_cta - 1) / per_cta;
     k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
-                                                             d_median, d_mean, d_stdev, d_per_kmer, ll);
+                                                             d_median, d_mean, d_stdev, d_per_kmer, ll, d_order);
     return cudaGetLastError();
 }
 
@@ -421,24 +367,32 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
     gsync<GS>();
 
     unsigned long long part = 0;
-    for (int p = gtid; p < nwin; p += GS) {
-        const int c = p >> 5, o = p & 31;
-        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
-        unsigned v = 0;
-        if (!bad) {
-            const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-            const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-            unsigned long long key = make_key(f0, f1);
-            if (canonical) {
-                const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
-                key = kr < key ? kr : key;
+    for (int pb = 0; pb < nwin; pb += GS) {     // every lane runs every iteration: table_lookup is warp-convergent
+        const int p = pb + gtid;
+        const bool live = p < nwin;
+        bool ok = false;
+        unsigned long long key = 0ull;
+        if (live) {
+            const int c = p >> 5, o = p & 31;
+            const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+            if (!bad) {
+                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+                key = make_key(f0, f1);
+                if (canonical) {
+                    const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                    key = kr < key ? kr : key;
+                }
+                ok = true;
             }
-            v = table_find_key(slots, geo, key).x;
         }
-        if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
-        cov[p] = v;
-        if (per_kmer) per_kmer[p] = v;
-        part += v;
+        unsigned v = table_lookup(slots, geo, key, ok);
+        if (live) {
+            if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
+            cov[p] = v;
+            if (per_kmer) per_kmer[p] = v;
+            part += v;
+        }
     }
     const unsigned long long sum = group_sum_u64<GS>(part, red, gtid);   // `long` sum, exact
     const float avg = __fdiv_rn(__ll2float_rn((long long)sum), __ull2float_rn((unsigned long long)nwin));
@@ -629,61 +583,28 @@ __device__ __forceinline__ void push_hits(int32_t* hits, unsigned& nh, unsigned 
     nh += __popc(mr);
 }
 
-__device__ __forceinline__ void assign_drain(AssignWarp& aw, const Slot* __restrict__ slots, const Geo& geo, unsigned nq,
-                                             unsigned& nh, int lane) {
-    __syncwarp();
-    for (unsigned e0 = 0; e0 < nq; e0 += 32) {        // nq <= WQ = 32: one round
-        const unsigned e = e0 + lane;
-        unsigned vf = 0, vr = 0;
-        if (e < nq) {
-            const unsigned long long key = aw.f.qkey[e];
-            const unsigned h = aw.f.qh[e], fl = aw.f.qx[e];
-            const unsigned long long base = (unsigned long long)(home_part(h, geo.nparts) - geo.part0) * geo.subcap;
-            const uint2 v = table_walk_find(slots, geo, base, key);
-            labels_of(v, fl & 1u, fl & 2u, fl & 4u, fl & 8u, vf, vr);
-        }
-        push_hits(aw.hits, nh, vf, vr, lane);
-    }
-    __syncwarp();
-}
-
 template <int PER>
 __device__ __forceinline__ void assign_read(AssignWarp& aw, const Slot* __restrict__ slots, const Geo& geo,
                                             const uint8_t* __restrict__ lut, int nwin, int k, unsigned mk, int strand, int lane,
                                             unsigned& nh_out) {
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned nq = 0, nh = 0;
+    unsigned nh = 0;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         const int p = 32 * i + lane;
         // label tables are keyed canonically whatever the library type: the strand flag only drops the second lookup
         const Window w = front_window(aw.f, p, nwin, k, mk, true);
-        bool do_f = false, do_r = false, need = false;
-        uint2 v = make_uint2(0u, 0u);
+        bool do_f = false, do_r = false;
         if (w.valid) {                     // a window with a non-ACGT character can never equal a table k-mer
             do_f = window_entropy_ok(lut, w.f0, w.f1, mk, false);
             do_r = !strand && window_entropy_ok(lut, w.f0, w.f1, mk, true);
-            if (do_f || do_r) {
-                const HomeProbe pr = table_home_find(slots, geo, w.key, w.hj);
-                v = pr.v;
-                need = pr.walk;
-            }
         }
+        // ONE probe answers both passes of the reference (forward window, then reverse-complemented window)
+        const uint2 v = table_lookup2(slots, geo, w.key, do_f || do_r);       // warp-convergent
         unsigned vf, vr2;
         labels_of(v, do_f, do_r, w.is_rc, w.pal, vf, vr2);
         push_hits(aw.hits, nh, vf, vr2, lane);
-        const unsigned mq = __ballot_sync(FULL, need);
-        if (mq) {
-            if (nq + __popc(mq) > WQ) { assign_drain(aw, slots, geo, nq, nh, lane); nq = 0; }
-            if (need) {
-                const unsigned e = nq + __popc(mq & lt);
-                aw.f.qkey[e] = w.key; aw.f.qh[e] = w.hj;
-                aw.f.qx[e] = (do_f ? 1u : 0u) | (do_r ? 2u : 0u) | (w.is_rc ? 4u : 0u) | (w.pal ? 8u : 0u);
-            }
-            nq += __popc(mq);
-        }
     }
-    if (nq) assign_drain(aw, slots, geo, nq, nh, lane); else __syncwarp();
+    __syncwarp();
     nh_out = nh;
 }
 
@@ -696,12 +617,14 @@ __device__ __forceinline__ int assign_pct(int score, int nwin) {
 __global__ void __launch_bounds__(PR_WARPS * 32, 4)
 k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int k,
          int strand, const Slot* __restrict__ slots, Geo geo, const uint8_t* __restrict__ lut,
-         int32_t* __restrict__ best, int32_t* __restrict__ pct, int32_t* __restrict__ score, LongList ll) {
+         int32_t* __restrict__ best, int32_t* __restrict__ pct, int32_t* __restrict__ score, LongList ll,
+         const uint32_t* __restrict__ order) {
     __shared__ AssignWarp smw[PR_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     AssignWarp& aw = smw[w];
-    const uint64_t r = (uint64_t)blockIdx.x * PR_WARPS + w;
-    if (r >= nreads) return;
+    const uint64_t i = (uint64_t)blockIdx.x * PR_WARPS + w;
+    if (i >= nreads) return;
+    const uint64_t r = order ? (uint64_t)order[i] : i;
     const uint64_t o0 = offs[r], o1 = offs[r + 1];
     const int L = (int)(o1 - o0 - 1);
     const int nwin = L - k + 1;        // num_kmer_pos, may be <= 0
@@ -716,8 +639,7 @@ k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, ui
     int b = -1, sc = 0, pc = 0;
     if (nwin > 0) {
         const unsigned mk = kmask(k);
-        const int m = mm_len(k);
-        front_planes_hashes(aw.f, recs + (o0 - rec_base), L, m, kmask(m), lane);
+        front_planes(aw.f, recs + (o0 - rec_base), L, lane);
         unsigned nh = 0;
         switch ((nwin + 31) >> 5) {
             case 1: assign_read<1>(aw, slots, geo, lut, nwin, k, mk, strand, lane, nh); break;
@@ -737,13 +659,12 @@ k_assign(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, ui
 
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                           int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok, int32_t* d_best,
-                          int32_t* d_pct, int32_t* d_score, LongList ll, cudaStream_t s) {
+                          int32_t* d_pct, int32_t* d_score, LongList ll, const uint32_t* d_order, cudaStream_t s) {
     TimedLaunch timed("k_assign", s);
     if (nreads == 0) return cudaSuccess;
-    if (k < MIN_FAST_K) return cudaErrorInvalidValue;
     const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
     k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, geo,
-                                                        d_entropy_ok, d_best, d_pct, d_score, ll);
+                                                        d_entropy_ok, d_best, d_pct, d_score, ll, d_order);
     return cudaGetLastError();
 }
 
@@ -764,18 +685,24 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
     if (gtid == 0) *nhits_p = 0;
     pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
     gsync<GS>();
-    for (int p = gtid; p < nwin; p += GS) {
-        const int c = p >> 5, o = p & 31;
-        const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
-        if (bad) continue;                 // a window with a non-ACGT character can never equal a table k-mer
-        const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
-        const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-        const bool do_f = window_entropy_ok(lut, f0, f1, mk, false);
-        const bool do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
-        if (!do_f && !do_r) continue;
-        const unsigned long long kf = make_key(f0, f1), kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
-        const bool is_rc = kr < kf, pal = kr == kf;
-        const uint2 v = table_find_key(slots, geo, is_rc ? kr : kf);
+    for (int pb = 0; pb < nwin; pb += GS) {         // every lane runs every iteration: table_lookup2 is warp-convergent
+        const int p = pb + gtid;
+        bool do_f = false, do_r = false, is_rc = false, pal = false;
+        unsigned long long key = 0ull;
+        if (p < nwin) {
+            const int c = p >> 5, o = p & 31;
+            const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
+            if (!bad) {                    // a window with a non-ACGT character can never equal a table k-mer
+                const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
+                const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
+                do_f = window_entropy_ok(lut, f0, f1, mk, false);
+                do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
+                const unsigned long long kf = make_key(f0, f1), kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                is_rc = kr < kf; pal = kr == kf;
+                key = is_rc ? kr : kf;
+            }
+        }
+        const uint2 v = table_lookup2(slots, geo, key, do_f || do_r);
         unsigned vf, vr;
         labels_of(v, do_f, do_r, is_rc, pal, vf, vr);
         if (vf) hits[atomicAdd(nhits_p, 1u)] = (int32_t)vf - 1;
@@ -867,6 +794,68 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
     k_assign_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, strand, slots, geo, d_entropy_ok, d_best,
                                                  d_pct, d_score, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
                                                  scratch_bytes / 4, d_error);
+    return cudaGetLastError();
+}
+
+
+// =========================================================================================================
+// locus signature: the smallest strand-symmetric m-mer hash of a read (see LOCUS ORDER at the top of the file)
+// =========================================================================================================
+// m = min(k, 20): long enough to be unique to its place in a transcriptome, short enough that two reads overlapping by a
+// third of their length usually share it.  A read and its reverse complement get the same signature (both strands of an
+// m-mer hash alike), so the two mates' orientations and unstranded libraries cluster together.
+constexpr int LOCUS_RPW = 8;          // consecutive reads per warp
+
+__device__ __forceinline__ unsigned locus_hash(unsigned f0, unsigned f1, int m) {
+    const unsigned r0 = __brev(~f0) >> (32 - m), r1 = __brev(~f1) >> (32 - m);
+    const unsigned a = f0 * 0x9E3779B1u + f1 * 0x85EBCA77u, b = r0 * 0x9E3779B1u + r1 * 0x85EBCA77u;
+    unsigned x = a < b ? a : b;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 13;
+    return x;
+}
+
+__global__ void __launch_bounds__(PR_WARPS * 32)
+k_read_locus(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int m,
+             uint32_t* __restrict__ sig, uint32_t* __restrict__ idx) {
+    __shared__ WarpFront fw[PR_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpFront& f = fw[w];
+    const uint64_t r0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * LOCUS_RPW;
+    if (r0 >= nreads) return;
+    const unsigned mm = kmask(m);
+    const uint64_t my_off = offs[min(r0 + (uint64_t)lane, nreads)];
+    unsigned mine = 0xFFFFFFFFu;                      // lane rr keeps the signature of the rr-th read
+    for (int rr = 0; rr < LOCUS_RPW && r0 + rr < nreads; rr++) {
+        const uint64_t o0 = __shfl_sync(FULL, my_off, rr), o1 = __shfl_sync(FULL, my_off, rr + 1);
+        int L = (int)(o1 - o0 - 1);
+        if (L > PR_MAXWIN) L = PR_MAXWIN;             // a long read is placed by its first 256 bases
+        unsigned best = 0xFFFFFFFFu;
+        if (L >= m) {
+            front_planes(f, recs + (o0 - rec_base), L, lane);
+            for (int q = lane; q <= L - m; q += 32) {
+                const int c = q >> 5, o = q & 31;
+                if (!(__funnelshift_r(f.pb[c], f.pb[c + 1], o) & mm))
+                    best = min(best, locus_hash(__funnelshift_r(f.p0[c], f.p0[c + 1], o) & mm,
+                                                __funnelshift_r(f.p1[c], f.p1[c + 1], o) & mm, m));
+            }
+            __syncwarp();
+        }
+        best = __reduce_min_sync(FULL, best);
+        if (lane == rr) mine = best;
+    }
+    if (lane < LOCUS_RPW && r0 + lane < nreads) { sig[r0 + lane] = mine; idx[r0 + lane] = (uint32_t)(r0 + lane); }
+}
+
+cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                              uint32_t* d_sig, uint32_t* d_idx, cudaStream_t s) {
+    TimedLaunch timed("k_read_locus", s);
+    if (nreads == 0) return cudaSuccess;
+    const int m = k < 20 ? k : 20;
+    const uint64_t per_cta = (uint64_t)PR_WARPS * LOCUS_RPW;
+    k_read_locus<<<(unsigned)((nreads + per_cta - 1) / per_cta), PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, m,
+                                                                                       d_sig, d_idx);
     return cudaGetLastError();
 }
 

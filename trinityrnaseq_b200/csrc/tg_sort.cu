@@ -32,3 +32,31 @@ cudaError_t sort_pairs(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, int k, cu
 }
 
 }  // namespace tg
+
+namespace tg {
+
+// Locus order (tg_perread.cu): ascending sort of (32-bit read signature, read index).  `work` holds, in this order,
+// sig[n] | idx[n] | sig_alt[n] | idx_alt[n] | CUB temporary storage; the caller has filled sig and idx.  Returns the
+// device pointer of the sorted index array (one of the two idx buffers) in *d_sorted.
+size_t locus_sort_bytes(uint64_t n) {
+    size_t tmp = 0;
+    cub::DoubleBuffer<uint32_t> kb(nullptr, nullptr), vb(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)n, 0, 32, (cudaStream_t)0);
+    return (size_t)n * 16 + ((tmp + 255) & ~(size_t)255) + 256;
+}
+
+cudaError_t locus_sort(void* work, size_t work_bytes, uint64_t n, const uint32_t** d_sorted, cudaStream_t s) {
+    if (n > 0x7FFFFFF0ull) return cudaErrorInvalidValue;
+    uint32_t* sig = (uint32_t*)work;
+    uint32_t* idx = sig + n;
+    uint32_t* sig_alt = idx + n;
+    uint32_t* idx_alt = sig_alt + n;
+    void* tmp = (void*)(((uintptr_t)(idx_alt + n) + 255) & ~(uintptr_t)255);
+    size_t tmp_bytes = work_bytes - (size_t)((char*)tmp - (char*)work);
+    cub::DoubleBuffer<uint32_t> kb(sig, sig_alt), vb(idx, idx_alt);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, (int)n, 0, 32, s);
+    *d_sorted = vb.Current();
+    return e;
+}
+
+}  // namespace tg

@@ -80,13 +80,13 @@ def exchange_bins(world, lp, max_bins=MAX_EXCHANGE_BINS):
     return c
 
 
-ENTRIES_PER_WINDOW = 0.5      # a log entry is a run of up to 8 windows sharing a minimizer (typically ~3.5 windows per entry)
+ENTRIES_PER_WINDOW = 1.0      # a log entry is one k-mer occurrence
 
 
 def log_capacity(nbytes, nbins, slack=1.2):
-    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window, an entry holds ~3.5
-    windows: laid out for one entry per two windows); the additive term covers the hash fluctuation of small batches, the
-    factor covers hot minimizers.  A bin that overflows all the same makes the caller double the head-room and repeat."""
+    """entries per log bin for a batch of nbytes record bytes (every byte starts at most one window = one entry); the
+    additive term covers the hash fluctuation of small batches, the factor covers hot k-mers.  A bin that overflows all
+    the same makes the caller double the head-room and repeat."""
     cap = int(nbytes * ENTRIES_PER_WINDOW / nbins * slack) + 1024
     return (cap + 15) // 16 * 16
 
@@ -106,8 +106,10 @@ class DeviceEngine:
         self.table = KmerCounter.sharded(self.ctx, self.k, self.canonical, subcap, nparts, part0, nlocal)
         return self.table
 
-    # a log entry is 16 bytes on the device (key + packed home of the k-mer): two int64 words
-    ENTRY_WORDS = 2
+    @property
+    def ENTRY_WORDS(self):
+        """int64 words of one log entry on the device (tg_log_entry_bytes: the 8-byte table key)"""
+        return max(1, int(_lib.lib().tg_log_entry_bytes()) // 8)
 
     def new_log(self, nbins, cap):
         t = self.torch
