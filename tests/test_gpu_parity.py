@@ -296,3 +296,60 @@ def test_held_records_one_upload_same_results(gpu_ctx, oracle, data):
             np.testing.assert_array_equal(hp, p2)
             np.testing.assert_array_equal(hs, s2)
     gpu_ctx.records_release()
+
+
+@pytest.mark.parametrize("batch_bytes", [64 << 20, 96 << 10])
+def test_locus_order_changes_nothing_but_the_order(oracle, data, batch_bytes):
+    """The per-read kernels visit the reads in LOCUS order (sorted by the smallest m-mer hash of the read) once a launch is
+    large enough; here the threshold is 0, so every launch is reordered: statistics, per-window coverage and assignments
+    must come back read by read exactly as the oracle computes them -- empty, short, all-N, long (CTA-per-read path) and
+    lower-case reads included, in one launch and split over many small batches, through the host-buffer, the held-buffer
+    and the device-resident entry points."""
+    txs, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    with tg.Context(0) as ctx:
+        ctx.set("locus_min_reads", 0)
+        ctx.set("batch_bytes", batch_bytes)
+        ctx.set("kernel_timing", 1)
+        ok, oc = oracle.jf_count(recs, 25, True, 1)
+        okc = oracle.KmerCounter(25, True)
+        for kmer, c in zip(ok, oc):
+            okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
+        om, omean, osd, oper = okc.coverage_stats(recs, offs, capture=True)
+        names, bundles = synth.bundles_from(np.random.default_rng(5), txs)
+        brecs, boffs = tg.records_from_sequences(bundles)
+        ot = oracle.BundleTable(25)
+        ot.label(brecs, boffs)
+        ob, op, os_ = ot.assign(recs, offs, strand=False)
+        with tg.KmerCounter(ctx, 25, is_ds=True, expected_keys=len(ok)) as kc, tg.BundleKmerTable(ctx, 25) as bt:
+            kc.add_records(recs)
+            bt.label_bundles(brecs, boffs)
+            ctx.kernel_times()
+            gm, gmean, gsd, gper = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+            assert "k_locus_tiles" in ctx.kernel_times()
+            np.testing.assert_array_equal(gper, oper)
+            np.testing.assert_array_equal(gm, om)
+            np.testing.assert_array_equal(_f32_bits(gmean), _f32_bits(omean))
+            np.testing.assert_array_equal(_f32_bits(gsd), _f32_bits(osd))
+            gb, gp, gs = bt.assign_reads(recs, offs, strand=False)
+            np.testing.assert_array_equal(gb, ob)
+            np.testing.assert_array_equal(gs, os_)
+            np.testing.assert_array_equal(gp[ob >= 0], op[ob >= 0])
+            # held buffer: one device copy, one launch over all reads
+            pinned, owner = ctx.pinned((recs.nbytes,), np.uint8)
+            pinned[:] = recs
+            ctx.records_hold(pinned)
+            hm, hmean, hsd = kc.coverage_stats(pinned, offs)
+            hb, hp, hs = bt.assign_reads(pinned, offs, strand=False)
+            ctx.records_release()
+            np.testing.assert_array_equal(hm, om)
+            np.testing.assert_array_equal(_f32_bits(hsd), _f32_bits(osd))
+            np.testing.assert_array_equal(hb, ob)
+            np.testing.assert_array_equal(hs, os_)
+            # the knob off: same answers
+            ctx.set("locus_order", 0)
+            ctx.kernel_times()
+            nm, nmean, nsd = kc.coverage_stats(recs, offs)
+            assert "k_locus_tiles" not in ctx.kernel_times()
+            np.testing.assert_array_equal(nm, om)
+            np.testing.assert_array_equal(_f32_bits(nsd), _f32_bits(osd))

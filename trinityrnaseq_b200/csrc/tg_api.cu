@@ -389,6 +389,7 @@ void tg_free(void* p) { free(p); }
 static int table_new(tg_ctx* c, int kind, int k, Geo g, tg_table** out) {
     tg_table* t = new tg_table();
     g.k = k; g.filter = kind == TG_TABLE_COUNT ? 1u : 0u;
+    if (g.subcap >= (1ull << 34)) return fail(TG_ERR_ARG, "a table partition holds at most 2^34 slots (bucket index is 32-bit)");
     t->ctx = c; t->kind = kind; t->k = k; t->g = g;
     t->cap = (uint64_t)g.nlocal * g.subcap;
     int rc = table_alloc(c, t->cap, &t->slots);
@@ -1306,7 +1307,7 @@ static int locus_order_async(tg_ctx* c, int b, const uint8_t* d_recs, const uint
     const size_t need = locus_sort_bytes(nreads);
     CU(c->locus[b].ensure(need));
     uint32_t* sig = (uint32_t*)c->locus[b].p;
-    CU(launch_read_locus(d_recs, d_offs, rec_base, nreads, k, sig, sig + nreads, c->stream[b]));
+    CU(launch_read_locus(d_recs, d_offs, rec_base, nreads, k, sig, sig + nreads, c->sm_count, c->stream[b]));
     CU(locus_sort(c->locus[b].p, need, nreads, d_order, c->stream[b]));
     c->launches += 2;
     return TG_OK;

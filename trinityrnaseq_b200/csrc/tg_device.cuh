@@ -100,20 +100,31 @@ __host__ __device__ __forceinline__ unsigned long long packed_revcomp(unsigned l
     return r;
 }
 
-// partition of a hash: top bits of the LOW hash word (the slot uses the high word), any partition count
-__device__ __forceinline__ unsigned hash_part(unsigned long long h, unsigned nparts) {
-    return (unsigned)(((h & 0xFFFFFFFFull) * (unsigned long long)nparts) >> 32);
+// Key hash: two 32-bit words from a dozen 32-bit instructions (a 64-bit murmur finalizer costs three times that in IMADs,
+// and every window of every read pays it).  x picks the PARTITION (and so the owner GPU), y the bucket inside it; the
+// two are mixed from different combinations of the key's plane words, so together they carry ~64 bits.
+struct KeyHash { unsigned x, y; };
+__device__ __forceinline__ KeyHash key_hash(unsigned long long key) {
+    const unsigned a = (unsigned)key * 0x9E3779B1u, b = (unsigned)(key >> 32) * 0x85EBCA77u;
+    KeyHash h;
+    h.x = a + b;
+    h.x ^= h.x >> 15; h.x *= 0x2C1B3C6Du; h.x ^= h.x >> 13;
+    h.y = a ^ __funnelshift_l(b, b, 15);
+    h.y ^= h.y >> 16; h.y *= 0x297A2D39u; h.y ^= h.y >> 15;
+    return h;
 }
+// partition of a hash, any partition count.  Nested: with nfine = f * ncoarse, hash_part(h, nfine) / f == hash_part(h, ncoarse)
+__device__ __forceinline__ unsigned hash_part(KeyHash h, unsigned nparts) { return __umulhi(h.x, nparts); }
 struct Probe {
     unsigned long long base;   // first slot of the key's partition inside this view
     unsigned long long off;    // current slot inside the partition
 };
 // returns false when the key's partition is not held by this view
 __device__ __forceinline__ bool probe_home(const Geo& g, unsigned long long key, Probe& p) {
-    const unsigned long long h = mix64(key);
+    const KeyHash h = key_hash(key);
     const unsigned part = hash_part(h, g.nparts) - g.part0;
     p.base = (unsigned long long)part * g.subcap;
-    p.off = __umul64hi(h, g.subcap / BUCKET_SLOTS) * BUCKET_SLOTS;      // first slot of the home bucket
+    p.off = (unsigned long long)__umulhi(h.y, (unsigned)(g.subcap / BUCKET_SLOTS)) * BUCKET_SLOTS;      // first slot of the home bucket
     return part < g.nlocal;
 }
 __device__ __forceinline__ void probe_next(const Geo& g, Probe& p) { p.off = (p.off + 1 == g.subcap) ? 0ull : p.off + 1; }
@@ -178,13 +189,13 @@ __device__ __forceinline__ void ld_slot_pair(const Slot* p, unsigned long long& 
 // together, so the DRAM-bound loads of a warp are issued as one request and not once per straggler group.
 __device__ __forceinline__ uint2 table_lookup2(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,
                                                 bool valid) {
-    const unsigned long long h = mix64(key);
+    const KeyHash h = key_hash(key);
     uint2 v = make_uint2(0u, 0u);   // {val, aux}
     bool open = valid;
     const unsigned part = hash_part(h, g.nparts) - g.part0;
     if (part >= g.nlocal) open = false;
     const unsigned long long base = (unsigned long long)part * g.subcap;
-    unsigned long long off = __umul64hi(h, g.subcap / BUCKET_SLOTS) * BUCKET_SLOTS;
+    unsigned long long off = (unsigned long long)__umulhi(h.y, (unsigned)(g.subcap / BUCKET_SLOTS)) * BUCKET_SLOTS;
     // one bucket per round, the four slots examined in fill order
     for (unsigned long long probes = 0; open && probes <= g.subcap; probes += BUCKET_SLOTS) {   // bounded: a full partition cannot hang
         const Slot* b = &slots[base + off];
@@ -206,6 +217,63 @@ __device__ __forceinline__ uint2 table_lookup2(const Slot* __restrict__ slots, c
         off = (off + BUCKET_SLOTS == g.subcap) ? 0ull : off + BUCKET_SLOTS;
     }
     __syncwarp();
+    return v;
+}
+// The same lookup in two halves, so that a caller can have the first sectors of SEVERAL keys in flight before it settles
+// any of them (the per-read kernels issue the loads of three rounds of 32 windows back to back: one memory latency per
+// three rounds instead of three).  lookup_issue: home bucket address + its first sector; lookup_settle: the answer.
+// CONVERGENT like table_lookup2: every lane of the warp calls both (lanes without a key pass valid = false); the rare
+// continuations (second sector of the bucket, further buckets) are entered by the whole warp on a vote, so the common
+// path has no divergence bookkeeping at all.
+struct LookupIssue { const Slot* bucket; unsigned long long k0, w0, k1, w1; };
+__device__ __forceinline__ LookupIssue lookup_issue(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,
+                                                    bool& valid) {
+    LookupIssue q;
+    const KeyHash h = key_hash(key);
+    const unsigned part = hash_part(h, g.nparts) - g.part0;
+    if (part >= g.nlocal) valid = false;                 // a shard that does not hold the partition: absent
+    const unsigned long long off = (unsigned long long)__umulhi(h.y, (unsigned)(g.subcap / BUCKET_SLOTS)) * BUCKET_SLOTS;
+    q.bucket = &slots[(unsigned long long)part * g.subcap + off];
+    q.k0 = q.w0 = q.k1 = q.w1 = 0ull;
+    if (valid) ld_slot_pair(q.bucket, q.k0, q.w0, q.k1, q.w1);
+    return q;
+}
+__device__ __forceinline__ uint2 lookup_settle(const Slot* __restrict__ slots, const Geo& g, unsigned long long key, bool valid,
+                                                const LookupIssue& q) {
+    uint2 v = make_uint2(0u, 0u);   // {val, aux}
+    bool open = valid;
+    if (open) {
+        if (q.k0 == key) { v = make_uint2((unsigned)q.w0, (unsigned)(q.w0 >> 32)); open = false; }
+        else if (q.k1 == key) { v = make_uint2((unsigned)q.w1, (unsigned)(q.w1 >> 32)); open = false; }
+        else if (q.k0 == 0ull || q.k1 == 0ull) open = false;                      // a free slot ends the walk
+    }
+    if (__any_sync(0xFFFFFFFFu, open)) {
+        unsigned long long k2 = 0ull, w2 = 0ull, k3 = 0ull, w3 = 0ull;
+        if (open) {
+            ld_slot_pair(q.bucket + 2, k2, w2, k3, w3);
+            if (k2 == key) { v = make_uint2((unsigned)w2, (unsigned)(w2 >> 32)); open = false; }
+            else if (k3 == key) { v = make_uint2((unsigned)w3, (unsigned)(w3 >> 32)); open = false; }
+            else if (k2 == 0ull || k3 == 0ull) open = false;
+        }
+        // whole bucket taken by other keys (rare): walk on, bucket by bucket, wrapping inside the partition
+        const KeyHash h = key_hash(key);
+        const unsigned long long base = (unsigned long long)(hash_part(h, g.nparts) - g.part0) * g.subcap;
+        unsigned long long off = (unsigned long long)__umulhi(h.y, (unsigned)(g.subcap / BUCKET_SLOTS)) * BUCKET_SLOTS;
+        for (unsigned long long probes = BUCKET_SLOTS; __any_sync(0xFFFFFFFFu, open) && probes <= g.subcap; probes += BUCKET_SLOTS) {
+            off = (off + BUCKET_SLOTS == g.subcap) ? 0ull : off + BUCKET_SLOTS;      // (bounded: a full partition cannot hang)
+            if (open) {
+                const Slot* b = &slots[base + off];
+                unsigned long long k0, w0, k1, w1;
+                ld_slot_pair(b, k0, w0, k1, w1);
+                ld_slot_pair(b + 2, k2, w2, k3, w3);
+                unsigned long long w = 0ull;
+                bool hit = true;
+                if (k0 == key) w = w0; else if (k1 == key) w = w1; else if (k2 == key) w = w2; else if (k3 == key) w = w3; else hit = false;
+                if (hit) { v = make_uint2((unsigned)w, (unsigned)(w >> 32)); open = false; }
+                else if (k0 == 0ull || k1 == 0ull || k2 == 0ull || k3 == 0ull) open = false;
+            }
+        }
+    }
     return v;
 }
 __device__ __forceinline__ unsigned table_lookup(const Slot* __restrict__ slots, const Geo& g, unsigned long long key,

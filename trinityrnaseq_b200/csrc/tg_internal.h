@@ -128,7 +128,7 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
 
 // locus order of the reads (tg_perread.cu, tg_sort.cu): signature per read, then a radix sort of (signature, index)
 cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                              uint32_t* d_sig, uint32_t* d_idx, cudaStream_t s);
+                              uint32_t* d_sig, uint32_t* d_idx, int sm_count, cudaStream_t s);
 size_t locus_sort_bytes(uint64_t n);
 cudaError_t locus_sort(void* work, size_t work_bytes, uint64_t n, const uint32_t** d_sorted, cudaStream_t s);
 

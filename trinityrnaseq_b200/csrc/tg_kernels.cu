@@ -326,7 +326,7 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
                     const unsigned code = (f0 & 1u) | ((f1 & 1u) << 1);
                     hpA += code == 0u; hpC += code == 1u; hpG += code == 2u; hpT += code == 3u;
                 } else {
-                    const unsigned bin = hash_part(mix64(window_key(f0, f1, k, canonical)), nbins);
+                    const unsigned bin = hash_part(key_hash(window_key(f0, f1, k, canonical)), nbins);
                     const unsigned shift = (bin & 1u) * 16u;
                     const unsigned old = atomicAdd(&cnt32[bin >> 1], 1u << shift);
                     m = (bin << 12) | ((old >> shift) & 0xFFFFu);
@@ -592,7 +592,7 @@ k_log_replay(const unsigned long long* __restrict__ keys, const unsigned int* __
                 const unsigned long long key = i < n ? __ldcs(base + i) : 0ull;
                 if (key != 0ull) {
                     // bits 40..: every key of a bin shares the top bits of the LOW hash word (they are the partition)
-                    unsigned h = (unsigned)(mix64(key) >> 40) & (RP_FOLD - 1);
+                    unsigned h = key_hash(key).y & (RP_FOLD - 1);
                     int tries = 0;
                     for (; tries < RP_FOLD_PROBES; tries++) {
                         const unsigned long long old = atomicCAS(&f_key[h], 0ull, key);
@@ -701,7 +701,7 @@ k_log_refine(const unsigned long long* __restrict__ keys, const unsigned int* __
         for (int j = 0; j < RF_PER_THREAD; j++) {
             meta[j] = 0xFFFFFFFFu;
             if (key[j] != 0ull) {
-                const unsigned bin = hash_part(mix64(key[j]), nfine_global) - first;
+                const unsigned bin = hash_part(key_hash(key[j]), nfine_global) - first;
                 if (bin < f) meta[j] = (bin << 12) | atomicAdd(&cnt[bin], 1u);
                 else atomicExch(error, 2);                         // a key that does not belong to this coarse bin
             }

@@ -205,22 +205,37 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
     return (uint32_t)(x1 + x2) / 2u;
 }
 
-// lookups of one read + sum, mean, median; the coverage vector is left in sw.cov[used .. used + nwin)
+// lookups of one read + sum, mean, median; the coverage vector is left in sw.cov[used .. used + nwin).  The first-sector
+// loads of LK rounds (LK x 32 windows) are issued back to back before any of them is examined.
 template <int PER>
 __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, int nwin, int k,
                                            unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean) {
+    constexpr int LK = PER <= 3 ? 3 : 2;           // rounds in flight (registers: longer reads keep more values)
     unsigned x[PER];
     unsigned mn = 0xFFFFFFFFu, mx = 0u;
     unsigned long long part = 0;
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const int p = 32 * i + lane;
-        const Window w = front_window(sw.f, p, nwin, k, mk, canonical);
-        unsigned v = table_lookup(slots, geo, w.key, w.valid);          // warp-convergent: every lane calls it
-        if (v < 1) v = 1;                          // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
-        const bool live = p < nwin;
-        x[i] = live ? v : 0xFFFFFFFFu;
-        if (live) { sw.cov[used + p] = v; mn = min(mn, v); mx = max(mx, v); part += v; }
+    for (int i0 = 0; i0 < PER; i0 += LK) {
+        unsigned long long key[LK];
+        bool ok[LK];
+        LookupIssue q[LK];
+#pragma unroll
+        for (int u = 0; u < LK; u++)
+            if (i0 + u < PER) {
+                const Window w = front_window(sw.f, 32 * (i0 + u) + lane, nwin, k, mk, canonical);
+                key[u] = w.key; ok[u] = w.valid;
+                q[u] = lookup_issue(slots, geo, key[u], ok[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < LK; u++)
+            if (i0 + u < PER) {
+                const int p = 32 * (i0 + u) + lane;
+                unsigned v = lookup_settle(slots, geo, key[u], ok[u], q[u]).x;
+                if (v < 1) v = 1;                  // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
+                const bool live = p < nwin;
+                x[i0 + u] = live ? v : 0xFFFFFFFFu;
+                if (live) { sw.cov[used + p] = v; mn = min(mn, v); mx = max(mx, v); part += v; }
+            }
     }
     const unsigned lo = __reduce_min_sync(FULL, mn), hi = __reduce_max_sync(FULL, mx);
     unsigned long long sum;
@@ -587,22 +602,37 @@ template <int PER>
 __device__ __forceinline__ void assign_read(AssignWarp& aw, const Slot* __restrict__ slots, const Geo& geo,
                                             const uint8_t* __restrict__ lut, int nwin, int k, unsigned mk, int strand, int lane,
                                             unsigned& nh_out) {
+    constexpr int LK = 3;                          // rounds in flight
     unsigned nh = 0;
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const int p = 32 * i + lane;
-        // label tables are keyed canonically whatever the library type: the strand flag only drops the second lookup
-        const Window w = front_window(aw.f, p, nwin, k, mk, true);
-        bool do_f = false, do_r = false;
-        if (w.valid) {                     // a window with a non-ACGT character can never equal a table k-mer
-            do_f = window_entropy_ok(lut, w.f0, w.f1, mk, false);
-            do_r = !strand && window_entropy_ok(lut, w.f0, w.f1, mk, true);
-        }
-        // ONE probe answers both passes of the reference (forward window, then reverse-complemented window)
-        const uint2 v = table_lookup2(slots, geo, w.key, do_f || do_r);       // warp-convergent
-        unsigned vf, vr2;
-        labels_of(v, do_f, do_r, w.is_rc, w.pal, vf, vr2);
-        push_hits(aw.hits, nh, vf, vr2, lane);
+    for (int i0 = 0; i0 < PER; i0 += LK) {
+        unsigned long long key[LK];
+        unsigned fl[LK];                   // 1 = forward pass wanted, 2 = reverse pass wanted, 4 = key is the rc, 8 = palindrome
+        bool ok[LK];
+        LookupIssue q[LK];
+#pragma unroll
+        for (int u = 0; u < LK; u++)
+            if (i0 + u < PER) {
+                // label tables are keyed canonically whatever the library type: the strand flag only drops the second lookup
+                const Window w = front_window(aw.f, 32 * (i0 + u) + lane, nwin, k, mk, true);
+                bool do_f = false, do_r = false;
+                if (w.valid) {             // a window with a non-ACGT character can never equal a table k-mer
+                    do_f = window_entropy_ok(lut, w.f0, w.f1, mk, false);
+                    do_r = !strand && window_entropy_ok(lut, w.f0, w.f1, mk, true);
+                }
+                key[u] = w.key; ok[u] = do_f || do_r;
+                fl[u] = (do_f ? 1u : 0u) | (do_r ? 2u : 0u) | (w.is_rc ? 4u : 0u) | (w.pal ? 8u : 0u);
+                q[u] = lookup_issue(slots, geo, key[u], ok[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < LK; u++)
+            if (i0 + u < PER) {
+                // ONE probe answers both passes of the reference (forward window, then reverse-complemented window)
+                const uint2 v = lookup_settle(slots, geo, key[u], ok[u], q[u]);
+                unsigned vf, vr2;
+                labels_of(v, fl[u] & 1u, fl[u] & 2u, fl[u] & 4u, fl[u] & 8u, vf, vr2);
+                push_hits(aw.hits, nh, vf, vr2, lane);
+            }
     }
     __syncwarp();
     nh_out = nh;
@@ -801,10 +831,16 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
 // =========================================================================================================
 // locus signature: the smallest strand-symmetric m-mer hash of a read (see LOCUS ORDER at the top of the file)
 // =========================================================================================================
-// m = min(k, 20): long enough to be unique to its place in a transcriptome, short enough that two reads overlapping by a
-// third of their length usually share it.  A read and its reverse complement get the same signature (both strands of an
-// m-mer hash alike), so the two mates' orientations and unstranded libraries cluster together.
-constexpr int LOCUS_RPW = 8;          // consecutive reads per warp
+// m = min(k, 16): long enough to be (nearly) unique to its place in a transcriptome, short enough that a sequencing error
+// rarely creates the read's smallest m-mer (an error touches m of the ~L m-mers of a read).  A read and its reverse
+// complement get the same signature (both strands of an m-mer hash alike), so both mates' orientations cluster together.
+//
+// Flat scan like the count kernels (no read structure, except to know which read a window belongs to): a CTA takes 8 KiB
+// of the record buffer per iteration, transposes it into bit planes (SWAR, four bases per lane), and every thread hashes
+// the 32 m-mers that start in its 32-base chunk -- all shifts of two register pairs -- keeping a running minimum per
+// record, which leaves through one atomicMin per (thread, record).  No padding is assumed behind the records: bytes at and
+// past nbytes read as terminators.
+constexpr int LC_GROUPS = CT_TILE / 128 + 1;      // 128-base SWAR groups per tile, + the halo group
 
 __device__ __forceinline__ unsigned locus_hash(unsigned f0, unsigned f1, int m) {
     const unsigned r0 = __brev(~f0) >> (32 - m), r1 = __brev(~f1) >> (32 - m);
@@ -812,50 +848,80 @@ __device__ __forceinline__ unsigned locus_hash(unsigned f0, unsigned f1, int m) 
     unsigned x = a < b ? a : b;
     x ^= x >> 15;
     x *= 0x2C1B3C6Du;
-    x ^= x >> 13;
-    return x;
+    return x ^ (x >> 13);
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32)
-k_read_locus(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads, int m,
-             uint32_t* __restrict__ sig, uint32_t* __restrict__ idx) {
-    __shared__ WarpFront fw[PR_WARPS];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    WarpFront& f = fw[w];
-    const uint64_t r0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * LOCUS_RPW;
-    if (r0 >= nreads) return;
+__global__ void __launch_bounds__(CT_THREADS, 4)
+k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t nrec, uint64_t rec_base, int m,
+              uint32_t* __restrict__ sig, uint32_t* __restrict__ idx) {
+    __shared__ uint32_t p0[4 * LC_GROUPS], p1[4 * LC_GROUPS], pb[4 * LC_GROUPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mm = kmask(m);
-    const uint64_t my_off = offs[min(r0 + (uint64_t)lane, nreads)];
-    unsigned mine = 0xFFFFFFFFu;                      // lane rr keeps the signature of the rr-th read
-    for (int rr = 0; rr < LOCUS_RPW && r0 + rr < nreads; rr++) {
-        const uint64_t o0 = __shfl_sync(FULL, my_off, rr), o1 = __shfl_sync(FULL, my_off, rr + 1);
-        int L = (int)(o1 - o0 - 1);
-        if (L > PR_MAXWIN) L = PR_MAXWIN;             // a long read is placed by its first 256 bases
-        unsigned best = 0xFFFFFFFFu;
-        if (L >= m) {
-            front_planes(f, recs + (o0 - rec_base), L, lane);
-            for (int q = lane; q <= L - m; q += 32) {
-                const int c = q >> 5, o = q & 31;
-                if (!(__funnelshift_r(f.pb[c], f.pb[c + 1], o) & mm))
-                    best = min(best, locus_hash(__funnelshift_r(f.p0[c], f.p0[c + 1], o) & mm,
-                                                __funnelshift_r(f.p1[c], f.p1[c + 1], o) & mm, m));
+    const uint64_t nbytes = offs[nrec] - rec_base;
+    const uint64_t ntiles = (nbytes + CT_TILE - 1) / CT_TILE;
+    for (uint64_t i = blockIdx.x * (uint64_t)CT_THREADS + tid; i < nrec; i += (uint64_t)gridDim.x * CT_THREADS) idx[i] = (uint32_t)i;
+    const unsigned* words = reinterpret_cast<const unsigned*>(recs);       // record buffers are at least 4-byte aligned
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * CT_TILE;
+        for (int g = warp; g < LC_GROUPS; g += CT_THREADS / 32) {
+            const uint64_t first = t0 + 128ull * g + 4ull * lane;           // this lane's four bases
+            unsigned w = 0x0A0A0A0Au;
+            if (first < nbytes) {
+                w = words[first >> 2];
+                if (first + 4 > nbytes) {                                   // the word that straddles the end of the records
+                    const unsigned keep = (unsigned)(nbytes - first) * 8u;
+                    w = (w & ((1u << keep) - 1u)) | (0x0A0A0A0Au << keep);
+                }
             }
-            __syncwarp();
+            const unsigned cc = (w >> 1) ^ (w >> 2);
+            const unsigned u = w & 0xDFDFDFDFu;
+            const unsigned ok = swar_zero_bytes(u ^ 0x41414141u) | swar_zero_bytes(u ^ 0x43434343u) |
+                                swar_zero_bytes(u ^ 0x47474747u) | swar_zero_bytes(u ^ 0x54545454u);
+            const unsigned n0 = swar_gather(cc), n1 = swar_gather(cc >> 1), nb = ~swar_gather(ok >> 7) & 0xFu;
+            const unsigned grp = 0xFFu << (lane & 24);
+            const int pos = 4 * (lane & 7);
+            const unsigned b0 = __reduce_or_sync(grp, n0 << pos);
+            const unsigned b1 = __reduce_or_sync(grp, n1 << pos);
+            const unsigned bb = __reduce_or_sync(grp, nb << pos);
+            if ((lane & 7) == 0) { const int c = 4 * g + (lane >> 3); p0[c] = b0; p1[c] = b1; pb[c] = bb; }
         }
-        best = __reduce_min_sync(FULL, best);
-        if (lane == rr) mine = best;
+        __syncthreads();
+        const unsigned a0 = p0[tid], a1 = p1[tid], ab = pb[tid];
+        const unsigned c0 = p0[tid + 1], c1 = p1[tid + 1], cb = pb[tid + 1];
+        if (ab != FULL) {                          // (an m-mer STARTS in this chunk only if the chunk has a base)
+            const uint64_t g0 = rec_base + t0 + (uint64_t)tid * 32;          // in the offs[] frame
+            uint64_t lo = 0, hi = nrec;            // record of this thread's first base: last offs[i] <= g0
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (offs[mid] <= g0) lo = mid; else hi = mid;
+            }
+            uint64_t rec = lo, next_off = offs[lo + 1];
+            unsigned cur = 0xFFFFFFFFu;
+#pragma unroll 4
+            for (int s = 0; s < 32; s++) {
+                if (__funnelshift_r(ab, cb, s) & mm) continue;
+                // a valid m-mer lies inside one record, so rec < nrec whenever we advance
+                if (g0 + s >= next_off) {
+                    if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);
+                    cur = 0xFFFFFFFFu;
+                    do { rec++; next_off = offs[rec + 1]; } while (g0 + s >= next_off);
+                }
+                cur = min(cur, locus_hash(__funnelshift_r(a0, c0, s) & mm, __funnelshift_r(a1, c1, s) & mm, m));
+            }
+            if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);
+        }
+        __syncthreads();
     }
-    if (lane < LOCUS_RPW && r0 + lane < nreads) { sig[r0 + lane] = mine; idx[r0 + lane] = (uint32_t)(r0 + lane); }
 }
 
 cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
-                              uint32_t* d_sig, uint32_t* d_idx, cudaStream_t s) {
-    TimedLaunch timed("k_read_locus", s);
+                              uint32_t* d_sig, uint32_t* d_idx, int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_locus_tiles", s);
     if (nreads == 0) return cudaSuccess;
-    const int m = k < 20 ? k : 20;
-    const uint64_t per_cta = (uint64_t)PR_WARPS * LOCUS_RPW;
-    k_read_locus<<<(unsigned)((nreads + per_cta - 1) / per_cta), PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, m,
-                                                                                       d_sig, d_idx);
+    const int m = k < 16 ? k : 16;
+    cudaError_t e = cudaMemsetAsync(d_sig, 0xFF, nreads * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_locus_tiles<<<sm_count * 4, CT_THREADS, 0, s>>>(d_recs, d_offs, nreads, rec_base, m, d_sig, d_idx);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,7 @@ size_t locus_sort_bytes(uint64_t n) {
 }
 
 cudaError_t locus_sort(void* work, size_t work_bytes, uint64_t n, const uint32_t** d_sorted, cudaStream_t s) {
+    TimedLaunch timed("locus_sort", s);
     if (n > 0x7FFFFFF0ull) return cudaErrorInvalidValue;
     uint32_t* sig = (uint32_t*)work;
     uint32_t* idx = sig + n;
