@@ -183,6 +183,13 @@ __device__ __forceinline__ void ld_slot_pair(const Slot* p, unsigned long long& 
     asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(w0), "=l"(k1), "=l"(w1) : "l"(p));
 }
 
+// The same through the read-only path (L1-cached: ld.global.nc).  Only for tables that no kernel in flight writes to -- the
+// per-read kernels; in locus order neighbouring reads ask for the same buckets, and L1 answers many of them.
+__device__ __forceinline__ void ld_slot_pair_ro(const Slot* p, unsigned long long& k0, unsigned long long& w0,
+                                                unsigned long long& k1, unsigned long long& w1) {
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(w0), "=l"(k1), "=l"(w1) : "l"(p));
+}
+
 // Read-only probe: returns {val, aux}, or 0 when the key is absent or !valid.  One round = one 64-B bucket.
 // CONVERGENT: every lane of the warp must call it (lanes without a key pass valid = false).  Lanes leave the probe
 // loops at different times; the __syncwarp() between the hot-table phase and the big-table phase brings them back
@@ -235,7 +242,7 @@ __device__ __forceinline__ LookupIssue lookup_issue(const Slot* __restrict__ slo
     const unsigned long long off = (unsigned long long)__umulhi(h.y, (unsigned)(g.subcap / BUCKET_SLOTS)) * BUCKET_SLOTS;
     q.bucket = &slots[(unsigned long long)part * g.subcap + off];
     q.k0 = q.w0 = q.k1 = q.w1 = 0ull;
-    if (valid) ld_slot_pair(q.bucket, q.k0, q.w0, q.k1, q.w1);
+    if (valid) ld_slot_pair_ro(q.bucket, q.k0, q.w0, q.k1, q.w1);
     return q;
 }
 __device__ __forceinline__ uint2 lookup_settle(const Slot* __restrict__ slots, const Geo& g, unsigned long long key, bool valid,
@@ -250,7 +257,7 @@ __device__ __forceinline__ uint2 lookup_settle(const Slot* __restrict__ slots, c
     if (__any_sync(0xFFFFFFFFu, open)) {
         unsigned long long k2 = 0ull, w2 = 0ull, k3 = 0ull, w3 = 0ull;
         if (open) {
-            ld_slot_pair(q.bucket + 2, k2, w2, k3, w3);
+            ld_slot_pair_ro(q.bucket + 2, k2, w2, k3, w3);
             if (k2 == key) { v = make_uint2((unsigned)w2, (unsigned)(w2 >> 32)); open = false; }
             else if (k3 == key) { v = make_uint2((unsigned)w3, (unsigned)(w3 >> 32)); open = false; }
             else if (k2 == 0ull || k3 == 0ull) open = false;
@@ -264,8 +271,8 @@ __device__ __forceinline__ uint2 lookup_settle(const Slot* __restrict__ slots, c
             if (open) {
                 const Slot* b = &slots[base + off];
                 unsigned long long k0, w0, k1, w1;
-                ld_slot_pair(b, k0, w0, k1, w1);
-                ld_slot_pair(b + 2, k2, w2, k3, w3);
+                ld_slot_pair_ro(b, k0, w0, k1, w1);
+                ld_slot_pair_ro(b + 2, k2, w2, k3, w3);
                 unsigned long long w = 0ull;
                 bool hit = true;
                 if (k0 == key) w = w0; else if (k1 == key) w = w1; else if (k2 == key) w = w2; else if (k3 == key) w = w3; else hit = false;

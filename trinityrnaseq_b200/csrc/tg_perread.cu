@@ -93,7 +93,7 @@ __device__ __forceinline__ unsigned long long group_sum_u64(unsigned long long v
 // The warp path's transpose: FOUR bases per lane and round (128 bases per round: one round for a 100-bp read instead of
 // four ballot rounds).  Lane l holds bases 4l .. 4l+3 of the round as one 32-bit word; code bits and validity are computed
 // for the four bytes at once (SWAR), gathered into nibbles, and the eight lanes that share a 32-base plane word OR their
-// nibbles together with a segmented redux.  Bytes are read as aligned words (two per lane, funnel-shifted by the record's
+// nibbles together (xor butterfly).  Bytes are read as aligned words (two per lane, funnel-shifted by the record's
 // misalignment); nothing past the record's terminator is touched beyond the padding every device record buffer carries.
 __device__ __forceinline__ unsigned swar_zero_bytes(unsigned z) {          // bit 7 of every byte of z that is 0
     return ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u;
@@ -101,12 +101,21 @@ __device__ __forceinline__ unsigned swar_zero_bytes(unsigned z) {          // bi
 __device__ __forceinline__ unsigned swar_gather(unsigned x) {             // bits 0, 8, 16, 24 -> bits 0..3
     return ((x & 0x01010101u) * 0x01020408u) >> 24;
 }
+// OR of three words over the 8 lanes that share a plane word: an xor butterfly (a redux.sync over a partial mask is
+// executed group by group -- four serialised collectives per word, measured at 10 % of the statistics kernel)
+__device__ __forceinline__ void or_over_8_lanes(unsigned& a, unsigned& b, unsigned& c) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        a |= __shfl_xor_sync(FULL, a, o);
+        b |= __shfl_xor_sync(FULL, b, o);
+        c |= __shfl_xor_sync(FULL, c, o);
+    }
+}
 __device__ __forceinline__ void pack_read_planes_warp(const uint8_t* __restrict__ seq, int L, int nch, uint32_t* P0,
                                                       uint32_t* P1, uint32_t* PB, int lane) {
     const unsigned long long a0 = reinterpret_cast<unsigned long long>(seq);
     const int sh = (int)(a0 & 3ull);
     const unsigned* words = reinterpret_cast<const unsigned*>(a0 - (unsigned long long)sh);
-    const unsigned grp = 0xFFu << (lane & 24);                              // the 8 lanes of this lane's plane word
     for (int g = 0; 4 * g <= nch; g++) {
         const int first = 128 * g + 4 * lane;                               // index of this lane's first base
         // aligned words covering bytes [first - sh, first - sh + 8)
@@ -122,9 +131,8 @@ __device__ __forceinline__ void pack_read_planes_warp(const uint8_t* __restrict_
         const unsigned n0 = swar_gather(cc), n1 = swar_gather(cc >> 1);
         const unsigned nb = ~(swar_gather(ok >> 7) & lm) & 0xFu;           // invalid: not ACGT, or past the record
         const int pos = 4 * (lane & 7);
-        const unsigned b0 = __reduce_or_sync(grp, n0 << pos);
-        const unsigned b1 = __reduce_or_sync(grp, n1 << pos);
-        const unsigned bb = __reduce_or_sync(grp, nb << pos);
+        unsigned b0 = n0 << pos, b1 = n1 << pos, bb = nb << pos;
+        or_over_8_lanes(b0, b1, bb);
         if ((lane & 7) == 0) { const int c = 4 * g + (lane >> 3); P0[c] = b0; P1[c] = b1; PB[c] = bb; }
     }
 }
@@ -854,7 +862,12 @@ __device__ __forceinline__ unsigned locus_hash(unsigned f0, unsigned f1, int m) 
 __global__ void __launch_bounds__(CT_THREADS, 4)
 k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t nrec, uint64_t rec_base, int m,
               uint32_t* __restrict__ sig, uint32_t* __restrict__ idx) {
-    __shared__ uint32_t p0[4 * LC_GROUPS], p1[4 * LC_GROUPS], pb[4 * LC_GROUPS];
+    // planes of the tile's chunks (+ halo group); pn = "is the record terminator": every record ends with exactly one '\n'
+    // (the record-buffer format), so the record of a position is the record of the tile's first byte plus the terminators
+    // before it -- ONE binary search per tile instead of one per thread
+    __shared__ uint32_t p0[4 * LC_GROUPS], p1[4 * LC_GROUPS], pb[4 * LC_GROUPS], pn[4 * LC_GROUPS];
+    __shared__ uint32_t wsum[CT_THREADS / 32];
+    __shared__ unsigned long long tile_rec;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mm = kmask(m);
     const uint64_t nbytes = offs[nrec] - rec_base;
@@ -863,6 +876,15 @@ k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
     const unsigned* words = reinterpret_cast<const unsigned*>(recs);       // record buffers are at least 4-byte aligned
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t t0 = tile * CT_TILE;
+        if (tid == 0) {                            // record of the tile's first byte: last offs[i] <= rec_base + t0
+            const uint64_t g0 = rec_base + t0;
+            uint64_t lo = 0, hi = nrec;
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (offs[mid] <= g0) lo = mid; else hi = mid;
+            }
+            tile_rec = lo;
+        }
         for (int g = warp; g < LC_GROUPS; g += CT_THREADS / 32) {
             const uint64_t first = t0 + 128ull * g + 4ull * lane;           // this lane's four bases
             unsigned w = 0x0A0A0A0Au;
@@ -878,37 +900,43 @@ k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
             const unsigned ok = swar_zero_bytes(u ^ 0x41414141u) | swar_zero_bytes(u ^ 0x43434343u) |
                                 swar_zero_bytes(u ^ 0x47474747u) | swar_zero_bytes(u ^ 0x54545454u);
             const unsigned n0 = swar_gather(cc), n1 = swar_gather(cc >> 1), nb = ~swar_gather(ok >> 7) & 0xFu;
-            const unsigned grp = 0xFFu << (lane & 24);
+            const unsigned nn = first < nbytes ? swar_gather(swar_zero_bytes(w ^ 0x0A0A0A0Au) >> 7) : 0u;   // (padding is no terminator)
             const int pos = 4 * (lane & 7);
-            const unsigned b0 = __reduce_or_sync(grp, n0 << pos);
-            const unsigned b1 = __reduce_or_sync(grp, n1 << pos);
-            const unsigned bb = __reduce_or_sync(grp, nb << pos);
-            if ((lane & 7) == 0) { const int c = 4 * g + (lane >> 3); p0[c] = b0; p1[c] = b1; pb[c] = bb; }
+            unsigned b0 = n0 << pos, b1 = n1 << pos, bb = nb << pos, bn = nn << pos;
+            or_over_8_lanes(b0, b1, bb);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) bn |= __shfl_xor_sync(FULL, bn, o);
+            if ((lane & 7) == 0) { const int c = 4 * g + (lane >> 3); p0[c] = b0; p1[c] = b1; pb[c] = bb; pn[c] = bn; }
         }
         __syncthreads();
-        const unsigned a0 = p0[tid], a1 = p1[tid], ab = pb[tid];
+        const unsigned a0 = p0[tid], a1 = p1[tid], ab = pb[tid], an = pn[tid];
         const unsigned c0 = p0[tid + 1], c1 = p1[tid + 1], cb = pb[tid + 1];
+        // terminators before this thread's chunk: exclusive scan of popc(an) over the CTA
+        const unsigned mine = (unsigned)__popc(an);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned before = incl - mine;
+        for (int w2 = 0; w2 < warp; w2++) before += wsum[w2];
         if (ab != FULL) {                          // (an m-mer STARTS in this chunk only if the chunk has a base)
-            const uint64_t g0 = rec_base + t0 + (uint64_t)tid * 32;          // in the offs[] frame
-            uint64_t lo = 0, hi = nrec;            // record of this thread's first base: last offs[i] <= g0
-            while (hi - lo > 1) {
-                const uint64_t mid = (lo + hi) >> 1;
-                if (offs[mid] <= g0) lo = mid; else hi = mid;
-            }
-            uint64_t rec = lo, next_off = offs[lo + 1];
+            uint64_t rec = tile_rec + before;
             unsigned cur = 0xFFFFFFFFu;
 #pragma unroll 4
             for (int s = 0; s < 32; s++) {
-                if (__funnelshift_r(ab, cb, s) & mm) continue;
-                // a valid m-mer lies inside one record, so rec < nrec whenever we advance
-                if (g0 + s >= next_off) {
+                if (s && ((an >> (s - 1)) & 1u)) {                          // position s - 1 ended a record
                     if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);
                     cur = 0xFFFFFFFFu;
-                    do { rec++; next_off = offs[rec + 1]; } while (g0 + s >= next_off);
+                    rec++;
                 }
+                if (__funnelshift_r(ab, cb, s) & mm) continue;
                 cur = min(cur, locus_hash(__funnelshift_r(a0, c0, s) & mm, __funnelshift_r(a1, c1, s) & mm, m));
             }
-            if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);
+            if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);             // rec < nrec: a valid m-mer lies inside a record
         }
         __syncthreads();
     }
