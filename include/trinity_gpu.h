@@ -236,6 +236,13 @@ int tg_ipc_close(tg_ctx* ctx, void* dptr);
 int tg_count_partition_peers_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
                                  uint32_t cap, uint32_t nranks, uint32_t my_rank, void* const* d_owner_keys,
                                  void* d_cursor, void* d_hpoly);
+/* Counting read by read, with the read offsets known (same record buffer + offs as tg_cov_stats_dev): the reads are
+ * visited in LOCUS order (neighbouring reads cover the same stretch of a transcript), so the slots their k-mers share stay
+ * L2-resident while they are incremented and no k-mer log / partition replay is needed.  Same counts as tg_count_reads_dev. */
+int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical);
+/* Declares a device record buffer (+ its offsets) immutable until the next tg_records_pin_dev (NULLs: nothing pinned): the
+ * locus order of its reads is then computed once and shared by every *_dev call that is given exactly these pointers. */
+int tg_records_pin_dev(tg_ctx* ctx, const void* d_recs, const void* d_offs, uint64_t nreads);
 int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
                      void* d_median, void* d_mean, void* d_stdev);
 int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,

@@ -353,3 +353,31 @@ def test_locus_order_changes_nothing_but_the_order(oracle, data, batch_bytes):
             assert "k_locus_tiles" not in ctx.kernel_times()
             np.testing.assert_array_equal(nm, om)
             np.testing.assert_array_equal(_f32_bits(nsd), _f32_bits(osd))
+
+
+@pytest.mark.parametrize("canonical", [True, False])
+@pytest.mark.parametrize("k", [25, 31, 9])
+def test_count_read_by_read_in_locus_order(oracle, data, canonical, k):
+    """tg_count_records_dev: reads counted one by one in locus order, straight into the table (no log): same dump and
+    histogram as the oracle -- homopolymer runs, reads longer than one warp segment, N's and empty reads included --
+    with the order computed per call, pinned (computed once, reused), and switched off."""
+    _, reads = data
+    reads = list(reads) + [b"A" * 400, b"T" * 90 + b"G" * 90, b"AC" * 300, b"\x00\xff"]
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, k, canonical, 1)
+    with tg.Context(0) as ctx:
+        ctx.set("locus_min_reads", 0)
+        d_recs = ctx.dev_records_alloc(recs.nbytes); ctx.h2d(d_recs, recs)
+        d_offs = ctx.dev_alloc(offs.nbytes); ctx.h2d(d_offs, offs)
+        for mode in ("fresh", "pinned", "off"):
+            if mode == "pinned":
+                ctx.records_pin_dev(d_recs, d_offs, len(reads))
+            if mode == "off":
+                ctx.records_pin_dev()
+                ctx.set("locus_order", 0)
+            with tg.KmerCounter(ctx, k, is_ds=canonical, expected_keys=len(ok) + 64) as kc:
+                for rep in range(2 if mode == "pinned" else 1):
+                    kc.add_read_records_dev(d_recs, d_offs, len(reads))
+                gk, gc = kc.dump()
+                np.testing.assert_array_equal(gk, ok)
+                np.testing.assert_array_equal(gc, oc * (2 if mode == "pinned" else 1))

@@ -14,6 +14,7 @@ ap.add_argument("--read-len", type=int, default=100)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--stats-load", type=float, default=0.40)
 ap.add_argument("--no-r2t", action="store_true")
+ap.add_argument("--pin", action="store_true", help="pin the device record buffer: one locus order for all calls")
 ap.add_argument("--set", action="append", default=[], help="ctx knob key=value")
 ap.add_argument("--count-variants", default="", help="';'-separated lists of knobs (k=v,k=v): the count is timed once per list")
 a = ap.parse_args()
@@ -31,6 +32,8 @@ d_offs = ctx.dev_alloc(offs.nbytes); ctx.h2d(d_offs, offs)
 d1, d2, d3 = ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads)
 q = None
 out = {}
+if a.pin:
+    ctx.records_pin_dev(d_recs, d_offs, nreads)
 if a.count_variants:
     out["count_variants"] = {}
     for var in a.count_variants.split(";"):
@@ -50,9 +53,15 @@ if a.count_variants:
 for rep in range(a.reps):
     ctx.set("kernel_timing", 1); ctx.kernel_times()
     kc.clear()
+    kc.add_read_records_dev(d_recs, d_offs, nreads)
+    ctx.sync()
+    out["count_by_read"] = {k_: round(v[0], 3) for k_, v in ctx.kernel_times().items()}
+    info_by_read = kc.info(); hist_by_read = kc.histo()
+    kc.clear()
     kc.add_records_dev(d_recs, nbytes)
     ctx.sync()
     out["count"] = {k_: round(v[0], 3) for k_, v in ctx.kernel_times().items()}
+    assert kc.info()["distinct"] == info_by_read["distinct"] and np.array_equal(kc.histo(), hist_by_read), "count by read != logged count"
     if q is None:
         q = kc.compacted(2, load=a.stats_load)
     else:

@@ -113,6 +113,10 @@ class Context:
         check(_lib.lib().tg_records_release(self._h))
         self._held = None
 
+    def records_pin_dev(self, d_recs=None, d_offs=None, nreads=0):
+        """declare a device record buffer immutable (its locus order is computed once); no arguments: unpin"""
+        check(_lib.lib().tg_records_pin_dev(self._h, d_recs, d_offs, nreads))
+
     def launch_count(self):
         return int(_lib.lib().tg_launch_count(self._h))
 
@@ -328,6 +332,11 @@ class KmerCounter(_Table):
     def add_records_dev(self, d_recs, nbytes, canonical=None):
         can = self.is_ds if canonical is None else canonical
         check(_lib.lib().tg_count_reads_dev(self._h, d_recs, nbytes, int(can)))
+
+    def add_read_records_dev(self, d_recs, d_offs, nreads, canonical=None):
+        """count read by read in locus order (tg_count_records_dev): needs the read offsets, no k-mer log"""
+        can = self.is_ds if canonical is None else canonical
+        check(_lib.lib().tg_count_records_dev(self._h, d_recs, d_offs, nreads, int(can)))
 
     def add_kmers(self, packed_keys, counts, canonical=None):
         """KmerCounter::add_kmer(kmer, count) for many k-mers (the `--kmers` dump loader)."""

@@ -71,6 +71,14 @@ struct tg_ctx {
     DevBuf recs[2], offs[2], out_a[2], out_b[2], out_c[2], per_kmer[2], long_idx[2], scratch;
     DevBuf lut;
     DevBuf locus[2];                                    // per stream: signatures, indices, sort scratch of the locus order
+    // locus orders that outlive a call: of the held host buffer's device copy, and of a device buffer the caller pinned
+    // (tg_records_pin_dev).  Both buffers are immutable by contract, so their order is computed once.
+    struct LocusCache {
+        const void* recs = nullptr; const void* offs_key = nullptr; uint64_t nreads = 0; int m = 0;
+        DevBuf buf; const uint32_t* order = nullptr; cudaEvent_t ready = nullptr; bool valid = false;
+        void forget() { valid = false; order = nullptr; }
+    } locus_held, locus_pin;
+    const void* pin_recs = nullptr; const void* pin_offs = nullptr; uint64_t pin_nreads = 0;
     bool locus_order = true;                            // per-read kernels visit the reads in locus order (tg_perread.cu)
     uint64_t locus_min_reads = 1ull << 15;              // ... when a launch has at least this many reads
     DevBuf long_scratch;                                // fixed budget of the device-driven CTA-per-read kernels (*_dev entry points)
@@ -162,6 +170,9 @@ static int sync_all(tg_ctx* c) {
     CU(cudaStreamSynchronize(c->stream[1]));
     return TG_OK;
 }
+
+static int locus_order_async(tg_ctx* c, int b, const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads,
+                             int k, const uint32_t** d_order, const void* held_offs_key = nullptr);
 
 static int table_refresh(tg_table* t) {   // after a sync: read back distinct count and the error flag
     unsigned long long n = 0;
@@ -261,7 +272,9 @@ void tg_destroy(tg_ctx* c) {
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
-    c->scratch.release(); c->lut.release(); c->long_scratch.release(); c->locus[0].release(); c->locus[1].release();
+    c->scratch.release(); c->lut.release(); c->long_scratch.release(); c->locus[0].release(); c->locus[1].release(); c->locus_held.buf.release(); c->locus_pin.buf.release();
+    if (c->locus_held.ready) cudaEventDestroy(c->locus_held.ready);
+    if (c->locus_pin.ready) cudaEventDestroy(c->locus_pin.ready);
     c->held.dev.release(); c->held.offs.release(); c->held.out_a.release(); c->held.out_b.release(); c->held.out_c.release();
     c->held.long_idx.release();
     for (int i = 0; i < 2; i++) if (c->held.chunk_done[i]) cudaEventDestroy(c->held.chunk_done[i]);
@@ -875,6 +888,7 @@ int tg_records_hold(tg_ctx* c, const char* recs, uint64_t nbytes) {
     int rc = sync_all(c);
     if (rc) return rc;
     c->held.host = nullptr; c->held.nbytes = 0; c->held.uploaded = false;
+    c->locus_held.forget();
     if (nbytes == 0) return TG_OK;
     CU(c->held.dev.ensure(padded_record_bytes(nbytes)));
     for (int i = 0; i < 2; i++)
@@ -888,6 +902,16 @@ int tg_records_release(tg_ctx* c) {
     if (bind(c)) return TG_ERR_CUDA;
     int rc = sync_all(c);
     c->held.host = nullptr; c->held.nbytes = 0; c->held.uploaded = false;
+    c->locus_held.forget();
+    return rc;
+}
+
+int tg_records_pin_dev(tg_ctx* c, const void* d_recs, const void* d_offs, uint64_t nreads) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    int rc = sync_all(c);
+    c->locus_pin.forget();
+    c->pin_recs = d_recs; c->pin_offs = d_offs; c->pin_nreads = d_recs && d_offs ? nreads : 0;
     return rc;
 }
 
@@ -1032,6 +1056,22 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
         t->log.pending_ub += log_launch_cost(c, t->log, n);
         if ((rc = replay_log_async(t))) return rc;
     }
+    return TG_OK;
+}
+
+int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical) {
+    if (!t || !d_recs || !d_offs) return fail(TG_ERR_ARG, "tg_count_records_dev: null argument");
+    if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_records_dev needs a TG_TABLE_COUNT table");
+    if (t->sharded()) return fail(TG_ERR_ARG, "tg_count_records_dev: sharded tables are counted through the exchange path");
+    if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_count_records_dev: at most 2^31 reads per call");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }
+    // stream-ordered like tg_count_reads_dev; the caller sizes the table
+    const uint32_t* ord = nullptr;
+    if (int rc = locus_order_async(c, 0, (const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, &ord)) return rc;
+    CU(launch_count_reads((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->view(), ord, c->stream[0]));
+    c->launches++;
     return TG_OK;
 }
 
@@ -1299,17 +1339,34 @@ static int held_pass(tg_ctx* c, const uint64_t* offs, uint64_t nreads, bool* don
 }
 
 // Locus order of the reads [0, nreads) of a device record buffer, queued on stream b: *d_order = u32[nreads], or nullptr
-// when the launch is too small to pay for it (or the knob is off).  Stream-ordered, no host synchronisation.
+// when the launch is too small to pay for it (or the knob is off).  Stream-ordered, no host synchronisation.  The order
+// of the held buffer's device copy (offs_key = the caller's host offsets) and of a pinned device buffer is kept.
 static int locus_order_async(tg_ctx* c, int b, const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads,
-                             int k, const uint32_t** d_order) {
+                             int k, const uint32_t** d_order, const void* held_offs_key) {
     *d_order = nullptr;
     if (!c->locus_order || nreads < c->locus_min_reads || nreads > 0x7FFFFFF0ull) return TG_OK;
+    const int m = k < 16 ? k : 16;
+    tg_ctx::LocusCache* lc = nullptr;
+    const void* offs_key = d_offs;
+    if (held_offs_key && c->held.uploaded && d_recs == (const uint8_t*)c->held.dev.p) { lc = &c->locus_held; offs_key = held_offs_key; }
+    else if (rec_base == 0 && c->pin_nreads && d_recs == c->pin_recs && d_offs == c->pin_offs && nreads == c->pin_nreads) lc = &c->locus_pin;
+    if (lc && lc->valid && lc->recs == d_recs && lc->offs_key == offs_key && lc->nreads == nreads && lc->m == m) {
+        CU(cudaStreamWaitEvent(c->stream[b], lc->ready, 0));
+        *d_order = lc->order;
+        return TG_OK;
+    }
     const size_t need = locus_sort_bytes(nreads);
-    CU(c->locus[b].ensure(need));
-    uint32_t* sig = (uint32_t*)c->locus[b].p;
+    DevBuf& buf = lc ? lc->buf : c->locus[b];
+    CU(buf.ensure(need));
+    uint32_t* sig = (uint32_t*)buf.p;
     CU(launch_read_locus(d_recs, d_offs, rec_base, nreads, k, sig, sig + nreads, c->sm_count, c->stream[b]));
-    CU(locus_sort(c->locus[b].p, need, nreads, d_order, c->stream[b]));
+    CU(locus_sort(buf.p, need, nreads, d_order, c->stream[b]));
     c->launches += 2;
+    if (lc) {
+        if (!lc->ready) CU(cudaEventCreateWithFlags(&lc->ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(lc->ready, c->stream[b]));
+        lc->recs = d_recs; lc->offs_key = offs_key; lc->nreads = nreads; lc->m = m; lc->order = *d_order; lc->valid = true;
+    }
     return TG_OK;
 }
 
@@ -1384,7 +1441,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
         bool done = false;
         if ((rc = held_pass(c, offs, nreads, &done, [&](const uint8_t* d, const uint64_t* d_offs, LongList ll) -> int {
                 const uint32_t* ord = nullptr;
-                if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord)) return r3;
+                if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord, offs)) return r3;
                 CU(launch_cov_stats(d, d_offs, 0, nreads, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
                                     (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, ord, c->stream[0]));
                 CU(launch_cov_stats_long_auto(d, d_offs, 0, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
@@ -1544,7 +1601,7 @@ int tg_assign_reads(tg_table* t, const char* recs, const uint64_t* offs, uint64_
         bool done = false;
         if ((rc = held_pass(c, offs, nreads, &done, [&](const uint8_t* d, const uint64_t* d_offs, LongList ll) -> int {
                 const uint32_t* ord = nullptr;
-                if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord)) return r3;
+                if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord, offs)) return r3;
                 CU(launch_assign(d, d_offs, 0, nreads, t->k, strand, t->slots, t->g, (const uint8_t*)c->lut.p,
                                  (int32_t*)c->held.out_a.p, (int32_t*)c->held.out_b.p, (int32_t*)c->held.out_c.p, ll, ord, c->stream[0]));
                 CU(launch_assign_long_auto(d, d_offs, 0, t->k, strand, t->slots, t->g, (const uint8_t*)c->lut.p,

@@ -126,6 +126,9 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
                                     int32_t* d_pct, int32_t* d_score, LongList ll, void* d_scratch, size_t scratch_bytes,
                                     int* d_error, int nctas, cudaStream_t s);
 
+// counting read by read, in the given order (tg_perread.cu): one ld.cg + RED.ADD per window straight into the table
+cudaError_t launch_count_reads(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                               int canonical, TableView t, const uint32_t* d_order, cudaStream_t s);
 // locus order of the reads (tg_perread.cu, tg_sort.cu): signature per read, then a radix sort of (signature, index)
 cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                               uint32_t* d_sig, uint32_t* d_idx, int sm_count, cudaStream_t s);

@@ -837,6 +837,94 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
 
 
 // =========================================================================================================
+// counting read by read (jellyfish count / KmerCounter::add_sequence) in locus order
+// =========================================================================================================
+// The flat-tile and log kernels (tg_kernels.cu) need no read structure.  This one does -- it visits the reads in LOCUS
+// order, and that is the point: the reads that cover one stretch of a transcript are counted together, so the slots their
+// k-mers share are L2-resident while they are being incremented, and the table needs no log, no partition replay and no
+// second pass over the k-mers: one ld.cg + one RED.ADD per window, straight into the table.  Reads of any length: a warp
+// walks a long read in segments of PR_MAXWIN windows.
+constexpr int CR_RPW = 16;            // reads per warp
+constexpr int CR_LK = 4;              // rounds (of 32 windows) whose home-slot loads are in flight together
+
+__global__ void __launch_bounds__(PR_WARPS * 32, 4)
+k_count_reads(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
+              int k, int canonical, TableView t, const uint32_t* __restrict__ order) {
+    __shared__ WarpFront fw[PR_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpFront& f = fw[w];
+    const uint64_t i0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * CR_RPW;
+    if (i0 >= nreads) return;
+    const unsigned mk = kmask(k);
+    unsigned claimed = 0;
+    uint64_t my_o0 = 0, my_o1 = 0;
+    if (lane < CR_RPW && i0 + lane < nreads) {
+        const uint64_t r = order ? (uint64_t)order[i0 + lane] : i0 + lane;
+        my_o0 = offs[r]; my_o1 = offs[r + 1];
+    }
+    for (int rr = 0; rr < CR_RPW && i0 + rr < nreads; rr++) {
+        const uint64_t o0 = __shfl_sync(FULL, my_o0, rr), o1 = __shfl_sync(FULL, my_o1, rr);
+        const long long L = (long long)(o1 - o0) - 1;            // the record's last byte is its '\n' terminator
+        const long long nwin = L >= k ? L - k + 1 : 0;
+        for (long long seg = 0; seg < nwin; seg += PR_MAXWIN) {
+            const int nseg = (int)min((long long)PR_MAXWIN, nwin - seg);
+            __syncwarp();
+            front_planes(f, recs + (o0 - rec_base) + seg, nseg + k - 1, lane);
+            for (int i = 0; 32 * i < nseg; i += CR_LK) {
+                unsigned long long key[CR_LK], cur[CR_LK];
+                unsigned cnt[CR_LK];
+                Probe pr[CR_LK];
+#pragma unroll
+                for (int u = 0; u < CR_LK; u++) {
+                    const Window wd = front_window(f, 32 * (i + u) + lane, nseg, k, mk, canonical != 0);
+                    key[u] = wd.valid ? wd.key : 0ull;
+                    cnt[u] = 1u;
+                    // a homopolymer run is one k-mer many times over: counted once per round, by its first lane
+                    const bool homo = wd.valid && (wd.f0 == 0u || wd.f0 == mk) && (wd.f1 == 0u || wd.f1 == mk);
+                    if (__any_sync(FULL, homo)) {
+                        const unsigned code = (wd.f0 & 1u) | ((wd.f1 & 1u) << 1);
+#pragma unroll
+                        for (unsigned c = 0; c < 4; c++) {
+                            const unsigned m = __ballot_sync(FULL, homo && code == c);
+                            if (homo && code == c) {
+                                if (lane == __ffs(m) - 1) cnt[u] = (unsigned)__popc(m); else key[u] = 0ull;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CR_LK; u++) {
+                    cur[u] = 0ull;
+                    if (key[u] != 0ull) {
+                        if (probe_home(t.g, key[u], pr[u])) cur[u] = __ldcg(&t.slots[pr[u].base + pr[u].off].key);
+                        else { key[u] = 0ull; atomicExch(t.error, 2); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CR_LK; u++)
+                    if (key[u] != 0ull) {
+                        Slot* sl = table_upsert_slot(t, key[u], pr[u], cur[u], claimed);
+                        if (sl) atomicAdd(&sl->val, cnt[u]);
+                    }
+                __syncwarp();   // lanes leave the probe loops at different times: reconverge before the next rounds
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
+    if (lane == 0 && claimed) atomicAdd(t.n_claimed, (unsigned long long)claimed);
+}
+
+cudaError_t launch_count_reads(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+                               int canonical, TableView t, const uint32_t* d_order, cudaStream_t s) {
+    TimedLaunch timed("k_count_reads", s);
+    if (nreads == 0) return cudaSuccess;
+    const uint64_t per_cta = (uint64_t)PR_WARPS * CR_RPW;
+    k_count_reads<<<(unsigned)((nreads + per_cta - 1) / per_cta), PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k,
+                                                                                        canonical, t, d_order);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
 // locus signature: the smallest strand-symmetric m-mer hash of a read (see LOCUS ORDER at the top of the file)
 // =========================================================================================================
 // m = min(k, 16): long enough to be (nearly) unique to its place in a transcriptome, short enough that a sequencing error
@@ -876,14 +964,19 @@ k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
     const unsigned* words = reinterpret_cast<const unsigned*>(recs);       // record buffers are at least 4-byte aligned
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t t0 = tile * CT_TILE;
-        if (tid == 0) {                            // record of the tile's first byte: last offs[i] <= rec_base + t0
+        if (warp == 0) {                           // record of the tile's first byte: last offs[i] <= rec_base + t0
+            // 32-ary search: every step the lanes probe 32 evenly spaced candidates of [lo, hi) at once, so the answer
+            // takes ~5 dependent loads instead of ~24
             const uint64_t g0 = rec_base + t0;
-            uint64_t lo = 0, hi = nrec;
+            uint64_t lo = 0, hi = nrec;            // invariant: offs[lo] <= g0 < offs[hi]
             while (hi - lo > 1) {
-                const uint64_t mid = (lo + hi) >> 1;
-                if (offs[mid] <= g0) lo = mid; else hi = mid;
+                const uint64_t width = hi - lo;
+                auto cand = [&](int j) { return lo + width * (uint64_t)(j + 1) / 33ull; };      // lo <= cand(j) < hi, ascending
+                const int n = __popc(__ballot_sync(FULL, offs[cand(lane)] <= g0));               // true for a prefix of the lanes
+                const uint64_t nlo = n ? cand(n - 1) : lo, nhi = n < 32 ? cand(n) : hi;
+                lo = nlo; hi = nhi;
             }
-            tile_rec = lo;
+            if (lane == 0) tile_rec = lo;
         }
         for (int g = warp; g < LC_GROUPS; g += CT_THREADS / 32) {
             const uint64_t first = t0 + 128ull * g + 4ull * lane;           // this lane's four bases
