@@ -384,8 +384,11 @@ def main():
               "l2_policy": "inputs (2.0 GB reads, multi-GB table) exceed the 126 MB L2; no flush needed",
               "table_sharding": (f"hash-sharded over {world} GPUs: k-mer log all-to-all (NCCL), shards all-gathered "
                                  f"for the statistics") if world > 1 else "single table",
-              "stats_table": "k-mers with count >= 2 (device-side `jellyfish dump -L 2`, as the normalisation pipeline "
-                             "does; statistics bit-identical)" if min_count == 2 else "full count table",
+              "stats_table": "k-mers with count >= 2 (`jellyfish dump -L 2`, as the normalisation pipeline does: "
+                             "util/insilico_read_normalization.pl:45,641): a count-floor view of the count table on one GPU, "
+                             "compacted + all-gathered shards on several; statistics bit-identical to a rebuilt -L 2 table "
+                             "(asserted in the run)" if min_count == 2 else "full count table",
+              "read_order": "per-read kernels visit the reads in locus order (signature + radix sort inside the timed step)",
               "count_mode": args.count_mode}
 
     if args.impl == "reference":
@@ -427,14 +430,13 @@ def main():
             kc.clear()
             kc.add_records_dev(recs_ptr, nbytes)
 
+        # one GPU: `dump -L 2` is a VIEW of the count table (tg_table_set_count_floor): a k-mer below the floor reads as
+        # absent, which is exactly what the statistics of the rebuilt -L 2 table are -- nothing is materialised.  (Several
+        # GPUs must materialise it: the compacted shards are what is all-gathered.)
+        kc.set_count_floor(min_count)
+
         def query_table():
-            if min_count == 1:
-                return kc
-            if state["q"] is None:
-                state["q"] = kc.compacted(min_count, load=0.40)
-            else:
-                kc.compact_into(min_count, state["q"])
-            return state["q"]
+            return kc
         table_info = kc.info
     else:
         from trinityrnaseq_b200 import sharded
@@ -590,11 +592,16 @@ def main():
     sd_d = ctx.d2h(d_sd, 4 * nreads, np.uint32)
     assert np.array_equal(med_d, med_h) and np.array_equal(sd_d, sd_h.view(np.uint32)), "device vs host path mismatch"
     if min_count > 1 and world == 1:
-        # ... and the `dump -L 2` table must give exactly the statistics of the full table
-        kc.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
+        # ... and the `dump -L 2` VIEW must give exactly the statistics of a materialised -L 2 table (rebuilt on the device
+        # from the count table), with the locus order switched off for the cross-check
+        q2 = kc.compacted(min_count, load=0.40)
+        ctx.set("locus_order", 0)
+        q2.coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
         ctx.sync()
-        assert np.array_equal(ctx.d2h(d_med, 4 * nreads, np.uint32), med_h), "min2 table changed a median"
-        assert np.array_equal(ctx.d2h(d_sd, 4 * nreads, np.uint32), sd_h.view(np.uint32)), "min2 table changed a stdev"
+        ctx.set("locus_order", 1)
+        assert np.array_equal(ctx.d2h(d_med, 4 * nreads, np.uint32), med_h), "-L 2 view != materialised -L 2 table (median)"
+        assert np.array_equal(ctx.d2h(d_sd, 4 * nreads, np.uint32), sd_h.view(np.uint32)), "-L 2 view != materialised -L 2 table (stdev)"
+        q2.close()
 
     r2t = None
     if not args.no_r2t:
@@ -620,7 +627,8 @@ def main():
     count_positions = nreads * nwin
     table_bytes = tinfo["capacity"] * 16 // world
     stage_of = {"k_log_tiles": "count", "k_log_replay": "count", "k_log_refine": "count", "k_flat_tiles<COUNT>": "count",
-                "k_log_plan": "count", "k_rehash": "dump_L2", "k_cov_stats": "stats", "k_cov_stats_long": "stats"}
+                "k_log_plan": "count", "k_rehash": "dump_L2", "k_cov_stats": "stats", "k_cov_stats_long": "stats",
+                "k_locus_tiles": "stats", "locus_sort": "stats"}
     stage_bytes = {"count": count_positions * 64 + nbytes,
                    "dump_L2": table_bytes + qinfo["distinct"] * 64 // world,
                    "stats": count_positions * 32 + nbytes + 12 * nreads}

@@ -236,6 +236,11 @@ int tg_ipc_close(tg_ctx* ctx, void* dptr);
 int tg_count_partition_peers_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins,
                                  uint32_t cap, uint32_t nranks, uint32_t my_rank, void* const* d_owner_keys,
                                  void* d_cursor, void* d_hpoly);
+/* `jellyfish dump -L n` as a VIEW: from now on tg_cov_stats[_dev] on this count table treats every k-mer whose count is
+ * below min_count as absent -- exactly what the statistics of a table rebuilt from `dump -L min_count` are (the
+ * normalisation pipeline's -L 2, util/insilico_read_normalization.pl:45,641), without materialising that table.  Counting,
+ * dump, histo and export are unaffected.  0 or 1 = the whole table. */
+int tg_table_set_count_floor(tg_table* t, uint32_t min_count);
 /* Counting read by read, with the read offsets known (same record buffer + offs as tg_cov_stats_dev): the reads are
  * visited in LOCUS order (neighbouring reads cover the same stretch of a transcript), so the slots their k-mers share stay
  * L2-resident while they are incremented and no k-mer log / partition replay is needed.  Same counts as tg_count_reads_dev. */

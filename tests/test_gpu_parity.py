@@ -381,3 +381,39 @@ def test_count_read_by_read_in_locus_order(oracle, data, canonical, k):
                 gk, gc = kc.dump()
                 np.testing.assert_array_equal(gk, ok)
                 np.testing.assert_array_equal(gc, oc * (2 if mode == "pinned" else 1))
+
+
+@pytest.mark.parametrize("floor", [2, 3])
+def test_count_floor_view_equals_rebuilt_dump_table(gpu_ctx, oracle, data, floor):
+    """tg_table_set_count_floor(n): the statistics read the count table as `jellyfish dump -L n` would leave it, without
+    rebuilding it.  Same medians / means / stdevs / per-window coverage as (a) the oracle's table loaded from the -L n dump and
+    (b) our own materialised -L n table; counting, dump and histo do not see the floor; floor 0 restores the full table."""
+    _, reads = data
+    recs, offs = tg.records_from_sequences(reads)
+    ok, oc = oracle.jf_count(recs, 25, True, floor)
+    okc = oracle.KmerCounter(25, True)
+    for kmer, c in zip(ok, oc):
+        okc.add_kmer(tg.packed_to_kmer(kmer, 25), int(c))
+    om, omean, osd, oper = okc.coverage_stats(recs, offs, capture=True)
+    with tg.KmerCounter(gpu_ctx, 25, is_ds=True) as kc:
+        kc.add_records(recs)
+        full = kc.coverage_stats(recs, offs)
+        kc.set_count_floor(floor)
+        gm, gmean, gsd, gper = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+        np.testing.assert_array_equal(gper, oper)
+        np.testing.assert_array_equal(gm, om)
+        np.testing.assert_array_equal(_f32_bits(gmean), _f32_bits(omean))
+        np.testing.assert_array_equal(_f32_bits(gsd), _f32_bits(osd))
+        q = kc.compacted(floor)
+        qm, qmean, qsd = q.coverage_stats(recs, offs)
+        q.close()
+        np.testing.assert_array_equal(qm, om)
+        np.testing.assert_array_equal(_f32_bits(qsd), _f32_bits(osd))
+        ak, ac = oracle.jf_count(recs, 25, True, 1)
+        gk, gc = kc.dump()                                  # the dump is not a read path of the view
+        np.testing.assert_array_equal(gk, ak)
+        np.testing.assert_array_equal(gc, ac)
+        kc.set_count_floor(0)
+        again = kc.coverage_stats(recs, offs)
+        for a, b in zip(full, again):
+            np.testing.assert_array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))

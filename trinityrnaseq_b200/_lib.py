@@ -64,6 +64,7 @@ SIGNATURES = {
     "tg_table_replay_log_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "tg_log_refine_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32]),
     "tg_log_entry_bytes": (_u32, []),
+    "tg_table_set_count_floor": (_i32, [_vp, _u32]),
     "tg_count_records_dev": (_i32, [_vp, _vp, _vp, _u64, _i32]),
     "tg_records_pin_dev": (_i32, [_vp, _vp, _vp, _u64]),
     "tg_weld_create": (_i32, [_vp, _i32, _vp, _u64, _pp]),

@@ -333,6 +333,10 @@ class KmerCounter(_Table):
         can = self.is_ds if canonical is None else canonical
         check(_lib.lib().tg_count_reads_dev(self._h, d_recs, nbytes, int(can)))
 
+    def set_count_floor(self, min_count):
+        """statistics see the table as `jellyfish dump -L min_count` would leave it (a view; nothing is rebuilt)"""
+        check(_lib.lib().tg_table_set_count_floor(self._h, int(min_count)))
+
     def add_read_records_dev(self, d_recs, d_offs, nreads, canonical=None):
         """count read by read in locus order (tg_count_records_dev): needs the read offsets, no k-mer log"""
         can = self.is_ds if canonical is None else canonical

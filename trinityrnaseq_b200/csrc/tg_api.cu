@@ -155,7 +155,7 @@ static Geo pick_geo(uint64_t slots, size_t part_bytes) {
     Geo g;
     g.nparts = (unsigned)np; g.part0 = 0; g.nlocal = (unsigned)np;
     g.subcap = whole_buckets((slots + np - 1) / np);
-    g.k = 0; g.filter = 0;            // set by table_new / table_regrow
+    g.k = 0; g.floor = 0;            // set by table_new / table_regrow
     return g;
 }
 
@@ -401,7 +401,7 @@ void tg_free(void* p) { free(p); }
 // ---------------------------------------------------------------------------------------------------------
 static int table_new(tg_ctx* c, int kind, int k, Geo g, tg_table** out) {
     tg_table* t = new tg_table();
-    g.k = k; g.filter = kind == TG_TABLE_COUNT ? 1u : 0u;
+    g.k = k; g.floor = 0u;
     if (g.subcap >= (1ull << 34)) return fail(TG_ERR_ARG, "a table partition holds at most 2^34 slots (bucket index is 32-bit)");
     t->ctx = c; t->kind = kind; t->k = k; t->g = g;
     t->cap = (uint64_t)g.nlocal * g.subcap;
@@ -470,6 +470,13 @@ void tg_table_destroy(tg_table* t) {
     delete t;
 }
 
+int tg_table_set_count_floor(tg_table* t, uint32_t min_count) {
+    if (!t) return fail(TG_ERR_ARG, "null table");
+    if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_table_set_count_floor needs a TG_TABLE_COUNT table");
+    t->g.floor = min_count;              // read by the kernels launched from now on (the geometry travels by value)
+    return TG_OK;
+}
+
 int tg_table_clear(tg_table* t) {
     if (!t) return fail(TG_ERR_ARG, "null table");
     tg_ctx* c = t->ctx;
@@ -507,7 +514,7 @@ static int rehash_by_priority(tg_table* t, TableView to, uint32_t min_count) {
 // Move the table into a new geometry (growth).  Both streams must be idle.
 static int table_regrow(tg_table* t, Geo ng) {
     tg_ctx* c = t->ctx;
-    ng.k = t->k; ng.filter = t->g.filter;
+    ng.k = t->k; ng.floor = t->g.floor;
     const uint64_t ncap = (uint64_t)ng.nlocal * ng.subcap;
     Slot* fresh = nullptr;
     int rc;
@@ -834,7 +841,7 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     const uint64_t per_entry = (uint64_t)le_max_run(t->k);
     if (sample == 0) { *est = total * per_entry; return TG_OK; }
     Geo sg;
-    sg.subcap = whole_buckets(sample * per_entry * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1; sg.k = t->k; sg.filter = 1u;
+    sg.subcap = whole_buckets(sample * per_entry * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1; sg.k = t->k; sg.floor = 0u;
     Slot* scratch = nullptr;
     unsigned long long* d_n = nullptr;
     int rc;

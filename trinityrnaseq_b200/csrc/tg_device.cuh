@@ -45,7 +45,7 @@ struct Geo {
     unsigned int part0;          // first partition held by this view
     unsigned int nlocal;         // partitions held by this view (slots[] has nlocal * subcap entries)
     int k;                       // k-mer length of the keys
-    unsigned int filter;         // (reserved)
+    unsigned int floor;          // count tables, read paths: a count below this reads as absent (a `dump -L floor` VIEW of the table)
 };
 
 struct TableView {
@@ -100,17 +100,22 @@ __host__ __device__ __forceinline__ unsigned long long packed_revcomp(unsigned l
     return r;
 }
 
-// Key hash: two 32-bit words from a dozen 32-bit instructions (a 64-bit murmur finalizer costs three times that in IMADs,
-// and every window of every read pays it).  x picks the PARTITION (and so the owner GPU), y the bucket inside it; the
-// two are mixed from different combinations of the key's plane words, so together they carry ~64 bits.
+// Key hash: two 32-bit words from ~16 32-bit instructions (a 64-bit murmur finalizer costs twice that in IMADs, and every
+// window of every read pays it).  x picks the PARTITION (and so the owner GPU and the log bin), y the bucket inside it;
+// both go through the full murmur3 fmix32 (consecutive windows of a read are shifted copies of each other: a weaker mix
+// sends neighbours to correlated bins, which the shared-memory counters of phase 1 feel), from different combinations of
+// the key's plane words, so together they carry ~64 bits.
+__device__ __forceinline__ unsigned fmix32(unsigned x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    return x ^ (x >> 16);
+}
 struct KeyHash { unsigned x, y; };
 __device__ __forceinline__ KeyHash key_hash(unsigned long long key) {
     const unsigned a = (unsigned)key * 0x9E3779B1u, b = (unsigned)(key >> 32) * 0x85EBCA77u;
     KeyHash h;
-    h.x = a + b;
-    h.x ^= h.x >> 15; h.x *= 0x2C1B3C6Du; h.x ^= h.x >> 13;
-    h.y = a ^ __funnelshift_l(b, b, 15);
-    h.y ^= h.y >> 16; h.y *= 0x297A2D39u; h.y ^= h.y >> 15;
+    h.x = fmix32(a + b);
+    h.y = fmix32(a ^ __funnelshift_l(b, b, 15));
     return h;
 }
 // partition of a hash, any partition count.  Nested: with nfine = f * ncoarse, hash_part(h, nfine) / f == hash_part(h, ncoarse)

@@ -838,22 +838,50 @@ cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, ui
     return cudaGetLastError();
 }
 
+// Only a fraction of the slots pass the filter of a compaction pass (and a third are occupied at all): the survivors of a
+// warp's 32 slots are queued in shared memory and re-inserted 32 at a time, so that the probe + CAS + RED sequence always
+// runs on full warps instead of on the few lanes whose slot qualified.
 __global__ void __launch_bounds__(256)
 k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val, uint32_t max_val) {
-    unsigned claimed = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < from_cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+    __shared__ uint4 queue[8][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned claimed = 0, nq = 0;
+    auto insert = [&](const uint4 s) {
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key == 0ull) continue;
         if (is_label) {        // both orientations' labels move with the key
             if (s.z && table_label_max(to, key, false, s.z)) claimed++;
             if (s.w && table_label_max(to, key, true, s.w)) claimed++;
-        } else if (s.z >= min_val && s.z <= max_val) {
+        } else {
             table_update<false>(to, key, s.z, claimed);
         }
+    };
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (from_cap + stride - 1) / stride;
+    for (uint64_t rd = 0; rd < rounds; rd++) {
+        const uint64_t i = rd * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        uint4 s = make_uint4(0u, 0u, 0u, 0u);
+        if (i < from_cap) s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+        const bool keep = (s.x | s.y) != 0u && (is_label || (s.z >= min_val && s.z <= max_val));
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) queue[w][nq + __popc(m & lt)] = s;
+        nq += __popc(m);
+        __syncwarp();
+        if (nq >= 32u) {
+            insert(queue[w][lane]);
+            __syncwarp();
+            nq -= 32u;
+            const bool mv = (unsigned)lane < nq;               // the leftovers move to the front
+            uint4 t2 = make_uint4(0u, 0u, 0u, 0u);
+            if (mv) t2 = queue[w][32 + lane];
+            __syncwarp();
+            if (mv) queue[w][lane] = t2;
+            __syncwarp();
+        }
     }
+    if ((unsigned)lane < nq) insert(queue[w][lane]);
     for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(FULL, claimed, o);
-    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
+    if (lane == 0 && claimed) atomicAdd(to.n_claimed, (unsigned long long)claimed);
 }
 
 cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int is_label, uint32_t min_val,

@@ -239,6 +239,7 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
             if (i0 + u < PER) {
                 const int p = 32 * (i0 + u) + lane;
                 unsigned v = lookup_settle(slots, geo, key[u], ok[u], q[u]).x;
+                if (v < geo.floor) v = 0;          // a `dump -L floor` view: rarer k-mers are not in that table
                 if (v < 1) v = 1;                  // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
                 const bool live = p < nwin;
                 x[i0 + u] = live ? v : 0xFFFFFFFFu;
@@ -411,6 +412,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
         }
         unsigned v = table_lookup(slots, geo, key, ok);
         if (live) {
+            if (v < geo.floor) v = 0;              // a `dump -L floor` view
             if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
             cov[p] = v;
             if (per_kmer) per_kmer[p] = v;
