@@ -490,7 +490,8 @@ def main():
         device_step()
     ms = ctx.timer_stop()
     barrier()
-    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None       # (sampled during the device-timed region only: every nvidia-smi
+    launches = ctx.launch_count() - launches0             # query takes driver locks that the host-synchronous e2e path would feel)
     ms = max_over_ranks(ms)
     value = world * positions_per_step * args.steps / (ms / 1e3)
 
@@ -585,7 +586,6 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * positions_per_step * e2e_steps / e2e_s
-    clocks = sampler.stop() if rank == 0 else None
 
     # parity spot check inside the bench: device-resident and host-buffer paths must agree bit for bit
     med_d = ctx.d2h(d_med, 4 * nreads, np.uint32)

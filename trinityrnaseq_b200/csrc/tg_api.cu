@@ -81,6 +81,7 @@ struct tg_ctx {
     const void* pin_recs = nullptr; const void* pin_offs = nullptr; uint64_t pin_nreads = 0;
     bool locus_order = true;                            // per-read kernels visit the reads in locus order (tg_perread.cu)
     uint64_t locus_min_reads = 1ull << 15;              // ... when a launch has at least this many reads
+    DevBuf est_scratch;                                 // scratch table + counter of estimate_log_distinct (kept: cudaFree would synchronise the device, uploads included)
     DevBuf long_scratch;                                // fixed budget of the device-driven CTA-per-read kernels (*_dev entry points)
     size_t long_scratch_bytes = 64ull << 20;            // reads up to ~2 M windows; longer ones: host-buffer entry points
     cudaEvent_t order[2] = {nullptr, nullptr};          // cross-stream ordering without host syncs
@@ -95,7 +96,7 @@ struct tg_ctx {
         const char* host = nullptr; uint64_t nbytes = 0;
         DevBuf dev; bool uploaded = false;
         DevBuf offs, out_a, out_b, out_c, long_idx;
-        cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+        std::vector<cudaEvent_t> chunk_events;             // one per upload chunk
     } held;
     size_t held_chunk_bytes = 64ull << 20;              // upload granularity of a held buffer (whole tiles)
     KernelTimer timer;                                  // optional per-kernel event timing
@@ -272,12 +273,12 @@ void tg_destroy(tg_ctx* c) {
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
-    c->scratch.release(); c->lut.release(); c->long_scratch.release(); c->locus[0].release(); c->locus[1].release(); c->locus_held.buf.release(); c->locus_pin.buf.release();
+    c->scratch.release(); c->lut.release(); c->long_scratch.release(); c->est_scratch.release(); c->locus[0].release(); c->locus[1].release(); c->locus_held.buf.release(); c->locus_pin.buf.release();
     if (c->locus_held.ready) cudaEventDestroy(c->locus_held.ready);
     if (c->locus_pin.ready) cudaEventDestroy(c->locus_pin.ready);
     c->held.dev.release(); c->held.offs.release(); c->held.out_a.release(); c->held.out_b.release(); c->held.out_c.release();
     c->held.long_idx.release();
-    for (int i = 0; i < 2; i++) if (c->held.chunk_done[i]) cudaEventDestroy(c->held.chunk_done[i]);
+    for (cudaEvent_t e : c->held.chunk_events) cudaEventDestroy(e);
     if (c->d_error) cudaFree(c->d_error);
     if (c->h_long_hdr) cudaFreeHost(c->h_long_hdr);
     for (int i = 0; i < 2; i++) if (c->order[i]) cudaEventDestroy(c->order[i]);
@@ -591,7 +592,7 @@ int tg_table_resize(tg_table* t, uint64_t slots_per_partition) {
     return table_regrow(t, ng);
 }
 
-static int flush_log(tg_table* t);
+static int flush_log(tg_table* t, bool only_stream0 = false);
 
 int tg_table_info(tg_table* t, uint64_t* capacity, uint64_t* distinct) {
     if (!t) return fail(TG_ERR_ARG, "null table");
@@ -842,12 +843,11 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     if (sample == 0) { *est = total * per_entry; return TG_OK; }
     Geo sg;
     sg.subcap = whole_buckets(sample * per_entry * 2 + 1024); sg.nparts = 1; sg.part0 = 0; sg.nlocal = 1; sg.k = t->k; sg.floor = 0u;
-    Slot* scratch = nullptr;
-    unsigned long long* d_n = nullptr;
-    int rc;
-    if ((rc = table_alloc(c, sg.subcap, &scratch))) return rc;
-    CU(cudaMalloc(&d_n, sizeof *d_n));
-    CU(cudaMemsetAsync(d_n, 0, sizeof *d_n, c->stream[0]));
+    if (sg.subcap < MIN_SLOTS) sg.subcap = whole_buckets(MIN_SLOTS);
+    CU(c->est_scratch.ensure(sg.subcap * sizeof(Slot) + 256));
+    Slot* scratch = (Slot*)c->est_scratch.p;
+    unsigned long long* d_n = (unsigned long long*)((char*)c->est_scratch.p + sg.subcap * sizeof(Slot));
+    CU(cudaMemsetAsync(scratch, 0, sg.subcap * sizeof(Slot) + sizeof *d_n, c->stream[0]));
     TableView sv{scratch, sg, d_n, t->d_error};
     CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, ns, 0, nbins, 1, t->log.chunk_start, nullptr, sv, 0,
                          c->sm_count, c->stream[0]));
@@ -855,18 +855,20 @@ static int estimate_log_distinct(tg_table* t, const std::vector<unsigned>& fill,
     unsigned long long d = 0;
     CU(cudaMemcpyAsync(&d, d_n, sizeof d, cudaMemcpyDeviceToHost, c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[0]));
-    cudaFree(scratch); cudaFree(d_n);
     *est = (uint64_t)((double)d * nbins / ns * 1.03) + 65536;
     if (*est > total * per_entry) *est = total * per_entry;
     return TG_OK;
 }
 
 // Apply every pending log entry to the table (growing it first if the log could overfill it).
-static int flush_log(tg_table* t) {
+// only_stream0: everything that fed the log ran on stream 0 and stream 1 is busy with something the flush must not wait
+// for (the uploads of a held buffer).
+static int flush_log(tg_table* t, bool only_stream0) {
     if (!t->log.keys || t->log.pending_ub == 0) return TG_OK;
     tg_ctx* c = t->ctx;
     int rc;
-    if ((rc = sync_all(c))) return rc;
+    if (only_stream0) CU(cudaStreamSynchronize(c->stream[0]));
+    else if ((rc = sync_all(c))) return rc;
     if ((rc = table_refresh(t))) return rc;
     std::vector<unsigned> fill(t->log.nbins);
     CU(cudaMemcpy(fill.data(), t->log.cursor, fill.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
@@ -898,8 +900,6 @@ int tg_records_hold(tg_ctx* c, const char* recs, uint64_t nbytes) {
     c->locus_held.forget();
     if (nbytes == 0) return TG_OK;
     CU(c->held.dev.ensure(padded_record_bytes(nbytes)));
-    for (int i = 0; i < 2; i++)
-        if (!c->held.chunk_done[i]) CU(cudaEventCreateWithFlags(&c->held.chunk_done[i], cudaEventDisableTiming));
     c->held.host = recs; c->held.nbytes = nbytes;
     return TG_OK;
 }
@@ -943,23 +943,27 @@ static int held_stream(tg_ctx* c, Consume consume) {
         }
         return TG_OK;
     }
+    // every upload is queued on stream 1 before the first chunk is consumed: a consumer that blocks the host (a log flush
+    // with its read-backs) then never holds the copies up
     const uint64_t padded = padded_record_bytes(h.nbytes);
     CU(cudaMemsetAsync(dev + h.nbytes, '\n', padded - h.nbytes, c->stream[1]));
     const uint64_t nchunks = (h.nbytes + chunk - 1) / chunk;
-    for (uint64_t i = 0; i <= nchunks; i++) {
-        if (i < nchunks) {
-            const uint64_t pos = i * chunk, n = std::min(chunk, h.nbytes - pos);
-            CU(cudaMemcpyAsync(dev + pos, h.host + pos, n, cudaMemcpyHostToDevice, c->stream[1]));
-            CU(cudaEventRecord(h.chunk_done[i & 1], c->stream[1]));
-        }
-        if (i >= 1) {           // chunk i - 1 is complete together with its halo (chunk i, or the padding after the last one)
-            if (i < nchunks) CU(cudaStreamWaitEvent(c->stream[0], h.chunk_done[i & 1], 0));
-            else CU(cudaStreamWaitEvent(c->stream[0], h.chunk_done[(i - 1) & 1], 0));
-            const uint64_t pos = (i - 1) * chunk;
-            int rc = consume(dev + pos, std::min(chunk, h.nbytes - pos));
-            if (rc) return rc;
-            // (the event slot is re-recorded two uploads later; a wait refers to the record that preceded it)
-        }
+    while (h.chunk_events.size() < nchunks) {
+        cudaEvent_t e = nullptr;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h.chunk_events.push_back(e);
+    }
+    for (uint64_t i = 0; i < nchunks; i++) {
+        const uint64_t pos = i * chunk, n = std::min(chunk, h.nbytes - pos);
+        CU(cudaMemcpyAsync(dev + pos, h.host + pos, n, cudaMemcpyHostToDevice, c->stream[1]));
+        CU(cudaEventRecord(h.chunk_events[i], c->stream[1]));
+    }
+    for (uint64_t i = 0; i < nchunks; i++) {
+        // chunk i is complete together with its halo once chunk i + 1 has arrived (or the padding behind the last one)
+        CU(cudaStreamWaitEvent(c->stream[0], h.chunk_events[std::min(i + 1, nchunks - 1)], 0));
+        const uint64_t pos = i * chunk;
+        int rc = consume(dev + pos, std::min(chunk, h.nbytes - pos));
+        if (rc) return rc;
     }
     h.uploaded = true;
     return TG_OK;
@@ -985,12 +989,33 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
     const uint64_t room = logged ? log_room(t->log) : 0;
     if (is_held(c, recs, nbytes)) {
         // the caller promised the buffer does not change: one device copy, uploaded here (or found in place) and left for
-        // the statistics call that follows
+        // the statistics call that follows.  The log is replayed in SEGMENTS (a quarter of the input each), so that the
+        // table work starts while the upload is still running; only the first segment's flush talks to the host (exact
+        // distinct count so far -> is the table large enough for the rest?), the later ones are stream-ordered.
         if ((rc = sync_all(c))) return rc;
+        const uint64_t seg_bytes = std::max<uint64_t>(nbytes / 4, 256ull << 20);
+        const uint64_t seg_cost = logged ? std::min<uint64_t>(room, log_launch_cost(c, t->log, seg_bytes)) : 0;
+        uint64_t done_bytes = 0, seg_start = 0;
+        bool async_ok = false;
+        uint64_t distinct_at_seg_start = t->distinct_ub;
+        auto flush_segment = [&]() -> int {
+            int r2;
+            if (async_ok) return replay_log_async(t);
+            if ((r2 = flush_log(t, true))) return r2;
+            // the segment [seg_start, done_bytes) added t->distinct_ub - distinct_at_seg_start keys; a later segment of the
+            // same size adds at most about as many new ones (the expressed k-mers are in already).  With 1.5x head-room
+            // on that, does everything fit below the load limit?  Then nobody needs to look again.
+            const uint64_t seg_len = std::max<uint64_t>(done_bytes - seg_start, 1);
+            const double per_byte = (double)(t->distinct_ub - distinct_at_seg_start) / (double)seg_len;
+            const double projected = (double)t->distinct_ub + 1.5 * per_byte * (double)(nbytes - done_bytes);
+            async_ok = projected <= MAX_LOAD * (double)t->cap;
+            seg_start = done_bytes; distinct_at_seg_start = t->distinct_ub;
+            return TG_OK;
+        };
         rc = held_stream(c, [&](const char* d, uint64_t n) -> int {
             int r2;
             if (logged) {
-                if (t->log.pending_ub + log_launch_cost(c, t->log, n) > room && t->log.pending_ub && (r2 = flush_log(t))) return r2;
+                if (t->log.pending_ub && t->log.pending_ub + log_launch_cost(c, t->log, n) > seg_cost && (r2 = flush_segment())) return r2;
                 CU(launch_log_tiles((const uint8_t*)d, n, t->k, canonical, log_view(t), t->view(), c->sm_count, c->stream[0]));
                 t->log.pending_ub += log_launch_cost(c, t->log, n);
             } else {
@@ -998,10 +1023,11 @@ int tg_count_reads(tg_table* t, const char* recs, uint64_t nbytes, int canonical
                 CU(launch_count_tiles((const uint8_t*)d, n, t->k, canonical, t->view(), c->sm_count, c->stream[0]));
             }
             c->launches++;
+            done_bytes += n;
             return TG_OK;
         });
         if (rc) return rc;
-        if (logged && (rc = flush_log(t))) return rc;
+        if (logged && t->log.pending_ub && (rc = flush_segment())) return rc;
         if ((rc = sync_all(c))) return rc;
         return table_refresh(t);
     }
