@@ -456,7 +456,12 @@ def main():
         def table_info():
             return {"capacity": sc.subcap * sc.nparts, "distinct": sc.size()}
 
+    # The reads of a step are declared immutable (pinned) and their locus order is queued first, on the library's second
+    # stream: it is computed -- every step anew -- beside the count, and the statistics wait for it on the device.
+    ctx.records_pin_dev(d_recs, d_offs, nreads)
+
     def device_step():
+        ctx.locus_prepare_dev(K, recompute=True)
         count_dev(d_recs)
         query_table().coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
 

@@ -248,6 +248,10 @@ int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, ui
 /* Declares a device record buffer (+ its offsets) immutable until the next tg_records_pin_dev (NULLs: nothing pinned): the
  * locus order of its reads is then computed once and shared by every *_dev call that is given exactly these pointers. */
 int tg_records_pin_dev(tg_ctx* ctx, const void* d_recs, const void* d_offs, uint64_t nreads);
+/* Queue the locus order of the pinned buffer NOW, on the library's second stream, so that it is computed beside whatever
+ * the first stream does next (the count); later *_dev calls on the pinned buffer wait for it on the device.
+ * recompute != 0: drop a cached order first (a benchmark step that must pay for the order every time). */
+int tg_locus_prepare_dev(tg_ctx* ctx, int k, int recompute);
 int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical,
                      void* d_median, void* d_mean, void* d_stdev);
 int tg_label_bundles_dev(tg_table* t, const void* d_recs, uint64_t nbytes, const void* d_offs, uint64_t nbundles,

@@ -58,6 +58,8 @@ for rep in range(a.reps):
     out["count_by_read"] = {k_: round(v[0], 3) for k_, v in ctx.kernel_times().items()}
     info_by_read = kc.info(); hist_by_read = kc.histo()
     kc.clear()
+    if a.pin:
+        ctx.locus_prepare_dev(K, recompute=True)
     kc.add_records_dev(d_recs, nbytes)
     ctx.sync()
     out["count"] = {k_: round(v[0], 3) for k_, v in ctx.kernel_times().items()}

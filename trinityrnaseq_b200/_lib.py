@@ -67,6 +67,7 @@ SIGNATURES = {
     "tg_table_set_count_floor": (_i32, [_vp, _u32]),
     "tg_count_records_dev": (_i32, [_vp, _vp, _vp, _u64, _i32]),
     "tg_records_pin_dev": (_i32, [_vp, _vp, _vp, _u64]),
+    "tg_locus_prepare_dev": (_i32, [_vp, _i32, _i32]),
     "tg_weld_create": (_i32, [_vp, _i32, _vp, _u64, _pp]),
     "tg_weld_destroy": (None, [_vp]),
     "tg_weld_count_reads": (_i32, [_vp, _vp, _u64]),

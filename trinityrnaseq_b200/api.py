@@ -117,6 +117,10 @@ class Context:
         """declare a device record buffer immutable (its locus order is computed once); no arguments: unpin"""
         check(_lib.lib().tg_records_pin_dev(self._h, d_recs, d_offs, nreads))
 
+    def locus_prepare_dev(self, k, recompute=False):
+        """queue the locus order of the pinned buffer on the second stream (it overlaps the work queued next)"""
+        check(_lib.lib().tg_locus_prepare_dev(self._h, int(k), int(bool(recompute))))
+
     def launch_count(self):
         return int(_lib.lib().tg_launch_count(self._h))
 

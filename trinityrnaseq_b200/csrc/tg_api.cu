@@ -1092,6 +1092,23 @@ int tg_count_reads_dev(tg_table* t, const void* d_recs, uint64_t nbytes, int can
     return TG_OK;
 }
 
+int tg_locus_prepare_dev(tg_ctx* c, int k, int recompute) {
+    if (!c) return fail(TG_ERR_ARG, "null ctx");
+    if (bind(c)) return TG_ERR_CUDA;
+    if (!c->pin_nreads) return fail(TG_ERR_ARG, "tg_locus_prepare_dev: no device record buffer is pinned (tg_records_pin_dev)");
+    // on stream 1, behind everything queued on stream 0 so far (an earlier consumer may still be reading the old order);
+    // the consumers on stream 0 wait for the `ready` event, so the scan and the sort run beside whatever stream 0 does next
+    if (recompute) c->locus_pin.forget();
+    if (!c->order[0]) {
+        CU(cudaEventCreateWithFlags(&c->order[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->order[1], cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(c->order[0], c->stream[0]));
+    CU(cudaStreamWaitEvent(c->stream[1], c->order[0], 0));
+    const uint32_t* ord = nullptr;
+    return locus_order_async(c, 1, (const uint8_t*)c->pin_recs, (const uint64_t*)c->pin_offs, 0, c->pin_nreads, k, &ord);
+}
+
 int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical) {
     if (!t || !d_recs || !d_offs) return fail(TG_ERR_ARG, "tg_count_records_dev: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_records_dev needs a TG_TABLE_COUNT table");
