@@ -458,10 +458,14 @@ def main():
 
     # The reads of a step are declared immutable (pinned) and their locus order is queued first, on the library's second
     # stream: it is computed -- every step anew -- beside the count, and the statistics wait for it on the device.
-    ctx.records_pin_dev(d_recs, d_offs, nreads)
+    if world > 1:
+        ctx.records_pin_dev(d_recs, d_offs, nreads)
 
     def device_step():
-        ctx.locus_prepare_dev(K, recompute=True)
+        if world > 1:
+            # several GPUs: the order is computed on the second stream, in the shadow of the exchange (one GPU: the count
+            # kernels leave no room beside them -- measured: 78.3 ms with, 76.5 ms without -- so the statistics call computes it)
+            ctx.locus_prepare_dev(K, recompute=True)
         count_dev(d_recs)
         query_table().coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
 

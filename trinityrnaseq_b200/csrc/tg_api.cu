@@ -81,6 +81,8 @@ struct tg_ctx {
     const void* pin_recs = nullptr; const void* pin_offs = nullptr; uint64_t pin_nreads = 0;
     bool locus_order = true;                            // per-read kernels visit the reads in locus order (tg_perread.cu)
     uint64_t locus_min_reads = 1ull << 15;              // ... when a launch has at least this many reads
+    int locus_m = 16;                                   // signature = smallest hash over the read's m-mers, m = min(k, locus_m)
+    int stats_arena = 1024;                             // coverage words per warp of k_cov_stats (shared memory vs L1)
     DevBuf est_scratch;                                 // scratch table + counter of estimate_log_distinct (kept: cudaFree would synchronise the device, uploads included)
     DevBuf long_scratch;                                // fixed budget of the device-driven CTA-per-read kernels (*_dev entry points)
     size_t long_scratch_bytes = 64ull << 20;            // reads up to ~2 M windows; longer ones: host-buffer entry points
@@ -374,6 +376,12 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
         c->replay_groups = (unsigned)v;
     } else if (!strcmp(key, "locus_order")) {
         c->locus_order = v != 0;
+    } else if (!strcmp(key, "locus_m")) {
+        if (v < 8 || v > 31) return fail(TG_ERR_ARG, "locus_m out of range (8..31)");
+        c->locus_m = (int)v;
+    } else if (!strcmp(key, "stats_arena")) {
+        if (v < 256 || v > 4096) return fail(TG_ERR_ARG, "stats_arena out of range (256..4096)");
+        c->stats_arena = (int)v;
     } else if (!strcmp(key, "locus_min_reads")) {
         if (v < 0) return fail(TG_ERR_ARG, "locus_min_reads out of range");
         c->locus_min_reads = (uint64_t)v;
@@ -1395,7 +1403,7 @@ static int locus_order_async(tg_ctx* c, int b, const uint8_t* d_recs, const uint
                              int k, const uint32_t** d_order, const void* held_offs_key) {
     *d_order = nullptr;
     if (!c->locus_order || nreads < c->locus_min_reads || nreads > 0x7FFFFFF0ull) return TG_OK;
-    const int m = k < 16 ? k : 16;
+    const int m = k < c->locus_m ? k : c->locus_m;
     tg_ctx::LocusCache* lc = nullptr;
     const void* offs_key = d_offs;
     if (held_offs_key && c->held.uploaded && d_recs == (const uint8_t*)c->held.dev.p) { lc = &c->locus_held; offs_key = held_offs_key; }
@@ -1409,7 +1417,7 @@ static int locus_order_async(tg_ctx* c, int b, const uint8_t* d_recs, const uint
     DevBuf& buf = lc ? lc->buf : c->locus[b];
     CU(buf.ensure(need));
     uint32_t* sig = (uint32_t*)buf.p;
-    CU(launch_read_locus(d_recs, d_offs, rec_base, nreads, k, sig, sig + nreads, c->sm_count, c->stream[b]));
+    CU(launch_read_locus(d_recs, d_offs, rec_base, nreads, m, sig, sig + nreads, c->sm_count, c->stream[b]));
     CU(locus_sort(buf.p, need, nreads, d_order, c->stream[b]));
     c->launches += 2;
     if (lc) {
@@ -1493,7 +1501,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
                 const uint32_t* ord = nullptr;
                 if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord, offs)) return r3;
                 CU(launch_cov_stats(d, d_offs, 0, nreads, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
-                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, ord, c->stream[0]));
+                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, ord, c->stats_arena, c->stream[0]));
                 CU(launch_cov_stats_long_auto(d, d_offs, 0, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
                                               (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, c->long_scratch.p,
                                               c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[0]));
@@ -1545,7 +1553,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
             if ((rc = locus_order_async(c, b, (const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, &ord))) return rc;
             CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
                                 t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
-                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, ord, c->stream[b]));
+                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, ord, c->stats_arena, c->stream[b]));
         } else {
             // k-mers shorter than the warp path's 8 m-mers per k-mer: every read through the CTA-per-read kernel
             int nctas = 0; size_t need = 0;
@@ -1584,7 +1592,7 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     const uint32_t* ord = nullptr;
     if (int rc = locus_order_async(c, b, (const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, &ord)) return rc;
     CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->g,
-                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, ord, c->stream[b]));
+                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, ord, c->stats_arena, c->stream[b]));
     CU(launch_cov_stats_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots, t->g,
                                   (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->long_scratch.p,
                                   c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[b]));

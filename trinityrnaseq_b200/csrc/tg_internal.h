@@ -100,7 +100,7 @@ cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int
 // per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, cudaStream_t s);
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, int arena, cudaStream_t s);
 cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
                                   const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
@@ -130,7 +130,7 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
 cudaError_t launch_count_reads(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                                int canonical, TableView t, const uint32_t* d_order, cudaStream_t s);
 // locus order of the reads (tg_perread.cu, tg_sort.cu): signature per read, then a radix sort of (signature, index)
-cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int m,
                               uint32_t* d_sig, uint32_t* d_idx, int sm_count, cudaStream_t s);
 size_t locus_sort_bytes(uint64_t n);
 cudaError_t locus_sort(void* work, size_t work_bytes, uint64_t n, const uint32_t** d_sorted, cudaStream_t s);

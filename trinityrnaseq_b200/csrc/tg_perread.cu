@@ -170,16 +170,16 @@ __device__ __forceinline__ Window front_window(const WarpFront& f, int p, int nw
 // =========================================================================================================
 // coverage statistics
 // =========================================================================================================
-constexpr int ST_ARENA = 1024;        // coverage words per warp: the reads of one batch
-constexpr int ST_BATCH = 16;          // reads per batch at most
+constexpr int ST_BATCH = 16;          // reads per batch at most (the arena -- coverage words per warp, a launch parameter -- may hold fewer)
 constexpr int ST_RPW = 16;            // consecutive reads handled by one warp
 
 struct StatsWarp {
     WarpFront f;
-    uint32_t cov[ST_ARENA];
     uint32_t b_off[ST_BATCH], b_n[ST_BATCH], b_r[ST_BATCH];
     float b_avg[ST_BATCH];
+    uint32_t cov[1];                  // [arena], the warp's coverage vectors (dynamic shared memory behind the header)
 };
+__host__ __device__ inline size_t stats_warp_bytes(int arena) { return (sizeof(StatsWarp) + (size_t)(arena - 1) * 4 + 15) / 16 * 16; }
 
 // Median of the n values a warp holds in registers (lane l owns x[i] = value 32 i + l; elements past n hold 0xFFFFFFFF,
 // which no pivot below the maximum reaches -- if every value IS 0xFFFFFFFF the answer is that value either way), WITHOUT
@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4)
 k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
             int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
             float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll,
-            const uint32_t* __restrict__ order) {
+            const uint32_t* __restrict__ order, int arena) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    StatsWarp& sw = reinterpret_cast<StatsWarp*>(dyn)[w];
+    StatsWarp& sw = *reinterpret_cast<StatsWarp*>(dyn + (size_t)w * stats_warp_bytes(arena));
     const uint64_t i0 = ((uint64_t)blockIdx.x * PR_WARPS + w) * ST_RPW;      // position in processing order
     if (i0 >= nreads) return;
     const unsigned mk = kmask(k);
@@ -327,7 +327,7 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
             if (lane == 0) { median[r] = 0u; mean[r] = 0.0f; stdev[r] = __int_as_float(0x80000000); }
             continue;
         }
-        if (nb == ST_BATCH || used + nwin > ST_ARENA) { stats_flush(sw, nb, stdev, lane); nb = 0; used = 0; }
+        if (nb == ST_BATCH || used + nwin > (unsigned)arena) { stats_flush(sw, nb, stdev, lane); nb = 0; used = 0; }
         const uint8_t* seq = recs + (o0 - rec_base);
         front_planes(sw.f, seq, L, lane);
         uint32_t med; float mu;
@@ -358,16 +358,18 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
 
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, cudaStream_t s) {
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, int arena,
+                             cudaStream_t s) {
     TimedLaunch timed("k_cov_stats", s);
     if (nreads == 0) return cudaSuccess;
-    const size_t dyn = sizeof(StatsWarp) * PR_WARPS;
+    if (arena < PR_MAXWIN) arena = PR_MAXWIN;              // one read of the warp path must fit
+    const size_t dyn = stats_warp_bytes(arena) * PR_WARPS;
     cudaError_t e = cudaFuncSetAttribute((const void*)k_cov_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     const uint64_t per_cta = (uint64_t)PR_WARPS * ST_RPW;
     const uint64_t blocks = (nreads + per_cta - 1) / per_cta;
     k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
-                                                             d_median, d_mean, d_stdev, d_per_kmer, ll, d_order);
+                                                             d_median, d_mean, d_stdev, d_per_kmer, ll, d_order, arena);
     return cudaGetLastError();
 }
 
@@ -1037,11 +1039,10 @@ k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
     }
 }
 
-cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
+cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int m,
                               uint32_t* d_sig, uint32_t* d_idx, int sm_count, cudaStream_t s) {
     TimedLaunch timed("k_locus_tiles", s);
     if (nreads == 0) return cudaSuccess;
-    const int m = k < 16 ? k : 16;
     cudaError_t e = cudaMemsetAsync(d_sig, 0xFF, nreads * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     k_locus_tiles<<<sm_count * 4, CT_THREADS, 0, s>>>(d_recs, d_offs, nreads, rec_base, m, d_sig, d_idx);
