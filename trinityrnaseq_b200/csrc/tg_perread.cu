@@ -116,7 +116,9 @@ __device__ __forceinline__ void pack_read_planes_warp(const uint8_t* __restrict_
     const unsigned long long a0 = reinterpret_cast<unsigned long long>(seq);
     const int sh = (int)(a0 & 3ull);
     const unsigned* words = reinterpret_cast<const unsigned*>(a0 - (unsigned long long)sh);
-    for (int g = 0; 4 * g <= nch; g++) {
+    // chunks 0 .. nch-1 hold the read.  (A window's funnel shifts may also READ word nch -- never more: the arrays are sized
+    // for it -- but every bit they take from it is masked off: a window ends inside the read.)
+    for (int g = 0; 4 * g < nch; g++) {
         const int first = 128 * g + 4 * lane;                               // index of this lane's first base
         // aligned words covering bytes [first - sh, first - sh + 8)
         const unsigned w0 = first - sh < L ? words[32 * g + lane] : 0x0A0A0A0Au;
