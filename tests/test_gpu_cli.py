@@ -238,3 +238,45 @@ def test_stats_from_real_jellyfish_dump():
     assert r.returncode == 0, r.stderr.decode()
     assert r.stdout == gold("stats_real_jf.expected")
     assert b"done parsing 3000 Kmers, 3000 added" in r.stderr
+
+
+def _gpu_lists():
+    """device lists for TRINITY_GPUS: distinct devices where the box has them, and always the same device twice (two
+    contexts on one GPU exercise the same splitting / replication code on a one-GPU box)"""
+    import torch
+    n = torch.cuda.device_count()
+    lists = ["0,0", "0,0,0"]
+    if n >= 2:
+        lists.append(",".join(str(i) for i in range(min(n, 8))))
+    return lists
+
+
+def test_stats_and_assignment_on_several_gpus(tmp_path):
+    """TRINITY_GPUS=0,1,..: the per-read tools replicate the table on every listed device and split every batch of reads
+    over them (host/multi_gpu.hpp).  Output must be byte-identical to the single-GPU run == the reference's goldens, in
+    all three table modes of the statistics tool (counted from the reads, loaded from a dump, with per-window coverage)
+    and for ReadsToTranscripts with small chunks."""
+    fa = os.path.join(GOLD, "reads.fa")
+    stats = os.path.join(BIN, "fastaToKmerCoverageStats")
+    r2t = os.path.join(BIN, "ReadsToTranscripts")
+    for gl in _gpu_lists():
+        env = dict(ENV, TRINITY_GPUS=gl)
+        r = subprocess.run([stats, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "25", "--DS"], capture_output=True,
+                           env=env, timeout=300)
+        assert r.returncode == 0, (gl, r.stderr.decode()[-2000:])
+        assert r.stdout == gold("stats_DS.expected"), gl
+        r = subprocess.run([stats, "--reads", fa, "--kmers_from_reads", fa, "--capture_coverage_info"], capture_output=True,
+                           env=env, timeout=300)
+        assert r.returncode == 0 and r.stdout == gold("stats_capture.expected"), gl
+        r = subprocess.run([stats, "--reads", fa, "--kmers", os.path.join(GOLD, "kmers_L2.fa"), "--kmer_size", "25", "--DS"],
+                           capture_output=True, env=env, timeout=300)
+        assert r.returncode == 0 and r.stdout == gold("stats_kmers_L2.expected"), gl
+        out = tmp_path / f"r2c_{gl.replace(',', '_')}.out"
+        r = subprocess.run([r2t, "-i", fa, "-f", os.path.join(GOLD, "bundles.fa"), "-o", str(out), "-max_mem_reads", "100",
+                            "-p", "10"], capture_output=True, env=env, timeout=300)
+        assert r.returncode == 0, (gl, r.stderr.decode()[-2000:])
+        assert out.read_bytes() == gold("r2t_p10_chunk100.expected"), gl
+    # a device that does not exist fails loudly (no fallback to fewer GPUs)
+    r = subprocess.run([stats, "--reads", fa, "--kmers_from_reads", fa], capture_output=True, env=dict(ENV, TRINITY_GPUS="0,99"),
+                       timeout=300)
+    assert r.returncode != 0

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "fasta_io.hpp"
+#include "multi_gpu.hpp"
 #include "tg_loader.hpp"
 
 using namespace tgio;
@@ -119,7 +120,8 @@ int main(int argc, char** argv) {
     if (num_threads > 0) fprintf(stderr, "-setting num threads to: %d\n", num_threads);   // accepted; the work is on the GPU
     const int k = 25;
 
-    tg_ctx* ctx = tgh::open_device();
+    tgh::GpuSet gpus;                       // TRINITY_GPUS=0,1,..: every device labels its own copy of the (small) bundle
+    gpus.open();                            // table, the reads of a chunk are split over the devices (multi_gpu.hpp)
     std::string err;
 
     // ---- bundles ----------------------------------------------------------------------------------------
@@ -137,10 +139,13 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < bundle_names.size(); i++)
         component_no[i] = bundle_names[i].size() > 3 ? atoi(bundle_names[i].c_str() + 3) : 0;
 
-    tg_table* table = nullptr;
-    TGC(tg_table_create(ctx, TG_TABLE_LABEL, k, bundles.recs.size() + 1024, &table));
+    std::vector<tg_table*> tables(gpus.size(), nullptr);
     fprintf(stderr, "Assigning kmers to Iworm bundles ... ");
-    TGC(tg_label_bundles(table, bundles.recs.data(), bundles.offs.data(), bundles.count(), 0));
+    tgh::on_every_gpu(gpus.size(), [&](size_t g) -> int {
+        int rc = tg_table_create(gpus.ctx[g], TG_TABLE_LABEL, k, bundles.recs.size() + 1024, &tables[g]);
+        if (rc == TG_OK) rc = tg_label_bundles(tables[g], bundles.recs.data(), bundles.offs.data(), bundles.count(), 0);
+        return rc;
+    });
     fprintf(stderr, "done!\n");
     std::vector<uint8_t> entropy_ok(26 * 26 * 26);
     tg_entropy_table(k, min_kmer_entropy, entropy_ok.data());
@@ -179,8 +184,15 @@ int main(int argc, char** argv) {
         fprintf(stderr, "done.  Read %ld reads.\n", got);
         const size_t n = rb.count();
         best.resize(n); pct.resize(n);
-        TGC(tg_assign_reads(table, rb.recs.data(), rb.offs.data(), n, strand, entropy_ok.data(), best.data(), pct.data(),
-                            nullptr));
+        {
+            const auto ranges = tgh::split_reads_by_bytes(rb.offs.data(), n, gpus.size());
+            tgh::on_every_gpu(gpus.size(), [&](size_t g) -> int {
+                const size_t a = ranges[g].first, b = ranges[g].second;
+                if (a == b) return TG_OK;
+                return tg_assign_reads(tables[g], rb.recs.data(), rb.offs.data() + a, b - a, strand, entropy_ok.data(),
+                                       best.data() + a, pct.data() + a, nullptr);
+            });
+        }
         total_reads_read += n;
         fprintf(stderr, "[%lu] reads analyzed for mapping.\n", total_reads_read);
 
@@ -225,7 +237,7 @@ int main(int argc, char** argv) {
     if (!f) { fprintf(stderr, "cannot write %s\n", rc_file.c_str()); return 1; }
     fprintf(f, "%lu\n", read_count);
     fclose(f);
-    tg_table_destroy(table);
-    tg_destroy(ctx);
+    for (tg_table* t : tables) tg_table_destroy(t);
+    gpus.close();
     return 0;
 }

@@ -12,6 +12,7 @@
 
 #include "fasta_io.hpp"
 #include "par_fasta.hpp"
+#include "multi_gpu.hpp"
 #include "tg_loader.hpp"
 #include "tg_sidecar.hpp"
 
@@ -78,7 +79,9 @@ int main(int argc, char** argv) {
     if (K > 31) { fprintf(stderr, "ERROR: kmer size 32 is not supported by the GPU k-mer table (max 31)\n"); return 1; }
     const bool capture = args.isSet("--capture_coverage_info");
 
-    tg_ctx* ctx = tgh::open_device();
+    tgh::GpuSet gpus;                       // TRINITY_GPUS=0,1,..: the reads of every batch are split over these devices
+    gpus.open();
+    tg_ctx* ctx = gpus.ctx[0];              // the table is built on the first one and replicated (multi_gpu.hpp)
     tg_table* table = nullptr;
     std::string err;
 
@@ -179,6 +182,25 @@ int main(int argc, char** argv) {
             if (!rb.recs.empty()) TGC(tg_count_reads(table, rb.recs.data(), rb.recs.size(), is_DS));
     }
 
+    // ---- several GPUs: every device gets a replica of the (now read-only) table ----------------------------------
+    std::vector<tg_table*> tables(1, table);
+    if (gpus.size() > 1) {
+        uint64_t cap = 0, distinct = 0, n = 0;
+        uint64_t* keys = nullptr; uint32_t* vals = nullptr;
+        TGC(tg_table_info(table, &cap, &distinct));
+        TGC(tg_table_export(table, 0, 0xFFFFFFFFu, 0, 0, &keys, &vals, &n));
+        tables.resize(gpus.size(), nullptr);
+        tgh::on_every_gpu(gpus.size(), [&](size_t g) -> int {
+            if (g == 0) return TG_OK;
+            int rc = tg_table_create(gpus.ctx[g], TG_TABLE_COUNT, K, distinct + 1024, &tables[g]);
+            const uint64_t STEP = 32u << 20;
+            for (uint64_t i = 0; rc == TG_OK && i < n; i += STEP)
+                rc = tg_table_load_pairs(tables[g], keys + i, vals + i, std::min<uint64_t>(STEP, n - i), is_DS);
+            return rc;
+        });
+        tg_free(keys); tg_free(vals);
+    }
+
     // ---- per-read statistics ----------------------------------------------------------------------------
     FileView rv;
     if (!rv.open(reads_file, &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
@@ -262,8 +284,19 @@ int main(int argc, char** argv) {
         if (n == 0) continue;
         jb.median.resize(n); jb.mean.resize(n); jb.stdev.resize(n);
         if (capture) jb.per_kmer.assign(jb.rb.recs.size(), 0);
-        TGC(tg_cov_stats(table, jb.rb.recs.data(), jb.rb.offs.data(), n, is_DS, jb.median.data(), jb.mean.data(), jb.stdev.data(),
-                         capture ? jb.per_kmer.data() : nullptr));
+        if (gpus.size() == 1) {
+            TGC(tg_cov_stats(table, jb.rb.recs.data(), jb.rb.offs.data(), n, is_DS, jb.median.data(), jb.mean.data(), jb.stdev.data(),
+                             capture ? jb.per_kmer.data() : nullptr));
+        } else {
+            // contiguous ranges of the batch's reads, one per GPU; results land at the reads' own positions
+            const auto ranges = tgh::split_reads_by_bytes(jb.rb.offs.data(), n, gpus.size());
+            tgh::on_every_gpu(gpus.size(), [&](size_t g) -> int {
+                const size_t a = ranges[g].first, b = ranges[g].second;
+                if (a == b) return TG_OK;
+                return tg_cov_stats(tables[g], jb.rb.recs.data(), jb.rb.offs.data() + a, b - a, is_DS, jb.median.data() + a,
+                                    jb.mean.data() + a, jb.stdev.data() + a, capture ? jb.per_kmer.data() : nullptr);
+            });
+        }
         for (size_t i = 0; i < n; i++)
             if (jb.rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
                 fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)jb.rb.seq_len(i), jb.rb.seq(i), K);
@@ -275,7 +308,7 @@ int main(int argc, char** argv) {
     if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }
     if (negative) { fprintf(stderr, "ERROR, cannot have negative coverage!!\n"); return 1; }
     fprintf(stderr, "STATS_GENERATION_TIME: %ld seconds.\n", (long)(time(NULL) - start_time));
-    tg_table_destroy(table);
-    tg_destroy(ctx);
+    for (tg_table* t : tables) tg_table_destroy(t);
+    gpus.close();
     return 0;
 }
