@@ -44,7 +44,7 @@ void tg_destroy(tg_ctx* ctx);
 int tg_device_info(tg_ctx* ctx, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes);
 int tg_sync(tg_ctx* ctx);
 /* tg_sync for the table-less log appends of the sharded count (tg_count_partition[_peers]_dev, tg_log_refine_dev): a full
- * bin -- a k-mer or minimizer far hotter than the per-bin head-room allowed for -- is not an error but *overflowed = 1
+ * bin -- a k-mer far hotter than the per-bin head-room allowed for -- is not an error but *overflowed = 1
  * (flag cleared): entries were dropped, so the caller repeats the batch with a larger per-bin capacity.  Every other
  * pending error is returned as by tg_sync. */
 int tg_log_overflow_check(tg_ctx* ctx, int* overflowed);
@@ -75,11 +75,9 @@ void tg_table_destroy(tg_table* t);
 int tg_table_reserve(tg_table* t, uint64_t additional_keys);
 int tg_table_info(tg_table* t, uint64_t* capacity_slots, uint64_t* distinct_keys);
 int tg_table_clear(tg_table* t);     /* stream-ordered (see the device-resident section): no host synchronisation */
-/* Geometry.  A table is `nparts` partitions of `slots_per_partition` slots.  A k-mer lives in the partition chosen by the
- * hash of its MINIMIZER (the smallest-hash (k-7)-mer inside it): its home is slot j of a 128-byte bucket of 8 slots, j = the
- * minimizer's position in the k-mer, so that the consecutive windows of a read fall into neighbouring slots of one bucket;
- * a k-mer whose home slot is taken is placed by its own hash inside the same partition.  slots_per_partition is
- * rounded up to whole buckets.  tg_table_create picks nparts so that one partition fits in L2.  A SHARD holds the contiguous partition
+/* Geometry.  A table is `nparts` partitions of `slots_per_partition` slots.  A k-mer lives in the partition chosen by one
+ * word of its hash and probes linearly, wrapping inside the partition, from the first slot of the 64-byte bucket (4 slots)
+ * chosen by the other word.  slots_per_partition is rounded up to whole buckets.  tg_table_create picks nparts so that one partition fits in L2.  A SHARD holds the contiguous partition
  * range [part0, part0 + nlocal) of the global geometry -- the unit by which the table is split across GPUs
  * (owner(k-mer) = partition / nlocal; prior art: MPIinchworm's `canonical k-mer % NUM_MPI_NODES`,
  * Inchworm/src/mpi_deprecated/MPIinchworm.cpp:1236-1257).  The concatenation of all shards' slot arrays, in rank

@@ -229,9 +229,9 @@ def _oracle_stats(oracle, recs, offs):
 
 
 @pytest.mark.parametrize("k", [5, 7, 8, 9])
-def test_short_kmers_use_the_slow_homes(gpu_ctx, oracle, k):
-    """k < 8 has fewer than 8 m-mers per k-mer: count and statistics go through the per-key home computation (and the
-    CTA-per-read kernel); k = 8, 9 are the first lengths of the fast paths.  Same answers as the oracle."""
+def test_short_kmers(gpu_ctx, oracle, k):
+    """very short k-mers (nearly every window repeats, reads shorter than k, windows of one chunk): count, per-window coverage
+    and statistics equal the oracle's."""
     rng = np.random.default_rng(k)
     txs = synth.transcriptome(rng, 5, mean_len=300, min_len=100, max_len=600)
     reads = synth.reads_from(rng, txs, 400, 60, var_len=True) + [b"A" * 40, b"ACGTN" * 9, b"", b"AC"]

@@ -83,9 +83,8 @@ def test_logged_count_more_partitions_than_log_bins_is_refined(ctx, oracle, data
     ok, oc = oracle.jf_count(recs, k, True, 1)
     assert oc.max() > 20000                                  # the repeat: tens of thousands of occurrences of two k-mers
     ctx.set("count_mode", "log")
-    # 512-slot partitions -> more than a thousand of them.  (A partition receives whole minimizer classes -- half a dozen
-    # k-mers each, dozens with their error variants -- so at this toy size its fill fluctuates far more than a 16-MB
-    # partition's; the table is laid out at half the usual load to keep the smallest partitions from filling up.)
+    # 512-slot partitions -> more than a thousand of them (at this toy size a partition's fill fluctuates far more than a
+    # 16-MB partition's; the table is laid out at half the usual load to keep the smallest partitions from filling up)
     ctx.set("part_bytes", 8 << 10)
     ctx.set("kernel_timing", 1)
     ctx.kernel_times()
@@ -417,11 +416,10 @@ def test_compacted_min2_table_gives_identical_stats(ctx, oracle, data, canonical
             assert q3.size() == int((2 * oc >= 3).sum())
 
 
-def test_displaced_keys_are_found(ctx, oracle):
-    """Minimizer placement under pressure: every single-base variant of a few sequences shares minimizers -- and hence home
-    slots -- with the original, so most variant k-mers are DISPLACED into the key-hashed walk of their partition; absent
-    variants land on flagged home slots too.  Counts, dumps and statistics must stay exact, on a table tight enough that
-    walks are long, through the direct and the logged count path."""
+def test_crowded_buckets_and_long_walks(ctx, oracle):
+    """A table under pressure: every single-base variant of a few sequences, on a table tight enough (load ~0.65) that
+    buckets overflow and walks are long; absent double variants are looked up too.  Counts, dumps and statistics must stay
+    exact through the direct and the logged count path."""
     rng = np.random.default_rng(99)
     base = [synth.ALPHA[rng.integers(0, 4, 120)].tobytes() for _ in range(6)]
     reads = []

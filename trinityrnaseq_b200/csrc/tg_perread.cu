@@ -1025,14 +1025,33 @@ k_locus_tiles(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ off
         if (ab != FULL) {                          // (an m-mer STARTS in this chunk only if the chunk has a base)
             uint64_t rec = tile_rec + before;
             unsigned cur = 0xFFFFFFFFu;
-#pragma unroll 4
-            for (int s = 0; s < 32; s++) {
-                if (s && ((an >> (s - 1)) & 1u)) {                          // position s - 1 ended a record
+            // Candidates: valid m-mers that start with A or C and end with G or T -- a quarter of them, and a property of
+            // the m-mer that its reverse complement shares (rc swaps the two ends and complements them), so the sampled
+            // set is the same on both strands and moves with the sequence, not with the read's start.  The thread walks
+            // the set bits of its 32-position mask: ~8 hashes instead of 32.
+            // bit s of ok_m: the m bases from position s on are all bases = no invalid flag in [s, s + m) of the 64-bit word
+            // cb:ab, by OR-smearing (windows of 2, 4, .. p bits, then two overlapping p-windows cover m)
+            unsigned long long inv = ((unsigned long long)cb << 32) | ab;
+            int p = 1;
+            while (2 * p <= m) { inv |= inv >> p; p *= 2; }
+            inv |= inv >> (m - p);
+            const unsigned ok_m = ~(unsigned)inv;
+            const unsigned first_ac = ~a1;                                          // code A=00, C=01: high bit clear
+            const unsigned last_gt = __funnelshift_r(a1, c1, (unsigned)(m - 1));     // code G=10, T=11: high bit set, at s + m - 1
+            unsigned cand = ok_m & first_ac & last_gt;
+            unsigned ends = an;                    // positions that END a record inside this chunk
+            int done = 0;                          // positions below this have been accounted for record changes
+            while (cand) {
+                const int s = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                // records that ended before position s: flush the running minimum once per record passed
+                const unsigned passed = ends & ((1u << s) - 1u) & ~((1u << done) - 1u);
+                if (passed) {
                     if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);
                     cur = 0xFFFFFFFFu;
-                    rec++;
+                    rec += (unsigned)__popc(passed);
                 }
-                if (__funnelshift_r(ab, cb, s) & mm) continue;
+                done = s;
                 cur = min(cur, locus_hash(__funnelshift_r(a0, c0, s) & mm, __funnelshift_r(a1, c1, s) & mm, m));
             }
             if (cur != 0xFFFFFFFFu) atomicMin(&sig[rec], cur);             // rec < nrec: a valid m-mer lies inside a record

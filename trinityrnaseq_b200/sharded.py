@@ -306,7 +306,7 @@ class ShardedKmerCounter:
         self.profile = None       # set to a dict to collect host-clock milliseconds per phase (syncs around each)
         self._log = None
         self._recv = None
-        self._grow = 1            # per-bin head-room multiplier: doubled whenever a batch overflowed a bin (hot k-mers / minimizers)
+        self._grow = 1            # per-bin head-room multiplier: doubled whenever a batch overflowed a bin (hot k-mers)
         self._fine_grow = 1
         self.overflow_retries = 0
         self._peers = None        # (PeerLogs, cap, (cursor, rcursor, hpoly))
@@ -384,7 +384,7 @@ class ShardedKmerCounter:
         max_windows: an upper bound on the k-mer windows of the buffer when the caller knows one tighter than
         nbytes (fixed-length reads: nreads * (L - k + 1)); it only sizes the exchange buffers.
 
-        Bins are laid out for an even spread plus head-room.  A k-mer (or minimizer) hot enough to overfill its bin on
+        Bins are laid out for an even spread plus head-room.  A k-mer hot enough to overfill its bin on
         any rank -- an adapter dimer in a tenth of the reads, say -- does not fail the batch: the ranks agree that a bin
         overflowed, double the head-room (kept for later batches) and repeat the partition step; nothing has touched the
         table at that point."""
