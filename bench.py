@@ -333,10 +333,16 @@ def cli_end_to_end(sample_recs, read_len, n_small, n_large):
         if n_large > n_small:
             fa2 = os.path.join(td, "large.fa")
             write_sample_fasta(fa2, sample_recs, read_len, n_large)
-            big, t_big = run(ours, fa2)
+            # stdout goes to a file, as in the pipeline (`... > left.fa.K25.stats`, util/insilico_read_normalization.pl:846)
+            stats_path = os.path.join(td, "large.stats")
+            t0 = time.perf_counter()
+            with open(stats_path, "wb") as so:
+                subprocess.run([ours, "--reads", fa2, "--kmers_from_reads", fa2, "--kmer_size", str(K), "--DS"], stdout=so,
+                               stderr=subprocess.DEVNULL, check=True)
+            t_big = time.perf_counter() - t0
             positions = 2 * n_large * (read_len - K + 1)
             out["large"] = {"reads": n_large, "seconds": round(t_big, 3), "value": round(positions / t_big, 1), "unit": UNIT,
-                            "fasta_bytes": os.path.getsize(fa2), "output_bytes": len(big)}
+                            "fasta_bytes": os.path.getsize(fa2), "output_bytes": os.path.getsize(stats_path)}
     return out
 
 

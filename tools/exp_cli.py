@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Whole-process run of the drop-in statistics executable on a configs[1]-shaped FASTA file with TRINITY_GPU_TRACE=1: prints
+the tool's own phase clock (stderr) and the wall time.   python tools/exp_cli.py [--reads N] [--gpus 0,1]"""
+import argparse, os, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import trinityrnaseq_b200 as tg
+from bench import make_transcriptome, write_sample_fasta, SEED, K
+ap = argparse.ArgumentParser()
+ap.add_argument("--reads", type=int, default=20_000_000)
+ap.add_argument("--read-len", type=int, default=100)
+ap.add_argument("--gpus", default="")
+a = ap.parse_args()
+ctx = tg.Context(0)
+tx, tx_offs, tx_cum = make_transcriptome(20000, SEED)
+d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, a.reads // 2, a.read_len, seed=SEED)
+recs = ctx.d2h(d_recs, nbytes, np.uint8).copy()
+ctx.close()
+exe = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "fastaToKmerCoverageStats")
+with tempfile.TemporaryDirectory() as td:
+    fa = os.path.join(td, "reads.fa")
+    write_sample_fasta(fa, recs, a.read_len, a.reads)
+    env = dict(os.environ, TRINITY_GPU_TRACE="1")
+    if a.gpus:
+        env["TRINITY_GPUS"] = a.gpus
+    for rep in range(2):
+        t0 = time.perf_counter()
+        with open(os.path.join(td, "out.stats"), "wb") as so:
+            r = subprocess.run([exe, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", str(K), "--DS"], stdout=so,
+                               stderr=subprocess.PIPE, env=env)
+        dt = time.perf_counter() - t0
+        print(f"rep {rep}: rc {r.returncode}, wall {dt:.3f} s, fasta {os.path.getsize(fa) / 1e9:.2f} GB, out "
+              f"{os.path.getsize(os.path.join(td, 'out.stats')) / 1e9:.2f} GB")
+        print("\n".join(l for l in r.stderr.decode().splitlines() if "[trace]" in l))

@@ -5,6 +5,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <thread>
 #include <string>
@@ -62,6 +63,15 @@ static int fmt_float(char* out, float f) {
     return sprintf(out, "%g", (double)f);
 }
 
+// TRINITY_GPU_TRACE=1: wall-clock seconds of the tool's phases on stderr (where does a whole-process run spend its time?)
+struct Trace {
+    bool on = getenv("TRINITY_GPU_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double acc[4] = {0, 0, 0, 0};                 // parse wait, GPU call, format/write wait, other
+    double now() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    void mark(const char* what) const { if (on) fprintf(stderr, "[trace] %8.3f s  %s\n", now(), what); }
+};
+
 int main(int argc, char** argv) {
     Args args(argc, argv);
     if (args.isSet("--help") || !(args.isSet("--reads") && (args.isSet("--kmers") || args.isSet("--kmers_from_reads")))) {
@@ -79,8 +89,10 @@ int main(int argc, char** argv) {
     if (K > 31) { fprintf(stderr, "ERROR: kmer size 32 is not supported by the GPU k-mer table (max 31)\n"); return 1; }
     const bool capture = args.isSet("--capture_coverage_info");
 
+    Trace trace;
     tgh::GpuSet gpus;                       // TRINITY_GPUS=0,1,..: the reads of every batch are split over these devices
     gpus.open();
+    trace.mark("device context(s) open");
     tg_ctx* ctx = gpus.ctx[0];              // the table is built on the first one and replicated (multi_gpu.hpp)
     tg_table* table = nullptr;
     std::string err;
@@ -182,6 +194,7 @@ int main(int argc, char** argv) {
             if (!rb.recs.empty()) TGC(tg_count_reads(table, rb.recs.data(), rb.recs.size(), is_DS));
     }
 
+    trace.mark("k-mer table loaded / counted");
     // ---- several GPUs: every device gets a replica of the (now read-only) table ----------------------------------
     std::vector<tg_table*> tables(1, table);
     if (gpus.size() > 1) {
@@ -278,12 +291,16 @@ int main(int argc, char** argv) {
     };
     for (unsigned it = 0;; it++) {
         Job& jb = jobs[it & 1];
+        double tt = trace.now();
         finish_job(jb);                          // the job that used this slot two batches ago
+        trace.acc[2] += trace.now() - tt; tt = trace.now();
         if (!parser.next(jb.rb)) break;
+        trace.acc[0] += trace.now() - tt;
         const size_t n = jb.rb.count();
         if (n == 0) continue;
         jb.median.resize(n); jb.mean.resize(n); jb.stdev.resize(n);
         if (capture) jb.per_kmer.assign(jb.rb.recs.size(), 0);
+        tt = trace.now();
         if (gpus.size() == 1) {
             TGC(tg_cov_stats(table, jb.rb.recs.data(), jb.rb.offs.data(), n, is_DS, jb.median.data(), jb.mean.data(), jb.stdev.data(),
                              capture ? jb.per_kmer.data() : nullptr));
@@ -297,6 +314,7 @@ int main(int argc, char** argv) {
                                     jb.mean.data() + a, jb.stdev.data() + a, capture ? jb.per_kmer.data() : nullptr);
             });
         }
+        trace.acc[1] += trace.now() - tt;
         for (size_t i = 0; i < n; i++)
             if (jb.rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
                 fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)jb.rb.seq_len(i), jb.rb.seq(i), K);
@@ -305,6 +323,9 @@ int main(int argc, char** argv) {
     }
     finish_job(jobs[0]);
     finish_job(jobs[1]);
+    if (trace.on) fprintf(stderr, "[trace] statistics loop: waiting for parsed batches %.3f s, GPU calls %.3f s, waiting for format+write %.3f s\n",
+                          trace.acc[0], trace.acc[1], trace.acc[2]);
+    trace.mark("statistics done");
     if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }
     if (negative) { fprintf(stderr, "ERROR, cannot have negative coverage!!\n"); return 1; }
     fprintf(stderr, "STATS_GENERATION_TIME: %ld seconds.\n", (long)(time(NULL) - start_time));
