@@ -3,9 +3,12 @@
 // and the per-read statistics run on the GPU through libtrinity_gpu.
 #include <math.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <map>
 #include <thread>
 #include <string>
@@ -244,8 +247,15 @@ int main(int argc, char** argv) {
         std::vector<std::vector<char>> bufs;
         std::vector<char> negs;
         std::thread formatter;
+        uint64_t ticket = 0;                      // position of the batch in file order
     } jobs[2];
     bool negative = false;
+    // Lines leave in file order, but not through the main thread: the thread that formatted batch i also writes it, as
+    // soon as batch i - 1 is out (a ticket), while the main thread is already running batch i + 1 on the GPU.
+    std::mutex out_mu;
+    std::condition_variable out_cv;
+    uint64_t out_next = 0;
+    bool out_failed = false;
     auto format_job = [&](Job& jb) {
         const RecordBatch& rb = jb.rb;
         const size_t n = rb.count();
@@ -280,15 +290,33 @@ int main(int argc, char** argv) {
             }
         });
     };
-    auto finish_job = [&](Job& jb) {           // wait for its lines and write them
+    auto write_job = [&](Job& jb) {            // (on the job's own thread) its lines, once every earlier batch is out
+        std::unique_lock<std::mutex> lk(out_mu);
+        out_cv.wait(lk, [&] { return out_next == jb.ticket; });
+        lk.unlock();
+        for (size_t w = 0; w < jb.bufs.size(); w++) {
+            const char* p = jb.bufs[w].data();
+            size_t n = jb.bufs[w].size();
+            while (n) {
+                const ssize_t wr = ::write(1, p, n);
+                if (wr < 0) { out_failed = true; break; }
+                p += wr; n -= (size_t)wr;
+            }
+        }
+        lk.lock();
+        out_next = jb.ticket + 1;
+        lk.unlock();
+        out_cv.notify_all();
+    };
+    auto finish_job = [&](Job& jb) {           // wait until its lines are formatted and written
         if (!jb.formatter.joinable()) return;
         jb.formatter.join();
-        for (size_t w = 0; w < jb.bufs.size(); w++) {
-            out.put(jb.bufs[w].data(), jb.bufs[w].size());
+        for (size_t w = 0; w < jb.negs.size(); w++)
             if (jb.negs[w]) negative = true;
-        }
         jb.bufs.clear();
     };
+    if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }     // the header line goes first
+    uint64_t next_ticket = 0;
     for (unsigned it = 0;; it++) {
         Job& jb = jobs[it & 1];
         double tt = trace.now();
@@ -318,18 +346,20 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < n; i++)
             if (jb.rb.seq_len(i) < (size_t)K)     // compute_kmer_coverage :305-310 (note the missing space, as in the reference)
                 fprintf(stderr, "Sequence: %.*sis smaller than %d base pairs, skipping\n", (int)jb.rb.seq_len(i), jb.rb.seq(i), K);
-        finish_job(jobs[(it & 1) ^ 1]);          // the previous batch's lines go out before this batch's (file order)
-        jb.formatter = std::thread([&format_job, &jb] { format_job(jb); });
+        jb.ticket = next_ticket++;
+        jb.formatter = std::thread([&format_job, &write_job, &jb] { format_job(jb); write_job(jb); });
     }
     finish_job(jobs[0]);
     finish_job(jobs[1]);
     if (trace.on) fprintf(stderr, "[trace] statistics loop: waiting for parsed batches %.3f s, GPU calls %.3f s, waiting for format+write %.3f s\n",
                           trace.acc[0], trace.acc[1], trace.acc[2]);
     trace.mark("statistics done");
-    if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }
+    if (out_failed || !out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }
     if (negative) { fprintf(stderr, "ERROR, cannot have negative coverage!!\n"); return 1; }
     fprintf(stderr, "STATS_GENERATION_TIME: %ld seconds.\n", (long)(time(NULL) - start_time));
-    for (tg_table* t : tables) tg_table_destroy(t);
-    gpus.close();
-    return 0;
+    trace.mark("output complete");
+    // Everything is written.  Leave without tearing gigabytes of tables, mappings and buffers down one by one: the
+    // operating system and the driver reclaim them at process exit (this was 0.4 s of a 2.7 s run on a 20 M-read file).
+    fflush(stderr);
+    _exit(0);
 }
