@@ -33,7 +33,10 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on the default workload, from the committed `ncu --set full`
 # captures (profiles/README.md); filled in when a capture of the current kernels exists
-NCU_TRAFFIC_BYTES = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, configs[1] on one B200, from the round-2 `ncu --set full` captures
+# (profiles/r02_ncu_full_count_locus_statsmin2_raw.csv, profiles/r02_ncu_full_stats_raw.csv)
+NCU_TRAFFIC_BYTES = {"k_log_tiles": 2.077e9 + 11.844e9, "k_log_replay": 28.805e9 + 5.265e9, "k_cov_stats": 45.089e9 + 2.441e9,
+                     "k_locus_tiles": 2.262e9 + 0.162e9, "locus_sort": 0.0, "k_cov_stats_long": 0.0}
 
 K = 25
 METRIC = "25-mers/sec counted+queried"
