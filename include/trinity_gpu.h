@@ -239,6 +239,24 @@ int tg_count_partition_peers_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbyte
  * normalisation pipeline's -L 2, util/insilico_read_normalization.pl:45,641), without materialising that table.  Counting,
  * dump, histo and export are unaffected.  0 or 1 = the whole table. */
 int tg_table_set_count_floor(tg_table* t, uint32_t min_count);
+/* ---- routed lookups: statistics against a SHARDED table without a replica (keys out, counts back, 12 B per
+ * lookup; prior art for owner routing: Inchworm/src/mpi_deprecated/MPIinchworm.cpp:519-531,1236-1257) -------------------
+ * requester: tg_query_partition_dev bins the key of every valid window by owner exactly like tg_count_partition_dev bins
+ *   counted k-mers ([nbins][cap] log + cursors) and records, at the same (bin, pos), the window's position in the record
+ *   buffer (d_posidx, u32 [nbins][cap]); the bins travel to their owners (all-to-all);
+ * owner:     tg_query_answer_dev looks the received keys up in its shard -> d_resp, same layout, value or 0; the answers
+ *   travel back;
+ * requester: tg_query_scatter_dev puts every answer at its window's position (d_counts: u32 per byte of the record buffer,
+ *   zeroed by the caller); tg_cov_stats_counts_dev computes the per-read statistics from those counts -- bit-identical
+ *   to tg_cov_stats_dev on a replica (trinityrnaseq_b200/sharded.py: coverage_stats_routed_dev). */
+int tg_query_partition_dev(tg_ctx* ctx, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins, uint32_t cap,
+                           void* d_keys, void* d_cursor, void* d_posidx);
+int tg_query_answer_dev(tg_table* t, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t lp, uint32_t cap,
+                        void* d_resp);
+int tg_query_scatter_dev(tg_ctx* ctx, const void* d_resp, const void* d_posidx, const void* d_cursor, uint32_t nbins, uint32_t cap,
+                         void* d_counts);
+int tg_cov_stats_counts_dev(tg_ctx* ctx, const void* d_recs, const void* d_offs, uint64_t nreads, int k, uint32_t count_floor,
+                            const void* d_counts, void* d_median, void* d_mean, void* d_stdev);
 /* Counting read by read, with the read offsets known (same record buffer + offs as tg_cov_stats_dev): the reads are
  * visited in LOCUS order (neighbouring reads cover the same stretch of a transcript), so the slots their k-mers share stay
  * L2-resident while they are incremented and no k-mer log / partition replay is needed.  Same counts as tg_count_reads_dev. */

@@ -75,6 +75,25 @@ def main():
             np.testing.assert_array_equal(gm, om[r0:r1])
             np.testing.assert_array_equal(gmean.view(np.uint32), omean[r0:r1].view(np.uint32))
             np.testing.assert_array_equal(gsd.view(np.uint32), osd[r0:r1].view(np.uint32))
+    # routed lookups: no replica, keys to the owners and counts back -- the same statistics, also through the -L 2 floor
+    if mine.nbytes:
+        d_offs = ctx.dev_alloc(sub_offs.nbytes)
+        ctx.h2d(d_offs, np.ascontiguousarray(sub_offs, dtype=np.uint64))
+    else:
+        d_offs = ctx.dev_alloc(8)
+    n_mine = r1 - r0
+    d_m, d_a, d_s = ctx.dev_alloc(4 * max(n_mine, 1)), ctx.dev_alloc(4 * max(n_mine, 1)), ctx.dev_alloc(4 * max(n_mine, 1))
+    okc2 = orc.KmerCounter(k, True)                      # what a table rebuilt from `dump -L 3` answers
+    for key, c in zip(ok.tolist(), oc.tolist()):
+        if 2 * c >= 3:
+            okc2.add_kmer(tg.packed_to_kmer(key, k), 2 * c)
+    om3, omean3, osd3 = okc2.coverage_stats(recs, offs)
+    for min_count, (wm, wmean, wsd) in ((1, (om, omean, osd)), (3, (om3, omean3, osd3))):
+        sc.coverage_stats_routed_dev(d, mine.nbytes, d_offs, n_mine, d_m, d_a, d_s, min_count=min_count)
+        if n_mine:
+            np.testing.assert_array_equal(ctx.d2h(d_m, 4 * n_mine, np.uint32), wm[r0:r1])
+            np.testing.assert_array_equal(ctx.d2h(d_a, 4 * n_mine, np.uint32), wmean[r0:r1].view(np.uint32))
+            np.testing.assert_array_equal(ctx.d2h(d_s, 4 * n_mine, np.uint32), wsd[r0:r1].view(np.uint32))
     sc.close()
     dist.barrier()
     if rank == 0:

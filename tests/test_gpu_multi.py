@@ -29,6 +29,14 @@ def _run(world, exchange, fold, coarse, nreads=6000):
     assert r.returncode == 0 and "MP_SHARDED_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-6000:])
 
 
+def test_sharded_world1_collectives_and_routed_lookups():
+    """one rank (runs on a one-GPU box too): the whole sharded code path -- log exchange through NCCL collectives, replica,
+    and the ROUTED lookups (keys out, counts back, statistics from counts) -- against the oracle"""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    _run(1, "collective", 0, 0, nreads=4000)
+
+
 @pytest.mark.parametrize("exchange,fold,coarse", [("peer", 0, 0), ("peer", 1, 2), ("collective", 0, 0), ("collective", 1, 1)])
 def test_sharded_world2(exchange, fold, coarse):
     if _ngpu() < 2:

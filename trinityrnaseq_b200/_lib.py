@@ -65,6 +65,10 @@ SIGNATURES = {
     "tg_log_refine_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32]),
     "tg_log_entry_bytes": (_u32, []),
     "tg_table_set_count_floor": (_i32, [_vp, _u32]),
+    "tg_query_partition_dev": (_i32, [_vp, _vp, _u64, _i32, _i32, _u32, _u32, _vp, _vp, _vp]),
+    "tg_query_answer_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "tg_query_scatter_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "tg_cov_stats_counts_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _u32, _vp, _vp, _vp, _vp]),
     "tg_count_records_dev": (_i32, [_vp, _vp, _vp, _u64, _i32]),
     "tg_records_pin_dev": (_i32, [_vp, _vp, _vp, _u64]),
     "tg_locus_prepare_dev": (_i32, [_vp, _i32, _i32]),

@@ -1182,6 +1182,69 @@ int tg_count_partition_peers_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes,
 }
 
 // owner-side split of a received coarse log into the table's partitions (see k_log_refine)
+// ---- routed lookups (multi-GPU statistics against a sharded table that is NOT replicated) -------------------------------
+// requester: keys binned by owner like counted k-mers (same bins, same log layout), return addresses kept locally
+int tg_query_partition_dev(tg_ctx* c, const void* d_recs, uint64_t nbytes, int k, int canonical, uint32_t nbins, uint32_t cap,
+                           void* d_keys, void* d_cursor, void* d_posidx) {
+    if (!c || !d_recs || !d_keys || !d_cursor || !d_posidx) return fail(TG_ERR_ARG, "tg_query_partition_dev: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (nbins == 0 || nbins > LOG_MAX_BINS || cap == 0 || cap > LOG_CAP_MAX)
+        return fail(TG_ERR_ARG, "tg_query_partition_dev: bad log shape (1..%u bins, capacity at most %u)", LOG_MAX_BINS, LOG_CAP_MAX);
+    if (nbytes > 0xFFFF0000ull) return fail(TG_ERR_ARG, "tg_query_partition_dev: at most 4 GiB of records per call");
+    if (bind(c)) return TG_ERR_CUDA;
+    LogView lg = local_log_view((LogEntry*)d_keys, (unsigned int*)d_cursor, nbins, cap, c->d_error, nullptr);
+    lg.posidx = (unsigned int*)d_posidx;
+    TableView none{nullptr, Geo{0, 1, 0, 1, k, 0u}, nullptr, nullptr};
+    CU(launch_log_tiles((const uint8_t*)d_recs, nbytes, k, canonical, lg, none, c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+// owner: received keys [nsrc][lp][cap] (lp = bins this rank owns) -> d_resp, same layout, the table's value or 0
+int tg_query_answer_dev(tg_table* t, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t lp, uint32_t cap,
+                        void* d_resp) {
+    if (!t || !d_keys || !d_cursor || !d_resp) return fail(TG_ERR_ARG, "tg_query_answer_dev: null argument");
+    tg_ctx* c = t->ctx;
+    if (bind(c)) return TG_ERR_CUDA;
+    if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }
+    CU(launch_query_answer((const unsigned long long*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, lp, t->slots, t->g,
+                           (unsigned int*)d_resp, c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+// requester: answers (its own log layout [nbins][cap]) -> d_counts[position of the window in the record buffer]
+int tg_query_scatter_dev(tg_ctx* c, const void* d_resp, const void* d_posidx, const void* d_cursor, uint32_t nbins, uint32_t cap,
+                         void* d_counts) {
+    if (!c || !d_resp || !d_posidx || !d_cursor || !d_counts) return fail(TG_ERR_ARG, "tg_query_scatter_dev: null argument");
+    if (bind(c)) return TG_ERR_CUDA;
+    CU(launch_query_scatter((const unsigned int*)d_resp, (const unsigned int*)d_posidx, (const unsigned int*)d_cursor, nbins, cap,
+                            (unsigned int*)d_counts, c->sm_count, c->stream[0]));
+    c->launches++;
+    return TG_OK;
+}
+// median / mean / stdev of every read from counts that sit at the windows' positions (u32 per byte of the record buffer,
+// 0 = absent or never asked); count_floor as in tg_table_set_count_floor
+int tg_cov_stats_counts_dev(tg_ctx* c, const void* d_recs, const void* d_offs, uint64_t nreads, int k, uint32_t count_floor,
+                            const void* d_counts, void* d_median, void* d_mean, void* d_stdev) {
+    if (!c || !d_recs || !d_offs || !d_counts || !d_median || !d_mean || !d_stdev)
+        return fail(TG_ERR_ARG, "tg_cov_stats_counts_dev: null argument");
+    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_cov_stats_counts_dev: at most 2^31 reads per call");
+    if (bind(c)) return TG_ERR_CUDA;
+    const int b = 0;
+    CU(c->long_idx[b].ensure(nreads * 4));
+    CU(c->long_scratch.ensure(c->long_scratch_bytes));
+    CU(cudaMemsetAsync(c->d_long_hdr[b], 0, 2 * sizeof(unsigned int), c->stream[b]));
+    LongList ll{c->d_long_hdr[b], c->d_long_hdr[b] + 1, (unsigned int*)c->long_idx[b].p};
+    Geo g{0, 1, 0, 1, k, count_floor};
+    CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, k, 1, nullptr, g, (uint32_t*)d_median,
+                        (float*)d_mean, (float*)d_stdev, nullptr, ll, nullptr, c->stats_arena, (const uint32_t*)d_counts, c->stream[b]));
+    CU(launch_cov_stats_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, k, 1, nullptr, g, (uint32_t*)d_median,
+                                  (float*)d_mean, (float*)d_stdev, nullptr, ll, c->long_scratch.p, c->long_scratch_bytes, c->d_error,
+                                  c->sm_count * 2, c->stream[b], (const uint32_t*)d_counts));
+    c->launches += 2;
+    return TG_OK;
+}
+
 int tg_log_refine_dev(tg_ctx* c, const void* d_keys, const void* d_cursor, uint32_t nsrc, uint32_t ncoarse, uint32_t cap,
                       void* d_out_keys, void* d_out_cursor, uint32_t nfine, uint32_t out_cap, uint32_t fine0,
                       uint32_t nfine_global) {
@@ -1501,7 +1564,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
                 const uint32_t* ord = nullptr;
                 if (int r3 = locus_order_async(c, 0, d, d_offs, 0, nreads, t->k, &ord, offs)) return r3;
                 CU(launch_cov_stats(d, d_offs, 0, nreads, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
-                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, ord, c->stats_arena, c->stream[0]));
+                                    (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, ord, c->stats_arena, nullptr, c->stream[0]));
                 CU(launch_cov_stats_long_auto(d, d_offs, 0, t->k, canonical, t->slots, t->g, (uint32_t*)c->held.out_a.p,
                                               (float*)c->held.out_b.p, (float*)c->held.out_c.p, nullptr, ll, c->long_scratch.p,
                                               c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[0]));
@@ -1553,7 +1616,7 @@ int tg_cov_stats(tg_table* t, const char* recs, const uint64_t* offs, uint64_t n
             if ((rc = locus_order_async(c, b, (const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, &ord))) return rc;
             CU(launch_cov_stats((const uint8_t*)c->recs[b].p, (const uint64_t*)c->offs[b].p, base, m, t->k, canonical,
                                 t->slots, t->g, (uint32_t*)c->out_a[b].p, (float*)c->out_b[b].p, (float*)c->out_c[b].p,
-                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, ord, c->stats_arena, c->stream[b]));
+                                per_kmer ? (uint32_t*)c->per_kmer[b].p : nullptr, ll, ord, c->stats_arena, nullptr, c->stream[b]));
         } else {
             // k-mers shorter than the warp path's 8 m-mers per k-mer: every read through the CTA-per-read kernel
             int nctas = 0; size_t need = 0;
@@ -1592,7 +1655,7 @@ int tg_cov_stats_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64
     const uint32_t* ord = nullptr;
     if (int rc = locus_order_async(c, b, (const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, &ord)) return rc;
     CU(launch_cov_stats((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, t->k, canonical, t->slots, t->g,
-                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, ord, c->stats_arena, c->stream[b]));
+                        (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, ord, c->stats_arena, nullptr, c->stream[b]));
     CU(launch_cov_stats_long_auto((const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, t->k, canonical, t->slots, t->g,
                                   (uint32_t*)d_median, (float*)d_mean, (float*)d_stdev, nullptr, ll, c->long_scratch.p,
                                   c->long_scratch_bytes, c->d_error, c->sm_count * 2, c->stream[b]));

@@ -319,6 +319,8 @@ struct LogView {
     unsigned int src;           // this rank = the segment it writes in every owner's log
     int* error;                 // device flag raised (3) when a bin overflows and there is no table to fall back to
     unsigned long long* hpoly;  // [8] homopolymer side channel
+    unsigned int* posidx;       // QUERY logs only: [nbins][cap] LOCAL, the record-buffer position of the window whose key went
+                                // to (bin, pos) -- the return address of the routed lookup
 };
 
 // ---- TMA (1-D bulk async copy) + mbarrier wrappers -----------------------------------------------------

@@ -100,7 +100,8 @@ cudaError_t launch_rehash(const Slot* from, uint64_t from_cap, TableView to, int
 // per-read coverage statistics; offs are absolute offsets into the host buffer, rec_base is the offset of d_recs[0]
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
-                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, int arena, cudaStream_t s);
+                             float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, int arena,
+                             const uint32_t* d_counts /* nullable: counts per window position, looked up elsewhere */, cudaStream_t s);
 cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k, int canonical,
                                   const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean, float* d_stdev,
                                   uint32_t* d_per_kmer, const unsigned int* d_long_idx, unsigned int n_long,
@@ -111,7 +112,7 @@ size_t cov_stats_long_scratch_bytes(unsigned int max_win, int k, int nctas);
 cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k,
                                        int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                                        float* d_stdev, uint32_t* d_per_kmer, LongList ll, void* d_scratch,
-                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s);
+                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s, const uint32_t* d_counts = nullptr);
 
 cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                           int strand, const Slot* slots, Geo geo, const uint8_t* d_entropy_ok,
@@ -129,6 +130,11 @@ cudaError_t launch_assign_long_auto(const uint8_t* d_recs, const uint64_t* d_off
 // counting read by read, in the given order (tg_perread.cu): one ld.cg + RED.ADD per window straight into the table
 cudaError_t launch_count_reads(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                                int canonical, TableView t, const uint32_t* d_order, cudaStream_t s);
+// routed lookups (multi-GPU statistics without a replica): owner side and the way back (tg_kernels.cu)
+cudaError_t launch_query_answer(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                                unsigned lp, const Slot* slots, Geo geo, unsigned int* d_resp, int sm_count, cudaStream_t s);
+cudaError_t launch_query_scatter(const unsigned int* d_resp, const unsigned int* d_posidx, const unsigned int* d_cursor,
+                                 unsigned nbins, unsigned cap, unsigned int* d_cov, int sm_count, cudaStream_t s);
 // locus order of the reads (tg_perread.cu, tg_sort.cu): signature per read, then a radix sort of (signature, index)
 cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int m,
                               uint32_t* d_sig, uint32_t* d_idx, int sm_count, cudaStream_t s);

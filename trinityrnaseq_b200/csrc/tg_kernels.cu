@@ -254,17 +254,23 @@ __device__ __forceinline__ unsigned long long window_key(unsigned f0, unsigned f
     return key;
 }
 
+// QUERY = the same partitioning for ROUTED LOOKUPS (multi-GPU statistics against a sharded table that is not replicated):
+// every valid window's key travels to its owner like a counted k-mer does -- homopolymers included, a lookup has no side
+// channel -- and the position of the window in the record buffer is kept locally in lg.posidx at the same (bin, pos): the
+// owner's answers come back in the log's layout and are scattered to those positions.
+template <bool QUERY>
 __global__ void __launch_bounds__(LT_THREADS, 2)
 k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canonical, LogView lg, TableView t) {
     __shared__ LogSmem sm;
     extern __shared__ __align__(16) unsigned char dyn[];
-    // dynamic: skey[LT_TILE] u64 | delta[nbins] u32 | sbin[LT_TILE] u16 | cnt16[nbins2] u16 | off16[nbins2] u16
+    // dynamic: skey[LT_TILE] u64 | delta[nbins] u32 | sbin[LT_TILE] u16 | cnt16[nbins2] u16 | off16[nbins2] u16 | QUERY: spos[LT_TILE] u16
     const unsigned nbins = lg.nbins, nbins2 = (nbins + 1u) & ~1u;
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(dyn);
     unsigned int* delta = reinterpret_cast<unsigned int*>(skey + LT_TILE);
     unsigned short* sbin = reinterpret_cast<unsigned short*>(delta + nbins);
     unsigned short* cnt16 = sbin + LT_TILE;
     unsigned short* off16 = cnt16 + nbins2;
+    unsigned short* spos = off16 + nbins2;
     unsigned int* cnt32 = reinterpret_cast<unsigned int*>(cnt16);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -319,7 +325,7 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
             const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
             const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
             const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-            const bool homo = (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
+            const bool homo = !QUERY && (f0 == 0u || f0 == mk) && (f1 == 0u || f1 == mk);
             unsigned m = 0xFFFFFFFFu;
             if (!bad) {
                 if (homo) {
@@ -377,6 +383,7 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
                 const unsigned idx = off16[bin] + (m & 0xFFFu);
                 skey[idx] = window_key(f0, f1, k, canonical);
                 sbin[idx] = (unsigned short)bin;
+                if (QUERY) spos[idx] = (unsigned short)(tid * LT_WIN + j);
             }
         }
         __syncthreads();
@@ -391,7 +398,8 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
                 // bin -> (owner, bin inside the owner); the store lands in local HBM or, over NVLink, in the owner's log
                 const unsigned o = bin >> lg.lp_shift, lb = bin - (o << lg.lp_shift);
                 sm.seg[o][(unsigned long long)lb * lg.cap + pos] = key;
-            } else if (t.slots) {      // bin full: count this occurrence directly
+                if (QUERY) lg.posidx[(unsigned long long)bin * lg.cap + pos] = (unsigned)(tile * LT_TILE + spos[i]);
+            } else if (!QUERY && t.slots) {      // bin full: count this occurrence directly
                 table_update<false>(t, key, 1u, claimed);
             } else {
                 atomicExch(lg.error, 3);
@@ -417,9 +425,9 @@ k_log_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canoni
     }
 }
 
-size_t log_tiles_smem_bytes(unsigned nbins) {
+size_t log_tiles_smem_bytes(unsigned nbins, bool query) {
     const unsigned nbins2 = (nbins + 1u) & ~1u;
-    return (size_t)LT_TILE * 8 + (size_t)nbins * 4 + (size_t)LT_TILE * 2 + (size_t)nbins2 * 2 * 2;
+    return (size_t)LT_TILE * 8 + (size_t)nbins * 4 + (size_t)LT_TILE * 2 + (size_t)nbins2 * 2 * 2 + (query ? (size_t)LT_TILE * 2 : 0);
 }
 
 cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int canonical, LogView lg, TableView t,
@@ -428,15 +436,76 @@ cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int 
     if (nbytes == 0) return cudaSuccess;
     if (lg.nbins > LOG_MAX_BINS) return cudaErrorInvalidValue;
     const uint64_t ntiles = (nbytes + LT_TILE - 1) / LT_TILE;
-    const size_t dyn = log_tiles_smem_bytes(lg.nbins);
-    cudaError_t e = cudaFuncSetAttribute((const void*)k_log_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    const bool query = lg.posidx != nullptr;
+    if (query && nbytes > 0xFFFF0000ull) return cudaErrorInvalidValue;      // return addresses are 32-bit buffer positions
+    const size_t dyn = log_tiles_smem_bytes(lg.nbins, query);
+    const void* kern = query ? (const void*)k_log_tiles<true> : (const void*)k_log_tiles<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_log_tiles, LT_THREADS, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LT_THREADS, dyn);
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)per_sm * sm_count;
     if (grid > ntiles) grid = ntiles;
-    k_log_tiles<<<(unsigned)grid, LT_THREADS, dyn, s>>>(d_recs, ntiles, k, canonical, lg, t);
+    if (query) k_log_tiles<true><<<(unsigned)grid, LT_THREADS, dyn, s>>>(d_recs, ntiles, k, canonical, lg, t);
+    else k_log_tiles<false><<<(unsigned)grid, LT_THREADS, dyn, s>>>(d_recs, ntiles, k, canonical, lg, t);
+    return cudaGetLastError();
+}
+
+// ---- routed lookups, owner side and way back -------------------------------------------------------------------
+// k_query_answer: the owner's receive log [nsrc][lp][cap] of QUERY keys -> resp[same layout] = the table's value (0 = absent).
+// Segments are visited bin-major (all sources of a bin together), so that the CTAs in flight probe the partitions of a few
+// neighbouring bins and those stay in L2 -- the replay's trick, without its counters.
+__global__ void __launch_bounds__(256)
+k_query_answer(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ cursor, unsigned cap, unsigned nsrc,
+               unsigned lp, const Slot* __restrict__ slots, Geo geo, unsigned int* __restrict__ resp) {
+    constexpr unsigned CHUNK = 2048;
+    const unsigned chunks_per_seg = (cap + CHUNK - 1) / CHUNK;
+    const unsigned long long nwork = (unsigned long long)nsrc * lp * chunks_per_seg;
+    for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const unsigned chunk = (unsigned)(w % chunks_per_seg);
+        const unsigned long long sb = w / chunks_per_seg;              // bin-major: sb = bin * nsrc + src
+        const unsigned src = (unsigned)(sb % nsrc), bin = (unsigned)(sb / nsrc);
+        const unsigned seg = src * lp + bin;
+        const unsigned n = min(cursor[seg], cap);
+        const unsigned i0 = chunk * CHUNK;
+        if (i0 >= n) continue;
+        const unsigned long long base = (unsigned long long)seg * cap;
+        for (unsigned i = i0 + threadIdx.x; i < min(i0 + CHUNK, (n + 31u) & ~31u); i += 256) {       // whole warps: the lookup is convergent
+            const bool live = i < n;
+            const unsigned long long key = live ? __ldcs(&keys[base + i]) : 0ull;
+            const unsigned v = table_lookup(slots, geo, key, live && key != 0ull);
+            if (live) resp[base + i] = v;
+        }
+    }
+}
+// k_query_scatter: answers back at the requester, in ITS log layout [nbins][cap] -> cov[position of the window]
+__global__ void __launch_bounds__(256)
+k_query_scatter(const unsigned int* __restrict__ resp, const unsigned int* __restrict__ posidx, const unsigned int* __restrict__ cursor,
+                unsigned nbins, unsigned cap, unsigned int* __restrict__ cov) {
+    constexpr unsigned CHUNK = 4096;
+    const unsigned chunks_per_bin = (cap + CHUNK - 1) / CHUNK;
+    const unsigned long long nwork = (unsigned long long)nbins * chunks_per_bin;
+    for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const unsigned bin = (unsigned)(w / chunks_per_bin), i0 = (unsigned)(w % chunks_per_bin) * CHUNK;
+        const unsigned n = min(cursor[bin], cap);
+        const unsigned long long base = (unsigned long long)bin * cap;
+        for (unsigned i = i0 + threadIdx.x; i < min(i0 + CHUNK, n); i += 256) cov[posidx[base + i]] = resp[base + i];
+    }
+}
+
+cudaError_t launch_query_answer(const unsigned long long* d_keys, const unsigned int* d_cursor, unsigned cap, unsigned nsrc,
+                                unsigned lp, const Slot* slots, Geo geo, unsigned int* d_resp, int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_query_answer", s);
+    if (nsrc == 0 || lp == 0 || cap == 0) return cudaSuccess;
+    k_query_answer<<<sm_count * 8, 256, 0, s>>>(d_keys, d_cursor, cap, nsrc, lp, slots, geo, d_resp);
+    return cudaGetLastError();
+}
+cudaError_t launch_query_scatter(const unsigned int* d_resp, const unsigned int* d_posidx, const unsigned int* d_cursor,
+                                 unsigned nbins, unsigned cap, unsigned int* d_cov, int sm_count, cudaStream_t s) {
+    TimedLaunch timed("k_query_scatter", s);
+    if (nbins == 0 || cap == 0) return cudaSuccess;
+    k_query_scatter<<<sm_count * 8, 256, 0, s>>>(d_resp, d_posidx, d_cursor, nbins, cap, d_cov);
     return cudaGetLastError();
 }
 

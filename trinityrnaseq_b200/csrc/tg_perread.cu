@@ -219,7 +219,8 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
 // loads of LK rounds (LK x 32 windows) are issued back to back before any of them is examined.
 template <int PER>
 __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, int nwin, int k,
-                                           unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean) {
+                                           unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean,
+                                           const uint32_t* __restrict__ pre) {
     constexpr int LK = PER <= 3 ? 3 : 2;           // rounds in flight (registers: longer reads keep more values)
     unsigned x[PER];
     unsigned mn = 0xFFFFFFFFu, mx = 0u;
@@ -229,18 +230,22 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
         unsigned long long key[LK];
         bool ok[LK];
         LookupIssue q[LK];
+        if (!pre) {
 #pragma unroll
-        for (int u = 0; u < LK; u++)
-            if (i0 + u < PER) {
-                const Window w = front_window(sw.f, 32 * (i0 + u) + lane, nwin, k, mk, canonical);
-                key[u] = w.key; ok[u] = w.valid;
-                q[u] = lookup_issue(slots, geo, key[u], ok[u]);
-            }
+            for (int u = 0; u < LK; u++)
+                if (i0 + u < PER) {
+                    const Window w = front_window(sw.f, 32 * (i0 + u) + lane, nwin, k, mk, canonical);
+                    key[u] = w.key; ok[u] = w.valid;
+                    q[u] = lookup_issue(slots, geo, key[u], ok[u]);
+                }
+        }
 #pragma unroll
         for (int u = 0; u < LK; u++)
             if (i0 + u < PER) {
                 const int p = 32 * (i0 + u) + lane;
-                unsigned v = lookup_settle(slots, geo, key[u], ok[u], q[u]).x;
+                // (pre: the counts were looked up elsewhere -- routed to the shards that own the k-mers -- and wait at the
+                // windows' positions; a window that was never sent holds 0)
+                unsigned v = pre ? (p < nwin ? pre[p] : 0u) : lookup_settle(slots, geo, key[u], ok[u], q[u]).x;
                 if (v < geo.floor) v = 0;          // a `dump -L floor` view: rarer k-mers are not in that table
                 if (v < 1) v = 1;                  // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
                 const bool live = p < nwin;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4)
 k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
             int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
             float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer, LongList ll,
-            const uint32_t* __restrict__ order, int arena) {
+            const uint32_t* __restrict__ order, int arena, const uint32_t* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     StatsWarp& sw = *reinterpret_cast<StatsWarp*>(dyn + (size_t)w * stats_warp_bytes(arena));
@@ -331,17 +336,18 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
         }
         if (nb == ST_BATCH || used + nwin > (unsigned)arena) { stats_flush(sw, nb, stdev, lane); nb = 0; used = 0; }
         const uint8_t* seq = recs + (o0 - rec_base);
-        front_planes(sw.f, seq, L, lane);
+        const uint32_t* pre = counts ? counts + (o0 - rec_base) : nullptr;
+        if (!pre) front_planes(sw.f, seq, L, lane);
         uint32_t med; float mu;
         switch ((nwin + 31) >> 5) {
-            case 1: stats_read<1>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            case 2: stats_read<2>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            case 3: stats_read<3>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            case 4: stats_read<4>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            case 5: stats_read<5>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            case 6: stats_read<6>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            case 7: stats_read<7>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
-            default: stats_read<8>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu); break;
+            case 1: stats_read<1>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 2: stats_read<2>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 3: stats_read<3>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 4: stats_read<4>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 5: stats_read<5>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 6: stats_read<6>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 7: stats_read<7>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            default: stats_read<8>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
         }
         if (per_kmer) {
             __syncwarp();
@@ -361,7 +367,7 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                              float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, int arena,
-                             cudaStream_t s) {
+                             const uint32_t* d_counts, cudaStream_t s) {
     TimedLaunch timed("k_cov_stats", s);
     if (nreads == 0) return cudaSuccess;
     if (arena < PR_MAXWIN) arena = PR_MAXWIN;              // one read of the warp path must fit
@@ -371,7 +377,7 @@ cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint
     const uint64_t per_cta = (uint64_t)PR_WARPS * ST_RPW;
     const uint64_t blocks = (nreads + per_cta - 1) / per_cta;
     k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
-                                                             d_median, d_mean, d_stdev, d_per_kmer, ll, d_order, arena);
+                                                             d_median, d_mean, d_stdev, d_per_kmer, ll, d_order, arena, d_counts);
     return cudaGetLastError();
 }
 
@@ -383,7 +389,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
                                                const Slot* __restrict__ slots, Geo geo, uint32_t* P0,
                                                uint32_t* P1, uint32_t* PB, uint32_t* cov, float* sq,
                                                unsigned long long* red, uint32_t* per_kmer, uint32_t& median,
-                                               float& mean, float& stdev, int gtid) {
+                                               float& mean, float& stdev, int gtid, const uint32_t* __restrict__ pre = nullptr) {
     const int nwin = L >= k ? L - k + 1 : 0;
     if (nwin == 0) {   // S6: shorter than k -> empty vector; S7-S9 on n = 0: 0, 0, sqrt(0/-1) = -0
         median = 0; mean = 0.0f; stdev = __int_as_float(0x80000000);
@@ -391,7 +397,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
     }
     const unsigned mk = kmask(k);
     const int nch = (L + 31) >> 5;
-    pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
+    if (!pre) pack_read_planes<GS>(seq, L, nch, P0, P1, PB, gtid);
     gsync<GS>();
 
     unsigned long long part = 0;
@@ -400,7 +406,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
         const bool live = p < nwin;
         bool ok = false;
         unsigned long long key = 0ull;
-        if (live) {
+        if (live && !pre) {
             const int c = p >> 5, o = p & 31;
             const unsigned bad = __funnelshift_r(PB[c], PB[c + 1], o) & mk;
             if (!bad) {
@@ -414,7 +420,7 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
                 ok = true;
             }
         }
-        unsigned v = table_lookup(slots, geo, key, ok);
+        unsigned v = pre ? (live ? pre[p] : 0u) : table_lookup(slots, geo, key, ok);
         if (live) {
             if (v < geo.floor) v = 0;              // a `dump -L floor` view
             if (v < 1) v = 1;                      // fastaToKmerCoverageStats.cpp:328-330
@@ -494,7 +500,7 @@ k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ 
                  float* __restrict__ mean, float* __restrict__ stdev, uint32_t* __restrict__ per_kmer,
                  const unsigned int* __restrict__ long_idx, unsigned int n_long_h, unsigned int max_win_h,
                  uint32_t* scratch, size_t words_per_cta_h, const unsigned int* __restrict__ hdr,
-                 unsigned long long scratch_words, int* error) {
+                 unsigned long long scratch_words, int* error, const uint32_t* __restrict__ counts) {
     __shared__ unsigned long long red[LONG_THREADS / 32];
     LongPlan pl;
     if (!long_plan(hdr, n_long_h, max_win_h, words_per_cta_h, scratch_words, k, 1, error, pl)) return;
@@ -510,7 +516,8 @@ k_cov_stats_long(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ 
         const int L = (int)(o1 - o0 - 1);
         uint32_t med; float mu, sd;
         read_cov_stats<LONG_THREADS>(recs + (o0 - rec_base), L, k, canonical, slots, geo, P0, P1, PB, cov, sq, red,
-                                     per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, threadIdx.x);
+                                     per_kmer ? per_kmer + (o0 - rec_base) : nullptr, med, mu, sd, threadIdx.x,
+                                     counts ? counts + (o0 - rec_base) : nullptr);
         if (threadIdx.x == 0) { median[r] = med; mean[r] = mu; stdev[r] = sd; }
         __syncthreads();
     }
@@ -525,18 +532,18 @@ cudaError_t launch_cov_stats_long(const uint8_t* d_recs, const uint64_t* d_offs,
     k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
                                                     d_stdev, d_per_kmer, d_long_idx, n_long, max_win,
                                                     (uint32_t*)d_scratch, long_scratch_words(max_win, k, 1), nullptr, 0,
-                                                    nullptr);
+                                                    nullptr, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_cov_stats_long_auto(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, int k,
                                        int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                                        float* d_stdev, uint32_t* d_per_kmer, LongList ll, void* d_scratch,
-                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s) {
+                                       size_t scratch_bytes, int* d_error, int nctas, cudaStream_t s, const uint32_t* d_counts) {
     TimedLaunch timed("k_cov_stats_long", s);
     k_cov_stats_long<<<nctas, LONG_THREADS, 0, s>>>(d_recs, d_offs, rec_base, k, canonical, slots, geo, d_median, d_mean,
                                                     d_stdev, d_per_kmer, ll.idx, 0, 0, (uint32_t*)d_scratch, 0, ll.count,
-                                                    scratch_bytes / 4, d_error);
+                                                    scratch_bytes / 4, d_error, d_counts);
     return cudaGetLastError();
 }
 

@@ -131,6 +131,40 @@ class DeviceEngine:
                                                 C.c_void_p(hpoly.data_ptr())))
         return self.ctx.log_overflow_check()          # (a sync: the exchange runs on torch's stream)
 
+    # -- routed lookups ------------------------------------------------------------------------------------
+    def new_query_log(self, nbins, cap):
+        t = self.torch
+        return (t.empty((nbins, cap), dtype=t.int64, device=self.device), t.zeros((nbins,), dtype=t.int32, device=self.device),
+                t.empty((nbins, cap), dtype=t.int32, device=self.device))
+
+    def query_partition(self, d_recs, nbytes, keys, cursor, posidx):
+        """requester: key of every valid window -> the bin of its owner partition; posidx = the windows' positions"""
+        nbins, cap = keys.shape
+        check(_lib.lib().tg_query_partition_dev(self.ctx._h, d_recs, nbytes, self.k, int(self.canonical), nbins, cap,
+                                                C.c_void_p(keys.data_ptr()), C.c_void_p(cursor.data_ptr()),
+                                                C.c_void_p(posidx.data_ptr())))
+        return self.ctx.log_overflow_check()
+
+    def query_answer(self, rkeys, rcur, resp):
+        """owner: received keys [nsrc, lp, cap] -> resp [nsrc, lp, cap] (int32: the shard's count, 0 = absent)"""
+        nsrc, lp, cap = rkeys.shape
+        self.torch.cuda.current_stream(self.device).synchronize()
+        check(_lib.lib().tg_query_answer_dev(self.table._h, C.c_void_p(rkeys.data_ptr()), C.c_void_p(rcur.data_ptr()), nsrc, lp, cap,
+                                             C.c_void_p(resp.data_ptr())))
+        self.ctx.sync()
+
+    def query_scatter_stats(self, back, posidx, cursor, d_recs, nbytes, d_offs, nreads, min_count, d_median, d_mean, d_stdev):
+        """requester: answers [nbins, cap] -> counts at the windows' positions -> per-read statistics"""
+        t = self.torch
+        nbins, cap = back.shape
+        counts = t.zeros((int(nbytes) + 64,), dtype=t.int32, device=self.device)
+        t.cuda.current_stream(self.device).synchronize()
+        check(_lib.lib().tg_query_scatter_dev(self.ctx._h, C.c_void_p(back.data_ptr()), C.c_void_p(posidx.data_ptr()),
+                                              C.c_void_p(cursor.data_ptr()), nbins, cap, C.c_void_p(counts.data_ptr())))
+        check(_lib.lib().tg_cov_stats_counts_dev(self.ctx._h, d_recs, d_offs, nreads, self.k, int(min_count),
+                                                 C.c_void_p(counts.data_ptr()), d_median, d_mean, d_stdev))
+        self.ctx.sync()
+
     def sync(self):
         self.ctx.sync()
 
@@ -467,6 +501,33 @@ class ShardedKmerCounter:
     def dump_local(self, min_count=1):
         """this rank's part of `jellyfish dump` (sorted); the global dump is the merge of all ranks' parts"""
         return self.eng.local_dump(min_count)
+
+    def coverage_stats_routed_dev(self, d_recs, nbytes, d_offs, nreads, d_median, d_mean, d_stdev, min_count=1):
+        """Per-read coverage statistics of this rank's reads against the SHARDED table, without a replica (collective): the
+        key of every window goes to the rank that owns its partition (8 B), the count comes back (4 B), and the statistics
+        are computed from the counts.  For tables that do not fit as replicas; bit-identical to the replica path.  A bin
+        that overflows (hot k-mers) makes all ranks double the head-room and repeat, like the count does."""
+        grow = 1
+        while True:
+            m = self.eng.scalar_tensor([int(nbytes)], _int64(self.eng))
+            self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
+            cap = log_capacity(int(m.item()), self.cbins) * grow
+            keys, cur, posidx = self.eng.new_query_log(self.cbins, cap)
+            ovf = self._timed("q.partition", lambda: self.eng.query_partition(d_recs, nbytes, keys, cur, posidx))
+            if not self._any(ovf):
+                break
+            if grow >= 64:
+                raise RuntimeError("query log bin still overflows at 64x head-room")
+            grow *= 2
+        rkeys, rcur, resp = self.eng.new_query_log(self.cbins, cap)
+        # bins [d*c, (d+1)*c) go to rank d; what arrives is [source rank][c][cap]
+        self._timed("q.exchange", lambda: (self.dist.all_to_all_single(rcur, cur, group=self.group),
+                                           self.dist.all_to_all_single(rkeys, keys, group=self.group)))
+        self._timed("q.answer", lambda: self.eng.query_answer(rkeys.view(self.world, self.c, cap), rcur, resp.view(self.world, self.c, cap)))
+        back = self.eng.new_query_log(self.cbins, cap)[2]
+        self._timed("q.return", lambda: self.dist.all_to_all_single(back, resp, group=self.group))
+        self._timed("q.stats", lambda: self.eng.query_scatter_stats(back, posidx, cur, d_recs, nbytes, d_offs, nreads, min_count,
+                                                                    d_median, d_mean, d_stdev))
 
     def replicate(self, min_count=1, load=TARGET_LOAD):
         """All-gather the shards into a full table on every rank -> KmerCounter for local queries.  min_count > 1
