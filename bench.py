@@ -375,6 +375,9 @@ def main():
                          "collective = NCCL all-to-all of the bins; auto = peer when peer memory maps")
     ap.add_argument("--replay-fold", type=int, default=-1, help="fold duplicate k-mers per replay chunk (-1 = auto: 4+ GPUs)")
     ap.add_argument("--exchange-bins", type=int, default=0, help="coarse bins the k-mers are exchanged in (0 = default)")
+    ap.add_argument("--routed", action="store_true",
+                    help="several GPUs: also time the statistics through ROUTED lookups (no replica: keys to the owners, counts "
+                         "back) and check them against the replica path bit for bit")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -534,6 +537,26 @@ def main():
             "k-mers stored into the owners' logs over NVLink peer memory by the partition kernel itself"
             if sc.exchange == "peer" else "k-mer log all-to-all (NCCL)")
         config["exchange"] = sc.exchange
+
+    routed = None
+    if world > 1 and args.routed:
+        d_m2, d_a2, d_s2 = ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads), ctx.dev_alloc(4 * nreads)
+        sc.coverage_stats_routed_dev(d_recs, nbytes, d_offs, nreads, d_m2, d_a2, d_s2, min_count=min_count)     # warm-up
+        barrier()
+        sc.profile = {}
+        t0 = time.perf_counter()
+        sc.coverage_stats_routed_dev(d_recs, nbytes, d_offs, nreads, d_m2, d_a2, d_s2, min_count=min_count)
+        barrier()
+        rms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        rph = {k_: round(max_over_ranks(v), 2) for k_, v in sorted(sc.profile.items())}
+        sc.profile = None
+        same = (np.array_equal(ctx.d2h(d_m2, 4 * nreads, np.uint32), ctx.d2h(d_med, 4 * nreads, np.uint32)) and
+                np.array_equal(ctx.d2h(d_s2, 4 * nreads, np.uint32), ctx.d2h(d_sd, 4 * nreads, np.uint32)))
+        assert same, "routed lookups != replica lookups"
+        routed = {"ms_synced_phases": rms, "phases_ms_synced": rph, "identical_to_replica_path": bool(same),
+                  "nvlink_bytes_per_lookup": 12, "lookups_per_gpu": nreads * nwin}
+        for p_ in (d_m2, d_a2, d_s2):
+            ctx.dev_free(p_)
 
     # ---- parity inside the bench (at the full size, on however many GPUs) ----------------------------------------
     # (1) conservation: the sum of all counts in the (sharded) table == the number of valid 25-mer windows of all reads,
@@ -730,6 +753,8 @@ def main():
     if phases is not None:
         out["multi_gpu"] = {"exchange": sc.exchange, "phases_ms_synced": phases, "partitions": sc.nparts, "partitions_per_rank": sc.lp,
                             "exchange_bins": sc.cbins, "replay_fold": sc.replay_fold}
+        if routed is not None:
+            out["multi_gpu"]["routed_statistics"] = routed
     if r2t is not None:
         out["reads_to_transcripts"] = r2t
     print(json.dumps(out))
