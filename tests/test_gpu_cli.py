@@ -276,6 +276,21 @@ def test_stats_and_assignment_on_several_gpus(tmp_path):
                             "-p", "10"], capture_output=True, env=env, timeout=300)
         assert r.returncode == 0, (gl, r.stderr.decode()[-2000:])
         assert out.read_bytes() == gold("r2t_p10_chunk100.expected"), gl
+        # jellyfish count: chunks dealt round robin to one table per device, tables summed at the end; the database must dump
+        # exactly like the single-GPU one
+        jf = os.path.join(BIN, "jellyfish")
+        one, many = tmp_path / "one.jf", tmp_path / f"many_{gl.replace(',', '_')}.jf"
+        assert subprocess.run([jf, "count", "-m", "25", "-s", "1000000", "--canonical", "-o", str(one), fa], capture_output=True,
+                              env=ENV, timeout=300).returncode == 0
+        r = subprocess.run([jf, "count", "-m", "25", "-s", "1000000", "--canonical", "-o", str(many), fa], capture_output=True,
+                           env=dict(env, TRINITY_GPU_COUNT_CHUNK="20000"), timeout=300)
+        assert r.returncode == 0, (gl, r.stderr.decode()[-2000:])
+        d1 = subprocess.run([jf, "dump", "-L", "1", str(one)], capture_output=True, env=ENV, timeout=300)
+        d2 = subprocess.run([jf, "dump", "-L", "1", str(many)], capture_output=True, env=ENV, timeout=300)
+        assert d1.returncode == 0 and d2.returncode == 0 and len(d1.stdout) > 1000 and d1.stdout == d2.stdout, gl
+        h1 = subprocess.run([jf, "histo", str(one)], capture_output=True, env=ENV, timeout=300)
+        h2 = subprocess.run([jf, "histo", str(many)], capture_output=True, env=ENV, timeout=300)
+        assert h1.stdout == h2.stdout and len(h1.stdout) > 0, gl
     # a device that does not exist fails loudly (no fallback to fewer GPUs)
     r = subprocess.run([stats, "--reads", fa, "--kmers_from_reads", fa], capture_output=True, env=dict(ENV, TRINITY_GPUS="0,99"),
                        timeout=300)

@@ -6,11 +6,15 @@
 #include <errno.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "fasta_io.hpp"
 #include "seq_file.hpp"
+#include "multi_gpu.hpp"
 #include "tg_loader.hpp"
 #include "tg_sidecar.hpp"
 
@@ -92,16 +96,66 @@ Opts scan(int argc, char** argv, int first, const std::string& short_with_val, c
 
 // ---- sequence files -> record batches ----------------------------------------------------------------------
 // FASTA (multi-line allowed: line breaks inside a record do not break k-mers) and FASTQ (4-line records).
-void count_file(tg_table* table, const std::string& path, int canonical) {
+// One GPU: chunks of parsed records are counted as they come.  Several GPUs (TRINITY_GPUS=0,1,..): every device has its
+// own table and a worker thread with a one-chunk mailbox; the parser deals the chunks round robin, and the tables are
+// summed into the first one at the end (export -> tg_table_load_pairs: counts add up, exactly like counting everything
+// into one table).
+struct CountWorker {
+    tg_ctx* ctx = nullptr;
+    tg_table* table = nullptr;
+    int canonical = 0;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> box;
+    bool full = false, stop = false;
+    std::string error;
+    void run() {
+        for (;;) {
+            std::vector<char> mine;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return full || stop; });
+                if (!full) return;
+                mine.swap(box);
+                full = false;
+            }
+            cv.notify_all();
+            if (error.empty() && tg_count_reads(table, mine.data(), mine.size(), canonical) != TG_OK) error = tg_last_error();
+        }
+    }
+    void give(std::vector<char>& recs) {           // blocks while the previous chunk is still waiting to be taken
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !full; });
+        box.swap(recs);
+        full = true;
+        lk.unlock();
+        cv.notify_all();
+    }
+    void finish() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+
+void count_file(std::vector<CountWorker>& workers, size_t& next, tg_table* table, const std::string& path, int canonical) {
     FileView fv;
     std::string err;
     if (!fv.open(path, &err)) { fprintf(stderr, "jellyfish: %s\n", err.c_str()); exit(1); }
     std::vector<char> recs;
-    const size_t FLUSH = 256u << 20;
+    // record bytes per counted chunk (TRINITY_GPU_COUNT_CHUNK: a test knob -- tiny chunks spread a tiny file over the devices)
+    const size_t FLUSH = getenv("TRINITY_GPU_COUNT_CHUNK") ? (size_t)strtoull(getenv("TRINITY_GPU_COUNT_CHUNK"), nullptr, 10) : (256u << 20);
     recs.reserve(FLUSH + (64u << 20));
     parse_sequence_file(fv.data, fv.data + fv.size, recs, FLUSH, [&]() {
         if (recs.empty()) return;
-        TGC(tg_count_reads(table, recs.data(), recs.size(), canonical));
+        if (workers.empty()) {
+            TGC(tg_count_reads(table, recs.data(), recs.size(), canonical));
+        } else {
+            workers[next % workers.size()].give(recs);
+            next++;
+            recs.reserve(FLUSH + (64u << 20));
+        }
         recs.clear();
     });
 }
@@ -121,7 +175,9 @@ int cmd_count(int argc, char** argv) {
     std::vector<std::string> files = o.positional;
     if (files.empty()) files.push_back("/dev/fd/0");
 
-    tg_ctx* ctx = tgh::open_device();
+    tgh::GpuSet gpus;
+    gpus.open();
+    tg_ctx* ctx = gpus.ctx[0];
     // -s is only an initial-size hint in jellyfish 2 (the hash grows); we additionally cap it by the input size so
     // that thousands of tiny phase-2 invocations do not each grab gigabytes
     uint64_t input_bytes = 0;
@@ -129,7 +185,27 @@ int cmd_count(int argc, char** argv) {
     const uint64_t expected = std::min<uint64_t>(size_hint, input_bytes / 2 + 1024);
     tg_table* table = nullptr;
     TGC(tg_table_create(ctx, TG_TABLE_COUNT, k, expected, &table));
-    for (auto& f : files) count_file(table, f, canonical);
+    std::vector<CountWorker> workers(gpus.size() > 1 ? gpus.size() : 0);
+    for (size_t g = 0; g < workers.size(); g++) {
+        workers[g].ctx = gpus.ctx[g];
+        workers[g].canonical = canonical;
+        if (g == 0) workers[g].table = table;
+        else TGC(tg_table_create(gpus.ctx[g], TG_TABLE_COUNT, k, expected / gpus.size() + 1024, &workers[g].table));
+        workers[g].th = std::thread([&workers, g] { workers[g].run(); });
+    }
+    size_t next = 0;
+    for (auto& f : files) count_file(workers, next, table, f, canonical);
+    for (auto& w : workers) w.finish();
+    for (size_t g = 0; g < workers.size(); g++)
+        if (!workers[g].error.empty()) { fprintf(stderr, "ERROR: GPU %zu: %s\n", g, workers[g].error.c_str()); return 3; }
+    for (size_t g = 1; g < workers.size(); g++) {          // sum the other devices' tables into the first
+        uint64_t* mk = nullptr; uint32_t* mc = nullptr; uint64_t mn = 0;
+        TGC(tg_table_export(workers[g].table, 1, 0xFFFFFFFFu, /*sorted=*/0, 0, &mk, &mc, &mn));
+        const uint64_t STEP = 32u << 20;
+        for (uint64_t i = 0; i < mn; i += STEP) TGC(tg_table_load_pairs(table, mk + i, mc + i, std::min<uint64_t>(STEP, mn - i), canonical));
+        tg_free(mk); tg_free(mc);
+        tg_table_destroy(workers[g].table);
+    }
 
     JfHeader h;
     memset(&h, 0, sizeof h);
@@ -147,7 +223,7 @@ int cmd_count(int argc, char** argv) {
     ok = (fclose(f) == 0) && ok;
     tg_free(keys); tg_free(counts);
     tg_table_destroy(table);
-    tg_destroy(ctx);
+    gpus.close();
     if (!ok) { fprintf(stderr, "jellyfish: write to '%s' failed\n", out_path.c_str()); unlink(out_path.c_str()); return 1; }
     return 0;
 }
