@@ -261,10 +261,6 @@ int tg_cov_stats_counts_dev(tg_ctx* ctx, const void* d_recs, const void* d_offs,
  * visited in LOCUS order (neighbouring reads cover the same stretch of a transcript), so the slots their k-mers share stay
  * L2-resident while they are incremented and no k-mer log / partition replay is needed.  Same counts as tg_count_reads_dev. */
 int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical);
-/* The reads of a record buffer copied into LOCUS order (d_out: a record buffer of the same size, tg_dev_records_alloc).  For
- * consumers that need no read identity -- counting: the k-mers of neighbouring reads repeat, which the replay's per-chunk fold
- * turns into fewer table updates. */
-int tg_records_gather_locus_dev(tg_ctx* ctx, const void* d_recs, const void* d_offs, uint64_t nreads, int k, void* d_out);
 /* Declares a device record buffer (+ its offsets) immutable until the next tg_records_pin_dev (NULLs: nothing pinned): the
  * locus order of its reads is then computed once and shared by every *_dev call that is given exactly these pointers. */
 int tg_records_pin_dev(tg_ctx* ctx, const void* d_recs, const void* d_offs, uint64_t nreads);

@@ -69,7 +69,6 @@ SIGNATURES = {
     "tg_query_answer_dev": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp]),
     "tg_query_scatter_dev": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "tg_cov_stats_counts_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _u32, _vp, _vp, _vp, _vp]),
-    "tg_records_gather_locus_dev": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "tg_count_records_dev": (_i32, [_vp, _vp, _vp, _u64, _i32]),
     "tg_records_pin_dev": (_i32, [_vp, _vp, _vp, _u64]),
     "tg_locus_prepare_dev": (_i32, [_vp, _i32, _i32]),

@@ -117,10 +117,6 @@ class Context:
         """declare a device record buffer immutable (its locus order is computed once); no arguments: unpin"""
         check(_lib.lib().tg_records_pin_dev(self._h, d_recs, d_offs, nreads))
 
-    def records_gather_locus_dev(self, d_recs, d_offs, nreads, k, d_out):
-        """copy the reads into locus order (for counting: neighbouring reads repeat their k-mers)"""
-        check(_lib.lib().tg_records_gather_locus_dev(self._h, d_recs, d_offs, nreads, int(k), d_out))
-
     def locus_prepare_dev(self, k, recompute=False):
         """queue the locus order of the pinned buffer on the second stream (it overlaps the work queued next)"""
         check(_lib.lib().tg_locus_prepare_dev(self._h, int(k), int(bool(recompute))))

@@ -1117,24 +1117,6 @@ int tg_locus_prepare_dev(tg_ctx* c, int k, int recompute) {
     return locus_order_async(c, 1, (const uint8_t*)c->pin_recs, (const uint64_t*)c->pin_offs, 0, c->pin_nreads, k, &ord);
 }
 
-int tg_records_gather_locus_dev(tg_ctx* c, const void* d_recs, const void* d_offs, uint64_t nreads, int k, void* d_out) {
-    if (!c || !d_recs || !d_offs || !d_out) return fail(TG_ERR_ARG, "tg_records_gather_locus_dev: null argument");
-    if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_records_gather_locus_dev: at most 2^31 reads per call");
-    if (bind(c)) return TG_ERR_CUDA;
-    const uint32_t* ord = nullptr;
-    const uint64_t keep = c->locus_min_reads;
-    c->locus_min_reads = 0;                                // the caller asked for the order: no size threshold
-    int rc = locus_order_async(c, 0, (const uint8_t*)d_recs, (const uint64_t*)d_offs, 0, nreads, k, &ord);
-    c->locus_min_reads = keep;
-    if (rc) return rc;
-    if (!ord) return fail(TG_ERR_ARG, "tg_records_gather_locus_dev: the locus order is switched off");
-    const size_t need = gather_scratch_bytes(nreads);
-    CU(c->scratch.ensure(need));
-    CU(gather_reads((const uint8_t*)d_recs, (const uint64_t*)d_offs, ord, nreads, c->scratch.p, need, (uint8_t*)d_out, c->stream[0]));
-    c->launches += 3;
-    return TG_OK;
-}
-
 int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, uint64_t nreads, int canonical) {
     if (!t || !d_recs || !d_offs) return fail(TG_ERR_ARG, "tg_count_records_dev: null argument");
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_records_dev needs a TG_TABLE_COUNT table");

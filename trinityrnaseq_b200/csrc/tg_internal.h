@@ -141,11 +141,6 @@ cudaError_t launch_read_locus(const uint8_t* d_recs, const uint64_t* d_offs, uin
 size_t locus_sort_bytes(uint64_t n);
 cudaError_t locus_sort(void* work, size_t work_bytes, uint64_t n, const uint32_t** d_sorted, cudaStream_t s);
 
-// reads copied into a given order (tg_sort.cu)
-size_t gather_scratch_bytes(uint64_t nreads);
-cudaError_t gather_reads(const uint8_t* d_recs, const uint64_t* d_offs, const uint32_t* d_order, uint64_t nreads, void* scratch,
-                         size_t scratch_bytes, uint8_t* d_out, cudaStream_t s);
-
 // ---- GraphFromFasta weldmer counting: a read-only set of kk-mers (33 <= kk <= 48), every FORWARD
 // window of every read that equals one of them bumps its counter (NonRedKmerTable::AddData, NonRedKmerTable.cc:162-200)
 struct __align__(16) WeldSlot {
