@@ -207,6 +207,70 @@ class StandinEngine:
                 for e in keys[s, p, :int(cursor[s, p])].tolist():
                     self.table.add(e - 1, 1)
 
+    # -- routed lookups (what DeviceEngine does with k_log_tiles<QUERY>, k_query_answer, k_query_scatter, k_cov_stats) ---------
+    def new_query_log(self, nbins, cap):
+        return (torch.zeros((nbins, cap), dtype=torch.int64), torch.zeros((nbins,), dtype=torch.int32),
+                torch.zeros((nbins, cap), dtype=torch.int32))
+
+    def query_partition(self, recs, nbytes, keys, cursor, posidx):
+        """the (canonical, packed, +1) key of every window of k bases -> the bin of its partition; posidx = where it starts"""
+        nbins, cap = keys.shape
+        buf = bytes(np.asarray(recs[:nbytes]).tobytes()).upper()
+        code = {65: 0, 67: 1, 71: 2, 84: 3}
+        k, overflow = self.k, False
+        for p in range(len(buf) - k + 1):
+            w = buf[p:p + k]
+            if any(ch not in code for ch in w):
+                continue
+            f = 0
+            for ch in w:
+                f = (f << 2) | code[ch]
+            r = 0
+            for ch in reversed(w):
+                r = (r << 2) | (3 - code[ch])
+            key = min(f, r) if self.canonical else f
+            b = key_bin(key, nbins)
+            pos = int(cursor[b])
+            if pos >= cap:
+                overflow = True
+                continue
+            keys[b, pos] = key + 1
+            posidx[b, pos] = p
+            cursor[b] += 1
+        self._qkeys = keys
+        return overflow
+
+    def query_answer(self, rkeys, rcur, resp):
+        nsrc, lp, cap = rkeys.shape
+        rc = rcur.reshape(nsrc, lp)
+        for s_ in range(nsrc):
+            for b in range(lp):
+                for i in range(int(rc[s_, b])):
+                    key = int(rkeys[s_, b, i]) - 1
+                    assert self.table.part0 <= key_bin(key, self.table.nparts) < self.table.part0 + self.table.nlocal, \
+                        "a query reached a shard that does not own its partition"
+                    resp[s_, b, i] = self.table.counts.get(key, 0)
+
+    def query_scatter_stats(self, back, posidx, cursor, recs, nbytes, offs, nreads, min_count, median, mean, stdev):
+        """answers -> counts at the windows' positions -> the oracle's per-read statistics over those counts"""
+        counts = np.zeros(int(nbytes) + 64, dtype=np.int64)
+        nbins = back.shape[0]
+        for b in range(nbins):
+            n = int(cursor[b])
+            counts[posidx[b, :n].numpy()] = back[b, :n].numpy()
+        # the statistics of a table that holds exactly the answered k-mers at or above the floor
+        kc = orc.KmerCounter(self.k, self.canonical)
+        seen = {}
+        for b in range(nbins):
+            for i in range(int(cursor[b])):
+                seen[int(self._qkeys[b, i]) - 1] = int(back[b, i])
+        for key, c in seen.items():
+            if c >= max(1, int(min_count)):
+                kc.add_kmer("".join("ACGT"[(key >> (2 * (self.k - 1 - j))) & 3] for j in range(self.k)), c)
+        m, a, sd = kc.coverage_stats(np.asarray(recs[:nbytes]), np.asarray(offs))
+        median[:nreads] = m; mean[:nreads] = a; stdev[:nreads] = sd
+        self.last_counts = counts
+
     def slots_of(self, table):
         return torch.from_numpy(table.slots().reshape(-1))
 

@@ -94,6 +94,23 @@ def _worker(rank, world, port, out_dir, exchange, coarse):
             gm2, _, gsd2 = rep2.coverage_stats(mine, sub_offs)
             np.testing.assert_array_equal(gm2, om[r0:r1])
             np.testing.assert_array_equal(gsd2.view(np.uint32), osd[r0:r1].view(np.uint32))
+        # routed lookups: no replica -- keys to the owners, counts back -- give the same statistics, also under a floor
+        n_mine = r1 - r0
+        t_recs = torch.from_numpy(mine.copy()) if len(mine) else torch.zeros(0, dtype=torch.uint8)
+        sub = (offs[r0:r1 + 1] - offs[r0]) if n_mine else np.zeros(1, np.uint64)
+        for min_count, want in ((1, (om, osd)), (3, None)):
+            med, mean, sd = np.zeros(max(n_mine, 1), np.uint32), np.zeros(max(n_mine, 1), np.float32), np.zeros(max(n_mine, 1), np.float32)
+            sc.coverage_stats_routed_dev(t_recs, len(mine), sub, n_mine, med, mean, sd, min_count=min_count)
+            if want is None:                             # what a table rebuilt from `dump -L 3` answers
+                okc3 = orc.KmerCounter(k, True)
+                for key, c in zip(ok.tolist(), oc.tolist()):
+                    if 2 * c >= 3:
+                        okc3.add_kmer("".join("ACGT"[(key >> (2 * (k - 1 - i))) & 3] for i in range(k)), 2 * c)
+                m3, _, s3 = okc3.coverage_stats(recs, offs)
+                want = (m3, s3)
+            if n_mine:
+                np.testing.assert_array_equal(med[:n_mine], want[0][r0:r1])
+                np.testing.assert_array_equal(sd[:n_mine].view(np.uint32), want[1][r0:r1].view(np.uint32))
         sc.close()
         dist.barrier()
     finally:
