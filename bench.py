@@ -375,6 +375,12 @@ def main():
                          "collective = NCCL all-to-all of the bins; auto = peer when peer memory maps")
     ap.add_argument("--replay-fold", type=int, default=-1, help="fold duplicate k-mers per replay chunk (-1 = auto: 4+ GPUs)")
     ap.add_argument("--exchange-bins", type=int, default=0, help="coarse bins the k-mers are exchanged in (0 = default)")
+    ap.add_argument("--batches", type=int, default=1,
+                    help="several GPUs: a rank's reads are counted (and, with --stats routed, queried) in this many slices, so that "
+                         "the exchange logs of one slice fit beside a large shard (BASELINE configs[4]: 125 M reads per GPU)")
+    ap.add_argument("--stats", default="replica", choices=["replica", "routed"],
+                    help="several GPUs: statistics on an all-gathered replica of the -L 2 shards (default) or through routed "
+                         "lookups against the sharded table (no replica: for tables too large to replicate)")
     ap.add_argument("--routed", action="store_true",
                     help="several GPUs: also time the statistics through ROUTED lookups (no replica: keys to the owners, counts "
                          "back) and check them against the replica path bit for bit")
@@ -458,12 +464,34 @@ def main():
                                         replay_fold=None if args.replay_fold < 0 else bool(args.replay_fold))
         kc = sc.table
 
+        import ctypes
+        B = max(1, args.batches)
+        # counting slices: whole tiles (the count kernels work on a flat stream; a slice that ended inside a tile would have
+        # that tile's windows counted again by the next slice); query slices: whole reads
+        tile = 8192
+        cuts_b = [min(nbytes, (nbytes * b // B + tile - 1) // tile * tile) for b in range(B)] + [nbytes]
+        cuts_r = [nreads * b // B for b in range(B + 1)]
+
+        def at(ptr, off):
+            return ctypes.c_void_p(ptr.value + int(off))
+
         def count_dev(recs_ptr):
             sc.clear()
-            sc.add_records_dev(recs_ptr, nbytes, max_windows=nreads * nwin)
+            for b in range(B):
+                n_b = cuts_b[b + 1] - cuts_b[b]
+                if n_b:
+                    sc.add_records_dev(at(recs_ptr, cuts_b[b]), n_b, max_windows=(n_b // stride + 2) * nwin)
 
         def query_table():
             return sc.replicate(min_count=min_count, load=0.40)
+
+        def stats_routed(recs_ptr):
+            # fixed-stride records: the offsets of any slice of reads, relative to its first byte, are the first entries of d_offs
+            for b in range(B):
+                r0, r1 = cuts_r[b], cuts_r[b + 1]
+                if r1 > r0:
+                    sc.coverage_stats_routed_dev(at(recs_ptr, r0 * stride), (r1 - r0) * stride, d_offs, r1 - r0, at(d_med, 4 * r0),
+                                                 at(d_mean, 4 * r0), at(d_sd, 4 * r0), min_count=min_count)
 
         def table_info():
             return {"capacity": sc.subcap * sc.nparts, "distinct": sc.size()}
@@ -474,12 +502,15 @@ def main():
         ctx.records_pin_dev(d_recs, d_offs, nreads)
 
     def device_step():
-        if world > 1:
+        if world > 1 and args.stats != "routed":
             # several GPUs: the order is computed on the second stream, in the shadow of the exchange (one GPU: the count
             # kernels leave no room beside them -- measured: 78.3 ms with, 76.5 ms without -- so the statistics call computes it)
             ctx.locus_prepare_dev(K, recompute=True)
         count_dev(d_recs)
-        query_table().coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
+        if world > 1 and args.stats == "routed":
+            stats_routed(d_recs)
+        else:
+            query_table().coverage_stats_dev(d_recs, d_offs, nreads, d_med, d_mean, d_sd)
 
     def barrier():
         ctx.sync()
@@ -498,7 +529,11 @@ def main():
     for _ in range(W):
         device_step()
     tinfo = table_info()
-    qinfo = query_table().info()
+    qinfo = query_table().info() if not (world > 1 and args.stats == "routed") else tinfo
+    if world > 1:
+        config["count_batches"] = max(1, args.batches)
+        config["statistics"] = ("routed lookups against the sharded table (no replica)" if args.stats == "routed"
+                                else "replica of the -L 2 shards, all-gathered per step")
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -613,7 +648,10 @@ def main():
             ctx.h2d(d_stage, recs_host)          # the sharded count takes the rank's reads from HBM
             ctx.h2d(d_offs, offs_host)
             count_dev(d_stage)
-            query_table().coverage_stats_dev(d_stage, d_offs, nreads, d_med, d_mean, d_sd)
+            if args.stats == "routed":
+                stats_routed(d_stage)
+            else:
+                query_table().coverage_stats_dev(d_stage, d_offs, nreads, d_med, d_mean, d_sd)
             ctx.d2h(d_med, med_h)
             ctx.d2h(d_mean, mean_h)
             ctx.d2h(d_sd, sd_h)

@@ -108,7 +108,6 @@ struct tg_ctx {
                                                         // (pays when many GPUs send their copies of the same hot k-mers to
                                                         // one owner; costs ~12 ms per 1.5 G entries otherwise)
     unsigned replay_groups = 8;                         // bins replayed concurrently (see k_log_replay)
-    bool replay_dense = false;                          // 4 CTAs of the replay kernel per SM (64 registers) instead of 3
 };
 
 // k-mer log of a count table (partitioned count path)
@@ -369,8 +368,6 @@ int tg_ctx_set(tg_ctx* c, const char* key, const char* value) {
         c->long_scratch_bytes = (size_t)v << 20;
     } else if (!strcmp(key, "replay_fold")) {
         c->replay_fold = v != 0;
-    } else if (!strcmp(key, "replay_dense")) {
-        c->replay_dense = v != 0;
     } else if (!strcmp(key, "replay_groups")) {
         if (v < 1 || v > 64) return fail(TG_ERR_ARG, "replay_groups out of range (1..64)");
         c->replay_groups = (unsigned)v;
@@ -822,14 +819,14 @@ static int replay_log_async(tg_table* t) {
     if (refine_log_async(t)) {
         CU(launch_log_replay(t->log.fine_keys, t->log.fine_cursor, t->log.fine_cap, 1, t->log.fine_bins, 0, t->log.fine_bins,
                              c->replay_groups, t->log.chunk_start, t->log.hpoly, t->view(),
-                             c->replay_prefetch | (c->replay_fold ? 2 : 0) | (c->replay_dense ? 4 : 0), c->sm_count, c->stream[0]));
+                             c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
         c->launches += 2;
         CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
         t->log.pending_ub = 0;
         return TG_OK;
     }
     CU(launch_log_replay(t->log.keys, t->log.cursor, t->log.cap, 1, t->log.nbins, 0, t->log.nbins, c->replay_groups,
-                         t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0) | (c->replay_dense ? 4 : 0), c->sm_count, c->stream[0]));
+                         t->log.chunk_start, t->log.hpoly, t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
     c->launches += 2;
     CU(cudaMemsetAsync(t->log.cursor, 0, t->log.nbins * sizeof(unsigned int), c->stream[0]));
     t->log.pending_ub = 0;
@@ -1303,7 +1300,7 @@ int tg_table_replay_log_dev(tg_table* t, const void* d_keys, const void* d_curso
     CU(c->scratch.ensure(need));
     CU(launch_log_replay((const LogEntry*)d_keys, (const unsigned int*)d_cursor, cap, nsrc, t->g.nlocal, t->g.part0,
                          t->g.nparts, c->replay_groups, (unsigned long long*)c->scratch.p, (unsigned long long*)d_hpoly,
-                         t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0) | (c->replay_dense ? 4 : 0), c->sm_count, c->stream[0]));
+                         t->view(), c->replay_prefetch | (c->replay_fold ? 2 : 0), c->sm_count, c->stream[0]));
     c->launches += 2;
     return TG_OK;
 }

@@ -157,7 +157,9 @@ class DeviceEngine:
         """requester: answers [nbins, cap] -> counts at the windows' positions -> per-read statistics"""
         t = self.torch
         nbins, cap = back.shape
-        counts = t.zeros((int(nbytes) + 64,), dtype=t.int32, device=self.device)
+        # (+ a tile: the partition kernel works on whole tiles, and windows that start past nbytes -- bytes of the caller's next
+        #  slice, or padding -- are looked up too; their answers land here and nobody reads them)
+        counts = t.zeros((int(nbytes) + 16384,), dtype=t.int32, device=self.device)
         t.cuda.current_stream(self.device).synchronize()
         check(_lib.lib().tg_query_scatter_dev(self.ctx._h, C.c_void_p(back.data_ptr()), C.c_void_p(posidx.data_ptr()),
                                               C.c_void_p(cursor.data_ptr()), nbins, cap, C.c_void_p(counts.data_ptr())))
