@@ -470,7 +470,7 @@ def main():
         # that tile's windows counted again by the next slice); query slices: whole reads
         tile = 8192
         cuts_b = [min(nbytes, (nbytes * b // B + tile - 1) // tile * tile) for b in range(B)] + [nbytes]
-        cuts_r = [nreads * b // B for b in range(B + 1)]
+        cuts_r = [nreads * b // B // 16 * 16 for b in range(B)] + [nreads]     # (16 reads: slices start 16-byte aligned for TMA)
 
         def at(ptr, off):
             return ctypes.c_void_p(ptr.value + int(off))

@@ -435,6 +435,7 @@ cudaError_t launch_log_tiles(const uint8_t* d_recs, uint64_t nbytes, int k, int 
     TimedLaunch timed("k_log_tiles", s);
     if (nbytes == 0) return cudaSuccess;
     if (lg.nbins > LOG_MAX_BINS) return cudaErrorInvalidValue;
+    if (reinterpret_cast<uintptr_t>(d_recs) & 15u) return cudaErrorMisalignedAddress;      // TMA bulk copies want 16-byte aligned tiles
     const uint64_t ntiles = (nbytes + LT_TILE - 1) / LT_TILE;
     const bool query = lg.posidx != nullptr;
     if (query && nbytes > 0xFFFF0000ull) return cudaErrorInvalidValue;      // return addresses are 32-bit buffer positions
