@@ -192,14 +192,23 @@ __host__ __device__ inline size_t stats_warp_bytes(int arena) { return (sizeof(S
 template <int PER>
 __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], int n, unsigned lo, unsigned hi) {
     const unsigned k1 = (unsigned)(n - 1) / 2u, k2 = (unsigned)n / 2u;
-    // smallest value with at least k1 + 1 elements <= it = the element of rank k1
+    // smallest value with at least k1 + 1 elements <= it = the element of rank k1.  Three pivots per round (the quartiles
+    // of the interval): each lane counts its elements below each of them in one word (10-bit fields: n <= 256), ONE redux
+    // adds all three up, and the interval shrinks to a quarter -- half the rounds of a bisection.
     while (lo < hi) {
-        const unsigned mid = lo + ((hi - lo) >> 1);
+        const unsigned span = hi - lo;                     // (span < 4: the pivots coincide with lo -- still one step forward)
+        const unsigned q = span >> 2;
+        const unsigned m1 = lo + q, m2 = lo + 2u * q, m3 = lo + 3u * q;          // lo <= m1 < m2 < m3 < hi
         unsigned cnt = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) cnt += x[i] <= mid ? 1u : 0u;          // (dead elements are 0xFFFFFFFF > mid)
+        for (int i = 0; i < PER; i++)
+            cnt += (x[i] <= m1 ? 1u : 0u) + (x[i] <= m2 ? 1u << 10 : 0u) + (x[i] <= m3 ? 1u << 20 : 0u);
         cnt = __reduce_add_sync(FULL, cnt);
-        if (cnt >= k1 + 1u) hi = mid; else lo = mid + 1u;
+        const unsigned c1 = cnt & 1023u, c2 = (cnt >> 10) & 1023u, c3 = cnt >> 20;
+        if (c1 >= k1 + 1u) hi = m1;
+        else if (c2 >= k1 + 1u) { lo = m1 + 1u; hi = m2; }
+        else if (c3 >= k1 + 1u) { lo = m2 + 1u; hi = m3; }
+        else lo = m3 + 1u;
     }
     const unsigned x1 = lo;
     if (k1 == k2) return x1;
@@ -217,7 +226,7 @@ __device__ __forceinline__ uint32_t warp_median_regs(const unsigned (&x)[PER], i
 
 // lookups of one read + sum, mean, median; the coverage vector is left in sw.cov[used .. used + nwin).  The first-sector
 // loads of LK rounds (LK x 32 windows) are issued back to back before any of them is examined.
-template <int PER>
+template <int PER, bool PRE>
 __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict__ slots, const Geo& geo, int nwin, int k,
                                            unsigned mk, bool canonical, unsigned used, int lane, uint32_t& median, float& mean,
                                            const uint32_t* __restrict__ pre) {
@@ -230,7 +239,7 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
         unsigned long long key[LK];
         bool ok[LK];
         LookupIssue q[LK];
-        if (!pre) {
+        if (!PRE) {
 #pragma unroll
             for (int u = 0; u < LK; u++)
                 if (i0 + u < PER) {
@@ -243,9 +252,12 @@ __device__ __forceinline__ void stats_read(StatsWarp& sw, const Slot* __restrict
         for (int u = 0; u < LK; u++)
             if (i0 + u < PER) {
                 const int p = 32 * (i0 + u) + lane;
-                // (pre: the counts were looked up elsewhere -- routed to the shards that own the k-mers -- and wait at the
-                // windows' positions; a window that was never sent holds 0)
-                unsigned v = pre ? (p < nwin ? pre[p] : 0u) : lookup_settle(slots, geo, key[u], ok[u], q[u]).x;
+                // (PRE: the counts were looked up elsewhere -- routed to the shards that own the k-mers -- and wait at the
+                // windows' positions; a window that was never sent holds 0.  A compile-time switch: the probing variant must
+                // not carry the other one's control flow -- as a run-time branch it cost 1.5 KB of spills)
+                unsigned v;
+                if (PRE) v = p < nwin ? pre[p] : 0u;
+                else v = lookup_settle(slots, geo, key[u], ok[u], q[u]).x;
                 if (v < geo.floor) v = 0;          // a `dump -L floor` view: rarer k-mers are not in that table
                 if (v < 1) v = 1;                  // fastaToKmerCoverageStats.cpp:328-330 (also windows with a non-base)
                 const bool live = p < nwin;
@@ -340,14 +352,14 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
         if (!pre) front_planes(sw.f, seq, L, lane);
         uint32_t med; float mu;
         switch ((nwin + 31) >> 5) {
-            case 1: stats_read<1>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 2: stats_read<2>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 3: stats_read<3>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 4: stats_read<4>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 5: stats_read<5>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 6: stats_read<6>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 7: stats_read<7>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            default: stats_read<8>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 1: if (pre) stats_read<1, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<1, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 2: if (pre) stats_read<2, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<2, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 3: if (pre) stats_read<3, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<3, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 4: if (pre) stats_read<4, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<4, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 5: if (pre) stats_read<5, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<5, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 6: if (pre) stats_read<6, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<6, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 7: if (pre) stats_read<7, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<7, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            default: if (pre) stats_read<8, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<8, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
         }
         if (per_kmer) {
             __syncwarp();
@@ -641,7 +653,9 @@ __device__ __forceinline__ void assign_read(AssignWarp& aw, const Slot* __restri
                     do_f = window_entropy_ok(lut, w.f0, w.f1, mk, false);
                     do_r = !strand && window_entropy_ok(lut, w.f0, w.f1, mk, true);
                 }
-                key[u] = w.key; ok[u] = do_f || do_r;
+                // the probe does not wait for the entropy verdict (two LUT loads): nearly every window passes, and a window
+                // that does not simply has its labels dropped when the probe is settled
+                key[u] = w.key; ok[u] = w.valid;
                 fl[u] = (do_f ? 1u : 0u) | (do_r ? 2u : 0u) | (w.is_rc ? 4u : 0u) | (w.pal ? 8u : 0u);
                 q[u] = lookup_issue(slots, geo, key[u], ok[u]);
             }
