@@ -302,6 +302,7 @@ __device__ __forceinline__ void stats_flush(StatsWarp& sw, unsigned nb, float* _
     __syncwarp();
 }
 
+template <bool PRE>          // PRE: statistics from counts looked up elsewhere (routed lookups) instead of probing the table
 __global__ void __launch_bounds__(PR_WARPS * 32, 4)
 k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs, uint64_t rec_base, uint64_t nreads,
             int k, int canonical, const Slot* __restrict__ slots, Geo geo, uint32_t* __restrict__ median,
@@ -340,18 +341,18 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
         }
         if (nb == ST_BATCH || used + nwin > (unsigned)arena) { stats_flush(sw, nb, stdev, lane); nb = 0; used = 0; }
         const uint8_t* seq = recs + (o0 - rec_base);
-        const uint32_t* pre = counts ? counts + (o0 - rec_base) : nullptr;
-        if (!pre) front_planes(sw.f, seq, L, lane);
+        const uint32_t* pre = PRE ? counts + (o0 - rec_base) : nullptr;
+        if (!PRE) front_planes(sw.f, seq, L, lane);
         uint32_t med; float mu;
         switch ((nwin + 31) >> 5) {
-            case 1: if (pre) stats_read<1, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<1, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 2: if (pre) stats_read<2, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<2, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 3: if (pre) stats_read<3, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<3, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 4: if (pre) stats_read<4, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<4, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 5: if (pre) stats_read<5, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<5, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 6: if (pre) stats_read<6, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<6, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            case 7: if (pre) stats_read<7, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<7, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
-            default: if (pre) stats_read<8, true>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); else stats_read<8, false>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 1: stats_read<1, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 2: stats_read<2, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 3: stats_read<3, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 4: stats_read<4, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 5: stats_read<5, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 6: stats_read<6, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            case 7: stats_read<7, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
+            default: stats_read<8, PRE>(sw, slots, geo, nwin, k, mk, canonical != 0, used, lane, med, mu, pre); break;
         }
         if (per_kmer) {
             __syncwarp();
@@ -376,12 +377,17 @@ cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint
     if (nreads == 0) return cudaSuccess;
     if (arena < PR_MAXWIN) arena = PR_MAXWIN;              // one read of the warp path must fit
     const size_t dyn = stats_warp_bytes(arena) * PR_WARPS;
-    cudaError_t e = cudaFuncSetAttribute((const void*)k_cov_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    const void* kern = d_counts ? (const void*)k_cov_stats<true> : (const void*)k_cov_stats<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     const uint64_t per_cta = (uint64_t)PR_WARPS * ST_RPW;
     const uint64_t blocks = (nreads + per_cta - 1) / per_cta;
-    k_cov_stats<<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
-                                                             d_median, d_mean, d_stdev, d_per_kmer, ll, d_order, arena, d_counts);
+    if (d_counts)
+        k_cov_stats<true><<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
+                                                                       d_median, d_mean, d_stdev, d_per_kmer, ll, d_order, arena, d_counts);
+    else
+        k_cov_stats<false><<<(unsigned)blocks, PR_WARPS * 32, dyn, s>>>(d_recs, d_offs, rec_base, nreads, k, canonical, slots, geo,
+                                                                        d_median, d_mean, d_stdev, d_per_kmer, ll, d_order, arena, d_counts);
     return cudaGetLastError();
 }
 
