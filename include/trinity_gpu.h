@@ -15,7 +15,9 @@
  *     offs[n] the end of the last terminator; record i has offs[i+1]-offs[i]-1 bases.  Bases are
  *     case-insensitive; any byte other than ACGTacgt is "not a base" and breaks every k-mer window over it.
  *   - "packed k-mer": 2 bits per base, A=0 C=1 G=2 T=3, first base most significant, in the low 2k bits of
- *     a uint64_t (so integer order == lexicographic order).  1 <= k <= 31 (the partitioned / sharded count path: 8 <= k).
+ *     a uint64_t (so integer order == lexicographic order).  Count tables: 1 <= k <= 32 (Inchworm's range,
+ *     Inchworm/src/KmerCounter.cpp:15-17; k = 32 is exact but runs on the direct-insert / CTA-per-read kernels and cannot
+ *     be sharded); label tables and the partitioned / sharded paths: k <= 31.
  *   - host buffers may be pageable; buffers from tg_host_alloc (pinned) are copied at full PCIe speed.
  *   - a tg_ctx owns one device and its streams; calls on one ctx must not overlap in time.
  */

@@ -295,3 +295,54 @@ def test_stats_and_assignment_on_several_gpus(tmp_path):
     r = subprocess.run([stats, "--reads", fa, "--kmers_from_reads", fa], capture_output=True, env=dict(ENV, TRINITY_GPUS="0,99"),
                        timeout=300)
     assert r.returncode != 0
+
+
+def test_kmer_size_32(tmp_path):
+    """--kmer_size 32 (the reference's maximum, Inchworm/src/KmerCounter.cpp:15-17): stdout byte-identical to the reference
+    binary on reads that hold poly-A / poly-T 32-mers -- the all-zero 64-bit key and its reverse complement
+    (tests/golden/make_golden_k32.py); jellyfish count -m 32 / dump / histo against the oracle; 33 is refused like the
+    reference refuses it."""
+    stats = os.path.join(BIN, "fastaToKmerCoverageStats")
+    jf = os.path.join(BIN, "jellyfish")
+    fa = os.path.join(GOLD, "reads_k32.fa")
+    for mode in ("DS", "SS"):
+        r = run([stats, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "32", "--" + mode])
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout == gold(f"stats_k32_{mode}.expected")
+    r = run([stats, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "32", "--capture_coverage_info"])
+    assert r.returncode == 0 and r.stdout == gold("stats_k32_capture.expected")
+    r = run([stats, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", "33"])
+    assert r.returncode == 1 and b"exceeds max of 32" in r.stderr
+    seqs = []
+    for line in gold("reads_k32.fa").split(b"\n"):
+        if line.startswith(b">"):
+            seqs.append(b"")
+        elif seqs:
+            seqs[-1] += line
+    recs, _ = tg.records_from_sequences(seqs)
+    for canonical in (True, False):
+        db = tmp_path / f"mer32_{int(canonical)}.jf"
+        r = run([jf, "count", "-t", "4", "-m", "32", "-s", "1000000", "-o", str(db)] + (["--canonical"] if canonical else []) + [fa])
+        assert r.returncode == 0, r.stderr.decode()
+        for L in (1, 2):
+            keys, cnts = orc.jf_count(recs, 32, canonical, L)
+            assert keys[0] == 0
+            expect = "".join(">%d\n%s\n" % (c, tg.packed_to_kmer(k, 32)) for k, c in zip(keys, cnts)).encode()
+            d = run([jf, "dump", "-L", str(L), str(db)])
+            assert d.returncode == 0 and d.stdout == expect
+        keys, cnts = orc.jf_count(recs, 32, canonical, 1)
+        bins = orc.jf_histo(cnts)
+        h = run([jf, "histo", "-t", "4", "-o", str(tmp_path / "h32.txt"), str(db)])
+        expect = "".join("%d %d\n" % (c, bins[c]) for c in range(1, 10002) if bins[c]).encode()
+        assert h.returncode == 0 and (tmp_path / "h32.txt").read_bytes() == expect
+    # the normalisation pipeline's hand-off at k = 32: dump -> --kmers == counting the reads (no read of exactly 32 bases)
+    entries = orc.read_fasta_inchworm(gold("reads_k32.fa"))
+    fa2 = tmp_path / "r.fa"
+    fa2.write_text("".join(">%s\n%s\n" % (h, s) for h, _, s in entries if len(s) != 32))
+    assert run([jf, "count", "-m", "32", "-s", "1000000", "--canonical", "-o", str(tmp_path / "m.jf"), str(fa2)]).returncode == 0
+    d = run([jf, "dump", "-L", "1", str(tmp_path / "m.jf")])
+    (tmp_path / "k.fa").write_bytes(d.stdout)
+    a = run([stats, "--reads", str(fa2), "--kmers", str(tmp_path / "k.fa"), "--kmer_size", "32", "--DS"])
+    b = run([stats, "--reads", str(fa2), "--kmers_from_reads", str(fa2), "--kmer_size", "32", "--DS"])
+    assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout and len(a.stdout) > 1000
+    assert run([jf, "count", "-m", "33", "-s", "1000", "-o", str(tmp_path / "x.jf"), fa]).returncode != 0

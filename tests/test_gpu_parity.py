@@ -417,3 +417,118 @@ def test_count_floor_view_equals_rebuilt_dump_table(gpu_ctx, oracle, data, floor
         again = kc.coverage_stats(recs, offs)
         for a, b in zip(full, again):
             np.testing.assert_array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+
+
+def _k32_reads(rng):
+    txs = synth.transcriptome(rng, 20, mean_len=600, min_len=200, max_len=2000)
+    reads = synth.reads_from(rng, txs, 1500, 100, lower_rate=0.1, var_len=True)
+    # the 32-mers a 64-bit key has no tag bit for: poly-A (the all-zero key) and its reverse complement, in runs of every
+    # kind -- exactly k, k + 1, long, lower case, broken after 31 bases, behind an N -- plus the other homopolymers
+    reads += [b"A" * 32, b"a" * 33, b"A" * 120, b"T" * 32, b"T" * 77, b"A" * 31, b"A" * 31 + b"C" + b"A" * 40,
+              b"T" * 31 + b"G" + b"T" * 33, b"C" * 45, b"G" * 45, b"ACGT" * 4 + b"A" * 36 + b"TTTT" + b"A" * 34 + b"N" + b"A" * 32,
+              b"", b"ACGT", b"N" * 40, txs[0][:32], txs[0][:33], txs[1][:400], txs[2][:1500]]
+    return txs, reads
+
+
+@pytest.mark.parametrize("canonical", [True, False])
+def test_k32_count_dump_histo_stats(gpu_ctx, oracle, canonical):
+    """k = 32 (Inchworm/src/KmerCounter.cpp:15-17 allows it): the planes fill all 64 bits of the key, poly-A lives in the
+    table's zero-key slot.  Count (with growth: the zero-key slot moves with the rehash), dump, dump -L 2, histo, sum of
+    counts, per-window coverage and statistics (host-buffer, held and device-resident entry points), the -L 2 view, and
+    the pair loader -- all against the oracle."""
+    rng = np.random.default_rng(3232)
+    _, reads = _k32_reads(rng)
+    recs, offs = tg.records_from_sequences(reads)
+    k = 32
+    ok, oc = oracle.jf_count(recs, k, canonical, 1)
+    assert ok[0] == 0                                    # poly-A is there
+    okc = oracle.KmerCounter(k, canonical)
+    for kmer, c in zip(ok, oc):
+        okc.add_kmer(tg.packed_to_kmer(kmer, k), int(c))
+    om, omean, osd, oper = okc.coverage_stats(recs, offs, capture=True)
+    ctx = gpu_ctx
+    with tg.KmerCounter(ctx, k, is_ds=canonical, expected_keys=500) as kc:       # tiny hint: forces growth
+        kc.add_records(recs)
+        assert kc.size() == len(ok)
+        gk, gc = kc.dump()
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc, oc)
+        ok2, oc2 = oracle.jf_count(recs, k, canonical, 2)
+        gk2, gc2 = kc.dump(min_count=2)
+        np.testing.assert_array_equal(gk2, ok2)
+        np.testing.assert_array_equal(gc2, oc2)
+        np.testing.assert_array_equal(kc.histo(), oracle.jf_histo(oc))
+        assert kc.count_sum() == int(oc.astype(np.uint64).sum())
+        gm, gmean, gsd, gper = kc.coverage_stats(recs, offs, capture_coverage_info=True)
+        np.testing.assert_array_equal(gper, oper)
+        np.testing.assert_array_equal(gm, om)
+        np.testing.assert_array_equal(_f32_bits(gmean), _f32_bits(omean))
+        np.testing.assert_array_equal(_f32_bits(gsd), _f32_bits(osd))
+        # held buffer and device-resident entry points
+        pinned, owner = ctx.pinned((recs.nbytes,), np.uint8)
+        pinned[:] = recs
+        ctx.records_hold(pinned)
+        hm, hmean, hsd = kc.coverage_stats(pinned, offs)
+        ctx.records_release()
+        np.testing.assert_array_equal(hm, om)
+        np.testing.assert_array_equal(_f32_bits(hsd), _f32_bits(osd))
+        n = len(reads)
+        d_recs = ctx.dev_records_alloc(recs.nbytes)
+        ctx.h2d(d_recs, recs)
+        d_offs = ctx.dev_alloc(offs.nbytes)
+        ctx.h2d(d_offs, offs)
+        d1, d2, d3 = ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n), ctx.dev_alloc(4 * n)
+        kc.coverage_stats_dev(d_recs, d_offs, n, d1, d2, d3)
+        ctx.sync()
+        np.testing.assert_array_equal(ctx.d2h(d1, 4 * n, np.uint32), om)
+        np.testing.assert_array_equal(ctx.d2h(d2, 4 * n, np.uint32), _f32_bits(omean))
+        np.testing.assert_array_equal(ctx.d2h(d3, 4 * n, np.uint32), _f32_bits(osd))
+        # the `dump -L 2` view and its materialised twin
+        okc2 = oracle.KmerCounter(k, canonical)
+        for kmer, c in zip(ok2, oc2):
+            okc2.add_kmer(tg.packed_to_kmer(kmer, k), int(c))
+        om2, _, osd2 = okc2.coverage_stats(recs, offs)
+        kc.set_count_floor(2)
+        fm, _, fsd = kc.coverage_stats(recs, offs)
+        np.testing.assert_array_equal(fm, om2)
+        np.testing.assert_array_equal(_f32_bits(fsd), _f32_bits(osd2))
+        q = kc.compacted(2)
+        qk, qc = q.dump()
+        qm, _, qsd = q.coverage_stats(recs, offs)
+        q.close()
+        np.testing.assert_array_equal(qk, ok2)
+        np.testing.assert_array_equal(qc, oc2)
+        np.testing.assert_array_equal(qm, om2)
+        np.testing.assert_array_equal(_f32_bits(qsd), _f32_bits(osd2))
+        kc.set_count_floor(0)
+        # counting the same buffer again, from the device copy, doubles every count
+        kc.add_records_dev(d_recs, recs.nbytes)
+        gk3, gc3 = kc.dump()
+        np.testing.assert_array_equal(gk3, ok)
+        np.testing.assert_array_equal(gc3, 2 * oc)
+        for p in (d_recs, d_offs, d1, d2, d3):
+            ctx.dev_free(p)
+    # the pair loader (--kmers): a non-canonical dump loaded into a table of either kind, poly-A and poly-T both present
+    fk, fc = oracle.jf_count(recs, k, False, 1)
+    assert fk[0] == 0 and fk[-1] == np.uint64(0xFFFFFFFFFFFFFFFF)
+    okl = oracle.KmerCounter(k, canonical)
+    for kmer, c in zip(fk, fc):
+        okl.add_kmer(tg.packed_to_kmer(kmer, k), int(c))
+    lm, lmean, lsd = okl.coverage_stats(recs, offs)
+    with tg.KmerCounter(ctx, k, is_ds=canonical, expected_keys=500) as kc:
+        kc.add_kmers(fk, fc)
+        assert kc.size() == okl.size()
+        gm, gmean, gsd = kc.coverage_stats(recs, offs)
+    np.testing.assert_array_equal(gm, lm)
+    np.testing.assert_array_equal(_f32_bits(gmean), _f32_bits(lmean))
+    np.testing.assert_array_equal(_f32_bits(gsd), _f32_bits(lsd))
+
+
+def test_k32_is_refused_where_the_key_tag_is_needed(gpu_ctx):
+    """label tables, sharded tables and the partitioned / read-by-read count entry points keep k <= 31; k = 33 nowhere"""
+    with pytest.raises(tg.TrinityGpuError):
+        tg.BundleKmerTable(gpu_ctx, 32)
+    with pytest.raises(tg.TrinityGpuError):
+        tg.KmerCounter.sharded(gpu_ctx, 32, True, 1024, 8, 0, 4)
+    with pytest.raises(tg.TrinityGpuError):
+        tg.KmerCounter(gpu_ctx, 33)

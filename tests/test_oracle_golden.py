@@ -79,6 +79,13 @@ def test_stats_capture_k21_and_dump_loader():
     assert oracle_stats_text(gold("reads.fa"), kmers_text=gold("kmers_L2.fa")) == gold("stats_kmers_L2.expected")
 
 
+def test_stats_k32():
+    """the reference's maximum k (Inchworm/src/KmerCounter.cpp:15-17): poly-A / poly-T 32-mers, the all-zero 64-bit value"""
+    for ds in (True, False):
+        assert oracle_stats_text(gold("reads_k32.fa"), k=32, ds=ds) == gold(f"stats_k32_{'DS' if ds else 'SS'}.expected")
+    assert oracle_stats_text(gold("reads_k32.fa"), k=32, capture=True) == gold("stats_k32_capture.expected")
+
+
 def test_stats_known_answers():
     """n == 0 -> 0 0 -0 ; n == 1 -> c c -nan ; empty sequence -> no line"""
     txt = gold("stats_DS.expected").decode().splitlines()

@@ -188,8 +188,12 @@ static int table_refresh(tg_table* t) {   // after a sync: read back distinct co
     return TG_OK;
 }
 
+// Every table carries one spare bucket behind its partitions: its first slot is the home of the zero key (poly-A at
+// k = 32, tg_device.cuh); the scan kernels read slot [cap] of any table.
+constexpr uint64_t SPARE_SLOTS = BUCKET_SLOTS;
 static int table_alloc(tg_ctx* c, uint64_t slots, Slot** out) {
     if (slots < MIN_SLOTS) slots = MIN_SLOTS;
+    slots += SPARE_SLOTS;
     Slot* p = nullptr;
     CU(cudaMalloc(&p, slots * sizeof(Slot)));
     cudaError_t e = cudaMemsetAsync(p, 0, slots * sizeof(Slot), c->stream[0]);
@@ -424,8 +428,10 @@ static int table_new(tg_ctx* c, int kind, int k, Geo g, tg_table** out) {
 
 int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table** out) {
     if (!c || !out) return fail(TG_ERR_ARG, "tg_table_create: null argument");
-    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (k < 1 || k > 32) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..32)", k);
     if (kind != TG_TABLE_COUNT && kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "unknown table kind %d", kind);
+    if (kind == TG_TABLE_LABEL && k > 31)        // (ReadsToTranscripts.cc:38 hard-codes k = 25; the entropy LUT holds k <= 25)
+        return fail(TG_ERR_ARG, "label tables take k-mer lengths 1..31");
     if (bind(c)) return TG_ERR_CUDA;
     uint64_t slots = (uint64_t)((double)expected_keys / TARGET_LOAD) + 1;
     if (slots < MIN_SLOTS) slots = MIN_SLOTS;
@@ -435,7 +441,9 @@ int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table
 int tg_table_create_sharded(tg_ctx* c, int kind, int k, uint64_t slots_per_partition, uint32_t nparts, uint32_t part0,
                             uint32_t nlocal, tg_table** out) {
     if (!c || !out) return fail(TG_ERR_ARG, "tg_table_create_sharded: null argument");
-    if (k < 1 || k > 31) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..31)", k);
+    if (k < 1 || k > 32) return fail(TG_ERR_ARG, "k-mer length %d unsupported (1..32)", k);
+    if (k == 32 && nlocal != nparts)
+        return fail(TG_ERR_ARG, "k = 32 tables cannot be sharded (the zero-key slot has no owner partition): 1..31");
     if (kind != TG_TABLE_COUNT && kind != TG_TABLE_LABEL) return fail(TG_ERR_ARG, "unknown table kind %d", kind);
     if (nparts == 0 || nlocal == 0 || (uint64_t)part0 + nlocal > nparts || nparts > LOG_MAX_BINS || slots_per_partition < 16)
         return fail(TG_ERR_ARG, "tg_table_create_sharded: bad geometry (%u partitions, local %u..+%u, %llu slots each)",
@@ -495,7 +503,7 @@ int tg_table_clear(tg_table* t) {
     }
     CU(cudaEventRecord(c->order[1], c->stream[1]));
     CU(cudaStreamWaitEvent(c->stream[0], c->order[1], 0));
-    CU(cudaMemsetAsync(t->slots, 0, t->cap * sizeof(Slot), c->stream[0]));
+    CU(cudaMemsetAsync(t->slots, 0, (t->cap + SPARE_SLOTS) * sizeof(Slot), c->stream[0]));
     CU(cudaMemsetAsync(t->d_claimed, 0, sizeof(unsigned long long), c->stream[0]));
     CU(cudaMemsetAsync(t->d_error, 0, sizeof(int), c->stream[0]));
     if (t->log.cursor) {
@@ -712,7 +720,7 @@ static unsigned log_bins_for(const tg_table* t) {
 // worth logging?  The replay streams the whole table through L2 once, so the batch must be large next to it.
 static bool log_pays(const tg_table* t, uint64_t nbytes) {
     const tg_ctx* c = t->ctx;
-    if (t->kind != TG_TABLE_COUNT || t->sharded() || t->k < MIN_FAST_K) return false;
+    if (t->kind != TG_TABLE_COUNT || t->sharded() || t->k < MIN_FAST_K || t->k > 31) return false;   // (k = 32: flat tiles only)
     if (c->count_mode == 1) return false;
     if (c->count_mode == 2) return true;
     return t->g.nparts >= 4 && nbytes * 16 >= t->cap * sizeof(Slot);
@@ -1119,6 +1127,7 @@ int tg_count_records_dev(tg_table* t, const void* d_recs, const void* d_offs, ui
     if (t->kind != TG_TABLE_COUNT) return fail(TG_ERR_ARG, "tg_count_records_dev needs a TG_TABLE_COUNT table");
     if (t->sharded()) return fail(TG_ERR_ARG, "tg_count_records_dev: sharded tables are counted through the exchange path");
     if (nreads > 0x7FFFFFF0ull) return fail(TG_ERR_ARG, "tg_count_records_dev: at most 2^31 reads per call");
+    if (t->k > 31) return fail(TG_ERR_ARG, "tg_count_records_dev: k = 32 is counted by tg_count_reads / tg_count_reads_dev");
     tg_ctx* c = t->ctx;
     if (bind(c)) return TG_ERR_CUDA;
     if (t->log.pending_ub) { int rc = flush_log(t); if (rc) return rc; }

@@ -7,7 +7,9 @@
 //  * a read tile is held BIT-SLICED: for every chunk of 32 bases three 32-bit planes (low code bit, high
 //    code bit, invalid flag), produced by three warp ballots.  A k-mer at offset o of a chunk is then two
 //    funnel shifts, and its reverse complement is two bit reversals (brev of the complemented plane).
-//  * the table key is the pair of k-bit planes: key = TAG | plane1 << 32 | plane0 (k <= 31).  It is a
+//  * the table key is the pair of k-bit planes: key = TAG | plane1 << 32 | plane0 (k <= 31; k = 32 fills all 64 bits,
+//    has no TAG, and its one k-mer that reads as "empty" -- poly-A, key 0 -- lives in a slot of its own behind the
+//    partitions: see zero_key_slot).  It is a
 //    bijection of the k-mer, which is all a hash table needs; the lexicographic 2-bit packing
 //    (first base most significant, A<C<G<T) that the C-ABI speaks is produced/consumed by
 //    planes_to_packed()/packed_to_planes() at the boundary (export, load_pairs).
@@ -74,6 +76,15 @@ __device__ __forceinline__ unsigned kmask(int k) { return k >= 32 ? 0xFFFFFFFFu 
 __device__ __forceinline__ unsigned long long make_key(unsigned p0, unsigned p1) {
     return KEY_TAG | ((unsigned long long)p1 << 32) | p0;
 }
+// k = 32 (Inchworm/src/KmerCounter.cpp:15-17 allows it): the two planes take all 64 bits, so the key carries no tag.  Every
+// k-mer but one still differs from the empty marker 0; poly-A (both planes 0) does not, and is kept OUTSIDE the probed
+// range: slot [nlocal * subcap], the first of the spare bucket every table is allocated with.  The kernels that accept
+// k = 32 build their keys with make_key_k and reach that slot through the `key == 0` branches of table_update /
+// table_label_max / table_lookup2; they are the flat-tile, pair-loading, CTA-per-read and scan kernels.  The warp-per-read
+// and log kernels (the measured path, k <= 31) keep the constant tag and never see a zero key.
+__device__ __forceinline__ unsigned long long make_key_k(unsigned p0, unsigned p1, int k) {
+    return (k < 32 ? KEY_TAG : 0ull) | ((unsigned long long)p1 << 32) | p0;
+}
 // reverse complement in plane form: complement flips both code bits, reversal is a bit reversal
 __device__ __forceinline__ unsigned rc_plane(unsigned p, int k) { return __brev(~p) >> (32 - k); }
 
@@ -133,6 +144,9 @@ __device__ __forceinline__ bool probe_home(const Geo& g, unsigned long long key,
     return part < g.nlocal;
 }
 __device__ __forceinline__ void probe_next(const Geo& g, Probe& p) { p.off = (p.off + 1 == g.subcap) ? 0ull : p.off + 1; }
+// home of the one key that equals the empty marker (poly-A at k = 32): behind the last partition of an unsharded table
+template <typename S>
+__device__ __forceinline__ S* zero_key_slot(S* slots, const Geo& g) { return slots + (unsigned long long)g.nlocal * g.subcap; }
 
 // ---- table primitives --------------------------------------------------------------------------------
 // Keys never change once written and slots never return to empty, so a stale (L1/L2) read of a key can
@@ -158,6 +172,12 @@ __device__ __forceinline__ Slot* table_upsert_slot(const TableView& t, unsigned 
 // val += cnt (count tables) or val = max(val, cnt) (label tables)
 template <bool IS_MAX>
 __device__ __forceinline__ void table_update(const TableView& t, unsigned long long key, unsigned v, unsigned& claimed) {
+    if (key == 0ull) {              // poly-A at k = 32: no claim, the slot is its own (a first non-zero value = a new key)
+        Slot* z = zero_key_slot(t.slots, t.g);
+        const unsigned old = IS_MAX ? atomicMax(&z->val, v) : atomicAdd(&z->val, v);
+        if (old == 0u && v != 0u) claimed++;
+        return;
+    }
     Probe p;
     if (!probe_home(t.g, key, p)) { atomicExch(t.error, 2); return; }
     const unsigned long long cur = __ldcg(&t.slots[p.base + p.off].key);
@@ -173,6 +193,10 @@ __device__ __forceinline__ void table_update(const TableView& t, unsigned long l
 // that had to walk to an empty slot).  `rc` says which orientation the caller's k-mer has relative to the key.
 // Returns true when this call gave the (key, orientation) its first label, i.e. a new distinct forward k-mer.
 __device__ __forceinline__ bool table_label_max(const TableView& t, unsigned long long key, bool rc, unsigned lab) {
+    if (key == 0ull) {              // poly-A at k = 32 (rc: the bundle holds poly-T)
+        Slot* z = zero_key_slot(t.slots, t.g);
+        return lab != 0u && atomicMax(rc ? &z->aux : &z->val, lab) == 0u;
+    }
     Probe p;
     if (!probe_home(t.g, key, p)) { atomicExch(t.error, 2); return false; }
     const unsigned long long cur = __ldcg(&t.slots[p.base + p.off].key);
@@ -206,6 +230,11 @@ __device__ __forceinline__ uint2 table_lookup2(const Slot* __restrict__ slots, c
     bool open = valid;
     const unsigned part = hash_part(h, g.nparts) - g.part0;
     if (part >= g.nlocal) open = false;
+    if (valid && key == 0ull) {     // poly-A at k = 32: its own slot behind the partitions, nothing to compare
+        const uint4 z = __ldcg(reinterpret_cast<const uint4*>(zero_key_slot(slots, g)));
+        v = make_uint2(z.z, z.w);
+        open = false;
+    }
     const unsigned long long base = (unsigned long long)part * g.subcap;
     unsigned long long off = (unsigned long long)__umulhi(h.y, (unsigned)(g.subcap / BUCKET_SLOTS)) * BUCKET_SLOTS;
     // one bucket per round, the four slots examined in fill order

@@ -122,10 +122,10 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                     const unsigned bad = __funnelshift_r(ab, cb, s) & mk;
                     const unsigned f0 = __funnelshift_r(a0, c0, s) & mk;
                     const unsigned f1 = __funnelshift_r(a1, c1, s) & mk;
-                    unsigned long long kf = make_key(f0, f1);
+                    unsigned long long kf = make_key_k(f0, f1, k);
                     if (MODE == MODE_COUNT) {
                         if (canonical) {
-                            const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                            const unsigned long long kr = make_key_k(rc_plane(f0, k), rc_plane(f1, k), k);
                             kf = kr < kf ? kr : kf;
                         }
                     } else {
@@ -133,11 +133,16 @@ k_flat_tiles(const uint8_t* __restrict__ recs, uint64_t ntiles, int k, int canon
                         if (!bad) while (g0 + s >= next_off) { label++; next_off = offs[label + 1]; }
                         lab[u] = first_index + label + 1;
                         // label tables are keyed canonically with one label per orientation (tg_device.cuh)
-                        const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                        const unsigned long long kr = make_key_k(rc_plane(f0, k), rc_plane(f1, k), k);
                         if (kr < kf) { kf = kr; rcs |= 1u << u; }
                     }
                     key[u] = bad ? 0ull : kf;
                     cnt[u] = 1;
+                    if (k == 32 && !bad && kf == 0ull) {       // poly-A 32-mer: the key that reads as "no key" (tg_device.cuh)
+                        Slot* z = zero_key_slot(t.slots, t.g);
+                        if (MODE == MODE_COUNT) { if (atomicAdd(&z->val, 1u) == 0u) claimed++; }
+                        else if (atomicMax((rcs >> u) & 1u ? &z->aux : &z->val, lab[u]) == 0u) claimed++;
+                    }
                 }
                 if (MODE == MODE_COUNT) {
                     // run-length merge inside the group: homopolymer runs hit one slot once, not four times
@@ -884,8 +889,8 @@ k_load_pairs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ val
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         unsigned p0, p1;
         packed_to_planes(keys[i], k, p0, p1);
-        unsigned long long key = make_key(p0, p1);
-        const unsigned long long kr = make_key(rc_plane(p0, k), rc_plane(p1, k));
+        unsigned long long key = make_key_k(p0, p1, k);
+        const unsigned long long kr = make_key_k(rc_plane(p0, k), rc_plane(p1, k), k);
         if (IS_MAX) {          // label table: (forward k-mer, bundle index + 1) -> the field of its orientation
             if (table_label_max(t, kr < key ? kr : key, kr < key, vals[i])) claimed++;
         } else {
@@ -908,6 +913,12 @@ cudaError_t launch_load_pairs(const uint64_t* d_keys, const uint32_t* d_vals, ui
     return cudaGetLastError();
 }
 
+// Table scans cover slots [0, cap] -- cap is the zero-key slot (poly-A at k = 32, tg_device.cuh), which is live when it holds
+// a value although its key reads as empty; at k <= 31 it stays all zero.
+__device__ __forceinline__ bool slot_live(const uint4& s, uint64_t i, uint64_t cap) {
+    return (s.x | s.y) != 0u || (i == cap && (s.z | s.w) != 0u);
+}
+
 // Only a fraction of the slots pass the filter of a compaction pass (and a third are occupied at all): the survivors of a
 // warp's 32 slots are queued in shared memory and re-inserted 32 at a time, so that the probe + CAS + RED sequence always
 // runs on full warps instead of on the few lanes whose slot qualified.
@@ -927,12 +938,12 @@ k_rehash(const Slot* __restrict__ from, uint64_t from_cap, TableView to, int is_
         }
     };
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (from_cap + stride - 1) / stride;
+    const uint64_t rounds = (from_cap + 1 + stride - 1) / stride;
     for (uint64_t rd = 0; rd < rounds; rd++) {
         const uint64_t i = rd * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
         uint4 s = make_uint4(0u, 0u, 0u, 0u);
-        if (i < from_cap) s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
-        const bool keep = (s.x | s.y) != 0u && (is_label || (s.z >= min_val && s.z <= max_val));
+        if (i <= from_cap) s = __ldcs(reinterpret_cast<const uint4*>(&from[i]));
+        const bool keep = slot_live(s, i, from_cap) && (is_label || (s.z >= min_val && s.z <= max_val));
         const unsigned m = __ballot_sync(FULL, keep);
         if (keep) queue[w][nq + __popc(m & lt)] = s;
         nq += __popc(m);
@@ -974,9 +985,9 @@ k_histo(const Slot* __restrict__ slots, uint64_t cap, unsigned long long* __rest
     __shared__ unsigned int sb[HISTO_BINS];
     for (int i = threadIdx.x; i < HISTO_BINS; i += blockDim.x) sb[i] = 0;
     __syncthreads();
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&slots[i]));
-        if ((s.x | s.y) == 0u) continue;
+        if (!slot_live(s, i, cap)) continue;
         const unsigned c = s.z;
         atomicAdd(&sb[c > 10000u ? 10001u : c], 1u);
     }
@@ -999,14 +1010,14 @@ k_export(const Slot* __restrict__ slots, uint64_t cap, uint32_t min_count, uint3
          uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals, unsigned long long* __restrict__ out_n) {
     const int lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (cap + stride - 1) / stride;
+    const uint64_t rounds = (cap + 1 + stride - 1) / stride;
     for (uint64_t rd = 0; rd < rounds; rd++) {
         const uint64_t i = rd * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
         bool keep = false;
         uint4 s = make_uint4(0, 0, 0, 0);
-        if (i < cap) {
+        if (i <= cap) {
             s = __ldcs(reinterpret_cast<const uint4*>(&slots[i]));
-            keep = (s.x | s.y) != 0u && s.z >= min_count && s.z <= max_count;
+            keep = slot_live(s, i, cap) && s.z >= min_count && s.z <= max_count;
         }
         const unsigned m = __ballot_sync(FULL, keep);
         if (m == 0) continue;
@@ -1016,7 +1027,7 @@ k_export(const Slot* __restrict__ slots, uint64_t cap, uint32_t min_count, uint3
         if (keep) {
             const uint64_t o = basei + __popc(m & ((1u << lane) - 1u));
             if (out_keys) {
-                unsigned long long pk = planes_to_packed(s.x, s.y & 0x7FFFFFFFu, k);
+                unsigned long long pk = planes_to_packed(s.x, s.y, k);        // (reads bits 0..k-1 of each plane: the tag is ignored)
                 if (canonical_repr) {           // jellyfish prints the lexicographically smaller strand (A<C<G<T)
                     const unsigned long long rc = packed_revcomp(pk, k);
                     pk = rc < pk ? rc : pk;
@@ -1047,9 +1058,9 @@ cudaError_t launch_export(const Slot* slots, uint64_t cap, uint32_t min_count, u
 __global__ void __launch_bounds__(256)
 k_table_sum(const Slot* __restrict__ slots, uint64_t cap, unsigned long long* __restrict__ out) {
     unsigned long long acc = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 s = __ldcs(reinterpret_cast<const uint4*>(&slots[i]));
-        if ((s.x | s.y) != 0u) acc += s.z;
+        if (slot_live(s, i, cap)) acc += s.z;
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);

@@ -369,12 +369,34 @@ k_cov_stats(const uint8_t* __restrict__ recs, const uint64_t* __restrict__ offs,
     stats_flush(sw, nb, stdev, lane);
 }
 
+// k = 32: the warp-per-read kernels build their keys with the constant tag (k <= 31, tg_device.cuh), so every read takes
+// the CTA-per-read path instead -- the long list is simply all reads.  (The caller has zeroed {count, max_win}.)
+__global__ void __launch_bounds__(256)
+k_list_all_reads(const uint64_t* __restrict__ offs, uint64_t nreads, int k, LongList ll) {
+    unsigned mw = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nreads; i += (uint64_t)gridDim.x * blockDim.x) {
+        ll.idx[i] = (unsigned)i;
+        const long long L = (long long)(offs[i + 1] - offs[i]) - 1;
+        if (L >= k) mw = max(mw, (unsigned)(L - k + 1));
+    }
+    mw = __reduce_max_sync(FULL, mw);
+    if ((threadIdx.x & 31) == 0 && mw) atomicMax(ll.max_win, mw);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(ll.count, (unsigned)nreads); atomicMax(ll.max_win, 1u); }   // (scratch sizes are never zero)
+}
+static cudaError_t launch_list_all_reads(const uint64_t* d_offs, uint64_t nreads, int k, LongList ll, cudaStream_t s) {
+    uint64_t blocks = (nreads + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_list_all_reads<<<(unsigned)blocks, 256, 0, s>>>(d_offs, nreads, k, ll);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cov_stats(const uint8_t* d_recs, const uint64_t* d_offs, uint64_t rec_base, uint64_t nreads, int k,
                              int canonical, const Slot* slots, Geo geo, uint32_t* d_median, float* d_mean,
                              float* d_stdev, uint32_t* d_per_kmer, LongList ll, const uint32_t* d_order, int arena,
                              const uint32_t* d_counts, cudaStream_t s) {
     TimedLaunch timed("k_cov_stats", s);
     if (nreads == 0) return cudaSuccess;
+    if (k > 31) return launch_list_all_reads(d_offs, nreads, k, ll, s);
     if (arena < PR_MAXWIN) arena = PR_MAXWIN;              // one read of the warp path must fit
     const size_t dyn = stats_warp_bytes(arena) * PR_WARPS;
     const void* kern = d_counts ? (const void*)k_cov_stats<true> : (const void*)k_cov_stats<false>;
@@ -422,9 +444,9 @@ __device__ __forceinline__ void read_cov_stats(const uint8_t* __restrict__ seq, 
             if (!bad) {
                 const unsigned f0 = __funnelshift_r(P0[c], P0[c + 1], o) & mk;
                 const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
-                key = make_key(f0, f1);
+                key = make_key_k(f0, f1, k);
                 if (canonical) {
-                    const unsigned long long kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                    const unsigned long long kr = make_key_k(rc_plane(f0, k), rc_plane(f1, k), k);
                     key = kr < key ? kr : key;
                 }
                 ok = true;
@@ -725,6 +747,7 @@ cudaError_t launch_assign(const uint8_t* d_recs, const uint64_t* d_offs, uint64_
                           int32_t* d_pct, int32_t* d_score, LongList ll, const uint32_t* d_order, cudaStream_t s) {
     TimedLaunch timed("k_assign", s);
     if (nreads == 0) return cudaSuccess;
+    if (k > 31) return launch_list_all_reads(d_offs, nreads, k, ll, s);
     const uint64_t blocks = (nreads + PR_WARPS - 1) / PR_WARPS;
     k_assign<<<(unsigned)blocks, PR_WARPS * 32, 0, s>>>(d_recs, d_offs, rec_base, nreads, k, strand, slots, geo,
                                                         d_entropy_ok, d_best, d_pct, d_score, ll, d_order);
@@ -760,7 +783,7 @@ __device__ __forceinline__ void read_assign(const uint8_t* __restrict__ seq, int
                 const unsigned f1 = __funnelshift_r(P1[c], P1[c + 1], o) & mk;
                 do_f = window_entropy_ok(lut, f0, f1, mk, false);
                 do_r = !strand && window_entropy_ok(lut, f0, f1, mk, true);
-                const unsigned long long kf = make_key(f0, f1), kr = make_key(rc_plane(f0, k), rc_plane(f1, k));
+                const unsigned long long kf = make_key_k(f0, f1, k), kr = make_key_k(rc_plane(f0, k), rc_plane(f1, k), k);
                 is_rc = kr < kf; pal = kr == kf;
                 key = is_rc ? kr : kf;
             }

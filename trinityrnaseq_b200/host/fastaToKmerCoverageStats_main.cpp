@@ -89,7 +89,6 @@ int main(int argc, char** argv) {
         if (K < 20) { fprintf(stderr, "Error, min kmer size is 20"); return 2; }
     }
     if (K > 32) { fprintf(stderr, "ERROR encountered: \n\nKmer length exceeds max of 32"); return 1; }
-    if (K > 31) { fprintf(stderr, "ERROR: kmer size 32 is not supported by the GPU k-mer table (max 31)\n"); return 1; }
     const bool capture = args.isSet("--capture_coverage_info");
 
     Trace trace;

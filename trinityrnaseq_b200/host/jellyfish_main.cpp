@@ -168,7 +168,7 @@ int cmd_count(int argc, char** argv) {
     if (!o.has("-m", "--mer-len")) die_usage("count: missing required option -m, --mer-len");
     if (!o.has("-s", "--size")) die_usage("count: missing required option -s, --size");
     const int k = atoi(o.get("-m", "--mer-len", "0").c_str());
-    if (k < 1 || k > 31) die_usage("count: mer length must be in 1..31 for the GPU k-mer table");
+    if (k < 1 || k > 32) die_usage("count: mer length must be in 1..32 for the GPU k-mer table");
     const uint64_t size_hint = parse_size(o.get("-s", "--size", "0"));
     const std::string out_path = o.get("-o", "--output", "mer_counts.jf");
     const int canonical = o.has("-C", "--canonical") ? 1 : 0;
