@@ -187,3 +187,15 @@ def test_parallel_fasta_parser_equals_serial(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "parallel parse == serial parse" in r.stdout
+
+
+def test_float_formatting_equals_printf_g(tmp_path):
+    """host/fmt_float.hpp (std::to_chars) prints what printf("%g") prints -- the reference's ostream default -- for 3 M floats
+    of every kind, NaN signs and infinities included (tests/cpp/fmt_float_test.cpp)."""
+    import subprocess
+    exe = tmp_path / "fmt_float_test"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "trinityrnaseq_b200", "host"),
+                    "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "fmt_float_test.cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "0 differences" in r.stdout

@@ -11,12 +11,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=20_000_000)
 ap.add_argument("--read-len", type=int, default=100)
 ap.add_argument("--gpus", default="")
+ap.add_argument("--variants", default="", help="environment variants, e.g. 'A=1,B=2;;C=3' (an empty one = defaults)")
 a = ap.parse_args()
 ctx = tg.Context(0)
 tx, tx_offs, tx_cum = make_transcriptome(20000, SEED)
 d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, a.reads // 2, a.read_len, seed=SEED)
 recs = ctx.d2h(d_recs, nbytes, np.uint8).copy()
-ctx.close()
+ctx.dev_free(d_recs)        # (the context stays open, as the bench's does while it times the executable)
 exe = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "fastaToKmerCoverageStats")
 with tempfile.TemporaryDirectory() as td:
     fa = os.path.join(td, "reads.fa")
@@ -24,12 +25,19 @@ with tempfile.TemporaryDirectory() as td:
     env = dict(os.environ, TRINITY_GPU_TRACE="1")
     if a.gpus:
         env["TRINITY_GPUS"] = a.gpus
-    for rep in range(2):
+    variants = [{}, {}, {}]
+    if a.variants:
+        variants = [dict(kv.split("=") for kv in v.split(",") if kv) for v in a.variants.split(";")]
+    for rep, extra in enumerate(variants):
+        run_env = dict(env, **extra)
+        print("env", extra)
+        print(f"launch at wall {time.time():.3f}")
         t0 = time.perf_counter()
         with open(os.path.join(td, "out.stats"), "wb") as so:
             r = subprocess.run([exe, "--reads", fa, "--kmers_from_reads", fa, "--kmer_size", str(K), "--DS"], stdout=so,
-                               stderr=subprocess.PIPE, env=env)
+                               stderr=subprocess.PIPE, env=run_env)
         dt = time.perf_counter() - t0
+        print(f"reaped at wall {time.time():.3f}")
         print(f"rep {rep}: rc {r.returncode}, wall {dt:.3f} s, fasta {os.path.getsize(fa) / 1e9:.2f} GB, out "
               f"{os.path.getsize(os.path.join(td, 'out.stats')) / 1e9:.2f} GB")
         print("\n".join(l for l in r.stderr.decode().splitlines() if "[trace]" in l))

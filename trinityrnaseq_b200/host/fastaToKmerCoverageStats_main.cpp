@@ -2,6 +2,7 @@
 // Inchworm/src/fastaToKmerCoverageStats.cpp).  Same argv, same stdout format, same exit codes; the k-mer table
 // and the per-read statistics run on the GPU through libtrinity_gpu.
 #include <math.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -10,11 +11,13 @@
 #include <condition_variable>
 #include <mutex>
 #include <map>
+#include <memory>
 #include <thread>
 #include <string>
 #include <vector>
 
 #include "fasta_io.hpp"
+#include "fmt_float.hpp"
 #include "par_fasta.hpp"
 #include "multi_gpu.hpp"
 #include "tg_loader.hpp"
@@ -60,12 +63,6 @@ static void usage() {
             "\n\n\n");
 }
 
-// iostream default float formatting (precision 6, %g); x86 default NaN carries the sign bit -> "-nan"
-static int fmt_float(char* out, float f) {
-    if (isnan(f)) return sprintf(out, signbit(f) ? "-nan" : "nan");
-    return sprintf(out, "%g", (double)f);
-}
-
 // TRINITY_GPU_TRACE=1: wall-clock seconds of the tool's phases on stderr (where does a whole-process run spend its time?)
 struct Trace {
     bool on = getenv("TRINITY_GPU_TRACE") != nullptr;
@@ -73,6 +70,12 @@ struct Trace {
     double acc[4] = {0, 0, 0, 0};                 // parse wait, GPU call, format/write wait, other
     double now() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
     void mark(const char* what) const { if (on) fprintf(stderr, "[trace] %8.3f s  %s\n", now(), what); }
+    // absolute time, to place the process's start and end inside the caller's own clock (exec + exit are not ours to see)
+    void wall(const char* what) const {
+        if (!on) return;
+        struct timespec ts; clock_gettime(CLOCK_REALTIME, &ts);
+        fprintf(stderr, "[trace] wall %.3f  %s\n", (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec, what);
+    }
 };
 
 int main(int argc, char** argv) {
@@ -92,12 +95,50 @@ int main(int argc, char** argv) {
     const bool capture = args.isSet("--capture_coverage_info");
 
     Trace trace;
+    trace.wall("main");
     tgh::GpuSet gpus;                       // TRINITY_GPUS=0,1,..: the reads of every batch are split over these devices
-    gpus.open();
-    trace.mark("device context(s) open");
-    tg_ctx* ctx = gpus.ctx[0];              // the table is built on the first one and replicated (multi_gpu.hpp)
+    // Creating the CUDA context(s) takes a few tenths of a second in which the host has nothing to wait for: it runs on a
+    // thread of its own while the first chunks of the input are being parsed, and is joined before the first library call.
+    struct Opener {
+        std::thread th; bool joined = false;
+        void wait() { if (!joined) { th.join(); joined = true; } }
+        ~Opener() { wait(); }
+    } opener;
+    opener.th = std::thread([&gpus] { gpus.open(); });
+    tg_ctx* ctx = nullptr;                  // the table is built on the first device and replicated (multi_gpu.hpp)
+    auto wait_ctx = [&] {
+        if (opener.joined) return;
+        opener.wait();
+        trace.mark("device context(s) open");
+        ctx = gpus.ctx[0];
+    };
     tg_table* table = nullptr;
     std::string err;
+    const unsigned nthreads_host = host_threads(HOST_THREADS_CAP);
+    const unsigned parse_window = nthreads_host + 2;      // parsed-or-in-flight chunks: every thread of the pool has one
+
+    FileView rv;
+    std::unique_ptr<OrderedChunkParser> reads_parser;
+    auto start_reads_parser = [&]() -> bool {
+        if (reads_parser) return true;
+        if (!rv.open(reads_file, &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return false; }
+        reads_parser.reset(new OrderedChunkParser(rv.data, rv.size, CHUNK_BYTES, nthreads_host, parse_window,
+            [](const char* d, size_t n, RecordBatch& rb) {
+                rb.recs.reserve(n); rb.offs.reserve(n / 48 + 16); rb.names.reserve(n / 6); rb.name_offs.reserve(n / 48 + 16);
+                InchwormFastaReader rd(d, n);
+                const char* h; size_t hl;
+                while (true) {
+                    const size_t before = rb.recs.size();
+                    if (!rd.next(&h, &hl, rb.recs)) break;                       // the cleaned sequence lands in the batch directly
+                    if (rb.recs.size() == before) continue;                      // :132-133
+                    const char* acc; size_t al;
+                    accession_of(h, hl, &acc, &al);
+                    rb.end_record();
+                    rb.add_name(acc, al);
+                }
+            }));
+        return true;
+    };
 
     // ---- load the k-mer table --------------------------------------------------------------------------
     if (args.isSet("--kmers")) {
@@ -107,6 +148,7 @@ int main(int argc, char** argv) {
         if (!fv.open(args.str("--kmers"), &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
         fprintf(stderr, "-reading Kmer occurrences...\n");
         time_t start = time(NULL);
+        wait_ctx();
         TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 32 + 1024, &table));
         // Binary hand-off (tg_sidecar.hpp): if our `jellyfish dump` left `<kmers>.tgk` and it provably describes THIS
         // file (length + content hash), load the packed pairs and skip the text parse.  Same records, same
@@ -178,10 +220,10 @@ int main(int argc, char** argv) {
         FileView fv;
         if (!fv.open(args.str("--kmers_from_reads"), &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
         fprintf(stderr, "-storing Kmers...\n");
-        TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 4 + 1024, &table));
         // chunks of the file are parsed by a pool of threads and counted in file order (par_fasta.hpp)
-        OrderedChunkParser parser(fv.data, fv.size, CHUNK_BYTES, host_threads(HOST_THREADS_CAP), 4,
+        OrderedChunkParser parser(fv.data, fv.size, CHUNK_BYTES, nthreads_host, parse_window,
             [K](const char* d, size_t n, RecordBatch& rb) {
+                rb.recs.reserve(n); rb.offs.reserve(n / 48 + 16);      // (no regrowth copies: the cleaned text is shorter than the chunk)
                 InchwormFastaReader rd(d, n);
                 const char* h; size_t hl;
                 while (true) {
@@ -191,6 +233,8 @@ int main(int argc, char** argv) {
                     rb.end_record();
                 }
             });
+        wait_ctx();
+        TGC(tg_table_create(ctx, TG_TABLE_COUNT, K, fv.size / 4 + 1024, &table));
         RecordBatch rb;
         while (parser.next(rb))
             if (!rb.recs.empty()) TGC(tg_count_reads(table, rb.recs.data(), rb.recs.size(), is_DS));
@@ -217,28 +261,13 @@ int main(int argc, char** argv) {
     }
 
     // ---- per-read statistics ----------------------------------------------------------------------------
-    FileView rv;
-    if (!rv.open(reads_file, &err)) { fprintf(stderr, "ERROR encountered: \n\nError, %s", err.c_str()); return 1; }
+    if (!start_reads_parser()) return 1;
+    OrderedChunkParser& parser = *reads_parser;
     time_t start_time = time(NULL);
     OutBuf out(1);
     out.put("acc\tmedian_cov\tmean_cov\tstdev\ttid\n");
     // Pipeline (all in file order): a pool of threads parses chunks of the file; the main thread runs the statistics of
     // batch i on the GPU while the lines of batch i - 1 are being formatted by the pool's cores, and writes them out.
-    const unsigned nthreads_host = host_threads(HOST_THREADS_CAP);
-    OrderedChunkParser parser(rv.data, rv.size, CHUNK_BYTES, nthreads_host, 4,
-        [](const char* d, size_t n, RecordBatch& rb) {
-            InchwormFastaReader rd(d, n);
-            const char* h; size_t hl;
-            while (true) {
-                const size_t before = rb.recs.size();
-                if (!rd.next(&h, &hl, rb.recs)) break;                       // the cleaned sequence lands in the batch directly
-                if (rb.recs.size() == before) continue;                      // :132-133
-                const char* acc; size_t al;
-                accession_of(h, hl, &acc, &al);
-                rb.end_record();
-                rb.add_name(acc, al);
-            }
-        });
     struct Job {
         RecordBatch rb;
         std::vector<uint32_t> median, per_kmer;
@@ -247,7 +276,9 @@ int main(int argc, char** argv) {
         std::vector<char> negs;
         std::thread formatter;
         uint64_t ticket = 0;                      // position of the batch in file order
-    } jobs[2];
+    };
+    constexpr unsigned NJOBS = 4;                 // batches between the GPU call and the last byte written
+    Job jobs[NJOBS];
     bool negative = false;
     // Lines leave in file order, but not through the main thread: the thread that formatted batch i also writes it, as
     // soon as batch i - 1 is out (a ticket), while the main thread is already running batch i + 1 on the GPU.
@@ -317,9 +348,9 @@ int main(int argc, char** argv) {
     if (!out.flush()) { fprintf(stderr, "ERROR: write to stdout failed\n"); return 1; }     // the header line goes first
     uint64_t next_ticket = 0;
     for (unsigned it = 0;; it++) {
-        Job& jb = jobs[it & 1];
+        Job& jb = jobs[it % NJOBS];
         double tt = trace.now();
-        finish_job(jb);                          // the job that used this slot two batches ago
+        finish_job(jb);                          // the job that used this slot NJOBS batches ago
         trace.acc[2] += trace.now() - tt; tt = trace.now();
         if (!parser.next(jb.rb)) break;
         trace.acc[0] += trace.now() - tt;
@@ -348,8 +379,7 @@ int main(int argc, char** argv) {
         jb.ticket = next_ticket++;
         jb.formatter = std::thread([&format_job, &write_job, &jb] { format_job(jb); write_job(jb); });
     }
-    finish_job(jobs[0]);
-    finish_job(jobs[1]);
+    for (unsigned j = 0; j < NJOBS; j++) finish_job(jobs[j]);
     if (trace.on) fprintf(stderr, "[trace] statistics loop: waiting for parsed batches %.3f s, GPU calls %.3f s, waiting for format+write %.3f s\n",
                           trace.acc[0], trace.acc[1], trace.acc[2]);
     trace.mark("statistics done");
@@ -359,6 +389,7 @@ int main(int argc, char** argv) {
     trace.mark("output complete");
     // Everything is written.  Leave without tearing gigabytes of tables, mappings and buffers down one by one: the
     // operating system and the driver reclaim them at process exit (this was 0.4 s of a 2.7 s run on a 20 M-read file).
+    trace.wall("exit");
     fflush(stderr);
     _exit(0);
 }
