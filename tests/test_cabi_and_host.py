@@ -199,3 +199,49 @@ def test_float_formatting_equals_printf_g(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "0 differences" in r.stdout
+
+
+def test_jellyfish_dump_blocks_and_threads(tmp_path):
+    """`jellyfish dump` formats its records on a pool of threads, block by block (host/jellyfish_main.cpp); the text, the
+    -L/-U filter and the .tgk sidecar (packed k-mers, counts, length and hash of the text) must be what one loop over the
+    table writes.  No GPU involved: dump only reads the database file.  2.5 M k-mers = two blocks, every thread busy."""
+    import struct
+    import subprocess
+    jf = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "jellyfish")
+    if not os.path.exists(jf):
+        pytest.skip("executables not built")
+    k, n = 25, 2_500_000
+    rng = np.random.default_rng(77)
+    keys = np.unique(rng.integers(0, 1 << 50, size=n, dtype=np.uint64))
+    n = len(keys)
+    cnts = rng.integers(10, 100, size=n).astype(np.uint32)          # two digits: fixed-width records, built with numpy below
+    db = tmp_path / "t.jf"
+    db.write_bytes(b"TGJF001\n" + struct.pack("<IIQ", k, 1, n) + b"\0" * (8 * 10002) + keys.tobytes() + cnts.tobytes())
+
+    def expected(sel):
+        kk, cc = keys[sel], cnts[sel]
+        m = len(kk)
+        lines = np.empty((m, 4 + k + 1), dtype=np.uint8)
+        lines[:, 0] = ord(">")
+        lines[:, 1] = ord("0") + cc // 10
+        lines[:, 2] = ord("0") + cc % 10
+        lines[:, 3] = ord("\n")
+        shifts = (2 * (k - 1 - np.arange(k))).astype(np.uint64)
+        codes = ((kk[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
+        lines[:, 4:4 + k] = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+        lines[:, 4 + k] = ord("\n")
+        return lines.tobytes()
+
+    for lo, hi in ((1, None), (20, 80)):
+        out = tmp_path / f"dump_{lo}.fa"
+        cmd = [jf, "dump", "-L", str(lo)] + (["-U", str(hi)] if hi else []) + ["-o", str(out), str(db)]
+        r = subprocess.run(cmd, capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+        sel = (cnts >= lo) & (cnts <= (hi if hi else 0xFFFFFFFF))
+        want = expected(sel)
+        assert out.read_bytes() == want
+        side = (tmp_path / f"dump_{lo}.fa.tgk").read_bytes()
+        magic, sk, _, sn, text_bytes, _ = struct.unpack("<8sIIQQQ", side[:40])
+        assert magic == b"TGKMER1\n" and sk == k and sn == int(sel.sum()) and text_bytes == len(want)
+        assert np.array_equal(np.frombuffer(side[40:40 + 8 * sn], dtype=np.uint64), keys[sel])
+        assert np.array_equal(np.frombuffer(side[40 + 8 * sn:], dtype=np.uint32), cnts[sel])

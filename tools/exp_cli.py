@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=20_000_000)
 ap.add_argument("--read-len", type=int, default=100)
 ap.add_argument("--gpus", default="")
+ap.add_argument("--jellyfish", action="store_true", help="also time jellyfish count / dump -L 1 / dump -L 2 on the file")
 ap.add_argument("--variants", default="", help="environment variants, e.g. 'A=1,B=2;;C=3' (an empty one = defaults)")
 a = ap.parse_args()
 ctx = tg.Context(0)
@@ -41,3 +42,17 @@ with tempfile.TemporaryDirectory() as td:
         print(f"rep {rep}: rc {r.returncode}, wall {dt:.3f} s, fasta {os.path.getsize(fa) / 1e9:.2f} GB, out "
               f"{os.path.getsize(os.path.join(td, 'out.stats')) / 1e9:.2f} GB")
         print("\n".join(l for l in r.stderr.decode().splitlines() if "[trace]" in l))
+
+    if a.jellyfish:
+        jf = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "jellyfish")
+        db = os.path.join(td, "mer.jf")
+        for rep in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([jf, "count", "-t", "16", "-m", str(K), "-s", "1000000000", "--canonical", "-o", db, fa], stderr=subprocess.PIPE)
+            t1 = time.perf_counter()
+            print(f"jellyfish count rep {rep}: rc {r.returncode}, {t1 - t0:.3f} s, db {os.path.getsize(db) / 1e9:.2f} GB")
+        for L in (1, 2):
+            t0 = time.perf_counter()
+            r = subprocess.run([jf, "dump", "-L", str(L), "-o", os.path.join(td, "dump.fa"), db], stderr=subprocess.PIPE)
+            t1 = time.perf_counter()
+            print(f"jellyfish dump -L {L}: rc {r.returncode}, {t1 - t0:.3f} s, text {os.path.getsize(os.path.join(td, 'dump.fa')) / 1e9:.2f} GB")

@@ -14,6 +14,7 @@
 
 #include "fasta_io.hpp"
 #include "seq_file.hpp"
+#include "par_fasta.hpp"
 #include "multi_gpu.hpp"
 #include "tg_loader.hpp"
 #include "tg_sidecar.hpp"
@@ -145,18 +146,40 @@ void count_file(std::vector<CountWorker>& workers, size_t& next, tg_table* table
     if (!fv.open(path, &err)) { fprintf(stderr, "jellyfish: %s\n", err.c_str()); exit(1); }
     std::vector<char> recs;
     // record bytes per counted chunk (TRINITY_GPU_COUNT_CHUNK: a test knob -- tiny chunks spread a tiny file over the devices)
-    const size_t FLUSH = getenv("TRINITY_GPU_COUNT_CHUNK") ? (size_t)strtoull(getenv("TRINITY_GPU_COUNT_CHUNK"), nullptr, 10) : (256u << 20);
+    const bool knob = getenv("TRINITY_GPU_COUNT_CHUNK") != nullptr;
+    const size_t FLUSH = knob ? (size_t)strtoull(getenv("TRINITY_GPU_COUNT_CHUNK"), nullptr, 10) : (256u << 20);
+    auto consume = [&](std::vector<char>& r) {
+        if (r.empty()) return;
+        if (workers.empty()) {
+            TGC(tg_count_reads(table, r.data(), r.size(), canonical));
+        } else {
+            workers[next % workers.size()].give(r);
+            next++;
+        }
+        r.clear();
+    };
+    // FASTA (what Trinity feeds it: both.fa) splits at any line that starts with '>': chunks are parsed by a pool of threads
+    // with the same parser and counted in file order (par_fasta.hpp) -- one thread walking a multi-gigabyte file was most of
+    // the tool's wall time.  FASTQ records cannot be told from quality lines without context: one thread, as before.
+    const char* q = fv.data;
+    const char* fend = fv.data + fv.size;
+    while (q < fend && (*q == '\n' || *q == '\r')) q++;
+    const bool fasta = q < fend && *q == '>';
+    const unsigned nthreads = host_threads(32);
+    if (fasta && !knob && fv.size >= (64u << 20) && nthreads > 1) {
+        OrderedChunkParser parser(fv.data, fv.size, 48u << 20, nthreads, nthreads + 2,
+            [](const char* d, size_t n, RecordBatch& rb) {
+                rb.recs.reserve(n);
+                parse_sequence_file(d, d + n, rb.recs, (size_t)-1, [] {});
+            });
+        RecordBatch rb;
+        while (parser.next(rb)) consume(rb.recs);
+        return;
+    }
     recs.reserve(FLUSH + (64u << 20));
     parse_sequence_file(fv.data, fv.data + fv.size, recs, FLUSH, [&]() {
-        if (recs.empty()) return;
-        if (workers.empty()) {
-            TGC(tg_count_reads(table, recs.data(), recs.size(), canonical));
-        } else {
-            workers[next % workers.size()].give(recs);
-            next++;
-            recs.reserve(FLUSH + (64u << 20));
-        }
-        recs.clear();
+        consume(recs);
+        if (!workers.empty()) recs.reserve(FLUSH + (64u << 20));
     });
 }
 
@@ -279,48 +302,95 @@ int cmd_dump(int argc, char** argv) {
     }
     tgside::TextHash hash;
     {
-        OutBuf out(fd, 16u << 20);
-        char line[96];
+        // The records are formatted by a pool of threads, a block of BLOCK k-mers at a time (thread w takes the w-th slice
+        // of the block and writes its lines -- and, for the sidecar, the packed k-mers it printed -- into buffers of its
+        // own); the main thread writes block i, hashes it and appends the sidecar keys while block i + 1 is being formatted.
+        // Same bytes in the same order as one loop over the table; memory stays O(BLOCK).
         auto put_uint = [](char* dst, uint32_t v) {             // decimal without sprintf: this loop runs 10^8 times
             char tmp[12]; int n = 0;
             do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
             for (int i = 0; i < n; i++) dst[i] = tmp[n - 1 - i];
             return n;
         };
-        for (uint64_t i = 0; i < jf.h->n; i++) {
-            const uint32_t c = jf.counts[i];
-            if (c < lower || c > upper) continue;
-            int n;
-            if (column) {                                       // "KMER COUNT"
-                tgh::unpack_kmer(jf.keys[i], k, line);
-                n = k;
-                line[n++] = tab ? '\t' : ' ';
-                n += put_uint(line + n, c);
-                line[n++] = '\n';
-            } else {                                            // FASTA: ">COUNT\nKMER\n"
-                line[0] = '>';
-                n = 1 + put_uint(line + 1, c);
-                line[n++] = '\n';
-                tgh::unpack_kmer(jf.keys[i], k, line + n);
-                n += k;
-                line[n++] = '\n';
+        const uint64_t total = jf.h->n;
+        const unsigned nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(host_threads(32), total / 65536 + 1));
+        const uint64_t BLOCK = 1u << 21;
+        struct Block { std::vector<std::vector<char>> text; std::vector<std::vector<uint64_t>> keys; };
+        Block blocks[2];
+        for (auto& b : blocks) { b.text.resize(nt); b.keys.resize(nt); }
+        const bool want_keys = sf != nullptr;
+        auto format_block = [&](Block& blk, uint64_t b0) {
+            const uint64_t b1 = std::min(total, b0 + BLOCK);
+            parallel_for_threads(nt, [&](unsigned w) {
+                std::vector<char>& buf = blk.text[w];
+                std::vector<uint64_t>& kk = blk.keys[w];
+                buf.clear(); kk.clear();
+                const uint64_t a = b0 + (b1 - b0) * w / nt, e = b0 + (b1 - b0) * (w + 1) / nt;
+                buf.resize((size_t)(e - a) * (size_t)(k + 14));          // (longest record: '>' + 10 digits + 2 newlines + k)
+                char* line = buf.data();
+                for (uint64_t i = a; i < e; i++) {
+                    const uint32_t c = jf.counts[i];
+                    if (c < lower || c > upper) continue;
+                    int n;
+                    if (column) {                                       // "KMER COUNT"
+                        tgh::unpack_kmer(jf.keys[i], k, line);
+                        n = k;
+                        line[n++] = tab ? '\t' : ' ';
+                        n += put_uint(line + n, c);
+                        line[n++] = '\n';
+                    } else {                                            // FASTA: ">COUNT\nKMER\n"
+                        line[0] = '>';
+                        n = 1 + put_uint(line + 1, c);
+                        line[n++] = '\n';
+                        tgh::unpack_kmer(jf.keys[i], k, line + n);
+                        n += k;
+                        line[n++] = '\n';
+                    }
+                    line += n;
+                    if (want_keys) kk.push_back(jf.keys[i]);
+                }
+                buf.resize((size_t)(line - buf.data()));
+            });
+        };
+        bool write_ok = true;
+        auto write_all = [&](const char* p, size_t n) {               // (the slices are megabytes: no staging copy)
+            while (n && write_ok) {
+                const ssize_t w = ::write(fd, p, n);
+                if (w < 0) { if (errno == EINTR) continue; write_ok = false; break; }
+                p += w; n -= (size_t)w;
             }
-            out.put(line, (size_t)n);
-            if (sf) {
-                hash.update(line, (size_t)n);
-                side_ok = side_ok && fwrite(&jf.keys[i], 8, 1, sf) == 1;
-                side_n++;
-            }
+        };
+        std::thread ahead;
+        if (total) format_block(blocks[0], 0);
+        for (uint64_t b0 = 0, it = 0; b0 < total; b0 += BLOCK, it++) {
+            Block& cur = blocks[it & 1];
+            if (b0 + BLOCK < total) ahead = std::thread([&, it, b0] { format_block(blocks[(it + 1) & 1], b0 + BLOCK); });
+            std::thread side_thread;                      // the sidecar's share of the block (hash of the text, packed k-mers) beside the write
+            if (sf) side_thread = std::thread([&] {
+                for (unsigned w = 0; w < nt; w++) {
+                    hash.update(cur.text[w].data(), cur.text[w].size());
+                    if (!cur.keys[w].empty())
+                        side_ok = side_ok && fwrite(cur.keys[w].data(), 8, cur.keys[w].size(), sf) == cur.keys[w].size();
+                    side_n += cur.keys[w].size();
+                }
+            });
+            for (unsigned w = 0; w < nt; w++) write_all(cur.text[w].data(), cur.text[w].size());
+            if (side_thread.joinable()) side_thread.join();
+            if (ahead.joinable()) ahead.join();
         }
-        if (!out.flush()) { fprintf(stderr, "jellyfish: write failed: %s\n", strerror(errno)); if (sf) { fclose(sf); unlink(side_tmp.c_str()); } return 1; }
+        if (!write_ok) { fprintf(stderr, "jellyfish: write failed: %s\n", strerror(errno)); if (sf) { fclose(sf); unlink(side_tmp.c_str()); } return 1; }
     }
     if (fd != 1) ::close(fd);
     if (sf) {
+        std::vector<uint32_t> pass;                       // the counts that passed the filter, a million at a time
+        pass.reserve(1u << 20);
         for (uint64_t i = 0; side_ok && i < jf.h->n; i++) {
             const uint32_t c = jf.counts[i];
             if (c < lower || c > upper) continue;
-            side_ok = fwrite(&c, 4, 1, sf) == 1;
+            pass.push_back(c);
+            if (pass.size() == (1u << 20)) { side_ok = fwrite(pass.data(), 4, pass.size(), sf) == pass.size(); pass.clear(); }
         }
+        if (side_ok && !pass.empty()) side_ok = fwrite(pass.data(), 4, pass.size(), sf) == pass.size();
         memcpy(sh.magic, tgside::TGK_MAGIC, 8);
         sh.k = (uint32_t)k; sh.n = side_n; sh.text_bytes = hash.total; sh.text_hash = hash.digest();
         side_ok = side_ok && fseek(sf, 0, SEEK_SET) == 0 && fwrite(&sh, sizeof sh, 1, sf) == 1;
