@@ -6,12 +6,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import trinityrnaseq_b200 as tg
-from bench import make_transcriptome, write_sample_fasta, SEED, K
+from bench import make_transcriptome, make_bundles, write_sample_fasta, SEED, K
 ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=20_000_000)
 ap.add_argument("--read-len", type=int, default=100)
 ap.add_argument("--gpus", default="")
 ap.add_argument("--jellyfish", action="store_true", help="also time jellyfish count / dump -L 1 / dump -L 2 on the file")
+ap.add_argument("--r2t", action="store_true", help="also time the ReadsToTranscripts executable on the file (bundles cut from the transcriptome)")
+ap.add_argument("--no-stats", action="store_true")
 ap.add_argument("--variants", default="", help="environment variants, e.g. 'A=1,B=2;;C=3' (an empty one = defaults)")
 a = ap.parse_args()
 ctx = tg.Context(0)
@@ -29,6 +31,8 @@ with tempfile.TemporaryDirectory() as td:
     variants = [{}, {}, {}]
     if a.variants:
         variants = [dict(kv.split("=") for kv in v.split(",") if kv) for v in a.variants.split(";")]
+    if a.no_stats:
+        variants = []
     for rep, extra in enumerate(variants):
         run_env = dict(env, **extra)
         print("env", extra)
@@ -56,3 +60,19 @@ with tempfile.TemporaryDirectory() as td:
             r = subprocess.run([jf, "dump", "-L", str(L), "-o", os.path.join(td, "dump.fa"), db], stderr=subprocess.PIPE)
             t1 = time.perf_counter()
             print(f"jellyfish dump -L {L}: rc {r.returncode}, {t1 - t0:.3f} s, text {os.path.getsize(os.path.join(td, 'dump.fa')) / 1e9:.2f} GB")
+
+    if a.r2t:
+        brecs, boffs, ncontigs = make_bundles(tx, tx_offs, SEED + 1)
+        bf = os.path.join(td, "bundles.fa")
+        with open(bf, "wb") as f:
+            for i in range(len(boffs) - 1):
+                f.write(b">s_%d 10\n" % i)
+                f.write(brecs[int(boffs[i]):int(boffs[i + 1])].tobytes())
+        r2t = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "ReadsToTranscripts")
+        for rep in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([r2t, "-i", fa, "-f", bf, "-o", os.path.join(td, "r2t.out"), "-t", "16", "-max_mem_reads", "50000000", "-p", "10"],
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+            dt = time.perf_counter() - t0
+            print(f"ReadsToTranscripts rep {rep}: rc {r.returncode}, {dt:.3f} s = {a.reads / dt / 1e6:.2f} M reads/s, out "
+                  f"{os.path.getsize(os.path.join(td, 'r2t.out')) / 1e9:.2f} GB, {ncontigs} contigs")

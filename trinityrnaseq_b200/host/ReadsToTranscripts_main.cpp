@@ -7,18 +7,25 @@
 // ReadsToTranscripts.cc:276-343).  We reproduce exactly that `-t 1` order, which is deterministic.
 #include <errno.h>
 
+#include <algorithm>
 #include <map>
+#include <memory>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fasta_io.hpp"
+#include "par_fasta.hpp"
 #include "multi_gpu.hpp"
 #include "tg_loader.hpp"
 
 using namespace tgio;
 
 namespace {
+
+const size_t PART_BYTES = 48u << 20;          // FASTA bytes per parsed part
+const size_t LINES_PER_BLOCK = 1u << 21;      // output lines formatted (and held in memory) at a time
 
 struct ArgDef { const char* name; const char* desc; bool is_bool; const char* def; };
 const ArgDef ARGS[] = {
@@ -151,50 +158,89 @@ int main(int argc, char** argv) {
     tg_entropy_table(k, min_kmer_entropy, entropy_ok.data());
 
     // ---- reads, in chunks of max_mem_reads ------------------------------------------------------------------
+    // The file is cut at header lines into parts that a pool of threads parses with the reference reader's rules
+    // (par_fasta.hpp; in file order).  A part is assigned on the GPU as soon as it arrives -- the pool is already parsing
+    // the next ones -- and a chunk of max_mem_reads reads is simply a run of (pieces of) parts: grouped by bundle over the
+    // whole chunk and written like the reference writes it, its lines formatted block by block on the pool's cores.
     FileView rf;
     if (!rf.open(reads_file, &err)) { fprintf(stderr, "ERROR: %s\n", err.c_str()); return 1; }
     int out_fd = ::open(out_file.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
     if (out_fd < 0) { fprintf(stderr, "error writing file %s: %s\n", out_file.c_str(), strerror(errno)); return 1; }
-    OutBuf out(out_fd, 32u << 20);
-    DnaStreamReader rd(rf.data, rf.size);
     fprintf(stderr, "Processing reads:\n");
+    const unsigned nthreads_host = host_threads(32);
+    OrderedChunkParser parser(rf.data, rf.size, PART_BYTES, nthreads_host, nthreads_host + 2,
+        [](const char* d, size_t n, RecordBatch& rb) {
+            rb.recs.reserve(n); rb.offs.reserve(n / 48 + 16); rb.names.reserve(n / 4); rb.name_offs.reserve(n / 48 + 16);
+            DnaStreamReader rd(d, n);
+            const char* name; size_t name_len;
+            while (rd.next(&name, &name_len, rb.recs)) {          // sequence lands in the batch directly
+                rb.end_record();
+                rb.add_name(name, name_len);
+            }
+        }, /*after_sequence_line=*/true);
 
+    struct Piece { std::shared_ptr<RecordBatch> rb; size_t a, b, base; };      // reads [a, b) of a part = reads [base, ..) of the chunk
     unsigned long read_count = 0, total_reads_read = 0;
-    RecordBatch rb;
     std::vector<int32_t> best, pct;
     std::vector<uint32_t> order, bucket_start;
-    std::string nm;
     const size_t nb = bundle_names.size();
     // host memory guard: the reference keeps a whole chunk in RAM too, but 2^31 reads is its "unlimited"
     const size_t CHUNK_BYTES_SOFT = (size_t)8 << 30;
-    bool more = true;
+    std::shared_ptr<RecordBatch> carry;          // a part whose tail belongs to the next chunk
+    size_t carry_pos = 0;
+    bool more = true, write_ok = true;
+    auto write_all = [&](const char* p, size_t n) {
+        while (n && write_ok) {
+            const ssize_t w = ::write(out_fd, p, n);
+            if (w < 0) { if (errno == EINTR) continue; write_ok = false; break; }
+            p += w; n -= (size_t)w;
+        }
+    };
     while (more) {
         fprintf(stderr, " reading another %ld... ", max_mem_reads);
-        rb.clear();
-        long got = 0;
-        const char* name; size_t name_len;
-        while (got < max_mem_reads) {
-            if (!rd.next(&name, &name_len, rb.recs)) { more = false; break; }   // sequence lands in the batch directly
-            rb.end_record();
-            rb.add_name(name, name_len);
-            got++;
-            if (max_mem_reads == 2147483647 && rb.recs.size() > CHUNK_BYTES_SOFT) break;   // "unlimited": bound RAM
+        std::vector<Piece> pieces;
+        size_t got = 0, got_bytes = 0;
+        best.clear(); pct.clear();
+        while ((long)got < max_mem_reads) {
+            std::shared_ptr<RecordBatch> part = carry;
+            size_t a = carry_pos;
+            carry.reset(); carry_pos = 0;
+            if (!part) {
+                part = std::make_shared<RecordBatch>();
+                if (!parser.next(*part)) { more = false; break; }
+                a = 0;
+            }
+            const size_t avail = part->count() - a;
+            if (avail == 0) continue;
+            const size_t take = std::min<size_t>(avail, (size_t)max_mem_reads - got);
+            if (take < avail) { carry = part; carry_pos = a + take; }
+            best.resize(got + take); pct.resize(got + take);
+            {   // the vote of these reads, now: the pool is parsing the parts behind this one meanwhile
+                const uint64_t* offs = part->offs.data() + a;
+                const auto ranges = tgh::split_reads_by_bytes(offs, take, gpus.size());
+                tgh::on_every_gpu(gpus.size(), [&](size_t g) -> int {
+                    const size_t x = ranges[g].first, y = ranges[g].second;
+                    if (x == y) return TG_OK;
+                    return tg_assign_reads(tables[g], part->recs.data(), offs + x, y - x, strand, entropy_ok.data(),
+                                           best.data() + got + x, pct.data() + got + x, nullptr);
+                });
+            }
+            pieces.push_back(Piece{part, a, a + take, got});
+            got += take;
+            got_bytes += (size_t)(part->offs[a + take] - part->offs[a]);
+            if (max_mem_reads == 2147483647 && got_bytes > CHUNK_BYTES_SOFT) break;   // "unlimited": bound RAM
         }
         if (got == 0) { fprintf(stderr, "finished reading reads\n"); break; }
-        fprintf(stderr, "done.  Read %ld reads.\n", got);
-        const size_t n = rb.count();
-        best.resize(n); pct.resize(n);
-        {
-            const auto ranges = tgh::split_reads_by_bytes(rb.offs.data(), n, gpus.size());
-            tgh::on_every_gpu(gpus.size(), [&](size_t g) -> int {
-                const size_t a = ranges[g].first, b = ranges[g].second;
-                if (a == b) return TG_OK;
-                return tg_assign_reads(tables[g], rb.recs.data(), rb.offs.data() + a, b - a, strand, entropy_ok.data(),
-                                       best.data() + a, pct.data() + a, nullptr);
-            });
-        }
+        fprintf(stderr, "done.  Read %zu reads.\n", got);
+        const size_t n = got;
         total_reads_read += n;
         fprintf(stderr, "[%lu] reads analyzed for mapping.\n", total_reads_read);
+        // read i of the chunk -> its piece (pieces are few: a binary search per use)
+        auto piece_of = [&](size_t i) -> const Piece& {
+            size_t lo = 0, hi = pieces.size();
+            while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (pieces[mid].base <= i) lo = mid; else hi = mid; }
+            return pieces[lo];
+        };
 
         // group by bundle index ascending, read order inside a bundle (stable counting sort)
         bucket_start.assign(nb + 1, 0);
@@ -202,8 +248,15 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < n; i++) {
             const bool ok = best[i] != -1 && pct[i] >= pct_required;
             if (ok) { bucket_start[(size_t)best[i] + 1]++; assigned++; }
-            else { best[i] = -1; if (verbose) fprintf(stderr, "WARNING: No component mapping for read: %.*s : %.*s\n",
-                                                     (int)rb.name_len(i), rb.name(i), (int)rb.seq_len(i), rb.seq(i)); }
+            else {
+                best[i] = -1;
+                if (verbose) {
+                    const Piece& pc = piece_of(i);
+                    const size_t r = pc.a + (i - pc.base);
+                    fprintf(stderr, "WARNING: No component mapping for read: %.*s : %.*s\n", (int)pc.rb->name_len(r), pc.rb->name(r),
+                            (int)pc.rb->seq_len(r), pc.rb->seq(r));
+                }
+            }
         }
         size_t components_written = 0;
         for (size_t b = 0; b < nb; b++) { if (bucket_start[b + 1]) components_written++; bucket_start[b + 1] += bucket_start[b]; }
@@ -212,23 +265,52 @@ int main(int argc, char** argv) {
             std::vector<uint32_t> cur(bucket_start.begin(), bucket_start.end() - 1);
             for (size_t i = 0; i < n; i++) if (best[i] >= 0) order[cur[(size_t)best[i]]++] = (uint32_t)i;
         }
-        for (size_t j = 0; j < assigned; j++) {
-            const size_t i = order[j];
-            out.put_int(component_no[(size_t)best[i]]);
-            out.putc('\t');
-            format_read_name(rb.name(i), rb.name_len(i), nm);
-            out.put(nm);
-            out.putc('\t');
-            out.put_int(pct[i]);
-            out.put("%\t", 2);
-            out.put(rb.seq(i), rb.seq_len(i));          // original case, as read
-            out.putc('\n');
+        // the lines, LINES_PER_BLOCK at a time: thread w formats the w-th slice of the block into a buffer of its own, the
+        // main thread writes block j while block j + 1 is being formatted
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads_host, assigned / 4096 + 1));
+        std::vector<std::vector<char>> bufs[2];
+        bufs[0].resize(nt); bufs[1].resize(nt);
+        auto format_block = [&](std::vector<std::vector<char>>& out_bufs, size_t j0) {
+            const size_t j1 = std::min(assigned, j0 + LINES_PER_BLOCK);
+            parallel_for_threads(nt, [&](unsigned w) {
+                std::vector<char>& buf = out_bufs[w];
+                buf.clear();
+                std::string nm;
+                char num[24];
+                auto put_int = [&](long long v) {
+                    int m = 0; bool neg = v < 0; unsigned long long u = neg ? (unsigned long long)(-v) : (unsigned long long)v;
+                    do { num[m++] = (char)('0' + u % 10); u /= 10; } while (u);
+                    if (neg) buf.push_back('-');
+                    while (m) buf.push_back(num[--m]);
+                };
+                const size_t a = j0 + (j1 - j0) * w / nt, e = j0 + (j1 - j0) * (w + 1) / nt;
+                for (size_t j = a; j < e; j++) {
+                    const size_t i = order[j];
+                    const Piece& pc = piece_of(i);
+                    const size_t r = pc.a + (i - pc.base);
+                    put_int(component_no[(size_t)best[i]]);
+                    buf.push_back('\t');
+                    format_read_name(pc.rb->name(r), pc.rb->name_len(r), nm);
+                    buf.insert(buf.end(), nm.begin(), nm.end());
+                    buf.push_back('\t');
+                    put_int(pct[i]);
+                    buf.push_back('%'); buf.push_back('\t');
+                    buf.insert(buf.end(), pc.rb->seq(r), pc.rb->seq(r) + pc.rb->seq_len(r));          // original case, as read
+                    buf.push_back('\n');
+                }
+            });
+        };
+        if (assigned) format_block(bufs[0], 0);
+        for (size_t j0 = 0, it = 0; j0 < assigned; j0 += LINES_PER_BLOCK, it++) {
+            std::thread ahead;
+            if (j0 + LINES_PER_BLOCK < assigned) ahead = std::thread([&, it, j0] { format_block(bufs[(it + 1) & 1], j0 + LINES_PER_BLOCK); });
+            for (unsigned w = 0; w < nt; w++) write_all(bufs[it & 1][w].data(), bufs[it & 1][w].size());
+            if (ahead.joinable()) ahead.join();
         }
         read_count += assigned;
-        if (out.failed()) { fprintf(stderr, "error writing file %s: %s\n", out_file.c_str(), strerror(errno)); return 1; }
+        if (!write_ok) { fprintf(stderr, "error writing file %s: %s\n", out_file.c_str(), strerror(errno)); return 1; }
         if (components_written) fprintf(stderr, "[%zu] components written.\n", components_written);
     }
-    if (!out.flush()) { fprintf(stderr, "error writing file %s: %s\n", out_file.c_str(), strerror(errno)); return 1; }
     ::close(out_fd);
     fprintf(stderr, "Done\n");
 

@@ -7,6 +7,8 @@
 // the parsed batches strictly in file order.  Only a window of chunks is in flight, so memory stays bounded whatever the
 // file size.
 #pragma once
+#include <string.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -19,20 +21,30 @@
 namespace tgio {
 
 // chunk boundaries: 0 = b[0] < b[1] < ... < b[n] = size, every inner boundary at a '>' that starts a line
-inline std::vector<size_t> fasta_chunks(const char* data, size_t size, size_t target) {
+// after_sequence_line: only cut at a '>' line whose PREVIOUS line does not start with '>'.  Chrysalis' DNAStringStreamFast
+// takes the line after a header as sequence whatever it starts with (DNAVector.cc:1456-1501), so of two consecutive '>'
+// lines the second may be sequence; a '>' line behind a plain line is a header for every reader.
+inline std::vector<size_t> fasta_chunks(const char* data, size_t size, size_t target, bool after_sequence_line = false) {
     std::vector<size_t> b{0};
     if (target == 0) target = 1;
     size_t pos = target;
+    const char* end = data + size;
+    auto cut_ok = [&](const char* p) {          // p: a line start holding '>'
+        if (!after_sequence_line) return true;
+        if (p - data < 2) return false;         // (the first line has no previous line; position 0 is a boundary anyway)
+        const char* prev = (const char*)memrchr(data, '\n', (size_t)(p - 1 - data));      // newline before the previous line
+        const char* ps = prev ? prev + 1 : data;
+        return *ps != '>';
+    };
     while (pos < size) {
         // next line start at or after pos that begins with '>'
         const char* p = data + pos;
-        const char* end = data + size;
-        if (!(pos > 0 && data[pos - 1] == '\n' && *p == '>')) {
+        if (!(pos > 0 && data[pos - 1] == '\n' && *p == '>' && cut_ok(p))) {
             for (;;) {
                 const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
                 if (!nl || nl + 1 >= end) { p = end; break; }
                 p = nl + 1;
-                if (*p == '>') break;
+                if (*p == '>' && cut_ok(p)) break;
             }
         }
         const size_t at = (size_t)(p - data);
@@ -49,8 +61,9 @@ inline std::vector<size_t> fasta_chunks(const char* data, size_t size, size_t ta
 class OrderedChunkParser {
 public:
     using ParseFn = std::function<void(const char*, size_t, RecordBatch&)>;
-    OrderedChunkParser(const char* data, size_t size, size_t target_chunk, unsigned threads, unsigned window, ParseFn parse)
-        : data_(data), bounds_(fasta_chunks(data, size, target_chunk)), window_(window < 2 ? 2 : window), parse_(std::move(parse)),
+    OrderedChunkParser(const char* data, size_t size, size_t target_chunk, unsigned threads, unsigned window, ParseFn parse,
+                       bool after_sequence_line = false)
+        : data_(data), bounds_(fasta_chunks(data, size, target_chunk, after_sequence_line)), window_(window < 2 ? 2 : window), parse_(std::move(parse)),
           slots_(window_), ready_(window_, 0) {
         const size_t n = nchunks();
         if (threads < 1) threads = 1;
