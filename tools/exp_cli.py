@@ -14,6 +14,9 @@ ap.add_argument("--gpus", default="")
 ap.add_argument("--jellyfish", action="store_true", help="also time jellyfish count / dump -L 1 / dump -L 2 on the file")
 ap.add_argument("--r2t", action="store_true", help="also time the ReadsToTranscripts executable on the file (bundles cut from the transcriptome)")
 ap.add_argument("--no-stats", action="store_true")
+ap.add_argument("--hold-gpu-gb", type=float, default=0, help="device memory the parent keeps allocated while the tool runs")
+ap.add_argument("--hold-pinned-gb", type=float, default=0, help="pinned host memory the parent keeps while the tool runs")
+ap.add_argument("--sleep", type=float, default=0, help="seconds between runs (the driver finishes a process's teardown in the background)")
 ap.add_argument("--variants", default="", help="environment variants, e.g. 'A=1,B=2;;C=3' (an empty one = defaults)")
 a = ap.parse_args()
 ctx = tg.Context(0)
@@ -21,6 +24,11 @@ tx, tx_offs, tx_cum = make_transcriptome(20000, SEED)
 d_recs, nbytes = ctx.synth_reads_dev(tx, tx_offs, tx_cum, a.reads // 2, a.read_len, seed=SEED)
 recs = ctx.d2h(d_recs, nbytes, np.uint8).copy()
 ctx.dev_free(d_recs)        # (the context stays open, as the bench's does while it times the executable)
+held = []
+if a.hold_gpu_gb:
+    held.append(ctx.dev_alloc(int(a.hold_gpu_gb * 2**30)))
+if a.hold_pinned_gb:
+    held.append(ctx.pinned((int(a.hold_pinned_gb * 2**30),), np.uint8))
 exe = os.path.join(ROOT, "trinityrnaseq_b200", "bin", "fastaToKmerCoverageStats")
 with tempfile.TemporaryDirectory() as td:
     fa = os.path.join(td, "reads.fa")
@@ -34,6 +42,7 @@ with tempfile.TemporaryDirectory() as td:
     if a.no_stats:
         variants = []
     for rep, extra in enumerate(variants):
+        time.sleep(a.sleep)
         run_env = dict(env, **extra)
         print("env", extra)
         print(f"launch at wall {time.time():.3f}")
