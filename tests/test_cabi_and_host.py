@@ -245,3 +245,22 @@ def test_jellyfish_dump_blocks_and_threads(tmp_path):
         assert magic == b"TGKMER1\n" and sk == k and sn == int(sel.sum()) and text_bytes == len(want)
         assert np.array_equal(np.frombuffer(side[40:40 + 8 * sn], dtype=np.uint64), keys[sel])
         assert np.array_equal(np.frombuffer(side[40 + 8 * sn:], dtype=np.uint32), cnts[sel])
+
+
+def test_executables_fail_loudly_without_gpu(tmp_path):
+    """no GPU -> the three drop-in executables leave with a non-zero status and say why (no CPU fallback anywhere)"""
+    import subprocess
+    if _lib.lib().tg_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    bin_dir = os.path.join(ROOT, "trinityrnaseq_b200", "bin")
+    if not os.path.exists(os.path.join(bin_dir, "jellyfish")):
+        pytest.skip("executables not built")
+    fa = os.path.join(ROOT, "tests", "golden", "reads.fa")
+    bundles = os.path.join(ROOT, "tests", "golden", "bundles.fa")
+    cmds = [[os.path.join(bin_dir, "fastaToKmerCoverageStats"), "--reads", fa, "--kmers_from_reads", fa],
+            [os.path.join(bin_dir, "ReadsToTranscripts"), "-i", fa, "-f", bundles, "-o", str(tmp_path / "o")],
+            [os.path.join(bin_dir, "jellyfish"), "count", "-m", "25", "-s", "1000", "-o", str(tmp_path / "m.jf"), fa]]
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, timeout=120)
+        assert r.returncode == 3, cmd
+        assert b"no CPU fallback" in r.stderr and r.stdout == b""
