@@ -435,6 +435,15 @@ int tg_table_create(tg_ctx* c, int kind, int k, uint64_t expected_keys, tg_table
     if (bind(c)) return TG_ERR_CUDA;
     uint64_t slots = (uint64_t)((double)expected_keys / TARGET_LOAD) + 1;
     if (slots < MIN_SLOTS) slots = MIN_SLOTS;
+    // expected_keys is a hint -- the executables derive it from a file size -- and the table grows on demand: never start
+    // with more than the device can reasonably give (an input of hundreds of gigabytes would ask for more than HBM holds)
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+        const uint64_t fit = (uint64_t)((double)fr * 0.60) / sizeof(Slot);
+        if (slots > fit && fit >= MIN_SLOTS) slots = fit;
+    } else {
+        cudaGetLastError();
+    }
     return table_new(c, kind, k, pick_geo(slots, c->part_bytes), out);
 }
 
